@@ -1,0 +1,425 @@
+"""ctypes mirror of the treeQP C API (reference: treeqp/src/tree_qp_common.h:139-323,
+treeqp/src/dual_Newton_tree.h:154-168, treeqp/utils/tree.h:56-73).
+
+The classes below drive *any* shared library that exports the reference's C symbols:
+``libtreeqp_b200.so`` (the product: CUDA kernels behind the C ABI) and, in the tests only, the
+unmodified reference compiled to ``oracle/_ref/libtreeqp_ref.so``.  The same Python code builds
+the QP through the same setters and calls the same ``treeqp_tdunes_*`` entry points on both, so
+a parity test reads like the reference's own examples (examples/spring_mass_dual_newton_tree.c).
+
+Python is harness only: nothing here computes; the arithmetic is in the shared library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "lib", "libtreeqp_b200.so")
+
+c_int_p = C.POINTER(C.c_int)
+c_double_p = C.POINTER(C.c_double)
+
+# return codes, treeqp/utils/types.h:55-78
+TREEQP_OPTIMAL_SOLUTION_FOUND = 0
+TREEQP_MAXIMUM_ITERATIONS_REACHED = 1
+TREEQP_DN_NOT_DESCENT_DIRECTION = 2
+TREEQP_OK = 7
+TREEQP_INVALID_OPTION = 9
+TREEQP_UNKNOWN_ERROR = 11
+TREEQP_SUMSQUAREDERRORS, TREEQP_TWONORM, TREEQP_INFNORM = 0, 1, 2
+TREEQP_CLIPPING_SOLVER, TREEQP_QPOASES_SOLVER = 0, 1
+TREEQP_NO_REGULARIZATION, TREEQP_ALWAYS_LM, TREEQP_ON_THE_FLY_LM = 0, 1, 2
+TREEQP_INF = 1e12
+
+
+class TdunesOpts(C.Structure):
+    """treeqp_tdunes_opts_t, dual_Newton_tree.h:67-87"""
+    _fields_ = [
+        ("maxIter", C.c_int),
+        ("qp_solver", c_int_p),
+        ("checkLastActiveSet", C.c_int),
+        ("stationarityTolerance", C.c_double),
+        ("termCondition", C.c_int),
+        ("regType", C.c_int),
+        ("regTol", C.c_double),
+        ("regValue", C.c_double),
+        ("lineSearchMaxIter", C.c_int),
+        ("lineSearchGamma", C.c_double),
+        ("lineSearchBeta", C.c_double),
+        ("lineSearchRestartTrigger", C.c_int),
+    ]
+
+
+class DVec(C.Structure):
+    """struct blasfeo_dvec (HIGH_PERFORMANCE), blasfeo_common.h:72-78"""
+    _fields_ = [("m", C.c_int), ("pm", C.c_int), ("pa", c_double_p), ("memsize", C.c_int)]
+
+
+class Info(C.Structure):
+    """treeqp_info_t, tree_qp_common.h:43-51"""
+    _fields_ = [("Nn", C.c_int), ("iter", C.c_int), ("total_time", C.c_double),
+                ("solver_time", C.c_double), ("interface_time", C.c_double)]
+
+
+class QpOutStruct(C.Structure):
+    """tree_qp_out, tree_qp_common.h:121-133"""
+    _fields_ = [("info", Info), ("x", C.POINTER(DVec)), ("u", C.POINTER(DVec)),
+                ("lam", C.POINTER(DVec)), ("mu_x", C.POINTER(DVec)), ("mu_u", C.POINTER(DVec)),
+                ("mu_d", C.POINTER(DVec))]
+
+
+class Stats(C.Structure):
+    """treeqp_b200_stats (include/treeqp_b200.h, additive)"""
+    _fields_ = [("iter", C.c_int), ("ls_total", C.c_int), ("ls_iters", C.c_int * 256),
+                ("n_reg", C.c_int), ("gpu_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("d2h_ms", C.c_double), ("pack_ms", C.c_double), ("h2d_bytes", C.c_longlong),
+                ("d2h_bytes", C.c_longlong), ("kernel_launches", C.c_longlong)]
+
+
+_DVEC_DT = np.dtype([("m", "<i4"), ("pm", "<i4"), ("pa", "<u8"), ("memsize", "<i4"), ("_pad", "<i4")])
+assert _DVEC_DT.itemsize == C.sizeof(DVec)
+
+
+@dataclass
+class Problem:
+    """A tree QP in flat column-major form (what the reference's ``set_ltv_*`` setters take).
+
+    nk/nx/nu per node (breadth-first); A,B,b concatenated per edge (edge e joins node e+1 to its
+    parent); Q,R either diagonals (``Qd``/``Rd``, clipping path) or dense blocks (``Q``/``R``/``S``
+    concatenated column-major, dense stage-QP path); q,r,bounds concatenated per node.
+    """
+    nk: np.ndarray
+    nx: np.ndarray
+    nu: np.ndarray
+    A: np.ndarray
+    B: np.ndarray
+    b: np.ndarray
+    q: np.ndarray
+    r: np.ndarray
+    xmin: np.ndarray
+    xmax: np.ndarray
+    umin: np.ndarray
+    umax: np.ndarray
+    Qd: Optional[np.ndarray] = None
+    Rd: Optional[np.ndarray] = None
+    Q: Optional[np.ndarray] = None
+    R: Optional[np.ndarray] = None
+    S: Optional[np.ndarray] = None
+    lam0: Optional[np.ndarray] = None
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def Nn(self) -> int:
+        return int(len(self.nk))
+
+    @property
+    def dad(self) -> np.ndarray:
+        dad = np.full(self.Nn, -1, dtype=np.int64)
+        first = np.concatenate([[1], 1 + np.cumsum(self.nk)[:-1]])
+        for i in np.nonzero(self.nk)[0]:
+            dad[first[i]:first[i] + self.nk[i]] = i
+        return dad
+
+    @property
+    def n_lambda(self) -> int:
+        return int(self.nx.sum() - self.nx[0])
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_int_p)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_double_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class TreeQpLib:
+    """A loaded shared library exporting the treeQP C API."""
+
+    def __init__(self, path: str = PRODUCT_LIB):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found: build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.path = path
+        self.lib = L = C.CDLL(path, mode=C.RTLD_LOCAL)
+        self.is_product = hasattr(L, "treeqp_b200_version")
+        vp = C.c_void_p
+        L.tree_qp_in_calculate_size.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, c_int_p]
+        L.tree_qp_in_calculate_size.restype = C.c_int
+        L.tree_qp_in_create.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, vp, vp]
+        L.tree_qp_in_create.restype = None
+        L.tree_qp_out_calculate_size.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p]
+        L.tree_qp_out_calculate_size.restype = C.c_int
+        L.tree_qp_out_create.argtypes = [C.c_int, c_int_p, c_int_p, c_int_p, vp, vp]
+        L.tree_qp_out_create.restype = None
+        L.tree_qp_in_set_ltv_dynamics_colmajor.argtypes = [c_double_p, c_double_p, c_double_p, vp]
+        L.tree_qp_in_set_ltv_dynamics_colmajor.restype = None
+        L.tree_qp_in_set_ltv_objective_diag.argtypes = [c_double_p] * 4 + [vp]
+        L.tree_qp_in_set_ltv_objective_diag.restype = None
+        L.tree_qp_in_set_ltv_bounds.argtypes = [c_double_p] * 4 + [vp]
+        L.tree_qp_in_set_ltv_bounds.restype = None
+        L.tree_qp_in_set_node_objective_colmajor.argtypes = [c_double_p] * 5 + [vp, C.c_int]
+        L.tree_qp_in_set_node_objective_colmajor.restype = None
+        L.tree_qp_out_max_KKT_res.argtypes = [vp, vp]
+        L.tree_qp_out_max_KKT_res.restype = C.c_double
+        L.treeqp_tdunes_opts_calculate_size.argtypes = [C.c_int]
+        L.treeqp_tdunes_opts_calculate_size.restype = C.c_int
+        L.treeqp_tdunes_opts_create.argtypes = [C.c_int, C.POINTER(TdunesOpts), vp]
+        L.treeqp_tdunes_opts_create.restype = None
+        L.treeqp_tdunes_opts_set_default.argtypes = [C.c_int, C.POINTER(TdunesOpts)]
+        L.treeqp_tdunes_opts_set_default.restype = None
+        L.treeqp_tdunes_calculate_size.argtypes = [vp, C.POINTER(TdunesOpts)]
+        L.treeqp_tdunes_calculate_size.restype = C.c_int
+        L.treeqp_tdunes_create.argtypes = [vp, C.POINTER(TdunesOpts), vp, vp]
+        L.treeqp_tdunes_create.restype = None
+        L.treeqp_tdunes_set_dual_initialization.argtypes = [c_double_p, vp]
+        L.treeqp_tdunes_set_dual_initialization.restype = None
+        L.treeqp_tdunes_solve.argtypes = [vp, vp, C.POINTER(TdunesOpts), vp]
+        L.treeqp_tdunes_solve.restype = C.c_int
+        L.setup_multistage_tree.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p]
+        L.setup_multistage_tree.restype = None
+        L.calculate_number_of_nodes.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.calculate_number_of_nodes.restype = C.c_int
+        if self.is_product:
+            L.treeqp_b200_version.restype = C.c_char_p
+            L.treeqp_b200_device_count.restype = C.c_int
+            L.treeqp_tdunes_destroy.argtypes = [vp]
+            L.treeqp_tdunes_destroy.restype = None
+            L.treeqp_tdunes_get_stats.argtypes = [vp, C.POINTER(Stats)]
+            L.treeqp_tdunes_get_stats.restype = None
+            L.treeqp_tdunes_upload.argtypes = [vp, C.POINTER(TdunesOpts), vp]
+            L.treeqp_tdunes_upload.restype = C.c_int
+            L.treeqp_tdunes_solve_resident.argtypes = [C.POINTER(TdunesOpts), vp]
+            L.treeqp_tdunes_solve_resident.restype = C.c_int
+            L.treeqp_tdunes_download.argtypes = [vp, vp]
+            L.treeqp_tdunes_download.restype = C.c_int
+            L.treeqp_tdunes_batch_create.argtypes = [C.c_int, C.POINTER(vp), C.POINTER(TdunesOpts)]
+            L.treeqp_tdunes_batch_create.restype = vp
+            L.treeqp_tdunes_batch_set_dual_initialization.argtypes = [vp, C.c_int, c_double_p]
+            L.treeqp_tdunes_batch_set_dual_initialization.restype = None
+            L.treeqp_tdunes_batch_upload.argtypes = [vp, C.POINTER(vp)]
+            L.treeqp_tdunes_batch_upload.restype = C.c_int
+            L.treeqp_tdunes_batch_solve_resident.argtypes = [vp, c_int_p]
+            L.treeqp_tdunes_batch_solve_resident.restype = C.c_int
+            L.treeqp_tdunes_batch_download.argtypes = [vp, C.POINTER(vp)]
+            L.treeqp_tdunes_batch_download.restype = C.c_int
+            L.treeqp_tdunes_solve_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), c_int_p]
+            L.treeqp_tdunes_solve_batch.restype = C.c_int
+            L.treeqp_tdunes_batch_get_stats.argtypes = [vp, C.POINTER(Stats)]
+            L.treeqp_tdunes_batch_get_stats.restype = None
+            L.treeqp_tdunes_batch_destroy.argtypes = [vp]
+            L.treeqp_tdunes_batch_destroy.restype = None
+
+    # -- small helpers mirroring utils/tree.c
+    def multistage_tree(self, md: int, Nr: int, Nh: int) -> np.ndarray:
+        Nn = self.lib.calculate_number_of_nodes(md, Nr, Nh)
+        nk = np.zeros(Nn, dtype=np.int32)
+        self.lib.setup_multistage_tree(md, Nr, Nh, _ip(nk))
+        return nk
+
+
+class _Buf:
+    """64-byte aligned host buffer (the caller-owned memory of the reference's protocol)."""
+
+    def __init__(self, nbytes: int):
+        self.raw = np.zeros(nbytes + 64, dtype=np.uint8)
+        off = (-self.raw.ctypes.data) % 64
+        self.arr = self.raw[off:off + nbytes]
+        self.ptr = C.c_void_p(self.arr.ctypes.data)
+        self.addr = self.arr.ctypes.data
+        self.nbytes = nbytes
+
+
+class QpIn:
+    """tree_qp_in built through the library's own setters (tree_qp_common.c:148, 1959-2100)."""
+
+    def __init__(self, lib: TreeQpLib, prob: Problem):
+        self.lib, self.prob = lib, prob
+        L = lib.lib
+        self.nk, self.nx, self.nu = _i32(prob.nk), _i32(prob.nx), _i32(prob.nu)
+        Nn = prob.Nn
+        size = L.tree_qp_in_calculate_size(Nn, _ip(self.nx), _ip(self.nu), None, _ip(self.nk))
+        assert size > 0, "tree_qp_in size overflows the int return type of the reference API"
+        self.mem = _Buf(size)
+        self.struct = _Buf(1024)  # opaque tree_qp_in (≈400 B)
+        L.tree_qp_in_create(Nn, _ip(self.nx), _ip(self.nu), None, _ip(self.nk), self.struct.ptr, self.mem.ptr)
+        self.ptr = self.struct.ptr
+        self.set_data(prob)
+
+    def set_data(self, prob: Problem):
+        L = self.lib.lib
+        A, B, b = _f64(prob.A), _f64(prob.B), _f64(prob.b)
+        L.tree_qp_in_set_ltv_dynamics_colmajor(_dp(A), _dp(B), _dp(b), self.ptr)
+        q, r = _f64(prob.q), _f64(prob.r)
+        if prob.Qd is not None:
+            Qd, Rd = _f64(prob.Qd), _f64(prob.Rd)
+            L.tree_qp_in_set_ltv_objective_diag(_dp(Qd), _dp(Rd), _dp(q), _dp(r), self.ptr)
+        else:
+            Q, R, S = _f64(prob.Q), _f64(prob.R), _f64(prob.S)
+            iq = ir = is_ = ix = iu = 0
+            for k in range(prob.Nn):
+                nx, nu = int(prob.nx[k]), int(prob.nu[k])
+                L.tree_qp_in_set_node_objective_colmajor(
+                    _dp(Q[iq:]), _dp(R[ir:]) if nu else None, _dp(S[is_:]) if nu * nx else None,
+                    _dp(q[ix:]), _dp(r[iu:]) if nu else None, self.ptr, k)
+                iq += nx * nx; ir += nu * nu; is_ += nu * nx; ix += nx; iu += nu
+        xmin, xmax, umin, umax = _f64(prob.xmin), _f64(prob.xmax), _f64(prob.umin), _f64(prob.umax)
+        L.tree_qp_in_set_ltv_bounds(_dp(xmin), _dp(xmax), _dp(umin), _dp(umax), self.ptr)
+
+
+class QpOut:
+    """tree_qp_out plus vectorised readers of its BLASFEO vector views."""
+
+    def __init__(self, lib: TreeQpLib, prob: Problem):
+        self.lib, self.prob = lib, prob
+        L = lib.lib
+        nx, nu = _i32(prob.nx), _i32(prob.nu)
+        size = L.tree_qp_out_calculate_size(prob.Nn, _ip(nx), _ip(nu), None)
+        self.mem = _Buf(size)
+        self.struct_buf = _Buf(C.sizeof(QpOutStruct) + 64)
+        L.tree_qp_out_create(prob.Nn, _ip(nx), _ip(nu), None, self.struct_buf.ptr, self.mem.ptr)
+        self.ptr = self.struct_buf.ptr
+        self.s = QpOutStruct.from_address(self.struct_buf.addr)
+
+    def _gather(self, field_ptr, count) -> np.ndarray:
+        """Concatenate `count` blasfeo_dvec views starting at field_ptr (all live in self.mem)."""
+        if count == 0:
+            return np.zeros(0)
+        addr = C.cast(field_ptr, C.c_void_p).value
+        recs = np.frombuffer((C.c_char * (count * _DVEC_DT.itemsize)).from_address(addr), dtype=_DVEC_DT)
+        m = recs["m"].astype(np.int64)
+        base = self.mem.addr
+        start = (recs["pa"].astype(np.int64) - base) // 8
+        assert (start >= 0).all() and ((start + m) * 8 <= self.mem.nbytes).all()
+        data = self.mem.arr[: self.mem.nbytes // 8 * 8].view(np.float64)
+        tot = int(m.sum())
+        if tot == 0:
+            return np.zeros(0)
+        seg = np.repeat(start - np.concatenate([[0], np.cumsum(m)[:-1]]), m)
+        return data[seg + np.arange(tot)].copy()
+
+    @property
+    def x(self): return self._gather(self.s.x, self.prob.Nn)
+    @property
+    def u(self): return self._gather(self.s.u, self.prob.Nn)
+    @property
+    def lam(self): return self._gather(self.s.lam, self.prob.Nn - 1)
+    @property
+    def mu_x(self): return self._gather(self.s.mu_x, self.prob.Nn)
+    @property
+    def mu_u(self): return self._gather(self.s.mu_u, self.prob.Nn)
+    @property
+    def iter(self): return int(self.s.info.iter)
+    @property
+    def total_time(self): return float(self.s.info.total_time)
+
+
+@dataclass
+class Solution:
+    status: int
+    iter: int
+    x: np.ndarray
+    u: np.ndarray
+    lam: np.ndarray
+    mu_x: np.ndarray
+    mu_u: np.ndarray
+    kkt: float
+    total_time: float = 0.0
+    stats: Optional[dict] = None
+
+
+class Tdunes:
+    """TDUNES solver object: opts + workspace protocol of dual_Newton_tree.h:154-168."""
+
+    def __init__(self, lib: TreeQpLib, qp_in: QpIn, **opt_overrides):
+        self.lib, self.qp_in = lib, qp_in
+        L = lib.lib
+        Nn = qp_in.prob.Nn
+        self.opts = TdunesOpts()
+        self.opts_mem = _Buf(max(L.treeqp_tdunes_opts_calculate_size(Nn), 8))
+        L.treeqp_tdunes_opts_create(Nn, C.byref(self.opts), self.opts_mem.ptr)
+        L.treeqp_tdunes_opts_set_default(Nn, C.byref(self.opts))
+        qp_solver = opt_overrides.pop("qp_solver", None)
+        if qp_solver is not None:
+            for k in range(Nn):
+                self.opts.qp_solver[k] = int(qp_solver if np.isscalar(qp_solver) else qp_solver[k])
+        for k, v in opt_overrides.items():
+            assert hasattr(self.opts, k), k
+            setattr(self.opts, k, v)
+        size = L.treeqp_tdunes_calculate_size(qp_in.ptr, C.byref(self.opts))
+        assert size > 0, "workspace size overflows int"
+        self.work_mem = _Buf(size)
+        self.work = _Buf(2048)  # opaque treeqp_tdunes_workspace
+        L.treeqp_tdunes_create(qp_in.ptr, C.byref(self.opts), self.work.ptr, self.work_mem.ptr)
+        self._alive = True
+
+    def set_dual_initialization(self, lam0: np.ndarray):
+        lam0 = _f64(lam0)
+        assert lam0.size == self.qp_in.prob.n_lambda
+        self._lam0 = lam0
+        self.lib.lib.treeqp_tdunes_set_dual_initialization(_dp(lam0), self.work.ptr)
+
+    def solve(self, qp_out: QpOut) -> int:
+        return int(self.lib.lib.treeqp_tdunes_solve(self.qp_in.ptr, qp_out.ptr, C.byref(self.opts), self.work.ptr))
+
+    # additive protocol (product library only)
+    def upload(self) -> int:
+        return int(self.lib.lib.treeqp_tdunes_upload(self.qp_in.ptr, C.byref(self.opts), self.work.ptr))
+
+    def solve_resident(self) -> int:
+        return int(self.lib.lib.treeqp_tdunes_solve_resident(C.byref(self.opts), self.work.ptr))
+
+    def download(self, qp_out: QpOut) -> int:
+        return int(self.lib.lib.treeqp_tdunes_download(qp_out.ptr, self.work.ptr))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.lib.lib.treeqp_tdunes_get_stats(self.work.ptr, C.byref(st))
+        n = min(st.iter, 256)
+        return dict(iter=st.iter, ls_total=st.ls_total, ls_iters=[st.ls_iters[i] for i in range(n)],
+                    n_reg=st.n_reg, gpu_ms=st.gpu_ms, h2d_ms=st.h2d_ms, d2h_ms=st.d2h_ms,
+                    pack_ms=st.pack_ms, h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes,
+                    kernel_launches=st.kernel_launches)
+
+    def destroy(self):
+        if self._alive and self.lib.is_product:
+            self.lib.lib.treeqp_tdunes_destroy(self.work.ptr)
+        self._alive = False
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def solve_tdunes(lib: TreeQpLib, prob: Problem, lam0: Optional[np.ndarray] = None, **opts) -> Solution:
+    """Build, solve once, read back: the sequence of examples/spring_mass_dual_newton_tree.c:52-158."""
+    qp_in = QpIn(lib, prob)
+    qp_out = QpOut(lib, prob)
+    solver = Tdunes(lib, qp_in, **opts)
+    if lam0 is None:
+        lam0 = prob.lam0 if prob.lam0 is not None else np.zeros(prob.n_lambda)
+    solver.set_dual_initialization(lam0)
+    status = solver.solve(qp_out)
+    kkt = float("nan")
+    if status in (TREEQP_OPTIMAL_SOLUTION_FOUND, TREEQP_MAXIMUM_ITERATIONS_REACHED):
+        kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
+    sol = Solution(status=status, iter=qp_out.iter, x=qp_out.x, u=qp_out.u, lam=qp_out.lam,
+                   mu_x=qp_out.mu_x, mu_u=qp_out.mu_u, kkt=kkt, total_time=qp_out.total_time,
+                   stats=solver.stats() if lib.is_product else None)
+    solver.destroy()
+    return sol

@@ -1,0 +1,216 @@
+"""Synthetic tree-QP generators for the parity tests and the benchmark.
+
+Harness code: produces `capi.Problem` objects (flat column-major arrays) that are then pushed
+through the C API's setters.  Every generator is seeded (numpy PCG64), so the reference, the
+oracle port and the GPU path see byte-identical inputs.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .capi import Problem, TREEQP_INF
+
+_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def multistage_nk(md: int, Nr: int, Nh: int) -> np.ndarray:
+    """children counts of a tree branching md-fold for Nr stages, then Nh-Nr chain stages
+    (treeqp/utils/tree.c:247-280)."""
+    nk, width = [], 1
+    for stage in range(Nh):
+        fan = md if stage < Nr else 1
+        nk += [fan] * width
+        width *= fan
+    nk += [0] * width
+    return np.asarray(nk, dtype=np.int32)
+
+
+def tree_tables(nk: np.ndarray):
+    """dad, stage, realisation id (treeqp/utils/tree.c:171-243) for breadth-first children counts."""
+    Nn = len(nk)
+    dad = np.full(Nn, -1, dtype=np.int64)
+    stage = np.zeros(Nn, dtype=np.int64)
+    real = np.full(Nn, -1, dtype=np.int64)
+    nxt = 1
+    for i in range(Nn):
+        for j in range(nk[i]):
+            k = nxt + j
+            dad[k], stage[k] = i, stage[i] + 1
+            real[k] = j if nk[i] > 1 else (real[i] if i > 0 else 0)
+        nxt += nk[i]
+    assert nxt == Nn
+    return dad, stage, real
+
+
+def spring_mass(md: int = 3, Nr: int = 2, Nh: int = 10, xmax1: float | None = None,
+                x0=None) -> Problem:
+    """Config 1/2: the reference's spring-mass example (examples/spring_mass_utils/data.c via
+    tree_qp_in_fill_lti_data_diag_weights, tree_qp_common.c:1837-1955).  x0 is pinned through
+    xmin[0]=xmax[0]=x0 as in examples/spring_mass_dual_newton_tree.c:105."""
+    d = np.load(os.path.join(_GOLDEN, "spring_mass_data.npz"))
+    NX, NU = int(d["NX"]), int(d["NU"])
+    # first realisation in the file is the nominal one and is skipped (example :105)
+    A = d["A"].reshape(-1, NX * NX)[1:]
+    B = d["B"].reshape(-1, NX * NU)[1:]
+    b = d["b"].reshape(-1, NX)[1:]
+    assert md <= A.shape[0]
+    nk = multistage_nk(md, Nr, Nh)
+    Nn = len(nk)
+    dad, stage, real = tree_tables(nk)
+    nx = np.full(Nn, NX, dtype=np.int32)
+    nu = np.where(nk > 0, NU, 0).astype(np.int32)
+    x0 = d["x0"] if x0 is None else np.asarray(x0, dtype=float)
+    xmax = d["xmax"].copy()
+    if xmax1 is not None:
+        xmax[1] = xmax1
+
+    n_leaves = int((stage == stage[-1]).sum())
+    As, Bs, bs, Qd, Rd, q, r, xlo, xhi, ulo, uhi = ([] for _ in range(11))
+    for k in range(Nn):
+        if k > 0:
+            As.append(A[real[k]]); Bs.append(B[real[k]]); bs.append(b[real[k]])
+        if nk[k] > 0:
+            # integer division exactly as the reference (tree_qp_common.c:1909)
+            scale = float(n_leaves // int((stage == stage[k]).sum()))
+            Qd.append(scale * d["dQ"]); q.append(scale * d["q"])
+            Rd.append(scale * d["dR"]); r.append(scale * d["r"])
+            ulo.append(d["umin"]); uhi.append(d["umax"])
+        else:
+            Qd.append(d["dP"]); q.append(d["p"])
+        if k == 0:
+            xlo.append(x0); xhi.append(x0)
+        else:
+            xlo.append(d["xmin"]); xhi.append(xmax)
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    return Problem(nk=nk, nx=nx, nu=nu, A=cat(As), B=cat(Bs), b=cat(bs), Qd=cat(Qd), Rd=cat(Rd),
+                   q=cat(q), r=cat(r), xmin=cat(xlo), xmax=cat(xhi), umin=cat(ulo), umax=cat(uhi),
+                   lam0=np.zeros(int(nx.sum() - nx[0])),
+                   meta=dict(name="spring_mass", md=md, Nr=Nr, Nh=Nh))
+
+
+def random_tree(nk: np.ndarray, nx: int = 12, nu: int = 4, seed: int = 0, ubound: float = 0.5,
+                xbound: float | None = None, a_scale: float | None = None,
+                vary_dims: bool = False) -> Problem:
+    """Config 3: random tree QP with diagonal weights (clipping path), restating the clipping
+    branch of examples/random_qp_utils/generate_random_tree.m:52-79 with the three documented
+    deviations of SURVEY.md §8d.3: A = a_scale*U(0,1) (default 0.96/nx), weights bounded away
+    from zero, bounds on the inputs only (|u|<=ubound) unless xbound is given.
+
+    vary_dims=True draws nx in [1,nx], nu in [0,nu] per node (the shape of the reference's unit
+    test data, examples/random_qp_utils/data0x.c)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nk = np.asarray(nk, dtype=np.int32)
+    Nn = len(nk)
+    dad, stage, _ = tree_tables(nk)
+    if vary_dims:
+        nxs = rng.integers(1, nx + 1, size=Nn).astype(np.int32)
+        nus = rng.integers(0, nu + 1, size=Nn).astype(np.int32)
+    else:
+        nxs = np.full(Nn, nx, dtype=np.int32)
+        nus = np.full(Nn, nu, dtype=np.int32)
+    nus[nk == 0] = 0
+    if a_scale is None:
+        a_scale = 0.96 / nx
+    nA = int((nxs[1:].astype(np.int64) * nxs[dad[1:]]).sum())
+    nB = int((nxs[1:].astype(np.int64) * nus[dad[1:]]).sum())
+    X, U = int(nxs.sum()), int(nus.sum())
+    A = a_scale * rng.random(nA)
+    B = rng.random(nB)
+    b = rng.random(X - int(nxs[0]))
+    Qd = 1.0 + 9.0 * rng.random(X)
+    Rd = 0.5 + rng.random(U)
+    q = rng.random(X)
+    r = rng.random(U)
+    xb = TREEQP_INF if xbound is None else xbound
+    return Problem(nk=nk, nx=nxs, nu=nus, A=A, B=B, b=b, Qd=Qd, Rd=Rd, q=q, r=r,
+                   xmin=np.full(X, -xb), xmax=np.full(X, xb),
+                   umin=np.full(U, -ubound), umax=np.full(U, ubound),
+                   lam0=np.zeros(X - int(nxs[0])),
+                   meta=dict(name="random_tree", seed=seed, nx=nx, nu=nu, ubound=ubound))
+
+
+def binary_tree_nk(depth: int, md: int = 2) -> np.ndarray:
+    """full md-ary tree with `depth` edges on every root-to-leaf path"""
+    return multistage_nk(md, depth, depth)
+
+
+def _expm(M: np.ndarray) -> np.ndarray:
+    """scaling-and-squaring Taylor exponential (enough for Ts*A of a spring chain)"""
+    nrm = np.linalg.norm(M, 1)
+    s = max(0, int(np.ceil(np.log2(max(nrm, 1e-16)))) + 4)
+    Ms = M / (2.0 ** s)
+    E = np.eye(M.shape[0])
+    term = np.eye(M.shape[0])
+    for i in range(1, 20):
+        term = term @ Ms / i
+        E = E + term
+    for _ in range(s):
+        E = E @ E
+    return E
+
+
+def linear_chain(nm: int = 4, nu: int = 3, md: int = 3, Nr: int = 2, Nh: int = 20, seed: int = 0,
+                 Ts: float = 0.05, eliminate_x0: bool = True, x0_kick: float = 1.5,
+                 x0_noise: float = 0.3) -> Problem:
+    """Config 4: chain of nm masses (nx = 2*nm), restating
+    benchmark/linear_chain/initialize_linear_chain.m:31-81 + default_params_linear_chain.m:6-23:
+    T = tridiag(1,-2,1), A_c=[0 I; k*T 0], B_c=[0; I_nu; 0], exact discretisation
+    expm([A_c B_c; 0 0]*Ts) (benchmark/common/discretize_model.m:8-10), k in linspace(4,8,md);
+    Q=10, R=1, P=Q, all bounds +-2, stage weights scaled md^(Nr-stage)
+    (benchmark/utils/setup_tree.m:84-91); x0 = x0_kick*e_{nm+nu+1} + x0_noise*U(-1,1) (the benchmark
+    starts at 2*e; 1.5 +- 0.3 keeps every instance of a batch strictly inside the +-2 box so
+    that the QP is feasible for every seed), eliminated into the
+    root's outgoing edges as tree_qp_in_eliminate_x0 does (tree_qp_common.c:404-525): nx[0]=0,
+    b <- A0 x0 + b."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nxs_ = 2 * nm
+    T = -2.0 * np.eye(nm) + np.eye(nm, k=1) + np.eye(nm, k=-1)
+    Ad, Bd = [], []
+    for kspr in np.linspace(4.0, 8.0, md):
+        Ac = np.zeros((nxs_, nxs_))
+        Ac[:nm, nm:] = np.eye(nm)
+        Ac[nm:, :nm] = kspr * T
+        Bc = np.zeros((nxs_, nu))
+        Bc[nm:nm + nu, :] = np.eye(nu)
+        M = np.zeros((nxs_ + nu, nxs_ + nu))
+        M[:nxs_, :nxs_] = Ac
+        M[:nxs_, nxs_:] = Bc
+        E = _expm(M * Ts)
+        Ad.append(E[:nxs_, :nxs_].copy())
+        Bd.append(E[:nxs_, nxs_:].copy())
+    nk = multistage_nk(md, Nr, Nh)
+    Nn = len(nk)
+    dad, stage, real = tree_tables(nk)
+    x0 = np.zeros(nxs_)
+    x0[min(nm + nu, nxs_ - 1)] = x0_kick
+    x0 += x0_noise * rng.uniform(-1.0, 1.0, nxs_)
+    nx = np.full(Nn, nxs_, dtype=np.int32)
+    nus = np.where(nk > 0, nu, 0).astype(np.int32)
+    if eliminate_x0:
+        nx[0] = 0
+    As, Bs, bs, Qd, Rd, q, r = ([] for _ in range(7))
+    for k in range(Nn):
+        w = float(md ** max(Nr - stage[k], 0))
+        if k > 0:
+            Ak, Bk = Ad[real[k]], Bd[real[k]]
+            if dad[k] == 0 and eliminate_x0:
+                As.append(np.zeros(0)); bs.append(Ak @ x0)
+            else:
+                As.append(Ak.flatten(order="F")); bs.append(np.zeros(nxs_))
+            Bs.append(Bk.flatten(order="F"))
+        if nx[k] > 0:
+            Qd.append(np.full(nxs_, 10.0 * w)); q.append(np.zeros(nxs_))
+        if nus[k] > 0:
+            Rd.append(np.full(nu, 1.0 * w)); r.append(np.zeros(nu))
+    X, U = int(nx.sum()), int(nus.sum())
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    p = Problem(nk=nk, nx=nx, nu=nus, A=cat(As), B=cat(Bs), b=cat(bs), Qd=cat(Qd), Rd=cat(Rd),
+                q=cat(q), r=cat(r), xmin=np.full(X, -2.0), xmax=np.full(X, 2.0),
+                umin=np.full(U, -2.0), umax=np.full(U, 2.0), lam0=np.zeros(X - int(nx[0])),
+                meta=dict(name="linear_chain", nm=nm, nu=nu, md=md, Nr=Nr, Nh=Nh, seed=seed))
+    if not eliminate_x0:
+        p.xmin[:nxs_] = x0
+        p.xmax[:nxs_] = x0
+    return p
