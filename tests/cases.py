@@ -1,0 +1,62 @@
+"""Seeded parity cases shared by the CPU (oracle) and GPU tests; goldens in tests/golden/."""
+import hashlib
+import os
+
+import numpy as np
+
+from treeqp_b200 import problems as P
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def cases():
+    yield "spring_mass_cfg1", P.spring_mass(3, 2, 10), {}
+    yield "spring_mass_tight", P.spring_mass(3, 2, 10, xmax1=0.2), {}
+    yield "spring_mass_cfg2tree", P.spring_mass(3, 4, 20), {}
+    yield "random_d6_u05", P.random_tree(P.binary_tree_nk(6), 12, 4, seed=1, ubound=0.5), dict(maxIter=200)
+    yield "random_d10_u02", P.random_tree(P.binary_tree_nk(10), 12, 4, seed=2, ubound=0.2), dict(maxIter=200)
+    yield "random_d8_u05", P.random_tree(P.binary_tree_nk(8), 12, 4, seed=3, ubound=0.5), dict(maxIter=200)
+    yield "random_vary_dims", P.random_tree(P.multistage_nk(3, 2, 5), 5, 3, seed=4, ubound=0.3, vary_dims=True), dict(maxIter=200)
+    yield "random_ternary_chain", P.random_tree(P.multistage_nk(3, 2, 8), 6, 2, seed=5, ubound=0.2, xbound=3.0), dict(maxIter=200)
+    yield "linear_chain_cfg4", P.linear_chain(4, 3, 3, 2, 20, seed=0), {}
+    yield "linear_chain_cfg4_s7", P.linear_chain(4, 3, 3, 2, 20, seed=7), {}
+    yield "linear_chain_pinned_x0", P.linear_chain(2, 1, 2, 2, 6, seed=1, eliminate_x0=False), {}
+
+
+CASE_NAMES = [c[0] for c in cases()]
+
+
+def get_case(name):
+    for n, p, o in cases():
+        if n == name:
+            return p, o
+    raise KeyError(name)
+
+
+def checksum(prob):
+    h = hashlib.sha256()
+    for name in ["nk", "nx", "nu", "A", "B", "b", "Qd", "Rd", "q", "r", "xmin", "xmax", "umin", "umax"]:
+        h.update(np.ascontiguousarray(getattr(prob, name)).tobytes())
+    return h.hexdigest()
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, "tdunes_%s.npz" % name))
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if b.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+PORT_OPT_NAMES = {"maxIter", "termCondition", "regType", "regTol", "regValue", "lineSearchMaxIter",
+                  "lineSearchGamma", "lineSearchBeta"}
+
+
+def port_opts(opts):
+    o = {k: v for k, v in opts.items() if k in PORT_OPT_NAMES}
+    if "stationarityTolerance" in opts:
+        o["tol"] = opts["stationarityTolerance"]
+    return o

@@ -20,6 +20,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(HERE))
 REF = os.environ.get("TREEQP_REFERENCE", "/root/reference")
 
 
@@ -47,27 +48,7 @@ def make_spring_mass_data():
     print("spring_mass_data.npz: NX=%d NU=%d realisations=%d" % (d["NX"], d["NU"], len(d["A"]) // d["NX"] ** 2))
 
 
-def checksum(prob):
-    import hashlib
-    h = hashlib.sha256()
-    for name in ["nk", "nx", "nu", "A", "B", "b", "Qd", "Rd", "q", "r", "xmin", "xmax", "umin", "umax"]:
-        h.update(np.ascontiguousarray(getattr(prob, name)).tobytes())
-    return h.hexdigest()
-
-
-def cases():
-    from treeqp_b200 import problems as P
-    yield "spring_mass_cfg1", P.spring_mass(3, 2, 10), {}
-    yield "spring_mass_tight", P.spring_mass(3, 2, 10, xmax1=0.2), {}
-    yield "spring_mass_cfg2tree", P.spring_mass(3, 4, 20), {}
-    yield "random_d6_u05", P.random_tree(P.binary_tree_nk(6), 12, 4, seed=1, ubound=0.5), dict(maxIter=200)
-    yield "random_d10_u02", P.random_tree(P.binary_tree_nk(10), 12, 4, seed=2, ubound=0.2), dict(maxIter=200)
-    yield "random_d8_u05", P.random_tree(P.binary_tree_nk(8), 12, 4, seed=3, ubound=0.5), dict(maxIter=200)
-    yield "random_vary_dims", P.random_tree(P.multistage_nk(3, 2, 5), 5, 3, seed=4, ubound=0.3, vary_dims=True), dict(maxIter=200)
-    yield "random_ternary_chain", P.random_tree(P.multistage_nk(3, 2, 8), 6, 2, seed=5, ubound=0.2, xbound=3.0), dict(maxIter=200)
-    yield "linear_chain_cfg4", P.linear_chain(4, 3, 3, 2, 20, seed=0), {}
-    yield "linear_chain_cfg4_s7", P.linear_chain(4, 3, 3, 2, 20, seed=7), {}
-    yield "linear_chain_pinned_x0", P.linear_chain(2, 1, 2, 2, 6, seed=1, eliminate_x0=False), {}
+from cases import cases, checksum  # noqa: E402  (tests/cases.py)
 
 
 def make_tdunes_goldens():

@@ -1,0 +1,114 @@
+"""GPU parity tests: treeqp_tdunes_solve of libtreeqp_b200.so (CUDA) through the C ABI versus
+(1) goldens produced by the unmodified reference, (2) the oracle port on the same inputs,
+(3) the compiled reference itself when oracle/_ref travelled to the box.
+
+Bar (BASELINE.json north_star): identical status, Newton iteration count, line-search trial
+counts and active sets; x, u, lambda, mu within 1e-10 relative (FP64)."""
+import numpy as np
+import pytest
+
+import cases as CS
+import oracle_port as OP
+from treeqp_b200 import capi, problems as P
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def check_against(sol, ref, prob, tol=TOL):
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        assert CS.rel_err(getattr(sol, k), ref[k]) < tol, k
+    for k, lo, hi in (("x", prob.xmin, prob.xmax), ("u", prob.umin, prob.umax)):
+        assert np.array_equal(getattr(sol, k) == lo, ref[k] == lo), "active set (lower) differs: " + k
+        assert np.array_equal(getattr(sol, k) == hi, ref[k] == hi), "active set (upper) differs: " + k
+
+
+@pytest.mark.parametrize("name", CS.CASE_NAMES)
+def test_solve_matches_reference_golden(name, product_lib):
+    prob, opts = CS.get_case(name)
+    g = CS.golden(name)
+    sol = capi.solve_tdunes(product_lib, prob, **opts)
+    assert sol.status == int(g["status"])
+    assert sol.iter == int(g["iter"]), "Newton iteration count differs from the reference"
+    check_against(sol, g, prob)
+    assert sol.kkt < 1e-8          # the reference's own acceptance threshold (spring_mass_dual_newton_tree.c:156)
+    assert sol.stats["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("name", ["spring_mass_tight", "random_d6_u05", "random_d8_u05", "random_d10_u02"])
+def test_line_search_counts_match_oracle(name, product_lib):
+    prob, opts = CS.get_case(name)
+    s = OP.solve_port(prob, **CS.port_opts(opts))
+    sol = capi.solve_tdunes(product_lib, prob, **opts)
+    assert sol.iter == s["iter"]
+    assert sol.stats["ls_iters"] == s["ls_iters"], "per-iteration line-search trial counts differ"
+    assert sol.stats["n_reg"] == s["n_reg"], "number of regularised blocks differs"
+
+
+@pytest.mark.parametrize("opts", [dict(regType=1), dict(termCondition=0, stationarityTolerance=1e-14),
+                                  dict(termCondition=1), dict(lineSearchBeta=0.3, lineSearchGamma=0.3),
+                                  dict(maxIter=7), dict(lineSearchMaxIter=3, maxIter=20)])
+def test_options_match_oracle(opts, product_lib):
+    prob, _ = CS.get_case("spring_mass_tight")
+    s = OP.solve_port(prob, **CS.port_opts(opts))
+    sol = capi.solve_tdunes(product_lib, prob, **opts)
+    assert (sol.status, sol.iter) == (s["status"], s["iter"])
+    check_against(sol, s, prob, tol=1e-9)
+
+
+def test_no_regularisation_on_regular_problem(product_lib):
+    prob, _ = CS.get_case("spring_mass_cfg1")
+    s = OP.solve_port(prob, regType=0)
+    sol = capi.solve_tdunes(product_lib, prob, regType=0)
+    assert (sol.status, sol.iter) == (s["status"], s["iter"]) == (0, 3)
+    check_against(sol, s, prob)
+
+
+def test_live_reference_when_available(product_lib, ref_lib):
+    prob = P.random_tree(P.binary_tree_nk(7), 12, 4, seed=11, ubound=0.3)
+    r = capi.solve_tdunes(ref_lib, prob, maxIter=200)
+    s = capi.solve_tdunes(product_lib, prob, maxIter=200)
+    assert (s.status, s.iter) == (r.status, r.iter)
+    check_against(s, dict(x=r.x, u=r.u, lam=r.lam, mu_x=r.mu_x, mu_u=r.mu_u), prob)
+
+
+def test_invalid_option_and_not_descent(product_lib):
+    prob, _ = CS.get_case("spring_mass_cfg1")
+    qp_in, qp_out = capi.QpIn(product_lib, prob), capi.QpOut(product_lib, prob)
+    solver = capi.Tdunes(product_lib, qp_in, termCondition=7)
+    solver.set_dual_initialization(np.zeros(prob.n_lambda))
+    assert solver.solve(qp_out) == capi.TREEQP_INVALID_OPTION
+    solver.destroy()
+
+
+def test_warm_start_and_resolve(product_lib):
+    """second solve from the optimal duals terminates at iteration 0 with the same solution
+    (the closed-loop MPC pattern: set_dual_initialization(previous lam), solve)"""
+    prob, _ = CS.get_case("spring_mass_tight")
+    qp_in, qp_out = capi.QpIn(product_lib, prob), capi.QpOut(product_lib, prob)
+    solver = capi.Tdunes(product_lib, qp_in)
+    solver.set_dual_initialization(np.zeros(prob.n_lambda))
+    assert solver.solve(qp_out) == 0
+    x1, lam1, it1 = qp_out.x, qp_out.lam, qp_out.iter
+    solver.set_dual_initialization(lam1)
+    assert solver.solve(qp_out) == 0
+    assert qp_out.iter == 0 and it1 == 58
+    assert CS.rel_err(qp_out.x, x1) < 1e-12
+    # cold start again: bit-identical to the first run (deterministic reductions)
+    solver.set_dual_initialization(np.zeros(prob.n_lambda))
+    assert solver.solve(qp_out) == 0
+    assert qp_out.iter == it1 and np.array_equal(qp_out.x, x1) and np.array_equal(qp_out.lam, lam1)
+    solver.destroy()
+
+
+def test_large_tree_properties(product_lib):
+    """Size-independent checks at a size the oracle would need minutes for: KKT of the reference's
+    checker, dual feasibility of the line search, repeatability."""
+    prob = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=5, ubound=0.2)
+    a = capi.solve_tdunes(product_lib, prob, maxIter=200)
+    b = capi.solve_tdunes(product_lib, prob, maxIter=200)
+    assert a.status == 0 and a.kkt < 1e-8
+    assert (a.iter, a.stats["ls_iters"]) == (b.iter, b.stats["ls_iters"])
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.lam, b.lam)
+    assert np.all(a.u <= prob.umax) and np.all(a.u >= prob.umin)
+    assert np.all(a.mu_u[a.u == prob.umax] >= 0) and np.all(a.mu_u[a.u == prob.umin] <= 0)

@@ -1,0 +1,306 @@
+/*
+ * device.cu -- device arena, stream, and the host-side driver of the dual Newton loop
+ * (treeqp_tdunes_solve, dual_Newton_tree.c:1166-1228) over the kernels in tdunes_kernels.cuh.
+ *
+ * The Newton loop is level-synchronous: per iteration one launch per phase and one launch per
+ * tree depth for the factorisation / substitution sweeps.  All decisions (termination, descent
+ * test, Armijo) are taken on the device per tree; the host only reads two counters ("trees still
+ * running", "trees with a pending line-search trial") through pinned memory to know when to stop
+ * launching.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tdunes_kernels.cuh"
+
+static thread_local char g_err[512] = "";
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) {                                                                 \
+            snprintf(g_err, sizeof g_err, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            fprintf(stderr, "[treeqp_b200] CUDA error %s\n", g_err);                             \
+            return 1;                                                                            \
+        }                                                                                        \
+    } while (0)
+
+struct tqb_device
+{
+    tqb_dims dims;
+    int *d_int;
+    double *d_in, *d_work;
+    int *d_tint;      /* per-tree ints + counters + ls history */
+    double *d_tdbl;   /* per-tree doubles */
+    int *h_counters;  /* pinned [4] */
+    int *lvl_ptr;     /* host copy [Nh+2] */
+    View v;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    int wpb_stage, wpb_hess, wpb_fact, wpb_back;
+    size_t sm_stage, sm_hess, sm_fact, sm_back;
+    int pw_fact, pw_back;
+    long long launches;
+    size_t out_doubles;
+};
+
+extern "C" const char *tqb_cuda_last_error(void) { return g_err; }
+
+extern "C" int tqb_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int tqb_cuda_set_device(int dev) { return cudaSetDevice(dev) == cudaSuccess ? 0 : 1; }
+
+extern "C" void *tqb_pinned_alloc(size_t bytes)
+{
+    void *p = NULL;
+    if (bytes == 0) bytes = 8;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess)
+    {
+        snprintf(g_err, sizeof g_err, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        fprintf(stderr, "[treeqp_b200] %s\n", g_err);
+        return NULL;
+    }
+    return p;
+}
+
+extern "C" void tqb_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+
+static int pick_wpb(size_t per_warp_bytes, size_t limit, int *wpb, size_t *smem)
+{
+    int w = 8;
+    while (w > 1 && (size_t) w * per_warp_bytes > limit) w >>= 1;
+    if ((size_t) w * per_warp_bytes > limit) return 1;
+    *wpb = w;
+    *smem = (size_t) w * per_warp_bytes;
+    return 0;
+}
+
+static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr)
+{
+    const tqb_dims *d = &D->dims;
+    CK(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&D->ev0));
+    CK(cudaEventCreate(&D->ev1));
+    CK(cudaMalloc(&D->d_int, sizeof(int) * (size_t) d->n_int));
+    CK(cudaMemcpy(D->d_int, h_int, sizeof(int) * (size_t) d->n_int, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&D->d_in, sizeof(double) * (size_t) d->n_in));
+    D->lvl_ptr = (int *) malloc(sizeof(int) * (size_t) (d->Nh + 2));
+    memcpy(D->lvl_ptr, lvl_ptr, sizeof(int) * (size_t) (d->Nh + 2));
+
+    View &v = D->v;
+    memset(&v, 0, sizeof v);
+    tqb_layout_tables(d, D->d_int, &v.T);
+    tqb_layout_inputs(d, D->d_in, &v.in);
+
+    const size_t X = d->X, U = d->U;
+    D->out_doubles = 3 * X + 2 * U;
+    size_t nwork = D->out_doubles + 8 /* x u lam mux muu */
+                   + 6 * X + 2 * U + 16      /* dlam res resMod xUnc P Linv | uUnc Rt */
+                   + (size_t) d->szW + (size_t) d->szUt + 4
+                   + 2 * (size_t) d->Nn + 2 * (size_t) d->nchunk + 4;
+    CK(cudaMalloc(&D->d_work, sizeof(double) * nwork));
+    double *p = D->d_work;
+    v.x = p; p += X; v.u = p; p += U; v.lam = p; p += X; v.mux = p; p += X; v.muu = p; p += U;
+    p += ((uintptr_t) p & 8) ? 1 : 0;
+    v.dlam = p; p += X; v.res = p; p += X; v.resMod = p; p += X; v.xUnc = p; p += X; v.P = p; p += X;
+    v.Linv = p; p += X; v.uUnc = p; p += U; v.Rt = p; p += U;
+    p += ((uintptr_t) p & 8) ? 1 : 0;
+    v.W = p; p += d->szW; v.Ut = p; p += d->szUt;
+    v.nva = p; p += d->Nn; v.nvb = p; p += d->Nn; v.cva = p; p += d->nchunk; v.cvb = p; p += d->nchunk;
+    if ((size_t) (p - D->d_work) > nwork) { snprintf(g_err, sizeof g_err, "work arena overflow"); return 1; }
+
+    const size_t nT = d->nT;
+    CK(cudaMalloc(&D->d_tint, sizeof(int) * (5 * nT + 4 + 256)));
+    CK(cudaMalloc(&D->d_tdbl, sizeof(double) * (5 * nT)));
+    CK(cudaMemset(D->d_tint, 0, sizeof(int) * (5 * nT + 4 + 256)));
+    v.status = D->d_tint; v.iter = v.status + nT; v.ls_cnt = v.iter + nT; v.ls_active = v.ls_cnt + nT;
+    v.restart_cnt = v.ls_active + nT; v.counters = v.restart_cnt + nT; v.ls_hist = v.counters + 4;
+    v.t_f0 = D->d_tdbl; v.t_dot = v.t_f0 + nT; v.t_tau = v.t_dot + nT; v.t_tauprev = v.t_tau + nT;
+    v.t_err = v.t_tauprev + nT;
+    CK(cudaMallocHost(&D->h_counters, sizeof(int) * 4));
+
+    v.Nn = d->Nn; v.nT = d->nT; v.X = d->X; v.U = d->U; v.nchunk = d->nchunk;
+    v.abmax = d->abmax; v.dmax = d->dmax; v.nxmax = d->nxmax; v.numax = d->numax;
+
+    /* shared memory per warp (bytes) and warps per CTA for the block kernels */
+    int dev = 0, smem_max = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const size_t lim = (size_t) smem_max > 8192 ? (size_t) smem_max - 2048 : 40000;
+    const int ldw = d->dmax | 1, ldu = d->nxmax | 1;
+    const size_t pw_stage = 8ull * (d->abmax + d->dmax);
+    const size_t pw_hess = 8ull * (d->abmax + d->nxmax + d->numax + d->dmax);
+    D->pw_fact = ldw * d->dmax + 2 * d->dmax + ldu * d->dmax;
+    D->pw_back = ldw * d->dmax + 2 * d->dmax + d->nxmax;
+    if (pick_wpb(pw_stage > 8 ? pw_stage : 8, lim, &D->wpb_stage, &D->sm_stage) ||
+        pick_wpb(pw_hess > 8 ? pw_hess : 8, lim, &D->wpb_hess, &D->sm_hess) ||
+        pick_wpb(8ull * (D->pw_fact > 1 ? D->pw_fact : 1), lim, &D->wpb_fact, &D->sm_fact) ||
+        pick_wpb(8ull * (D->pw_back > 1 ? D->pw_back : 1), lim, &D->wpb_back, &D->sm_back))
+    {
+        snprintf(g_err, sizeof g_err, "block dimension %d needs more shared memory than one SM has", d->dmax);
+        fprintf(stderr, "[treeqp_b200] %s\n", g_err);
+        return 1;
+    }
+    CK(cudaFuncSetAttribute(k_stage<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
+    CK(cudaFuncSetAttribute(k_stage<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
+    CK(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_hess));
+    CK(cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_fact));
+    CK(cudaFuncSetAttribute(k_backsolve_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
+    return 0;
+}
+
+extern "C" tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int, const int *lvl_ptr)
+{
+    if (tqb_cuda_device_count() <= 0)
+    {
+        snprintf(g_err, sizeof g_err, "no CUDA device visible: libtreeqp_b200 has no CPU fallback");
+        fprintf(stderr, "[treeqp_b200] %s\n", g_err);
+        return NULL;
+    }
+    tqb_device *D = (tqb_device *) calloc(1, sizeof(tqb_device));
+    D->dims = *dims;
+    if (device_build(D, h_int, lvl_ptr)) { tqb_device_destroy(D); return NULL; }
+    return D;
+}
+
+extern "C" void tqb_device_destroy(tqb_device *D)
+{
+    if (!D) return;
+    if (D->stream) cudaStreamSynchronize(D->stream);
+    cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
+    if (D->h_counters) cudaFreeHost(D->h_counters);
+    if (D->ev0) cudaEventDestroy(D->ev0);
+    if (D->ev1) cudaEventDestroy(D->ev1);
+    if (D->stream) cudaStreamDestroy(D->stream);
+    free(D->lvl_ptr);
+    free(D);
+}
+
+extern "C" int tqb_device_upload(tqb_device *D, const double *h_in, long long n_in, double *ms)
+{
+    CK(cudaEventRecord(D->ev0, D->stream));
+    CK(cudaMemcpyAsync(D->d_in, h_in, sizeof(double) * (size_t) n_in, cudaMemcpyHostToDevice, D->stream));
+    CK(cudaEventRecord(D->ev1, D->stream));
+    CK(cudaStreamSynchronize(D->stream));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, D->ev0, D->ev1));
+    if (ms) *ms = t;
+    return 0;
+}
+
+extern "C" int tqb_device_download(tqb_device *D, double *h_out, double *ms)
+{
+    CK(cudaEventRecord(D->ev0, D->stream));
+    CK(cudaMemcpyAsync(h_out, D->v.x, sizeof(double) * D->out_doubles, cudaMemcpyDeviceToHost, D->stream));
+    CK(cudaEventRecord(D->ev1, D->stream));
+    CK(cudaStreamSynchronize(D->stream));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, D->ev0, D->ev1));
+    if (ms) *ms = t;
+    return 0;
+}
+
+#define LAUNCH(kern, grid, block, smem, ...)                          \
+    do {                                                              \
+        kern<<<(grid), (block), (smem), D->stream>>>(__VA_ARGS__);    \
+        D->launches++;                                                \
+    } while (0)
+
+static inline int cdiv(long long a, int b) { return (int) ((a + b - 1) / b); }
+
+static int read_counters(tqb_device *D)
+{
+    CK(cudaMemcpyAsync(D->h_counters, D->v.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, D->stream));
+    CK(cudaStreamSynchronize(D->stream));
+    return 0;
+}
+
+/* dual function of all trees with ls_active set -> cvb (per-chunk partial sums) */
+static void launch_eval(tqb_device *D)
+{
+    const View &v = D->v;
+    LAUNCH(k_stage<1>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
+    LAUNCH(k_chunk_reduce, v.nchunk, 256, 0, v, v.nvb, v.cvb, 0);
+}
+
+extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status, int *h_iter,
+                                int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms,
+                                long long *launches)
+{
+    View &v = D->v;
+    v.o = *o;
+    const tqb_dims *d = &D->dims;
+    const int nT = d->nT, Nh = d->Nh;
+    const int tgrid = cdiv(nT, 4);
+    D->launches = 0;
+
+    CK(cudaEventRecord(D->ev0, D->stream));
+    {
+        int n = v.X > nT ? v.X : nT;
+        if (n < 256) n = 256;
+        LAUNCH(k_init, cdiv(n, 256), 256, 0, v);
+    }
+    for (int it = 0; it < o->maxIter; it++)
+    {
+        CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
+        LAUNCH(k_stage<0>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
+        LAUNCH(k_gradient, cdiv(v.Nn, 8), 256, 0, v);
+        LAUNCH(k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
+        LAUNCH(k_decide_term, tgrid, 128, 0, v);
+        if (read_counters(D)) return 1;
+        if (D->h_counters[0] == 0) break;
+
+        LAUNCH(k_hessian, cdiv(v.Nn, D->wpb_hess), 32 * D->wpb_hess, D->sm_hess, v);
+        for (int l = Nh - 1; l >= 0; l--)
+        {
+            const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+            if (cnt > 0)
+                LAUNCH(k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[l], cnt, D->pw_fact);
+        }
+        for (int l = 1; l < Nh; l++)
+        {
+            const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+            if (cnt > 0)
+                LAUNCH(k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back);
+        }
+        LAUNCH(k_dot, cdiv(v.Nn, 256), 256, 0, v);
+        LAUNCH(k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, 0);
+        launch_eval(D);
+        LAUNCH(k_decide_ls_init, tgrid, 128, 0, v);
+        for (int ls = 0; ls <= o->lsMaxIter; ls++)
+        {
+            CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
+            LAUNCH(k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
+            launch_eval(D);
+            LAUNCH(k_decide_ls_trial, tgrid, 128, 0, v);
+            if (read_counters(D)) return 1;
+            if (D->h_counters[1] == 0) break;
+        }
+    }
+    LAUNCH(k_finalize_status, cdiv(nT, 256), 256, 0, v);
+    {
+        int n = v.X > v.U ? v.X : v.U;
+        LAUNCH(k_finish, cdiv(n > 0 ? n : 1, 256), 256, 0, v);
+    }
+    CK(cudaEventRecord(D->ev1, D->stream));
+    CK(cudaMemcpyAsync(h_status, v.status, sizeof(int) * (size_t) (2 * nT), cudaMemcpyDeviceToHost, D->stream));
+    CK(cudaMemcpyAsync(D->h_counters, v.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, D->stream));
+    if (ls_iters256)
+        CK(cudaMemcpyAsync(ls_iters256, v.ls_hist, sizeof(int) * 256, cudaMemcpyDeviceToHost, D->stream));
+    CK(cudaStreamSynchronize(D->stream));
+    CK(cudaGetLastError());
+    (void) h_iter; /* h_iter == h_status + nT: filled by the copy above (status and iter are adjacent) */
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, D->ev0, D->ev1));
+    if (gpu_ms) *gpu_ms = ms;
+    if (ls_total) *ls_total = D->h_counters[3];
+    if (n_reg) *n_reg = D->h_counters[2];
+    if (launches) *launches = D->launches;
+    return 0;
+}

@@ -1,0 +1,648 @@
+/*
+ * tdunes_kernels.cuh -- sm_100a kernels of the dual Newton strategy on a forest of tree QPs.
+ *
+ * One warp owns one unit of work (a node for the stage QPs / gradient, a parent block for the
+ * Hessian, factorisation and substitutions).  Every unit's data is contiguous in HBM
+ * (children of a node are numbered consecutively, so [A_kids], [B_kids], lambda_kids, W_p, Ut_p
+ * are single ranges) and is read with unit-stride warp accesses; small dense blocks are staged
+ * in shared memory and factorised there by the warp (no library call per block).
+ *
+ * Kernel                replaces (reference file:line)
+ *   k_stage<0>          solve_stage_problems dual_Newton_tree.c:218 + stage_qp_clipping_solve_extended clipping.c:188
+ *   k_stage<1>          evaluate_dual_function :823 + stage_qp_clipping_solve clipping.c:231 + eval_dual_term clipping.c:359
+ *   k_gradient          build_dual_problem :519-539 + calculate_error_in_residuals :412
+ *   k_hessian           build_dual_problem :551-615 + clipping.c:264-355 (set_CmPnCmT/add_EPmE/add_CmPnCkT)
+ *   k_factor_level      calculate_delta_lambda :668-758 + treeqp_dpotrf_l_with_reg_opts dual_Newton_common.c:35
+ *   k_backsolve_level   calculate_delta_lambda :760-775
+ *   k_dot / k_lambda_step / k_decide_*   line_search :922-1019, gradient_trans_times_direction :808
+ *   k_finish            stage_qp_clipping_export_mu clipping.c:386
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../host/host_internal.h"
+
+#define TQB_RUNNING (-1)
+#define FULL 0xffffffffu
+
+struct View
+{
+    tqb_tables T;
+    tqb_inputs in;
+    /* outputs / iterates (x,u,lam,mux,muu contiguous: one D2H copy) */
+    double *x, *u, *lam, *mux, *muu;
+    double *dlam, *res, *resMod, *xUnc, *uUnc, *P, *Rt, *Linv;
+    double *W, *Ut;
+    double *nva, *nvb, *cva, *cvb; /* per-node and per-chunk reduction scratch */
+    /* per tree */
+    int *status, *iter, *ls_cnt, *ls_active, *restart_cnt;
+    double *t_f0, *t_dot, *t_tau, *t_tauprev, *t_err;
+    int *counters; /* [0] trees still running, [1] trees with a pending line-search trial, [2] regularised blocks, [3] total trials */
+    int *ls_hist;  /* [256] trials per Newton iteration of tree 0 */
+    int Nn, nT, X, U, nchunk;
+    /* per-warp shared memory layout, in doubles */
+    int abmax, dmax, nxmax, numax;
+    tqb_opts o;
+};
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+/* inclusive clip, lower bound wins when both fire (blasfeo_dveccl_mask, AVX branch,
+ * external/blasfeo/auxiliary/d_aux_lib4.c:4412-4417) */
+__device__ __forceinline__ double clip_mask(double v, double lo, double hi, int &mask)
+{
+    const bool up = hi <= v, dn = v <= lo;
+    mask = dn ? -1 : (up ? 1 : 0);
+    return dn ? lo : (up ? hi : v);
+}
+
+__global__ void k_init(View v)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.X) v.lam[i] = v.in.lam0[i];
+    if (i < v.nT)
+    {
+        v.status[i] = TQB_RUNNING;
+        v.iter[i] = 0;
+        v.ls_cnt[i] = 0;
+        v.ls_active[i] = 0;
+        v.restart_cnt[i] = 0;
+    }
+    if (i < 256) v.ls_hist[i] = 0;
+    if (i < 4) v.counters[i] = 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Stage QPs of all nodes.  MODE 0: "extended" solve (keeps the unconstrained solution and the
+ * elimination vectors P = Qinv.*[inactive], Rt = Rinv.*[inactive]);  MODE 1: clip-only solve +
+ * this node's term of the dual function, written to nvb[g].
+ * Algorithmic bytes per node: (5nx+4nu) + sum_kids (nx_j(nx+nu) + nx_j) read, 4nx+4nu written.
+ * ---------------------------------------------------------------------------------------- */
+template <int MODE>
+__global__ void __launch_bounds__(256) k_stage(View v)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int g = blockIdx.x * wpb + wib;
+    if (g >= v.Nn) return;
+    const int t = v.T.tree[g];
+    if (MODE == 0) { if (v.status[t] != TQB_RUNNING) return; }
+    else           { if (!v.ls_active[t]) return; }
+
+    double *sAB = smem + (size_t) wib * (v.abmax + v.dmax);
+    double *sL = sAB + v.abmax;
+    const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
+    const int nk = v.T.nkids[g], k0 = v.T.kid0[g], d = v.T.dim[g];
+    const bool root = v.T.dad[g] < 0;
+
+    /* stage [A_kids] (d*nx), [B_kids] (d*nu) and lambda_kids (d): three contiguous ranges */
+    double cpart = 0.0;
+    if (nk > 0)
+    {
+        const double *Ag = v.in.A + v.T.aoff[k0], *Bg = v.in.B + v.T.boff[k0];
+        const double *lg = v.lam + v.T.xoff[k0];
+        const int na = d * nx, nb = d * nu;
+        for (int e = lane; e < na; e += 32) sAB[e] = Ag[e];
+        for (int e = lane; e < nb; e += 32) sAB[na + e] = Bg[e];
+        for (int e = lane; e < d; e += 32)
+        {
+            const double l = lg[e];
+            sL[e] = l;
+            if (MODE == 1) cpart += v.in.b[v.T.xoff[k0] + e] * l;
+        }
+        __syncwarp();
+    }
+
+    double xQx = 0.0, xq = 0.0, uRu = 0.0, ur = 0.0;
+    for (int w = lane; w < nx + nu; w += 32)
+    {
+        const bool isx = w < nx;
+        const int i = isx ? w : w - nx;
+        double acc;
+        if (isx) acc = -v.in.q[xo + i] + (root ? 0.0 : v.lam[xo + i]);
+        else     acc = -v.in.r[uo + i];
+        /* acc -= A_j' lambda_j (resp. B_j' lambda_j) child by child (dgemv_t per child) */
+        int oa = isx ? 0 : d * nx, pos = 0;
+        const int ncol = isx ? nx : nu;
+        for (int j = 0; j < nk; j++)
+        {
+            const int nxj = v.T.nx[k0 + j];
+            const double *col = sAB + oa + i * nxj;
+            double s = 0.0;
+            for (int r = 0; r < nxj; r++) s += col[r] * sL[pos + r];
+            acc -= s;
+            oa += nxj * ncol;
+            pos += nxj;
+        }
+        int mask;
+        if (isx)
+        {
+            const double unc = v.in.Qinv[xo + i] * acc;
+            const double val = clip_mask(unc, v.in.xmin[xo + i], v.in.xmax[xo + i], mask);
+            v.x[xo + i] = val;
+            if (MODE == 0)
+            {
+                v.xUnc[xo + i] = unc;
+                v.P[xo + i] = mask == 0 ? v.in.Qinv[xo + i] : 0.0;
+            }
+            else
+            {
+                xQx += (v.in.Qd[xo + i] * val) * val;
+                xq += acc * val;
+            }
+        }
+        else
+        {
+            const double unc = v.in.Rinv[uo + i] * acc;
+            const double val = clip_mask(unc, v.in.umin[uo + i], v.in.umax[uo + i], mask);
+            v.u[uo + i] = val;
+            if (MODE == 0)
+            {
+                v.uUnc[uo + i] = unc;
+                v.Rt[uo + i] = mask == 0 ? v.in.Rinv[uo + i] : 0.0;
+            }
+            else
+            {
+                uRu += (v.in.Rd[uo + i] * val) * val;
+                ur += acc * val;
+            }
+        }
+    }
+    if (MODE == 1)
+    {
+        xQx = warp_sum(xQx); xq = warp_sum(xq); uRu = warp_sum(uRu); ur = warp_sum(ur);
+        const double cmod = warp_sum(cpart);
+        if (lane == 0)
+        {   /* order of clipping.c:375-381 */
+            double f = -0.5 * xQx - cmod;
+            f += xq;
+            f -= 0.5 * uRu;
+            f += ur;
+            v.nvb[g] = f;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Dual gradient: res_k = b_k - x_k + A_k x_dad + B_k u_dad for every non-root node, plus the
+ * node's contribution to the termination norm in nva[g].
+ * Bytes per edge: nx_k(nx_p+nu_p) + 2nx_k + nx_p + nu_p read, 2nx_k written.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) k_gradient(View v)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= v.Nn) return;
+    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+    const int p = v.T.dad[g];
+    double part = 0.0;
+    if (p >= 0)
+    {
+        const int nx = v.T.nx[g], nxp = v.T.nx[p], nup = v.T.nu[p], xo = v.T.xoff[g];
+        const double *A = v.in.A + v.T.aoff[g], *B = v.in.B + v.T.boff[g];
+        const double *xp = v.x + v.T.xoff[p], *up = v.u + v.T.uoff[p];
+        for (int r = lane; r < nx; r += 32)
+        {
+            double s = v.in.b[xo + r] - v.x[xo + r];
+            double s1 = 0.0, s2 = 0.0;
+            for (int c = 0; c < nxp; c++) s1 += A[r + c * nx] * xp[c];
+            for (int c = 0; c < nup; c++) s2 += B[r + c * nx] * up[c];
+            s += s1;
+            s += s2;
+            v.res[xo + r] = s;
+            v.resMod[xo + r] = s;
+            if (v.o.termCondition == 2) part = fmax(part, fabs(s));
+            else part += s * s;
+        }
+    }
+    part = (v.o.termCondition == 2) ? warp_max(part) : warp_sum(part);
+    if (lane == 0) v.nva[g] = part;
+}
+
+/* fixed-shape reduction of a per-node array over each chunk of <=1024 consecutive nodes */
+__global__ void __launch_bounds__(256) k_chunk_reduce(View v, const double *src, double *dst, int is_max)
+{
+    __shared__ double sh[256];
+    const int c = blockIdx.x;
+    const int beg = v.T.chunk_beg[c], end = v.T.chunk_end[c];
+    double acc = 0.0;
+    for (int g = beg + threadIdx.x; g < end; g += 256)
+    {
+        const double val = src[g];
+        acc = is_max ? fmax(acc, val) : acc + val;
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1)
+    {
+        if (threadIdx.x < s)
+            sh[threadIdx.x] = is_max ? fmax(sh[threadIdx.x], sh[threadIdx.x + s]) : sh[threadIdx.x] + sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) dst[c] = sh[0];
+}
+
+/* per-tree reduction of the chunk values: every lane returns the result */
+__device__ __forceinline__ double tree_reduce(const View &v, const double *cv, int t, int lane, bool is_max)
+{
+    const int c0 = v.T.tchunk0[t], c1 = v.T.tchunk0[t + 1];
+    double acc = 0.0;
+    for (int c = c0 + lane; c < c1; c += 32) acc = is_max ? fmax(acc, cv[c]) : acc + cv[c];
+    return is_max ? warp_max(acc) : warp_sum(acc);
+}
+
+/* termination test per tree (dual_Newton_tree.c:542-546) */
+__global__ void k_decide_term(View v)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= v.nT) return;
+    if (v.status[t] != TQB_RUNNING) { if (lane == 0) v.ls_active[t] = 0; return; }
+    double err = tree_reduce(v, v.cva, t, lane, v.o.termCondition == 2);
+    if (v.o.termCondition == 1) err = sqrt(err);
+    if (lane == 0)
+    {
+        v.t_err[t] = err;
+        if (err < v.o.tol) { v.status[t] = 0; v.ls_active[t] = 0; }
+        else { v.ls_active[t] = 1; atomicAdd(&v.counters[0], 1); }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Dual Hessian block of every parent p:
+ *   W_p[k,s] = A_k P_p A_s' + B_k Rt_p B_s' (+ P_k if k==s), lower triangle, column-major d x d
+ *   Ut_p     = -P_p [A_k1' ... A_km']  (nx_p x d), only if p is not a root
+ * Bytes per parent: d(nx+nu) + nx + nu + d read; d(d+1)/2 + nx*d written.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) k_hessian(View v)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int per_warp = v.abmax + v.nxmax + v.numax + v.dmax; /* doubles; last dmax hold 2 int tables */
+    const int g = blockIdx.x * wpb + wib;
+    if (g >= v.Nn) return;
+    const int nk = v.T.nkids[g];
+    if (nk == 0) return;
+    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+
+    double *sAB = smem + (size_t) wib * per_warp;
+    double *sP = sAB + v.abmax;
+    int *rbase = (int *) (sP + v.nxmax + v.numax);
+    int *rstr = rbase + v.dmax;
+
+    const int nx = v.T.nx[g], nu = v.T.nu[g], d = v.T.dim[g], k0 = v.T.kid0[g];
+    const int na = d * nx, nb = d * nu;
+    const double *Ag = v.in.A + v.T.aoff[k0], *Bg = v.in.B + v.T.boff[k0];
+    for (int e = lane; e < na; e += 32) sAB[e] = Ag[e];
+    for (int e = lane; e < nb; e += 32) sAB[na + e] = Bg[e];
+    for (int e = lane; e < nx; e += 32) sP[e] = v.P[v.T.xoff[g] + e];
+    for (int e = lane; e < nu; e += 32) sP[nx + e] = v.Rt[v.T.uoff[g] + e];
+    /* row tables: row I of the stacked [A_kids;B_kids] belongs to a kid that starts at stacked row
+     * `rows` and has nxj rows: element (I,c) of A is sAB[rows*nx + i + c*nxj], of B is
+     * sAB[na + rows*nu + i + c*nxj].  rbase packs (rows<<16 | i). */
+    if (lane == 0)
+    {
+        int rows = 0, I = 0;
+        for (int j = 0; j < nk; j++)
+        {
+            const int nxj = v.T.nx[k0 + j];
+            for (int i = 0; i < nxj; i++) { rbase[I] = rows * 65536 + i; rstr[I] = nxj; I++; }
+            rows += nxj;
+        }
+    }
+    __syncwarp();
+    double *Wp = v.W + v.T.woff[g];
+    const double *Pk = v.P + v.T.xoff[k0];
+    for (int J = 0; J < d; J++)
+    {
+        const int rowsJ = rbase[J] >> 16, jj = rbase[J] & 65535, nxs = rstr[J];
+        const double *aJ = sAB + rowsJ * nx + jj;
+        const double *bJ = sAB + na + rowsJ * nu + jj;
+        for (int I = J + lane; I < d; I += 32)
+        {
+            const int rowsI = rbase[I] >> 16, ii = rbase[I] & 65535, nxk = rstr[I];
+            const double *aI = sAB + rowsI * nx + ii;
+            const double *bI = sAB + na + rowsI * nu + ii;
+            double acc = 0.0, acc2 = 0.0;
+            for (int c = 0; c < nx; c++) acc += aI[c * nxk] * (aJ[c * nxs] * sP[c]);
+            for (int c = 0; c < nu; c++) acc2 += bI[c * nxk] * (bJ[c * nxs] * sP[nx + c]);
+            acc += acc2;
+            if (I == J) acc += Pk[I];
+            Wp[I + J * d] = acc;
+        }
+    }
+    if (v.T.dad[g] >= 0)
+    {
+        double *Utp = v.Ut + v.T.utoff[g];
+        for (int e = lane; e < nx * d; e += 32)
+        {
+            const int c = e % nx, I = e / nx;
+            const int rowsI = rbase[I] >> 16, ii = rbase[I] & 65535, nxk = rstr[I];
+            Utp[e] = -(sAB[rowsI * nx + ii + c * nxk] * sP[c]);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * In-shared-memory Cholesky of a d x d block by one warp (left-looking, column by column) with
+ * BLASFEO's pivot rule (kernel_dgemm_4x4_lib4.c:4633-4646): pivot>0 ? (l=sqrt,inv=1/l) : (0,0).
+ * ---------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void warp_potrf(double *sW, int ld, int d, double *sinv, int lane)
+{
+    for (int j = 0; j < d; j++)
+    {
+        for (int i = j + lane; i < d; i += 32)
+        {
+            double s = sW[i + j * ld];
+            for (int t = 0; t < j; t++) s -= sW[i + t * ld] * sW[j + t * ld];
+            sW[i + j * ld] = s;
+        }
+        __syncwarp();
+        double piv = sW[j + j * ld], inv;
+        if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
+        else { piv = 0.0; inv = 0.0; }
+        __syncwarp();
+        for (int i = j + lane; i < d; i += 32)
+        {
+            if (i == j) { sW[j + j * ld] = piv; sinv[j] = inv; }
+            else sW[i + j * ld] *= inv;
+        }
+        __syncwarp();
+    }
+}
+
+/* y <- L^-T y in shared memory (dtrsv_ltn with the stored inverse diagonal) */
+__device__ __forceinline__ void warp_trsv_ltn(const double *sW, int ld, int d, const double *sinv,
+                                              double *sy, int lane)
+{
+    for (int i = d - 1; i >= 0; i--)
+    {
+        const double yi = sy[i] * sinv[i];
+        __syncwarp();
+        if (lane == 0) sy[i] = yi;
+        for (int t = lane; t < i; t += 32) sy[t] -= sW[i + t * ld] * yi;
+        __syncwarp();
+    }
+}
+
+/* One depth level of the leaves-to-root sweep: factor W_p (+ Levenberg-Marquardt policy of
+ * dual_Newton_common.c:35-78), y = L^-1 resMod_p, Utilde = Ut_p L^-T, then downdate the parent's
+ * diagonal sub-block and right-hand side.  Roots finish with the backward substitution.
+ * Bytes per block: d^2 + d + nx*d read, d(d+1)/2 + d + nx*d + d written, nx(nx+1)+2nx RMW. */
+__global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int count, int per_warp)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (w >= count) return;
+    const int g = v.T.lvl_nodes[lvl_begin + w];
+    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+
+    const int d = v.T.dim[g], nx = v.T.nx[g], k0 = v.T.kid0[g], dad = v.T.dad[g];
+    const int ld = d | 1, ldu = nx | 1;
+    double *sW = smem + (size_t) wib * per_warp;
+    double *sy = sW + (v.dmax | 1) * v.dmax;
+    double *sinv = sy + v.dmax;
+    double *sU = sinv + v.dmax;
+    double *Wp = v.W + v.T.woff[g];
+    const int xb = v.T.xoff[k0]; /* start of this block's segment in x-space */
+
+    for (int e = lane; e < d * d; e += 32)
+    {
+        const int i = e % d, j = e / d;
+        double val = Wp[e];
+        if (i == j && v.o.regType == 1) val += v.o.regValue;
+        sW[i + j * ld] = val;
+    }
+    for (int e = lane; e < d; e += 32) sy[e] = v.resMod[xb + e];
+    __syncwarp();
+    warp_potrf(sW, ld, d, sinv, lane);
+    if (v.o.regType == 2)
+    {
+        bool small = false;
+        for (int j = lane; j < d; j += 32) small |= (sW[j + j * ld] <= v.o.regTol);
+        if (__any_sync(FULL, small))
+        {
+            __syncwarp();
+            for (int e = lane; e < d * d; e += 32)
+            {
+                const int i = e % d, j = e / d;
+                sW[i + j * ld] = Wp[e] + (i == j ? v.o.regValue : 0.0);
+            }
+            __syncwarp();
+            warp_potrf(sW, ld, d, sinv, lane);
+            if (lane == 0) atomicAdd(&v.counters[2], 1);
+        }
+    }
+    /* store the factor (lower triangle) and its inverse diagonal */
+    for (int e = lane; e < d * d; e += 32)
+    {
+        const int i = e % d, j = e / d;
+        if (i >= j) Wp[e] = sW[i + j * ld];
+    }
+    for (int e = lane; e < d; e += 32) v.Linv[xb + e] = sinv[e];
+
+    /* forward substitution y = L^-1 resMod (dtrsv_lnn) */
+    for (int j = 0; j < d; j++)
+    {
+        const double yj = sy[j] * sinv[j];
+        __syncwarp();
+        if (lane == 0) sy[j] = yj;
+        for (int i = j + 1 + lane; i < d; i += 32) sy[i] -= sW[i + j * ld] * yj;
+        __syncwarp();
+    }
+
+    if (dad >= 0)
+    {
+        /* Utilde = Ut L^-T (dtrsm_rltn): each lane owns one row of Ut */
+        double *Utp = v.Ut + v.T.utoff[g];
+        for (int e = lane; e < nx * d; e += 32) sU[(e % nx) + (e / nx) * ldu] = Utp[e];
+        __syncwarp();
+        for (int c = lane; c < nx; c += 32)
+            for (int j = 0; j < d; j++)
+            {
+                double s = sU[c + j * ldu];
+                for (int t = 0; t < j; t++) s -= sU[c + t * ldu] * sW[j + t * ld];
+                sU[c + j * ldu] = s * sinv[j];
+            }
+        __syncwarp();
+        for (int e = lane; e < nx * d; e += 32) Utp[e] = sU[(e % nx) + (e / nx) * ldu];
+        /* parent's diagonal sub-block -= Utilde Utilde' (dsyrk_ln), rhs -= Utilde y (dgemv_n) */
+        const int dd = v.T.dim[dad], off = v.T.pos[g];
+        double *Wd = v.W + v.T.woff[dad];
+        for (int e = lane; e < nx * nx; e += 32)
+        {
+            const int a = e % nx, b = e / nx;
+            if (a < b) continue;
+            double s = 0.0;
+            for (int t = 0; t < d; t++) s += sU[a + t * ldu] * sU[b + t * ldu];
+            Wd[(off + a) + (off + b) * dd] -= s;
+        }
+        const int xo = v.T.xoff[g];
+        for (int a = lane; a < nx; a += 32)
+        {
+            double s = 0.0;
+            for (int t = 0; t < d; t++) s += sU[a + t * ldu] * sy[t];
+            v.resMod[xo + a] -= s;
+        }
+    }
+    else
+        warp_trsv_ltn(sW, ld, d, sinv, sy, lane);
+    __syncwarp();
+    for (int e = lane; e < d; e += 32) v.dlam[xb + e] = sy[e];
+}
+
+/* One depth level of the root-to-leaves sweep:
+ * dlam_p <- L_p^-T (y_p - Utilde_p' dlam_dad[segment of p])   (dual_Newton_tree.c:764-773) */
+__global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, int count, int per_warp)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (w >= count) return;
+    const int g = v.T.lvl_nodes[lvl_begin + w];
+    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+    const int d = v.T.dim[g], nx = v.T.nx[g], k0 = v.T.kid0[g];
+    const int ld = d | 1;
+    double *sW = smem + (size_t) wib * per_warp;
+    double *sy = sW + (v.dmax | 1) * v.dmax;
+    double *sinv = sy + v.dmax;
+    double *sd = sinv + v.dmax;
+    const double *Wp = v.W + v.T.woff[g], *Utp = v.Ut + v.T.utoff[g];
+    const int xb = v.T.xoff[k0], xo = v.T.xoff[g];
+    for (int e = lane; e < d * d; e += 32)
+    {
+        const int i = e % d, j = e / d;
+        if (i >= j) sW[i + j * ld] = Wp[e];
+    }
+    for (int e = lane; e < d; e += 32) { sinv[e] = v.Linv[xb + e]; }
+    for (int e = lane; e < nx; e += 32) sd[e] = v.dlam[xo + e];
+    __syncwarp();
+    for (int j = lane; j < d; j += 32)
+    {
+        double s = 0.0;
+        for (int c = 0; c < nx; c++) s += Utp[c + j * nx] * sd[c];
+        sy[j] = v.dlam[xb + j] - s;
+    }
+    __syncwarp();
+    warp_trsv_ltn(sW, ld, d, sinv, sy, lane);
+    __syncwarp();
+    for (int e = lane; e < d; e += 32) v.dlam[xb + e] = sy[e];
+}
+
+/* per-node part of res' * dlam (gradient_trans_times_direction, dual_Newton_tree.c:808-820) */
+__global__ void k_dot(View v)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= v.Nn) return;
+    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+    double s = 0.0;
+    if (v.T.dad[g] >= 0)
+    {
+        const int xo = v.T.xoff[g], nx = v.T.nx[g];
+        for (int i = 0; i < nx; i++) s += v.res[xo + i] * v.dlam[xo + i];
+    }
+    v.nva[g] = s;
+}
+
+/* start of a line search (dual_Newton_tree.c:940-956): descent test, tau = 1 */
+__global__ void k_decide_ls_init(View v)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= v.nT) return;
+    if (v.status[t] != TQB_RUNNING) return;
+    const double dot = -tree_reduce(v, v.cva, t, lane, false);
+    const double f0 = tree_reduce(v, v.cvb, t, lane, false);
+    if (lane == 0)
+    {
+        v.t_dot[t] = dot;
+        v.t_f0[t] = f0;
+        if (dot > 1e-10 || !((dot > 1e-10) || (dot < 1e-10)))
+        {
+            v.status[t] = 2; /* TREEQP_DN_NOT_DESCENT_DIRECTION */
+            v.ls_active[t] = 0;
+        }
+        else
+        {
+            v.t_tau[t] = 1.0;
+            v.t_tauprev[t] = 0.0;
+            v.ls_cnt[t] = 0;
+            v.ls_active[t] = 1;
+        }
+    }
+}
+
+/* lambda += (tau - tauPrev) * dlam for the trees with a pending trial (dual_Newton_tree.c:964-968) */
+__global__ void k_lambda_step(View v)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= v.Nn) return;
+    const int t = v.T.tree[g];
+    if (!v.ls_active[t] || v.T.dad[g] < 0) return;
+    const double step = v.t_tau[t] - v.t_tauprev[t];
+    const int xo = v.T.xoff[g], nx = v.T.nx[g];
+    for (int i = 0; i < nx; i++) v.lam[xo + i] += step * v.dlam[xo + i];
+}
+
+/* Armijo test of one trial (dual_Newton_tree.c:970-1000) */
+__global__ void k_decide_ls_trial(View v)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= v.nT) return;
+    if (!v.ls_active[t]) return;
+    const double f = tree_reduce(v, v.cvb, t, lane, false);
+    if (lane == 0)
+    {
+        const int ls = ++v.ls_cnt[t];
+        const double tau = v.t_tau[t];
+        bool done = false;
+        int recorded = ls;
+        if (v.restart_cnt[t] == v.o.lsRestartTrigger) done = true; /* full step when stuck (:973-977) */
+        else if (f <= v.t_f0[t] + v.o.gamma * tau * v.t_dot[t]) done = true;
+        else
+        {
+            v.t_tauprev[t] = tau;
+            v.t_tau[t] = v.o.beta * tau;
+            if (ls >= v.o.lsMaxIter) { done = true; recorded = v.o.lsMaxIter + 1; }
+        }
+        if (done)
+        {
+            v.ls_active[t] = 0;
+            v.restart_cnt[t] = (recorded >= v.o.lsMaxIter) ? v.restart_cnt[t] + 1 : 0; /* :993-1000 */
+            const int it = v.iter[t]++;
+            if (t == 0 && it < 256) v.ls_hist[it] = recorded;
+            atomicAdd(&v.counters[3], ls);
+        }
+        else
+            atomicAdd(&v.counters[1], 1);
+    }
+}
+
+/* trees still running after maxIter iterations (dual_Newton_tree.c:1252) */
+__global__ void k_finalize_status(View v)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < v.nT && v.status[t] == TQB_RUNNING) v.status[t] = 1;
+}
+
+/* bound multipliers mu = Q.*(xUnc - x) (clipping.c:386-399) */
+__global__ void k_finish(View v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.X) v.mux[i] = v.in.Qd[i] * (v.xUnc[i] - v.x[i]);
+    if (i < v.U) v.muu[i] = v.in.Rd[i] * (v.uUnc[i] - v.u[i]);
+}

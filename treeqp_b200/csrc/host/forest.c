@@ -1,0 +1,321 @@
+/*
+ * forest.c -- host side of the boundary: turns one or many tree_qp_in (BLASFEO panel-major
+ * views, arrays of structs per node) into the flat structure-of-arrays the kernels stream, and
+ * writes the device results back into tree_qp_out.
+ *
+ * Replaces the per-node bookkeeping of treeqp_tdunes_create (dual_Newton_tree.c:1411-1648:
+ * setup_npar :166, setup_idxpos :177) and the data staging of stage_qp_clipping_init
+ * (dual_Newton_tree_clipping.c:149-170: diagonal extraction + reciprocals).
+ */
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "treeqp_b200.h"
+#include "host_internal.h"
+
+#define TQB_CHUNK 1024 /* nodes per fixed-shape reduction chunk */
+
+double tqb_wall_ms(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return 1e3 * (double) ts.tv_sec + 1e-6 * (double) ts.tv_nsec;
+}
+
+/* carve the integer block; identical code computes host and device pointers */
+void tqb_layout_tables(const tqb_dims *d, int *base, tqb_tables *t)
+{
+    int *p = base;
+#define TK(field, n) t->field = p; p += (n)
+    TK(nx, d->Nn); TK(nu, d->Nn); TK(dad, d->Nn); TK(kid0, d->Nn); TK(nkids, d->Nn);
+    TK(tree, d->Nn); TK(depth, d->Nn); TK(pos, d->Nn); TK(dim, d->Nn);
+    TK(xoff, d->Nn); TK(uoff, d->Nn); TK(aoff, d->Nn); TK(boff, d->Nn);
+    TK(woff, d->Nn); TK(utoff, d->Nn);
+    TK(lvl_nodes, d->Np > 0 ? d->Np : 1);
+    TK(tnode0, d->nT + 1);
+    TK(chunk_beg, d->nchunk); TK(chunk_end, d->nchunk); TK(chunk_tree, d->nchunk);
+    TK(tchunk0, d->nT + 1);
+#undef TK
+    assert(p - base == d->n_int);
+}
+
+static long long pad2(long long n) { return (n + 1) / 2 * 2; } /* keep 16-byte alignment */
+
+void tqb_layout_inputs(const tqb_dims *d, double *base, tqb_inputs *in)
+{
+    double *p = base;
+#define TK(field, n) in->field = p; p += pad2(n)
+    TK(A, d->szA); TK(B, d->szB);
+    TK(b, d->X); TK(q, d->X); TK(Qd, d->X); TK(Qinv, d->X); TK(xmin, d->X); TK(xmax, d->X);
+    TK(r, d->U); TK(Rd, d->U); TK(Rinv, d->U); TK(umin, d->U); TK(umax, d->U);
+    TK(lam0, d->X);
+#undef TK
+    assert(p - base == d->n_in);
+}
+
+static long long inputs_size(const tqb_dims *d)
+{
+    return pad2(d->szA) + pad2(d->szB) + 7 * pad2(d->X) + 5 * pad2(d->U);
+}
+
+int tqb_clipping_applicable(const tree_qp_in *qp, int k)
+{
+    int nx = qp->nx[k], nu = qp->nu[k];
+    if (qp->nc[k] > 0) return NO;
+    for (int j = 0; j < nx; j++)
+        for (int i = 0; i < nx; i++)
+            if (i != j && BLASFEO_DMATEL(&qp->Q[k], i, j) != 0.0) return NO;
+    for (int j = 0; j < nu; j++)
+        for (int i = 0; i < nu; i++)
+            if (i != j && BLASFEO_DMATEL(&qp->R[k], i, j) != 0.0) return NO;
+    for (int j = 0; j < nx; j++)
+        for (int i = 0; i < nu; i++)
+            if (BLASFEO_DMATEL(&qp->S[k], i, j) != 0.0) return NO;
+    return YES;
+}
+
+tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
+{
+    tqb_forest *f = (tqb_forest *) calloc(1, sizeof(tqb_forest));
+    tqb_dims *d = &f->dims;
+    d->nT = nT;
+    long long Nn = 0;
+    for (int t = 0; t < nT; t++) Nn += qps[t]->N;
+    if (Nn > 2000000000LL) { free(f); return NULL; }
+    d->Nn = (int) Nn;
+
+    /* pass 1: counts */
+    long long X = 0, U = 0, szA = 0, szB = 0, szW = 0, szUt = 0;
+    int Np = 0, Nh = 0, nchunk = 0;
+    for (int t = 0; t < nT; t++)
+    {
+        const tree_qp_in *qp = qps[t];
+        nchunk += (qp->N + TQB_CHUNK - 1) / TQB_CHUNK;
+        for (int k = 0; k < qp->N; k++)
+        {
+            const struct node *nd = &qp->tree[k];
+            X += qp->nx[k];
+            U += qp->nu[k];
+            if (nd->stage > Nh) Nh = nd->stage;
+            if (k > 0)
+            {
+                szA += (long long) qp->nx[k] * qp->nx[nd->dad];
+                szB += (long long) qp->nx[k] * qp->nu[nd->dad];
+            }
+            if (nd->nkids > 0)
+            {
+                long long dim = 0;
+                for (int j = 0; j < nd->nkids; j++) dim += qp->nx[nd->kids[j]];
+                Np++;
+                szW += dim * dim;
+                if (k > 0) szUt += dim * qp->nx[k];
+            }
+        }
+    }
+    if (X > 2000000000LL || szA > 2000000000LL || szW > 2000000000LL || szB > 2000000000LL)
+    {
+        fprintf(stderr, "[treeqp_b200] problem too large for 32-bit element offsets\n");
+        free(f);
+        return NULL;
+    }
+    d->X = (int) X; d->U = (int) U; d->szA = szA; d->szB = szB; d->szW = szW; d->szUt = szUt;
+    d->Np = Np; d->Nh = Nh; d->nchunk = nchunk;
+    d->n_int = 15 * d->Nn + (Np > 0 ? Np : 1) + 2 * (nT + 1) + 3 * nchunk;
+    d->n_in = inputs_size(d);
+
+    f->h_int = (int *) malloc(sizeof(int) * (size_t) d->n_int);
+    tqb_layout_tables(d, f->h_int, &f->ht);
+    tqb_tables *T = &f->ht;
+
+    /* pass 2: tables */
+    int g0 = 0, xo = 0, uo = 0, ao = 0, bo = 0, wo = 0, uto = 0, c = 0;
+    int *lvl_count = (int *) calloc((size_t) Nh + 2, sizeof(int));
+    for (int t = 0; t < nT; t++)
+    {
+        const tree_qp_in *qp = qps[t];
+        T->tnode0[t] = g0;
+        T->tchunk0[t] = c;
+        for (int s = 0; s < qp->N; s += TQB_CHUNK)
+        {
+            T->chunk_beg[c] = g0 + s;
+            T->chunk_end[c] = g0 + (s + TQB_CHUNK < qp->N ? s + TQB_CHUNK : qp->N);
+            T->chunk_tree[c] = t;
+            c++;
+        }
+        for (int k = 0; k < qp->N; k++)
+        {
+            const struct node *nd = &qp->tree[k];
+            int g = g0 + k;
+            T->nx[g] = qp->nx[k];
+            T->nu[g] = qp->nu[k];
+            T->dad[g] = nd->dad < 0 ? -1 : g0 + nd->dad;
+            T->nkids[g] = nd->nkids;
+            T->kid0[g] = nd->nkids > 0 ? g0 + nd->kids[0] : -1;
+            T->tree[g] = t;
+            T->depth[g] = nd->stage;
+            T->xoff[g] = xo; xo += qp->nx[k];
+            T->uoff[g] = uo; uo += qp->nu[k];
+            T->aoff[g] = ao; T->boff[g] = bo;
+            if (k > 0)
+            {
+                ao += qp->nx[k] * qp->nx[nd->dad];
+                bo += qp->nx[k] * qp->nu[nd->dad];
+            }
+            int dim = 0;
+            for (int j = 0; j < nd->nkids; j++)
+            {
+                /* children must be numbered consecutively (breadth-first numbering) */
+                assert(nd->kids[j] == nd->kids[0] + j);
+                dim += qp->nx[nd->kids[j]];
+            }
+            T->dim[g] = dim;
+            T->woff[g] = wo; T->utoff[g] = uto;
+            if (nd->nkids > 0)
+            {
+                wo += dim * dim;
+                if (k > 0) uto += dim * qp->nx[k];
+                lvl_count[nd->stage]++;
+                if (dim > d->dmax) d->dmax = dim;
+                if (nd->nkids > d->nkmax) d->nkmax = nd->nkids;
+                int ab = dim * (qp->nx[k] + qp->nu[k]);
+                if (ab > d->abmax) d->abmax = ab;
+            }
+            if (qp->nx[k] > d->nxmax) d->nxmax = qp->nx[k];
+            if (qp->nu[k] > d->numax) d->numax = qp->nu[k];
+        }
+        /* idxpos (dual_Newton_tree.c:177-194) */
+        for (int k = 0; k < qp->N; k++)
+        {
+            const struct node *nd = &qp->tree[k];
+            int acc = 0;
+            for (int j = 0; j < nd->nkids; j++)
+            {
+                T->pos[g0 + nd->kids[j]] = acc;
+                acc += qp->nx[nd->kids[j]];
+            }
+            if (k == 0) T->pos[g0] = 0;
+        }
+        g0 += qp->N;
+    }
+    T->tnode0[nT] = g0;
+    T->tchunk0[nT] = c;
+
+    /* level lists of parents: counting sort by depth, node order inside a level */
+    f->lvl_ptr = (int *) malloc(sizeof(int) * (size_t) (Nh + 2));
+    f->lvl_ptr[0] = 0;
+    for (int l = 0; l <= Nh; l++) f->lvl_ptr[l + 1] = f->lvl_ptr[l] + lvl_count[l];
+    memset(lvl_count, 0, sizeof(int) * (size_t) (Nh + 2));
+    for (int g = 0; g < d->Nn; g++)
+        if (T->nkids[g] > 0)
+        {
+            int l = T->depth[g];
+            T->lvl_nodes[f->lvl_ptr[l] + lvl_count[l]++] = g;
+        }
+    free(lvl_count);
+
+    f->h_in = (double *) tqb_pinned_alloc(sizeof(double) * (size_t) d->n_in);
+    size_t nout = (size_t) 3 * d->X + 2 * d->U + 8;
+    f->h_out = (double *) tqb_pinned_alloc(sizeof(double) * nout);
+    f->h_status = (int *) tqb_pinned_alloc(sizeof(int) * (size_t) (2 * nT + 2));
+    if (!f->h_in || !f->h_out || !f->h_status) { tqb_forest_destroy(f); return NULL; }
+    f->h_iter = f->h_status + nT;
+    memset(f->h_in, 0, sizeof(double) * (size_t) d->n_in);
+    tqb_layout_inputs(d, f->h_in, &f->hin);
+
+    f->dev = tqb_device_create(d, f->h_int, f->lvl_ptr);
+    if (!f->dev) { tqb_forest_destroy(f); return NULL; }
+    return f;
+}
+
+void tqb_forest_destroy(tqb_forest *f)
+{
+    if (!f) return;
+    if (f->dev) tqb_device_destroy(f->dev);
+    if (f->h_in) tqb_pinned_free(f->h_in);
+    if (f->h_out) tqb_pinned_free(f->h_out);
+    if (f->h_status) tqb_pinned_free(f->h_status);
+    free(f->lvl_ptr);
+    free(f->h_int);
+    free(f);
+}
+
+/* panel-major -> column-major, 4 rows of a panel at a time */
+static void unpack_dmat(const struct blasfeo_dmat *M, double *dst)
+{
+    int m = M->m, n = M->n;
+    for (int j = 0; j < n; j++)
+        for (int i = 0; i < m; i++) dst[i + (size_t) j * m] = BLASFEO_DMATEL(M, i, j);
+}
+
+void tqb_forest_pack(tqb_forest *f, int t, const tree_qp_in *qp)
+{
+    const tqb_tables *T = &f->ht;
+    tqb_inputs *in = &f->hin;
+    int g0 = T->tnode0[t];
+    assert(T->tnode0[t + 1] - g0 == qp->N);
+    for (int k = 0; k < qp->N; k++)
+    {
+        int g = g0 + k, nx = qp->nx[k], nu = qp->nu[k], xo = T->xoff[g], uo = T->uoff[g];
+        assert(nx == T->nx[g] && nu == T->nu[g]);
+        if (k > 0)
+        {
+            unpack_dmat(&qp->A[k - 1], in->A + T->aoff[g]);
+            unpack_dmat(&qp->B[k - 1], in->B + T->boff[g]);
+            memcpy(in->b + xo, qp->b[k - 1].pa, sizeof(double) * (size_t) nx);
+        }
+        else
+            for (int i = 0; i < nx; i++) in->b[xo + i] = 0.0;
+        for (int i = 0; i < nx; i++)
+        {
+            double w = BLASFEO_DMATEL(&qp->Q[k], i, i);
+            in->Qd[xo + i] = w;
+            in->Qinv[xo + i] = 1.0 / w;
+        }
+        for (int i = 0; i < nu; i++)
+        {
+            double w = BLASFEO_DMATEL(&qp->R[k], i, i);
+            in->Rd[uo + i] = w;
+            in->Rinv[uo + i] = 1.0 / w;
+        }
+        memcpy(in->q + xo, qp->q[k].pa, sizeof(double) * (size_t) nx);
+        memcpy(in->xmin + xo, qp->xmin[k].pa, sizeof(double) * (size_t) nx);
+        memcpy(in->xmax + xo, qp->xmax[k].pa, sizeof(double) * (size_t) nx);
+        memcpy(in->r + uo, qp->r[k].pa, sizeof(double) * (size_t) nu);
+        memcpy(in->umin + uo, qp->umin[k].pa, sizeof(double) * (size_t) nu);
+        memcpy(in->umax + uo, qp->umax[k].pa, sizeof(double) * (size_t) nu);
+    }
+}
+
+/* lambda: multipliers of nodes 1..N-1 of tree t, concatenated (dual_Newton_tree.c:1654-1663) */
+void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda)
+{
+    const tqb_tables *T = &f->ht;
+    int g0 = T->tnode0[t], g1 = T->tnode0[t + 1];
+    int xroot = T->xoff[g0], nx0 = T->nx[g0];
+    int xend = (g1 < f->dims.Nn) ? T->xoff[g1] : f->dims.X;
+    for (int i = 0; i < nx0; i++) f->hin.lam0[xroot + i] = 0.0;
+    memcpy(f->hin.lam0 + xroot + nx0, lambda, sizeof(double) * (size_t) (xend - xroot - nx0));
+}
+
+/* device results (pinned staging) -> BLASFEO views of tree_qp_out
+ * (copy-out loop of dual_Newton_tree.c:1235-1247) */
+void tqb_forest_unpack(const tqb_forest *f, int t, tree_qp_out *out)
+{
+    const tqb_tables *T = &f->ht;
+    const tqb_dims *d = &f->dims;
+    const double *x = f->h_out, *u = x + d->X, *lam = u + d->U, *mux = lam + d->X, *muu = mux + d->X;
+    int g0 = T->tnode0[t], N = T->tnode0[t + 1] - g0;
+    for (int k = 0; k < N; k++)
+    {
+        int g = g0 + k, nx = T->nx[g], nu = T->nu[g], xo = T->xoff[g], uo = T->uoff[g];
+        memcpy(out->x[k].pa, x + xo, sizeof(double) * (size_t) nx);
+        memcpy(out->u[k].pa, u + uo, sizeof(double) * (size_t) nu);
+        memcpy(out->mu_x[k].pa, mux + xo, sizeof(double) * (size_t) nx);
+        memcpy(out->mu_u[k].pa, muu + uo, sizeof(double) * (size_t) nu);
+        if (k > 0) memcpy(out->lam[k - 1].pa, lam + xo, sizeof(double) * (size_t) nx);
+    }
+}

@@ -1,0 +1,130 @@
+/*
+ * host_internal.h -- internal interface between the C host layer (containers.c, forest.c,
+ * tdunes.c) and the CUDA layer (cuda/device.cu, cuda/kernels.cu).  Plain C, no CUDA types.
+ *
+ * Vocabulary
+ *   forest   nT independent tree QPs laid out back to back ("tree-major"); a single
+ *            treeqp_tdunes_solve is a forest of one tree, a batch of MPC QPs is a forest of n.
+ *   node     global index g = tnode0[t] + local breadth-first index
+ *   x-space  all per-state vectors (x, q, xmin, lambda, res, ...) concatenated in node order;
+ *            the multiplier lambda_k of node k's dynamics sits at xoff[k] (unused for roots), so
+ *            the reference's per-parent block vector slambda[p] (dual_Newton_tree.c:177-194) is the
+ *            contiguous range [xoff[kid0[p]], +dim[p]).
+ *   u-space  same for inputs.
+ *   block    a parent node p: dual Hessian block W_p (dim[p] x dim[p], dim = sum of the kids' nx)
+ *            and, if p is not a root, the coupling Ut_p (nx[p] x dim[p]).
+ */
+#ifndef TQB_HOST_INTERNAL_H_
+#define TQB_HOST_INTERNAL_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- integer tables (one allocation; same layout on host and device) ---- */
+typedef struct tqb_tables
+{
+    int *nx, *nu;        /* [Nn] */
+    int *dad;            /* [Nn] global index of the parent, -1 for roots */
+    int *kid0, *nkids;   /* [Nn] first child / number of children */
+    int *tree;           /* [Nn] owning tree */
+    int *depth;          /* [Nn] */
+    int *pos;            /* [Nn] offset of lambda_k inside its parent's block (idxpos) */
+    int *dim;            /* [Nn] block dimension (0 for leaves) */
+    int *xoff, *uoff;    /* [Nn] offsets into x-/u-space */
+    int *aoff, *boff;    /* [Nn] offsets of A_k (nx[k] x nx[dad]) / B_k (nx[k] x nu[dad]), column-major */
+    int *woff, *utoff;   /* [Nn] offsets of W_p / Ut_p */
+    int *lvl_nodes;      /* [Np] parents sorted by depth (level lists) */
+    int *tnode0;         /* [nT+1] node range of each tree */
+    int *chunk_beg, *chunk_end, *chunk_tree; /* [nchunk] fixed-shape reduction chunks */
+    int *tchunk0;        /* [nT+1] chunk range of each tree */
+} tqb_tables;
+
+typedef struct tqb_dims
+{
+    int nT, Nn, Np, Nh;  /* trees, nodes, parents, max depth */
+    int X, U;            /* x-/u-space sizes */
+    long long szA, szB, szW, szUt;
+    int dmax, nxmax, numax, nkmax, abmax; /* abmax = max over parents of dim*(nx+nu) */
+    int nchunk;
+    int n_int;           /* ints in the table block */
+    long long n_in;      /* doubles in the input block */
+} tqb_dims;
+
+/* ---- input block (doubles; one allocation, one H2D copy) ---- */
+typedef struct tqb_inputs
+{
+    double *A, *B;       /* [szA], [szB] */
+    double *b;           /* [X] b_k at xoff[k] (unused for roots) */
+    double *q, *Qd, *Qinv, *xmin, *xmax; /* [X] */
+    double *r, *Rd, *Rinv, *umin, *umax; /* [U] */
+    double *lam0;        /* [X] dual start, lambda_k at xoff[k] */
+} tqb_inputs;
+
+/* ---- options forwarded to the device ---- */
+typedef struct tqb_opts
+{
+    int maxIter, termCondition, regType, lsMaxIter, lsRestartTrigger;
+    double tol, regTol, regValue, gamma, beta;
+} tqb_opts;
+
+/* opaque device context (cuda/device.cu) */
+typedef struct tqb_device tqb_device;
+
+/* host-side forest: tables + pinned staging for the inputs and the outputs */
+typedef struct tqb_forest
+{
+    tqb_dims dims;
+    int *lvl_ptr;            /* [Nh+1] host only: ranges of lvl_nodes per depth */
+    int *h_int;              /* host table block (n_int ints) */
+    tqb_tables ht;           /* pointers into h_int */
+    double *h_in;            /* pinned input staging (n_in doubles) */
+    tqb_inputs hin;          /* pointers into h_in */
+    double *h_out;           /* pinned output staging: x[X] u[U] lam[X] mu_x[X] mu_u[U] */
+    int *h_status, *h_iter;  /* pinned [nT] */
+    tqb_device *dev;
+    /* statistics of the last solve */
+    int ls_iters[256];
+    int iter_max, ls_total, n_reg;
+    double gpu_ms, h2d_ms, d2h_ms, pack_ms;
+    long long h2d_bytes, d2h_bytes, launches;
+} tqb_forest;
+
+/* ---- forest.c ---- */
+struct tree_qp_in_;
+struct tree_qp_out_;
+tqb_forest *tqb_forest_create(int nT, const struct tree_qp_in_ *const *qps);
+void tqb_forest_destroy(tqb_forest *f);
+/* BLASFEO views -> pinned staging (reciprocals of the weights are formed here,
+ * dual_Newton_tree_clipping.c:149-170) */
+void tqb_forest_pack(tqb_forest *f, int t, const struct tree_qp_in_ *qp);
+void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda);
+void tqb_forest_unpack(const tqb_forest *f, int t, struct tree_qp_out_ *out);
+void tqb_layout_tables(const tqb_dims *d, int *base, tqb_tables *t);
+void tqb_layout_inputs(const tqb_dims *d, double *base, tqb_inputs *in);
+/* returns YES(0)/NO(1) like stage_qp_clipping_is_applicable (clipping.c:45-77) */
+int tqb_clipping_applicable(const struct tree_qp_in_ *qp, int node);
+double tqb_wall_ms(void);
+
+/* ---- cuda/device.cu ---- */
+int tqb_cuda_device_count(void);
+int tqb_cuda_set_device(int dev);
+void *tqb_pinned_alloc(size_t bytes);
+void tqb_pinned_free(void *p);
+tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int, const int *lvl_ptr);
+void tqb_device_destroy(tqb_device *d);
+/* async H2D of the input block, returns 0 on success */
+int tqb_device_upload(tqb_device *d, const double *h_in, long long n_in, double *ms);
+/* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
+int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,
+                     int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms, long long *launches);
+/* async D2H of x,u,lam,mu_x,mu_u into h_out */
+int tqb_device_download(tqb_device *d, double *h_out, double *ms);
+const char *tqb_cuda_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

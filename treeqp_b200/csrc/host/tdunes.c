@@ -1,0 +1,433 @@
+/*
+ * tdunes.c -- the reference's TDUNES C API (treeqp/src/dual_Newton_tree.h:154-168) on top of the
+ * CUDA engine, plus the additive device-resident and batch entry points.
+ *
+ * Ownership follows the reference: the caller owns the host buffer handed to
+ * treeqp_tdunes_create (sized by treeqp_tdunes_calculate_size).  Device memory cannot live in
+ * that buffer, so `create` also allocates a device arena that treeqp_tdunes_destroy releases
+ * (an API extension: callers that never call it leak the arena at exit, nothing else changes).
+ */
+#include <assert.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "treeqp_b200.h"
+#include "host_internal.h"
+
+#define TQB_MAGIC 0x7D0B200u
+
+typedef struct tqb_ctx
+{
+    unsigned magic;
+    tqb_forest *forest;
+    int lam_dirty;  /* lambda0 changed on the host since the last upload */
+    int uploaded;   /* problem data present on the device */
+    return_t last_status;
+} tqb_ctx;
+
+struct treeqp_tdunes_batch_
+{
+    int n;
+    tqb_forest *forest;
+    tqb_opts o;
+    int opts_ok;
+    int uploaded;
+};
+
+const char *treeqp_b200_version(void) { return "treeqp_b200 0.1 (sm_100a)"; }
+int treeqp_b200_device_count(void) { return tqb_cuda_device_count(); }
+int treeqp_b200_set_device(int device) { return tqb_cuda_set_device(device); }
+
+/* ----------------------------------------------------------------------------- options ---- */
+
+int treeqp_tdunes_opts_calculate_size(int Nn) { return Nn * (int) sizeof(stage_qp_t); }
+
+void treeqp_tdunes_opts_create(int Nn, treeqp_tdunes_opts_t *opts, void *ptr)
+{
+    (void) Nn;
+    opts->qp_solver = (stage_qp_t *) ptr;
+}
+
+/* defaults of dual_Newton_tree.c:92-120 */
+void treeqp_tdunes_opts_set_default(int Nn, treeqp_tdunes_opts_t *opts)
+{
+    opts->maxIter = 100;
+    opts->termCondition = TREEQP_INFNORM;
+    opts->stationarityTolerance = 1.0e-8;
+    opts->checkLastActiveSet = 1;
+    for (int i = 0; i < Nn; i++) opts->qp_solver[i] = TREEQP_CLIPPING_SOLVER;
+    opts->lineSearchMaxIter = 50;
+    opts->lineSearchGamma = 0.1;
+    opts->lineSearchBeta = 0.6;
+    opts->lineSearchRestartTrigger = -1;
+    opts->regType = TREEQP_ON_THE_FLY_LEVENBERG_MARQUARDT;
+    opts->regTol = 1.0e-6;
+    opts->regValue = 1.0e-6;
+}
+
+/* dual_Newton_tree.c:1078-1100 */
+static return_t validate_opts(const treeqp_tdunes_opts_t *o)
+{
+    if (o->termCondition != TREEQP_SUMSQUAREDERRORS && o->termCondition != TREEQP_TWONORM &&
+        o->termCondition != TREEQP_INFNORM)
+        return TREEQP_INVALID_OPTION;
+    if ((int) o->regType != TREEQP_NO_REGULARIZATION &&
+        (int) o->regType != TREEQP_ALWAYS_LEVENBERG_MARQUARDT &&
+        (int) o->regType != TREEQP_ON_THE_FLY_LEVENBERG_MARQUARDT)
+        return TREEQP_INVALID_OPTION;
+    if (o->regValue < 0) return TREEQP_INVALID_OPTION;
+    return TREEQP_OK;
+}
+
+static void forward_opts(const treeqp_tdunes_opts_t *o, tqb_opts *d)
+{
+    d->maxIter = o->maxIter;
+    d->termCondition = (int) o->termCondition;
+    d->regType = (int) o->regType;
+    d->lsMaxIter = o->lineSearchMaxIter;
+    d->lsRestartTrigger = o->lineSearchRestartTrigger;
+    d->tol = o->stationarityTolerance;
+    d->regTol = o->regTol;
+    d->regValue = o->regValue;
+    d->gamma = o->lineSearchGamma;
+    d->beta = o->lineSearchBeta;
+}
+
+/* --------------------------------------------------------------------------- workspace ---- */
+
+static int host_bytes(int Nn, int Nh)
+{
+    long long b = 0;
+    b += (long long) (Nh + 1) * sizeof(int);   /* npar */
+    b += (long long) Nn * sizeof(int);         /* idxpos */
+    b += 2LL * Nn * sizeof(double);            /* fval, cmod */
+    b += (long long) Nn * sizeof(void *);      /* stage_qp_data */
+    b = (b + 63) / 64 * 64 + 3 * 64;
+    return (int) b;
+}
+
+int treeqp_tdunes_calculate_size(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts)
+{
+    (void) opts;
+    int Nn = qp_in->N;
+    return host_bytes(Nn, qp_in->tree[Nn - 1].stage);
+}
+
+static void check_stage_solvers(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts)
+{
+    for (int k = 0; k < qp_in->N; k++)
+    {
+        if (opts->qp_solver[k] == TREEQP_CLIPPING_SOLVER)
+        {
+            if (tqb_clipping_applicable(qp_in, k) == NO)
+            {   /* same reaction as clipping.c:70-74 */
+                printf("[TREEQP]: Error! Specified stage QP solver (clipping) not applicable.\n");
+                exit(1);
+            }
+        }
+        else if (opts->qp_solver[k] == TREEQP_QPOASES_SOLVER)
+        {
+            printf("[TREEQP_B200]: Error! Dense stage QPs are not available in this build.\n");
+            exit(1);
+        }
+        else
+        {   /* dual_Newton_tree.c:158-160 */
+            printf("[TREEQP] Error! Unknown stage QP solver specified.\n");
+            exit(1);
+        }
+    }
+}
+
+void treeqp_tdunes_create(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts,
+                          treeqp_tdunes_workspace *work, void *ptr)
+{
+    const int Nn = qp_in->N, Nh = qp_in->tree[Nn - 1].stage;
+    memset(work, 0, sizeof *work);
+    check_stage_solvers(qp_in, opts);
+
+    char *cur = (char *) ptr;
+    uintptr_t a = ((uintptr_t) cur + 63u) / 64u * 64u;
+    cur = (char *) a;
+    work->stage_qp_data = (void **) cur; cur += (size_t) Nn * sizeof(void *);
+    work->fval = (double *) cur;         cur += (size_t) Nn * sizeof(double);
+    work->cmod = (double *) cur;         cur += (size_t) Nn * sizeof(double);
+    work->npar = (int *) cur;            cur += (size_t) (Nh + 1) * sizeof(int);
+    work->idxpos = (int *) cur;          cur += (size_t) Nn * sizeof(int);
+    assert(cur <= (char *) ptr + host_bytes(Nn, Nh));
+
+    int Np = 0;
+    for (int l = 0; l <= Nh; l++) work->npar[l] = 0;
+    for (int k = 0; k < Nn; k++)
+    {   /* setup_npar :166, setup_idxpos :177 */
+        const struct node *nd = &qp_in->tree[k];
+        work->npar[nd->stage]++;
+        if (nd->nkids > 0) Np++;
+        int acc = 0;
+        for (int j = 0; j < nd->nkids; j++)
+        {
+            work->idxpos[nd->kids[j]] = acc;
+            acc += qp_in->nx[nd->kids[j]];
+        }
+        work->stage_qp_data[k] = NULL;
+        work->fval[k] = work->cmod[k] = 0.0;
+    }
+    work->idxpos[0] = 0;
+    work->Nn = Nn;
+    work->Np = Np;
+
+    tqb_ctx *ctx = (tqb_ctx *) calloc(1, sizeof(tqb_ctx));
+    ctx->magic = TQB_MAGIC;
+    const tree_qp_in *one[1] = {qp_in};
+    ctx->forest = tqb_forest_create(1, one);
+    if (!ctx->forest)
+    {
+        fprintf(stderr, "[treeqp_b200] treeqp_tdunes_create: no device arena (%s); solve will return "
+                        "TREEQP_UNKNOWN_ERROR\n", tqb_cuda_last_error());
+    }
+    else
+    {   /* dual start defaults to zero until set_dual_initialization is called */
+        memset(ctx->forest->hin.lam0, 0, sizeof(double) * (size_t) ctx->forest->dims.X);
+    }
+    ctx->lam_dirty = 1;
+    work->stage_qp_data[0] = ctx;
+}
+
+static tqb_ctx *ctx_of(const treeqp_tdunes_workspace *work)
+{
+    if (!work || !work->stage_qp_data) return NULL;
+    tqb_ctx *ctx = (tqb_ctx *) work->stage_qp_data[0];
+    if (!ctx || ctx->magic != TQB_MAGIC) return NULL;
+    return ctx;
+}
+
+void treeqp_tdunes_destroy(treeqp_tdunes_workspace *work)
+{
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx) return;
+    tqb_forest_destroy(ctx->forest);
+    ctx->magic = 0;
+    free(ctx);
+    work->stage_qp_data[0] = NULL;
+}
+
+void treeqp_tdunes_set_dual_initialization(const double *lambda, treeqp_tdunes_workspace *work)
+{
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest) return;
+    tqb_forest_set_lambda0(ctx->forest, 0, lambda);
+    ctx->lam_dirty = 1;
+}
+
+void treeqp_tdunes_get_stats(const treeqp_tdunes_workspace *work, treeqp_b200_stats *s)
+{
+    memset(s, 0, sizeof *s);
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest) return;
+    const tqb_forest *f = ctx->forest;
+    s->iter = f->iter_max;
+    s->ls_total = f->ls_total;
+    memcpy(s->ls_iters, f->ls_iters, sizeof s->ls_iters);
+    s->n_reg = f->n_reg;
+    s->gpu_ms = f->gpu_ms; s->h2d_ms = f->h2d_ms; s->d2h_ms = f->d2h_ms; s->pack_ms = f->pack_ms;
+    s->h2d_bytes = f->h2d_bytes; s->d2h_bytes = f->d2h_bytes;
+    s->kernel_launches = f->launches;
+}
+
+/* ------------------------------------------------------------------------------- solve ---- */
+
+static return_t forest_upload(tqb_forest *f)
+{
+    if (tqb_device_upload(f->dev, f->h_in, f->dims.n_in, &f->h2d_ms)) return TREEQP_UNKNOWN_ERROR;
+    f->h2d_bytes = (long long) sizeof(double) * f->dims.n_in;
+    return TREEQP_OK;
+}
+
+static return_t forest_solve(tqb_forest *f, const tqb_opts *o)
+{
+    if (tqb_device_solve(f->dev, o, f->h_status, f->h_iter, f->ls_iters, &f->ls_total, &f->n_reg,
+                         &f->gpu_ms, &f->launches))
+        return TREEQP_UNKNOWN_ERROR;
+    int it = 0;
+    for (int t = 0; t < f->dims.nT; t++)
+        if (f->h_iter[t] > it) it = f->h_iter[t];
+    f->iter_max = it;
+    return TREEQP_OK;
+}
+
+static return_t forest_download(tqb_forest *f)
+{
+    if (tqb_device_download(f->dev, f->h_out, &f->d2h_ms)) return TREEQP_UNKNOWN_ERROR;
+    f->d2h_bytes = (long long) sizeof(double) * (3LL * f->dims.X + 2LL * f->dims.U);
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_upload(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts,
+                              treeqp_tdunes_workspace *work)
+{
+    (void) opts;
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest) return TREEQP_UNKNOWN_ERROR;
+    double t0 = tqb_wall_ms();
+    tqb_forest_pack(ctx->forest, 0, qp_in);
+    ctx->forest->pack_ms = tqb_wall_ms() - t0;
+    if (forest_upload(ctx->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    ctx->uploaded = 1;
+    ctx->lam_dirty = 0;
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_solve_resident(const treeqp_tdunes_opts_t *opts, treeqp_tdunes_workspace *work)
+{
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest || !ctx->uploaded) return TREEQP_UNKNOWN_ERROR;
+    return_t st = validate_opts(opts);
+    if (st != TREEQP_OK) return st;
+    tqb_forest *f = ctx->forest;
+    if (ctx->lam_dirty)
+    {   /* lambda0 is the tail of the input block: re-send the block (rare on this path) */
+        if (forest_upload(f) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+        ctx->lam_dirty = 0;
+    }
+    tqb_opts o;
+    forward_opts(opts, &o);
+    work->lineSearchRestartCounter = 0;
+    if (forest_solve(f, &o) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    ctx->last_status = (return_t) f->h_status[0];
+    int it = f->h_iter[0];
+    work->lsIter = (it > 0 && it <= 256) ? f->ls_iters[it - 1] : 0;
+    return ctx->last_status;
+}
+
+return_t treeqp_tdunes_download(tree_qp_out *qp_out, treeqp_tdunes_workspace *work)
+{
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest) return TREEQP_UNKNOWN_ERROR;
+    tqb_forest *f = ctx->forest;
+    if (forest_download(f) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    double t0 = tqb_wall_ms();
+    tqb_forest_unpack(f, 0, qp_out);
+    f->pack_ms += tqb_wall_ms() - t0;
+    qp_out->info.iter = f->h_iter[0];
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
+                             const treeqp_tdunes_opts_t *opts, treeqp_tdunes_workspace *work)
+{
+    const double t_total = tqb_wall_ms();
+    return_t st = validate_opts(opts);
+    if (st != TREEQP_OK) return st;
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest)
+    {
+        fprintf(stderr, "[treeqp_b200] treeqp_tdunes_solve: workspace has no device arena (no GPU?)\n");
+        return TREEQP_UNKNOWN_ERROR;
+    }
+    /* "interface" part 1: BLASFEO views -> pinned SoA -> HBM */
+    st = treeqp_tdunes_upload(qp_in, opts, work);
+    if (st != TREEQP_OK) return st;
+    const double t_solver = tqb_wall_ms();
+    qp_out->info.interface_time = 1e-3 * (t_solver - t_total);
+
+    st = treeqp_tdunes_solve_resident(opts, work);
+    const double t_after = tqb_wall_ms();
+    if (st == TREEQP_UNKNOWN_ERROR) return st;
+    /* the reference returns early, leaving qp_out untouched, when the line search reports a
+     * non-descent direction (dual_Newton_tree.c:1214-1215) */
+    if (st == TREEQP_DN_NOT_DESCENT_DIRECTION) return st;
+    qp_out->info.solver_time = 1e-3 * (t_after - t_solver);
+
+    if (treeqp_tdunes_download(qp_out, work) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    const double t_end = tqb_wall_ms();
+    qp_out->info.interface_time += 1e-3 * (t_end - t_after);
+    qp_out->info.total_time = 1e-3 * (t_end - t_total);
+    return st;
+}
+
+/* ------------------------------------------------------------------------------- batch ---- */
+
+treeqp_tdunes_batch *treeqp_tdunes_batch_create(int n, const tree_qp_in *const *qp_in,
+                                                const treeqp_tdunes_opts_t *opts)
+{
+    if (n <= 0) return NULL;
+    for (int i = 0; i < n; i++) check_stage_solvers(qp_in[i], opts);
+    treeqp_tdunes_batch *b = (treeqp_tdunes_batch *) calloc(1, sizeof *b);
+    b->n = n;
+    b->forest = tqb_forest_create(n, qp_in);
+    if (!b->forest) { free(b); return NULL; }
+    memset(b->forest->hin.lam0, 0, sizeof(double) * (size_t) b->forest->dims.X);
+    b->opts_ok = validate_opts(opts) == TREEQP_OK;
+    forward_opts(opts, &b->o);
+    return b;
+}
+
+void treeqp_tdunes_batch_set_dual_initialization(treeqp_tdunes_batch *b, int i, const double *lambda)
+{
+    if (b && i >= 0 && i < b->n) tqb_forest_set_lambda0(b->forest, i, lambda);
+}
+
+return_t treeqp_tdunes_batch_upload(treeqp_tdunes_batch *b, const tree_qp_in *const *qp_in)
+{
+    double t0 = tqb_wall_ms();
+    for (int i = 0; i < b->n; i++) tqb_forest_pack(b->forest, i, qp_in[i]);
+    b->forest->pack_ms = tqb_wall_ms() - t0;
+    if (forest_upload(b->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    b->uploaded = 1;
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_batch_solve_resident(treeqp_tdunes_batch *b, return_t *status)
+{
+    if (!b->opts_ok) return TREEQP_INVALID_OPTION;
+    if (!b->uploaded) return TREEQP_UNKNOWN_ERROR;
+    if (forest_solve(b->forest, &b->o) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    if (status)
+        for (int i = 0; i < b->n; i++) status[i] = (return_t) b->forest->h_status[i];
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_batch_download(treeqp_tdunes_batch *b, tree_qp_out *const *qp_out)
+{
+    if (forest_download(b->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    double t0 = tqb_wall_ms();
+    for (int i = 0; i < b->n; i++)
+    {
+        if (b->forest->h_status[i] == TREEQP_DN_NOT_DESCENT_DIRECTION) continue; /* untouched */
+        tqb_forest_unpack(b->forest, i, qp_out[i]);
+        qp_out[i]->info.iter = b->forest->h_iter[i];
+    }
+    b->forest->pack_ms += tqb_wall_ms() - t0;
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_solve_batch(treeqp_tdunes_batch *b, const tree_qp_in *const *qp_in,
+                                   tree_qp_out *const *qp_out, return_t *status)
+{
+    return_t st = treeqp_tdunes_batch_upload(b, qp_in);
+    if (st != TREEQP_OK) return st;
+    st = treeqp_tdunes_batch_solve_resident(b, status);
+    if (st != TREEQP_OK) return st;
+    return treeqp_tdunes_batch_download(b, qp_out);
+}
+
+void treeqp_tdunes_batch_get_stats(const treeqp_tdunes_batch *b, treeqp_b200_stats *s)
+{
+    memset(s, 0, sizeof *s);
+    const tqb_forest *f = b->forest;
+    s->iter = f->iter_max;
+    s->ls_total = f->ls_total;
+    memcpy(s->ls_iters, f->ls_iters, sizeof s->ls_iters);
+    s->n_reg = f->n_reg;
+    s->gpu_ms = f->gpu_ms; s->h2d_ms = f->h2d_ms; s->d2h_ms = f->d2h_ms; s->pack_ms = f->pack_ms;
+    s->h2d_bytes = f->h2d_bytes; s->d2h_bytes = f->d2h_bytes;
+    s->kernel_launches = f->launches;
+}
+
+void treeqp_tdunes_batch_destroy(treeqp_tdunes_batch *b)
+{
+    if (!b) return;
+    tqb_forest_destroy(b->forest);
+    free(b);
+}
