@@ -43,7 +43,7 @@ def test_reference_golden_iteration_counts():
 
 
 @pytest.mark.parametrize("opts", [dict(regType=1), dict(termCondition=0, stationarityTolerance=1e-14),
-                                  dict(termCondition=1), dict(lineSearchBeta=0.3, lineSearchGamma=0.3)])
+                                  dict(termCondition=1), dict(lineSearchBeta=0.5, lineSearchGamma=0.2), dict(lineSearchBeta=0.8, lineSearchGamma=0.05)])
 def test_port_options_vs_live_reference(opts, ref_lib):
     prob, _ = CS.get_case("spring_mass_tight")
     r = capi.solve_tdunes(ref_lib, prob, **opts)

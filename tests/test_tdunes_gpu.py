@@ -46,7 +46,7 @@ def test_line_search_counts_match_oracle(name, product_lib):
 
 
 @pytest.mark.parametrize("opts", [dict(regType=1), dict(termCondition=0, stationarityTolerance=1e-14),
-                                  dict(termCondition=1), dict(lineSearchBeta=0.3, lineSearchGamma=0.3),
+                                  dict(termCondition=1), dict(lineSearchBeta=0.5, lineSearchGamma=0.2), dict(lineSearchBeta=0.8, lineSearchGamma=0.05),
                                   dict(maxIter=7), dict(lineSearchMaxIter=3, maxIter=20)])
 def test_options_match_oracle(opts, product_lib):
     prob, _ = CS.get_case("spring_mass_tight")
