@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native TDUNES hot path.
+
+Metric (BASELINE.json): tree-QP solves/sec (and us per dual Newton iteration) on the 10^5-node
+random tree (config 3: full binary tree of depth 16 = 131071 nodes, nx=12, nu=4, clipping stage
+QPs, FP64).  One "step" = one complete dual Newton solve of that QP from the dual start lambda=0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--depth D]
+
+  value  whole-job throughput with the QP data already resident in HBM (treeqp_tdunes_solve_resident)
+  e2e    same metric through the drop-in C-ABI call treeqp_tdunes_solve with HOST buffers
+         (BLASFEO views -> pinned SoA -> H2D -> Newton loop -> D2H -> BLASFEO views), every step
+  roofline      dominant kernel class: algorithmic bytes (SURVEY.md 8d formulas) / CUDA-event time
+  cpu_baseline  the unmodified reference (oracle/_ref, OpenMP build, all host cores) on the same QP
+
+N>1: one process per GPU (torchrun), each rank solves its own tree of the same shape (seed = rank):
+the path partitions by independent QP, no data-path collective -> weak scaling.
+--impl reference: times the reference's own CPU implementation (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from treeqp_b200 import capi, problems as P  # noqa: E402
+
+METRIC = "tree_qp_solves_per_sec"
+UNIT = "solves/s"
+
+
+def workload(depth, seed):
+    return P.random_tree(P.binary_tree_nk(depth), 12, 4, seed=seed, ubound=0.2)
+
+
+OPTS = dict(maxIter=200)
+
+
+# ------------------------------------------------------------------ algorithmic bytes
+def algorithmic_bytes(prob):
+    """bytes each kernel class must move per call, from the problem dimensions only"""
+    nx, nu, nk = prob.nx.astype(np.int64), prob.nu.astype(np.int64), prob.nk.astype(np.int64)
+    dad = prob.dad
+    Nn = prob.Nn
+    ab = np.zeros(Nn, dtype=np.int64)
+    ab[1:] = nx[1:] * (nx[dad[1:]] + nu[dad[1:]])
+    kid_ab = np.bincount(dad[1:], weights=ab[1:], minlength=Nn).astype(np.int64)
+    d = np.bincount(dad[1:], weights=nx[1:], minlength=Nn).astype(np.int64)
+    par = nk > 0
+    nonroot_par = par.copy(); nonroot_par[0] = False
+    k1 = 8 * int(((5 * nx + 4 * nu) + kid_ab + d + 4 * nx + 4 * nu).sum())
+    k5 = 8 * int(((6 * nx + 5 * nu) + kid_ab + 2 * d + nx + nu).sum())
+    grad = 8 * int((ab[1:] + 4 * nx[1:] + nx[dad[1:]] + nu[dad[1:]]).sum())
+    hess = 8 * int((kid_ab + nx + nu + d + d * (d + 1) // 2)[par].sum() + (nx * d)[nonroot_par].sum())
+    k3 = 8 * int((d * (d + 1) + 2 * d)[par].sum() + (2 * nx * d + nx * (nx + 1) + 2 * nx)[nonroot_par].sum())
+    k4 = 8 * int((d * (d + 1) // 2 + 2 * d)[par].sum() + (nx * d + nx)[nonroot_par].sum())
+    return {"k_stage<0>": k1, "k_stage<1>": k5, "k_gradient": grad, "k_hessian": hess,
+            "k_factor_level": k3, "k_backsolve_level": k4}
+
+
+def launches_per_call(prob):
+    """how many launches make up ONE call of each phase (level kernels: one per depth)"""
+    stage = P.tree_tables(prob.nk)[1]
+    Nh = int(stage.max())
+    return {"k_stage<0>": 1, "k_stage<1>": 1, "k_gradient": 1, "k_hessian": 1,
+            "k_factor_level": Nh, "k_backsolve_level": max(Nh - 1, 1)}
+
+
+# ------------------------------------------------------------------------------ clock sampling
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+             "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------ reference arm
+def ref_lib_path(omp=True):
+    p = os.path.join(ROOT, "oracle", "_ref", "libtreeqp_ref_omp.so" if omp else "libtreeqp_ref.so")
+    return p if os.path.exists(p) else None
+
+
+def run_reference_solve(prob, max_iter=None):
+    """one treeqp_tdunes_solve of the UNMODIFIED reference (OpenMP build, all host cores)"""
+    path = ref_lib_path(True)
+    lib = capi.TreeQpLib(path)
+    qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+    opts = dict(OPTS)
+    if max_iter is not None:
+        opts["maxIter"] = max_iter
+    solver = capi.Tdunes(lib, qp_in, **opts)
+    lam0 = np.zeros(prob.n_lambda)
+
+    def once():
+        solver.set_dual_initialization(lam0)
+        t = time.perf_counter()
+        st = solver.solve(qp_out)
+        return time.perf_counter() - t, st, qp_out.iter
+    return once
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic"}
+    if ref_lib_path(True) is None:
+        print(json.dumps(dict(base, unavailable="oracle/_ref/libtreeqp_ref_omp.so missing (built from /root/reference)")))
+        return
+    prob = workload(args.depth, 0)
+    once = run_reference_solve(prob)
+    t_full, st, iters_full = once()  # untimed probe = first warm-up step, full solve
+    budget = 240.0
+    total_steps = args.steps + max(args.warmup - 1, 0)
+    if t_full * total_steps <= budget:
+        sample, scale, fn = "full solve (%d Newton iterations) per step" % iters_full, 1.0, once
+    else:
+        n = max(1, int(iters_full * budget / (t_full * total_steps)))
+        fn = run_reference_solve(prob, max_iter=n)
+        scale = iters_full / float(n)
+        sample = "first %d of %d Newton iterations of the same QP per step, time scaled by %d/%d" % (n, iters_full, iters_full, n)
+    for _ in range(max(args.warmup - 1, 0)):
+        fn()
+    times = []
+    for _ in range(args.steps):
+        t, _, _ = fn()
+        times.append(t * scale)
+    sec = float(np.sum(times)) / args.steps
+    value = 1.0 / sec
+    print(json.dumps(dict(
+        base, value=value, ms_per_step=1e3 * sec, us_per_newton_iter=1e6 * sec / iters_full,
+        config={"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, 1 tree" % (args.depth, prob.Nn),
+                "newton_iters": iters_full, "status": st},
+        cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        gpu_launches=0)))
+
+
+# ------------------------------------------------------------------------------------- own arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--depth", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+
+    lib = capi.TreeQpLib(capi.PRODUCT_LIB)
+    assert lib.lib.treeqp_b200_set_device(local) == 0
+    prob = workload(args.depth, rank)
+    qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+    solver = capi.Tdunes(lib, qp_in, **OPTS)
+    lam0 = np.zeros(prob.n_lambda)
+    solver.set_dual_initialization(lam0)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- resident (inputs already in HBM): value
+    assert solver.upload() == capi.TREEQP_OK
+    for _ in range(args.warmup):
+        st = solver.solve_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        st = solver.solve_resident()
+        dev_ms += solver.stats()["gpu_ms"]
+    barrier()
+    t_res = max_over_ranks(time.perf_counter() - t0)
+    stats = solver.stats()
+    assert st == 0, "benchmark QP did not converge: status %d" % st
+    iters = stats["iter"]
+    launches = stats["kernel_launches"] * args.steps
+
+    # ---- end to end through the drop-in call with host buffers
+    for _ in range(min(args.warmup, 1)):
+        solver.set_dual_initialization(lam0)
+        solver.solve(qp_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver.set_dual_initialization(lam0)
+        st2 = solver.solve(qp_out)
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_stats = solver.stats()
+    clk = clocks.stop() if rank == 0 else None
+    assert st2 == 0 and qp_out.iter == iters
+    kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
+
+    # ---- roofline of the dominant kernel class: one profiled solve (CUDA events per launch)
+    lib.lib.treeqp_b200_set_profiling(1)
+    solver.solve_resident()
+    prof = solver.stats()
+    lib.lib.treeqp_b200_set_profiling(0)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks, peak_src = float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    alg = algorithmic_bytes(prob)
+    lpc = launches_per_call(prob)
+    kern = prof["kernels"]
+    top = max((k for k in kern if k in alg), key=lambda k: kern[k][0])
+    t_ms, n_launch = kern[top]
+    calls = n_launch / lpc[top]
+    achieved = alg[top] * calls / (t_ms * 1e-3) / 1e9
+    breakdown = {k: {"ms": round(v[0], 4), "launches": v[1],
+                     "GBps": round(alg[k] * (v[1] / lpc[k]) / (v[0] * 1e-3) / 1e9, 1) if k in alg else None}
+                 for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks, "unit": "GB/s",
+                "frac": achieved / peaks, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_call": alg[top], "launches_per_call": lpc[top],
+                "avg_launch_us": 1e3 * t_ms / n_launch, "kernel_share_of_solve": t_ms / prof["gpu_ms"],
+                "per_kernel": breakdown}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and args.gpus == 1 and ref_lib_path(True):
+        cores = os.cpu_count() or 1
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        once = run_reference_solve(prob)
+        t_cpu, st_cpu, it_cpu = once()
+        cpu_baseline = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cores, "kind": "reference",
+                        "sample": "1 full solve of the same QP (%d Newton iterations, status %d), OpenMP build of the unmodified reference" % (it_cpu, st_cpu),
+                        "us_per_newton_iter": 1e6 * t_cpu / max(it_cpu, 1), "newton_iters": it_cpu}
+    elif not args.no_cpu_baseline and args.gpus == 1:
+        cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+
+    n = world
+    out = {
+        "metric": METRIC, "value": n * args.steps / t_res, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, 1 tree per GPU" % (args.depth, prob.Nn),
+                   "newton_iters": iters, "ls_trials": stats["ls_total"], "kkt": kkt,
+                   "l2": "inputs %.2f GB + iterates/Hessian blocks, all >> 126 MB L2: no flush between steps" % (stats["h2d_bytes"] / 1e9),
+                   "parallelism": "1 QP per GPU, no collective"},
+        "us_per_newton_iter": 1e3 * (1e3 * t_res / args.steps) / max(iters, 1),
+        "device_ms_per_step": dev_ms / args.steps,
+        "e2e": {"value": n * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": e2e_stats["h2d_bytes"],
+                "d2h_bytes_per_step": e2e_stats["d2h_bytes"], "ms_per_step": 1e3 * t_e2e / args.steps,
+                "pack_ms": e2e_stats["pack_ms"], "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"],
+                "gpu_ms": e2e_stats["gpu_ms"]},
+        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

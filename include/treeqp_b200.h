@@ -382,6 +382,10 @@ typedef struct treeqp_b200_stats_
     double pack_ms;        /* host time spent packing/unpacking BLASFEO views */
     long long h2d_bytes, d2h_bytes;
     long long kernel_launches; /* kernels launched by the last solve */
+    /* per kernel class (see treeqp_b200_kernel_class_name), filled when profiling is on:
+     * device time from CUDA events recorded on the solver's stream around every launch */
+    double kernel_ms[16];
+    int kernel_count[16];
 } treeqp_b200_stats;
 void treeqp_tdunes_get_stats(const treeqp_tdunes_workspace *work, treeqp_b200_stats *stats);
 
@@ -415,6 +419,12 @@ return_t treeqp_tdunes_solve_batch(treeqp_tdunes_batch *batch, const tree_qp_in 
                                    tree_qp_out *const *qp_out, return_t *status);
 void treeqp_tdunes_batch_get_stats(const treeqp_tdunes_batch *batch, treeqp_b200_stats *stats);
 void treeqp_tdunes_batch_destroy(treeqp_tdunes_batch *batch);
+
+/* per-launch CUDA-event timing of every kernel class (adds two event records per launch);
+ * off by default, also switched on by the environment variable TREEQP_B200_PROFILE=1 */
+void treeqp_b200_set_profiling(int on);
+int treeqp_b200_num_kernel_classes(void);
+const char *treeqp_b200_kernel_class_name(int k);
 
 /* library / device introspection */
 const char *treeqp_b200_version(void);

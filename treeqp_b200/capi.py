@@ -78,7 +78,8 @@ class Stats(C.Structure):
     _fields_ = [("iter", C.c_int), ("ls_total", C.c_int), ("ls_iters", C.c_int * 256),
                 ("n_reg", C.c_int), ("gpu_ms", C.c_double), ("h2d_ms", C.c_double),
                 ("d2h_ms", C.c_double), ("pack_ms", C.c_double), ("h2d_bytes", C.c_longlong),
-                ("d2h_bytes", C.c_longlong), ("kernel_launches", C.c_longlong)]
+                ("d2h_bytes", C.c_longlong), ("kernel_launches", C.c_longlong),
+                ("kernel_ms", C.c_double * 16), ("kernel_count", C.c_int * 16)]
 
 
 _DVEC_DT = np.dtype([("m", "<i4"), ("pm", "<i4"), ("pa", "<u8"), ("memsize", "<i4"), ("_pad", "<i4")])
@@ -196,6 +197,13 @@ class TreeQpLib:
         if self.is_product:
             L.treeqp_b200_version.restype = C.c_char_p
             L.treeqp_b200_device_count.restype = C.c_int
+            L.treeqp_b200_set_device.argtypes = [C.c_int]
+            L.treeqp_b200_set_device.restype = C.c_int
+            L.treeqp_b200_set_profiling.argtypes = [C.c_int]
+            L.treeqp_b200_set_profiling.restype = None
+            L.treeqp_b200_num_kernel_classes.restype = C.c_int
+            L.treeqp_b200_kernel_class_name.argtypes = [C.c_int]
+            L.treeqp_b200_kernel_class_name.restype = C.c_char_p
             L.treeqp_tdunes_destroy.argtypes = [vp]
             L.treeqp_tdunes_destroy.restype = None
             L.treeqp_tdunes_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -229,6 +237,17 @@ class TreeQpLib:
         nk = np.zeros(Nn, dtype=np.int32)
         self.lib.setup_multistage_tree(md, Nr, Nh, _ip(nk))
         return nk
+
+
+def stats_dict(lib: "TreeQpLib", st: Stats) -> dict:
+    n = min(st.iter, 256)
+    nk = lib.lib.treeqp_b200_num_kernel_classes()
+    kernels = {lib.lib.treeqp_b200_kernel_class_name(k).decode(): (st.kernel_ms[k], st.kernel_count[k])
+               for k in range(nk) if st.kernel_count[k] > 0}
+    return dict(iter=st.iter, ls_total=st.ls_total, ls_iters=[st.ls_iters[i] for i in range(n)],
+                n_reg=st.n_reg, gpu_ms=st.gpu_ms, h2d_ms=st.h2d_ms, d2h_ms=st.d2h_ms,
+                pack_ms=st.pack_ms, h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes,
+                kernel_launches=st.kernel_launches, kernels=kernels)
 
 
 class _Buf:
@@ -388,11 +407,7 @@ class Tdunes:
     def stats(self) -> dict:
         st = Stats()
         self.lib.lib.treeqp_tdunes_get_stats(self.work.ptr, C.byref(st))
-        n = min(st.iter, 256)
-        return dict(iter=st.iter, ls_total=st.ls_total, ls_iters=[st.ls_iters[i] for i in range(n)],
-                    n_reg=st.n_reg, gpu_ms=st.gpu_ms, h2d_ms=st.h2d_ms, d2h_ms=st.d2h_ms,
-                    pack_ms=st.pack_ms, h2d_bytes=st.h2d_bytes, d2h_bytes=st.d2h_bytes,
-                    kernel_launches=st.kernel_launches)
+        return stats_dict(self.lib, st)
 
     def destroy(self):
         if self._alive and self.lib.is_product:

@@ -26,8 +26,31 @@ static thread_local char g_err[512] = "";
         }                                                                                        \
     } while (0)
 
+enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DOT, K_EVAL, K_STEP, K_FINISH, K_NCLASS };
+static const char *const k_names[K_NCLASS] = {"k_init", "k_stage<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
+                                              "k_hessian", "k_factor_level", "k_backsolve_level", "k_dot",
+                                              "k_stage<1>", "k_lambda_step", "k_finish"};
+static int g_profile = -1;
+#define TQB_MAX_EVENTS 65536
+
+extern "C" void tqb_set_profiling(int on) { g_profile = on ? 1 : 0; }
+extern "C" int tqb_num_kernel_classes(void) { return K_NCLASS; }
+extern "C" const char *tqb_kernel_class_name(int k) { return (k >= 0 && k < K_NCLASS) ? k_names[k] : ""; }
+static int profiling_on(void)
+{
+    if (g_profile < 0)
+    {
+        const char *e = getenv("TREEQP_B200_PROFILE");
+        g_profile = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_profile;
+}
+
 struct tqb_device
 {
+    cudaEvent_t *pev; /* profiling event pool (pairs) */
+    unsigned char *pev_class;
+    int pev_n, pev_on;
     tqb_dims dims;
     int *d_int;
     double *d_in, *d_work;
@@ -177,6 +200,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
+    if (D->pev) { for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) cudaEventDestroy(D->pev[i]); free(D->pev); free(D->pev_class); }
     if (D->stream) cudaStreamDestroy(D->stream);
     free(D->lvl_ptr);
     free(D);
@@ -206,10 +230,13 @@ extern "C" int tqb_device_download(tqb_device *D, double *h_out, double *ms)
     return 0;
 }
 
-#define LAUNCH(kern, grid, block, smem, ...)                          \
-    do {                                                              \
-        kern<<<(grid), (block), (smem), D->stream>>>(__VA_ARGS__);    \
-        D->launches++;                                                \
+#define LAUNCH(cls, kern, grid, block, smem, ...)                                          \
+    do {                                                                                   \
+        const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;        \
+        if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = (cls); } \
+        kern<<<(grid), (block), (smem), D->stream>>>(__VA_ARGS__);                         \
+        if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);                     \
+        D->launches++;                                                                     \
     } while (0)
 
 static inline int cdiv(long long a, int b) { return (int) ((a + b - 1) / b); }
@@ -225,14 +252,22 @@ static int read_counters(tqb_device *D)
 static void launch_eval(tqb_device *D)
 {
     const View &v = D->v;
-    LAUNCH(k_stage<1>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
-    LAUNCH(k_chunk_reduce, v.nchunk, 256, 0, v, v.nvb, v.cvb, 0);
+    LAUNCH(K_EVAL, k_stage<1>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
+    LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nvb, v.cvb, 0);
 }
 
 extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status, int *h_iter,
                                 int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms,
-                                long long *launches)
+                                long long *launches, double *kernel_ms16, int *kernel_count16)
 {
+    D->pev_on = profiling_on();
+    D->pev_n = 0;
+    if (D->pev_on && !D->pev)
+    {
+        D->pev = (cudaEvent_t *) calloc(2 * TQB_MAX_EVENTS, sizeof(cudaEvent_t));
+        D->pev_class = (unsigned char *) calloc(TQB_MAX_EVENTS, 1);
+        for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) CK(cudaEventCreate(&D->pev[i]));
+    }
     View &v = D->v;
     v.o = *o;
     const tqb_dims *d = &D->dims;
@@ -244,49 +279,49 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     {
         int n = v.X > nT ? v.X : nT;
         if (n < 256) n = 256;
-        LAUNCH(k_init, cdiv(n, 256), 256, 0, v);
+        LAUNCH(K_INIT, k_init, cdiv(n, 256), 256, 0, v);
     }
     for (int it = 0; it < o->maxIter; it++)
     {
         CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
-        LAUNCH(k_stage<0>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
-        LAUNCH(k_gradient, cdiv(v.Nn, 8), 256, 0, v);
-        LAUNCH(k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
-        LAUNCH(k_decide_term, tgrid, 128, 0, v);
+        LAUNCH(K_STAGE, k_stage<0>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
+        LAUNCH(K_GRAD, k_gradient, cdiv(v.Nn, 8), 256, 0, v);
+        LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
+        LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
         if (read_counters(D)) return 1;
         if (D->h_counters[0] == 0) break;
 
-        LAUNCH(k_hessian, cdiv(v.Nn, D->wpb_hess), 32 * D->wpb_hess, D->sm_hess, v);
+        LAUNCH(K_HESS, k_hessian, cdiv(v.Nn, D->wpb_hess), 32 * D->wpb_hess, D->sm_hess, v);
         for (int l = Nh - 1; l >= 0; l--)
         {
             const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
             if (cnt > 0)
-                LAUNCH(k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[l], cnt, D->pw_fact);
+                LAUNCH(K_FACTOR, k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[l], cnt, D->pw_fact);
         }
         for (int l = 1; l < Nh; l++)
         {
             const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
             if (cnt > 0)
-                LAUNCH(k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back);
+                LAUNCH(K_BACK, k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back);
         }
-        LAUNCH(k_dot, cdiv(v.Nn, 256), 256, 0, v);
-        LAUNCH(k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, 0);
+        LAUNCH(K_DOT, k_dot, cdiv(v.Nn, 256), 256, 0, v);
+        LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, 0);
         launch_eval(D);
-        LAUNCH(k_decide_ls_init, tgrid, 128, 0, v);
+        LAUNCH(K_DECIDE, k_decide_ls_init, tgrid, 128, 0, v);
         for (int ls = 0; ls <= o->lsMaxIter; ls++)
         {
             CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
-            LAUNCH(k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
+            LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
             launch_eval(D);
-            LAUNCH(k_decide_ls_trial, tgrid, 128, 0, v);
+            LAUNCH(K_DECIDE, k_decide_ls_trial, tgrid, 128, 0, v);
             if (read_counters(D)) return 1;
             if (D->h_counters[1] == 0) break;
         }
     }
-    LAUNCH(k_finalize_status, cdiv(nT, 256), 256, 0, v);
+    LAUNCH(K_DECIDE, k_finalize_status, cdiv(nT, 256), 256, 0, v);
     {
         int n = v.X > v.U ? v.X : v.U;
-        LAUNCH(k_finish, cdiv(n > 0 ? n : 1, 256), 256, 0, v);
+        LAUNCH(K_FINISH, k_finish, cdiv(n > 0 ? n : 1, 256), 256, 0, v);
     }
     CK(cudaEventRecord(D->ev1, D->stream));
     CK(cudaMemcpyAsync(h_status, v.status, sizeof(int) * (size_t) (2 * nT), cudaMemcpyDeviceToHost, D->stream));
@@ -302,5 +337,16 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     if (ls_total) *ls_total = D->h_counters[3];
     if (n_reg) *n_reg = D->h_counters[2];
     if (launches) *launches = D->launches;
+    if (kernel_ms16 && kernel_count16)
+    {
+        for (int k = 0; k < 16; k++) { kernel_ms16[k] = 0.0; kernel_count16[k] = 0; }
+        for (int i = 0; i < D->pev_n; i++)
+        {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, D->pev[2 * i], D->pev[2 * i + 1]));
+            kernel_ms16[D->pev_class[i]] += t;
+            kernel_count16[D->pev_class[i]]++;
+        }
+    }
     return 0;
 }

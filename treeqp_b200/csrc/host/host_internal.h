@@ -90,6 +90,8 @@ typedef struct tqb_forest
     int iter_max, ls_total, n_reg;
     double gpu_ms, h2d_ms, d2h_ms, pack_ms;
     long long h2d_bytes, d2h_bytes, launches;
+    double kernel_ms[16];
+    int kernel_count[16];
 } tqb_forest;
 
 /* ---- forest.c ---- */
@@ -119,7 +121,11 @@ void tqb_device_destroy(tqb_device *d);
 int tqb_device_upload(tqb_device *d, const double *h_in, long long n_in, double *ms);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
 int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,
-                     int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms, long long *launches);
+                     int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms, long long *launches,
+                     double *kernel_ms16, int *kernel_count16);
+void tqb_set_profiling(int on);
+int tqb_num_kernel_classes(void);
+const char *tqb_kernel_class_name(int k);
 /* async D2H of x,u,lam,mu_x,mu_u into h_out */
 int tqb_device_download(tqb_device *d, double *h_out, double *ms);
 const char *tqb_cuda_last_error(void);

@@ -39,6 +39,9 @@ struct treeqp_tdunes_batch_
 const char *treeqp_b200_version(void) { return "treeqp_b200 0.1 (sm_100a)"; }
 int treeqp_b200_device_count(void) { return tqb_cuda_device_count(); }
 int treeqp_b200_set_device(int device) { return tqb_cuda_set_device(device); }
+void treeqp_b200_set_profiling(int on) { tqb_set_profiling(on); }
+int treeqp_b200_num_kernel_classes(void) { return tqb_num_kernel_classes(); }
+const char *treeqp_b200_kernel_class_name(int k) { return tqb_kernel_class_name(k); }
 
 /* ----------------------------------------------------------------------------- options ---- */
 
@@ -233,6 +236,8 @@ void treeqp_tdunes_get_stats(const treeqp_tdunes_workspace *work, treeqp_b200_st
     s->gpu_ms = f->gpu_ms; s->h2d_ms = f->h2d_ms; s->d2h_ms = f->d2h_ms; s->pack_ms = f->pack_ms;
     s->h2d_bytes = f->h2d_bytes; s->d2h_bytes = f->d2h_bytes;
     s->kernel_launches = f->launches;
+    memcpy(s->kernel_ms, f->kernel_ms, sizeof s->kernel_ms);
+    memcpy(s->kernel_count, f->kernel_count, sizeof s->kernel_count);
 }
 
 /* ------------------------------------------------------------------------------- solve ---- */
@@ -247,7 +252,7 @@ static return_t forest_upload(tqb_forest *f)
 static return_t forest_solve(tqb_forest *f, const tqb_opts *o)
 {
     if (tqb_device_solve(f->dev, o, f->h_status, f->h_iter, f->ls_iters, &f->ls_total, &f->n_reg,
-                         &f->gpu_ms, &f->launches))
+                         &f->gpu_ms, &f->launches, f->kernel_ms, f->kernel_count))
         return TREEQP_UNKNOWN_ERROR;
     int it = 0;
     for (int t = 0; t < f->dims.nT; t++)
@@ -423,6 +428,8 @@ void treeqp_tdunes_batch_get_stats(const treeqp_tdunes_batch *b, treeqp_b200_sta
     s->gpu_ms = f->gpu_ms; s->h2d_ms = f->h2d_ms; s->d2h_ms = f->d2h_ms; s->pack_ms = f->pack_ms;
     s->h2d_bytes = f->h2d_bytes; s->d2h_bytes = f->d2h_bytes;
     s->kernel_launches = f->launches;
+    memcpy(s->kernel_ms, f->kernel_ms, sizeof s->kernel_ms);
+    memcpy(s->kernel_count, f->kernel_count, sizeof s->kernel_count);
 }
 
 void treeqp_tdunes_batch_destroy(treeqp_tdunes_batch *b)
