@@ -55,13 +55,14 @@ def algorithmic_bytes(prob):
     d = np.bincount(dad[1:], weights=nx[1:], minlength=Nn).astype(np.int64)
     par = nk > 0
     nonroot_par = par.copy(); nonroot_par[0] = False
-    k1 = 8 * int(((5 * nx + 4 * nu) + kid_ab + d + 4 * nx + 4 * nu).sum())
-    k5 = 8 * int(((6 * nx + 5 * nu) + kid_ab + 2 * d + nx + nu).sum())
+    k1 = 8 * int(((5 * nx + 4 * nu) + kid_ab + 2 * d + 5 * nx + 5 * nu + 1).sum())   # k_stage<0>
+    k5 = 8 * int((2 * nx + kid_ab + 2 * d + nx + nu + 2).sum())                        # k_stage<2>
+    trial = 8 * int(6 * nx.sum() + 6 * nu.sum() + 2 * Nn)                               # k_trial
     grad = 8 * int((ab[1:] + 4 * nx[1:] + nx[dad[1:]] + nu[dad[1:]]).sum())
     hess = 8 * int((kid_ab + nx + nu + d + d * (d + 1) // 2)[par].sum() + (nx * d)[nonroot_par].sum())
     k3 = 8 * int((d * (d + 1) + 2 * d)[par].sum() + (2 * nx * d + nx * (nx + 1) + 2 * nx)[nonroot_par].sum())
     k4 = 8 * int((d * (d + 1) // 2 + 2 * d)[par].sum() + (nx * d + nx)[nonroot_par].sum())
-    return {"k_stage<0>": k1, "k_stage<1>": k5, "k_gradient": grad, "k_hessian": hess,
+    return {"k_stage<0>": k1, "k_stage<2>": k5, "k_trial": trial, "k_gradient": grad, "k_hessian": hess,
             "k_factor_level": k3, "k_backsolve_level": k4}
 
 
@@ -69,7 +70,7 @@ def launches_per_call(prob):
     """how many launches make up ONE call of each phase (level kernels: one per depth)"""
     stage = P.tree_tables(prob.nk)[1]
     Nh = int(stage.max())
-    return {"k_stage<0>": 1, "k_stage<1>": 1, "k_gradient": 1, "k_hessian": 1,
+    return {"k_stage<0>": 1, "k_stage<2>": 1, "k_trial": 1, "k_gradient": 1, "k_hessian": 1,
             "k_factor_level": Nh, "k_backsolve_level": max(Nh - 1, 1)}
 
 

@@ -23,8 +23,12 @@ def check_against(sol, ref, prob, tol=TOL):
         assert np.array_equal(getattr(sol, k) == hi, ref[k] == hi), "active set (upper) differs: " + k
 
 
+@pytest.mark.parametrize("path", ["fast", "generic"])
 @pytest.mark.parametrize("name", CS.CASE_NAMES)
-def test_solve_matches_reference_golden(name, product_lib):
+def test_solve_matches_reference_golden(name, path, product_lib, monkeypatch):
+    """path=fast: compile-time-dimension fused kernels where the tree is uniform (tdunes_fused.cuh);
+    path=generic: runtime-dimension kernels forced through TREEQP_B200_GENERIC=1 (read at create)"""
+    monkeypatch.setenv("TREEQP_B200_GENERIC", "1" if path == "generic" else "0")
     prob, opts = CS.get_case(name)
     g = CS.golden(name)
     sol = capi.solve_tdunes(product_lib, prob, **opts)
@@ -35,8 +39,10 @@ def test_solve_matches_reference_golden(name, product_lib):
     assert sol.stats["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("path", ["fast", "generic"])
 @pytest.mark.parametrize("name", ["spring_mass_tight", "random_d6_u05", "random_d8_u05", "random_d10_u02"])
-def test_line_search_counts_match_oracle(name, product_lib):
+def test_line_search_counts_match_oracle(name, path, product_lib, monkeypatch):
+    monkeypatch.setenv("TREEQP_B200_GENERIC", "1" if path == "generic" else "0")
     prob, opts = CS.get_case(name)
     s = OP.solve_port(prob, **CS.port_opts(opts))
     sol = capi.solve_tdunes(product_lib, prob, **opts)

@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include "tdunes_kernels.cuh"
+#include "tdunes_fused.cuh"
 
 static thread_local char g_err[512] = "";
 #define CK(call)                                                                                 \
@@ -26,10 +27,10 @@ static thread_local char g_err[512] = "";
         }                                                                                        \
     } while (0)
 
-enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DOT, K_EVAL, K_STEP, K_FINISH, K_NCLASS };
+enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DIR, K_TRIAL, K_STEP, K_FINISH, K_NCLASS };
 static const char *const k_names[K_NCLASS] = {"k_init", "k_stage<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
-                                              "k_hessian", "k_factor_level", "k_backsolve_level", "k_dot",
-                                              "k_stage<1>", "k_lambda_step", "k_finish"};
+                                              "k_hessian", "k_factor_level", "k_backsolve_level", "k_stage<2>",
+                                              "k_trial", "k_lambda_step", "k_finish"};
 static int g_profile = -1;
 #define TQB_MAX_EVENTS 65536
 
@@ -66,6 +67,10 @@ struct tqb_device
     int pw_fact, pw_back;
     long long launches;
     size_t out_doubles;
+    /* fast path (uniform dimensions, see tdunes_fused.cuh) */
+    int fast, f_nx, f_nu, f_pnx;
+    int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
+    double *d_schur;
 };
 
 extern "C" const char *tqb_cuda_last_error(void) { return g_err; }
@@ -104,6 +109,126 @@ static int pick_wpb(size_t per_warp_bytes, size_t limit, int *wpb, size_t *smem)
     return 0;
 }
 
+/* ---- fast-path dispatch: the (NX,NU,MD) combinations compiled in ---------------------------- */
+#define TQB_FUSED_LIST(X) \
+    X(4, 1, 1) X(4, 1, 2) X(4, 1, 3) X(4, 1, 4) \
+    X(6, 4, 1) X(6, 4, 2) X(6, 4, 3) X(6, 4, 4) \
+    X(8, 3, 1) X(8, 3, 2) X(8, 3, 3) X(8, 3, 4) \
+    X(12, 4, 1) X(12, 4, 2)
+
+static bool fused_supported(int nx, int nu, int md)
+{
+#define X(a, b, c) if (nx == a && nu == b && md == c) return true;
+    TQB_FUSED_LIST(X)
+#undef X
+    return false;
+}
+
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+static int launch_bf(tqb_device *D, int begin, int cnt, int kp)
+{
+    using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
+    static bool attr_done = false;
+    const int wpb = 4;
+    const size_t smem = (size_t) wpb * Cfg::SMEM * sizeof(double);
+    if (!attr_done)
+    {
+        CK(cudaFuncSetAttribute(k_build_factor<NX, NU, MD, PNX, ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_done = true;
+    }
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
+    k_build_factor<NX, NU, MD, PNX, ROOT><<<(cnt + wpb - 1) / wpb, 32 * wpb, smem, D->stream>>>(D->v, begin, cnt, kp);
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    return 0;
+}
+
+template <int NX, int MD>
+static int launch_bs(tqb_device *D, int begin, int cnt)
+{
+    const int wpb = 4;
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    k_backsolve_fused<NX, MD><<<(cnt + wpb - 1) / wpb, 32 * wpb, 0, D->stream>>>(D->v, begin, cnt);
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    return 0;
+}
+
+static int fused_factor_level(tqb_device *D, int l)
+{
+    const int begin = D->lvl_ptr[l], cnt = D->lvl_ptr[l + 1] - begin;
+    if (cnt <= 0) return 0;
+    const int nx = D->f_nx, nu = D->f_nu, md = D->lvl_md[l], kp = D->lvl_kp[l];
+    const bool root = (l == 0), pnx0 = root && D->f_pnx == 0;
+#define X(a, b, c)                                                                   \
+    if (nx == a && nu == b && md == c)                                               \
+    {                                                                                \
+        if (!root) return launch_bf<a, b, c, a, false>(D, begin, cnt, kp);           \
+        if (pnx0) return launch_bf<a, b, c, 0, true>(D, begin, cnt, kp);             \
+        return launch_bf<a, b, c, a, true>(D, begin, cnt, kp);                       \
+    }
+    TQB_FUSED_LIST(X)
+#undef X
+    return 1;
+}
+
+static int fused_backsolve_level(tqb_device *D, int l)
+{
+    const int begin = D->lvl_ptr[l], cnt = D->lvl_ptr[l + 1] - begin;
+    if (cnt <= 0) return 0;
+    const int nx = D->f_nx, nu = D->f_nu, md = D->lvl_md[l];
+#define X(a, b, c) if (nx == a && nu == b && md == c) return launch_bs<a, c>(D, begin, cnt);
+    TQB_FUSED_LIST(X)
+#undef X
+    return 1;
+}
+
+/* The fast path needs: every non-root node nx == NX, every root nx in {0, NX} (the same for all
+ * trees), every parent nu == NU, all parents of one depth the same number of kids, kids of one
+ * depth either all parents or all leaves, and the combination compiled in. */
+static int detect_fast_path(tqb_device *D, const int *h_int)
+{
+    const tqb_dims *d = &D->dims;
+    tqb_tables T;
+    tqb_layout_tables(d, const_cast<int *>(h_int), &T);
+    D->fast = 0;
+    const char *env = getenv("TREEQP_B200_GENERIC");
+    if (env && env[0] == '1') return 0;
+    if (d->Np == 0 || d->Nn < 2) return 0;
+    int NX = -1, NU = -1, PNX = -1;
+    D->lvl_md = (int *) calloc((size_t) d->Nh + 1, sizeof(int));
+    D->lvl_kp = (int *) calloc((size_t) d->Nh + 1, sizeof(int));
+    for (int l = 0; l <= d->Nh; l++) D->lvl_kp[l] = -1;
+    for (int g = 0; g < d->Nn; g++)
+    {
+        const bool root = T.dad[g] < 0;
+        if (root) { if (PNX < 0) PNX = T.nx[g]; else if (PNX != T.nx[g]) return 0; }
+        else { if (NX < 0) NX = T.nx[g]; else if (NX != T.nx[g]) return 0; }
+        if (T.nkids[g] > 0)
+        {
+            if (NU < 0) NU = T.nu[g]; else if (NU != T.nu[g]) return 0;
+            const int l = T.depth[g];
+            if (D->lvl_md[l] == 0) D->lvl_md[l] = T.nkids[g]; else if (D->lvl_md[l] != T.nkids[g]) return 0;
+            for (int j = 0; j < T.nkids[g]; j++)
+            {
+                const int kp = T.nkids[T.kid0[g] + j] > 0;
+                if (D->lvl_kp[l] < 0) D->lvl_kp[l] = kp; else if (D->lvl_kp[l] != kp) return 0;
+            }
+        }
+    }
+    if (NX <= 0 || NU < 0 || (PNX != 0 && PNX != NX)) return 0;
+    for (int l = 0; l < d->Nh; l++)
+        if (D->lvl_md[l] > 0 && !fused_supported(NX, NU, D->lvl_md[l])) return 0;
+    D->f_nx = NX; D->f_nu = NU; D->f_pnx = PNX;
+    CK(cudaMalloc(&D->d_schur, sizeof(double) * ((size_t) d->Nn * NX * NX + (size_t) d->X + 4)));
+    D->v.schur = D->d_schur;
+    D->v.rsub = D->d_schur + (size_t) d->Nn * NX * NX;
+    D->fast = 1;
+    return 0;
+}
+
 static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr)
 {
     const tqb_dims *d = &D->dims;
@@ -124,32 +249,35 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr)
     const size_t X = d->X, U = d->U;
     D->out_doubles = 3 * X + 2 * U;
     size_t nwork = D->out_doubles + 8 /* x u lam mux muu */
-                   + 6 * X + 2 * U + 16      /* dlam res resMod xUnc P Linv | uUnc Rt */
+                   + 8 * X + 4 * U + 16      /* dlam res resMod xUnc P Linv qmod0 dq | uUnc Rt rmod0 dr */
                    + (size_t) d->szW + (size_t) d->szUt + 4
-                   + 2 * (size_t) d->Nn + 2 * (size_t) d->nchunk + 4;
+                   + 4 * (size_t) d->Nn + 2 * (size_t) d->nchunk + 4;
     CK(cudaMalloc(&D->d_work, sizeof(double) * nwork));
     double *p = D->d_work;
     v.x = p; p += X; v.u = p; p += U; v.lam = p; p += X; v.mux = p; p += X; v.muu = p; p += U;
     p += ((uintptr_t) p & 8) ? 1 : 0;
     v.dlam = p; p += X; v.res = p; p += X; v.resMod = p; p += X; v.xUnc = p; p += X; v.P = p; p += X;
     v.Linv = p; p += X; v.uUnc = p; p += U; v.Rt = p; p += U;
+    v.qmod0 = p; p += X; v.dq = p; p += X; v.rmod0 = p; p += U; v.dr = p; p += U;
     p += ((uintptr_t) p & 8) ? 1 : 0;
     v.W = p; p += d->szW; v.Ut = p; p += d->szUt;
-    v.nva = p; p += d->Nn; v.nvb = p; p += d->Nn; v.cva = p; p += d->nchunk; v.cvb = p; p += d->nchunk;
+    v.nva = p; p += d->Nn; v.nvb = p; p += d->Nn; v.cmod0 = p; p += d->Nn; v.dc = p; p += d->Nn; v.cva = p; p += d->nchunk; v.cvb = p; p += d->nchunk;
     if ((size_t) (p - D->d_work) > nwork) { snprintf(g_err, sizeof g_err, "work arena overflow"); return 1; }
 
     const size_t nT = d->nT;
     CK(cudaMalloc(&D->d_tint, sizeof(int) * (5 * nT + 4 + 256)));
-    CK(cudaMalloc(&D->d_tdbl, sizeof(double) * (5 * nT)));
+    CK(cudaMalloc(&D->d_tdbl, sizeof(double) * (6 * nT)));
     CK(cudaMemset(D->d_tint, 0, sizeof(int) * (5 * nT + 4 + 256)));
     v.status = D->d_tint; v.iter = v.status + nT; v.ls_cnt = v.iter + nT; v.ls_active = v.ls_cnt + nT;
     v.restart_cnt = v.ls_active + nT; v.counters = v.restart_cnt + nT; v.ls_hist = v.counters + 4;
     v.t_f0 = D->d_tdbl; v.t_dot = v.t_f0 + nT; v.t_tau = v.t_dot + nT; v.t_tauprev = v.t_tau + nT;
-    v.t_err = v.t_tauprev + nT;
+    v.t_err = v.t_tauprev + nT; v.t_taufin = v.t_err + nT;
     CK(cudaMallocHost(&D->h_counters, sizeof(int) * 4));
 
     v.Nn = d->Nn; v.nT = d->nT; v.X = d->X; v.U = d->U; v.nchunk = d->nchunk;
     v.abmax = d->abmax; v.dmax = d->dmax; v.nxmax = d->nxmax; v.numax = d->numax;
+
+    if (detect_fast_path(D, h_int)) return 1;
 
     /* shared memory per warp (bytes) and warps per CTA for the block kernels */
     int dev = 0, smem_max = 0;
@@ -171,7 +299,8 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr)
         return 1;
     }
     CK(cudaFuncSetAttribute(k_stage<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
-    CK(cudaFuncSetAttribute(k_stage<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
+    CK(cudaFuncSetAttribute(k_stage<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
+    CK(cudaFuncSetAttribute(k_stage<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
     CK(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_hess));
     CK(cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_fact));
     CK(cudaFuncSetAttribute(k_backsolve_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
@@ -197,6 +326,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (!D) return;
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
+    cudaFree(D->d_schur); free(D->lvl_md); free(D->lvl_kp);
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
@@ -248,14 +378,6 @@ static int read_counters(tqb_device *D)
     return 0;
 }
 
-/* dual function of all trees with ls_active set -> cvb (per-chunk partial sums) */
-static void launch_eval(tqb_device *D)
-{
-    const View &v = D->v;
-    LAUNCH(K_EVAL, k_stage<1>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
-    LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nvb, v.cvb, 0);
-}
-
 extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status, int *h_iter,
                                 int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms,
                                 long long *launches, double *kernel_ms16, int *kernel_count16)
@@ -285,39 +407,58 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     {
         CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
         LAUNCH(K_STAGE, k_stage<0>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
-        LAUNCH(K_GRAD, k_gradient, cdiv(v.Nn, 8), 256, 0, v);
-        LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
-        LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
-        if (read_counters(D)) return 1;
-        if (D->h_counters[0] == 0) break;
+        if (D->fast)
+        {   /* gradient + Hessian + factorisation fused, leaves to root; the termination test comes
+             * after the sweep (the sweep of the last iteration is the price of the fusion) */
+            CK(cudaMemsetAsync(v.nva, 0, sizeof(double) * (size_t) v.Nn, D->stream));
+            for (int l = Nh - 1; l >= 0; l--)
+                if (fused_factor_level(D, l)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+            LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
+            LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
+            if (read_counters(D)) return 1;
+            if (D->h_counters[0] == 0) break;
+            for (int l = 1; l < Nh; l++)
+                if (fused_backsolve_level(D, l)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+        }
+        else
+        {
+            LAUNCH(K_GRAD, k_gradient, cdiv(v.Nn, 8), 256, 0, v);
+            LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
+            LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
+            if (read_counters(D)) return 1;
+            if (D->h_counters[0] == 0) break;
 
-        LAUNCH(K_HESS, k_hessian, cdiv(v.Nn, D->wpb_hess), 32 * D->wpb_hess, D->sm_hess, v);
-        for (int l = Nh - 1; l >= 0; l--)
-        {
-            const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
-            if (cnt > 0)
-                LAUNCH(K_FACTOR, k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[l], cnt, D->pw_fact);
+            LAUNCH(K_HESS, k_hessian, cdiv(v.Nn, D->wpb_hess), 32 * D->wpb_hess, D->sm_hess, v);
+            for (int l = Nh - 1; l >= 0; l--)
+            {
+                const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+                if (cnt > 0)
+                    LAUNCH(K_FACTOR, k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[l], cnt, D->pw_fact);
+            }
+            for (int l = 1; l < Nh; l++)
+            {
+                const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+                if (cnt > 0)
+                    LAUNCH(K_BACK, k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back);
+            }
         }
-        for (int l = 1; l < Nh; l++)
-        {
-            const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
-            if (cnt > 0)
-                LAUNCH(K_BACK, k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back);
-        }
-        LAUNCH(K_DOT, k_dot, cdiv(v.Nn, 256), 256, 0, v);
+        /* affine model of the stage gradients along dlam + res'*dlam, then f(0), then trials */
+        LAUNCH(K_DIR, k_stage<2>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
         LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, 0);
-        launch_eval(D);
+        LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 1);
         LAUNCH(K_DECIDE, k_decide_ls_init, tgrid, 128, 0, v);
         for (int ls = 0; ls <= o->lsMaxIter; ls++)
         {
             CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
-            LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
-            launch_eval(D);
+            LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 0);
             LAUNCH(K_DECIDE, k_decide_ls_trial, tgrid, 128, 0, v);
             if (read_counters(D)) return 1;
             if (D->h_counters[1] == 0) break;
         }
+        LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
     }
+    /* trees that ran out of iterations: x,u of the last trial point (what the reference holds) */
+    LAUNCH(K_STAGE, k_stage<3>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
     LAUNCH(K_DECIDE, k_finalize_status, cdiv(nT, 256), 256, 0, v);
     {
         int n = v.X > v.U ? v.X : v.U;

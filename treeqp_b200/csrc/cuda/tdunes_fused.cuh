@@ -1,0 +1,294 @@
+/*
+ * tdunes_fused.cuh -- compile-time-dimension fast path of the leaves-to-root / root-to-leaves
+ * sweeps for uniform trees (every non-root node has NX states, every parent NU inputs, all
+ * parents of one depth have the same number of children MD; D = MD*NX <= 32).
+ *
+ * k_build_factor<NX,NU,MD,PNX,ROOT>: one warp per parent block p of one depth.  Fuses what the
+ * reference does in four places so that the dual Hessian block never travels through HBM:
+ *   - dual gradient of the kids   res_k = b_k - x_k + A_k x_p + B_k u_p      (dual_Newton_tree.c:519-539)
+ *   - dual Hessian block          W_p = C diag(P_p,Rt_p) C' + blkdiag(P_kids) (:551-615, clipping.c:264-355)
+ *                                 Ut_p = -P_p A_kids'                         (:581-589)
+ *     minus the kids' Schur complements (the dsyrk/dgemv updates of :726-732, received through
+ *     small per-node buffers instead of read-modify-write on W in HBM)
+ *   - Cholesky with BLASFEO's pivot rule + Levenberg-Marquardt policy         (dual_Newton_common.c:35-78)
+ *   - y = L^-1 resMod, Utilde = Ut L^-T, S_p = Utilde Utilde', s_p = Utilde y  (:712-732)
+ *   - roots: dlam = L^-T y                                                    (:748-758)
+ * Layout inside the warp: lane r owns ROW r of the augmented matrix [W_p ; Ut_p] in registers
+ * (rows >= 32 form a second register row-set on the low lanes); the factorisation is
+ * right-looking: at step j the finished column j is published to shared memory and every lane
+ * downdates its own row with broadcast reads.  The right-hand side is kept transposed (lane i
+ * holds resMod_i) and substituted on the fly with one shuffle per column.
+ *
+ * k_backsolve_fused<NX,MD>: dlam_p = L_p^-T (y_p - Utilde_p' dlam_dad[p]), lane t owns COLUMN t of L.
+ *
+ * HBM format of a factored block: L packed by rows (row i at i(i+1)/2, i+1 entries), Utilde
+ * row-major NX x D, inverse diagonal in x-space (Linv), Schur complement S_p (NX x NX row-major,
+ * lower triangle valid) and s_p in x-space (rsub).
+ */
+#pragma once
+#include "tdunes_kernels.cuh"
+
+__host__ __device__ constexpr int tqb_ld2(int n) { return n + ((6 - (n & 3)) & 3); } /* smallest >= n with ld%4==2 */
+
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+struct FusedCfg
+{
+    static constexpr int D = NX * MD;
+    static constexpr int NCOL = PNX + NU;           /* columns of C = [A_kids B_kids] */
+    static constexpr int NUT = ROOT ? 0 : NX;       /* rows of Ut */
+    static constexpr int R = D + NUT;               /* rows of the augmented matrix */
+    static constexpr bool SETB = R > 32;
+    static constexpr int LDC = tqb_ld2(NCOL > 0 ? NCOL : 2);
+    static constexpr int LDR = tqb_ld2(R);
+    /* shared memory per warp, in doubles: Cp (D x LDC) | Ms (D x LDR) | p (NCOL) | z (NCOL) | ys (D) */
+    static constexpr int SMEM = D * LDC + D * LDR + 2 * (NCOL + 2) + D + 2;
+};
+
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+__global__ void __launch_bounds__(128) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents)
+{
+    using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
+    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, R = Cfg::R, LDC = Cfg::LDC, LDR = Cfg::LDR;
+    constexpr bool SETB = Cfg::SETB;
+    static_assert(D <= 32, "block dimension must fit one warp");
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (w >= count) return;
+    const int g = v.T.lvl_nodes[lvl_begin + w];
+    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+
+    double *Cp = smem + (size_t) wib * Cfg::SMEM; /* Cp[K][c] = p_c * C[K][c] */
+    double *Ms = Cp + D * LDC;                    /* Ms[j][r] = column j of the factored augmented matrix */
+    double *ps = Ms + D * LDR;                    /* [P_p ; Rt_p] */
+    double *zs = ps + NCOL + 2;                   /* [x_p ; u_p] */
+    double *ys = zs + NCOL + 2;                   /* y = L^-1 resMod */
+
+    const int k0 = v.T.kid0[g];
+    const int xb = v.T.xoff[k0];                  /* this block's segment of x-space */
+    const int xo = v.T.xoff[g], uo = v.T.uoff[g];
+    const double *Ag = v.in.A + v.T.aoff[k0], *Bg = v.in.B + v.T.boff[k0];
+
+    for (int c = lane; c < NCOL; c += 32)
+    {
+        ps[c] = c < PNX ? v.P[xo + c] : v.Rt[uo + c - PNX];
+        zs[c] = c < PNX ? v.x[xo + c] : v.u[uo + c - PNX];
+    }
+    /* own row of C straight from HBM: kid k = lane/NX, A_k is NX x PNX column-major */
+    const bool isW = lane < D;
+    const int kid = isW ? lane / NX : 0, ii = isW ? lane - kid * NX : 0;
+    double crow[NCOL > 0 ? NCOL : 1];
+#pragma unroll
+    for (int c = 0; c < NCOL; c++)
+    {
+        double val = 0.0;
+        if (isW) val = c < PNX ? Ag[kid * NX * PNX + ii + c * NX] : Bg[kid * NX * NU + ii + (c - PNX) * NX];
+        crow[c] = val;
+    }
+    __syncwarp();
+    /* gradient of this lane's multiplier component, and its scaled C row for the others */
+    double res = 0.0;
+    if (isW)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+        {
+            s += crow[c] * zs[c];
+            Cp[lane * LDC + c] = crow[c] * ps[c];
+        }
+        res = (v.in.b[xb + lane] - v.x[xb + lane]) + s;
+        v.res[xb + lane] = res;
+    }
+    {   /* contribution to the termination norm (calculate_error_in_residuals, :412-442) */
+        double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
+        part = (v.o.termCondition == 2) ? warp_max(part) : warp_sum(part);
+        if (lane == 0) v.nva[g] = part;
+    }
+    double rr0 = res;
+    if (kids_are_parents && isW) rr0 -= v.rsub[xb + lane];
+    __syncwarp();
+
+    double wA[D], wB[SETB ? D : 1];
+    double myinv = 0.0, rr = 0.0;
+    bool small = false;
+    static_assert((D & 1) == 0, "even block dimension required (vectorised rows)");
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        const double shift = (v.o.regType == 1 || attempt == 1) ? v.o.regValue : 0.0;
+        /* ---- build the rows: W rows on lanes < D, Ut rows on the following rows ---- */
+#pragma unroll
+        for (int K = 0; K < D; K++)
+        {
+            double s = 0.0;
+            const double2 *cpk = reinterpret_cast<const double2 *>(Cp + K * LDC);
+#pragma unroll
+            for (int c2 = 0; c2 < NCOL / 2; c2++)
+            {
+                const double2 t2 = cpk[c2];
+                s += crow[2 * c2] * t2.x;
+                s += crow[2 * c2 + 1] * t2.y;
+            }
+            if (NCOL & 1) s += crow[NCOL - 1] * Cp[K * LDC + NCOL - 1];
+            wA[K] = s;
+        }
+        if (isW)
+        {
+            const double pk = v.P[xb + lane];
+#pragma unroll
+            for (int K = 0; K < D; K++)
+                if (K == lane) wA[K] += pk + shift;
+            if (kids_are_parents)
+            {   /* minus the Schur complement of the kid this row belongs to (lower triangle) */
+                const double *Sk = v.schur + (size_t) (k0 + kid) * NX * NX + ii * NX;
+#pragma unroll
+                for (int kk = 0; kk < NX; kk++)
+                {
+                    const double sv = (kk <= ii) ? Sk[kk] : 0.0;
+#pragma unroll
+                    for (int m = 0; m < MD; m++)
+                        if (m == kid) wA[m * NX + kk] -= sv;
+                }
+            }
+        }
+        if (!ROOT)
+        {   /* Ut rows: M[D+c][K] = -P_p[c] * A[K][c] = -Cp[K][c] */
+            if (!isW && lane < R)
+            {
+#pragma unroll
+                for (int K = 0; K < D; K++) wA[K] = -Cp[K * LDC + (lane - D)];
+            }
+            if (SETB)
+            {
+#pragma unroll
+                for (int K = 0; K < D; K++) wB[K] = (32 + lane < R) ? -Cp[K * LDC + (32 + lane - D)] : 0.0;
+            }
+        }
+        rr = rr0;
+        small = false;
+        /* ---- right-looking Cholesky of the augmented matrix ---- */
+#pragma unroll
+        for (int j = 0; j < D; j++)
+        {
+            double piv = __shfl_sync(FULL, wA[j], j), inv;
+            if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
+            else { piv = 0.0; inv = 0.0; }
+            small |= (piv <= v.o.regTol);
+            if (lane == j) { wA[j] = piv; myinv = inv; }
+            else if (lane > j) wA[j] *= inv;
+            if (SETB) wB[j] *= inv;
+            /* forward substitution of the right-hand side on the fly (dtrsv_lnn) */
+            const double yj = __shfl_sync(FULL, rr, j) * inv;
+            if (lane == j) rr = yj;
+            else if (lane > j) rr -= wA[j] * yj;
+            __syncwarp();
+            if (lane < LDR) Ms[j * LDR + lane] = wA[j];
+            if (SETB && 32 + lane < LDR) Ms[j * LDR + 32 + lane] = wB[j];
+            if (lane == 0) ys[j] = yj;
+            __syncwarp();
+            if (j + 1 < D)
+            {
+                const double lj = wA[j], ljB = SETB ? wB[j] : 0.0;
+                const double *col = Ms + j * LDR;
+#pragma unroll
+                for (int k = j + 1; k < D; k++)
+                {
+                    const double lk = col[k];
+                    wA[k] -= lj * lk;
+                    if (SETB) wB[k] -= ljB * lk;
+                }
+            }
+        }
+        if (!(v.o.regType == 2 && attempt == 0 && small)) break;
+        if (lane == 0) atomicAdd(&v.counters[2], 1);
+        __syncwarp();
+    }
+
+    /* ---- results to HBM ---- */
+    if (isW)
+    {
+        double *Lp = v.W + v.T.woff[g] + (lane * (lane + 1)) / 2;
+#pragma unroll
+        for (int t = 0; t < D; t++)
+            if (t <= lane) Lp[t] = wA[t];
+        v.Linv[xb + lane] = myinv;
+    }
+    if (!ROOT)
+    {
+        if (isW) v.dlam[xb + lane] = rr;
+        double *Up = v.Ut + v.T.utoff[g];
+        if (!isW && lane < R)
+        {
+            double2 *dst = reinterpret_cast<double2 *>(Up + (lane - D) * D);
+#pragma unroll
+            for (int t = 0; t < D / 2; t++) dst[t] = make_double2(wA[2 * t], wA[2 * t + 1]);
+        }
+        if (SETB && 32 + lane < R)
+        {
+            double2 *dst = reinterpret_cast<double2 *>(Up + (32 + lane - D) * D);
+#pragma unroll
+            for (int t = 0; t < D / 2; t++) dst[t] = make_double2(wB[2 * t], wB[2 * t + 1]);
+        }
+        /* Schur complement for the parent's block: S = Utilde Utilde' (lower), s = Utilde y */
+        double *Sg = v.schur + (size_t) g * NX * NX;
+        for (int e = lane; e < NX * NX; e += 32)
+        {
+            const int a = e / NX, b = e - a * NX;
+            if (b > a) continue;
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) s += Ms[j * LDR + D + a] * Ms[j * LDR + D + b];
+            Sg[e] = s;
+        }
+        for (int a = lane; a < NX; a += 32)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) s += Ms[j * LDR + D + a] * ys[j];
+            v.rsub[xo + a] = s;
+        }
+    }
+    else
+    {   /* root: backward substitution dlam = L^-T y; lane t owns column t of L = Ms[t][*] */
+#pragma unroll
+        for (int i = D - 1; i >= 0; i--)
+        {
+            const double yi = __shfl_sync(FULL, rr, i) * __shfl_sync(FULL, myinv, i);
+            if (lane == i) rr = yi;
+            else if (lane < i) rr -= Ms[lane * LDR + i] * yi;
+        }
+        if (isW) v.dlam[xb + lane] = rr;
+    }
+}
+
+template <int NX, int MD>
+__global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, int count)
+{
+    constexpr int D = NX * MD;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= count) return;
+    const int g = v.T.lvl_nodes[lvl_begin + w];
+    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+    const int xb = v.T.xoff[v.T.kid0[g]], xo = v.T.xoff[g];
+    const double *Lp = v.W + v.T.woff[g], *Up = v.Ut + v.T.utoff[g];
+    const bool act = lane < D;
+    double lcol[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) lcol[i] = (act && lane <= i) ? Lp[(i * (i + 1)) / 2 + lane] : 0.0;
+    double y = act ? v.dlam[xb + lane] : 0.0;
+    const double inv = act ? v.Linv[xb + lane] : 0.0;
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; c++) s += (act ? Up[c * D + lane] : 0.0) * v.dlam[xo + c];
+    y -= s;
+#pragma unroll
+    for (int i = D - 1; i >= 0; i--)
+    {
+        const double yi = __shfl_sync(FULL, y, i) * __shfl_sync(FULL, inv, i);
+        if (lane == i) y = yi;
+        else if (lane < i) y -= lcol[i] * yi;
+    }
+    if (act) v.dlam[xb + lane] = y;
+}

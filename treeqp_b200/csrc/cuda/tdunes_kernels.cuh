@@ -9,12 +9,12 @@
  *
  * Kernel                replaces (reference file:line)
  *   k_stage<0>          solve_stage_problems dual_Newton_tree.c:218 + stage_qp_clipping_solve_extended clipping.c:188
- *   k_stage<1>          evaluate_dual_function :823 + stage_qp_clipping_solve clipping.c:231 + eval_dual_term clipping.c:359
+ *   k_stage<2>, k_trial evaluate_dual_function :823 + stage_qp_clipping_solve clipping.c:231 + eval_dual_term clipping.c:359
  *   k_gradient          build_dual_problem :519-539 + calculate_error_in_residuals :412
  *   k_hessian           build_dual_problem :551-615 + clipping.c:264-355 (set_CmPnCmT/add_EPmE/add_CmPnCkT)
  *   k_factor_level      calculate_delta_lambda :668-758 + treeqp_dpotrf_l_with_reg_opts dual_Newton_common.c:35
  *   k_backsolve_level   calculate_delta_lambda :760-775
- *   k_dot / k_lambda_step / k_decide_*   line_search :922-1019, gradient_trans_times_direction :808
+ *   k_lambda_step / k_decide_*           line_search :922-1019, gradient_trans_times_direction :808
  *   k_finish            stage_qp_clipping_export_mu clipping.c:386
  */
 #pragma once
@@ -33,11 +33,13 @@ struct View
     /* outputs / iterates (x,u,lam,mux,muu contiguous: one D2H copy) */
     double *x, *u, *lam, *mux, *muu;
     double *dlam, *res, *resMod, *xUnc, *uUnc, *P, *Rt, *Linv;
+    double *qmod0, *rmod0, *dq, *dr, *cmod0, *dc; /* affine model of the stage gradients along dlam */
     double *W, *Ut;
+    double *schur, *rsub; /* fast path: per-node Schur complement (NX x NX) and its rhs part (x-space) */
     double *nva, *nvb, *cva, *cvb; /* per-node and per-chunk reduction scratch */
     /* per tree */
     int *status, *iter, *ls_cnt, *ls_active, *restart_cnt;
-    double *t_f0, *t_dot, *t_tau, *t_tauprev, *t_err;
+    double *t_f0, *t_dot, *t_tau, *t_tauprev, *t_err, *t_taufin;
     int *counters; /* [0] trees still running, [1] trees with a pending line-search trial, [2] regularised blocks, [3] total trials */
     int *ls_hist;  /* [256] trials per Newton iteration of tree 0 */
     int Nn, nT, X, U, nchunk;
@@ -85,10 +87,18 @@ __global__ void k_init(View v)
 }
 
 /* ------------------------------------------------------------------------------------------
- * Stage QPs of all nodes.  MODE 0: "extended" solve (keeps the unconstrained solution and the
- * elimination vectors P = Qinv.*[inactive], Rt = Rinv.*[inactive]);  MODE 1: clip-only solve +
- * this node's term of the dual function, written to nvb[g].
- * Algorithmic bytes per node: (5nx+4nu) + sum_kids (nx_j(nx+nu) + nx_j) read, 4nx+4nu written.
+ * Stage gradients / stage QPs of all nodes, one warp per node.
+ *   MODE 0  "extended" solve at lambda (solve_stage_problems + stage_qp_clipping_solve_extended):
+ *           qmod = -q + lambda_k - sum_kids A_j' lambda_j, rmod = -r - sum_kids B_j' lambda_j,
+ *           x = clip(Qinv.*qmod), P = Qinv.*[inactive] (same for u); keeps qmod/rmod/cmod as the
+ *           constant part of the affine model used by the line search.
+ *   MODE 2  direction: the same operator applied to dlam (without q, r): dq, dr, dc and the
+ *           node's part of res'*dlam.  Along lambda + tau*dlam the stage gradients are
+ *           qmod0 + tau*dq, so a line-search trial never touches A or B again (k_trial).
+ *   MODE 3  clip-only solve at lambda writing x,u (state of the reference's work->sx after its
+ *           last line-search trial; only needed when maxIter is hit).
+ * Algorithmic bytes per node (MODE 0): (5nx+4nu) + sum_kids (nx_j(nx+nu) + 2nx_j) read,
+ * 5nx+5nu+1 written.
  * ---------------------------------------------------------------------------------------- */
 template <int MODE>
 __global__ void __launch_bounds__(256) k_stage(View v)
@@ -98,21 +108,21 @@ __global__ void __launch_bounds__(256) k_stage(View v)
     const int g = blockIdx.x * wpb + wib;
     if (g >= v.Nn) return;
     const int t = v.T.tree[g];
-    if (MODE == 0) { if (v.status[t] != TQB_RUNNING) return; }
-    else           { if (!v.ls_active[t]) return; }
+    if (v.status[t] != TQB_RUNNING) return;
 
     double *sAB = smem + (size_t) wib * (v.abmax + v.dmax);
     double *sL = sAB + v.abmax;
     const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
     const int nk = v.T.nkids[g], k0 = v.T.kid0[g], d = v.T.dim[g];
     const bool root = v.T.dad[g] < 0;
+    const double *src = (MODE == 2) ? v.dlam : v.lam;
 
-    /* stage [A_kids] (d*nx), [B_kids] (d*nu) and lambda_kids (d): three contiguous ranges */
+    /* stage [A_kids] (d*nx), [B_kids] (d*nu) and the kids' multipliers (d): contiguous ranges */
     double cpart = 0.0;
     if (nk > 0)
     {
         const double *Ag = v.in.A + v.T.aoff[k0], *Bg = v.in.B + v.T.boff[k0];
-        const double *lg = v.lam + v.T.xoff[k0];
+        const double *lg = src + v.T.xoff[k0];
         const int na = d * nx, nb = d * nu;
         for (int e = lane; e < na; e += 32) sAB[e] = Ag[e];
         for (int e = lane; e < nb; e += 32) sAB[na + e] = Bg[e];
@@ -120,20 +130,27 @@ __global__ void __launch_bounds__(256) k_stage(View v)
         {
             const double l = lg[e];
             sL[e] = l;
-            if (MODE == 1) cpart += v.in.b[v.T.xoff[k0] + e] * l;
+            if (MODE != 3) cpart += v.in.b[v.T.xoff[k0] + e] * l;
         }
         __syncwarp();
     }
+    if (MODE != 3)
+    {   /* cmod = sum_kids b_j' lambda_j (dual_Newton_tree.c:892) */
+        const double c = warp_sum(cpart);
+        if (lane == 0) { if (MODE == 0) v.cmod0[g] = c; else v.dc[g] = c; }
+    }
 
-    double xQx = 0.0, xq = 0.0, uRu = 0.0, ur = 0.0;
+    double dotp = 0.0;
     for (int w = lane; w < nx + nu; w += 32)
     {
         const bool isx = w < nx;
         const int i = isx ? w : w - nx;
         double acc;
-        if (isx) acc = -v.in.q[xo + i] + (root ? 0.0 : v.lam[xo + i]);
-        else     acc = -v.in.r[uo + i];
-        /* acc -= A_j' lambda_j (resp. B_j' lambda_j) child by child (dgemv_t per child) */
+        if (MODE == 2) acc = (isx && !root) ? src[xo + i] : 0.0;
+        else if (isx) acc = -v.in.q[xo + i] + (root ? 0.0 : src[xo + i]);
+        else acc = -v.in.r[uo + i];
+        if (MODE == 2 && isx && !root) dotp += v.res[xo + i] * src[xo + i];
+        /* acc -= A_j' l_j (resp. B_j' l_j) child by child (dgemv_t per child) */
         int oa = isx ? 0 : d * nx, pos = 0;
         const int ncol = isx ? nx : nu;
         for (int j = 0; j < nk; j++)
@@ -146,53 +163,82 @@ __global__ void __launch_bounds__(256) k_stage(View v)
             oa += nxj * ncol;
             pos += nxj;
         }
+        if (MODE == 2)
+        {
+            if (isx) v.dq[xo + i] = acc; else v.dr[uo + i] = acc;
+            continue;
+        }
         int mask;
         if (isx)
         {
             const double unc = v.in.Qinv[xo + i] * acc;
-            const double val = clip_mask(unc, v.in.xmin[xo + i], v.in.xmax[xo + i], mask);
-            v.x[xo + i] = val;
+            v.x[xo + i] = clip_mask(unc, v.in.xmin[xo + i], v.in.xmax[xo + i], mask);
             if (MODE == 0)
             {
+                v.qmod0[xo + i] = acc;
                 v.xUnc[xo + i] = unc;
                 v.P[xo + i] = mask == 0 ? v.in.Qinv[xo + i] : 0.0;
-            }
-            else
-            {
-                xQx += (v.in.Qd[xo + i] * val) * val;
-                xq += acc * val;
             }
         }
         else
         {
             const double unc = v.in.Rinv[uo + i] * acc;
-            const double val = clip_mask(unc, v.in.umin[uo + i], v.in.umax[uo + i], mask);
-            v.u[uo + i] = val;
+            v.u[uo + i] = clip_mask(unc, v.in.umin[uo + i], v.in.umax[uo + i], mask);
             if (MODE == 0)
             {
+                v.rmod0[uo + i] = acc;
                 v.uUnc[uo + i] = unc;
                 v.Rt[uo + i] = mask == 0 ? v.in.Rinv[uo + i] : 0.0;
             }
-            else
-            {
-                uRu += (v.in.Rd[uo + i] * val) * val;
-                ur += acc * val;
-            }
         }
     }
-    if (MODE == 1)
+    if (MODE == 2)
     {
-        xQx = warp_sum(xQx); xq = warp_sum(xq); uRu = warp_sum(uRu); ur = warp_sum(ur);
-        const double cmod = warp_sum(cpart);
-        if (lane == 0)
-        {   /* order of clipping.c:375-381 */
-            double f = -0.5 * xQx - cmod;
-            f += xq;
-            f -= 0.5 * uRu;
-            f += ur;
-            v.nvb[g] = f;
-        }
+        dotp = warp_sum(dotp);
+        if (lane == 0) v.nva[g] = dotp;
     }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * One line-search trial (evaluate_dual_function, dual_Newton_tree.c:823-918, with
+ * stage_qp_clipping_solve + eval_dual_term, clipping.c:231-382) for every tree with a pending
+ * trial, at that tree's step length tau:
+ *   f(tau) = sum_x [ -1/2 Q x^2 + qmod x ] + sum_u [ -1/2 R u^2 + rmod u ] - sum_nodes cmod,
+ *   qmod = qmod0 + tau*dq,  x = clip(Qinv.*qmod)   (same for u, cmod).
+ * One CTA per reduction chunk (<=1024 consecutive nodes of one tree), fixed-shape reduction.
+ * Bytes per trial: 6(X+U) + 2 Nn doubles read, nothing written but one double per chunk.
+ * ---------------------------------------------------------------------------------------- */
+__global__ void __launch_bounds__(256) k_trial(View v, int at_zero)
+{
+    __shared__ double sh[256];
+    const int c = blockIdx.x;
+    const int t = v.T.chunk_tree[c];
+    if (!v.ls_active[t]) return;
+    const double tau = at_zero ? 0.0 : v.t_tau[t];
+    double acc = 0.0;
+    int dummy;
+    for (int i = v.T.chunk_x0[c] + threadIdx.x; i < v.T.chunk_x1[c]; i += 256)
+    {
+        const double qm = v.qmod0[i] + tau * v.dq[i];
+        const double val = clip_mask(v.in.Qinv[i] * qm, v.in.xmin[i], v.in.xmax[i], dummy);
+        acc += -0.5 * ((v.in.Qd[i] * val) * val) + qm * val;
+    }
+    for (int i = v.T.chunk_u0[c] + threadIdx.x; i < v.T.chunk_u1[c]; i += 256)
+    {
+        const double rm = v.rmod0[i] + tau * v.dr[i];
+        const double val = clip_mask(v.in.Rinv[i] * rm, v.in.umin[i], v.in.umax[i], dummy);
+        acc += -0.5 * ((v.in.Rd[i] * val) * val) + rm * val;
+    }
+    for (int g = v.T.chunk_beg[c] + threadIdx.x; g < v.T.chunk_end[c]; g += 256)
+        acc -= v.cmod0[g] + tau * v.dc[g];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1)
+    {
+        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) v.cvb[c] = sh[0];
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -542,21 +588,6 @@ __global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, 
     for (int e = lane; e < d; e += 32) v.dlam[xb + e] = sy[e];
 }
 
-/* per-node part of res' * dlam (gradient_trans_times_direction, dual_Newton_tree.c:808-820) */
-__global__ void k_dot(View v)
-{
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= v.Nn) return;
-    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
-    double s = 0.0;
-    if (v.T.dad[g] >= 0)
-    {
-        const int xo = v.T.xoff[g], nx = v.T.nx[g];
-        for (int i = 0; i < nx; i++) s += v.res[xo + i] * v.dlam[xo + i];
-    }
-    v.nva[g] = s;
-}
-
 /* start of a line search (dual_Newton_tree.c:940-956): descent test, tau = 1 */
 __global__ void k_decide_ls_init(View v)
 {
@@ -585,14 +616,16 @@ __global__ void k_decide_ls_init(View v)
     }
 }
 
-/* lambda += (tau - tauPrev) * dlam for the trees with a pending trial (dual_Newton_tree.c:964-968) */
+/* lambda += tau_final * dlam once the line search of a tree is over.  (The reference moves
+ * lambda incrementally by (tau - tauPrev)*dlam at every trial, dual_Newton_tree.c:964-968; the
+ * end point is the same up to rounding.) */
 __global__ void k_lambda_step(View v)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= v.Nn) return;
     const int t = v.T.tree[g];
-    if (!v.ls_active[t] || v.T.dad[g] < 0) return;
-    const double step = v.t_tau[t] - v.t_tauprev[t];
+    if (v.status[t] != TQB_RUNNING || v.T.dad[g] < 0) return;
+    const double step = v.t_taufin[t];
     const int xo = v.T.xoff[g], nx = v.T.nx[g];
     for (int i = 0; i < nx; i++) v.lam[xo + i] += step * v.dlam[xo + i];
 }
@@ -609,6 +642,7 @@ __global__ void k_decide_ls_trial(View v)
     {
         const int ls = ++v.ls_cnt[t];
         const double tau = v.t_tau[t];
+        v.t_taufin[t] = tau; /* lambda of the last evaluated trial */
         bool done = false;
         int recorded = ls;
         if (v.restart_cnt[t] == v.o.lsRestartTrigger) done = true; /* full step when stuck (:973-977) */

@@ -17,7 +17,7 @@
 #include "treeqp_b200.h"
 #include "host_internal.h"
 
-#define TQB_CHUNK 1024 /* nodes per fixed-shape reduction chunk */
+#define TQB_CHUNK 128 /* nodes per fixed-shape reduction chunk */
 
 double tqb_wall_ms(void)
 {
@@ -38,6 +38,7 @@ void tqb_layout_tables(const tqb_dims *d, int *base, tqb_tables *t)
     TK(lvl_nodes, d->Np > 0 ? d->Np : 1);
     TK(tnode0, d->nT + 1);
     TK(chunk_beg, d->nchunk); TK(chunk_end, d->nchunk); TK(chunk_tree, d->nchunk);
+    TK(chunk_x0, d->nchunk); TK(chunk_x1, d->nchunk); TK(chunk_u0, d->nchunk); TK(chunk_u1, d->nchunk);
     TK(tchunk0, d->nT + 1);
 #undef TK
     assert(p - base == d->n_int);
@@ -124,7 +125,7 @@ tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
     }
     d->X = (int) X; d->U = (int) U; d->szA = szA; d->szB = szB; d->szW = szW; d->szUt = szUt;
     d->Np = Np; d->Nh = Nh; d->nchunk = nchunk;
-    d->n_int = 15 * d->Nn + (Np > 0 ? Np : 1) + 2 * (nT + 1) + 3 * nchunk;
+    d->n_int = 15 * d->Nn + (Np > 0 ? Np : 1) + 2 * (nT + 1) + 7 * nchunk;
     d->n_in = inputs_size(d);
 
     f->h_int = (int *) malloc(sizeof(int) * (size_t) d->n_int);
@@ -203,6 +204,14 @@ tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
     }
     T->tnode0[nT] = g0;
     T->tchunk0[nT] = c;
+    for (int i = 0; i < nchunk; i++)
+    {
+        const int e = T->chunk_end[i];
+        T->chunk_x0[i] = T->xoff[T->chunk_beg[i]];
+        T->chunk_u0[i] = T->uoff[T->chunk_beg[i]];
+        T->chunk_x1[i] = e < d->Nn ? T->xoff[e] : d->X;
+        T->chunk_u1[i] = e < d->Nn ? T->uoff[e] : d->U;
+    }
 
     /* level lists of parents: counting sort by depth, node order inside a level */
     f->lvl_ptr = (int *) malloc(sizeof(int) * (size_t) (Nh + 2));
@@ -257,6 +266,7 @@ void tqb_forest_pack(tqb_forest *f, int t, const tree_qp_in *qp)
     tqb_inputs *in = &f->hin;
     int g0 = T->tnode0[t];
     assert(T->tnode0[t + 1] - g0 == qp->N);
+#pragma omp parallel for schedule(static) if (qp->N > 2048)
     for (int k = 0; k < qp->N; k++)
     {
         int g = g0 + k, nx = qp->nx[k], nu = qp->nu[k], xo = T->xoff[g], uo = T->uoff[g];
@@ -309,6 +319,7 @@ void tqb_forest_unpack(const tqb_forest *f, int t, tree_qp_out *out)
     const tqb_dims *d = &f->dims;
     const double *x = f->h_out, *u = x + d->X, *lam = u + d->U, *mux = lam + d->X, *muu = mux + d->X;
     int g0 = T->tnode0[t], N = T->tnode0[t + 1] - g0;
+#pragma omp parallel for schedule(static) if (N > 2048)
     for (int k = 0; k < N; k++)
     {
         int g = g0 + k, nx = T->nx[g], nu = T->nu[g], xo = T->xoff[g], uo = T->uoff[g];

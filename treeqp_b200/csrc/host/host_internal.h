@@ -38,7 +38,8 @@ typedef struct tqb_tables
     int *woff, *utoff;   /* [Nn] offsets of W_p / Ut_p */
     int *lvl_nodes;      /* [Np] parents sorted by depth (level lists) */
     int *tnode0;         /* [nT+1] node range of each tree */
-    int *chunk_beg, *chunk_end, *chunk_tree; /* [nchunk] fixed-shape reduction chunks */
+    int *chunk_beg, *chunk_end, *chunk_tree; /* [nchunk] fixed-shape reduction chunks (node ranges) */
+    int *chunk_x0, *chunk_x1, *chunk_u0, *chunk_u1; /* [nchunk] the same chunks as x-/u-space ranges */
     int *tchunk0;        /* [nT+1] chunk range of each tree */
 } tqb_tables;
 

@@ -376,6 +376,7 @@ void treeqp_tdunes_batch_set_dual_initialization(treeqp_tdunes_batch *b, int i, 
 return_t treeqp_tdunes_batch_upload(treeqp_tdunes_batch *b, const tree_qp_in *const *qp_in)
 {
     double t0 = tqb_wall_ms();
+#pragma omp parallel for schedule(dynamic, 16) if (b->n > 32)
     for (int i = 0; i < b->n; i++) tqb_forest_pack(b->forest, i, qp_in[i]);
     b->forest->pack_ms = tqb_wall_ms() - t0;
     if (forest_upload(b->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
@@ -397,6 +398,7 @@ return_t treeqp_tdunes_batch_download(treeqp_tdunes_batch *b, tree_qp_out *const
 {
     if (forest_download(b->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
     double t0 = tqb_wall_ms();
+#pragma omp parallel for schedule(dynamic, 16) if (b->n > 32)
     for (int i = 0; i < b->n; i++)
     {
         if (b->forest->h_status[i] == TREEQP_DN_NOT_DESCENT_DIRECTION) continue; /* untouched */
