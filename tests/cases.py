@@ -23,7 +23,48 @@ def cases():
     yield "linear_chain_pinned_x0", P.linear_chain(2, 1, 2, 2, 6, seed=1, eliminate_x0=False), {}
 
 
+def _ubox(prob, ub, xb=None):
+    prob.umin[:] = -ub
+    prob.umax[:] = ub
+    if xb is not None:
+        prob.xmin[:] = -xb
+        prob.xmax[:] = xb
+    return prob
+
+
+_X0B = [0.3, 0.5, -0.4, 0.2]
+
+
+def sdunes_cases():
+    """SDUNES parity cases (x0 eliminated).  The reference's SDUNES does not converge once state
+    bounds make the scenario Hessians singular (measured: 100 iterations on every such probe), so
+    the converging cases bound the inputs; `*_tight_maxit3` pins the first iterations of such a
+    degenerate path instead (regularised blocks, 40-51 line-search trials per iteration)."""
+    E = P.eliminate_x0
+    yield "spring_mass_cfg1", E(P.spring_mass(3, 2, 10)), {}
+    yield "spring_mass_cfg2", E(P.spring_mass(3, 4, 20)), {}
+    yield "spring_mass_cfg2_u01", _ubox(E(P.spring_mass(3, 4, 20, x0=_X0B)), 0.1, 1e12), {}
+    yield "spring_mass_u02_nocache", _ubox(E(P.spring_mass(3, 2, 10, x0=_X0B)), 0.2, 1e12), dict(checkLastActiveSet=0)
+    yield "linear_chain_u05", _ubox(P.linear_chain(4, 3, 3, 2, 20, seed=0), 0.5, 1e12), {}
+    yield "linear_chain_nm8_md4", _ubox(P.linear_chain(8, 7, 4, 2, 20, seed=2), 0.3, 1e12), {}
+    yield "linear_chain_md2_Nr3", _ubox(P.linear_chain(2, 1, 2, 3, 10, seed=1), 0.3, 1e12), {}
+    yield "linear_chain_md3_Nr3", _ubox(P.linear_chain(3, 2, 3, 3, 12, seed=2), 0.3, 1e12), dict(regType=1)
+    yield "spring_mass_tight_maxit3", E(P.spring_mass(3, 2, 10, xmax1=0.2)), dict(maxIter=3)
+
+
 CASE_NAMES = [c[0] for c in cases()]
+SDUNES_CASE_NAMES = [c[0] for c in sdunes_cases()]
+
+
+def get_sdunes_case(name):
+    for n, p, o in sdunes_cases():
+        if n == name:
+            return p, o
+    raise KeyError(name)
+
+
+def sdunes_golden(name):
+    return np.load(os.path.join(GOLDEN, "sdunes_%s.npz" % name))
 
 
 def get_case(name):
@@ -51,7 +92,7 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
 
 
-PORT_OPT_NAMES = {"maxIter", "termCondition", "regType", "regTol", "regValue", "lineSearchMaxIter",
+PORT_OPT_NAMES = {"checkLastActiveSet", "maxIter", "termCondition", "regType", "regTol", "regValue", "lineSearchMaxIter",
                   "lineSearchGamma", "lineSearchBeta"}
 
 

@@ -6,6 +6,7 @@ by `make -C oracle ref`).  The GPU box never runs this: tests read the .npz file
 
   spring_mass_data.npz   numeric arrays parsed out of examples/spring_mass_utils/data.c and
                          x0.txt (the reference's own example data; lambda0_tree.txt is all zeros)
+  sdunes_<case>.npz      the same for treeqp_sdunes_solve (x0 eliminated)
   tdunes_<case>.npz      outputs of the UNMODIFIED reference (treeqp_tdunes_solve, clipping) on the
                          seeded problems of treeqp_b200/problems.py: status, Newton iterations,
                          x, u, lam, mu_x, mu_u, KKT residual.  Inputs are regenerated from the
@@ -48,7 +49,7 @@ def make_spring_mass_data():
     print("spring_mass_data.npz: NX=%d NU=%d realisations=%d" % (d["NX"], d["NU"], len(d["A"]) // d["NX"] ** 2))
 
 
-from cases import cases, checksum  # noqa: E402  (tests/cases.py)
+from cases import cases, checksum, sdunes_cases  # noqa: E402  (tests/cases.py)
 
 
 def make_tdunes_goldens():
@@ -63,6 +64,24 @@ def make_tdunes_goldens():
             name, prob.Nn, sol.status, sol.iter, sol.kkt, 1e3 * sol.total_time))
 
 
+def make_sdunes_goldens():
+    """outputs of the UNMODIFIED reference treeqp_sdunes_solve (dual_Newton_scenarios.c:1850)"""
+    from treeqp_b200 import capi
+    ref = capi.TreeQpLib(os.path.join(ROOT, "oracle/_ref/libtreeqp_ref.so"))
+    for name, prob, opts in sdunes_cases():
+        sol = capi.solve_sdunes(ref, prob, **opts)
+        np.savez_compressed(os.path.join(HERE, "sdunes_%s.npz" % name), status=sol.status, iter=sol.iter,
+                            x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u, kkt=sol.kkt,
+                            input_sha256=checksum(prob), opts=repr(opts))
+        print("sdunes %-28s Nn=%6d status=%d iter=%3d kkt=%.2e time=%.3f ms" % (
+            name, prob.Nn, sol.status, sol.iter, sol.kkt, 1e3 * sol.total_time))
+
+
 if __name__ == "__main__":
-    make_spring_mass_data()
-    make_tdunes_goldens()
+    what = sys.argv[1:] or ["data", "tdunes", "sdunes"]
+    if "data" in what:
+        make_spring_mass_data()
+    if "tdunes" in what:
+        make_tdunes_goldens()
+    if "sdunes" in what:
+        make_sdunes_goldens()

@@ -28,8 +28,8 @@ class PortOpts(C.Structure):
 
 def build_port():
     """compile the port if missing (gcc only; needs nothing from /root/reference)"""
-    if not os.path.exists(PORT_LIB) or os.path.getmtime(PORT_LIB) < os.path.getmtime(
-            os.path.join(ROOT, "oracle", "tdunes_port.c")):
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("tdunes_port.c", "sdunes_port.c", "port_common.h")]
+    if not os.path.exists(PORT_LIB) or os.path.getmtime(PORT_LIB) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
     return PORT_LIB
 
@@ -66,3 +66,44 @@ def solve_port(prob, lam0=None, maxIter=100, termCondition=2, tol=1e-8, regType=
                ls.ctypes.data_as(_ip), xas.ctypes.data_as(_ip), uas.ctypes.data_as(_ip), C.byref(nreg))
     return dict(status=status, iter=it.value, x=x[:X], u=u[:U], lam=lam[:nl], mu_x=mux[:X], mu_u=muu[:U],
                 ls_iters=ls[:it.value].tolist(), xas=xas[:X], uas=uas[:U], n_reg=nreg.value)
+
+
+def solve_sdunes_port(prob, lam0=None, mu0=None, checkLastActiveSet=1, maxIter=100, termCondition=2, tol=1e-8,
+                      regType=2, regTol=1e-6, regValue=1e-6, lineSearchMaxIter=50, lineSearchGamma=0.1,
+                      lineSearchBeta=0.6):
+    """oracle/sdunes_port.c on a Problem with x0 eliminated (nx[0] == 0)"""
+    lib = C.CDLL(build_port())
+    f = lib.oracle_sdunes_solve
+    f.restype = C.c_int
+    keep = {}
+
+    def d(a):
+        a = np.ascontiguousarray(a, dtype=np.float64); keep[id(a)] = a
+        return a.ctypes.data_as(_dp)
+
+    def i(a):
+        a = np.ascontiguousarray(a, dtype=np.int32); keep[id(a)] = a
+        return a.ctypes.data_as(_ip)
+
+    qp = PortQp(prob.Nn, i(prob.nk), i(prob.nx), i(prob.nu), d(prob.A), d(prob.B), d(prob.b), d(prob.Qd),
+                d(prob.Rd), d(prob.q), d(prob.r), d(prob.xmin), d(prob.xmax), d(prob.umin), d(prob.umax))
+    o = PortOpts(maxIter, termCondition, tol, regType, regTol, regValue, lineSearchMaxIter,
+                 lineSearchGamma, lineSearchBeta)
+    Ns, Nh, Nr, nl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    lib.oracle_sdunes_dims(C.byref(qp), C.byref(Ns), C.byref(Nh), C.byref(Nr), C.byref(nl))
+    Ns, Nh, Nr, nl = Ns.value, Nh.value, Nr.value, nl.value
+    nmu = Ns * Nh * int(prob.nx[1])
+    X, U = int(np.sum(prob.nx)), int(np.sum(prob.nu))
+    lam0 = np.zeros(nl + 1) if lam0 is None else np.ascontiguousarray(lam0, dtype=np.float64)
+    mu0 = np.zeros(nmu + 1) if mu0 is None else np.ascontiguousarray(mu0, dtype=np.float64)
+    x, u, lam = np.zeros(X + 1), np.zeros(U + 1), np.zeros(X + 1)
+    mux, muu = np.zeros(X + 1), np.zeros(U + 1)
+    lam_s, mu_s = np.zeros(nl + 1), np.zeros(nmu + 1)
+    ls = np.zeros(maxIter + 1, dtype=np.int32)
+    it, nreg = C.c_int(0), C.c_int(0)
+    p = lambda a: a.ctypes.data_as(_dp)
+    status = f(C.byref(qp), C.byref(o), C.c_int(checkLastActiveSet), p(lam0), p(mu0), p(x), p(u), p(lam), p(mux),
+               p(muu), p(lam_s), p(mu_s), C.byref(it), ls.ctypes.data_as(_ip), C.byref(nreg))
+    return dict(status=status, iter=it.value, x=x[:X], u=u[:U], lam=lam[:X - int(prob.nx[0])], mu_x=mux[:X],
+                mu_u=muu[:U], ls_iters=ls[:it.value].tolist(), n_reg=nreg.value, lam_scen=lam_s[:nl],
+                mu_scen=mu_s[:nmu], Ns=Ns, Nh=Nh, Nr=Nr)

@@ -55,6 +55,22 @@ class TdunesOpts(C.Structure):
     ]
 
 
+class SdunesOpts(C.Structure):
+    """treeqp_sdunes_opts_t, dual_Newton_scenarios.h:49-66"""
+    _fields_ = [
+        ("maxIter", C.c_int),
+        ("checkLastActiveSet", C.c_int),
+        ("stationarityTolerance", C.c_double),
+        ("termCondition", C.c_int),
+        ("regType", C.c_int),
+        ("regTol", C.c_double),
+        ("regValue", C.c_double),
+        ("lineSearchMaxIter", C.c_int),
+        ("lineSearchGamma", C.c_double),
+        ("lineSearchBeta", C.c_double),
+    ]
+
+
 class DVec(C.Structure):
     """struct blasfeo_dvec (HIGH_PERFORMANCE), blasfeo_common.h:72-78"""
     _fields_ = [("m", C.c_int), ("pm", C.c_int), ("pa", c_double_p), ("memsize", C.c_int)]
@@ -190,6 +206,23 @@ class TreeQpLib:
         L.treeqp_tdunes_set_dual_initialization.restype = None
         L.treeqp_tdunes_solve.argtypes = [vp, vp, C.POINTER(TdunesOpts), vp]
         L.treeqp_tdunes_solve.restype = C.c_int
+        # SDUNES septet + dual dimension, dual_Newton_scenarios.h:143-163
+        L.treeqp_sdunes_opts_calculate_size.argtypes = [C.c_int]
+        L.treeqp_sdunes_opts_calculate_size.restype = C.c_int
+        L.treeqp_sdunes_opts_create.argtypes = [C.c_int, C.POINTER(SdunesOpts), vp]
+        L.treeqp_sdunes_opts_create.restype = None
+        L.treeqp_sdunes_opts_set_default.argtypes = [C.c_int, C.POINTER(SdunesOpts)]
+        L.treeqp_sdunes_opts_set_default.restype = None
+        L.treeqp_sdunes_calculate_size.argtypes = [vp, C.POINTER(SdunesOpts)]
+        L.treeqp_sdunes_calculate_size.restype = C.c_int
+        L.treeqp_sdunes_create.argtypes = [vp, C.POINTER(SdunesOpts), vp, vp]
+        L.treeqp_sdunes_create.restype = None
+        L.treeqp_sdunes_calculate_dual_dimension.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.treeqp_sdunes_calculate_dual_dimension.restype = C.c_int
+        L.treeqp_sdunes_set_dual_initialization.argtypes = [c_double_p, c_double_p, vp]
+        L.treeqp_sdunes_set_dual_initialization.restype = None
+        L.treeqp_sdunes_solve.argtypes = [vp, vp, C.POINTER(SdunesOpts), vp]
+        L.treeqp_sdunes_solve.restype = C.c_int
         L.setup_multistage_tree.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p]
         L.setup_multistage_tree.restype = None
         L.calculate_number_of_nodes.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -230,6 +263,18 @@ class TreeQpLib:
             L.treeqp_tdunes_batch_get_stats.restype = None
             L.treeqp_tdunes_batch_destroy.argtypes = [vp]
             L.treeqp_tdunes_batch_destroy.restype = None
+            L.treeqp_sdunes_destroy.argtypes = [vp]
+            L.treeqp_sdunes_destroy.restype = None
+            L.treeqp_sdunes_get_stats.argtypes = [vp, C.POINTER(Stats)]
+            L.treeqp_sdunes_get_stats.restype = None
+            L.treeqp_sdunes_upload.argtypes = [vp, C.POINTER(SdunesOpts), vp]
+            L.treeqp_sdunes_upload.restype = C.c_int
+            L.treeqp_sdunes_solve_resident.argtypes = [C.POINTER(SdunesOpts), vp]
+            L.treeqp_sdunes_solve_resident.restype = C.c_int
+            L.treeqp_sdunes_download.argtypes = [vp, vp]
+            L.treeqp_sdunes_download.restype = C.c_int
+            L.treeqp_sdunes_get_duals.argtypes = [c_double_p, c_double_p, vp]
+            L.treeqp_sdunes_get_duals.restype = None
 
     # -- small helpers mirroring utils/tree.c
     def multistage_tree(self, md: int, Nr: int, Nh: int) -> np.ndarray:
@@ -433,6 +478,92 @@ def solve_tdunes(lib: TreeQpLib, prob: Problem, lam0: Optional[np.ndarray] = Non
     kkt = float("nan")
     if status in (TREEQP_OPTIMAL_SOLUTION_FOUND, TREEQP_MAXIMUM_ITERATIONS_REACHED):
         kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
+    sol = Solution(status=status, iter=qp_out.iter, x=qp_out.x, u=qp_out.u, lam=qp_out.lam,
+                   mu_x=qp_out.mu_x, mu_u=qp_out.mu_u, kkt=kkt, total_time=qp_out.total_time,
+                   stats=solver.stats() if lib.is_product else None)
+    solver.destroy()
+    return sol
+
+
+class Sdunes:
+    """SDUNES solver object: opts + workspace protocol of dual_Newton_scenarios.h:143-163.
+    The QP must have x0 eliminated (nx[0] == 0), uniform nx/nu and a multistage tree."""
+
+    def __init__(self, lib: TreeQpLib, qp_in: QpIn, **opt_overrides):
+        self.lib, self.qp_in = lib, qp_in
+        L = lib.lib
+        prob = qp_in.prob
+        Nn = prob.Nn
+        self.opts = SdunesOpts()
+        self.opts_mem = _Buf(max(L.treeqp_sdunes_opts_calculate_size(Nn), 8))
+        L.treeqp_sdunes_opts_create(Nn, C.byref(self.opts), self.opts_mem.ptr)
+        L.treeqp_sdunes_opts_set_default(Nn, C.byref(self.opts))
+        for k, v in opt_overrides.items():
+            assert hasattr(self.opts, k), k
+            setattr(self.opts, k, v)
+        size = L.treeqp_sdunes_calculate_size(qp_in.ptr, C.byref(self.opts))
+        assert size > 0, "workspace size overflows int"
+        self.work_mem = _Buf(size)
+        self.work = _Buf(2048)  # opaque treeqp_sdunes_workspace
+        L.treeqp_sdunes_create(qp_in.ptr, C.byref(self.opts), self.work.ptr, self.work_mem.ptr)
+        dims = np.frombuffer((C.c_char * 16).from_address(self.work.addr), dtype=np.int32)
+        self.Ns, self.Nh, self.Nr, self.md = (int(v) for v in dims)
+        self.nx, self.nu = int(prob.nx[1]), int(prob.nu[0])
+        self.n_lambda = max(L.treeqp_sdunes_calculate_dual_dimension(self.Nr, self.md, self.nu), 0)
+        self.n_mu = self.Ns * self.Nh * self.nx
+        self._alive = True
+
+    def set_dual_initialization(self, lam0: np.ndarray, mu0: np.ndarray):
+        lam0, mu0 = _f64(lam0), _f64(mu0)
+        assert lam0.size == self.n_lambda and mu0.size == self.n_mu
+        self._keep = (lam0, mu0)
+        self.lib.lib.treeqp_sdunes_set_dual_initialization(_dp(lam0), _dp(mu0), self.work.ptr)
+
+    def solve(self, qp_out: QpOut) -> int:
+        return int(self.lib.lib.treeqp_sdunes_solve(self.qp_in.ptr, qp_out.ptr, C.byref(self.opts), self.work.ptr))
+
+    # additive protocol (product library only)
+    def upload(self) -> int:
+        return int(self.lib.lib.treeqp_sdunes_upload(self.qp_in.ptr, C.byref(self.opts), self.work.ptr))
+
+    def solve_resident(self) -> int:
+        return int(self.lib.lib.treeqp_sdunes_solve_resident(C.byref(self.opts), self.work.ptr))
+
+    def download(self, qp_out: QpOut) -> int:
+        return int(self.lib.lib.treeqp_sdunes_download(qp_out.ptr, self.work.ptr))
+
+    def duals(self):
+        """scenario duals after the last solve: (lambda [n_lambda], mu [Ns*Nh*nx])"""
+        lam, mu = np.zeros(max(self.n_lambda, 1)), np.zeros(max(self.n_mu, 1))
+        self.lib.lib.treeqp_sdunes_get_duals(_dp(lam), _dp(mu), self.work.ptr)
+        return lam[:self.n_lambda], mu[:self.n_mu]
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.lib.lib.treeqp_sdunes_get_stats(self.work.ptr, C.byref(st))
+        return stats_dict(self.lib, st)
+
+    def destroy(self):
+        if self._alive and self.lib.is_product:
+            self.lib.lib.treeqp_sdunes_destroy(self.work.ptr)
+        self._alive = False
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def solve_sdunes(lib: TreeQpLib, prob: Problem, lam0=None, mu0=None, **opts) -> Solution:
+    """Build, solve once, read back: examples/spring_mass_dual_newton_scenarios.c:100-166."""
+    qp_in = QpIn(lib, prob)
+    qp_out = QpOut(lib, prob)
+    solver = Sdunes(lib, qp_in, **opts)
+    solver.set_dual_initialization(np.zeros(solver.n_lambda) if lam0 is None else lam0,
+                                   np.zeros(solver.n_mu) if mu0 is None else mu0)
+    status = solver.solve(qp_out)
+    kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
     sol = Solution(status=status, iter=qp_out.iter, x=qp_out.x, u=qp_out.u, lam=qp_out.lam,
                    mu_x=qp_out.mu_x, mu_u=qp_out.mu_u, kkt=kkt, total_time=qp_out.total_time,
                    stats=solver.stats() if lib.is_product else None)

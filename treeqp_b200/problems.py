@@ -214,3 +214,52 @@ def linear_chain(nm: int = 4, nu: int = 3, md: int = 3, Nr: int = 2, Nh: int = 2
         p.xmin[:nxs_] = x0
         p.xmax[:nxs_] = x0
     return p
+
+
+def eliminate_x0(prob: Problem) -> Problem:
+    """Fold a pinned initial state (xmin[0] == xmax[0] == x0) into the dynamics of the root's
+    children, as tree_qp_in_eliminate_x0 does (tree_qp_common.c:404-525): nx[0] <- 0,
+    b_k <- A_k x0 + b_k for the children k of the root, A_k loses its columns.  This is the form
+    SDUNES requires (dual_Newton_scenarios.c:1498) and the JSON driver always uses
+    (solve_qp_json.cpp:353)."""
+    nx0 = int(prob.nx[0])
+    if nx0 == 0:
+        return prob
+    x0 = np.asarray(prob.xmin[:nx0], dtype=float)
+    assert np.array_equal(x0, prob.xmax[:nx0]), "x0 is not pinned"
+    dad = prob.dad
+    As, bs = [], []
+    ia = ix = 0
+    for k in range(1, prob.Nn):
+        nxk, nxp = int(prob.nx[k]), int(prob.nx[dad[k]])
+        Ak = prob.A[ia:ia + nxk * nxp]
+        bk = prob.b[ix:ix + nxk]
+        if dad[k] == 0:
+            bs.append(Ak.reshape(nxp, nxk).T @ x0 + bk)
+        else:
+            As.append(Ak); bs.append(bk)
+        ia += nxk * nxp; ix += nxk
+    nx = prob.nx.copy(); nx[0] = 0
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    return Problem(nk=prob.nk, nx=nx, nu=prob.nu, A=cat(As), B=prob.B, b=cat(bs), Qd=prob.Qd[nx0:],
+                   Rd=prob.Rd, q=prob.q[nx0:], r=prob.r, xmin=prob.xmin[nx0:], xmax=prob.xmax[nx0:],
+                   umin=prob.umin, umax=prob.umax, lam0=prob.lam0,
+                   meta=dict(prob.meta, x0_eliminated=True))
+
+
+def scenario_dims(prob: Problem):
+    """(Ns, Nh, Nr, md, nl): scenarios, horizon, robust horizon, branching and the number of
+    non-anticipativity multipliers (treeqp_sdunes_calculate_dual_dimension,
+    dual_Newton_scenarios.c:99-107)."""
+    nk = np.asarray(prob.nk)
+    _, stage, _ = tree_tables(nk)
+    Ns, Nh, md = int((nk == 0).sum()), int(stage.max()), int(nk[0])
+    Nr = 0
+    for k in range(len(nk)):
+        if nk[k] > 1:
+            Nr = int(stage[k]) + 1
+        else:
+            break
+    nu = int(prob.nu[0])
+    nl = -1 if Ns == 1 else (Nr * Ns - (Ns - 1) // (md - 1)) * nu
+    return Ns, Nh, Nr, md, nl
