@@ -38,8 +38,9 @@ _X0B = [0.3, 0.5, -0.4, 0.2]
 def sdunes_cases():
     """SDUNES parity cases (x0 eliminated).  The reference's SDUNES does not converge once state
     bounds make the scenario Hessians singular (measured: 100 iterations on every such probe), so
-    the converging cases bound the inputs; `*_tight_maxit3` pins the first iterations of such a
-    degenerate path instead (regularised blocks, 40-51 line-search trials per iteration)."""
+    the converging cases bound the inputs.  (On those degenerate paths the reference produces
+    directions of magnitude 1e17 out of regularised singular systems: the outcome is rounding
+    noise, there is nothing to pin.)"""
     E = P.eliminate_x0
     yield "spring_mass_cfg1", E(P.spring_mass(3, 2, 10)), {}
     yield "spring_mass_cfg2", E(P.spring_mass(3, 4, 20)), {}
@@ -49,7 +50,10 @@ def sdunes_cases():
     yield "linear_chain_nm8_md4", _ubox(P.linear_chain(8, 7, 4, 2, 20, seed=2), 0.3, 1e12), {}
     yield "linear_chain_md2_Nr3", _ubox(P.linear_chain(2, 1, 2, 3, 10, seed=1), 0.3, 1e12), {}
     yield "linear_chain_md3_Nr3", _ubox(P.linear_chain(3, 2, 3, 3, 12, seed=2), 0.3, 1e12), dict(regType=1)
-    yield "spring_mass_tight_maxit3", E(P.spring_mass(3, 2, 10, xmax1=0.2)), dict(maxIter=3)
+    # gamma > 0.5 rejects full Newton steps even on a quadratic: exercises the backtracking.  The
+    # tolerance is 1e-6 because below ~1e-8 the Armijo test compares differences of 1e-16 (noise).
+    yield "linear_chain_u05_ls", _ubox(P.linear_chain(4, 3, 3, 2, 20, seed=4), 0.5, 1e12), dict(lineSearchGamma=0.6, lineSearchBeta=0.7, stationarityTolerance=1e-6)
+    yield "spring_mass_cfg1_ls", E(P.spring_mass(3, 2, 10)), dict(lineSearchGamma=0.55, lineSearchBeta=0.8, stationarityTolerance=1e-6)
 
 
 CASE_NAMES = [c[0] for c in cases()]

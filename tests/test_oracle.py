@@ -64,8 +64,7 @@ def test_port_no_regularisation_on_regular_problem(ref_lib):
 
 # ------------------------------------------------------------------------------- SDUNES port
 def _sd_tol(name):
-    # the degenerate path (singular scenario Hessians, regularised) is only pinned loosely
-    return 1e-5 if name.endswith("maxit3") else 1e-10
+    return 1e-10
 
 
 @pytest.mark.parametrize("name", CS.SDUNES_CASE_NAMES)
@@ -83,7 +82,7 @@ def test_sdunes_port_matches_reference_golden(name):
             assert np.array_equal(s[k] == lo, g[k] == lo) and np.array_equal(s[k] == hi, g[k] == hi)
 
 
-@pytest.mark.parametrize("name", ["spring_mass_cfg1", "linear_chain_u05", "spring_mass_u02_nocache"])
+@pytest.mark.parametrize("name", ["spring_mass_cfg2_u01", "linear_chain_u05", "spring_mass_u02_nocache"])
 def test_sdunes_port_matches_live_reference_with_dual_start(name, ref_lib):
     """non-zero dual start through treeqp_sdunes_set_dual_initialization (scenarios.c:2094)"""
     from treeqp_b200 import problems as P
