@@ -20,6 +20,7 @@
  *   3. tree + QP containers                            (treeqp/utils/tree.h:41-51,
  *                                                       treeqp/src/tree_qp_common.h:43-133)
  *   4. TDUNES options / workspace / solve  -- THE HOT PATH (dual_Newton_tree.h:48-172)
+ *   4b. SDUNES options / workspace / solve               (dual_Newton_scenarios.h:49-163)
  *   5. container helpers (the subset of tree_qp_common.h:139-323 a standalone user needs)
  *   6. additive B200 entry points (device-resident solves, batches of independent QPs)
  */
@@ -317,6 +318,121 @@ return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
                              const treeqp_tdunes_opts_t *opts, treeqp_tdunes_workspace *work);
 
 /* ------------------------------------------------------------------------------------------
+ * 4b. SDUNES: dual Newton strategy on the scenario decomposition (dual_Newton_scenarios.h:49-163)
+ * ---------------------------------------------------------------------------------------- */
+#ifndef TREEQP_SRC_DUAL_NEWTON_SCENARIOS_H_
+
+/* dual_Newton_scenarios.h:49-66 */
+typedef struct treeqp_sdunes_opts_t_
+{
+    int maxIter;
+    int checkLastActiveSet; /* also selects the order of the banded factorisation (reverseCholesky) */
+    double stationarityTolerance;
+    termination_t termCondition;
+    regType_t regType;
+    double regTol;
+    double regValue;
+    int lineSearchMaxIter;
+    double lineSearchGamma;
+    double lineSearchBeta;
+} treeqp_sdunes_opts_t;
+
+/* dual_Newton_scenarios.h:70-139 (PROFILE=0).  Field order is the reference's; on this
+ * implementation the members marked [host] are valid host memory after `create` / `solve` (they
+ * are what the reference's callers read, examples/solve_qp_json.cpp:165-188, 470-471); the other
+ * iterates live in HBM.  sTmpMats holds the device context. */
+typedef struct treeqp_sdunes_workspace_
+{
+    int Ns; /* [host] scenarios */
+    int Nh; /* [host] prediction horizon */
+    int Nr; /* [host] robust horizon */
+    int md; /* [host] realisations */
+
+    int reverseCholesky; /* [host] */
+
+    int **nodeIdx;       /* [host] Ns x (Nh+1) tree node of every scenario node */
+    int **boundsRemoved; /* [host] Ns x (Nh+1) */
+
+    int **xasChanged;
+    int **uasChanged;
+
+    int *commonNodes; /* [host] Ns-1 */
+    double *fvals;    /* [host] Ns (scratch) */
+
+    struct blasfeo_dmat *sJayD;
+    struct blasfeo_dmat *sJayL;
+    struct blasfeo_dmat *sCholJayD;
+    struct blasfeo_dmat *sCholJayL;
+    struct blasfeo_dmat *sUt;
+    struct blasfeo_dmat *sK;
+
+    struct blasfeo_dmat *sTmpMats; /* device context (opaque) */
+    struct blasfeo_dvec *sTmpVecs;
+
+    struct blasfeo_dvec *sResNonAnticip;
+    struct blasfeo_dvec *sRhsNonAnticip;
+    struct blasfeo_dvec *slambda; /* [host] Ns-1 multipliers of the non-anticipativity constraints */
+    struct blasfeo_dvec *sDeltalambda;
+
+    struct blasfeo_dmat **sZbar;
+    struct blasfeo_dmat **sLambdaD;
+    struct blasfeo_dmat **sLambdaL;
+    struct blasfeo_dmat **sCholLambdaD;
+    struct blasfeo_dmat **sCholLambdaL;
+
+    struct blasfeo_dvec *sQ;
+    struct blasfeo_dvec *sR;
+    struct blasfeo_dvec *sq;
+    struct blasfeo_dvec *sr;
+    struct blasfeo_dvec *sQinv;
+    struct blasfeo_dvec *sRinv;
+
+    struct blasfeo_dvec **sQinvCal;
+    struct blasfeo_dvec **sRinvCal;
+
+    struct blasfeo_dvec **sx; /* [host] Ns x Nh scenario states after the last solve */
+    struct blasfeo_dvec **su; /* [host] Ns x Nh scenario inputs */
+    struct blasfeo_dvec **sxas;
+    struct blasfeo_dvec **suas;
+    struct blasfeo_dvec **sxUnc;
+    struct blasfeo_dvec **suUnc;
+
+    struct blasfeo_dvec **sresk;
+    struct blasfeo_dvec **sreskMod;
+    struct blasfeo_dvec **smu; /* [host] Ns x Nh multipliers of the scenario dynamics */
+    struct blasfeo_dvec **sDeltamu;
+
+    struct blasfeo_dvec **sxasPrev;
+    struct blasfeo_dvec **suasPrev;
+    struct blasfeo_dmat **sTmpLambdaD;
+} treeqp_sdunes_workspace;
+
+#endif /* TREEQP_SRC_DUAL_NEWTON_SCENARIOS_H_ */
+
+/* replaces dual_Newton_scenarios.c:66 */
+int treeqp_sdunes_opts_calculate_size(int Nn);
+/* replaces dual_Newton_scenarios.c:73 */
+void treeqp_sdunes_opts_create(int Nn, treeqp_sdunes_opts_t *opts, void *ptr);
+/* replaces dual_Newton_scenarios.c:80 (same defaults) */
+void treeqp_sdunes_opts_set_default(int Nn, treeqp_sdunes_opts_t *opts);
+/* replaces dual_Newton_scenarios.c:1495: HOST bytes the caller must hand to `create` */
+int treeqp_sdunes_calculate_size(tree_qp_in *qp_in, treeqp_sdunes_opts_t *opts);
+/* replaces dual_Newton_scenarios.c:1607: carves the host buffer AND allocates the device arena.
+ * Exits if the QP violates the preconditions of the scenario decomposition (x0 eliminated, uniform
+ * nx/nu, diagonal weights, bounds only, scenarios.c:1498-1504). */
+void treeqp_sdunes_create(tree_qp_in *qp_in, treeqp_sdunes_opts_t *opts, treeqp_sdunes_workspace *work,
+                          void *ptr);
+/* replaces dual_Newton_scenarios.c:99 */
+int treeqp_sdunes_calculate_dual_dimension(int Nr, int md, int nu);
+/* replaces dual_Newton_scenarios.c:2094: lam over the scenario pairs, mu over (scenario, stage) */
+void treeqp_sdunes_set_dual_initialization(double *lam, double *mu, treeqp_sdunes_workspace *work);
+/* replaces dual_Newton_scenarios.c:1850.  Host buffers in, host buffers out; the whole Newton loop
+ * is one persistent kernel.  Returns 0 / 1 like the reference, TREEQP_UNKNOWN_ERROR on a CUDA
+ * failure.  No CPU fallback. */
+return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdunes_opts_t *opts,
+                             treeqp_sdunes_workspace *work);
+
+/* ------------------------------------------------------------------------------------------
  * 5. container helpers (same names and semantics as tree_qp_common.h / utils/tree.h)
  * ---------------------------------------------------------------------------------------- */
 int calculate_number_of_nodes(int md, int Nr, int Nh);                /* utils/tree.c:36  */
@@ -419,6 +535,19 @@ return_t treeqp_tdunes_solve_batch(treeqp_tdunes_batch *batch, const tree_qp_in 
                                    tree_qp_out *const *qp_out, return_t *status);
 void treeqp_tdunes_batch_get_stats(const treeqp_tdunes_batch *batch, treeqp_b200_stats *stats);
 void treeqp_tdunes_batch_destroy(treeqp_tdunes_batch *batch);
+
+/* SDUNES: same additive protocol as TDUNES (destroy, statistics, device-resident solves) */
+void treeqp_sdunes_destroy(treeqp_sdunes_workspace *work);
+void treeqp_sdunes_get_stats(const treeqp_sdunes_workspace *work, treeqp_b200_stats *stats);
+return_t treeqp_sdunes_upload(tree_qp_in *qp_in, treeqp_sdunes_opts_t *opts, treeqp_sdunes_workspace *work);
+return_t treeqp_sdunes_solve_resident(treeqp_sdunes_opts_t *opts, treeqp_sdunes_workspace *work);
+return_t treeqp_sdunes_download(tree_qp_out *qp_out, treeqp_sdunes_workspace *work);
+/* the SDUNES solve is ONE persistent kernel; treeqp_b200_stats.kernel_ms[k] then holds the time
+ * spent in phase k of that kernel (device globaltimer), named by treeqp_sdunes_phase_name */
+int treeqp_sdunes_num_phases(void);
+const char *treeqp_sdunes_phase_name(int k);
+/* scenario duals after the last solve: lam [dual dimension], mu [Ns*Nh*nx] */
+void treeqp_sdunes_get_duals(double *lam, double *mu, const treeqp_sdunes_workspace *work);
 
 /* per-launch CUDA-event timing of every kernel class (adds two event records per launch);
  * off by default, also switched on by the environment variable TREEQP_B200_PROFILE=1 */

@@ -275,6 +275,9 @@ class TreeQpLib:
             L.treeqp_sdunes_download.restype = C.c_int
             L.treeqp_sdunes_get_duals.argtypes = [c_double_p, c_double_p, vp]
             L.treeqp_sdunes_get_duals.restype = None
+            L.treeqp_sdunes_num_phases.restype = C.c_int
+            L.treeqp_sdunes_phase_name.argtypes = [C.c_int]
+            L.treeqp_sdunes_phase_name.restype = C.c_char_p
 
     # -- small helpers mirroring utils/tree.c
     def multistage_tree(self, md: int, Nr: int, Nh: int) -> np.ndarray:
@@ -284,10 +287,13 @@ class TreeQpLib:
         return nk
 
 
-def stats_dict(lib: "TreeQpLib", st: Stats) -> dict:
+def stats_dict(lib: "TreeQpLib", st: Stats, sdunes: bool = False) -> dict:
     n = min(st.iter, 256)
-    nk = lib.lib.treeqp_b200_num_kernel_classes()
-    kernels = {lib.lib.treeqp_b200_kernel_class_name(k).decode(): (st.kernel_ms[k], st.kernel_count[k])
+    if sdunes:  # phases of the single persistent kernel
+        nk, name = lib.lib.treeqp_sdunes_num_phases(), lib.lib.treeqp_sdunes_phase_name
+    else:
+        nk, name = lib.lib.treeqp_b200_num_kernel_classes(), lib.lib.treeqp_b200_kernel_class_name
+    kernels = {name(k).decode(): (st.kernel_ms[k], st.kernel_count[k])
                for k in range(nk) if st.kernel_count[k] > 0}
     return dict(iter=st.iter, ls_total=st.ls_total, ls_iters=[st.ls_iters[i] for i in range(n)],
                 n_reg=st.n_reg, gpu_ms=st.gpu_ms, h2d_ms=st.h2d_ms, d2h_ms=st.d2h_ms,
@@ -541,7 +547,7 @@ class Sdunes:
     def stats(self) -> dict:
         st = Stats()
         self.lib.lib.treeqp_sdunes_get_stats(self.work.ptr, C.byref(st))
-        return stats_dict(self.lib, st)
+        return stats_dict(self.lib, st, sdunes=True)
 
     def destroy(self):
         if self._alive and self.lib.is_product:

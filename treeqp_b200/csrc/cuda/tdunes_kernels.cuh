@@ -23,8 +23,9 @@
 
 #include "../host/host_internal.h"
 
+#include "warp_helpers.cuh"
+
 #define TQB_RUNNING (-1)
-#define FULL 0xffffffffu
 
 struct View
 {
@@ -47,28 +48,6 @@ struct View
     int abmax, dmax, nxmax, numax;
     tqb_opts o;
 };
-
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ double warp_max(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
-    return v;
-}
-
-/* inclusive clip, lower bound wins when both fire (blasfeo_dveccl_mask, AVX branch,
- * external/blasfeo/auxiliary/d_aux_lib4.c:4412-4417) */
-__device__ __forceinline__ double clip_mask(double v, double lo, double hi, int &mask)
-{
-    const bool up = hi <= v, dn = v <= lo;
-    mask = dn ? -1 : (up ? 1 : 0);
-    return dn ? lo : (up ? hi : v);
-}
 
 __global__ void k_init(View v)
 {
@@ -398,48 +377,6 @@ __global__ void __launch_bounds__(256) k_hessian(View v)
             const int rowsI = rbase[I] >> 16, ii = rbase[I] & 65535, nxk = rstr[I];
             Utp[e] = -(sAB[rowsI * nx + ii + c * nxk] * sP[c]);
         }
-    }
-}
-
-/* ------------------------------------------------------------------------------------------
- * In-shared-memory Cholesky of a d x d block by one warp (left-looking, column by column) with
- * BLASFEO's pivot rule (kernel_dgemm_4x4_lib4.c:4633-4646): pivot>0 ? (l=sqrt,inv=1/l) : (0,0).
- * ---------------------------------------------------------------------------------------- */
-__device__ __forceinline__ void warp_potrf(double *sW, int ld, int d, double *sinv, int lane)
-{
-    for (int j = 0; j < d; j++)
-    {
-        for (int i = j + lane; i < d; i += 32)
-        {
-            double s = sW[i + j * ld];
-            for (int t = 0; t < j; t++) s -= sW[i + t * ld] * sW[j + t * ld];
-            sW[i + j * ld] = s;
-        }
-        __syncwarp();
-        double piv = sW[j + j * ld], inv;
-        if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
-        else { piv = 0.0; inv = 0.0; }
-        __syncwarp();
-        for (int i = j + lane; i < d; i += 32)
-        {
-            if (i == j) { sW[j + j * ld] = piv; sinv[j] = inv; }
-            else sW[i + j * ld] *= inv;
-        }
-        __syncwarp();
-    }
-}
-
-/* y <- L^-T y in shared memory (dtrsv_ltn with the stored inverse diagonal) */
-__device__ __forceinline__ void warp_trsv_ltn(const double *sW, int ld, int d, const double *sinv,
-                                              double *sy, int lane)
-{
-    for (int i = d - 1; i >= 0; i--)
-    {
-        const double yi = sy[i] * sinv[i];
-        __syncwarp();
-        if (lane == 0) sy[i] = yi;
-        for (int t = lane; t < i; t += 32) sy[t] -= sW[i + t * ld] * yi;
-        __syncwarp();
     }
 }
 

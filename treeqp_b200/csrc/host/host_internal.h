@@ -131,6 +131,71 @@ const char *tqb_kernel_class_name(int k);
 int tqb_device_download(tqb_device *d, double *h_out, double *ms);
 const char *tqb_cuda_last_error(void);
 
+
+/* =========================================================================================
+ * SDUNES (dual Newton strategy on the scenario decomposition, dual_Newton_scenarios.c)
+ *
+ * Vocabulary
+ *   scenario   one root-to-leaf path i of the multistage tree (Ns of them, Nh stages each)
+ *   (i,k)      stage k of scenario i: state of tree node nodeIdx[i][k+1], input of node
+ *              nodeIdx[i][k]; all per-(i,k) vectors are stored scenario-major, ik = i*Nh + k
+ *   pair i     neighbouring scenarios (i, i+1): non-anticipativity multiplier lambda_i of
+ *              dimension nu*cn[i] (cn = number of common nodes), stored at lo[i]
+ *   node slot  per-node inputs use uniform slots: element a of node n at n*nx + a (n*nu + a)
+ * ========================================================================================= */
+typedef struct tqb_sd_dims
+{
+    int Nn, Np, Ns, Nh, Nr, md, nx, nu;
+    int nK;              /* nu*Nr: rows of Ut_i, dimension of K_i */
+    int nl;              /* total dimension of lambda */
+    int SK;              /* Ns*Nh */
+    int njd, njl, mJ;    /* doubles in the J diagonal / sub-diagonal blocks, largest J block */
+    int n_int;
+    long long n_in, n_out;
+} tqb_sd_dims;
+
+typedef struct tqb_sd_tables
+{
+    int *nodeIdx, *removed;   /* [Ns*(Nh+1)] tree node of (i,k), bounds-removed flag (scenarios.c:1650-1668) */
+    int *cn;                  /* [Ns] common nodes of pair i (last entry unused) */
+    int *lo, *jdo, *jlo;      /* [Ns+1] offsets of lambda_i / J diagonal block i / J sub-diagonal block i */
+    int *pair_of;             /* [nl] pair owning each lambda element */
+    int *nfirst, *ncount;     /* [Nn] first scenario through a node, number of scenarios through it */
+    int *nstage;              /* [Nn] depth of the node */
+} tqb_sd_tables;
+
+typedef struct tqb_sd_inputs
+{
+    double *A, *B, *b;                       /* node slots: nx*nx, nx*nu, nx */
+    double *Q, *q, *Qinv, *xmin, *xmax;      /* node slots nx (weights un-scaled, scenarios.c:1885-1898) */
+    double *R, *r, *Rinv, *umin, *umax;      /* node slots nu */
+    double *lam0, *mu0;                      /* [nl], [SK*nx] dual start */
+} tqb_sd_inputs;
+
+/* output block (one D2H copy): node results, then the scenario duals and iterates */
+typedef struct tqb_sd_outputs
+{
+    double *x, *u, *lam, *mux, *muu;         /* node slots nx / nu */
+    double *lam_s, *mu_s;                    /* [nl], [SK*nx] */
+    double *xs, *us;                         /* [SK*nx], [SK*nu] scenario iterates */
+} tqb_sd_outputs;
+
+void tqb_sd_layout_tables(const tqb_sd_dims *d, int *base, tqb_sd_tables *t);
+void tqb_sd_layout_inputs(const tqb_sd_dims *d, double *base, tqb_sd_inputs *in);
+void tqb_sd_layout_outputs(const tqb_sd_dims *d, double *base, tqb_sd_outputs *out);
+
+#define TQB_SD_INFO_INTS (8 + 256 + 16) /* status, iter, ls_total, n_reg, 4 spare, trials per iteration, ns per phase */
+#define TQB_SD_NPHASE 10
+
+typedef struct tqb_sd_device tqb_sd_device;
+tqb_sd_device *tqb_sd_device_create(const tqb_sd_dims *dims, const int *h_int);
+void tqb_sd_device_destroy(tqb_sd_device *d);
+int tqb_sd_device_upload(tqb_sd_device *d, const double *h_in, double *ms);
+/* the whole Newton loop in ONE persistent kernel; h_info is pinned [TQB_SD_INFO_INTS] */
+int tqb_sd_device_solve(tqb_sd_device *d, const tqb_opts *o, int reverse, int *h_info, double *gpu_ms,
+                        long long *launches);
+int tqb_sd_device_download(tqb_sd_device *d, double *h_out, double *ms);
+
 #ifdef __cplusplus
 }
 #endif
