@@ -120,3 +120,44 @@ def test_large_tree_properties(product_lib):
     assert np.array_equal(a.x, b.x) and np.array_equal(a.lam, b.lam)
     assert np.all(a.u <= prob.umax) and np.all(a.u >= prob.umin)
     assert np.all(a.mu_u[a.u == prob.umax] >= 0) and np.all(a.mu_u[a.u == prob.umin] <= 0)
+
+
+def test_batch_matches_individual_solves(product_lib):
+    """treeqp_tdunes_solve_batch (config-4 shape: independent linear_chain MPC QPs that differ in
+    x0) returns, per QP, exactly what treeqp_tdunes_solve returns for that QP alone"""
+    probs = P.linear_chain_batch(12, seed=3)
+    singles = [capi.solve_tdunes(product_lib, p) for p in probs]
+    qp_ins = [capi.QpIn(product_lib, p) for p in probs]
+    qp_outs = [capi.QpOut(product_lib, p) for p in probs]
+    batch = capi.TdunesBatch(product_lib, qp_ins)
+    assert batch.solve(qp_outs) == capi.TREEQP_OK
+    assert len(set(s.iter for s in singles)) > 1, "the instances should need different iteration counts"
+    for i, (s, o) in enumerate(zip(singles, qp_outs)):
+        assert batch.status[i] == s.status == 0
+        assert o.iter == s.iter
+        assert np.array_equal(o.x, s.x) and np.array_equal(o.u, s.u) and np.array_equal(o.lam, s.lam), i
+        assert np.array_equal(o.mu_x, s.mu_x) and np.array_equal(o.mu_u, s.mu_u), i
+    g = CS.golden("linear_chain_cfg4")   # seed 0 instance against the reference golden
+    p0 = P.linear_chain_batch(1, seed=0, x0_kick=1.5, ubound=2.0, xbound=2.0)[0]
+    qi, qo = capi.QpIn(product_lib, p0), capi.QpOut(product_lib, p0)
+    b1 = capi.TdunesBatch(product_lib, [qi])
+    assert b1.solve([qo]) == capi.TREEQP_OK and qo.iter == int(g["iter"])
+    assert CS.rel_err(qo.x, g["x"]) < TOL and CS.rel_err(qo.lam, g["lam"]) < TOL
+    batch.destroy(); b1.destroy()
+
+
+def test_batch_mixed_shapes_and_warm_start(product_lib):
+    """a forest may mix tree shapes; per-QP dual starts are honoured"""
+    probs = [CS.get_case("spring_mass_cfg1")[0], CS.get_case("random_vary_dims")[0], CS.get_case("linear_chain_cfg4")[0]]
+    singles = [capi.solve_tdunes(product_lib, p, maxIter=200) for p in probs]
+    qp_ins = [capi.QpIn(product_lib, p) for p in probs]
+    qp_outs = [capi.QpOut(product_lib, p) for p in probs]
+    batch = capi.TdunesBatch(product_lib, qp_ins, maxIter=200)
+    assert batch.solve(qp_outs) == capi.TREEQP_OK
+    for s, o in zip(singles, qp_outs):
+        assert o.iter == s.iter and CS.rel_err(o.x, s.x) < 1e-12 and CS.rel_err(o.lam, s.lam) < 1e-12
+    for i, s in enumerate(singles):
+        batch.set_dual_initialization(i, s.lam)
+    assert batch.solve(qp_outs) == capi.TREEQP_OK
+    assert all(o.iter == 0 for o in qp_outs)
+    batch.destroy()

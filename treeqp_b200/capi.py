@@ -19,7 +19,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(_HERE, "lib", "libtreeqp_b200.so")
+PRODUCT_LIB = os.environ.get("TREEQP_B200_LIB", os.path.join(_HERE, "lib", "libtreeqp_b200.so"))
 
 c_int_p = C.POINTER(C.c_int)
 c_double_p = C.POINTER(C.c_double)
@@ -489,6 +489,66 @@ def solve_tdunes(lib: TreeQpLib, prob: Problem, lam0: Optional[np.ndarray] = Non
                    stats=solver.stats() if lib.is_product else None)
     solver.destroy()
     return sol
+
+
+class TdunesBatch:
+    """Batch of independent tree QPs solved as one forest (additive API of include/treeqp_b200.h:
+    treeqp_tdunes_batch_*): every kernel launch covers the same tree level of all QPs."""
+
+    def __init__(self, lib: TreeQpLib, qp_ins, **opt_overrides):
+        assert lib.is_product
+        self.lib, self.qp_ins, self.n = lib, list(qp_ins), len(qp_ins)
+        L = lib.lib
+        Nn = max(q.prob.Nn for q in self.qp_ins)
+        self.opts = TdunesOpts()
+        self.opts_mem = _Buf(max(L.treeqp_tdunes_opts_calculate_size(Nn), 8))
+        L.treeqp_tdunes_opts_create(Nn, C.byref(self.opts), self.opts_mem.ptr)
+        L.treeqp_tdunes_opts_set_default(Nn, C.byref(self.opts))
+        for k, v in opt_overrides.items():
+            assert hasattr(self.opts, k), k
+            setattr(self.opts, k, v)
+        self.in_ptrs = (C.c_void_p * self.n)(*[q.ptr.value for q in self.qp_ins])
+        self.handle = C.c_void_p(L.treeqp_tdunes_batch_create(self.n, self.in_ptrs, C.byref(self.opts)))
+        if not self.handle.value:
+            raise RuntimeError("treeqp_tdunes_batch_create failed (no CUDA device?)")
+        self.status = np.zeros(self.n, dtype=np.int32)
+
+    def set_dual_initialization(self, i: int, lam0: np.ndarray):
+        lam0 = _f64(lam0)
+        self.lib.lib.treeqp_tdunes_batch_set_dual_initialization(self.handle, i, _dp(lam0))
+
+    def upload(self) -> int:
+        return int(self.lib.lib.treeqp_tdunes_batch_upload(self.handle, self.in_ptrs))
+
+    def solve_resident(self) -> int:
+        return int(self.lib.lib.treeqp_tdunes_batch_solve_resident(self.handle, _ip(self.status)))
+
+    def _out_ptrs(self, qp_outs):
+        return (C.c_void_p * self.n)(*[q.ptr.value for q in qp_outs])
+
+    def download(self, qp_outs) -> int:
+        return int(self.lib.lib.treeqp_tdunes_batch_download(self.handle, self._out_ptrs(qp_outs)))
+
+    def solve(self, qp_outs) -> int:
+        """treeqp_tdunes_solve_batch: host buffers in, host buffers out"""
+        return int(self.lib.lib.treeqp_tdunes_solve_batch(self.handle, self.in_ptrs, self._out_ptrs(qp_outs),
+                                                          _ip(self.status)))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.lib.lib.treeqp_tdunes_batch_get_stats(self.handle, C.byref(st))
+        return stats_dict(self.lib, st)
+
+    def destroy(self):
+        if self.handle and self.handle.value:
+            self.lib.lib.treeqp_tdunes_batch_destroy(self.handle)
+            self.handle = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
 
 
 class Sdunes:

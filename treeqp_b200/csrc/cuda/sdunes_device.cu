@@ -64,6 +64,8 @@ struct SdView
     tqb_opts o;
     int reverse;                      /* reverseCholesky = checkLastActiveSet (scenarios.c:1922) */
     int per_warp;                     /* doubles of shared-memory scratch per warp */
+    double *jarena;                   /* operands of the J chain when they do not fit in shared memory */
+    int jay_in_smem;
 };
 
 struct Team
@@ -256,105 +258,116 @@ __device__ double sd_build(const SdView &v, const Team &tm)
     return part;
 }
 
-__device__ __forceinline__ void warp_load_mat(double *dst, int ld, const double *src, int n, int lane)
+/* ---- asynchronous global -> shared staging (LDGSTS): the next block of a serial chain is in
+ * flight while the current one is factorised, so the L2 latency leaves the dependent chain ---- */
+__device__ __forceinline__ void cp_async8(double *dst_smem, const double *src)
+{
+    const unsigned d = (unsigned) __cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void warp_fetch_mat(double *dst, int ld, const double *src, int n, int lane)
 {
     for (int e = lane; e < n * n; e += 32)
     {
         const int b = e / n, a = e - b * n;
-        dst[a + b * ld] = src[e];
+        cp_async8(dst + a + b * ld, src + e);
     }
 }
 
 struct WarpScratch
 {
-    double *sD, *sD0, *sL, *sinv, *sy, *sz, *tA, *tB;
+    double *bD0, *bL0, *sD0, *binv0, *bvec0, *sz, *tA, *tB;
+    int ms, vs; /* strides between the two buffers of a pair (matrix / vector) */
+    __device__ __forceinline__ double *bD(int q) const { return bD0 + q * ms; }
+    __device__ __forceinline__ double *bL(int q) const { return bL0 + q * ms; }
+    __device__ __forceinline__ double *binv(int q) const { return binv0 + q * vs; }
+    __device__ __forceinline__ double *bvec(int q) const { return bvec0 + q * vs; }
 };
+
+__host__ __device__ inline size_t sd_per_warp_doubles(int nx, int nK)
+{
+    const size_t ld = nx | 1;
+    const size_t n = 5 * (size_t) nx * ld + 5 * (size_t) nx + 2 * (size_t) nK * nx;
+    return (n + 1) / 2 * 2;
+}
 
 __device__ __forceinline__ WarpScratch warp_scratch(const SdView &v, double *base)
 {
     const int nx = v.d.nx, ld = nx | 1;
     WarpScratch s;
-    s.sD = base; s.sD0 = s.sD + nx * ld; s.sL = s.sD0 + nx * ld;
-    s.sinv = s.sL + nx * ld; s.sy = s.sinv + nx; s.sz = s.sy + nx;
+    s.ms = nx * ld; s.vs = nx;
+    s.bD0 = base; s.bL0 = s.bD0 + 2 * s.ms;
+    s.sD0 = s.bL0 + 2 * s.ms;
+    s.binv0 = s.sD0 + s.ms;
+    s.bvec0 = s.binv0 + 2 * nx;
+    s.sz = s.bvec0 + 2 * nx;
     s.tA = s.sz + nx; s.tB = s.tA + v.d.nK * nx;
     return s;
 }
 
 /* banded substitution with the factor of Lambda_i (scenarios.c:893-958 and :1129-1188):
- * out = Lambda_i^-1 rhs.  mode 0: rhs = res_i; mode 1: rhs = -res_i + Zbar*(dlam_{i-1} - dlam_i). */
-__device__ void sd_banded_solve(const SdView &v, int i, int mode, double *out_vec, const WarpScratch &S, int lane)
+ * out = Lambda_i^-1 in (in may alias out).  One element per lane (nx <= 32); the factor blocks of
+ * the next stage are prefetched while the current stage is substituted. */
+__device__ void sd_banded_solve(const SdView &v, int i, const double *in_vec, double *out_vec, const WarpScratch &S, int lane)
 {
-    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, Ns = v.d.Ns, Nr = v.d.Nr, nxx = nx * nx, ld = nx | 1;
+    const int nx = v.d.nx, Nh = v.d.Nh, nxx = nx * nx, ld = nx | 1;
     const size_t ik0 = (size_t) i * Nh;
-    for (int s = 0; s < Nh; s++)
-    {   /* L-solves in factorisation order */
-        const int k = v.reverse ? Nh - 1 - s : s;
-        warp_load_mat(S.sD, ld, v.CLD + (ik0 + k) * nxx, nx, lane);
-        for (int a = lane; a < nx; a += 32) S.sinv[a] = v.CLDi[(ik0 + k) * nx + a];
-        if (s > 0) warp_load_mat(S.sL, ld, v.CLL + (ik0 + (v.reverse ? k : k - 1)) * nxx, nx, lane);
-        __syncwarp();
-        for (int a = lane; a < nx; a += 32)
+    for (int phase = 0; phase < 2; phase++)
+    {   /* phase 0: L-solves in factorisation order; phase 1: L'-solves in the opposite order */
+        const bool down = (phase == 0) == (v.reverse != 0); /* stage index decreasing */
+#define SD_K(s_) (down ? Nh - 1 - (s_) : (s_))
+#define SD_FETCH(s_)                                                                              \
+        do {                                                                                      \
+            const int k_ = SD_K(s_), q_ = (s_) & 1;                                               \
+            warp_fetch_mat(S.bD(q_), ld, v.CLD + (ik0 + k_) * nxx, nx, lane);                     \
+            if (lane < nx) cp_async8(S.binv(q_) + lane, v.CLDi + (ik0 + k_) * nx + lane);         \
+            if ((s_) > 0)                                                                         \
+            {   /* sub-diagonal block linking this stage with the previous one of the sweep */    \
+                const int kl_ = down ? k_ : k_ - 1;                                               \
+                warp_fetch_mat(S.bL(q_), ld, v.CLL + (ik0 + kl_) * nxx, nx, lane);                \
+            }                                                                                     \
+            if (phase == 0 || (s_) > 0)                                                           \
+            {                                                                                     \
+                const double *src_ = phase == 0 ? in_vec : out_vec;                               \
+                if (lane < nx) cp_async8(S.bvec(q_) + lane, src_ + k_ * nx + lane);               \
+            }                                                                                     \
+            cp_async_commit();                                                                    \
+        } while (0)
+        SD_FETCH(0);
+        for (int s = 0; s < Nh; s++)
         {
-            double val;
-            const double r = v.res[(ik0 + k) * nx + a];
-            if (mode == 0) val = r;
-            else if (k < Nr)
+            const int k = SD_K(s), q = s & 1;
+            cp_async_wait_all();
+            __syncwarp();
+            if (s + 1 < Nh) SD_FETCH(s + 1);
+            const double *sD = S.bD(q), *sL = S.bL(q);
+            double y = 0.0, inv = 0.0;
+            if (lane < nx)
             {
-                const double *Z = v.Zbar + (ik0 + k) * nx * nu;
-                double t = 0.0;
-                for (int c = 0; c < nu; c++)
+                inv = S.binv(q)[lane];
+                y = (phase == 1 && s == 0) ? S.sz[lane] : S.bvec(q)[lane];
+                if (s > 0)
                 {
-                    double vv = 0.0;
-                    if (i > 0 && k < v.T.cn[i - 1]) vv = vv + v.dlam[v.T.lo[i - 1] + k * nu + c];
-                    if (i < Ns - 1 && k < v.T.cn[i]) vv = vv - v.dlam[v.T.lo[i] + k * nu + c];
-                    t += Z[a + c * nx] * vv;
+                    double t = 0.0;
+                    if (phase == 0) for (int c = 0; c < nx; c++) t += sL[lane + c * ld] * S.sz[c];
+                    else for (int c = 0; c < nx; c++) t += sL[c + lane * ld] * S.sz[c];
+                    y = y - t;
                 }
-                val = -r + t;
             }
-            else val = 0.0 - r;
-            if (s > 0)
+            y = phase == 0 ? warp_trsv_lnn32(sD, ld, nx, inv, y, lane) : warp_trsv_ltn32(sD, ld, nx, inv, y, lane);
+            __syncwarp();
+            if (lane < nx)
             {
-                double t = 0.0;
-                for (int c = 0; c < nx; c++) t += S.sL[a + c * ld] * S.sz[c];
-                val = val - t;
+                S.sz[lane] = y;
+                out_vec[k * nx + lane] = y;
             }
-            S.sy[a] = val;
+            __syncwarp();
         }
-        __syncwarp();
-        warp_trsv_lnn(S.sD, ld, nx, S.sinv, S.sy, lane);
-        for (int a = lane; a < nx; a += 32)
-        {
-            S.sz[a] = S.sy[a];
-            out_vec[k * nx + a] = S.sy[a];
-        }
-        __syncwarp();
-    }
-    for (int s = 0; s < Nh; s++)
-    {   /* L'-solves in the opposite order */
-        const int k = v.reverse ? s : Nh - 1 - s;
-        warp_load_mat(S.sD, ld, v.CLD + (ik0 + k) * nxx, nx, lane);
-        for (int a = lane; a < nx; a += 32) S.sinv[a] = v.CLDi[(ik0 + k) * nx + a];
-        if (s > 0) warp_load_mat(S.sL, ld, v.CLL + (ik0 + (v.reverse ? k - 1 : k)) * nxx, nx, lane);
-        __syncwarp();
-        for (int a = lane; a < nx; a += 32)
-        {
-            double val = out_vec[k * nx + a];
-            if (s > 0)
-            {
-                double t = 0.0;
-                for (int c = 0; c < nx; c++) t += S.sL[c + a * ld] * S.sz[c];
-                val = val - t;
-            }
-            S.sy[a] = val;
-        }
-        __syncwarp();
-        warp_trsv_ltn(S.sD, ld, nx, S.sinv, S.sy, lane);
-        for (int a = lane; a < nx; a += 32)
-        {
-            S.sz[a] = S.sy[a];
-            out_vec[k * nx + a] = S.sy[a];
-        }
-        __syncwarp();
+#undef SD_FETCH
+#undef SD_K
     }
 }
 
@@ -366,57 +379,66 @@ __device__ void sd_banded_solve(const SdView &v, int i, int mode, double *out_ve
  * ---------------------------------------------------------------------------------------- */
 __device__ void sd_factor_scenario(const SdView &v, int i, const WarpScratch &S, int lane)
 {
-    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, Nr = v.d.Nr, nK = v.d.nK, nxx = nx * nx, ld = nx | 1;
+    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, nK = v.d.nK, nxx = nx * nx, ld = nx | 1;
     const size_t ik0 = (size_t) i * Nh;
+    double *sinv = S.binv(0);
     int nreg = 0;
+#define SD_FETCH(s_)                                                                              \
+    do {                                                                                          \
+        const int k_ = v.reverse ? Nh - 1 - (s_) : (s_), q_ = (s_) & 1;                           \
+        warp_fetch_mat(S.bD(q_), ld, v.LD + (ik0 + k_) * nxx, nx, lane);                          \
+        if ((s_) < Nh - 1) warp_fetch_mat(S.bL(q_), ld, v.LL + (ik0 + (v.reverse ? k_ - 1 : k_)) * nxx, nx, lane); \
+        cp_async_commit();                                                                        \
+    } while (0)
+    SD_FETCH(0);
     for (int s = 0; s < Nh; s++)
     {
-        const int k = v.reverse ? Nh - 1 - s : s;
-        if (s == 0) warp_load_mat(S.sD, ld, v.LD + (ik0 + k) * nxx, nx, lane);
+        const int k = v.reverse ? Nh - 1 - s : s, q = s & 1;
+        double *sD = S.bD(q), *sL = S.bL(q);
+        cp_async_wait_all();
         __syncwarp();
-        nreg += warp_potrf_reg(S.sD, S.sD0, ld, nx, S.sinv, lane, v.o.regType, v.o.regTol, v.o.regValue);
+        if (s > 0)
+        {   /* LambdaD -= CholLambdaL CholLambdaL' of the previous stage (dsyrk_ln) */
+            const double *sLp = S.bL(q ^ 1);
+            for (int e = lane; e < nxx; e += 32)
+            {
+                const int b = e / nx, a = e - b * nx;
+                if (a < b) continue;
+                double t = 0.0;
+                for (int c = 0; c < nx; c++) t += sLp[a + c * ld] * sLp[b + c * ld];
+                sD[a + b * ld] -= t;
+            }
+            __syncwarp();
+        }
+        if (s + 1 < Nh) SD_FETCH(s + 1);
+        nreg += warp_potrf_reg(sD, S.sD0, ld, nx, sinv, lane, v.o.regType, v.o.regTol, v.o.regValue);
         for (int e = lane; e < nxx; e += 32)
         {
             const int b = e / nx, a = e - b * nx;
-            v.CLD[(ik0 + k) * nxx + e] = S.sD[a + b * ld];
+            v.CLD[(ik0 + k) * nxx + e] = sD[a + b * ld];
         }
-        for (int a = lane; a < nx; a += 32) v.CLDi[(ik0 + k) * nx + a] = S.sinv[a];
+        if (lane < nx) v.CLDi[(ik0 + k) * nx + lane] = sinv[lane];
         if (s < Nh - 1)
         {
-            const int kl = v.reverse ? k - 1 : k, kn = v.reverse ? k - 1 : k + 1;
-            warp_load_mat(S.sL, ld, v.LL + (ik0 + kl) * nxx, nx, lane);
-            __syncwarp();
+            const int kl = v.reverse ? k - 1 : k;
             /* CholLambdaL = LambdaL CholLambdaD^-T (dtrsm_rltn): one row per lane */
-            for (int r = lane; r < nx; r += 32)
+            if (lane < nx)
                 for (int j = 0; j < nx; j++)
                 {
-                    double t = S.sL[r + j * ld];
-                    for (int c = 0; c < j; c++) t -= S.sL[r + c * ld] * S.sD[j + c * ld];
-                    S.sL[r + j * ld] = t * S.sinv[j];
+                    double t = sL[lane + j * ld];
+                    for (int c = 0; c < j; c++) t -= sL[lane + c * ld] * sD[j + c * ld];
+                    sL[lane + j * ld] = t * sinv[j];
                 }
             __syncwarp();
             for (int e = lane; e < nxx; e += 32)
             {
                 const int b = e / nx, a = e - b * nx;
-                v.CLL[(ik0 + kl) * nxx + e] = S.sL[a + b * ld];
-            }
-            __syncwarp();
-            /* next diagonal block: LambdaD -= CholLambdaL CholLambdaL' (dsyrk_ln) */
-            for (int e = lane; e < nxx; e += 32)
-            {
-                const int b = e / nx, a = e - b * nx;
-                double val = v.LD[(ik0 + kn) * nxx + e];
-                if (a >= b)
-                {
-                    double t = 0.0;
-                    for (int c = 0; c < nx; c++) t += S.sL[a + c * ld] * S.sL[b + c * ld];
-                    val -= t;
-                }
-                S.sD[a + b * ld] = val;
+                v.CLL[(ik0 + kl) * nxx + e] = sL[a + b * ld];
             }
         }
         __syncwarp();
     }
+#undef SD_FETCH
     if (nreg > 0 && lane == 0) atomicAdd(&v.info[3], nreg);
 
     /* Ut_i: row r = j*nu + c of block row j starts from Zbar[j]' at stage j and is propagated
@@ -468,100 +490,147 @@ __device__ void sd_factor_scenario(const SdView &v, int i, const WarpScratch &S,
         if (a == b) val += v.Rc[(ik0 + ja) * nu + (a - ja * nu)];
         K[a + b * nK] = val;
     }
-    (void) Nr;
-    sd_banded_solve(v, i, 0, v.resMod + ik0 * nx, S, lane);
+    sd_banded_solve(v, i, v.res + ik0 * nx, v.resMod + ik0 * nx, S, lane);
 }
 
 /* ------------------------------------------------------------------------------------------
- * The non-anticipativity system (one warp; a serial block-tridiagonal recursion over the
- * scenario pairs): J_i = K_i + K_{i+1} restricted to the common inputs, sub-diagonal -K_{i+1};
- * Cholesky merged with the forward substitution, then the backward substitution.
- * (form_and_factorize_Jay :795-868, form_RHS_non_anticipaticity :960-1000, calculate_delta_lambda :1004-1074)
+ * The non-anticipativity system: J_i = K_i + K_{i+1} restricted to the common inputs, sub-diagonal
+ * -K_{i+1}: a serial block-tridiagonal recursion over the scenario pairs
+ * (form_and_factorize_Jay :795-868, form_RHS_non_anticipaticity :960-1000, calculate_delta_lambda :1004-1074).
+ * All operands are first gathered into one arena (shared memory of CTA 0 when they fit, else HBM)
+ * by every warp of the CTA; then ONE warp walks the chain without touching L2: Cholesky merged with
+ * the forward substitution, then the backward substitution.
  * ---------------------------------------------------------------------------------------- */
-__device__ void sd_jay_chain(const SdView &v, double *sm, int lane)
+struct JayArena
 {
-    const int nu = v.d.nu, nx = v.d.nx, Ns = v.d.Ns, Nh = v.d.Nh, nK = v.d.nK, m = v.d.mJ, ld = m | 1;
-    double *sJ = sm, *sJ0 = sJ + m * ld, *sJL = sJ0 + m * ld, *sCar = sJL + m * ld;
-    double *sinv = sCar + m * ld, *sy = sinv + m, *scv = sy + m;
-    for (int e = lane; e < v.d.nl; e += 32)
+    double *JD0, *JD1, *JL, *rhs, *inv, *car, *w0, *scv, *sy;
+    int *cn, *lo, *jdo, *jlo;
+};
+
+__host__ __device__ inline size_t sd_pad2(size_t n) { return (n + 1) / 2 * 2; }
+__host__ __device__ inline size_t sd_jay_doubles(const tqb_sd_dims &d)
+{
+    const size_t m = d.mJ > 0 ? d.mJ : 1;
+    return 2 * sd_pad2(d.njd) + sd_pad2(d.njl) + 2 * sd_pad2(d.nl) + 2 * sd_pad2(m * m) + 2 * sd_pad2(m) + 2 * (size_t) (d.Ns + 1) + 2;
+}
+__device__ __forceinline__ JayArena jay_arena(const SdView &v, double *base)
+{
+    const size_t m = v.d.mJ > 0 ? v.d.mJ : 1;
+    JayArena a;
+    a.JD0 = base; a.JD1 = a.JD0 + sd_pad2(v.d.njd); a.JL = a.JD1 + sd_pad2(v.d.njd);
+    a.rhs = a.JL + sd_pad2(v.d.njl); a.inv = a.rhs + sd_pad2(v.d.nl);
+    a.car = a.inv + sd_pad2(v.d.nl); a.w0 = a.car + sd_pad2(m * m);
+    a.scv = a.w0 + sd_pad2(m * m); a.sy = a.scv + sd_pad2(m);
+    a.cn = (int *) (a.sy + sd_pad2(m)); a.lo = a.cn + (v.d.Ns + 1); a.jdo = a.lo + (v.d.Ns + 1); a.jlo = a.jdo + (v.d.Ns + 1);
+    return a;
+}
+
+/* gather phase: every warp of CTA 0, one scenario pair per warp */
+__device__ void sd_jay_gather(const SdView &v, const JayArena &A, const Team &tm)
+{
+    const int nu = v.d.nu, nx = v.d.nx, Ns = v.d.Ns, Nh = v.d.Nh, nK = v.d.nK, lane = tm.lane;
+    for (int e = threadIdx.x; e < Ns + 1; e += blockDim.x)
     {
-        const int i = v.T.pair_of[e], le = e - v.T.lo[i], k = le / nu, c = le - k * nu;
-        double s = v.resNA[e], t = 0.0;
-        const double *Z = v.Zbar + (size_t) (i * Nh + k) * nx * nu, *rm = v.resMod + (size_t) (i * Nh + k) * nx;
-        for (int a = 0; a < nx; a++) t += Z[a + c * nx] * rm[a];
-        s = s - t;
-        Z = v.Zbar + (size_t) ((i + 1) * Nh + k) * nx * nu;
-        rm = v.resMod + (size_t) ((i + 1) * Nh + k) * nx;
-        t = 0.0;
-        for (int a = 0; a < nx; a++) t += Z[a + c * nx] * rm[a];
-        s = s + t;
-        v.rhsNA[e] = s;
+        A.cn[e] = e < Ns ? v.T.cn[e] : 0;
+        A.lo[e] = v.T.lo[e]; A.jdo[e] = v.T.jdo[e]; A.jlo[e] = v.T.jlo[e];
     }
-    __syncwarp();
-    int nreg = 0;
-    for (int i = 0; i < Ns - 1; i++)
+    for (int i = tm.wib; i < Ns - 1; i += tm.wpb)
     {
-        const int dim = nu * v.T.cn[i], lo = v.T.lo[i];
+        const int dim = nu * v.T.cn[i], lo = v.T.lo[i], jdo = v.T.jdo[i];
         const double *K0 = v.K + (size_t) i * nK * nK, *K1 = K0 + nK * nK;
         for (int e = lane; e < dim * dim; e += 32)
         {
             const int b = e / dim, a = e - b * dim;
-            double val = (i > 0 && a >= b) ? sCar[a + b * ld] : 0.0;
-            val += K0[a + b * nK];
-            val += K1[a + b * nK];
-            sJ[a + b * ld] = val;
+            A.JD0[jdo + e] = K0[a + b * nK];
+            A.JD1[jdo + e] = K1[a + b * nK];
+        }
+        if (i < Ns - 2)
+        {
+            const int dimN = nu * v.T.cn[i + 1], jlo = v.T.jlo[i];
+            for (int e = lane; e < dimN * dim; e += 32)
+            {
+                const int b = e / dimN, a = e - b * dimN;
+                A.JL[jlo + e] = 0.0 + -1.0 * K1[a + b * nK];
+            }
         }
         for (int e = lane; e < dim; e += 32)
-        {
-            double rhs = v.rhsNA[lo + e];
-            if (i > 0) rhs = rhs + scv[e];
-            sy[e] = -1.0 * rhs;
+        {   /* right-hand side (scenarios.c:960-1000) */
+            const int k = e / nu, c = e - k * nu;
+            double s = v.resNA[lo + e], t = 0.0;
+            const double *Z = v.Zbar + (size_t) (i * Nh + k) * nx * nu, *rm = v.resMod + (size_t) (i * Nh + k) * nx;
+            for (int a = 0; a < nx; a++) t += Z[a + c * nx] * rm[a];
+            s = s - t;
+            Z = v.Zbar + (size_t) ((i + 1) * Nh + k) * nx * nu;
+            rm = v.resMod + (size_t) ((i + 1) * Nh + k) * nx;
+            t = 0.0;
+            for (int a = 0; a < nx; a++) t += Z[a + c * nx] * rm[a];
+            s = s + t;
+            A.rhs[lo + e] = s;
         }
-        __syncwarp();
-        nreg += warp_potrf_reg(sJ, sJ0, ld, dim, sinv, lane, v.o.regType, v.o.regTol, v.o.regValue);
+    }
+}
+
+__device__ void sd_jay_chain(const SdView &v, const JayArena &A, int lane)
+{
+    const int nu = v.d.nu, Ns = v.d.Ns;
+    int nreg = 0;
+    for (int i = 0; i < Ns - 1; i++)
+    {
+        const int dim = nu * A.cn[i], lo = A.lo[i];
+        double *W = A.JD0 + A.jdo[i];
+        const double *W1 = A.JD1 + A.jdo[i];
         for (int e = lane; e < dim * dim; e += 32)
         {
             const int b = e / dim, a = e - b * dim;
-            v.CJD[v.T.jdo[i] + e] = sJ[a + b * ld];
+            double val = (i > 0 && a >= b) ? A.car[e] : 0.0;
+            val += W[e];
+            val += W1[e];
+            W[e] = val;
         }
-        for (int e = lane; e < dim; e += 32) v.CJDi[lo + e] = sinv[e];
-        warp_trsv_lnn(sJ, ld, dim, sinv, sy, lane);
-        for (int e = lane; e < dim; e += 32) v.rhsNA[lo + e] = sy[e];
+        for (int e = lane; e < dim; e += 32)
+        {
+            double rhs = A.rhs[lo + e];
+            if (i > 0) rhs = rhs + A.scv[e];
+            A.sy[e] = -1.0 * rhs;
+        }
+        __syncwarp();
+        nreg += warp_potrf_reg(W, A.w0, dim, dim, A.inv + lo, lane, v.o.regType, v.o.regTol, v.o.regValue);
+        if (dim <= 32)
+        {
+            double y = lane < dim ? A.sy[lane] : 0.0;
+            const double inv = lane < dim ? A.inv[lo + lane] : 0.0;
+            y = warp_trsv_lnn32(W, dim, dim, inv, y, lane);
+            if (lane < dim) A.sy[lane] = y;
+            __syncwarp();
+        }
+        else
+            warp_trsv_lnn(W, dim, dim, A.inv + lo, A.sy, lane);
+        for (int e = lane; e < dim; e += 32) A.rhs[lo + e] = A.sy[e];
         if (i < Ns - 2)
         {
-            const int dimN = nu * v.T.cn[i + 1];
-            for (int e = lane; e < dimN * dim; e += 32)
-            {
-                const int b = e / dimN, a = e - b * dimN;
-                sJL[a + b * ld] = 0.0 + -1.0 * K1[a + b * nK];
-            }
-            __syncwarp();
+            const int dimN = nu * A.cn[i + 1];
+            double *JL = A.JL + A.jlo[i];
             for (int a = lane; a < dimN; a += 32)
                 for (int j = 0; j < dim; j++)
                 {
-                    double t = sJL[a + j * ld];
-                    for (int c = 0; c < j; c++) t -= sJL[a + c * ld] * sJ[j + c * ld];
-                    sJL[a + j * ld] = t * sinv[j];
+                    double t = JL[a + j * dimN];
+                    for (int c = 0; c < j; c++) t -= JL[a + c * dimN] * W[j + c * dim];
+                    JL[a + j * dimN] = t * A.inv[lo + j];
                 }
             __syncwarp();
-            for (int e = lane; e < dimN * dim; e += 32)
-            {
-                const int b = e / dimN, a = e - b * dimN;
-                v.CJL[v.T.jlo[i] + e] = sJL[a + b * ld];
-            }
             for (int e = lane; e < dimN * dimN; e += 32)
             {
                 const int b = e / dimN, a = e - b * dimN;
                 if (a < b) continue;
                 double t = 0.0;
-                for (int c = 0; c < dim; c++) t += sJL[a + c * ld] * sJL[b + c * ld];
-                sCar[a + b * ld] = 0.0 - t;
+                for (int c = 0; c < dim; c++) t += JL[a + c * dimN] * JL[b + c * dimN];
+                A.car[e] = 0.0 - t;
             }
             for (int a = lane; a < dimN; a += 32)
             {
                 double t = 0.0;
-                for (int c = 0; c < dim; c++) t += sJL[a + c * ld] * sy[c];
-                scv[a] = t;
+                for (int c = 0; c < dim; c++) t += JL[a + c * dimN] * A.sy[c];
+                A.scv[a] = t;
             }
         }
         __syncwarp();
@@ -569,31 +638,36 @@ __device__ void sd_jay_chain(const SdView &v, double *sm, int lane)
     if (nreg > 0 && lane == 0) atomicAdd(&v.info[3], nreg);
     for (int i = Ns - 2; i >= 0; i--)
     {
-        const int dim = nu * v.T.cn[i], lo = v.T.lo[i];
-        for (int e = lane; e < dim * dim; e += 32)
-        {
-            const int b = e / dim, a = e - b * dim;
-            sJ[a + b * ld] = v.CJD[v.T.jdo[i] + e];
-        }
+        const int dim = nu * A.cn[i], lo = A.lo[i];
+        const double *W = A.JD0 + A.jdo[i];
         for (int e = lane; e < dim; e += 32)
         {
-            sinv[e] = v.CJDi[lo + e];
-            double rhs = v.rhsNA[lo + e];
-            if (i < Ns - 2) rhs = rhs - scv[e];
-            sy[e] = rhs;
+            double rhs = A.rhs[lo + e];
+            if (i < Ns - 2) rhs = rhs - A.scv[e];
+            A.sy[e] = rhs;
         }
         __syncwarp();
-        warp_trsv_ltn(sJ, ld, dim, sinv, sy, lane);
-        for (int e = lane; e < dim; e += 32) v.dlam[lo + e] = sy[e];
+        if (dim <= 32)
+        {
+            double y = lane < dim ? A.sy[lane] : 0.0;
+            const double inv = lane < dim ? A.inv[lo + lane] : 0.0;
+            y = warp_trsv_ltn32(W, dim, dim, inv, y, lane);
+            __syncwarp();
+            if (lane < dim) A.sy[lane] = y;
+            __syncwarp();
+        }
+        else
+            warp_trsv_ltn(W, dim, dim, A.inv + lo, A.sy, lane);
+        for (int e = lane; e < dim; e += 32) v.dlam[lo + e] = A.sy[e];
         if (i > 0)
         {
-            const int dimP = nu * v.T.cn[i - 1];
-            const double *CJL = v.CJL + v.T.jlo[i - 1]; /* dim x dimP */
+            const int dimP = nu * A.cn[i - 1];
+            const double *CJL = A.JL + A.jlo[i - 1]; /* dim x dimP */
             for (int c = lane; c < dimP; c += 32)
             {
                 double t = 0.0;
-                for (int a = 0; a < dim; a++) t += CJL[a + c * dim] * sy[a];
-                scv[c] = t;
+                for (int a = 0; a < dim; a++) t += CJL[a + c * dim] * A.sy[a];
+                A.scv[c] = t;
             }
         }
         __syncwarp();
@@ -608,10 +682,32 @@ __device__ void sd_jay_chain(const SdView &v, double *sm, int lane)
  * ---------------------------------------------------------------------------------------- */
 __device__ double sd_delta_mu_scenario(const SdView &v, int i, const WarpScratch &S, int lane)
 {
-    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, Ns = v.d.Ns, nv = nx + nu;
+    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, Ns = v.d.Ns, Nr = v.d.Nr, nv = nx + nu;
     const size_t ik0 = (size_t) i * Nh;
     double *dmu = v.dmu + ik0 * nx;
-    sd_banded_solve(v, i, 1, dmu, S, lane);
+    for (int e = lane; e < Nh * nx; e += 32)
+    {   /* right-hand side -res + Zbar (dlam_{i-1} - dlam_i), :1095-1127 */
+        const int k = e / nx, a = e - k * nx;
+        const double r = v.res[ik0 * nx + e];
+        double val;
+        if (k < Nr)
+        {
+            const double *Z = v.Zbar + (ik0 + k) * nx * nu;
+            double t = 0.0;
+            for (int c = 0; c < nu; c++)
+            {
+                double vv = 0.0;
+                if (i > 0 && k < v.T.cn[i - 1]) vv = vv + v.dlam[v.T.lo[i - 1] + k * nu + c];
+                if (i < Ns - 1 && k < v.T.cn[i]) vv = vv - v.dlam[v.T.lo[i] + k * nu + c];
+                t += Z[a + c * nx] * vv;
+            }
+            val = -r + t;
+        }
+        else val = 0.0 - r;
+        dmu[e] = val;
+    }
+    __syncwarp();
+    sd_banded_solve(v, i, dmu, dmu, S, lane);
     double part = 0.0;
     for (int e = lane; e < Nh * nv; e += 32)
     {
@@ -765,7 +861,13 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
         PHASE(2);
         if (Ns > 1)
         {
-            if (tm.gw == 0) sd_jay_chain(v, smem, tm.lane);
+            if (tm.rank == 0)
+            {
+                const JayArena A = jay_arena(v, v.jay_in_smem ? smem : v.jarena);
+                sd_jay_gather(v, A, tm);
+                __syncthreads();
+                if (tm.wib == 0) sd_jay_chain(v, A, tm.lane);
+            }
             team_sync();
         }
         PHASE(3);
@@ -821,7 +923,7 @@ struct tqb_sd_device
 {
     tqb_sd_dims dims;
     int *d_int;
-    double *d_in, *d_out, *d_work;
+    double *d_in, *d_out, *d_work, *d_jarena;
     int *d_info;
     SdView v;
     cudaStream_t stream;
@@ -873,29 +975,34 @@ static int sd_build_device(tqb_sd_device *D, const int *h_int)
     int dev = 0, smem_max = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const size_t ld = nx | 1, mJ = d->mJ > 0 ? d->mJ : 1, ldm = mJ | 1;
-    size_t per_warp = 3 * nx * ld + 3 * nx + 2 * nK * nx;
-    per_warp = (per_warp + 1) / 2 * 2;
-    const size_t jay = 4 * mJ * ldm + 3 * mJ;
+    const size_t per_warp = sd_per_warp_doubles(d->nx, d->nK);
+    const size_t jay = sd_jay_doubles(*d);
     const size_t lim = (size_t) smem_max - 4096;
     int wpb = 16;
     while (wpb > 1 && (size_t) wpb * per_warp * 8 > lim) wpb >>= 1;
-    if ((size_t) wpb * per_warp * 8 > lim || jay * 8 > lim)
+    if ((size_t) wpb * per_warp * 8 > lim || d->nx > 32)
     {
-        snprintf(g_sd_err, sizeof g_sd_err, "SDUNES blocks (nx=%d, nu*Nr=%d) need more shared memory than one SM has",
+        snprintf(g_sd_err, sizeof g_sd_err, "SDUNES blocks (nx=%d, nu*Nr=%d) exceed what one SM holds (nx <= 32 and the block scratch must fit in shared memory)",
                  d->nx, d->nK);
         fprintf(stderr, "[treeqp_b200] %s\n", g_sd_err);
         return 1;
     }
+    /* team size: one warp per scenario for the chains, enough threads for the element-wise phases */
     int nb = (d->Ns + wpb - 1) / wpb;
+    const long long elems = (long long) d->SK * d->nx * d->nx;
+    const int nb_el = (int) ((elems + 32LL * wpb * 4 - 1) / (32LL * wpb * 4));
+    if (nb_el > nb) nb = nb_el;
     if (nb > 8) nb = 8;
     if (nb < 1) nb = 1;
     D->wpb = wpb;
     D->nblocks = nb;
     size_t sm = (size_t) wpb * per_warp;
-    if (jay > sm) sm = jay;
+    v.jay_in_smem = jay * 8 <= lim;
+    if (v.jay_in_smem && jay > sm) sm = jay;
     D->smem = sm * 8;
     v.per_warp = (int) per_warp;
+    CK(cudaMalloc(&D->d_jarena, sizeof(double) * jay));
+    v.jarena = D->d_jarena;
     CK(cudaFuncSetAttribute(k_sdunes_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->smem));
     return 0;
 }
@@ -917,7 +1024,7 @@ extern "C" void tqb_sd_device_destroy(tqb_sd_device *D)
 {
     if (!D) return;
     if (D->stream) cudaStreamSynchronize(D->stream);
-    cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_out); cudaFree(D->d_work); cudaFree(D->d_info);
+    cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_out); cudaFree(D->d_work); cudaFree(D->d_info); cudaFree(D->d_jarena);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
     if (D->stream) cudaStreamDestroy(D->stream);

@@ -44,8 +44,11 @@ struct FusedCfg
     static constexpr int SMEM = D * LDC + D * LDR + 2 * (NCOL + 2) + D + 2;
 };
 
+#ifndef TQB_BF_MINBLOCKS
+#define TQB_BF_MINBLOCKS 1
+#endif
 template <int NX, int NU, int MD, int PNX, bool ROOT>
-__global__ void __launch_bounds__(128) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents)
+__global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents)
 {
     using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
     constexpr int D = Cfg::D, NCOL = Cfg::NCOL, R = Cfg::R, LDC = Cfg::LDC, LDR = Cfg::LDR;
@@ -172,8 +175,7 @@ __global__ void __launch_bounds__(128) k_build_factor(View v, int lvl_begin, int
         for (int j = 0; j < D; j++)
         {
             double piv = __shfl_sync(FULL, wA[j], j), inv;
-            if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
-            else { piv = 0.0; inv = 0.0; }
+            tqb_pivot(piv, inv);
             small |= (piv <= v.o.regTol);
             if (lane == j) { wA[j] = piv; myinv = inv; }
             else if (lane > j) wA[j] *= inv;

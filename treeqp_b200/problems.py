@@ -216,6 +216,48 @@ def linear_chain(nm: int = 4, nu: int = 3, md: int = 3, Nr: int = 2, Nh: int = 2
     return p
 
 
+def linear_chain_batch(n: int, nm: int = 4, nu: int = 3, md: int = 3, Nr: int = 2, Nh: int = 20,
+                       seed: int = 0, x0_kick: float = 1.0, x0_noise: float = 0.3, ubound: float = 0.5,
+                       xbound: float = 1e12):
+    """Config 4: n independent linear_chain MPC QPs of the same shape that differ only in the
+    initial state (seed + i), i.e. only in b of the root's children (x0 is eliminated).
+    Deviations from benchmark/linear_chain (all bounds +-2, x0 = 2*e), chosen on the reference
+    itself: whenever a state reaches its bound the reference's TDUNES may not converge in 100
+    iterations (x0 = 1.5 +- 0.3: 5 % of the seeds; x0 = 1.0 +- 0.3: 2 of 4096), so the batch bounds the
+    inputs only, as config 3 does: |u| <= 0.5 makes ~250 of the 522 inputs active (3-5 Newton
+    iterations per QP instead of a single unconstrained one) and the dual Hessian stays positive
+    definite, i.e. every instance converges."""
+    base = linear_chain(nm, nu, md, Nr, Nh, seed=seed, x0_kick=x0_kick, x0_noise=x0_noise)
+    base.umin[:] = -ubound
+    base.umax[:] = ubound
+    base.xmin[:] = -xbound
+    base.xmax[:] = xbound
+    nxs_ = 2 * nm
+    dad, stage, real = tree_tables(base.nk)
+    kids0 = [k for k in range(1, base.Nn) if dad[k] == 0]
+    Ts = 0.05
+    T = -2.0 * np.eye(nm) + np.eye(nm, k=1) + np.eye(nm, k=-1)
+    Ad = []
+    for kspr in np.linspace(4.0, 8.0, md):
+        Ac = np.zeros((nxs_, nxs_)); Ac[:nm, nm:] = np.eye(nm); Ac[nm:, :nm] = kspr * T
+        Bc = np.zeros((nxs_, nu)); Bc[nm:nm + nu, :] = np.eye(nu)
+        M = np.zeros((nxs_ + nu, nxs_ + nu)); M[:nxs_, :nxs_] = Ac; M[:nxs_, nxs_:] = Bc
+        Ad.append(_expm(M * Ts)[:nxs_, :nxs_].copy())
+    probs = []
+    for i in range(n):
+        rng = np.random.Generator(np.random.PCG64(seed + i))
+        x0 = np.zeros(nxs_)
+        x0[min(nm + nu, nxs_ - 1)] = x0_kick
+        x0 += x0_noise * rng.uniform(-1.0, 1.0, nxs_)
+        b = base.b.copy()
+        for k in kids0:
+            b[(k - 1) * nxs_:k * nxs_] = Ad[real[k]] @ x0
+        probs.append(Problem(nk=base.nk, nx=base.nx, nu=base.nu, A=base.A, B=base.B, b=b, Qd=base.Qd, Rd=base.Rd,
+                             q=base.q, r=base.r, xmin=base.xmin, xmax=base.xmax, umin=base.umin, umax=base.umax,
+                             lam0=base.lam0, meta=dict(base.meta, seed=seed + i)))
+    return probs
+
+
 def eliminate_x0(prob: Problem) -> Problem:
     """Fold a pinned initial state (xmin[0] == xmax[0] == x0) into the dynamics of the root's
     children, as tree_qp_in_eliminate_x0 does (tree_qp_common.c:404-525): nx[0] <- 0,
