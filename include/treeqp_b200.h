@@ -536,6 +536,37 @@ return_t treeqp_tdunes_solve_batch(treeqp_tdunes_batch *batch, const tree_qp_in 
 void treeqp_tdunes_batch_get_stats(const treeqp_tdunes_batch *batch, treeqp_b200_stats *stats);
 void treeqp_tdunes_batch_destroy(treeqp_tdunes_batch *batch);
 
+/* ONE tree QP sharded by subtree over the GPUs of a box (one process per GPU).  The tree is cut
+ * at the first depth with as many nodes as ranks; every rank factors its subtrees locally, the cut
+ * nodes' Schur complements are all-gathered once per Newton iteration, the few levels above the
+ * cut are factored redundantly, and the line-search scalars are all-reduced (NCCL over NVLink).
+ * All ranks pass the SAME qp_in; each rank uploads only its share and writes into qp_out only the
+ * nodes it owns (its subtrees; rank 0 also the levels above the cut).
+ *   comm:  rank 0 calls treeqp_b200_comm_unique_id and hands the 128 bytes to the other ranks
+ *          (MPI, torch.distributed, a file ...); every rank then calls treeqp_b200_comm_create. */
+typedef struct treeqp_b200_comm_ treeqp_b200_comm;
+int treeqp_b200_comm_unique_id(char *id128);
+treeqp_b200_comm *treeqp_b200_comm_create(int rank, int nranks, const char *id128, int device);
+void treeqp_b200_comm_destroy(treeqp_b200_comm *comm);
+
+typedef struct treeqp_tdunes_sharded_ treeqp_tdunes_sharded;
+treeqp_tdunes_sharded *treeqp_tdunes_sharded_create(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts,
+                                                    treeqp_b200_comm *comm);
+/* lambda: the full vector of treeqp_tdunes_set_dual_initialization */
+void treeqp_tdunes_sharded_set_dual_initialization(treeqp_tdunes_sharded *sh, const double *lambda,
+                                                   const tree_qp_in *qp_in);
+return_t treeqp_tdunes_sharded_upload(treeqp_tdunes_sharded *sh, const tree_qp_in *qp_in);
+return_t treeqp_tdunes_sharded_solve_resident(treeqp_tdunes_sharded *sh);
+return_t treeqp_tdunes_sharded_download(treeqp_tdunes_sharded *sh, tree_qp_out *qp_out);
+return_t treeqp_tdunes_sharded_solve(treeqp_tdunes_sharded *sh, const tree_qp_in *qp_in, tree_qp_out *qp_out);
+void treeqp_tdunes_sharded_get_stats(const treeqp_tdunes_sharded *sh, treeqp_b200_stats *stats);
+void treeqp_tdunes_sharded_get_plan(const treeqp_tdunes_sharded *sh, int *cut_depth, int *ncut, int *n_local,
+                                    int *n_owned);
+void treeqp_tdunes_sharded_destroy(treeqp_tdunes_sharded *sh);
+/* the sharding plan alone (host logic, no GPU): owned_global / ghost_global are [N] 0/1 masks */
+int treeqp_b200_shard_plan(const tree_qp_in *qp_in, int rank, int nranks, int *cut_depth, int *ncut, int *n_local,
+                           int *owned_global, int *ghost_global);
+
 /* SDUNES: same additive protocol as TDUNES (destroy, statistics, device-resident solves) */
 void treeqp_sdunes_destroy(treeqp_sdunes_workspace *work);
 void treeqp_sdunes_get_stats(const treeqp_sdunes_workspace *work, treeqp_b200_stats *stats);

@@ -161,3 +161,21 @@ def test_batch_mixed_shapes_and_warm_start(product_lib):
     assert batch.solve(qp_outs) == capi.TREEQP_OK
     assert all(o.iter == 0 for o in qp_outs)
     batch.destroy()
+
+
+def test_sharded_solve_matches_single_gpu():
+    """one tree QP sharded by subtree over 2 GPUs (NCCL all-gather of the cut nodes' Schur complements,
+    all-reduce of the line-search scalars) equals the single-GPU solve; needs >= 2 GPUs"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs (gpurun --gpus 2)")
+    world = 4 if n >= 4 else 2
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "run_sharded.py"), "9"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" OK") == 2, r.stdout[-3000:]

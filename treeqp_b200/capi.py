@@ -263,6 +263,32 @@ class TreeQpLib:
             L.treeqp_tdunes_batch_get_stats.restype = None
             L.treeqp_tdunes_batch_destroy.argtypes = [vp]
             L.treeqp_tdunes_batch_destroy.restype = None
+            L.treeqp_b200_comm_unique_id.argtypes = [C.c_char_p]
+            L.treeqp_b200_comm_unique_id.restype = C.c_int
+            L.treeqp_b200_comm_create.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_int]
+            L.treeqp_b200_comm_create.restype = vp
+            L.treeqp_b200_comm_destroy.argtypes = [vp]
+            L.treeqp_b200_comm_destroy.restype = None
+            L.treeqp_tdunes_sharded_create.argtypes = [vp, C.POINTER(TdunesOpts), vp]
+            L.treeqp_tdunes_sharded_create.restype = vp
+            L.treeqp_tdunes_sharded_set_dual_initialization.argtypes = [vp, c_double_p, vp]
+            L.treeqp_tdunes_sharded_set_dual_initialization.restype = None
+            L.treeqp_tdunes_sharded_upload.argtypes = [vp, vp]
+            L.treeqp_tdunes_sharded_upload.restype = C.c_int
+            L.treeqp_tdunes_sharded_solve_resident.argtypes = [vp]
+            L.treeqp_tdunes_sharded_solve_resident.restype = C.c_int
+            L.treeqp_tdunes_sharded_download.argtypes = [vp, vp]
+            L.treeqp_tdunes_sharded_download.restype = C.c_int
+            L.treeqp_tdunes_sharded_solve.argtypes = [vp, vp, vp]
+            L.treeqp_tdunes_sharded_solve.restype = C.c_int
+            L.treeqp_tdunes_sharded_get_stats.argtypes = [vp, C.POINTER(Stats)]
+            L.treeqp_tdunes_sharded_get_stats.restype = None
+            L.treeqp_tdunes_sharded_get_plan.argtypes = [vp, c_int_p, c_int_p, c_int_p, c_int_p]
+            L.treeqp_tdunes_sharded_get_plan.restype = None
+            L.treeqp_tdunes_sharded_destroy.argtypes = [vp]
+            L.treeqp_tdunes_sharded_destroy.restype = None
+            L.treeqp_b200_shard_plan.argtypes = [vp, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]
+            L.treeqp_b200_shard_plan.restype = C.c_int
             L.treeqp_sdunes_destroy.argtypes = [vp]
             L.treeqp_sdunes_destroy.restype = None
             L.treeqp_sdunes_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -549,6 +575,89 @@ class TdunesBatch:
             self.destroy()
         except Exception:
             pass
+
+
+def shard_plan(lib: TreeQpLib, qp_in: "QpIn", rank: int, nranks: int) -> dict:
+    """treeqp_b200_shard_plan: which nodes rank `rank` of `nranks` owns / sees as ghosts (host logic only)"""
+    N = qp_in.prob.Nn
+    owned, ghost = np.zeros(N, dtype=np.int32), np.zeros(N, dtype=np.int32)
+    cd, nc, nl = C.c_int(), C.c_int(), C.c_int()
+    rc = lib.lib.treeqp_b200_shard_plan(qp_in.ptr, rank, nranks, C.byref(cd), C.byref(nc), C.byref(nl), _ip(owned), _ip(ghost))
+    if rc != 0:
+        raise ValueError("tree cannot be cut for %d ranks" % nranks)
+    return dict(cut_depth=cd.value, ncut=nc.value, n_local=nl.value, owned=owned.astype(bool), ghost=ghost.astype(bool))
+
+
+class Comm:
+    """NCCL communicator of the sharded solves; `bcast(bytes_or_None) -> bytes` distributes rank 0's
+    128-byte id (e.g. over torch.distributed)."""
+
+    def __init__(self, lib: TreeQpLib, rank: int, nranks: int, device: int, bcast):
+        self.lib = lib
+        buf = C.create_string_buffer(128)
+        if rank == 0:
+            assert lib.lib.treeqp_b200_comm_unique_id(buf) == 0, "NCCL unavailable"
+        ident = bcast(buf.raw if rank == 0 else None)
+        assert len(ident) == 128
+        self.handle = C.c_void_p(lib.lib.treeqp_b200_comm_create(rank, nranks, ident, device))
+        if not self.handle.value:
+            raise RuntimeError("treeqp_b200_comm_create failed")
+        self.rank, self.nranks = rank, nranks
+
+    def destroy(self):
+        if self.handle and self.handle.value:
+            self.lib.lib.treeqp_b200_comm_destroy(self.handle)
+            self.handle = C.c_void_p(None)
+
+
+class TdunesSharded:
+    """One tree QP sharded by subtree over the ranks of `comm` (treeqp_tdunes_sharded_*)."""
+
+    def __init__(self, lib: TreeQpLib, qp_in: "QpIn", comm: Comm, **opt_overrides):
+        self.lib, self.qp_in, self.comm = lib, qp_in, comm
+        L = lib.lib
+        Nn = qp_in.prob.Nn
+        self.opts = TdunesOpts()
+        self.opts_mem = _Buf(max(L.treeqp_tdunes_opts_calculate_size(Nn), 8))
+        L.treeqp_tdunes_opts_create(Nn, C.byref(self.opts), self.opts_mem.ptr)
+        L.treeqp_tdunes_opts_set_default(Nn, C.byref(self.opts))
+        for k, v in opt_overrides.items():
+            assert hasattr(self.opts, k), k
+            setattr(self.opts, k, v)
+        self.handle = C.c_void_p(L.treeqp_tdunes_sharded_create(qp_in.ptr, C.byref(self.opts), comm.handle))
+        if not self.handle.value:
+            raise RuntimeError("treeqp_tdunes_sharded_create failed")
+
+    def plan(self) -> dict:
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.lib.lib.treeqp_tdunes_sharded_get_plan(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        return dict(cut_depth=a.value, ncut=b.value, n_local=c.value, n_owned=d.value)
+
+    def set_dual_initialization(self, lam0: np.ndarray):
+        lam0 = _f64(lam0)
+        self.lib.lib.treeqp_tdunes_sharded_set_dual_initialization(self.handle, _dp(lam0), self.qp_in.ptr)
+
+    def upload(self) -> int:
+        return int(self.lib.lib.treeqp_tdunes_sharded_upload(self.handle, self.qp_in.ptr))
+
+    def solve_resident(self) -> int:
+        return int(self.lib.lib.treeqp_tdunes_sharded_solve_resident(self.handle))
+
+    def download(self, qp_out: "QpOut") -> int:
+        return int(self.lib.lib.treeqp_tdunes_sharded_download(self.handle, qp_out.ptr))
+
+    def solve(self, qp_out: "QpOut") -> int:
+        return int(self.lib.lib.treeqp_tdunes_sharded_solve(self.handle, self.qp_in.ptr, qp_out.ptr))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self.lib.lib.treeqp_tdunes_sharded_get_stats(self.handle, C.byref(st))
+        return stats_dict(self.lib, st)
+
+    def destroy(self):
+        if self.handle and self.handle.value:
+            self.lib.lib.treeqp_tdunes_sharded_destroy(self.handle)
+            self.handle = C.c_void_p(None)
 
 
 class Sdunes:

@@ -15,6 +15,7 @@
 
 #include "tdunes_kernels.cuh"
 #include "tdunes_fused.cuh"
+#include "comm.cuh"
 
 static thread_local char g_err[512] = "";
 #define CK(call)                                                                                 \
@@ -27,10 +28,10 @@ static thread_local char g_err[512] = "";
         }                                                                                        \
     } while (0)
 
-enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DIR, K_TRIAL, K_STEP, K_FINISH, K_NCLASS };
+enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DIR, K_TRIAL, K_STEP, K_FINISH, K_COMM, K_NCLASS };
 static const char *const k_names[K_NCLASS] = {"k_init", "k_stage<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
                                               "k_hessian", "k_factor_level", "k_backsolve_level", "k_stage<2>",
-                                              "k_trial", "k_lambda_step", "k_finish"};
+                                              "k_trial", "k_lambda_step", "k_finish", "nccl+pack"};
 static int g_profile = -1;
 #define TQB_MAX_EVENTS 65536
 
@@ -71,6 +72,11 @@ struct tqb_device
     int fast, f_nx, f_nu, f_pnx;
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
     double *d_schur;
+    /* subtree sharding (tqb_device_enable_sharding) */
+    tqb_comm *comm;
+    int cut_depth, ncut, my_cut0, my_ncut;
+    int *d_cut_nodes;
+    double *d_send, *d_recv, *d_tred;
 };
 
 extern "C" const char *tqb_cuda_last_error(void) { return g_err; }
@@ -188,7 +194,7 @@ static int fused_backsolve_level(tqb_device *D, int l)
 /* The fast path needs: every non-root node nx == NX, every root nx in {0, NX} (the same for all
  * trees), every parent nu == NU, all parents of one depth the same number of kids, kids of one
  * depth either all parents or all leaves, and the combination compiled in. */
-static int detect_fast_path(tqb_device *D, const int *h_int)
+static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
 {
     const tqb_dims *d = &D->dims;
     tqb_tables T;
@@ -213,7 +219,8 @@ static int detect_fast_path(tqb_device *D, const int *h_int)
             if (D->lvl_md[l] == 0) D->lvl_md[l] = T.nkids[g]; else if (D->lvl_md[l] != T.nkids[g]) return 0;
             for (int j = 0; j < T.nkids[g]; j++)
             {
-                const int kp = T.nkids[T.kid0[g] + j] > 0;
+                const int kid = T.kid0[g] + j;
+                const int kp = T.nkids[kid] > 0 || (ghost && ghost[kid]);
                 if (D->lvl_kp[l] < 0) D->lvl_kp[l] = kp; else if (D->lvl_kp[l] != kp) return 0;
             }
         }
@@ -229,7 +236,7 @@ static int detect_fast_path(tqb_device *D, const int *h_int)
     return 0;
 }
 
-static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr)
+static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, const int *ghost)
 {
     const tqb_dims *d = &D->dims;
     CK(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
@@ -277,7 +284,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr)
     v.Nn = d->Nn; v.nT = d->nT; v.X = d->X; v.U = d->U; v.nchunk = d->nchunk;
     v.abmax = d->abmax; v.dmax = d->dmax; v.nxmax = d->nxmax; v.numax = d->numax;
 
-    if (detect_fast_path(D, h_int)) return 1;
+    if (detect_fast_path(D, h_int, ghost)) return 1;
 
     /* shared memory per warp (bytes) and warps per CTA for the block kernels */
     int dev = 0, smem_max = 0;
@@ -307,7 +314,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr)
     return 0;
 }
 
-extern "C" tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int, const int *lvl_ptr)
+extern "C" tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int, const int *lvl_ptr, const int *ghost)
 {
     if (tqb_cuda_device_count() <= 0)
     {
@@ -317,7 +324,7 @@ extern "C" tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int,
     }
     tqb_device *D = (tqb_device *) calloc(1, sizeof(tqb_device));
     D->dims = *dims;
-    if (device_build(D, h_int, lvl_ptr)) { tqb_device_destroy(D); return NULL; }
+    if (device_build(D, h_int, lvl_ptr, ghost)) { tqb_device_destroy(D); return NULL; }
     return D;
 }
 
@@ -327,6 +334,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
     cudaFree(D->d_schur); free(D->lvl_md); free(D->lvl_kp);
+    cudaFree(D->d_cut_nodes); cudaFree(D->d_send); cudaFree(D->d_recv); cudaFree(D->d_tred);
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
@@ -378,6 +386,63 @@ static int read_counters(tqb_device *D)
     return 0;
 }
 
+extern "C" int tqb_device_enable_sharding(tqb_device *D, tqb_comm *comm, int cut_depth, int ncut, int my_cut0,
+                                          int my_ncut, const int *cut_nodes_local)
+{
+    if (!D->fast)
+    {
+        snprintf(g_err, sizeof g_err, "subtree sharding needs a uniform tree (compile-time-dimension kernels)");
+        fprintf(stderr, "[treeqp_b200] %s\n", g_err);
+        return 1;
+    }
+    D->comm = comm; D->cut_depth = cut_depth; D->ncut = ncut; D->my_cut0 = my_cut0; D->my_ncut = my_ncut;
+    const size_t per = (size_t) D->f_nx * (D->f_nx + 3);
+    CK(cudaMalloc(&D->d_cut_nodes, sizeof(int) * (size_t) ncut));
+    CK(cudaMemcpy(D->d_cut_nodes, cut_nodes_local, sizeof(int) * (size_t) ncut, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&D->d_send, sizeof(double) * per * (size_t) my_ncut));
+    CK(cudaMalloc(&D->d_recv, sizeof(double) * per * (size_t) ncut));
+    CK(cudaMalloc(&D->d_tred, sizeof(double) * 2 * (size_t) D->dims.nT));
+    D->v.t_red = D->d_tred;
+    D->v.sharded = 1;
+    return 0;
+}
+
+/* cut nodes -> every rank: one all-gather per Newton iteration, between the sweeps of the
+ * subtrees (depth >= cut) and of the replicated top (depth < cut) */
+static int exchange_cut_nodes(tqb_device *D)
+{
+    const int nx = D->f_nx;
+    const size_t per = (size_t) nx * (nx + 3);
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
+    k_cut_pack<<<(D->my_ncut + 3) / 4, 128, 0, D->stream>>>(D->v, D->d_cut_nodes, D->my_cut0, D->my_ncut, nx, D->d_send);
+    if (tqb_comm_allgather(D->comm, D->d_send, D->d_recv, per * (size_t) D->my_ncut, D->stream)) return 1;
+    k_cut_unpack<<<(D->ncut + 3) / 4, 128, 0, D->stream>>>(D->v, D->d_cut_nodes, D->ncut, nx, D->d_recv);
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches += 2;
+    return 0;
+}
+
+/* this rank's per-tree partial sums (cva -> t_red[0..nT), cvb -> t_red[nT..2nT)), all-reduced */
+static int allreduce_tree_sums(tqb_device *D, int use_a, int use_b, int a_is_max)
+{
+    View &v = D->v;
+    const int nT = D->dims.nT, grid = (nT + 3) / 4;
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
+    if (use_a) { k_tree_partial<<<grid, 128, 0, D->stream>>>(v, v.cva, D->d_tred, a_is_max); D->launches++; }
+    if (use_b) { k_tree_partial<<<grid, 128, 0, D->stream>>>(v, v.cvb, D->d_tred + nT, 0); D->launches++; }
+    int rc = 0;
+    if (use_a && use_b && !a_is_max) rc = tqb_comm_allreduce(D->comm, D->d_tred, 2 * (size_t) nT, 0, D->stream);
+    else
+    {
+        if (use_a) rc |= tqb_comm_allreduce(D->comm, D->d_tred, (size_t) nT, a_is_max, D->stream);
+        if (use_b) rc |= tqb_comm_allreduce(D->comm, D->d_tred + nT, (size_t) nT, 0, D->stream);
+    }
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    return rc;
+}
+
 extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status, int *h_iter,
                                 int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms,
                                 long long *launches, double *kernel_ms16, int *kernel_count16)
@@ -412,8 +477,12 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
              * after the sweep (the sweep of the last iteration is the price of the fusion) */
             CK(cudaMemsetAsync(v.nva, 0, sizeof(double) * (size_t) v.Nn, D->stream));
             for (int l = Nh - 1; l >= 0; l--)
+            {
+                if (D->comm && l == D->cut_depth - 1 && exchange_cut_nodes(D)) return 1;
                 if (fused_factor_level(D, l)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+            }
             LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
+            if (D->comm && allreduce_tree_sums(D, 1, 0, o->termCondition == 2)) return 1;
             LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
             if (read_counters(D)) return 1;
             if (D->h_counters[0] == 0) break;
@@ -446,11 +515,13 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         LAUNCH(K_DIR, k_stage<2>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
         LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, 0);
         LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 1);
+        if (D->comm && allreduce_tree_sums(D, 1, 1, 0)) return 1;
         LAUNCH(K_DECIDE, k_decide_ls_init, tgrid, 128, 0, v);
         for (int ls = 0; ls <= o->lsMaxIter; ls++)
         {
             CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
             LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 0);
+            if (D->comm && allreduce_tree_sums(D, 0, 1, 0)) return 1;
             LAUNCH(K_DECIDE, k_decide_ls_trial, tgrid, 128, 0, v);
             if (read_counters(D)) return 1;
             if (D->h_counters[1] == 0) break;

@@ -44,6 +44,10 @@ struct View
     int *counters; /* [0] trees still running, [1] trees with a pending line-search trial, [2] regularised blocks, [3] total trials */
     int *ls_hist;  /* [256] trials per Newton iteration of tree 0 */
     int Nn, nT, X, U, nchunk;
+    /* sharded solve: per-tree sums come all-reduced in t_red ([0,nT): norm / descent product,
+     * [nT,2nT): dual function) instead of from this rank's chunk values */
+    double *t_red;
+    int sharded;
     /* per-warp shared memory layout, in doubles */
     int abmax, dmax, nxmax, numax;
     tqb_opts o;
@@ -288,6 +292,53 @@ __device__ __forceinline__ double tree_reduce(const View &v, const double *cv, i
     return is_max ? warp_max(acc) : warp_sum(acc);
 }
 
+/* sharded solve: this rank's part of a per-tree sum / max, to be all-reduced */
+__global__ void k_tree_partial(View v, const double *cv, double *out, int is_max)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= v.nT) return;
+    const double r = tree_reduce(v, cv, t, lane, is_max != 0);
+    if (lane == 0) out[t] = r;
+}
+
+/* sharded solve: what a cut node contributes to its parent's block (stage solution, active-set
+ * mask, right-hand side part, Schur complement), packed for the all-gather / scattered after it.
+ * One warp per cut node; `per` = nx(nx+3) doubles. */
+__global__ void k_cut_pack(View v, const int *cut_nodes, int first, int count, int nx, double *buf)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= count) return;
+    const int g = cut_nodes[first + w], xo = v.T.xoff[g];
+    double *dst = buf + (size_t) w * nx * (nx + 3);
+    for (int e = lane; e < nx; e += 32)
+    {
+        dst[e] = v.x[xo + e];
+        dst[nx + e] = v.P[xo + e];
+        dst[2 * nx + e] = v.rsub[xo + e];
+    }
+    const double *S = v.schur + (size_t) g * nx * nx;
+    for (int e = lane; e < nx * nx; e += 32) dst[3 * nx + e] = S[e];
+}
+
+__global__ void k_cut_unpack(View v, const int *cut_nodes, int count, int nx, const double *buf)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= count) return;
+    const int g = cut_nodes[w], xo = v.T.xoff[g];
+    const double *src = buf + (size_t) w * nx * (nx + 3);
+    for (int e = lane; e < nx; e += 32)
+    {
+        v.x[xo + e] = src[e];
+        v.P[xo + e] = src[nx + e];
+        v.rsub[xo + e] = src[2 * nx + e];
+    }
+    double *S = v.schur + (size_t) g * nx * nx;
+    for (int e = lane; e < nx * nx; e += 32) S[e] = src[3 * nx + e];
+}
+
 /* termination test per tree (dual_Newton_tree.c:542-546) */
 __global__ void k_decide_term(View v)
 {
@@ -295,7 +346,7 @@ __global__ void k_decide_term(View v)
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= v.nT) return;
     if (v.status[t] != TQB_RUNNING) { if (lane == 0) v.ls_active[t] = 0; return; }
-    double err = tree_reduce(v, v.cva, t, lane, v.o.termCondition == 2);
+    double err = v.sharded ? v.t_red[t] : tree_reduce(v, v.cva, t, lane, v.o.termCondition == 2);
     if (v.o.termCondition == 1) err = sqrt(err);
     if (lane == 0)
     {
@@ -532,8 +583,8 @@ __global__ void k_decide_ls_init(View v)
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= v.nT) return;
     if (v.status[t] != TQB_RUNNING) return;
-    const double dot = -tree_reduce(v, v.cva, t, lane, false);
-    const double f0 = tree_reduce(v, v.cvb, t, lane, false);
+    const double dot = -(v.sharded ? v.t_red[t] : tree_reduce(v, v.cva, t, lane, false));
+    const double f0 = v.sharded ? v.t_red[v.nT + t] : tree_reduce(v, v.cvb, t, lane, false);
     if (lane == 0)
     {
         v.t_dot[t] = dot;
@@ -574,7 +625,7 @@ __global__ void k_decide_ls_trial(View v)
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= v.nT) return;
     if (!v.ls_active[t]) return;
-    const double f = tree_reduce(v, v.cvb, t, lane, false);
+    const double f = v.sharded ? v.t_red[v.nT + t] : tree_reduce(v, v.cvb, t, lane, false);
     if (lane == 0)
     {
         const int ls = ++v.ls_cnt[t];

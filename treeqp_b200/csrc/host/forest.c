@@ -81,6 +81,27 @@ int tqb_clipping_applicable(const tree_qp_in *qp, int k)
 
 tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
 {
+    return tqb_forest_create_ex(nT, qps, NULL, NULL);
+}
+
+/* number of reduction chunks of one tree: runs of owned nodes cut into pieces of TQB_CHUNK */
+static int count_chunks(int N, const int *owned)
+{
+    if (!owned) return (N + TQB_CHUNK - 1) / TQB_CHUNK;
+    int n = 0, k = 0;
+    while (k < N)
+    {
+        if (!owned[k]) { k++; continue; }
+        int e = k;
+        while (e < N && owned[e] && e - k < TQB_CHUNK) e++;
+        n++;
+        k = e;
+    }
+    return n;
+}
+
+tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int *ghost, const int *owned)
+{
     tqb_forest *f = (tqb_forest *) calloc(1, sizeof(tqb_forest));
     tqb_dims *d = &f->dims;
     d->nT = nT;
@@ -95,7 +116,7 @@ tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
     for (int t = 0; t < nT; t++)
     {
         const tree_qp_in *qp = qps[t];
-        nchunk += (qp->N + TQB_CHUNK - 1) / TQB_CHUNK;
+        nchunk += count_chunks(qp->N, owned);
         for (int k = 0; k < qp->N; k++)
         {
             const struct node *nd = &qp->tree[k];
@@ -140,12 +161,16 @@ tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
         const tree_qp_in *qp = qps[t];
         T->tnode0[t] = g0;
         T->tchunk0[t] = c;
-        for (int s = 0; s < qp->N; s += TQB_CHUNK)
+        for (int s = 0; s < qp->N;)
         {
+            if (owned && !owned[s]) { s++; continue; }
+            int e = s;
+            while (e < qp->N && (!owned || owned[e]) && e - s < TQB_CHUNK) e++;
             T->chunk_beg[c] = g0 + s;
-            T->chunk_end[c] = g0 + (s + TQB_CHUNK < qp->N ? s + TQB_CHUNK : qp->N);
+            T->chunk_end[c] = g0 + e;
             T->chunk_tree[c] = t;
             c++;
+            s = e;
         }
         for (int k = 0; k < qp->N; k++)
         {
@@ -235,7 +260,7 @@ tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
     memset(f->h_in, 0, sizeof(double) * (size_t) d->n_in);
     tqb_layout_inputs(d, f->h_in, &f->hin);
 
-    f->dev = tqb_device_create(d, f->h_int, f->lvl_ptr);
+    f->dev = tqb_device_create(d, f->h_int, f->lvl_ptr, ghost);
     if (!f->dev) { tqb_forest_destroy(f); return NULL; }
     return f;
 }
@@ -260,16 +285,19 @@ static void unpack_dmat(const struct blasfeo_dmat *M, double *dst)
         for (int i = 0; i < m; i++) dst[i + (size_t) j * m] = BLASFEO_DMATEL(M, i, j);
 }
 
-void tqb_forest_pack(tqb_forest *f, int t, const tree_qp_in *qp)
+/* gmap == NULL: tree t of the forest is qp itself; otherwise local node j is node gmap[j] of qp */
+void tqb_forest_pack_mapped_(tqb_forest *f, int t, const tree_qp_in *qp, const int *gmap)
 {
     const tqb_tables *T = &f->ht;
     tqb_inputs *in = &f->hin;
     int g0 = T->tnode0[t];
-    assert(T->tnode0[t + 1] - g0 == qp->N);
-#pragma omp parallel for schedule(static) if (qp->N > 2048)
-    for (int k = 0; k < qp->N; k++)
+    const int N = T->tnode0[t + 1] - g0;
+    assert(gmap || N == qp->N);
+#pragma omp parallel for schedule(static) if (N > 2048)
+    for (int j = 0; j < N; j++)
     {
-        int g = g0 + k, nx = qp->nx[k], nu = qp->nu[k], xo = T->xoff[g], uo = T->uoff[g];
+        const int k = gmap ? gmap[j] : j;
+        int g = g0 + j, nx = qp->nx[k], nu = qp->nu[k], xo = T->xoff[g], uo = T->uoff[g];
         assert(nx == T->nx[g] && nu == T->nu[g]);
         if (k > 0)
         {
@@ -299,6 +327,8 @@ void tqb_forest_pack(tqb_forest *f, int t, const tree_qp_in *qp)
         memcpy(in->umax + uo, qp->umax[k].pa, sizeof(double) * (size_t) nu);
     }
 }
+
+void tqb_forest_pack(tqb_forest *f, int t, const tree_qp_in *qp) { tqb_forest_pack_mapped_(f, t, qp, NULL); }
 
 /* lambda: multipliers of nodes 1..N-1 of tree t, concatenated (dual_Newton_tree.c:1654-1663) */
 void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda)

@@ -93,12 +93,17 @@ typedef struct tqb_forest
     long long h2d_bytes, d2h_bytes, launches;
     double kernel_ms[16];
     int kernel_count[16];
+    double comm_ms;          /* sharded solves: device time spent in collectives */
+    int n_collectives;
 } tqb_forest;
 
 /* ---- forest.c ---- */
 struct tree_qp_in_;
 struct tree_qp_out_;
 tqb_forest *tqb_forest_create(int nT, const struct tree_qp_in_ *const *qps);
+/* general form: `ghost` marks nodes to be treated as parents whose block lives elsewhere, `owned`
+ * restricts the reduction chunks (both per node, NULL = none / all) */
+tqb_forest *tqb_forest_create_ex(int nT, const struct tree_qp_in_ *const *qps, const int *ghost, const int *owned);
 void tqb_forest_destroy(tqb_forest *f);
 /* BLASFEO views -> pinned staging (reciprocals of the weights are formed here,
  * dual_Newton_tree_clipping.c:149-170) */
@@ -116,7 +121,7 @@ int tqb_cuda_device_count(void);
 int tqb_cuda_set_device(int dev);
 void *tqb_pinned_alloc(size_t bytes);
 void tqb_pinned_free(void *p);
-tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int, const int *lvl_ptr);
+tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int, const int *lvl_ptr, const int *ghost);
 void tqb_device_destroy(tqb_device *d);
 /* async H2D of the input block, returns 0 on success */
 int tqb_device_upload(tqb_device *d, const double *h_in, long long n_in, double *ms);
@@ -131,6 +136,54 @@ const char *tqb_kernel_class_name(int k);
 int tqb_device_download(tqb_device *d, double *h_out, double *ms);
 const char *tqb_cuda_last_error(void);
 
+
+/* =========================================================================================
+ * Subtree sharding of ONE tree QP over the GPUs of a box (TDUNES)
+ *
+ * The tree is cut at depth c (the first depth with at least `nranks` nodes).  The nodes of depth
+ * <= c form the TOP, replicated on every rank; the nodes of depth c are the CUT nodes, dealt to the
+ * ranks in equal contiguous groups; a rank's LOCAL tree is the top plus the subtrees below its own
+ * cut nodes.  Cut nodes of other ranks are GHOSTS: leaves of the local tree whose stage solution and
+ * Schur complement arrive by all-gather.  Every reduction counts a node on exactly one rank
+ * (`owned`): the top on rank 0, a subtree (with its cut node) on its rank.
+ * ========================================================================================= */
+struct node;
+typedef struct tqb_shard_plan
+{
+    int rank, nranks;
+    int cut_depth, ncut;       /* cut nodes = all nodes of depth cut_depth */
+    int cut_first;             /* global (= local) index of the first cut node */
+    int my_cut0, my_ncut;      /* this rank's cut nodes: cut_first + my_cut0 .. + my_ncut */
+    int Nl;                    /* local nodes */
+    int *gmap;                 /* [Nl] local -> global node index */
+    int *ghost;                /* [Nl] cut node of another rank */
+    int *owned;                /* [Nl] counted by this rank in reductions / reported in qp_out */
+    struct node *ltree;        /* [Nl] local tree (kids point into lkids) */
+    int *lkids;
+    int *lnx, *lnu, *lnc;      /* [Nl] */
+} tqb_shard_plan;
+
+/* returns NULL (with a message on stderr) if the tree cannot be cut for this number of ranks */
+tqb_shard_plan *tqb_shard_plan_create(const struct tree_qp_in_ *qp, int rank, int nranks);
+void tqb_shard_plan_destroy(tqb_shard_plan *p);
+
+/* forest of ONE local tree described by `plan`; data is read from the FULL qp through plan->gmap */
+tqb_forest *tqb_forest_create_sharded(const struct tree_qp_in_ *full_qp, const tqb_shard_plan *plan, void *comm);
+void tqb_forest_pack_sharded(tqb_forest *f, const struct tree_qp_in_ *full_qp, const tqb_shard_plan *plan);
+void tqb_forest_set_lambda0_sharded(tqb_forest *f, const double *lambda_full, const struct tree_qp_in_ *full_qp,
+                                    const tqb_shard_plan *plan);
+void tqb_forest_unpack_sharded(const tqb_forest *f, const tqb_shard_plan *plan, struct tree_qp_out_ *out_full);
+
+/* ---- cuda/comm.cu: NCCL (loaded with dlopen) ---- */
+typedef struct tqb_comm tqb_comm;
+int tqb_comm_unique_id(char *id128);
+tqb_comm *tqb_comm_create(int rank, int nranks, const char *id128, int device);
+void tqb_comm_destroy(tqb_comm *c);
+int tqb_comm_rank(const tqb_comm *c);
+int tqb_comm_size(const tqb_comm *c);
+/* device side of a sharded forest: cut-node exchange + scalar all-reduces on the solver stream */
+int tqb_device_enable_sharding(tqb_device *d, tqb_comm *comm, int cut_depth, int ncut, int my_cut0, int my_ncut,
+                               const int *cut_nodes_local);
 
 /* =========================================================================================
  * SDUNES (dual Newton strategy on the scenario decomposition, dual_Newton_scenarios.c)

@@ -440,3 +440,154 @@ void treeqp_tdunes_batch_destroy(treeqp_tdunes_batch *b)
     tqb_forest_destroy(b->forest);
     free(b);
 }
+
+/* ------------------------------------------------------------- one tree over several GPUs ---- */
+
+struct treeqp_b200_comm_ { tqb_comm *c; };
+
+int treeqp_b200_comm_unique_id(char *id128) { return tqb_comm_unique_id(id128); }
+
+treeqp_b200_comm *treeqp_b200_comm_create(int rank, int nranks, const char *id128, int device)
+{
+    tqb_comm *c = tqb_comm_create(rank, nranks, id128, device);
+    if (!c) return NULL;
+    treeqp_b200_comm *w = (treeqp_b200_comm *) calloc(1, sizeof *w);
+    w->c = c;
+    return w;
+}
+
+void treeqp_b200_comm_destroy(treeqp_b200_comm *comm)
+{
+    if (!comm) return;
+    tqb_comm_destroy(comm->c);
+    free(comm);
+}
+
+struct treeqp_tdunes_sharded_
+{
+    tqb_shard_plan *plan;
+    tqb_forest *forest;
+    tqb_opts o;
+    int opts_ok, uploaded, lam_dirty;
+    return_t last_status;
+};
+
+int treeqp_b200_shard_plan(const tree_qp_in *qp_in, int rank, int nranks, int *cut_depth, int *ncut, int *n_local,
+                           int *owned_global, int *ghost_global)
+{
+    tqb_shard_plan *p = tqb_shard_plan_create(qp_in, rank, nranks);
+    if (!p) return 1;
+    if (cut_depth) *cut_depth = p->cut_depth;
+    if (ncut) *ncut = p->ncut;
+    if (n_local) *n_local = p->Nl;
+    if (owned_global) memset(owned_global, 0, sizeof(int) * (size_t) qp_in->N);
+    if (ghost_global) memset(ghost_global, 0, sizeof(int) * (size_t) qp_in->N);
+    for (int j = 0; j < p->Nl; j++)
+    {
+        if (owned_global && p->owned[j]) owned_global[p->gmap[j]] = 1;
+        if (ghost_global && p->ghost[j]) ghost_global[p->gmap[j]] = 1;
+    }
+    tqb_shard_plan_destroy(p);
+    return 0;
+}
+
+treeqp_tdunes_sharded *treeqp_tdunes_sharded_create(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts,
+                                                    treeqp_b200_comm *comm)
+{
+    if (!comm) return NULL;
+    check_stage_solvers(qp_in, opts);
+    tqb_shard_plan *plan = tqb_shard_plan_create(qp_in, tqb_comm_rank(comm->c), tqb_comm_size(comm->c));
+    if (!plan) return NULL;
+    treeqp_tdunes_sharded *sh = (treeqp_tdunes_sharded *) calloc(1, sizeof *sh);
+    sh->plan = plan;
+    sh->forest = tqb_forest_create_sharded(qp_in, plan, comm->c);
+    if (!sh->forest) { tqb_shard_plan_destroy(plan); free(sh); return NULL; }
+    memset(sh->forest->hin.lam0, 0, sizeof(double) * (size_t) sh->forest->dims.X);
+    sh->opts_ok = validate_opts(opts) == TREEQP_OK;
+    forward_opts(opts, &sh->o);
+    sh->lam_dirty = 1;
+    return sh;
+}
+
+void treeqp_tdunes_sharded_set_dual_initialization(treeqp_tdunes_sharded *sh, const double *lambda,
+                                                   const tree_qp_in *qp_in)
+{
+    tqb_forest_set_lambda0_sharded(sh->forest, lambda, qp_in, sh->plan);
+    sh->lam_dirty = 1;
+}
+
+return_t treeqp_tdunes_sharded_upload(treeqp_tdunes_sharded *sh, const tree_qp_in *qp_in)
+{
+    double t0 = tqb_wall_ms();
+    tqb_forest_pack_sharded(sh->forest, qp_in, sh->plan);
+    sh->forest->pack_ms = tqb_wall_ms() - t0;
+    if (forest_upload(sh->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    sh->uploaded = 1;
+    sh->lam_dirty = 0;
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_sharded_solve_resident(treeqp_tdunes_sharded *sh)
+{
+    if (!sh->opts_ok) return TREEQP_INVALID_OPTION;
+    if (!sh->uploaded) return TREEQP_UNKNOWN_ERROR;
+    if (sh->lam_dirty)
+    {
+        if (forest_upload(sh->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+        sh->lam_dirty = 0;
+    }
+    if (forest_solve(sh->forest, &sh->o) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    sh->last_status = (return_t) sh->forest->h_status[0];
+    return sh->last_status;
+}
+
+return_t treeqp_tdunes_sharded_download(treeqp_tdunes_sharded *sh, tree_qp_out *qp_out)
+{
+    if (forest_download(sh->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    double t0 = tqb_wall_ms();
+    tqb_forest_unpack_sharded(sh->forest, sh->plan, qp_out);
+    sh->forest->pack_ms += tqb_wall_ms() - t0;
+    qp_out->info.iter = sh->forest->h_iter[0];
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_sharded_solve(treeqp_tdunes_sharded *sh, const tree_qp_in *qp_in, tree_qp_out *qp_out)
+{
+    return_t st = treeqp_tdunes_sharded_upload(sh, qp_in);
+    if (st != TREEQP_OK) return st;
+    st = treeqp_tdunes_sharded_solve_resident(sh);
+    if (st == TREEQP_UNKNOWN_ERROR || st == TREEQP_INVALID_OPTION || st == TREEQP_DN_NOT_DESCENT_DIRECTION) return st;
+    if (treeqp_tdunes_sharded_download(sh, qp_out) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    return st;
+}
+
+void treeqp_tdunes_sharded_get_stats(const treeqp_tdunes_sharded *sh, treeqp_b200_stats *s)
+{
+    treeqp_tdunes_batch tmp;
+    memset(&tmp, 0, sizeof tmp);
+    tmp.forest = sh->forest;
+    treeqp_tdunes_batch_get_stats(&tmp, s);
+}
+
+void treeqp_tdunes_sharded_get_plan(const treeqp_tdunes_sharded *sh, int *cut_depth, int *ncut, int *n_local,
+                                    int *n_owned)
+{
+    const tqb_shard_plan *p = sh->plan;
+    if (cut_depth) *cut_depth = p->cut_depth;
+    if (ncut) *ncut = p->ncut;
+    if (n_local) *n_local = p->Nl;
+    if (n_owned)
+    {
+        int n = 0;
+        for (int j = 0; j < p->Nl; j++) n += p->owned[j];
+        *n_owned = n;
+    }
+}
+
+void treeqp_tdunes_sharded_destroy(treeqp_tdunes_sharded *sh)
+{
+    if (!sh) return;
+    tqb_forest_destroy(sh->forest);
+    tqb_shard_plan_destroy(sh->plan);
+    free(sh);
+}
