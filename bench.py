@@ -87,7 +87,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "100"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -186,6 +186,113 @@ def reference_arm(args):
         gpu_launches=0)))
 
 
+# ----------------------------------------------------------------- secondary workloads (N = 1)
+def bench_batch(lib, n=4096, reps=3):
+    """config 4: n independent linear_chain tree QPs (175 nodes each) as one forest"""
+    probs = P.linear_chain_batch(n, seed=0)
+    qp_ins = [capi.QpIn(lib, p) for p in probs]
+    qp_outs = [capi.QpOut(lib, p) for p in probs]
+    batch = capi.TdunesBatch(lib, qp_ins)
+    assert batch.upload() == capi.TREEQP_OK
+    batch.solve_resident()
+    t_res = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); batch.solve_resident(); t_res.append(time.perf_counter() - t0)
+    assert (batch.status == 0).all()
+    t_e2e = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); batch.solve(qp_outs); t_e2e.append(time.perf_counter() - t0)
+    st = batch.stats()
+    iters = np.array([o.iter for o in qp_outs])
+    out = {"workload": "%d x linear_chain nm=4 nu=3 md=3 Nr=2 Nh=20 (175 nodes), |u|<=0.5, x0 seeded" % n,
+           "qp_per_s_resident": n / min(t_res), "qp_per_s_e2e": n / min(t_e2e), "ms_per_batch_resident": 1e3 * min(t_res),
+           "ms_per_batch_e2e": 1e3 * min(t_e2e), "newton_iters_max": int(iters.max()), "newton_iters_median": float(np.median(iters)),
+           "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "launches": st["kernel_launches"]}
+    path = ref_lib_path(False)
+    if path:
+        ref = capi.TreeQpLib(path)
+        m, tt = 32, 0.0
+        for i in range(m):
+            rin, rout = capi.QpIn(ref, probs[i]), capi.QpOut(ref, probs[i])
+            rs = capi.Tdunes(ref, rin)
+            rs.set_dual_initialization(np.zeros(probs[i].n_lambda))
+            t0 = time.perf_counter(); rs.solve(rout); tt += time.perf_counter() - t0
+            assert rout.iter == iters[i]
+        out["cpu_reference_qp_per_s_per_core"] = m / tt
+        out["cpu_sample"] = "first %d QPs of the batch, 1 thread, unmodified reference; iteration counts identical" % m
+    batch.destroy()
+    return out
+
+
+def bench_sdunes(lib, reps=10):
+    """config 2: spring-mass SDUNES, md=3 Nr=4 Nh=20 -> 81 scenarios, 1417 nodes"""
+    prob = P.eliminate_x0(P.spring_mass(3, 4, 20))
+    qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+    s = capi.Sdunes(lib, qp_in)
+    z = (np.zeros(s.n_lambda), np.zeros(s.n_mu))
+    s.set_dual_initialization(*z)
+    s.upload()
+    best, e2e = 1e9, 1e9
+    for _ in range(reps):
+        s.solve_resident(); best = min(best, s.stats()["gpu_ms"])
+    for _ in range(reps):
+        s.set_dual_initialization(*z)
+        t0 = time.perf_counter(); st = s.solve(qp_out); e2e = min(e2e, 1e3 * (time.perf_counter() - t0))
+    stats = s.stats()
+    out = {"workload": "spring-mass SDUNES md=3 Nr=4 Nh=20 (81 scenarios, 1417 nodes)", "status": st, "newton_iters": qp_out.iter,
+           "ms_per_solve_resident": best, "ms_per_solve_e2e": e2e, "solves_per_s_resident": 1e3 / best,
+           "us_per_newton_iter": 1e3 * best / max(qp_out.iter, 1), "kernel_launches": stats["kernel_launches"],
+           "phases_ms": {k: round(v[0], 4) for k, v in stats["kernels"].items()}}
+    path = ref_lib_path(False)
+    if path:
+        ref = capi.TreeQpLib(path)
+        rin, rout = capi.QpIn(ref, prob), capi.QpOut(ref, prob)
+        rs = capi.Sdunes(ref, rin)
+        tb = 1e9
+        for _ in range(reps):
+            rs.set_dual_initialization(*z); rs.solve(rout); tb = min(tb, 1e3 * rout.total_time)
+        out["cpu_reference_ms_per_solve"] = tb
+        out["cpu_reference_newton_iters"] = rout.iter
+    s.destroy()
+    return out
+
+
+def bench_sharded(lib, args, rank, world, local, dist, barrier, max_over_ranks):
+    """N > 1: ONE tree (the N=1 workload) sharded by subtree over the ranks: strong scaling"""
+    def bcast(b):
+        obj = [b]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    comm = capi.Comm(lib, rank, world, local, bcast)
+    prob = workload(args.depth, 0)
+    qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+    sh = capi.TdunesSharded(lib, qp_in, comm, **OPTS)
+    sh.set_dual_initialization(np.zeros(prob.n_lambda))
+    assert sh.upload() == capi.TREEQP_OK
+    for _ in range(max(args.warmup, 1)):
+        st = sh.solve_resident()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = sh.solve_resident()
+    barrier()
+    t = max_over_ranks(time.perf_counter() - t0)
+    stats, plan = sh.stats(), sh.plan()
+    lib.lib.treeqp_b200_set_profiling(1)
+    sh.solve_resident()
+    prof = sh.stats()
+    lib.lib.treeqp_b200_set_profiling(0)
+    comm_ms = prof["kernels"].get("nccl+pack", (0.0, 0))
+    out = {"workload": "the N=1 tree (%d nodes) sharded by subtree over %d GPUs" % (prob.Nn, world), "scaling": "strong",
+           "status": st, "newton_iters": stats["iter"], "ls_trials": stats["ls_total"], "ms_per_solve": 1e3 * t / args.steps,
+           "solves_per_s": args.steps / t, "us_per_newton_iter": 1e6 * t / args.steps / max(stats["iter"], 1),
+           "cut_depth": plan["cut_depth"], "cut_nodes": plan["ncut"], "local_nodes": plan["n_local"],
+           "collectives_ms_per_solve": comm_ms[0], "collectives_per_solve": comm_ms[1]}
+    sh.destroy()
+    comm.destroy()
+    return out
+
+
 # ------------------------------------------------------------------------------------- own arm
 def main():
     ap = argparse.ArgumentParser()
@@ -195,6 +302,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--depth", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (config 4 batch, config 2 SDUNES)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -275,6 +383,13 @@ def main():
     prof = solver.stats()
     lib.lib.treeqp_b200_set_profiling(0)
 
+    sharded = None
+    if dist is not None:
+        try:
+            sharded = bench_sharded(lib, args, rank, world, local, dist, barrier, max_over_ranks)
+        except Exception as e:  # report, never hide
+            sharded = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -289,6 +404,11 @@ def main():
     alg = algorithmic_bytes(prob)
     lpc = launches_per_call(prob)
     kern = prof["kernels"]
+    fused = "k_hessian" not in kern
+    if fused:
+        # uniform trees run k_build_factor: dual gradient + Hessian blocks + Cholesky + Schur complement
+        # in one kernel per depth (event class "k_factor_level"), i.e. SURVEY 8d's K2 + K3 together
+        alg["k_factor_level"] = alg["k_gradient"] + alg["k_hessian"] + alg["k_factor_level"]
     top = max((k for k in kern if k in alg), key=lambda k: kern[k][0])
     t_ms, n_launch = kern[top]
     calls = n_launch / lpc[top]
@@ -296,7 +416,8 @@ def main():
     breakdown = {k: {"ms": round(v[0], 4), "launches": v[1],
                      "GBps": round(alg[k] * (v[1] / lpc[k]) / (v[0] * 1e-3) / 1e9, 1) if k in alg else None}
                  for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
-    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peaks, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": ("k_build_factor (fused K2+K3, one launch per depth)" if fused and top == "k_factor_level" else top),
+                "achieved": achieved, "peak": peaks, "unit": "GB/s",
                 "frac": achieved / peaks, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_call": alg[top], "launches_per_call": lpc[top],
                 "avg_launch_us": 1e3 * t_ms / n_launch, "kernel_share_of_solve": t_ms / prof["gpu_ms"],
@@ -314,6 +435,14 @@ def main():
     elif not args.no_cpu_baseline and args.gpus == 1:
         cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
 
+    extra = {}
+    if world == 1 and not args.no_extra:
+        for name, fn in (("batch4096_linear_chain", bench_batch), ("sdunes_spring_mass_cfg2", bench_sdunes)):
+            try:
+                extra[name] = fn(lib)
+            except Exception as e:
+                extra[name] = {"error": repr(e)}
+
     n = world
     out = {
         "metric": METRIC, "value": n * args.steps / t_res, "unit": UNIT, "n_gpus": n, "steps": args.steps,
@@ -330,6 +459,7 @@ def main():
                 "pack_ms": e2e_stats["pack_ms"], "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"],
                 "gpu_ms": e2e_stats["gpu_ms"]},
         "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "other_workloads": extra, "sharded_single_tree": sharded,
     }
     print(json.dumps(out))
     if dist is not None:
