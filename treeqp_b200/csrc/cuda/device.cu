@@ -72,6 +72,7 @@ struct tqb_device
     int fast, f_nx, f_nu, f_pnx;
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
     double *d_schur;
+    int *d_lvl_desc;
     /* subtree sharding (tqb_device_enable_sharding) */
     tqb_comm *comm;
     int cut_depth, ncut, my_cut0, my_ncut;
@@ -232,6 +233,22 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
     CK(cudaMalloc(&D->d_schur, sizeof(double) * ((size_t) d->Nn * NX * NX + (size_t) d->X + 4)));
     D->v.schur = D->d_schur;
     D->v.rsub = D->d_schur + (size_t) d->Nn * NX * NX;
+    {   /* level descriptors (LvlDesc): one 48-byte record per parent in level order */
+        const size_t n = (size_t) d->Np;
+        int *h = (int *) calloc(12 * n + 4, sizeof(int));
+        for (size_t e = 0; e < n; e++)
+        {
+            const int g = T.lvl_nodes[e], k0 = T.kid0[g];
+            int *r = h + 12 * e;
+            r[0] = g; r[1] = k0; r[2] = T.xoff[g]; r[3] = T.uoff[g];
+            r[4] = T.xoff[k0]; r[5] = T.aoff[k0]; r[6] = T.boff[k0]; r[7] = T.woff[g];
+            r[8] = T.utoff[g]; r[9] = T.tree[g];
+        }
+        CK(cudaMalloc(&D->d_lvl_desc, sizeof(int) * (12 * n + 4)));
+        CK(cudaMemcpy(D->d_lvl_desc, h, sizeof(int) * (12 * n + 4), cudaMemcpyHostToDevice));
+        free(h);
+        D->v.lvl_desc = D->d_lvl_desc;
+    }
     D->fast = 1;
     return 0;
 }
@@ -333,7 +350,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (!D) return;
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
-    cudaFree(D->d_schur); free(D->lvl_md); free(D->lvl_kp);
+    cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); free(D->lvl_md); free(D->lvl_kp);
     cudaFree(D->d_cut_nodes); cudaFree(D->d_send); cudaFree(D->d_recv); cudaFree(D->d_tred);
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);

@@ -30,6 +30,16 @@
 
 __host__ __device__ constexpr int tqb_ld2(int n) { return n + ((6 - (n & 3)) & 3); } /* smallest >= n with ld%4==2 */
 
+/* level descriptor: everything a warp needs to find its block, one 48-byte record per parent in
+ * level order (built at create, device.cu) -- one dependent load instead of the chain
+ * lvl_nodes -> kid0/xoff/... -> xoff[kid0]/aoff[kid0] */
+struct LvlDesc
+{
+    int g, k0, xo, uo;      /* node, first kid, offsets of the node in x-/u-space */
+    int xb, ao, bo, wo;     /* x-space offset of the block (= xoff[k0]), A/B of the kids, packed L */
+    int uto, tree, r0, r1;  /* Ut offset, owning tree */
+};
+
 template <int NX, int NU, int MD, int PNX, bool ROOT>
 struct FusedCfg
 {
@@ -37,90 +47,95 @@ struct FusedCfg
     static constexpr int NCOL = PNX + NU;           /* columns of C = [A_kids B_kids] */
     static constexpr int NUT = ROOT ? 0 : NX;       /* rows of Ut */
     static constexpr int R = D + NUT;               /* rows of the augmented matrix */
-    static constexpr bool SETB = R > 32;
+    static constexpr int NROWL = NUT < 32 - D ? NUT : 32 - D; /* Ut rows that get a lane of their own */
+    static constexpr int NCOLU = NUT - NROWL;       /* Ut rows held column-wise by the W lanes */
+    static constexpr int RL = D + NROWL;            /* lanes that own a row */
     static constexpr int LDC = tqb_ld2(NCOL > 0 ? NCOL : 2);
     static constexpr int LDR = tqb_ld2(R);
-    /* shared memory per warp, in doubles: Cp (D x LDC) | Ms (D x LDR) | p (NCOL) | z (NCOL) | ys (D) */
-    static constexpr int SMEM = D * LDC + D * LDR + 2 * (NCOL + 2) + D + 2;
+    /* shared memory per warp, in doubles: Ms (D x LDR; its head doubles as Cp, D x LDC, during the
+     * build) | p (NCOL) | z (NCOL) | ys (D) */
+    static constexpr int SM_M = D * LDR > D * LDC ? D * LDR : D * LDC;
+    static constexpr int SMEM = SM_M + 2 * (NCOL + 2) + D + 2;
 };
 
 #ifndef TQB_BF_MINBLOCKS
-#define TQB_BF_MINBLOCKS 1
+#define TQB_BF_MINBLOCKS 4
 #endif
 template <int NX, int NU, int MD, int PNX, bool ROOT>
 __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents)
 {
     using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
-    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, R = Cfg::R, LDC = Cfg::LDC, LDR = Cfg::LDR;
-    constexpr bool SETB = Cfg::SETB;
+    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, LDC = Cfg::LDC, LDR = Cfg::LDR;
+    constexpr int NROWL = Cfg::NROWL, NCOLU = Cfg::NCOLU, RL = Cfg::RL;
     static_assert(D <= 32, "block dimension must fit one warp");
+    static_assert((D & 1) == 0, "even block dimension required (vectorised rows)");
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = blockIdx.x * wpb + wib;
     if (w >= count) return;
-    const int g = v.T.lvl_nodes[lvl_begin + w];
-    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+    const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) (lvl_begin + w);
+    const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
+    if (v.status[d2.y] != TQB_RUNNING) return;
 
-    double *Cp = smem + (size_t) wib * Cfg::SMEM; /* Cp[K][c] = p_c * C[K][c] */
-    double *Ms = Cp + D * LDC;                    /* Ms[j][r] = column j of the factored augmented matrix */
-    double *ps = Ms + D * LDR;                    /* [P_p ; Rt_p] */
+    double *Ms = smem + (size_t) wib * Cfg::SMEM; /* Ms[j][r] = column j of the factored augmented matrix */
+    double *Cp = Ms;                              /* Cp[K][c] = p_c * C[K][c] (build phase only) */
+    double *ps = Ms + Cfg::SM_M;                  /* [P_p ; Rt_p] */
     double *zs = ps + NCOL + 2;                   /* [x_p ; u_p] */
     double *ys = zs + NCOL + 2;                   /* y = L^-1 resMod */
 
-    const int k0 = v.T.kid0[g];
-    const int xb = v.T.xoff[k0];                  /* this block's segment of x-space */
-    const int xo = v.T.xoff[g], uo = v.T.uoff[g];
-    const double *Ag = v.in.A + v.T.aoff[k0], *Bg = v.in.B + v.T.boff[k0];
-
-    for (int c = lane; c < NCOL; c += 32)
-    {
-        ps[c] = c < PNX ? v.P[xo + c] : v.Rt[uo + c - PNX];
-        zs[c] = c < PNX ? v.x[xo + c] : v.u[uo + c - PNX];
-    }
-    /* own row of C straight from HBM: kid k = lane/NX, A_k is NX x PNX column-major */
+    const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
     const bool isW = lane < D;
     const int kid = isW ? lane / NX : 0, ii = isW ? lane - kid * NX : 0;
-    double crow[NCOL > 0 ? NCOL : 1];
-#pragma unroll
-    for (int c = 0; c < NCOL; c++)
-    {
-        double val = 0.0;
-        if (isW) val = c < PNX ? Ag[kid * NX * PNX + ii + c * NX] : Bg[kid * NX * NU + ii + (c - PNX) * NX];
-        crow[c] = val;
-    }
-    __syncwarp();
-    /* gradient of this lane's multiplier component, and its scaled C row for the others */
-    double res = 0.0;
-    if (isW)
-    {
-        double s = 0.0;
-#pragma unroll
-        for (int c = 0; c < NCOL; c++)
-        {
-            s += crow[c] * zs[c];
-            Cp[lane * LDC + c] = crow[c] * ps[c];
-        }
-        res = (v.in.b[xb + lane] - v.x[xb + lane]) + s;
-        v.res[xb + lane] = res;
-    }
-    {   /* contribution to the termination norm (calculate_error_in_residuals, :412-442) */
-        double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
-        part = (v.o.termCondition == 2) ? warp_max(part) : warp_sum(part);
-        if (lane == 0) v.nva[g] = part;
-    }
-    double rr0 = res;
-    if (kids_are_parents && isW) rr0 -= v.rsub[xb + lane];
-    __syncwarp();
 
-    double wA[D], wB[SETB ? D : 1];
+    double wA[D], utc[NCOLU > 0 ? NCOLU : 1];
     double myinv = 0.0, rr = 0.0;
     bool small = false;
-    static_assert((D & 1) == 0, "even block dimension required (vectorised rows)");
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; attempt++)
     {
         const double shift = (v.o.regType == 1 || attempt == 1) ? v.o.regValue : 0.0;
-        /* ---- build the rows: W rows on lanes < D, Ut rows on the following rows ---- */
+        for (int c = lane; c < NCOL; c += 32)
+        {
+            ps[c] = c < PNX ? v.P[xo + c] : v.Rt[uo + c - PNX];
+            zs[c] = c < PNX ? v.x[xo + c] : v.u[uo + c - PNX];
+        }
+        /* own row of C straight from HBM: kid k = lane/NX, A_k is NX x PNX column-major */
+        double crow[NCOL > 0 ? NCOL : 1];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+        {
+            double val = 0.0;
+            if (isW) val = c < PNX ? Ag[kid * NX * PNX + ii + c * NX] : Bg[kid * NX * NU + ii + (c - PNX) * NX];
+            crow[c] = val;
+        }
+        double res = 0.0;
+        if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
+        rr = (kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0;
+        __syncwarp();
+        /* gradient of this lane's multiplier component, and its scaled C row for the others */
+        if (isW)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCOL; c++)
+            {
+                s += crow[c] * zs[c];
+                Cp[lane * LDC + c] = crow[c] * ps[c];
+            }
+            res += s;
+            v.res[xb + lane] = res;
+        }
+        rr = res - rr;
+        if (attempt == 0)
+        {   /* contribution to the termination norm (calculate_error_in_residuals, :412-442) */
+            double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
+            part = (v.o.termCondition == 2) ? warp_max(part) : warp_sum(part);
+            if (lane == 0) v.nva[g] = part;
+        }
+        __syncwarp();
+
+        /* ---- build the rows: W rows on lanes < D, Ut rows on the lanes after them ---- */
 #pragma unroll
         for (int K = 0; K < D; K++)
         {
@@ -135,6 +150,11 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
             }
             if (NCOL & 1) s += crow[NCOL - 1] * Cp[K * LDC + NCOL - 1];
             wA[K] = s;
+        }
+        if (NCOLU > 0)
+        {   /* Ut rows without a lane: element (row, K = lane) = -P_p[row] * A[K][row] */
+#pragma unroll
+            for (int cc = 0; cc < NCOLU; cc++) utc[cc] = -(crow[NROWL + cc] * ps[NROWL + cc]);
         }
         if (isW)
         {
@@ -155,21 +175,13 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
                 }
             }
         }
-        if (!ROOT)
+        else if (!ROOT && lane < RL)
         {   /* Ut rows: M[D+c][K] = -P_p[c] * A[K][c] = -Cp[K][c] */
-            if (!isW && lane < R)
-            {
 #pragma unroll
-                for (int K = 0; K < D; K++) wA[K] = -Cp[K * LDC + (lane - D)];
-            }
-            if (SETB)
-            {
-#pragma unroll
-                for (int K = 0; K < D; K++) wB[K] = (32 + lane < R) ? -Cp[K * LDC + (32 + lane - D)] : 0.0;
-            }
+            for (int K = 0; K < D; K++) wA[K] = -Cp[K * LDC + (lane - D)];
         }
-        rr = rr0;
         small = false;
+        __syncwarp(); /* Cp is dead, Ms may be written */
         /* ---- right-looking Cholesky of the augmented matrix ---- */
 #pragma unroll
         for (int j = 0; j < D; j++)
@@ -179,26 +191,40 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
             small |= (piv <= v.o.regTol);
             if (lane == j) { wA[j] = piv; myinv = inv; }
             else if (lane > j) wA[j] *= inv;
-            if (SETB) wB[j] *= inv;
             /* forward substitution of the right-hand side on the fly (dtrsv_lnn) */
             const double yj = __shfl_sync(FULL, rr, j) * inv;
             if (lane == j) rr = yj;
             else if (lane > j) rr -= wA[j] * yj;
-            __syncwarp();
-            if (lane < LDR) Ms[j * LDR + lane] = wA[j];
-            if (SETB && 32 + lane < LDR) Ms[j * LDR + 32 + lane] = wB[j];
+            if (lane < RL) Ms[j * LDR + lane] = wA[j];
+            if (NCOLU > 0 && lane == j)
+            {
+#pragma unroll
+                for (int cc = 0; cc < NCOLU; cc++)
+                {
+                    utc[cc] *= inv;
+                    Ms[j * LDR + RL + cc] = utc[cc];
+                }
+            }
             if (lane == 0) ys[j] = yj;
             __syncwarp();
+            const double lj = wA[j];
+            const double *col = Ms + j * LDR;
             if (j + 1 < D)
             {
-                const double lj = wA[j], ljB = SETB ? wB[j] : 0.0;
-                const double *col = Ms + j * LDR;
+                /* wA[k] -= L[lane][j] * L[k][j], k > j: column j broadcast from shared memory, two at a time */
+                if ((j + 1) & 1) wA[j + 1] -= lj * col[j + 1];
 #pragma unroll
-                for (int k = j + 1; k < D; k++)
+                for (int k = (j + 2) & ~1; k < D; k += 2)
                 {
-                    const double lk = col[k];
-                    wA[k] -= lj * lk;
-                    if (SETB) wB[k] -= ljB * lk;
+                    const double2 l2 = *reinterpret_cast<const double2 *>(col + k);
+                    wA[k] -= lj * l2.x;
+                    wA[k + 1] -= lj * l2.y;
+                }
+                if (NCOLU > 0)
+                {   /* Ut[c][lane] -= Utilde[c][j] * L[lane][j] on the lanes still to come */
+                    const double ljm = (isW && lane > j) ? lj : 0.0;
+#pragma unroll
+                    for (int cc = 0; cc < NCOLU; cc++) utc[cc] -= col[RL + cc] * ljm;
                 }
             }
         }
@@ -210,7 +236,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
     /* ---- results to HBM ---- */
     if (isW)
     {
-        double *Lp = v.W + v.T.woff[g] + (lane * (lane + 1)) / 2;
+        double *Lp = v.W + d1.w + (lane * (lane + 1)) / 2;
 #pragma unroll
         for (int t = 0; t < D; t++)
             if (t <= lane) Lp[t] = wA[t];
@@ -219,29 +245,40 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
     if (!ROOT)
     {
         if (isW) v.dlam[xb + lane] = rr;
-        double *Up = v.Ut + v.T.utoff[g];
-        if (!isW && lane < R)
+        double *Up = v.Ut + d2.x;
+        if (!isW && lane < RL)
         {
             double2 *dst = reinterpret_cast<double2 *>(Up + (lane - D) * D);
 #pragma unroll
             for (int t = 0; t < D / 2; t++) dst[t] = make_double2(wA[2 * t], wA[2 * t + 1]);
         }
-        if (SETB && 32 + lane < R)
+        if (NCOLU > 0 && isW)
         {
-            double2 *dst = reinterpret_cast<double2 *>(Up + (32 + lane - D) * D);
 #pragma unroll
-            for (int t = 0; t < D / 2; t++) dst[t] = make_double2(wB[2 * t], wB[2 * t + 1]);
+            for (int cc = 0; cc < NCOLU; cc++) Up[(NROWL + cc) * D + lane] = utc[cc];
         }
-        /* Schur complement for the parent's block: S = Utilde Utilde' (lower), s = Utilde y */
+        /* Schur complement for the parent's block: S = Utilde Utilde' (lower), s = Utilde y.
+         * Lower-triangle entries enumerated as a (NX/2) x (NX+1) rectangle: rows p and NX-1-p share a line */
         double *Sg = v.schur + (size_t) g * NX * NX;
-        for (int e = lane; e < NX * NX; e += 32)
+        constexpr int NE = (NX % 2 == 0) ? (NX / 2) * (NX + 1) : NX * NX;
+        for (int e = lane; e < NE; e += 32)
         {
-            const int a = e / NX, b = e - a * NX;
-            if (b > a) continue;
+            int a, b;
+            if (NX % 2 == 0)
+            {
+                const int p = e / (NX + 1), q = e - p * (NX + 1);
+                a = q <= p ? p : NX - 1 - p;
+                b = q <= p ? q : q - p - 1;
+            }
+            else
+            {
+                a = e / NX; b = e - a * NX;
+                if (b > a) continue;
+            }
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < D; j++) s += Ms[j * LDR + D + a] * Ms[j * LDR + D + b];
-            Sg[e] = s;
+            Sg[a * NX + b] = s;
         }
         for (int a = lane; a < NX; a += 32)
         {
@@ -271,10 +308,11 @@ __global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, 
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (w >= count) return;
-    const int g = v.T.lvl_nodes[lvl_begin + w];
-    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
-    const int xb = v.T.xoff[v.T.kid0[g]], xo = v.T.xoff[g];
-    const double *Lp = v.W + v.T.woff[g], *Up = v.Ut + v.T.utoff[g];
+    const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) (lvl_begin + w);
+    const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    if (v.status[d2.y] != TQB_RUNNING) return;
+    const int xb = d1.x, xo = d0.z;
+    const double *Lp = v.W + d1.w, *Up = v.Ut + d2.x;
     const bool act = lane < D;
     double lcol[D];
 #pragma unroll

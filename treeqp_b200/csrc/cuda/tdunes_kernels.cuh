@@ -36,6 +36,7 @@ struct View
     double *dlam, *res, *resMod, *xUnc, *uUnc, *P, *Rt, *Linv;
     double *qmod0, *rmod0, *dq, *dr, *cmod0, *dc; /* affine model of the stage gradients along dlam */
     double *W, *Ut;
+    const int *lvl_desc;  /* fast path: LvlDesc records (tdunes_fused.cuh), one per parent in level order */
     double *schur, *rsub; /* fast path: per-node Schur complement (NX x NX) and its rhs part (x-space) */
     double *nva, *nvb, *cva, *cvb; /* per-node and per-chunk reduction scratch */
     /* per tree */
