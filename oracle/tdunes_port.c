@@ -2,7 +2,8 @@
  * oracle/tdunes_port.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * Plain-C (column-major, no BLASFEO, no SIMD, one thread) restatement of the reference's
- * TDUNES algorithm with the clipping stage solver, used only as the checker in tests/,
+ * TDUNES algorithm with the clipping stage solver and the dense stage-QP path
+ * (dual_Newton_tree_qpoases.c; the box QP itself is restated in port_common.h), used only as the checker in tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline leg.  Nothing under treeqp_b200/ may
  * include, link or call it.
  *
@@ -31,7 +32,13 @@ typedef struct
     double *W, *L, *Ld, *Ut, *LUt;         /* per parent block */
     double *fval;
     int *xas, *uas;
+    /* dense stage-QP path: per node offset of H / P (nv*nv), projector, multipliers, scratch */
+    int *ho, nvmax;
+    double *Pd, *mudx, *mudu, *scr;
+    int fail;
 } port_work;
+
+static int is_dense(const port_qp *qp, int k) { return qp->solver != NULL && qp->solver[k] == 1; }
 
 /* utils/tree.c:171-243 (breadth-first numbering: kids of node i follow kids of node i-1)
  * and dual_Newton_tree.c:177-194 (idxpos) */
@@ -80,6 +87,18 @@ static void port_setup(const port_qp *qp, port_work *w)
     w->lam = D(X); w->dlam = D(X); w->res = D(X); w->resMod = D(X);
     w->W = D(iw); w->L = D(iw); w->Ld = D(X); w->Ut = D(iu); w->LUt = D(iu);
     w->fval = D(Nn);
+    w->ho = malloc(sizeof(int) * (Nn + 1));
+    w->ho[0] = 0; w->nvmax = 0;
+    for (int k = 0; k < Nn; k++)
+    {
+        int nv = qp->nx[k] + qp->nu[k];
+        w->ho[k + 1] = w->ho[k] + nv * nv;
+        if (nv > w->nvmax) w->nvmax = nv;
+    }
+    w->Pd = D(qp->solver ? w->ho[Nn] : 0);
+    w->mudx = D(X); w->mudu = D(U);
+    w->scr = D(4 * w->nvmax * w->nvmax + 16 * w->nvmax + 16);
+    w->fail = 0;
 #undef D
     w->xas = calloc((size_t) X + 1, sizeof(int)); w->uas = calloc((size_t) U + 1, sizeof(int));
 }
@@ -92,6 +111,27 @@ static void port_free(port_work *w)
     free(w->xUnc); free(w->uUnc); free(w->qmod); free(w->rmod); free(w->lam); free(w->dlam);
     free(w->res); free(w->resMod); free(w->W); free(w->L); free(w->Ld); free(w->Ut); free(w->LUt);
     free(w->fval); free(w->xas); free(w->uas);
+    free(w->ho); free(w->Pd); free(w->mudx); free(w->mudu); free(w->scr);
+}
+
+/* dual_Newton_tree_qpoases.c:311-357 (QProblem_solve: hotstart at g = -[qmod; rmod]) and, when
+ * `extended`, :153-214 (projector P) -- the stage solution, multipliers and working set of node k */
+static void port_dense_stage(const port_qp *qp, port_work *w, int k, int extended)
+{
+    int nx = qp->nx[k], nu = qp->nu[k], nv = nx + nu, xo = w->xo[k], uo = w->uo[k];
+    const double *H = qp->H + w->ho[k];
+    double *g = w->scr, *lb = g + nv, *ub = lb + nv, *z = ub + nv, *mu = z + nv, *t = mu + nv;
+    double *L = t + 3 * nv + nv * nv;
+    int ws[64];
+    for (int i = 0; i < nx; i++) { g[i] = w->qmod[xo + i]; lb[i] = qp->xmin[xo + i]; ub[i] = qp->xmax[xo + i]; ws[i] = w->xas[xo + i]; }
+    for (int i = 0; i < nu; i++) { g[nx + i] = w->rmod[uo + i]; lb[nx + i] = qp->umin[uo + i]; ub[nx + i] = qp->umax[uo + i]; ws[nx + i] = w->uas[uo + i]; }
+    if (port_boxqp(nv, H, g, lb, ub, ws, z, mu, L, t)) w->fail = 1;
+    for (int i = 0; i < nx; i++) w->x[xo + i] = z[i];
+    for (int i = 0; i < nu; i++) w->u[uo + i] = z[nx + i];
+    if (!extended) return;
+    for (int i = 0; i < nx; i++) { w->xas[xo + i] = ws[i]; w->mudx[xo + i] = mu[i]; }
+    for (int i = 0; i < nu; i++) { w->uas[uo + i] = ws[nx + i]; w->mudu[uo + i] = mu[nx + i]; }
+    port_boxqp_projector(nv, H, ws, w->Pd + w->ho[k], w->scr + 8 * w->nvmax);
 }
 
 /* dual_Newton_tree.c:259-292 / :862-903: modified stage gradients at the dual point lam.
@@ -133,6 +173,7 @@ static void port_solve_stage_problems(const port_qp *qp, port_work *w)
     for (int k = 0; k < qp->Nn; k++)
     {
         port_stage_gradient(qp, w, k);
+        if (is_dense(qp, k)) { port_dense_stage(qp, w, k, 1); continue; }
         for (int i = 0; i < qp->nx[k]; i++)
         {
             int g = w->xo[k] + i;
@@ -160,6 +201,22 @@ static double port_evaluate_dual_function(const port_qp *qp, port_work *w)
         double cmod = port_stage_gradient(qp, w, k);
         double xQx = 0.0, xq = 0.0, uRu = 0.0, ur = 0.0;
         int dummy;
+        if (is_dense(qp, k))
+        {   /* dual_Newton_tree_qpoases.c:478-523: x'Qx and u'Ru only -- the reference leaves the
+             * cross term u'Sx out of the dual function value, and so does this restatement */
+            int nx = qp->nx[k], nu = qp->nu[k], nv = nx + nu;
+            const double *H = qp->H + w->ho[k];
+            const double *xk = w->x + w->xo[k], *uk = w->u + w->uo[k];
+            port_dense_stage(qp, w, k, 0);
+            for (int j = 0; j < nx; j++)
+                for (int i = 0; i < nx; i++) xQx += xk[i] * H[i + j * nv] * xk[j];
+            for (int j = 0; j < nu; j++)
+                for (int i = 0; i < nu; i++) uRu += uk[i] * H[(nx + i) + (nx + j) * nv] * uk[j];
+            for (int i = 0; i < nx; i++) xq += w->qmod[w->xo[k] + i] * xk[i];
+            for (int i = 0; i < nu; i++) ur += w->rmod[w->uo[k] + i] * uk[i];
+        }
+        else
+        {
         for (int i = 0; i < qp->nx[k]; i++)
         {
             int g = w->xo[k] + i;
@@ -173,6 +230,7 @@ static double port_evaluate_dual_function(const port_qp *qp, port_work *w)
             w->u[g] = clip(w->Rinv[g] * w->rmod[g], qp->umin[g], qp->umax[g], &dummy);
             uRu += (qp->Rd[g] * w->u[g]) * w->u[g];
             ur += w->rmod[g] * w->u[g];
+        }
         }
         double f = -0.5 * xQx - cmod;
         f += xq;
@@ -224,6 +282,50 @@ static void port_dual_hessian(const port_qp *qp, port_work *w)
         int d = w->dim[p], nxp = qp->nx[p], nup = qp->nu[p];
         double *Wp = w->W + w->wo[p], *Utp = w->Ut + w->uto[p];
         const double *Pp = w->P + w->xo[p], *Rp = w->Rt + w->uo[p];
+        if (is_dense(qp, p))
+        {   /* dual_Newton_tree_qpoases.c:401-475: M_s = C_s P_p (C = [A B]), W[k,s] = C_k M_s',
+             * Ut[:,k] = -(first nx_p columns of M_k)'; the kid's own term is the xx block of ITS
+             * elimination matrix (dense kid, :430-445) or diag(P_k) (clipping kid, clipping.c:301) */
+            int nvp = nxp + nup;
+            const double *PP = w->Pd + w->ho[p];
+            double *M = malloc(sizeof(double) * (size_t) d * nvp + 8);
+            for (int jk = 0; jk < qp->nk[p]; jk++)
+            {
+                int k = w->kid0[p] + jk, nxk = qp->nx[k], rk = w->idxpos[k];
+                const double *Ak = qp->A + w->ao[k], *Bk = qp->B + w->bo[k];
+                for (int i = 0; i < nxk; i++)
+                    for (int a = 0; a < nvp; a++)
+                    {
+                        double acc = 0.0;
+                        for (int c = 0; c < nvp; c++)
+                            acc += (c < nxp ? Ak[i + c * nxk] : Bk[i + (c - nxp) * nxk]) * PP[c + a * nvp];
+                        M[(rk + i) + a * d] = acc;
+                    }
+            }
+            for (int jk = 0; jk < qp->nk[p]; jk++)
+            {
+                int k = w->kid0[p] + jk, nxk = qp->nx[k], rk = w->idxpos[k], nvk = nxk + qp->nu[k];
+                const double *Ak = qp->A + w->ao[k], *Bk = qp->B + w->bo[k];
+                for (int i = 0; i < nxk; i++)
+                    for (int J = 0; J <= rk + i; J++)
+                    {
+                        double acc = 0.0;
+                        for (int c = 0; c < nvp; c++)
+                            acc += (c < nxp ? Ak[i + c * nxk] : Bk[i + (c - nxp) * nxk]) * M[J + c * d];
+                        if (J >= rk)
+                        {
+                            if (is_dense(qp, k)) acc += w->Pd[w->ho[k] + i + (J - rk) * nvk];
+                            else if (J == rk + i) acc += w->P[w->xo[k] + i];
+                        }
+                        Wp[(rk + i) + J * d] = acc;
+                    }
+                if (w->dad[p] >= 0)
+                    for (int i = 0; i < nxk; i++)
+                        for (int c = 0; c < nxp; c++) Utp[c + (rk + i) * nxp] = -M[(rk + i) + c * d];
+            }
+            free(M);
+            continue;
+        }
         for (int jk = 0; jk < qp->nk[p]; jk++)
         {
             int k = w->kid0[p] + jk, nxk = qp->nx[k], rk = w->idxpos[k];
@@ -241,7 +343,8 @@ static void port_dual_hessian(const port_qp *qp, port_work *w)
                         double acc2 = 0.0;
                         for (int c = 0; c < nup; c++) acc2 += Bk[i + c * nxk] * (Bs[j + c * nxs] * Rp[c]);
                         acc += acc2;
-                        if (s == k && i == j) acc += w->P[w->xo[k] + i];
+                        if (s == k && is_dense(qp, k)) acc += w->Pd[w->ho[k] + i + j * (nxk + qp->nu[k])];
+                        else if (s == k && i == j) acc += w->P[w->xo[k] + i];
                         Wp[(rk + i) + (cs + j) * d] = acc;
                     }
             }
@@ -345,6 +448,7 @@ int oracle_tdunes_solve(const port_qp *qp, const port_opts *o, const double *lam
     int status = 7, it, nreg = 0;
     for (int g = 0; g < X; g++) w->Qinv[g] = 1.0 / qp->Qd[g];   /* clipping.c:163-170 */
     for (int g = 0; g < U; g++) w->Rinv[g] = 1.0 / qp->Rd[g];
+    /* dense nodes start from an empty working set (QProblemB_init is a cold start, qpoases.c:286) */
     for (int g = nx0; g < X; g++) w->lam[g] = lambda0[g - nx0];
 
     for (it = 0; it < o->maxIter; it++)
@@ -388,6 +492,13 @@ int oracle_tdunes_solve(const port_qp *qp, const port_opts *o, const double *lam
     memcpy(lam, w->lam + nx0, sizeof(double) * (X - nx0));
     for (int g = 0; g < X; g++) mu_x[g] = qp->Qd[g] * (w->xUnc[g] - x[g]);
     for (int g = 0; g < U; g++) mu_u[g] = qp->Rd[g] * (w->uUnc[g] - u[g]);
+    for (int k = 0; k < Nn; k++)
+    {   /* dual_Newton_tree_qpoases.c:527-565: multipliers of the last extended solve, sign flipped */
+        if (!is_dense(qp, k)) continue;
+        for (int i = 0; i < qp->nx[k]; i++) mu_x[w->xo[k] + i] = w->mudx[w->xo[k] + i];
+        for (int i = 0; i < qp->nu[k]; i++) mu_u[w->uo[k] + i] = w->mudu[w->uo[k] + i];
+    }
+    if (w->fail) status = 4; /* TREEQP_DN_STAGE_QP_SOLVE_FAILED */
     if (xas) memcpy(xas, w->xas, sizeof(int) * X);
     if (uas) memcpy(uas, w->uas, sizeof(int) * U);
     *iter_out = it;

@@ -23,6 +23,37 @@ def cases():
     yield "linear_chain_pinned_x0", P.linear_chain(2, 1, 2, 2, 6, seed=1, eliminate_x0=False), {}
 
 
+def dense_cases():
+    """Dense stage-QP path (qp_solver = TREEQP_QPOASES_SOLVER, dual_Newton_tree_qpoases.c): name,
+    problem, options (qp_solver is per node or a scalar)."""
+    D = P.densify
+    Q = dict(qp_solver=1)
+    yield "spring_mass_cfg1", D(P.spring_mass(3, 2, 10), 1, 0.05, 0.0), dict(Q)
+    yield "spring_mass_tight", D(P.spring_mass(3, 2, 10, xmax1=0.2), 1, 0.05, 0.05), dict(Q)
+    yield "spring_mass_diag", P.spring_mass(3, 2, 10, xmax1=0.2), dict(Q)      # diagonal weights, dense solver
+    yield "random_unconstrained", D(P.random_tree(P.multistage_nk(2, 2, 4), 5, 3, seed=6, ubound=1e12, vary_dims=True), 2, 0.2, 0.3), dict(Q)
+    yield "random_vary_dims", D(P.random_tree(P.binary_tree_nk(5), 5, 2, seed=7, ubound=0.5, vary_dims=True), 3, 0.1, 0.1), dict(Q)
+    yield "random_nx6_nu4_md3", D(P.random_tree(P.multistage_nk(3, 2, 8), 6, 4, seed=8, ubound=0.3), 4, 0.1, 0.0), dict(Q, maxIter=200)
+    yield "random_nx4_nu1_xbox", D(P.random_tree(P.multistage_nk(3, 2, 8), 4, 1, seed=9, ubound=0.2, xbound=3.0), 5, 0.05, 0.0), dict(Q, maxIter=200)
+    yield "linear_chain_nm8_md4", D(_ubox(P.linear_chain(8, 7, 4, 2, 5, seed=2), 0.3, 1e12), 6, 0.1, 0.0), dict(Q)
+    lc = _ubox(P.linear_chain(4, 3, 3, 2, 8, seed=3), 0.4, 1e12)
+    # per-node choice: dense solver on the parents, clipping on the leaves (the reference's own
+    # workspace carving only supports mixes whose dense nodes come first: create_strmat asserts
+    # 64-byte alignment after a clipping node's odd-sized data, treeqp/utils/memory.c:117)
+    yield "linear_chain_mixed", lc, dict(qp_solver=[1 if lc.nk[k] > 0 else 0 for k in range(lc.Nn)])
+
+
+def get_dense_case(name):
+    for n, p, o in dense_cases():
+        if n == name:
+            return p, o
+    raise KeyError(name)
+
+
+def dense_golden(name):
+    return np.load(os.path.join(GOLDEN, "tdunes_dense_%s.npz" % name))
+
+
 def _ubox(prob, ub, xb=None):
     prob.umin[:] = -ub
     prob.umax[:] = ub
@@ -57,6 +88,7 @@ def sdunes_cases():
 
 
 CASE_NAMES = [c[0] for c in cases()]
+DENSE_CASE_NAMES = [c[0] for c in dense_cases()]
 SDUNES_CASE_NAMES = [c[0] for c in sdunes_cases()]
 
 
@@ -80,8 +112,9 @@ def get_case(name):
 
 def checksum(prob):
     h = hashlib.sha256()
-    for name in ["nk", "nx", "nu", "A", "B", "b", "Qd", "Rd", "q", "r", "xmin", "xmax", "umin", "umax"]:
-        h.update(np.ascontiguousarray(getattr(prob, name)).tobytes())
+    for name in ["nk", "nx", "nu", "A", "B", "b", "Qd", "Rd", "Q", "R", "S", "q", "r", "xmin", "xmax", "umin", "umax"]:
+        if getattr(prob, name) is not None:
+            h.update(np.ascontiguousarray(getattr(prob, name)).tobytes())
     return h.hexdigest()
 
 
@@ -96,7 +129,7 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
 
 
-PORT_OPT_NAMES = {"checkLastActiveSet", "maxIter", "termCondition", "regType", "regTol", "regValue", "lineSearchMaxIter",
+PORT_OPT_NAMES = {"qp_solver", "checkLastActiveSet", "maxIter", "termCondition", "regType", "regTol", "regValue", "lineSearchMaxIter",
                   "lineSearchGamma", "lineSearchBeta"}
 
 

@@ -49,7 +49,7 @@ def make_spring_mass_data():
     print("spring_mass_data.npz: NX=%d NU=%d realisations=%d" % (d["NX"], d["NU"], len(d["A"]) // d["NX"] ** 2))
 
 
-from cases import cases, checksum, sdunes_cases  # noqa: E402  (tests/cases.py)
+from cases import cases, checksum, dense_cases, sdunes_cases  # noqa: E402  (tests/cases.py)
 
 
 def make_tdunes_goldens():
@@ -61,6 +61,19 @@ def make_tdunes_goldens():
                             x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u, kkt=sol.kkt,
                             input_sha256=checksum(prob), opts=repr(opts))
         print("%-28s Nn=%6d status=%d iter=%3d kkt=%.2e time=%.3f ms" % (
+            name, prob.Nn, sol.status, sol.iter, sol.kkt, 1e3 * sol.total_time))
+
+
+def make_dense_goldens():
+    """outputs of the UNMODIFIED reference with qp_solver = TREEQP_QPOASES_SOLVER (qpOASES_e stage QPs)"""
+    from treeqp_b200 import capi
+    ref = capi.TreeQpLib(os.path.join(ROOT, "oracle/_ref/libtreeqp_ref.so"))
+    for name, prob, opts in dense_cases():
+        sol = capi.solve_tdunes(ref, prob, **opts)
+        np.savez_compressed(os.path.join(HERE, "tdunes_dense_%s.npz" % name), status=sol.status, iter=sol.iter,
+                            x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u, kkt=sol.kkt,
+                            input_sha256=checksum(prob), opts=repr(opts))
+        print("dense  %-28s Nn=%6d status=%d iter=%3d kkt=%.2e time=%.3f ms" % (
             name, prob.Nn, sol.status, sol.iter, sol.kkt, 1e3 * sol.total_time))
 
 
@@ -78,7 +91,9 @@ def make_sdunes_goldens():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["data", "tdunes", "sdunes"]
+    what = sys.argv[1:] or ["data", "tdunes", "sdunes", "dense"]
+    if "dense" in what:
+        make_dense_goldens()
     if "data" in what:
         make_spring_mass_data()
     if "tdunes" in what:

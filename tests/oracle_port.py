@@ -17,7 +17,7 @@ _ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
 class PortQp(C.Structure):
     _fields_ = [("Nn", C.c_int), ("nk", _ip), ("nx", _ip), ("nu", _ip), ("A", _dp), ("B", _dp), ("b", _dp),
                 ("Qd", _dp), ("Rd", _dp), ("q", _dp), ("r", _dp), ("xmin", _dp), ("xmax", _dp),
-                ("umin", _dp), ("umax", _dp)]
+                ("umin", _dp), ("umax", _dp), ("solver", _ip), ("H", _dp)]
 
 
 class PortOpts(C.Structure):
@@ -34,7 +34,23 @@ def build_port():
     return PORT_LIB
 
 
-def solve_port(prob, lam0=None, maxIter=100, termCondition=2, tol=1e-8, regType=2, regTol=1e-6,
+def dense_blocks(prob):
+    """per node H = [Q S'; S R] ((nx+nu)^2 column-major, concatenated) and the diagonals of Q, R"""
+    H, Qd, Rd = [], [], []
+    iq = ir = is_ = 0
+    for k in range(prob.Nn):
+        nx, nu = int(prob.nx[k]), int(prob.nu[k])
+        Q = np.asarray(prob.Q[iq:iq + nx * nx]).reshape(nx, nx, order="F")
+        R = np.asarray(prob.R[ir:ir + nu * nu]).reshape(nu, nu, order="F")
+        S = np.asarray(prob.S[is_:is_ + nu * nx]).reshape(nu, nx, order="F")
+        Hk = np.block([[Q, S.T], [S, R]]) if nu else Q
+        H.append(Hk.flatten(order="F")); Qd.append(np.diag(Q).copy()); Rd.append(np.diag(R).copy())
+        iq += nx * nx; ir += nu * nu; is_ += nu * nx
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    return cat(H), cat(Qd), cat(Rd)
+
+
+def solve_port(prob, lam0=None, qp_solver=None, maxIter=100, termCondition=2, tol=1e-8, regType=2, regTol=1e-6,
                regValue=1e-6, lineSearchMaxIter=50, lineSearchGamma=0.1, lineSearchBeta=0.6):
     lib = C.CDLL(build_port())
     f = lib.oracle_tdunes_solve
@@ -49,8 +65,19 @@ def solve_port(prob, lam0=None, maxIter=100, termCondition=2, tol=1e-8, regType=
         a = np.ascontiguousarray(a, dtype=np.int32); keep[id(a)] = a
         return a.ctypes.data_as(_ip)
 
-    qp = PortQp(prob.Nn, i(prob.nk), i(prob.nx), i(prob.nu), d(prob.A), d(prob.B), d(prob.b), d(prob.Qd),
-                d(prob.Rd), d(prob.q), d(prob.r), d(prob.xmin), d(prob.xmax), d(prob.umin), d(prob.umax))
+    Qd, Rd, solver, H = prob.Qd, prob.Rd, None, None
+    if prob.Qd is None:
+        H, Qd, Rd = dense_blocks(prob)
+        assert qp_solver is not None, "dense weights need the dense stage solver"
+    if qp_solver is not None:
+        solver = i(np.full(prob.Nn, qp_solver) if np.isscalar(qp_solver) else qp_solver)
+        if H is None:   # diagonal weights through the dense path
+            H = np.concatenate([np.diag(np.concatenate([prob.Qd[xo:xo + nx], prob.Rd[uo:uo + nu]])).flatten()
+                                for xo, nx, uo, nu in zip(np.cumsum(prob.nx) - prob.nx, prob.nx,
+                                                          np.cumsum(prob.nu) - prob.nu, prob.nu)])
+        H = d(H)
+    qp = PortQp(prob.Nn, i(prob.nk), i(prob.nx), i(prob.nu), d(prob.A), d(prob.B), d(prob.b), d(Qd),
+                d(Rd), d(prob.q), d(prob.r), d(prob.xmin), d(prob.xmax), d(prob.umin), d(prob.umax), solver, H)
     o = PortOpts(maxIter, termCondition, tol, regType, regTol, regValue, lineSearchMaxIter,
                  lineSearchGamma, lineSearchBeta)
     X, U = int(np.sum(prob.nx)), int(np.sum(prob.nu))
@@ -86,7 +113,7 @@ def solve_sdunes_port(prob, lam0=None, mu0=None, checkLastActiveSet=1, maxIter=1
         return a.ctypes.data_as(_ip)
 
     qp = PortQp(prob.Nn, i(prob.nk), i(prob.nx), i(prob.nu), d(prob.A), d(prob.B), d(prob.b), d(prob.Qd),
-                d(prob.Rd), d(prob.q), d(prob.r), d(prob.xmin), d(prob.xmax), d(prob.umin), d(prob.umax))
+                d(prob.Rd), d(prob.q), d(prob.r), d(prob.xmin), d(prob.xmax), d(prob.umin), d(prob.umax), None, None)
     o = PortOpts(maxIter, termCondition, tol, regType, regTol, regValue, lineSearchMaxIter,
                  lineSearchGamma, lineSearchBeta)
     Ns, Nh, Nr, nl = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -101,3 +101,32 @@ def test_sdunes_reference_golden_iteration_counts():
     """BASELINE.md parity targets for SDUNES: 3 iterations (config 1 data), 5 (config 2)."""
     assert int(CS.sdunes_golden("spring_mass_cfg1")["iter"]) == 3
     assert int(CS.sdunes_golden("spring_mass_cfg2")["iter"]) == 5
+
+
+# ------------------------------------------------------------------ dense stage-QP path (F3)
+@pytest.mark.parametrize("name", CS.DENSE_CASE_NAMES)
+def test_dense_port_matches_reference_golden(name):
+    """oracle/tdunes_port.c dense path (box QP restated in port_common.h) versus the unmodified
+    reference running qpOASES_e: same status, Newton iterations, solution, multipliers, active sets"""
+    prob, opts = CS.get_dense_case(name)
+    g = CS.dense_golden(name)
+    assert str(g["input_sha256"]) == CS.checksum(prob), "generator drifted from the committed golden"
+    s = OP.solve_port(prob, **CS.port_opts(opts))
+    assert s["status"] == int(g["status"])
+    assert s["iter"] == int(g["iter"])
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        assert CS.rel_err(s[k], g[k]) < 1e-10, k
+    for k, lo, hi in (("x", prob.xmin, prob.xmax), ("u", prob.umin, prob.umax)):
+        assert np.array_equal(np.abs(s[k] - lo) < 1e-12, np.abs(g[k] - lo) < 1e-12)
+        assert np.array_equal(np.abs(s[k] - hi) < 1e-12, np.abs(g[k] - hi) < 1e-12)
+
+
+@pytest.mark.parametrize("name", ["spring_mass_tight", "random_nx6_nu4_md3"])
+def test_dense_port_matches_live_reference(name, ref_lib):
+    prob, opts = CS.get_dense_case(name)
+    opts = dict(opts, lineSearchBeta=0.5, lineSearchGamma=0.2)
+    r = capi.solve_tdunes(ref_lib, prob, **opts)
+    s = OP.solve_port(prob, **CS.port_opts(opts))
+    assert (s["status"], s["iter"]) == (r.status, r.iter)
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        assert CS.rel_err(s[k], getattr(r, k)) < 1e-10, k

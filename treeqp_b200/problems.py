@@ -131,6 +131,29 @@ def random_tree(nk: np.ndarray, nx: int = 12, nu: int = 4, seed: int = 0, ubound
                    meta=dict(name="random_tree", seed=seed, nx=nx, nu=nu, ubound=ubound))
 
 
+def densify(prob: Problem, seed: int = 1, coupling: float = 0.1, s_scale: float = 0.3) -> Problem:
+    """Config 5: the same QP with genuinely dense stage Hessians, as the non-diagonal branch of
+    examples/random_qp_utils/generate_random_tree.m:65-70 does: Q <- diag(Qd) + coupling*(G+G'),
+    R likewise, S ~ s_scale*U(0,1) (nu x nx).  Needs the dense stage-QP path
+    (qp_solver = TREEQP_QPOASES_SOLVER).  coupling = s_scale = 0 keeps the weights diagonal but
+    still stores them as dense blocks."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    Q, R, S = [], [], []
+    ix = iu = 0
+    for k in range(prob.Nn):
+        nx, nu = int(prob.nx[k]), int(prob.nu[k])
+        G = rng.random((nx, nx))
+        Q.append((np.diag(prob.Qd[ix:ix + nx]) + coupling * (G + G.T)).flatten(order="F"))
+        G = rng.random((nu, nu))
+        R.append((np.diag(prob.Rd[iu:iu + nu]) + coupling * (G + G.T)).flatten(order="F"))
+        S.append((s_scale * rng.random((nu, nx))).flatten(order="F"))
+        ix += nx; iu += nu
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    return Problem(nk=prob.nk, nx=prob.nx, nu=prob.nu, A=prob.A, B=prob.B, b=prob.b, q=prob.q, r=prob.r,
+                   xmin=prob.xmin, xmax=prob.xmax, umin=prob.umin, umax=prob.umax,
+                   Q=cat(Q), R=cat(R), S=cat(S), lam0=prob.lam0, meta=dict(prob.meta, dense=True))
+
+
 def binary_tree_nk(depth: int, md: int = 2) -> np.ndarray:
     """full md-ary tree with `depth` edges on every root-to-leaf path"""
     return multistage_nk(md, depth, depth)
