@@ -530,6 +530,10 @@ class TdunesBatch:
         self.opts_mem = _Buf(max(L.treeqp_tdunes_opts_calculate_size(Nn), 8))
         L.treeqp_tdunes_opts_create(Nn, C.byref(self.opts), self.opts_mem.ptr)
         L.treeqp_tdunes_opts_set_default(Nn, C.byref(self.opts))
+        qp_solver = opt_overrides.pop("qp_solver", None)
+        if qp_solver is not None:
+            for k in range(Nn):
+                self.opts.qp_solver[k] = int(qp_solver if np.isscalar(qp_solver) else qp_solver[k])
         for k, v in opt_overrides.items():
             assert hasattr(self.opts, k), k
             setattr(self.opts, k, v)

@@ -63,8 +63,8 @@ struct tqb_device
     View v;
     cudaStream_t stream;
     cudaEvent_t ev0, ev1;
-    int wpb_stage, wpb_hess, wpb_fact, wpb_back;
-    size_t sm_stage, sm_hess, sm_fact, sm_back;
+    int wpb_stage, wpb_hess, wpb_fact, wpb_back, wpb_dense;
+    size_t sm_stage, sm_hess, sm_fact, sm_back, sm_dense;
     int pw_fact, pw_back;
     long long launches;
     size_t out_doubles;
@@ -204,6 +204,7 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
     const char *env = getenv("TREEQP_B200_GENERIC");
     if (env && env[0] == '1') return 0;
     if (d->Np == 0 || d->Nn < 2) return 0;
+    if (d->has_dense) return 0; /* dense stage QPs run on the runtime-dimension kernels */
     int NX = -1, NU = -1, PNX = -1;
     D->lvl_md = (int *) calloc((size_t) d->Nh + 1, sizeof(int));
     D->lvl_kp = (int *) calloc((size_t) d->Nh + 1, sizeof(int));
@@ -275,7 +276,8 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     size_t nwork = D->out_doubles + 8 /* x u lam mux muu */
                    + 8 * X + 4 * U + 16      /* dlam res resMod xUnc P Linv qmod0 dq | uUnc Rt rmod0 dr */
                    + (size_t) d->szW + (size_t) d->szUt + 4
-                   + 4 * (size_t) d->Nn + 2 * (size_t) d->nchunk + 4;
+                   + 4 * (size_t) d->Nn + 2 * (size_t) d->nchunk + 4
+                   + (d->has_dense ? (size_t) d->szH + (size_t) d->Nn + 4 : 0);
     CK(cudaMalloc(&D->d_work, sizeof(double) * nwork));
     double *p = D->d_work;
     v.x = p; p += X; v.u = p; p += U; v.lam = p; p += X; v.mux = p; p += X; v.muu = p; p += U;
@@ -286,6 +288,8 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     p += ((uintptr_t) p & 8) ? 1 : 0;
     v.W = p; p += d->szW; v.Ut = p; p += d->szUt;
     v.nva = p; p += d->Nn; v.nvb = p; p += d->Nn; v.cmod0 = p; p += d->Nn; v.dc = p; p += d->Nn; v.cva = p; p += d->nchunk; v.cvb = p; p += d->nchunk;
+    if (d->has_dense) { v.Pd = p; p += d->szH; v.fdense = p; p += d->Nn; }
+    v.has_dense = d->has_dense; v.nvmax = d->nvmax;
     if ((size_t) (p - D->d_work) > nwork) { snprintf(g_err, sizeof g_err, "work arena overflow"); return 1; }
 
     const size_t nT = d->nT;
@@ -309,8 +313,16 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t lim = (size_t) smem_max > 8192 ? (size_t) smem_max - 2048 : 40000;
     const int ldw = d->dmax | 1, ldu = d->nxmax | 1;
-    const size_t pw_stage = 8ull * (d->abmax + d->dmax);
-    const size_t pw_hess = 8ull * (d->abmax + d->nxmax + d->numax + d->dmax);
+    v.pw_stage = d->abmax + d->dmax + (d->has_dense ? tqb_dense_smem(d->nvmax) : 0);
+    v.pw_hess = d->abmax + d->nxmax + d->numax + d->dmax +
+                (d->has_dense ? d->dmax / 2 + 1 + d->nvmax * d->nvmax + d->dmax * d->nvmax : 0);
+    const size_t pw_stage = 8ull * v.pw_stage;
+    const size_t pw_hess = 8ull * v.pw_hess;
+    if (d->has_dense)
+    {
+        if (pick_wpb(8ull * tqb_dense_smem(d->nvmax), lim, &D->wpb_dense, &D->sm_dense)) return 1;
+        CK(cudaFuncSetAttribute(k_trial_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_dense));
+    }
     D->pw_fact = ldw * d->dmax + 2 * d->dmax + ldu * d->dmax;
     D->pw_back = ldw * d->dmax + 2 * d->dmax + d->nxmax;
     if (pick_wpb(pw_stage > 8 ? pw_stage : 8, lim, &D->wpb_stage, &D->sm_stage) ||
@@ -483,6 +495,8 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     {
         int n = v.X > nT ? v.X : nT;
         if (n < 256) n = 256;
+        if (v.has_dense && n < v.U) n = v.U;
+        if (v.has_dense && n < v.Nn) n = v.Nn;
         LAUNCH(K_INIT, k_init, cdiv(n, 256), 256, 0, v);
     }
     for (int it = 0; it < o->maxIter; it++)
@@ -531,12 +545,14 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         /* affine model of the stage gradients along dlam + res'*dlam, then f(0), then trials */
         LAUNCH(K_DIR, k_stage<2>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
         LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, 0);
+        if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 1);
         LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 1);
         if (D->comm && allreduce_tree_sums(D, 1, 1, 0)) return 1;
         LAUNCH(K_DECIDE, k_decide_ls_init, tgrid, 128, 0, v);
         for (int ls = 0; ls <= o->lsMaxIter; ls++)
         {
             CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
+            if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 0);
             LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 0);
             if (D->comm && allreduce_tree_sums(D, 0, 1, 0)) return 1;
             LAUNCH(K_DECIDE, k_decide_ls_trial, tgrid, 128, 0, v);
@@ -551,6 +567,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     {
         int n = v.X > v.U ? v.X : v.U;
         LAUNCH(K_FINISH, k_finish, cdiv(n > 0 ? n : 1, 256), 256, 0, v);
+        if (v.has_dense) LAUNCH(K_FINISH, k_finish_dense, cdiv(v.Nn, 256), 256, 0, v);
     }
     CK(cudaEventRecord(D->ev1, D->stream));
     CK(cudaMemcpyAsync(h_status, v.status, sizeof(int) * (size_t) (2 * nT), cudaMemcpyDeviceToHost, D->stream));

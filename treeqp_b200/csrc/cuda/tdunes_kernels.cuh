@@ -24,8 +24,10 @@
 #include "../host/host_internal.h"
 
 #include "warp_helpers.cuh"
+#include "tdunes_dense.cuh"
 
 #define TQB_RUNNING (-1)
+#define TQB_STAGE_QP_SOLVE_FAILED 4 /* TREEQP_DN_STAGE_QP_SOLVE_FAILED, utils/types.h:55-78 */
 
 struct View
 {
@@ -49,8 +51,13 @@ struct View
      * [nT,2nT): dual function) instead of from this rank's chunk values */
     double *t_red;
     int sharded;
+    /* dense stage QPs (tdunes_dense.cuh): projectors P_k at hoff[k], dual terms of the dense nodes
+     * of the current line-search trial; for a dense node the x-/u-space slots of P/Rt hold its
+     * working set (-1, 0, +1) and those of xUnc/uUnc its bound multipliers */
+    double *Pd, *fdense;
+    int has_dense, nvmax;
     /* per-warp shared memory layout, in doubles */
-    int abmax, dmax, nxmax, numax;
+    int abmax, dmax, nxmax, numax, pw_stage, pw_hess;
     tqb_opts o;
 };
 
@@ -58,6 +65,12 @@ __global__ void k_init(View v)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < v.X) v.lam[i] = v.in.lam0[i];
+    if (v.has_dense)
+    {   /* empty working sets (QProblemB_init is a cold start, qpoases.c:286) */
+        if (i < v.X) v.P[i] = 0.0;
+        if (i < v.U) v.Rt[i] = 0.0;
+        if (i < v.Nn) v.fdense[i] = 0.0;
+    }
     if (i < v.nT)
     {
         v.status[i] = TQB_RUNNING;
@@ -94,9 +107,11 @@ __global__ void __launch_bounds__(256) k_stage(View v)
     const int t = v.T.tree[g];
     if (v.status[t] != TQB_RUNNING) return;
 
-    double *sAB = smem + (size_t) wib * (v.abmax + v.dmax);
+    double *sAB = smem + (size_t) wib * v.pw_stage;
     double *sL = sAB + v.abmax;
     const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
+    const int hoff = v.has_dense ? v.T.hoff[g] : -1;
+    double gz = 0.0; /* dense node: stage gradient component of this lane's variable */
     const int nk = v.T.nkids[g], k0 = v.T.kid0[g], d = v.T.dim[g];
     const bool root = v.T.dad[g] < 0;
     const double *src = (MODE == 2) ? v.dlam : v.lam;
@@ -152,6 +167,7 @@ __global__ void __launch_bounds__(256) k_stage(View v)
             if (isx) v.dq[xo + i] = acc; else v.dr[uo + i] = acc;
             continue;
         }
+        if (hoff >= 0) { gz = acc; continue; } /* nx + nu <= 32: one variable per lane */
         int mask;
         if (isx)
         {
@@ -181,6 +197,80 @@ __global__ void __launch_bounds__(256) k_stage(View v)
         dotp = warp_sum(dotp);
         if (lane == 0) v.nva[g] = dotp;
     }
+    if (MODE != 2 && hoff >= 0)
+    {   /* dense stage QP (stage_qp_qpoases_solve_extended / _solve, qpoases.c:360-398) */
+        const int n = nx + nu, ld = tqb_dense_ld(v.nvmax);
+        double *Hs = sL + v.dmax, *sLd = Hs + v.nvmax * ld, *sY = sLd + v.nvmax * ld, *sinv = sY + v.nvmax * ld;
+        __syncwarp();
+        warp_load_H(n, ld, v.in.H + hoff, Hs, lane);
+        const bool isx = lane < nx, act = lane < n;
+        const int i = isx ? lane : lane - nx;
+        double lb = 0.0, ub = 0.0, z = 0.0, mu = 0.0;
+        int ws = 0;
+        if (act)
+        {
+            lb = isx ? v.in.dxmin[xo + i] : v.in.dumin[uo + i];
+            ub = isx ? v.in.dxmax[xo + i] : v.in.dumax[uo + i];
+            ws = (int) (isx ? v.P[xo + i] : v.Rt[uo + i]);
+        }
+        const int fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
+        if (fail && lane == 0) v.status[t] = TQB_STAGE_QP_SOLVE_FAILED;
+        if (act)
+        {
+            if (isx) v.x[xo + i] = z; else v.u[uo + i] = z;
+            if (MODE == 0)
+            {
+                if (isx) { v.qmod0[xo + i] = gz; v.P[xo + i] = (double) ws; v.xUnc[xo + i] = mu; }
+                else { v.rmod0[uo + i] = gz; v.Rt[uo + i] = (double) ws; v.uUnc[uo + i] = mu; }
+            }
+        }
+        if (MODE == 0) warp_boxqp_projector(n, ld, ws, sLd, sinv, sY, v.Pd + hoff, lane);
+    }
+}
+
+/* Line-search trial of the dense nodes (stage_qp_qpoases_solve + eval_dual_term, qpoases.c:384,478):
+ * box QP at the stage gradient g0 + tau*dg, warm-started from the working set of the last extended
+ * solve; the node's dual term goes to fdense[g] and is picked up by k_trial's chunk reduction. */
+__global__ void __launch_bounds__(256) k_trial_dense(View v, int at_zero)
+{
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int g = blockIdx.x * wpb + wib;
+    if (g >= v.Nn) return;
+    const int hoff = v.T.hoff[g];
+    if (hoff < 0) return;
+    const int t = v.T.tree[g];
+    if (!v.ls_active[t]) return;
+    const double tau = at_zero ? 0.0 : v.t_tau[t];
+    const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
+    const int n = nx + nu, ld = tqb_dense_ld(v.nvmax);
+    double *Hs = smem + (size_t) wib * tqb_dense_smem(v.nvmax), *sLd = Hs + v.nvmax * ld, *sinv = sLd + 2 * v.nvmax * ld;
+    warp_load_H(n, ld, v.in.H + hoff, Hs, lane);
+    const bool isx = lane < nx, act = lane < n;
+    const int i = isx ? lane : lane - nx;
+    double lb = 0.0, ub = 0.0, z = 0.0, mu = 0.0, gz = 0.0;
+    int ws = 0;
+    if (act)
+    {
+        lb = isx ? v.in.dxmin[xo + i] : v.in.dumin[uo + i];
+        ub = isx ? v.in.dxmax[xo + i] : v.in.dumax[uo + i];
+        ws = (int) (isx ? v.P[xo + i] : v.Rt[uo + i]);
+        gz = isx ? v.qmod0[xo + i] + tau * v.dq[xo + i] : v.rmod0[uo + i] + tau * v.dr[uo + i];
+    }
+    const int fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
+    if (fail && lane == 0) v.status[t] = TQB_STAGE_QP_SOLVE_FAILED;
+    const double f = warp_dense_dual_term(nx, n, Hs, ld, z, gz, lane);
+    if (lane == 0) v.fdense[g] = f;
+}
+
+/* mu_x, mu_u of the dense nodes: the multipliers of the last extended solve (qpoases.c:527-565) */
+__global__ void k_finish_dense(View v)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= v.Nn || v.T.hoff[g] < 0) return;
+    const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
+    for (int i = 0; i < nx; i++) v.mux[xo + i] = v.xUnc[xo + i];
+    for (int i = 0; i < nu; i++) v.muu[uo + i] = v.uUnc[uo + i];
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -215,6 +305,8 @@ __global__ void __launch_bounds__(256) k_trial(View v, int at_zero)
     }
     for (int g = v.T.chunk_beg[c] + threadIdx.x; g < v.T.chunk_end[c]; g += 256)
         acc -= v.cmod0[g] + tau * v.dc[g];
+    if (v.has_dense)
+        for (int g = v.T.chunk_beg[c] + threadIdx.x; g < v.T.chunk_end[c]; g += 256) acc += v.fdense[g];
     sh[threadIdx.x] = acc;
     __syncthreads();
     for (int s = 128; s > 0; s >>= 1)
@@ -367,25 +459,35 @@ __global__ void __launch_bounds__(256) k_hessian(View v)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int per_warp = v.abmax + v.nxmax + v.numax + v.dmax; /* doubles; last dmax hold 2 int tables */
+    /* per warp (doubles): sAB (abmax) | sP (nxmax+numax) | row tables (dmax doubles = 2 int tables)
+     * and with dense stage QPs: kid table (dmax/2+1) | P_p (nvmax^2) | CP (dmax*nvmax) */
     const int g = blockIdx.x * wpb + wib;
     if (g >= v.Nn) return;
     const int nk = v.T.nkids[g];
     if (nk == 0) return;
     if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
 
-    double *sAB = smem + (size_t) wib * per_warp;
+    double *sAB = smem + (size_t) wib * v.pw_hess;
     double *sP = sAB + v.abmax;
     int *rbase = (int *) (sP + v.nxmax + v.numax);
     int *rstr = rbase + v.dmax;
+    int *rkid = rstr + v.dmax;                                 /* only with dense stage QPs */
+    double *sPd = (double *) (rbase + 2 * v.dmax) + v.dmax / 2 + 1; /* P_p, nv x nv */
+    double *sCP = sPd + v.nvmax * v.nvmax;                     /* C P_p, d x nv */
 
     const int nx = v.T.nx[g], nu = v.T.nu[g], d = v.T.dim[g], k0 = v.T.kid0[g];
-    const int na = d * nx, nb = d * nu;
+    const int hp = v.has_dense ? v.T.hoff[g] : -1;
+    const int na = d * nx, nb = d * nu, nv = nx + nu;
     const double *Ag = v.in.A + v.T.aoff[k0], *Bg = v.in.B + v.T.boff[k0];
     for (int e = lane; e < na; e += 32) sAB[e] = Ag[e];
     for (int e = lane; e < nb; e += 32) sAB[na + e] = Bg[e];
-    for (int e = lane; e < nx; e += 32) sP[e] = v.P[v.T.xoff[g] + e];
-    for (int e = lane; e < nu; e += 32) sP[nx + e] = v.Rt[v.T.uoff[g] + e];
+    if (hp >= 0)
+        for (int e = lane; e < nv * nv; e += 32) sPd[e] = v.Pd[hp + e];
+    else
+    {
+        for (int e = lane; e < nx; e += 32) sP[e] = v.P[v.T.xoff[g] + e];
+        for (int e = lane; e < nu; e += 32) sP[nx + e] = v.Rt[v.T.uoff[g] + e];
+    }
     /* row tables: row I of the stacked [A_kids;B_kids] belongs to a kid that starts at stacked row
      * `rows` and has nxj rows: element (I,c) of A is sAB[rows*nx + i + c*nxj], of B is
      * sAB[na + rows*nu + i + c*nxj].  rbase packs (rows<<16 | i). */
@@ -395,11 +497,30 @@ __global__ void __launch_bounds__(256) k_hessian(View v)
         for (int j = 0; j < nk; j++)
         {
             const int nxj = v.T.nx[k0 + j];
-            for (int i = 0; i < nxj; i++) { rbase[I] = rows * 65536 + i; rstr[I] = nxj; I++; }
+            for (int i = 0; i < nxj; i++)
+            {
+                rbase[I] = rows * 65536 + i; rstr[I] = nxj;
+                if (v.has_dense) rkid[I] = j;
+                I++;
+            }
             rows += nxj;
         }
     }
     __syncwarp();
+    if (hp >= 0)
+    {   /* CP[I][a] = sum_c C[I][c] P_p[c][a]  (M = C P, set_CmPnCmT qpoases.c:401-426) */
+        for (int e = lane; e < d * nv; e += 32)
+        {
+            const int I = e % d, a = e / d;
+            const int rowsI = rbase[I] >> 16, ii = rbase[I] & 65535, nxk = rstr[I];
+            const double *aI = sAB + rowsI * nx + ii, *bI = sAB + na + rowsI * nu + ii;
+            double acc = 0.0;
+            for (int c = 0; c < nx; c++) acc += aI[c * nxk] * sPd[c + a * nv];
+            for (int c = 0; c < nu; c++) acc += bI[c * nxk] * sPd[nx + c + a * nv];
+            sCP[I + a * d] = acc;
+        }
+        __syncwarp();
+    }
     double *Wp = v.W + v.T.woff[g];
     const double *Pk = v.P + v.T.xoff[k0];
     for (int J = 0; J < d; J++)
@@ -413,10 +534,29 @@ __global__ void __launch_bounds__(256) k_hessian(View v)
             const double *aI = sAB + rowsI * nx + ii;
             const double *bI = sAB + na + rowsI * nu + ii;
             double acc = 0.0, acc2 = 0.0;
-            for (int c = 0; c < nx; c++) acc += aI[c * nxk] * (aJ[c * nxs] * sP[c]);
-            for (int c = 0; c < nu; c++) acc2 += bI[c * nxk] * (bJ[c * nxs] * sP[nx + c]);
-            acc += acc2;
-            if (I == J) acc += Pk[I];
+            if (hp >= 0)
+            {   /* W[I][J] = sum_a C[I][a] (C P)[J][a] */
+                for (int c = 0; c < nx; c++) acc += aI[c * nxk] * sCP[J + c * d];
+                for (int c = 0; c < nu; c++) acc += bI[c * nxk] * sCP[J + (nx + c) * d];
+            }
+            else
+            {
+                for (int c = 0; c < nx; c++) acc += aI[c * nxk] * (aJ[c * nxs] * sP[c]);
+                for (int c = 0; c < nu; c++) acc2 += bI[c * nxk] * (bJ[c * nxs] * sP[nx + c]);
+                acc += acc2;
+            }
+            /* the kid's own term E P_k E' (add_EPmE): diagonal for a clipping kid, the xx block of
+             * its projector for a dense kid */
+            if (v.has_dense)
+            {
+                if (rkid[I] == rkid[J])
+                {
+                    const int kid = k0 + rkid[I], hk = v.T.hoff[kid];
+                    if (hk >= 0) acc += v.Pd[hk + ii + jj * (nxk + v.T.nu[kid])];
+                    else if (I == J) acc += Pk[I];
+                }
+            }
+            else if (I == J) acc += Pk[I];
             Wp[I + J * d] = acc;
         }
     }
@@ -426,6 +566,7 @@ __global__ void __launch_bounds__(256) k_hessian(View v)
         for (int e = lane; e < nx * d; e += 32)
         {
             const int c = e % nx, I = e / nx;
+            if (hp >= 0) { Utp[e] = -sCP[I + c * d]; continue; }
             const int rowsI = rbase[I] >> 16, ii = rbase[I] & 65535, nxk = rstr[I];
             Utp[e] = -(sAB[rowsI * nx + ii + c * nxk] * sP[c]);
         }

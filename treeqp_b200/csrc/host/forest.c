@@ -34,7 +34,7 @@ void tqb_layout_tables(const tqb_dims *d, int *base, tqb_tables *t)
     TK(nx, d->Nn); TK(nu, d->Nn); TK(dad, d->Nn); TK(kid0, d->Nn); TK(nkids, d->Nn);
     TK(tree, d->Nn); TK(depth, d->Nn); TK(pos, d->Nn); TK(dim, d->Nn);
     TK(xoff, d->Nn); TK(uoff, d->Nn); TK(aoff, d->Nn); TK(boff, d->Nn);
-    TK(woff, d->Nn); TK(utoff, d->Nn);
+    TK(woff, d->Nn); TK(utoff, d->Nn); TK(hoff, d->Nn);
     TK(lvl_nodes, d->Np > 0 ? d->Np : 1);
     TK(tnode0, d->nT + 1);
     TK(chunk_beg, d->nchunk); TK(chunk_end, d->nchunk); TK(chunk_tree, d->nchunk);
@@ -54,13 +54,21 @@ void tqb_layout_inputs(const tqb_dims *d, double *base, tqb_inputs *in)
     TK(b, d->X); TK(q, d->X); TK(Qd, d->X); TK(Qinv, d->X); TK(xmin, d->X); TK(xmax, d->X);
     TK(r, d->U); TK(Rd, d->U); TK(Rinv, d->U); TK(umin, d->U); TK(umax, d->U);
     TK(lam0, d->X);
+    if (d->has_dense)
+    {
+        TK(H, d->szH); TK(dxmin, d->X); TK(dxmax, d->X); TK(dumin, d->U); TK(dumax, d->U);
+    }
+    else
+        in->H = in->dxmin = in->dxmax = in->dumin = in->dumax = NULL;
 #undef TK
     assert(p - base == d->n_in);
 }
 
 static long long inputs_size(const tqb_dims *d)
 {
-    return pad2(d->szA) + pad2(d->szB) + 7 * pad2(d->X) + 5 * pad2(d->U);
+    long long n = pad2(d->szA) + pad2(d->szB) + 7 * pad2(d->X) + 5 * pad2(d->U);
+    if (d->has_dense) n += pad2(d->szH) + 2 * pad2(d->X) + 2 * pad2(d->U);
+    return n;
 }
 
 int tqb_clipping_applicable(const tree_qp_in *qp, int k)
@@ -79,9 +87,9 @@ int tqb_clipping_applicable(const tree_qp_in *qp, int k)
     return YES;
 }
 
-tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps)
+tqb_forest *tqb_forest_create(int nT, const tree_qp_in *const *qps, const int *solver)
 {
-    return tqb_forest_create_ex(nT, qps, NULL, NULL);
+    return tqb_forest_create_ex(nT, qps, NULL, NULL, solver);
 }
 
 /* number of reduction chunks of one tree: runs of owned nodes cut into pieces of TQB_CHUNK */
@@ -100,7 +108,8 @@ static int count_chunks(int N, const int *owned)
     return n;
 }
 
-tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int *ghost, const int *owned)
+tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int *ghost, const int *owned,
+                                 const int *solver)
 {
     tqb_forest *f = (tqb_forest *) calloc(1, sizeof(tqb_forest));
     tqb_dims *d = &f->dims;
@@ -111,7 +120,7 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
     d->Nn = (int) Nn;
 
     /* pass 1: counts */
-    long long X = 0, U = 0, szA = 0, szB = 0, szW = 0, szUt = 0;
+    long long X = 0, U = 0, szA = 0, szB = 0, szW = 0, szUt = 0, szH = 0;
     int Np = 0, Nh = 0, nchunk = 0;
     for (int t = 0; t < nT; t++)
     {
@@ -122,6 +131,13 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
             const struct node *nd = &qp->tree[k];
             X += qp->nx[k];
             U += qp->nu[k];
+            if (solver && solver[k] == TREEQP_QPOASES_SOLVER)
+            {
+                const int nv = qp->nx[k] + qp->nu[k];
+                szH += (long long) nv * nv;
+                d->has_dense = 1;
+                if (nv > d->nvmax) d->nvmax = nv;
+            }
             if (nd->stage > Nh) Nh = nd->stage;
             if (k > 0)
             {
@@ -138,15 +154,15 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
             }
         }
     }
-    if (X > 2000000000LL || szA > 2000000000LL || szW > 2000000000LL || szB > 2000000000LL)
+    if (X > 2000000000LL || szA > 2000000000LL || szW > 2000000000LL || szB > 2000000000LL || szH > 2000000000LL)
     {
         fprintf(stderr, "[treeqp_b200] problem too large for 32-bit element offsets\n");
         free(f);
         return NULL;
     }
-    d->X = (int) X; d->U = (int) U; d->szA = szA; d->szB = szB; d->szW = szW; d->szUt = szUt;
+    d->X = (int) X; d->U = (int) U; d->szA = szA; d->szB = szB; d->szW = szW; d->szUt = szUt; d->szH = szH;
     d->Np = Np; d->Nh = Nh; d->nchunk = nchunk;
-    d->n_int = 15 * d->Nn + (Np > 0 ? Np : 1) + 2 * (nT + 1) + 7 * nchunk;
+    d->n_int = 16 * d->Nn + (Np > 0 ? Np : 1) + 2 * (nT + 1) + 7 * nchunk;
     d->n_in = inputs_size(d);
 
     f->h_int = (int *) malloc(sizeof(int) * (size_t) d->n_int);
@@ -154,7 +170,7 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
     tqb_tables *T = &f->ht;
 
     /* pass 2: tables */
-    int g0 = 0, xo = 0, uo = 0, ao = 0, bo = 0, wo = 0, uto = 0, c = 0;
+    int g0 = 0, xo = 0, uo = 0, ao = 0, bo = 0, wo = 0, uto = 0, c = 0, ho = 0;
     int *lvl_count = (int *) calloc((size_t) Nh + 2, sizeof(int));
     for (int t = 0; t < nT; t++)
     {
@@ -185,6 +201,12 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
             T->depth[g] = nd->stage;
             T->xoff[g] = xo; xo += qp->nx[k];
             T->uoff[g] = uo; uo += qp->nu[k];
+            T->hoff[g] = -1;
+            if (solver && solver[k] == TREEQP_QPOASES_SOLVER)
+            {
+                T->hoff[g] = ho;
+                ho += (qp->nx[k] + qp->nu[k]) * (qp->nx[k] + qp->nu[k]);
+            }
             T->aoff[g] = ao; T->boff[g] = bo;
             if (k > 0)
             {
@@ -307,6 +329,36 @@ void tqb_forest_pack_mapped_(tqb_forest *f, int t, const tree_qp_in *qp, const i
         }
         else
             for (int i = 0; i < nx; i++) in->b[xo + i] = 0.0;
+        memcpy(in->q + xo, qp->q[k].pa, sizeof(double) * (size_t) nx);
+        memcpy(in->r + uo, qp->r[k].pa, sizeof(double) * (size_t) nu);
+        if (T->hoff[g] >= 0)
+        {   /* dense stage QP (stage_qp_qpoases_init, dual_Newton_tree_qpoases.c:241-249):
+             * H = [Q S'; S R] column-major, real bounds in the d* arrays */
+            const int nv = nx + nu;
+            double *H = in->H + T->hoff[g];
+            for (int j = 0; j < nx; j++)
+            {
+                for (int i = 0; i < nx; i++) H[i + j * nv] = BLASFEO_DMATEL(&qp->Q[k], i, j);
+                for (int i = 0; i < nu; i++) H[nx + i + j * nv] = H[j + (nx + i) * nv] = BLASFEO_DMATEL(&qp->S[k], i, j);
+            }
+            for (int j = 0; j < nu; j++)
+                for (int i = 0; i < nu; i++) H[nx + i + (nx + j) * nv] = BLASFEO_DMATEL(&qp->R[k], i, j);
+            memcpy(in->dxmin + xo, qp->xmin[k].pa, sizeof(double) * (size_t) nx);
+            memcpy(in->dxmax + xo, qp->xmax[k].pa, sizeof(double) * (size_t) nx);
+            memcpy(in->dumin + uo, qp->umin[k].pa, sizeof(double) * (size_t) nu);
+            memcpy(in->dumax + uo, qp->umax[k].pa, sizeof(double) * (size_t) nu);
+            for (int i = 0; i < nx; i++)
+            {
+                in->Qd[xo + i] = 1.0; in->Qinv[xo + i] = 0.0;
+                in->xmin[xo + i] = -1e300; in->xmax[xo + i] = 1e300;
+            }
+            for (int i = 0; i < nu; i++)
+            {
+                in->Rd[uo + i] = 1.0; in->Rinv[uo + i] = 0.0;
+                in->umin[uo + i] = -1e300; in->umax[uo + i] = 1e300;
+            }
+            continue;
+        }
         for (int i = 0; i < nx; i++)
         {
             double w = BLASFEO_DMATEL(&qp->Q[k], i, i);
@@ -319,10 +371,8 @@ void tqb_forest_pack_mapped_(tqb_forest *f, int t, const tree_qp_in *qp, const i
             in->Rd[uo + i] = w;
             in->Rinv[uo + i] = 1.0 / w;
         }
-        memcpy(in->q + xo, qp->q[k].pa, sizeof(double) * (size_t) nx);
         memcpy(in->xmin + xo, qp->xmin[k].pa, sizeof(double) * (size_t) nx);
         memcpy(in->xmax + xo, qp->xmax[k].pa, sizeof(double) * (size_t) nx);
-        memcpy(in->r + uo, qp->r[k].pa, sizeof(double) * (size_t) nu);
         memcpy(in->umin + uo, qp->umin[k].pa, sizeof(double) * (size_t) nu);
         memcpy(in->umax + uo, qp->umax[k].pa, sizeof(double) * (size_t) nu);
     }

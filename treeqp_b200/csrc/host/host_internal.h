@@ -36,6 +36,7 @@ typedef struct tqb_tables
     int *xoff, *uoff;    /* [Nn] offsets into x-/u-space */
     int *aoff, *boff;    /* [Nn] offsets of A_k (nx[k] x nx[dad]) / B_k (nx[k] x nu[dad]), column-major */
     int *woff, *utoff;   /* [Nn] offsets of W_p / Ut_p */
+    int *hoff;           /* [Nn] dense stage QP: offset of H_k / P_k ((nx+nu)^2 doubles), -1 = clipping node */
     int *lvl_nodes;      /* [Np] parents sorted by depth (level lists) */
     int *tnode0;         /* [nT+1] node range of each tree */
     int *chunk_beg, *chunk_end, *chunk_tree; /* [nchunk] fixed-shape reduction chunks (node ranges) */
@@ -48,6 +49,8 @@ typedef struct tqb_dims
     int nT, Nn, Np, Nh;  /* trees, nodes, parents, max depth */
     int X, U;            /* x-/u-space sizes */
     long long szA, szB, szW, szUt;
+    long long szH;       /* doubles in the dense stage Hessians (0: every node uses clipping) */
+    int has_dense, nvmax; /* any dense stage QP; largest nx+nu among them */
     int dmax, nxmax, numax, nkmax, abmax; /* abmax = max over parents of dim*(nx+nu) */
     int nchunk;
     int n_int;           /* ints in the table block */
@@ -62,6 +65,11 @@ typedef struct tqb_inputs
     double *q, *Qd, *Qinv, *xmin, *xmax; /* [X] */
     double *r, *Rd, *Rinv, *umin, *umax; /* [U] */
     double *lam0;        /* [X] dual start, lambda_k at xoff[k] */
+    /* dense stage QPs (only allocated when dims.has_dense): H_k = [Q S'; S R] column-major at
+     * hoff[k], and the bounds of the dense nodes (their slots in xmin.. hold +-1e300 so that the
+     * vector-only line-search kernel sees an inactive, weightless variable) */
+    double *H;           /* [szH] */
+    double *dxmin, *dxmax, *dumin, *dumax; /* [X] [X] [U] [U] */
 } tqb_inputs;
 
 /* ---- options forwarded to the device ---- */
@@ -100,10 +108,12 @@ typedef struct tqb_forest
 /* ---- forest.c ---- */
 struct tree_qp_in_;
 struct tree_qp_out_;
-tqb_forest *tqb_forest_create(int nT, const struct tree_qp_in_ *const *qps);
+/* `solver`: stage QP solver per node (stage_qp_t values, the same for every tree of the forest), NULL = clipping */
+tqb_forest *tqb_forest_create(int nT, const struct tree_qp_in_ *const *qps, const int *solver);
 /* general form: `ghost` marks nodes to be treated as parents whose block lives elsewhere, `owned`
  * restricts the reduction chunks (both per node, NULL = none / all) */
-tqb_forest *tqb_forest_create_ex(int nT, const struct tree_qp_in_ *const *qps, const int *ghost, const int *owned);
+tqb_forest *tqb_forest_create_ex(int nT, const struct tree_qp_in_ *const *qps, const int *ghost, const int *owned,
+                                 const int *solver);
 void tqb_forest_destroy(tqb_forest *f);
 /* BLASFEO views -> pinned staging (reciprocals of the weights are formed here,
  * dual_Newton_tree_clipping.c:149-170) */

@@ -121,7 +121,7 @@ tqb_forest *tqb_forest_create_sharded(const tree_qp_in *full_qp, const tqb_shard
     shell.nx = plan->lnx; shell.nu = plan->lnu; shell.nc = plan->lnc;
     shell.tree = plan->ltree;
     const tree_qp_in *one[1] = {&shell};
-    tqb_forest *f = tqb_forest_create_ex(1, one, plan->ghost, plan->owned);
+    tqb_forest *f = tqb_forest_create_ex(1, one, plan->ghost, plan->owned, NULL);
     if (!f) return NULL;
     int *cut_local = (int *) malloc(sizeof(int) * (size_t) plan->ncut);
     for (int q = 0; q < plan->ncut; q++) cut_local[q] = plan->cut_first + q; /* the top keeps its numbering */

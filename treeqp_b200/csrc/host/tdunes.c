@@ -131,9 +131,14 @@ static void check_stage_solvers(const tree_qp_in *qp_in, const treeqp_tdunes_opt
             }
         }
         else if (opts->qp_solver[k] == TREEQP_QPOASES_SOLVER)
-        {
-            printf("[TREEQP_B200]: Error! Dense stage QPs are not available in this build.\n");
-            exit(1);
+        {   /* dense stage QP: one warp per node, one lane per variable; general constraints are a
+             * "next" row */
+            if (qp_in->nc[k] > 0 || qp_in->nx[k] + qp_in->nu[k] > 32)
+            {
+                printf("[TREEQP_B200]: Error! Dense stage QPs need nc = 0 and nx + nu <= 32 (node %d: nx=%d nu=%d nc=%d).\n",
+                       k, qp_in->nx[k], qp_in->nu[k], qp_in->nc[k]);
+                exit(1);
+            }
         }
         else
         {   /* dual_Newton_tree.c:158-160 */
@@ -183,7 +188,7 @@ void treeqp_tdunes_create(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *o
     tqb_ctx *ctx = (tqb_ctx *) calloc(1, sizeof(tqb_ctx));
     ctx->magic = TQB_MAGIC;
     const tree_qp_in *one[1] = {qp_in};
-    ctx->forest = tqb_forest_create(1, one);
+    ctx->forest = tqb_forest_create(1, one, (const int *) opts->qp_solver);
     if (!ctx->forest)
     {
         fprintf(stderr, "[treeqp_b200] treeqp_tdunes_create: no device arena (%s); solve will return "
@@ -360,7 +365,7 @@ treeqp_tdunes_batch *treeqp_tdunes_batch_create(int n, const tree_qp_in *const *
     for (int i = 0; i < n; i++) check_stage_solvers(qp_in[i], opts);
     treeqp_tdunes_batch *b = (treeqp_tdunes_batch *) calloc(1, sizeof *b);
     b->n = n;
-    b->forest = tqb_forest_create(n, qp_in);
+    b->forest = tqb_forest_create(n, qp_in, (const int *) opts->qp_solver);
     if (!b->forest) { free(b); return NULL; }
     memset(b->forest->hin.lam0, 0, sizeof(double) * (size_t) b->forest->dims.X);
     b->opts_ok = validate_opts(opts) == TREEQP_OK;
@@ -496,6 +501,12 @@ treeqp_tdunes_sharded *treeqp_tdunes_sharded_create(const tree_qp_in *qp_in, con
 {
     if (!comm) return NULL;
     check_stage_solvers(qp_in, opts);
+    for (int k = 0; k < qp_in->N; k++)
+        if (opts->qp_solver[k] != TREEQP_CLIPPING_SOLVER)
+        {
+            fprintf(stderr, "[treeqp_b200] subtree sharding supports the clipping stage solver only\n");
+            return NULL;
+        }
     tqb_shard_plan *plan = tqb_shard_plan_create(qp_in, tqb_comm_rank(comm->c), tqb_comm_size(comm->c));
     if (!plan) return NULL;
     treeqp_tdunes_sharded *sh = (treeqp_tdunes_sharded *) calloc(1, sizeof *sh);
