@@ -131,8 +131,31 @@ static bool fused_supported(int nx, int nu, int md)
     return false;
 }
 
+/* launch with programmatic stream serialisation (see pdl_wait in tdunes_fused.cuh); plain launch
+ * while profiling (the event records between launches would serialise them anyway) or with
+ * TREEQP_B200_NO_PDL=1 */
+static int g_pdl = -1;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args)
+{
+    if (g_pdl < 0)
+    {
+        const char *e = getenv("TREEQP_B200_NO_PDL");
+        g_pdl = (e && e[0] == '1') ? 0 : 1;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (pdl && g_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int NX, int NU, int MD, int PNX, bool ROOT>
-static int launch_bf(tqb_device *D, int begin, int cnt, int kp)
+static int launch_bf(tqb_device *D, int begin, int cnt, int kp, int pre_ok)
 {
     using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
     static bool attr_done = false;
@@ -145,7 +168,8 @@ static int launch_bf(tqb_device *D, int begin, int cnt, int kp)
     }
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
-    k_build_factor<NX, NU, MD, PNX, ROOT><<<(cnt + wpb - 1) / wpb, 32 * wpb, smem, D->stream>>>(D->v, begin, cnt, kp);
+    CK(launch_pdl(k_build_factor<NX, NU, MD, PNX, ROOT>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
+                  D->v, begin, cnt, kp, pre_ok));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
     return 0;
@@ -157,13 +181,13 @@ static int launch_bs(tqb_device *D, int begin, int cnt)
     const int wpb = 4;
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
-    k_backsolve_fused<NX, MD><<<(cnt + wpb - 1) / wpb, 32 * wpb, 0, D->stream>>>(D->v, begin, cnt);
+    CK(launch_pdl(k_backsolve_fused<NX, MD>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, begin, cnt));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
     return 0;
 }
 
-static int fused_factor_level(tqb_device *D, int l)
+static int fused_factor_level(tqb_device *D, int l, int pre_ok)
 {
     const int begin = D->lvl_ptr[l], cnt = D->lvl_ptr[l + 1] - begin;
     if (cnt <= 0) return 0;
@@ -172,9 +196,9 @@ static int fused_factor_level(tqb_device *D, int l)
 #define X(a, b, c)                                                                   \
     if (nx == a && nu == b && md == c)                                               \
     {                                                                                \
-        if (!root) return launch_bf<a, b, c, a, false>(D, begin, cnt, kp);           \
-        if (pnx0) return launch_bf<a, b, c, 0, true>(D, begin, cnt, kp);             \
-        return launch_bf<a, b, c, a, true>(D, begin, cnt, kp);                       \
+        if (!root) return launch_bf<a, b, c, a, false>(D, begin, cnt, kp, pre_ok);   \
+        if (pnx0) return launch_bf<a, b, c, 0, true>(D, begin, cnt, kp, pre_ok);     \
+        return launch_bf<a, b, c, a, true>(D, begin, cnt, kp, pre_ok);               \
     }
     TQB_FUSED_LIST(X)
 #undef X
@@ -276,7 +300,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     size_t nwork = D->out_doubles + 8 /* x u lam mux muu */
                    + 8 * X + 4 * U + 16      /* dlam res resMod xUnc P Linv qmod0 dq | uUnc Rt rmod0 dr */
                    + (size_t) d->szW + (size_t) d->szUt + 4
-                   + 4 * (size_t) d->Nn + 2 * (size_t) d->nchunk + 4
+                   + 4 * (size_t) d->Nn + (1 + TQB_LS_NT) * (size_t) d->nchunk + 4
                    + (d->has_dense ? (size_t) d->szH + (size_t) d->Nn + 4 : 0);
     CK(cudaMalloc(&D->d_work, sizeof(double) * nwork));
     double *p = D->d_work;
@@ -287,7 +311,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     v.qmod0 = p; p += X; v.dq = p; p += X; v.rmod0 = p; p += U; v.dr = p; p += U;
     p += ((uintptr_t) p & 8) ? 1 : 0;
     v.W = p; p += d->szW; v.Ut = p; p += d->szUt;
-    v.nva = p; p += d->Nn; v.nvb = p; p += d->Nn; v.cmod0 = p; p += d->Nn; v.dc = p; p += d->Nn; v.cva = p; p += d->nchunk; v.cvb = p; p += d->nchunk;
+    v.nva = p; p += d->Nn; v.nvb = p; p += d->Nn; v.cmod0 = p; p += d->Nn; v.dc = p; p += d->Nn; v.cva = p; p += d->nchunk; v.cvb = p; p += (size_t) TQB_LS_NT * d->nchunk;
     if (d->has_dense) { v.Pd = p; p += d->szH; v.fdense = p; p += d->Nn; }
     v.has_dense = d->has_dense; v.nvmax = d->nvmax;
     if ((size_t) (p - D->d_work) > nwork) { snprintf(g_err, sizeof g_err, "work arena overflow"); return 1; }
@@ -300,7 +324,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     v.restart_cnt = v.ls_active + nT; v.counters = v.restart_cnt + nT; v.ls_hist = v.counters + 4;
     v.t_f0 = D->d_tdbl; v.t_dot = v.t_f0 + nT; v.t_tau = v.t_dot + nT; v.t_tauprev = v.t_tau + nT;
     v.t_err = v.t_tauprev + nT; v.t_taufin = v.t_err + nT;
-    CK(cudaMallocHost(&D->h_counters, sizeof(int) * 4));
+    CK(cudaMallocHost(&D->h_counters, sizeof(int) * 8));
 
     v.Nn = d->Nn; v.nT = d->nT; v.X = d->X; v.U = d->U; v.nchunk = d->nchunk;
     v.abmax = d->abmax; v.dmax = d->dmax; v.nxmax = d->nxmax; v.numax = d->numax;
@@ -408,13 +432,6 @@ extern "C" int tqb_device_download(tqb_device *D, double *h_out, double *ms)
 
 static inline int cdiv(long long a, int b) { return (int) ((a + b - 1) / b); }
 
-static int read_counters(tqb_device *D)
-{
-    CK(cudaMemcpyAsync(D->h_counters, D->v.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, D->stream));
-    CK(cudaStreamSynchronize(D->stream));
-    return 0;
-}
-
 extern "C" int tqb_device_enable_sharding(tqb_device *D, tqb_comm *comm, int cut_depth, int ncut, int my_cut0,
                                           int my_ncut, const int *cut_nodes_local)
 {
@@ -430,7 +447,7 @@ extern "C" int tqb_device_enable_sharding(tqb_device *D, tqb_comm *comm, int cut
     CK(cudaMemcpy(D->d_cut_nodes, cut_nodes_local, sizeof(int) * (size_t) ncut, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&D->d_send, sizeof(double) * per * (size_t) my_ncut));
     CK(cudaMalloc(&D->d_recv, sizeof(double) * per * (size_t) ncut));
-    CK(cudaMalloc(&D->d_tred, sizeof(double) * 2 * (size_t) D->dims.nT));
+    CK(cudaMalloc(&D->d_tred, sizeof(double) * (1 + TQB_LS_NT) * (size_t) D->dims.nT));
     D->v.t_red = D->d_tred;
     D->v.sharded = 1;
     return 0;
@@ -472,6 +489,28 @@ static int allreduce_tree_sums(tqb_device *D, int use_a, int use_b, int a_is_max
     return rc;
 }
 
+/* batched line search: res'*dlam (first batch only) and the NT dual function values per tree */
+static int allreduce_ls_batch(tqb_device *D, int first)
+{
+    View &v = D->v;
+    const int nT = D->dims.nT;
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
+    k_tree_partial_ls<<<dim3((nT + 3) / 4, 1 + TQB_LS_NT), 128, 0, D->stream>>>(v, D->d_tred);
+    D->launches++;
+    const size_t off = first ? 0 : (size_t) nT;
+    const int rc = tqb_comm_allreduce(D->comm, D->d_tred + off, (size_t) (1 + TQB_LS_NT) * nT - off, 0, D->stream);
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    return rc;
+}
+
+/* counters[idx] -> pinned slot, stream-ordered; read after the next synchronisation */
+static int peek_counter(tqb_device *D, int idx, int slot)
+{
+    CK(cudaMemcpyAsync(D->h_counters + slot, D->v.counters + idx, sizeof(int), cudaMemcpyDeviceToHost, D->stream));
+    return 0;
+}
+
 extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status, int *h_iter,
                                 int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms,
                                 long long *launches, double *kernel_ms16, int *kernel_count16)
@@ -495,10 +534,13 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     {
         int n = v.X > nT ? v.X : nT;
         if (n < 256) n = 256;
+        if (n < v.Nn) n = v.Nn;
         if (v.has_dense && n < v.U) n = v.U;
-        if (v.has_dense && n < v.Nn) n = v.Nn;
         LAUNCH(K_INIT, k_init, cdiv(n, 256), 256, 0, v);
     }
+    /* Host round trips: ONE per Newton iteration (after the first line-search batch).  The
+     * termination counter is fetched asynchronously and everything behind the termination test is
+     * enqueued at once: kernels of a finished tree return at their status check. */
     for (int it = 0; it < o->maxIter; it++)
     {
         CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
@@ -506,17 +548,16 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         if (D->fast)
         {   /* gradient + Hessian + factorisation fused, leaves to root; the termination test comes
              * after the sweep (the sweep of the last iteration is the price of the fusion) */
-            CK(cudaMemsetAsync(v.nva, 0, sizeof(double) * (size_t) v.Nn, D->stream));
             for (int l = Nh - 1; l >= 0; l--)
             {
-                if (D->comm && l == D->cut_depth - 1 && exchange_cut_nodes(D)) return 1;
-                if (fused_factor_level(D, l)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+                const bool exch = D->comm && l == D->cut_depth - 1;
+                if (exch && exchange_cut_nodes(D)) return 1;
+                if (fused_factor_level(D, l, (l < Nh - 1 && !exch) ? 1 : 0)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
             }
             LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
             if (D->comm && allreduce_tree_sums(D, 1, 0, o->termCondition == 2)) return 1;
             LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
-            if (read_counters(D)) return 1;
-            if (D->h_counters[0] == 0) break;
+            if (peek_counter(D, 0, 4)) return 1;
             for (int l = 1; l < Nh; l++)
                 if (fused_backsolve_level(D, l)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
         }
@@ -525,8 +566,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             LAUNCH(K_GRAD, k_gradient, cdiv(v.Nn, 8), 256, 0, v);
             LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
             LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
-            if (read_counters(D)) return 1;
-            if (D->h_counters[0] == 0) break;
+            if (peek_counter(D, 0, 4)) return 1;
 
             LAUNCH(K_HESS, k_hessian, cdiv(v.Nn, D->wpb_hess), 32 * D->wpb_hess, D->sm_hess, v);
             for (int l = Nh - 1; l >= 0; l--)
@@ -542,23 +582,40 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                     LAUNCH(K_BACK, k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back);
             }
         }
-        /* affine model of the stage gradients along dlam + res'*dlam, then f(0), then trials */
+        /* affine model of the stage gradients along dlam + res'*dlam, then the line search */
         LAUNCH(K_DIR, k_stage<2>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
-        LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, 0);
-        if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 1);
-        LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 1);
-        if (D->comm && allreduce_tree_sums(D, 1, 1, 0)) return 1;
-        LAUNCH(K_DECIDE, k_decide_ls_init, tgrid, 128, 0, v);
-        for (int ls = 0; ls <= o->lsMaxIter; ls++)
-        {
-            CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
-            if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 0);
-            LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 0);
-            if (D->comm && allreduce_tree_sums(D, 0, 1, 0)) return 1;
-            LAUNCH(K_DECIDE, k_decide_ls_trial, tgrid, 128, 0, v);
-            if (read_counters(D)) return 1;
-            if (D->h_counters[1] == 0) break;
+        if (!v.has_dense)
+        {   /* f(0), res'*dlam and the first TQB_LS_NT-1 step lengths in one pass, Armijo on the device */
+            for (int batch = 0; batch * TQB_LS_NT <= o->lsMaxIter + 1; batch++)
+            {
+                LAUNCH(K_TRIAL, k_ls_eval, v.nchunk, 256, 0, v, batch == 0);
+                if (D->comm && allreduce_ls_batch(D, batch == 0)) return 1;
+                LAUNCH(K_DECIDE, k_ls_decide, tgrid, 128, 0, v, batch == 0);
+                if (peek_counter(D, 1, 5)) return 1;
+                CK(cudaStreamSynchronize(D->stream));
+                if (D->h_counters[4] == 0 || D->h_counters[5] == 0) break;
+            }
         }
+        else
+        {
+            LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nvb, v.cva, 0);
+            LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 1);
+            LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 1);
+            if (D->comm && allreduce_tree_sums(D, 1, 1, 0)) return 1;
+            LAUNCH(K_DECIDE, k_decide_ls_init, tgrid, 128, 0, v);
+            for (int ls = 0; ls <= o->lsMaxIter; ls++)
+            {
+                CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
+                LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 0);
+                LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 0);
+                if (D->comm && allreduce_tree_sums(D, 0, 1, 0)) return 1;
+                LAUNCH(K_DECIDE, k_decide_ls_trial, tgrid, 128, 0, v);
+                if (peek_counter(D, 1, 5)) return 1;
+                CK(cudaStreamSynchronize(D->stream));
+                if (D->h_counters[4] == 0 || D->h_counters[5] == 0) break;
+            }
+        }
+        if (D->h_counters[4] == 0) break; /* every tree has terminated */
         LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
     }
     /* trees that ran out of iterations: x,u of the last trial point (what the reference holds) */

@@ -28,6 +28,15 @@
 #pragma once
 #include "tdunes_kernels.cuh"
 
+/* Programmatic dependent launch (sm_90+): the level kernels of one sweep are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so level l starts while level l+1 still
+ * runs, does everything that does not depend on it (descriptor + A/B loads, gradient, the
+ * C diag(P,Rt) C' build; for the substitution: the loads of L and Utilde) and only then waits.
+ * Every warp waits before it exits (keeps completion transitive along the chain), and releases
+ * its own dependents right after its wait. */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __host__ __device__ constexpr int tqb_ld2(int n) { return n + ((6 - (n & 3)) & 3); } /* smallest >= n with ld%4==2 */
 
 /* level descriptor: everything a warp needs to find its block, one 48-byte record per parent in
@@ -53,16 +62,16 @@ struct FusedCfg
     static constexpr int LDC = tqb_ld2(NCOL > 0 ? NCOL : 2);
     static constexpr int LDR = tqb_ld2(R);
     /* shared memory per warp, in doubles: Ms (D x LDR; its head doubles as Cp, D x LDC, during the
-     * build) | p (NCOL) | z (NCOL) | ys (D) */
+     * build) | p (NCOL) | z (NCOL) | ys (D) | dgs (D) | invs (D) */
     static constexpr int SM_M = D * LDR > D * LDC ? D * LDR : D * LDC;
-    static constexpr int SMEM = SM_M + 2 * (NCOL + 2) + D + 2;
+    static constexpr int SMEM = SM_M + 2 * (NCOL + 2) + 3 * D + 2;
 };
 
 #ifndef TQB_BF_MINBLOCKS
 #define TQB_BF_MINBLOCKS 4
 #endif
 template <int NX, int NU, int MD, int PNX, bool ROOT>
-__global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents)
+__global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents, int pre_ok)
 {
     using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
     constexpr int D = Cfg::D, NCOL = Cfg::NCOL, LDC = Cfg::LDC, LDR = Cfg::LDR;
@@ -72,17 +81,21 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = blockIdx.x * wpb + wib;
-    if (w >= count) return;
+    /* pre_ok = 0: the launch before this one wrote data read by the build phase (k_stage<0> before
+     * the bottom level, the cut-node exchange of a sharded solve): wait first */
+    if (!pre_ok) { pdl_wait(); pdl_release(); }
+    if (w >= count) { pdl_wait(); pdl_release(); return; }
     const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) (lvl_begin + w);
     const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
     const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
-    if (v.status[d2.y] != TQB_RUNNING) return;
+    if (v.status[d2.y] != TQB_RUNNING) { pdl_wait(); pdl_release(); return; }
 
     double *Ms = smem + (size_t) wib * Cfg::SMEM; /* Ms[j][r] = column j of the factored augmented matrix */
     double *Cp = Ms;                              /* Cp[K][c] = p_c * C[K][c] (build phase only) */
     double *ps = Ms + Cfg::SM_M;                  /* [P_p ; Rt_p] */
     double *zs = ps + NCOL + 2;                   /* [x_p ; u_p] */
     double *ys = zs + NCOL + 2;                   /* y = L^-1 resMod */
+    double *dgs = ys + D, *invs = dgs + D;        /* diagonal of L and its inverse */
 
     const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
     const bool isW = lane < D;
@@ -111,7 +124,6 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
         }
         double res = 0.0;
         if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
-        rr = (kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0;
         __syncwarp();
         /* gradient of this lane's multiplier component, and its scaled C row for the others */
         if (isW)
@@ -126,7 +138,6 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
             res += s;
             v.res[xb + lane] = res;
         }
-        rr = res - rr;
         if (attempt == 0)
         {   /* contribution to the termination norm (calculate_error_in_residuals, :412-442) */
             double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
@@ -160,8 +171,13 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
         {
             const double pk = v.P[xb + lane];
 #pragma unroll
-            for (int K = 0; K < D; K++)
-                if (K == lane) wA[K] += pk + shift;
+            for (int K = 0; K < D; K++) wA[K] += (K == lane) ? pk + shift : 0.0;
+        }
+        /* ---- everything below needs the kids' level ---- */
+        if (attempt == 0) { pdl_wait(); pdl_release(); }
+        rr = res - ((kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0);
+        if (isW)
+        {
             if (kids_are_parents)
             {   /* minus the Schur complement of the kid this row belongs to (lower triangle) */
                 const double *Sk = v.schur + (size_t) (k0 + kid) * NX * NX + ii * NX;
@@ -170,8 +186,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
                 {
                     const double sv = (kk <= ii) ? Sk[kk] : 0.0;
 #pragma unroll
-                    for (int m = 0; m < MD; m++)
-                        if (m == kid) wA[m * NX + kk] -= sv;
+                    for (int m = 0; m < MD; m++) wA[m * NX + kk] -= (m == kid) ? sv : 0.0;
                 }
             }
         }
@@ -186,15 +201,15 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
 #pragma unroll
         for (int j = 0; j < D; j++)
         {
+            /* lanes <= j carry don't-care values in column j and in rr from here on: the diagonal,
+             * its inverse and y are published by lane 0 (no per-lane selects in the loop) */
             double piv = __shfl_sync(FULL, wA[j], j), inv;
             tqb_pivot(piv, inv);
             small |= (piv <= v.o.regTol);
-            if (lane == j) { wA[j] = piv; myinv = inv; }
-            else if (lane > j) wA[j] *= inv;
+            wA[j] *= inv;
             /* forward substitution of the right-hand side on the fly (dtrsv_lnn) */
             const double yj = __shfl_sync(FULL, rr, j) * inv;
-            if (lane == j) rr = yj;
-            else if (lane > j) rr -= wA[j] * yj;
+            rr = fma(-wA[j], yj, rr);
             if (lane < RL) Ms[j * LDR + lane] = wA[j];
             if (NCOLU > 0 && lane == j)
             {
@@ -205,7 +220,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
                     Ms[j * LDR + RL + cc] = utc[cc];
                 }
             }
-            if (lane == 0) ys[j] = yj;
+            if (lane == 0) { ys[j] = yj; dgs[j] = piv; invs[j] = inv; }
             __syncwarp();
             const double lj = wA[j];
             const double *col = Ms + j * LDR;
@@ -222,9 +237,8 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
                 }
                 if (NCOLU > 0)
                 {   /* Ut[c][lane] -= Utilde[c][j] * L[lane][j] on the lanes still to come */
-                    const double ljm = (isW && lane > j) ? lj : 0.0;
 #pragma unroll
-                    for (int cc = 0; cc < NCOLU; cc++) utc[cc] -= col[RL + cc] * ljm;
+                    for (int cc = 0; cc < NCOLU; cc++) utc[cc] -= col[RL + cc] * lj;
                 }
             }
         }
@@ -236,10 +250,13 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
     /* ---- results to HBM ---- */
     if (isW)
     {
+        rr = ys[lane];
+        myinv = invs[lane];
         double *Lp = v.W + d1.w + (lane * (lane + 1)) / 2;
 #pragma unroll
         for (int t = 0; t < D; t++)
-            if (t <= lane) Lp[t] = wA[t];
+            if (t < lane) Lp[t] = wA[t];
+        Lp[lane] = dgs[lane];
         v.Linv[xb + lane] = myinv;
     }
     if (!ROOT)
@@ -255,7 +272,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
         if (NCOLU > 0 && isW)
         {
 #pragma unroll
-            for (int cc = 0; cc < NCOLU; cc++) Up[(NROWL + cc) * D + lane] = utc[cc];
+            for (int cc = 0; cc < NCOLU; cc++) Up[(NROWL + cc) * D + lane] = Ms[lane * LDR + RL + cc]; /* lane's register copy is stale */
         }
         /* Schur complement for the parent's block: S = Utilde Utilde' (lower), s = Utilde y.
          * Lower-triangle entries enumerated as a (NX/2) x (NX+1) rectangle: rows p and NX-1-p share a line */
@@ -307,21 +324,26 @@ __global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, 
     constexpr int D = NX * MD;
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= count) return;
+    if (w >= count) { pdl_wait(); pdl_release(); return; }
     const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) (lvl_begin + w);
     const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
-    if (v.status[d2.y] != TQB_RUNNING) return;
     const int xb = d1.x, xo = d0.z;
     const double *Lp = v.W + d1.w, *Up = v.Ut + d2.x;
     const bool act = lane < D;
-    double lcol[D];
+    /* the factor of this block is several launches old: load it before waiting for the parents */
+    double lcol[D], ucol[NX];
 #pragma unroll
     for (int i = 0; i < D; i++) lcol[i] = (act && lane <= i) ? Lp[(i * (i + 1)) / 2 + lane] : 0.0;
+#pragma unroll
+    for (int c = 0; c < NX; c++) ucol[c] = act ? Up[c * D + lane] : 0.0;
     double y = act ? v.dlam[xb + lane] : 0.0;
     const double inv = act ? v.Linv[xb + lane] : 0.0;
+    pdl_wait();
+    pdl_release();
+    if (v.status[d2.y] != TQB_RUNNING) return;
     double s = 0.0;
 #pragma unroll
-    for (int c = 0; c < NX; c++) s += (act ? Up[c * D + lane] : 0.0) * v.dlam[xo + c];
+    for (int c = 0; c < NX; c++) s += ucol[c] * v.dlam[xo + c];
     y -= s;
 #pragma unroll
     for (int i = D - 1; i >= 0; i--)

@@ -65,6 +65,7 @@ __global__ void k_init(View v)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < v.X) v.lam[i] = v.in.lam0[i];
+    if (i < v.Nn) v.nva[i] = 0.0; /* leaves never write their slot of the termination norm */
     if (v.has_dense)
     {   /* empty working sets (QProblemB_init is a cold start, qpoases.c:286) */
         if (i < v.X) v.P[i] = 0.0;
@@ -195,7 +196,7 @@ __global__ void __launch_bounds__(256) k_stage(View v)
     if (MODE == 2)
     {
         dotp = warp_sum(dotp);
-        if (lane == 0) v.nva[g] = dotp;
+        if (lane == 0) v.nvb[g] = dotp;
     }
     if (MODE != 2 && hoff >= 0)
     {   /* dense stage QP (stage_qp_qpoases_solve_extended / _solve, qpoases.c:360-398) */
@@ -794,6 +795,169 @@ __global__ void k_decide_ls_trial(View v)
         else
             atomicAdd(&v.counters[1], 1);
     }
+}
+
+
+/* ------------------------------------------------------------------------------------------
+ * Batched line search (clipping stage QPs only).  The Armijo sequence tau, beta*tau, ... is known
+ * in advance and a trial only streams the affine model (qmod0, dq, ...), so TQB_LS_NT step lengths
+ * are evaluated in ONE pass over the vectors and the Armijo loop of dual_Newton_tree.c:960-1000
+ * then runs on the device over the batch: no host round trip per trial.
+ *   first = 1: slot 0 is f(0), slots 1.. are tau = 1, beta, beta^2, ...; the chunk sums of
+ *              res'*dlam (nvb, written by k_stage<2>) are taken in the same pass.
+ *   first = 0: slots 0.. are tau, beta*tau, ... for the trees whose line search is still open.
+ * Step lengths are generated by repeated multiplication exactly as k_ls_decide does.
+ * Bytes per pass: 6(X+U) + 3 Nn doubles read, (NT+1) doubles per chunk written.
+ * ---------------------------------------------------------------------------------------- */
+#ifndef TQB_LS_NT
+#define TQB_LS_NT 8
+#endif
+__global__ void __launch_bounds__(256) k_ls_eval(View v, int first)
+{
+    constexpr int NT = TQB_LS_NT;
+    __shared__ double sh[NT + 1][256];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (c == 0 && tid == 0) v.counters[1] = 0;
+    const int t = v.T.chunk_tree[c];
+    if (first ? (v.status[t] != TQB_RUNNING) : !v.ls_active[t]) return;
+    double tau[NT], acc[NT];
+    {
+        double tm = first ? 1.0 : v.t_tau[t];
+#pragma unroll
+        for (int m = 0; m < NT; m++)
+        {
+            acc[m] = 0.0;
+            if (first && m == 0) { tau[0] = 0.0; continue; }
+            tau[m] = tm;
+            tm = v.o.beta * tm;
+        }
+    }
+    int dummy;
+    for (int i = v.T.chunk_x0[c] + tid; i < v.T.chunk_x1[c]; i += 256)
+    {
+        const double q0 = v.qmod0[i], dq = v.dq[i], qi = v.in.Qinv[i], lo = v.in.xmin[i], hi = v.in.xmax[i], Qd = v.in.Qd[i];
+#pragma unroll
+        for (int m = 0; m < NT; m++)
+        {
+            const double qm = q0 + tau[m] * dq;
+            const double val = clip_mask(qi * qm, lo, hi, dummy);
+            acc[m] += -0.5 * ((Qd * val) * val) + qm * val;
+        }
+    }
+    for (int i = v.T.chunk_u0[c] + tid; i < v.T.chunk_u1[c]; i += 256)
+    {
+        const double r0 = v.rmod0[i], dr = v.dr[i], ri = v.in.Rinv[i], lo = v.in.umin[i], hi = v.in.umax[i], Rd = v.in.Rd[i];
+#pragma unroll
+        for (int m = 0; m < NT; m++)
+        {
+            const double rm = r0 + tau[m] * dr;
+            const double val = clip_mask(ri * rm, lo, hi, dummy);
+            acc[m] += -0.5 * ((Rd * val) * val) + rm * val;
+        }
+    }
+    double accd = 0.0;
+    for (int g = v.T.chunk_beg[c] + tid; g < v.T.chunk_end[c]; g += 256)
+    {
+        const double c0 = v.cmod0[g], dc = v.dc[g];
+#pragma unroll
+        for (int m = 0; m < NT; m++) acc[m] -= c0 + tau[m] * dc;
+        if (first) accd += v.nvb[g];
+    }
+#pragma unroll
+    for (int m = 0; m < NT; m++) sh[m][tid] = acc[m];
+    sh[NT][tid] = accd;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1)
+    {
+        if (tid < s)
+        {
+#pragma unroll
+            for (int m = 0; m <= NT; m++) sh[m][tid] += sh[m][tid + s];
+        }
+        __syncthreads();
+    }
+    if (tid < NT) v.cvb[(size_t) tid * v.nchunk + c] = sh[tid][0];
+    if (first && tid == NT) v.cva[c] = sh[NT][0];
+}
+
+/* descent test (first) + Armijo loop over the batch of k_ls_eval (dual_Newton_tree.c:940-1000) */
+__global__ void k_ls_decide(View v, int first)
+{
+    constexpr int NT = TQB_LS_NT;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= v.nT) return;
+    if (first ? (v.status[t] != TQB_RUNNING) : !v.ls_active[t]) return;
+    double f[NT];
+#pragma unroll
+    for (int m = 0; m < NT; m++)
+        f[m] = v.sharded ? v.t_red[(size_t) (1 + m) * v.nT + t] : tree_reduce(v, v.cvb + (size_t) m * v.nchunk, t, lane, false);
+    double dot = 0.0;
+    if (first) dot = -(v.sharded ? v.t_red[t] : tree_reduce(v, v.cva, t, lane, false));
+    if (lane != 0) return;
+    int m0 = 0;
+    if (first)
+    {
+        v.t_dot[t] = dot;
+        v.t_f0[t] = f[0];
+        if (dot > 1e-10 || !((dot > 1e-10) || (dot < 1e-10)))
+        {
+            v.status[t] = 2; /* TREEQP_DN_NOT_DESCENT_DIRECTION */
+            v.ls_active[t] = 0;
+            return;
+        }
+        v.t_tau[t] = 1.0;
+        v.t_tauprev[t] = 0.0;
+        v.ls_cnt[t] = 0;
+        v.ls_active[t] = 1;
+        m0 = 1;
+    }
+    const double f0 = v.t_f0[t], tdot = v.t_dot[t];
+    double tau = v.t_tau[t];
+    int ls = v.ls_cnt[t];
+    bool done = false;
+    int recorded = 0;
+#pragma unroll
+    for (int m = 0; m < NT; m++)
+    {
+        if (m < m0 || done) continue;
+        ls++;
+        recorded = ls;
+        v.t_taufin[t] = tau; /* lambda of the last evaluated trial */
+        if (v.restart_cnt[t] == v.o.lsRestartTrigger) done = true; /* full step when stuck (:973-977) */
+        else if (f[m] <= f0 + v.o.gamma * tau * tdot) done = true;
+        else
+        {
+            v.t_tauprev[t] = tau;
+            tau = v.o.beta * tau;
+            if (ls >= v.o.lsMaxIter) { done = true; recorded = v.o.lsMaxIter + 1; }
+        }
+    }
+    v.t_tau[t] = tau;
+    v.ls_cnt[t] = ls;
+    if (done)
+    {
+        v.ls_active[t] = 0;
+        v.restart_cnt[t] = (recorded >= v.o.lsMaxIter) ? v.restart_cnt[t] + 1 : 0; /* :993-1000 */
+        const int it = v.iter[t]++;
+        if (t == 0 && it < 256) v.ls_hist[it] = recorded;
+        atomicAdd(&v.counters[3], ls);
+    }
+    else
+        atomicAdd(&v.counters[1], 1);
+}
+
+/* sharded solve, batched line search: this rank's parts of res'*dlam (slot 0) and of the NT dual
+ * function values (slots 1..NT) per tree; grid.y = slot */
+__global__ void k_tree_partial_ls(View v, double *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= v.nT) return;
+    const int y = blockIdx.y;
+    const double *cv = y == 0 ? v.cva : v.cvb + (size_t) (y - 1) * v.nchunk;
+    const double r = tree_reduce(v, cv, t, lane, false);
+    if (lane == 0) out[(size_t) y * v.nT + t] = r;
 }
 
 /* trees still running after maxIter iterations (dual_Newton_tree.c:1252) */

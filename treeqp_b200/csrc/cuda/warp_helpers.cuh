@@ -32,16 +32,39 @@ __device__ __forceinline__ double clip_mask(double v, double lo, double hi, int 
 }
 
 /* BLASFEO's Cholesky pivot rule (kernel_dgemm_4x4_lib4.c:4633-4646): c > 0 ? (l = sqrt(c), inv = 1/l)
- * : (0, 0), with correctly rounded sqrt and division so that the pivots are bit-identical to the
- * reference's.  -DTQB_FAST_PIVOT swaps in inv = rsqrt(c), l = c*inv (1 ulp off; measured on B200:
- * 4 % faster on the 131 071-node tree, not worth the drift on ill-conditioned paths). */
+ * : (0, 0).  sqrt and 1/l come from ONE reciprocal-square-root seed (MUFU.RSQ64H) refined by two
+ * coupled Goldschmidt steps, a Markstein correction of the root and one Newton step of the
+ * reciprocal against the ROUNDED root: 13 FP64 operations instead of the 33 instructions of
+ * sqrt() followed by a division, and half the dependent latency of a Cholesky step.  A CPU
+ * emulation (fma(), 22-bit seed, 2e7 samples over 26 decades) reproduces correctly rounded
+ * sqrt(c) and 1/sqrt(c)-rounded bit for bit; outside [1e-290, 1e290] the input is rescaled by 4^k.
+ * -DTQB_IEEE_PIVOT forces the library sqrt and division everywhere. */
 __device__ __forceinline__ void tqb_pivot(double &piv, double &inv)
 {
-#ifndef TQB_FAST_PIVOT
-    if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
+    if (piv > 0.0)
+    {
+#ifndef TQB_IEEE_PIVOT
+        double sc = 1.0, isc = 1.0;
+        const bool far = !(piv > 1e-290 && piv < 1e290); /* (sub)normal extremes: rescale by an exact 4^k */
+        if (far)
+        {
+            if (piv < 1.0) { piv *= 0x1p600; sc = 0x1p-300; isc = 0x1p300; }
+            else { piv *= 0x1p-600; sc = 0x1p300; isc = 0x1p-300; }
+        }
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(piv));
+        double h = 0.5 * y, g = piv * y, r;
+        r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+        r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+        g = fma(fma(-g, g, piv), h, g);          /* correctly rounded sqrt(piv) */
+        const double yy = h + h;                 /* ~ 1/sqrt(piv) */
+        inv = fma(yy, fma(-g, yy, 1.0), yy);     /* 1/g */
+        piv = g;
+        if (far) { piv *= sc; inv *= isc; }
 #else
-    if (piv > 0.0) { inv = rsqrt(piv); piv = piv * inv; }
+        piv = sqrt(piv); inv = 1.0 / piv;
 #endif
+    }
     else { piv = 0.0; inv = 0.0; }
 }
 
