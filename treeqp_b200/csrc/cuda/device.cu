@@ -15,6 +15,7 @@
 
 #include "tdunes_kernels.cuh"
 #include "tdunes_fused.cuh"
+#include "tdunes_stage.cuh"
 #include "comm.cuh"
 
 static thread_local char g_err[512] = "";
@@ -73,6 +74,8 @@ struct tqb_device
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
     double *d_schur;
     int *d_lvl_desc;
+    int *d_leaf_desc; /* LeafDesc records (tdunes_stage.cuh) */
+    int nleaf, fast_stage;
     /* subtree sharding (tqb_device_enable_sharding) */
     tqb_comm *comm;
     int cut_depth, ncut, my_cut0, my_ncut;
@@ -267,7 +270,7 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
             int *r = h + 12 * e;
             r[0] = g; r[1] = k0; r[2] = T.xoff[g]; r[3] = T.uoff[g];
             r[4] = T.xoff[k0]; r[5] = T.aoff[k0]; r[6] = T.boff[k0]; r[7] = T.woff[g];
-            r[8] = T.utoff[g]; r[9] = T.tree[g];
+            r[8] = T.utoff[g]; r[9] = T.tree[g]; r[10] = T.nkids[g];
         }
         CK(cudaMalloc(&D->d_lvl_desc, sizeof(int) * (12 * n + 4)));
         CK(cudaMemcpy(D->d_lvl_desc, h, sizeof(int) * (12 * n + 4), cudaMemcpyHostToDevice));
@@ -275,6 +278,65 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
         D->v.lvl_desc = D->d_lvl_desc;
     }
     D->fast = 1;
+    {   /* leaf records for k_stage_fused; it needs leaves without inputs and few (kid, column) pairs */
+        int nleaf = 0, ok = 1;
+        for (int g = 0; g < d->Nn; g++)
+            if (T.nkids[g] == 0) { nleaf++; if (T.nu[g] != 0 || T.nx[g] != (T.dad[g] < 0 ? PNX : NX)) ok = 0; }
+        for (int l = 0; l < d->Nh; l++)
+            if (D->lvl_md[l] * (NX + NU) > TQB_STAGE_MAXPAIR || D->lvl_md[l] * NX > 32) ok = 0;
+        const char *e2 = getenv("TREEQP_B200_GENERIC_STAGE");
+        if (e2 && e2[0] == '1') ok = 0;
+        if (ok)
+        {
+            int *h = (int *) calloc(4 * (size_t) nleaf + 4, sizeof(int));
+            size_t e = 0;
+            for (int g = 0; g < d->Nn; g++)
+                if (T.nkids[g] == 0)
+                {
+                    int *r = h + 4 * e++;
+                    r[0] = g; r[1] = T.xoff[g]; r[2] = T.tree[g]; r[3] = T.dad[g] < 0;
+                }
+            CK(cudaMalloc(&D->d_leaf_desc, sizeof(int) * (4 * (size_t) nleaf + 4)));
+            CK(cudaMemcpy(D->d_leaf_desc, h, sizeof(int) * (4 * (size_t) nleaf + 4), cudaMemcpyHostToDevice));
+            free(h);
+            D->v.leaf_desc = D->d_leaf_desc;
+            D->nleaf = nleaf;
+            D->fast_stage = 1;
+        }
+    }
+    return 0;
+}
+
+/* stage QPs of every node: compile-time-dimension kernel on uniform trees, generic otherwise */
+template <int MODE>
+static int launch_stage(tqb_device *D, int cls)
+{
+    View &v = D->v;
+    if (D->fast_stage)
+    {
+        constexpr int wpb = TQB_STAGE_WPB;
+        const int nx = D->f_nx, nu = D->f_nu, Np = D->dims.Np, nroots = D->lvl_ptr[1] - D->lvl_ptr[0];
+#define X(a, b)                                                                                        \
+        if (nx == a && nu == b)                                                                        \
+        {                                                                                              \
+            constexpr int lpw = 32 / tqb_pow2_ge(a);                                                   \
+            const int warps = Np + (D->nleaf + lpw - 1) / lpw;                                         \
+            const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;                \
+            if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = cls; }    \
+            k_stage_fused<a, b, MODE><<<(warps + wpb - 1) / wpb, 32 * wpb, 0, D->stream>>>(v, Np, nroots, D->f_pnx, D->nleaf); \
+            if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);                             \
+            D->launches++;                                                                             \
+            return 0;                                                                                  \
+        }
+        X(4, 1) X(6, 4) X(8, 3) X(12, 4)
+#undef X
+        return 1;
+    }
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = cls; }
+    k_stage<MODE><<<(v.Nn + D->wpb_stage - 1) / D->wpb_stage, 32 * D->wpb_stage, D->sm_stage, D->stream>>>(v);
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
     return 0;
 }
 
@@ -386,7 +448,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (!D) return;
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
-    cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); free(D->lvl_md); free(D->lvl_kp);
+    cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); cudaFree(D->d_leaf_desc); free(D->lvl_md); free(D->lvl_kp);
     cudaFree(D->d_cut_nodes); cudaFree(D->d_send); cudaFree(D->d_recv); cudaFree(D->d_tred);
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
@@ -544,7 +606,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     for (int it = 0; it < o->maxIter; it++)
     {
         CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
-        LAUNCH(K_STAGE, k_stage<0>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
+        if (launch_stage<0>(D, K_STAGE)) return 1;
         if (D->fast)
         {   /* gradient + Hessian + factorisation fused, leaves to root; the termination test comes
              * after the sweep (the sweep of the last iteration is the price of the fusion) */
@@ -583,7 +645,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             }
         }
         /* affine model of the stage gradients along dlam + res'*dlam, then the line search */
-        LAUNCH(K_DIR, k_stage<2>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
+        if (launch_stage<2>(D, K_DIR)) return 1;
         if (!v.has_dense)
         {   /* f(0), res'*dlam and the first TQB_LS_NT-1 step lengths in one pass, Armijo on the device */
             for (int batch = 0; batch * TQB_LS_NT <= o->lsMaxIter + 1; batch++)
@@ -619,7 +681,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
     }
     /* trees that ran out of iterations: x,u of the last trial point (what the reference holds) */
-    LAUNCH(K_STAGE, k_stage<3>, cdiv(v.Nn, D->wpb_stage), 32 * D->wpb_stage, D->sm_stage, v);
+    if (launch_stage<3>(D, K_STAGE)) return 1;
     LAUNCH(K_DECIDE, k_finalize_status, cdiv(nT, 256), 256, 0, v);
     {
         int n = v.X > v.U ? v.X : v.U;

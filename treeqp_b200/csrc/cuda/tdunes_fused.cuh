@@ -46,7 +46,7 @@ struct LvlDesc
 {
     int g, k0, xo, uo;      /* node, first kid, offsets of the node in x-/u-space */
     int xb, ao, bo, wo;     /* x-space offset of the block (= xoff[k0]), A/B of the kids, packed L */
-    int uto, tree, r0, r1;  /* Ut offset, owning tree */
+    int uto, tree, md, r1;  /* Ut offset, owning tree, number of kids */
 };
 
 template <int NX, int NU, int MD, int PNX, bool ROOT>
@@ -211,16 +211,19 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
             const double yj = __shfl_sync(FULL, rr, j) * inv;
             rr = fma(-wA[j], yj, rr);
             if (lane < RL) Ms[j * LDR + lane] = wA[j];
-            if (NCOLU > 0 && lane == j)
-            {
+            if (NCOLU > 0)
+            {   /* lane j finishes its elements of the column-wise Ut rows (its registers are dead afterwards) */
+                double us[NCOLU > 0 ? NCOLU : 1];
 #pragma unroll
-                for (int cc = 0; cc < NCOLU; cc++)
+                for (int cc = 0; cc < NCOLU; cc++) us[cc] = utc[cc] * inv;
+                if (lane == j)
                 {
-                    utc[cc] *= inv;
-                    Ms[j * LDR + RL + cc] = utc[cc];
+#pragma unroll
+                    for (int cc = 0; cc < NCOLU; cc++) Ms[j * LDR + RL + cc] = us[cc];
                 }
             }
-            if (lane == 0) { ys[j] = yj; dgs[j] = piv; invs[j] = inv; }
+            /* piv, inv and yj are warp-uniform: every lane stores the same value to the same word (no branch) */
+            ys[j] = yj; dgs[j] = piv; invs[j] = inv;
             __syncwarp();
             const double lj = wA[j];
             const double *col = Ms + j * LDR;

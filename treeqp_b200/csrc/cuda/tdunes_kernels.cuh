@@ -38,6 +38,7 @@ struct View
     double *dlam, *res, *resMod, *xUnc, *uUnc, *P, *Rt, *Linv;
     double *qmod0, *rmod0, *dq, *dr, *cmod0, *dc; /* affine model of the stage gradients along dlam */
     double *W, *Ut;
+    const int *leaf_desc; /* fast path: LeafDesc records (tdunes_stage.cuh), one per leaf in node order */
     const int *lvl_desc;  /* fast path: LvlDesc records (tdunes_fused.cuh), one per parent in level order */
     double *schur, *rsub; /* fast path: per-node Schur complement (NX x NX) and its rhs part (x-space) */
     double *nva, *nvb, *cva, *cvb; /* per-node and per-chunk reduction scratch */
@@ -888,12 +889,34 @@ __global__ void k_ls_decide(View v, int first)
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= v.nT) return;
     if (first ? (v.status[t] != TQB_RUNNING) : !v.ls_active[t]) return;
-    double f[NT];
+    double f[NT], dot = 0.0;
+    if (v.sharded)
+    {
 #pragma unroll
-    for (int m = 0; m < NT; m++)
-        f[m] = v.sharded ? v.t_red[(size_t) (1 + m) * v.nT + t] : tree_reduce(v, v.cvb + (size_t) m * v.nchunk, t, lane, false);
-    double dot = 0.0;
-    if (first) dot = -(v.sharded ? v.t_red[t] : tree_reduce(v, v.cva, t, lane, false));
+        for (int m = 0; m < NT; m++) f[m] = v.t_red[(size_t) (1 + m) * v.nT + t];
+        if (first) dot = -v.t_red[t];
+    }
+    else
+    {   /* all NT+1 per-tree sums in one sweep over the chunk values (same additions as tree_reduce,
+         * but the loads of one sweep step are independent: one memory latency instead of NT+1) */
+        const int c0 = v.T.tchunk0[t], c1 = v.T.tchunk0[t + 1];
+#pragma unroll
+        for (int m = 0; m < NT; m++) f[m] = 0.0;
+#pragma unroll 2
+        for (int c = c0 + lane; c < c1; c += 32)
+        {
+            double ld[NT + 1];
+#pragma unroll
+            for (int m = 0; m < NT; m++) ld[m] = v.cvb[(size_t) m * v.nchunk + c];
+            ld[NT] = first ? v.cva[c] : 0.0;
+#pragma unroll
+            for (int m = 0; m < NT; m++) f[m] += ld[m];
+            dot += ld[NT];
+        }
+#pragma unroll
+        for (int m = 0; m < NT; m++) f[m] = warp_sum(f[m]);
+        dot = -warp_sum(dot);
+    }
     if (lane != 0) return;
     int m0 = 0;
     if (first)

@@ -1,0 +1,188 @@
+/*
+ * tdunes_stage.cuh -- compile-time-dimension stage-QP kernel for uniform trees (the same class of
+ * trees as tdunes_fused.cuh: every non-root node NX states, every parent NU inputs, clipping
+ * stage QPs, leaves without inputs).
+ *
+ * k_stage_fused<NX,NU,MODE> replaces k_stage<MODE> (tdunes_kernels.cuh) on that class, with the
+ * same arithmetic in the same order (the results are bit-identical):
+ *   MODE 0  solve_stage_problems (dual_Newton_tree.c:218) + stage_qp_clipping_solve_extended
+ *           (dual_Newton_tree_clipping.c:188): qmod, rmod, x, u, xUnc, uUnc, P, Rt, cmod
+ *   MODE 2  the same operator applied to dlam: dq, dr, dc and the node's part of res'*dlam
+ *           (gradient_trans_times_direction, dual_Newton_tree.c:808)
+ *   MODE 3  clip-only solve (stage_qp_clipping_solve, clipping.c:231)
+ *
+ * Work split.  The generic kernel stages [A_kids B_kids] in shared memory and then walks its
+ * columns with a stride of nx_kid doubles (an 8-way bank conflict for nx = 12) and spends a whole
+ * warp on every leaf.  Here
+ *   - a PARENT warp gives each lane one (kid, column) pair of C = [A_kids B_kids]: the column is
+ *     NX contiguous doubles in HBM, read with 16-byte loads straight into registers and folded
+ *     with the kid's multiplier by a sequential fma chain (dgemv_t order); the MD partial products
+ *     of a column are then combined kid by kid by the lane that owns the column's variable;
+ *   - a LEAF warp handles 32/NXP leaves at once (NXP = NX rounded up to a power of two): leaves
+ *     are a pure element-wise clip of -q + lambda.
+ * Algorithmic bytes are those of k_stage; nothing is staged, nothing is re-read.
+ */
+#pragma once
+#include "tdunes_fused.cuh"
+
+#define TQB_STAGE_WPB 8       /* warps per CTA */
+#define TQB_STAGE_MAXPAIR 64  /* max kids * (NX + NU) per parent */
+
+struct LeafDesc { int g, xo, tree, root; };
+
+__host__ __device__ constexpr int tqb_pow2_ge(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+
+template <int NX, int NU, int MODE>
+__global__ void __launch_bounds__(32 * TQB_STAGE_WPB) k_stage_fused(View v, int Np, int nroots, int root_nx, int nleaf)
+{
+    constexpr int NXP = tqb_pow2_ge(NX), LPW = 32 / NXP;
+    __shared__ double sLs[TQB_STAGE_WPB][32];
+    __shared__ double sSs[TQB_STAGE_WPB][TQB_STAGE_MAXPAIR];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * TQB_STAGE_WPB + wib;
+    const double *src = (MODE == 2) ? v.dlam : v.lam;
+
+    if (w < Np)
+    {   /* ------------------------------ parent ------------------------------ */
+        const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) w;
+        const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+        const int g = d0.x, xo = d0.z, uo = d0.w, xb = d1.x, md = d2.z;
+        if (v.status[d2.y] != TQB_RUNNING) return;
+        const bool root = w < nroots;
+        const int pnx = root ? root_nx : NX, ncol = pnx + NU, D = md * NX, npair = md * ncol;
+        double *sL = sLs[wib], *sS = sSs[wib];
+
+        /* inputs of the epilogue first (independent of everything below) */
+        const bool own = lane < ncol, isx = lane < pnx;
+        const int i = isx ? lane : lane - pnx;
+        double base = 0.0, winv = 0.0, lo = 0.0, hi = 0.0, rs = 0.0;
+        if (own)
+        {
+            if (isx)
+            {
+                const double l = root ? 0.0 : src[xo + i];
+                if (MODE == 2) { base = l; rs = root ? 0.0 : v.res[xo + i]; }
+                else
+                {
+                    base = -v.in.q[xo + i] + l;
+                    winv = v.in.Qinv[xo + i]; lo = v.in.xmin[xo + i]; hi = v.in.xmax[xo + i];
+                }
+            }
+            else if (MODE != 2)
+            {
+                base = -v.in.r[uo + i];
+                winv = v.in.Rinv[uo + i]; lo = v.in.umin[uo + i]; hi = v.in.umax[uo + i];
+            }
+        }
+        /* the kids' multipliers (one contiguous range) and cmod = sum_kids b_j' lambda_j (:892) */
+        double cpart = 0.0;
+        if (lane < D)
+        {
+            const double l = src[xb + lane];
+            sL[lane] = l;
+            if (MODE != 3) cpart = v.in.b[xb + lane] * l;
+        }
+        __syncwarp();
+        if (MODE != 3)
+        {
+            const double c = warp_sum(cpart);
+            if (lane == 0) { if (MODE == 0) v.cmod0[g] = c; else v.dc[g] = c; }
+        }
+        /* one (kid, column) pair per lane: s = column' * lambda_kid */
+        for (int p = lane; p < npair; p += 32)
+        {
+            const int kid = p / ncol, c = p - kid * ncol;
+            const double *col = c < pnx ? v.in.A + d1.y + (size_t) (kid * pnx + c) * NX
+                                        : v.in.B + d1.z + (size_t) (kid * NU + (c - pnx)) * NX;
+            const double *lk = sL + kid * NX;
+            double cr[NX];
+            if (NX % 2 == 0)
+            {
+                const double2 *c2 = reinterpret_cast<const double2 *>(col);
+#pragma unroll
+                for (int r = 0; r < NX / 2; r++) { const double2 t = __ldg(c2 + r); cr[2 * r] = t.x; cr[2 * r + 1] = t.y; }
+            }
+            else
+            {
+#pragma unroll
+                for (int r = 0; r < NX; r++) cr[r] = __ldg(col + r);
+            }
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < NX; r++) s += cr[r] * lk[r];
+            sS[p] = s;
+        }
+        __syncwarp();
+        if (own)
+        {
+            double acc = base;
+            for (int j = 0; j < md; j++) acc -= sS[j * ncol + lane];
+            if (MODE == 2)
+            {
+                if (isx) v.dq[xo + i] = acc; else v.dr[uo + i] = acc;
+            }
+            else
+            {
+                int mask;
+                const double unc = winv * acc;
+                const double val = clip_mask(unc, lo, hi, mask);
+                if (isx)
+                {
+                    v.x[xo + i] = val;
+                    if (MODE == 0) { v.qmod0[xo + i] = acc; v.xUnc[xo + i] = unc; v.P[xo + i] = mask == 0 ? winv : 0.0; }
+                }
+                else
+                {
+                    v.u[uo + i] = val;
+                    if (MODE == 0) { v.rmod0[uo + i] = acc; v.uUnc[uo + i] = unc; v.Rt[uo + i] = mask == 0 ? winv : 0.0; }
+                }
+            }
+        }
+        if (MODE == 2)
+        {   /* node's part of res'*dlam */
+            const double dotp = warp_sum((own && isx) ? rs * base : 0.0);
+            if (lane == 0) v.nvb[g] = dotp;
+        }
+        return;
+    }
+
+    /* -------------------------------- leaves -------------------------------- */
+    const int slot = lane / NXP, i = lane - slot * NXP;
+    const int lf = (w - Np) * LPW + slot;
+    const bool act = lf < nleaf && i < NX;
+    double part = 0.0;
+    int g = -1;
+    if (lf < nleaf)
+    {
+        const int4 ld = __ldg(reinterpret_cast<const int4 *>(v.leaf_desc) + lf);
+        if (v.status[ld.z] == TQB_RUNNING) g = ld.x;
+        if (act && g >= 0)
+        {
+            const int e = ld.y + i;
+            const double l = ld.w ? 0.0 : src[e];
+            if (MODE == 2)
+            {
+                v.dq[e] = l;
+                part = ld.w ? 0.0 : v.res[e] * l;
+            }
+            else
+            {
+                const double acc = -v.in.q[e] + l, winv = v.in.Qinv[e];
+                const double unc = winv * acc;
+                int mask;
+                v.x[e] = clip_mask(unc, v.in.xmin[e], v.in.xmax[e], mask);
+                if (MODE == 0) { v.qmod0[e] = acc; v.xUnc[e] = unc; v.P[e] = mask == 0 ? winv : 0.0; }
+            }
+        }
+    }
+    if (MODE == 2)
+    {   /* segmented butterfly: the same additions as a full-warp sum padded with zeros */
+#pragma unroll
+        for (int o = NXP / 2; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+        if (g >= 0 && i == 0) { v.nvb[g] = part; v.dc[g] = 0.0; }
+    }
+    else if (MODE == 0)
+    {
+        if (g >= 0 && i == 0) v.cmod0[g] = 0.0;
+    }
+}

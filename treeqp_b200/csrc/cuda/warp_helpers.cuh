@@ -39,33 +39,38 @@ __device__ __forceinline__ double clip_mask(double v, double lo, double hi, int 
  * emulation (fma(), 22-bit seed, 2e7 samples over 26 decades) reproduces correctly rounded
  * sqrt(c) and 1/sqrt(c)-rounded bit for bit; outside [1e-290, 1e290] the input is rescaled by 4^k.
  * -DTQB_IEEE_PIVOT forces the library sqrt and division everywhere. */
+/* one rsqrt seed -> correctly rounded sqrt(c) and the rounded reciprocal of that root */
+__device__ __forceinline__ void tqb_rsqrt_core(double c, double &root, double &inv)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(c));
+    double h = 0.5 * y, g = c * y, r;
+    r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
+    g = fma(fma(-g, g, c), h, g);            /* correctly rounded sqrt(c) */
+    const double yy = h + h;                 /* ~ 1/sqrt(c) */
+    inv = fma(yy, fma(-g, yy, 1.0), yy);     /* 1/g */
+    root = g;
+}
+/* rare pivots: non-positive (BLASFEO: l = 0, inv = 0) or outside [1e-290, 1e290] (rescaled by an exact 4^k) */
+static __device__ __noinline__ void tqb_pivot_rare(double &piv, double &inv)
+{
+    if (!(piv > 0.0)) { piv = 0.0; inv = 0.0; return; }
+    double sc, isc;
+    if (piv < 1.0) { piv *= 0x1p600; sc = 0x1p-300; isc = 0x1p300; }
+    else { piv *= 0x1p-600; sc = 0x1p300; isc = 0x1p-300; }
+    tqb_rsqrt_core(piv, piv, inv);
+    piv *= sc; inv *= isc;
+}
 __device__ __forceinline__ void tqb_pivot(double &piv, double &inv)
 {
-    if (piv > 0.0)
-    {
 #ifndef TQB_IEEE_PIVOT
-        double sc = 1.0, isc = 1.0;
-        const bool far = !(piv > 1e-290 && piv < 1e290); /* (sub)normal extremes: rescale by an exact 4^k */
-        if (far)
-        {
-            if (piv < 1.0) { piv *= 0x1p600; sc = 0x1p-300; isc = 0x1p300; }
-            else { piv *= 0x1p-600; sc = 0x1p300; isc = 0x1p-300; }
-        }
-        double y;
-        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(piv));
-        double h = 0.5 * y, g = piv * y, r;
-        r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
-        r = fma(-g, h, 0.5); g = fma(g, r, g); h = fma(h, r, h);
-        g = fma(fma(-g, g, piv), h, g);          /* correctly rounded sqrt(piv) */
-        const double yy = h + h;                 /* ~ 1/sqrt(piv) */
-        inv = fma(yy, fma(-g, yy, 1.0), yy);     /* 1/g */
-        piv = g;
-        if (far) { piv *= sc; inv *= isc; }
+    if (piv > 1e-290 && piv < 1e290) tqb_rsqrt_core(piv, piv, inv); /* the only branch of the common case */
+    else tqb_pivot_rare(piv, inv);
 #else
-        piv = sqrt(piv); inv = 1.0 / piv;
-#endif
-    }
+    if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
     else { piv = 0.0; inv = 0.0; }
+#endif
 }
 
 /* ------------------------------------------------------------------------------------------
