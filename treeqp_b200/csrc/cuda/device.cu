@@ -75,7 +75,7 @@ struct tqb_device
     double *d_schur;
     int *d_lvl_desc;
     int *d_leaf_desc; /* LeafDesc records (tdunes_stage.cuh) */
-    int nleaf, fast_stage;
+    int nleaf, fast_stage, stage_grid, n_sm;
     /* subtree sharding (tqb_device_enable_sharding) */
     tqb_comm *comm;
     int cut_depth, ncut, my_cut0, my_ncut;
@@ -302,6 +302,12 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
             D->v.leaf_desc = D->d_leaf_desc;
             D->nleaf = nleaf;
             D->fast_stage = 1;
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const char *e3 = getenv("TREEQP_B200_STAGE_CTAS_PER_SM");
+            D->n_sm = sms;
+            D->stage_grid = e3 ? sms * atoi(e3) : 0; /* persistent warps: as many CTAs as are resident at once */
         }
     }
     return 0;
@@ -323,7 +329,11 @@ static int launch_stage(tqb_device *D, int cls)
             const int warps = Np + (D->nleaf + lpw - 1) / lpw;                                         \
             const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;                \
             if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = cls; }    \
-            k_stage_fused<a, b, MODE><<<(warps + wpb - 1) / wpb, 32 * wpb, 0, D->stream>>>(v, Np, nroots, D->f_pnx, D->nleaf); \
+            static int per_sm = 0;                                                                     \
+            if (per_sm == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stage_fused<a, b, MODE>, 32 * wpb, 0) != cudaSuccess) per_sm = 2; \
+            const int res = D->stage_grid > 0 ? D->stage_grid : D->n_sm * per_sm;                      \
+            const int full = (warps + wpb - 1) / wpb, grid = full < res ? full : res;                  \
+            k_stage_fused<a, b, MODE><<<grid, 32 * wpb, 0, D->stream>>>(v, Np, nroots, D->f_pnx, D->nleaf); \
             if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);                             \
             D->launches++;                                                                             \
             return 0;                                                                                  \
@@ -652,7 +662,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             {
                 LAUNCH(K_TRIAL, k_ls_eval, v.nchunk, 256, 0, v, batch == 0);
                 if (D->comm && allreduce_ls_batch(D, batch == 0)) return 1;
-                LAUNCH(K_DECIDE, k_ls_decide, tgrid, 128, 0, v, batch == 0);
+                LAUNCH(K_DECIDE, k_ls_decide, nT, 32 * (TQB_LS_NT + 1), 0, v, batch == 0);
                 if (peek_counter(D, 1, 5)) return 1;
                 CK(cudaStreamSynchronize(D->stream));
                 if (D->h_counters[4] == 0 || D->h_counters[5] == 0) break;
@@ -678,7 +688,11 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             }
         }
         if (D->h_counters[4] == 0) break; /* every tree has terminated */
-        LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
+        if (v.nxmax <= 4) LAUNCH(K_STEP, k_lambda_step_w<4>, cdiv(v.Nn, 64), 256, 0, v);
+        else if (v.nxmax <= 8) LAUNCH(K_STEP, k_lambda_step_w<8>, cdiv(v.Nn, 32), 256, 0, v);
+        else if (v.nxmax <= 16) LAUNCH(K_STEP, k_lambda_step_w<16>, cdiv(v.Nn, 16), 256, 0, v);
+        else if (v.nxmax <= 32) LAUNCH(K_STEP, k_lambda_step_w<32>, cdiv(v.Nn, 8), 256, 0, v);
+        else LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
     }
     /* trees that ran out of iterations: x,u of the last trial point (what the reference holds) */
     if (launch_stage<3>(D, K_STAGE)) return 1;

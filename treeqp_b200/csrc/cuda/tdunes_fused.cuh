@@ -63,9 +63,23 @@ struct FusedCfg
     static constexpr int LDR = tqb_ld2(R);
     /* shared memory per warp, in doubles: Ms (D x LDR; its head doubles as Cp, D x LDC, during the
      * build) | p (NCOL) | z (NCOL) | ys (D) | dgs (D) | invs (D) */
-    static constexpr int SM_M = D * LDR > D * LDC ? D * LDR : D * LDC;
+    /* FP64 tensor-core (DMMA m8n8k4) build of C diag(p) C' and of the Schur complement for the
+     * larger blocks: 8x8 output tiles, operands in fragment layout straight from HBM / shared memory */
+    static constexpr bool DMMA = D >= 16;
+    static constexpr int TR = (D + 7) / 8;          /* row tiles of W */
+    static constexpr int KS = (NCOL + 3) / 4;       /* k-steps of the build */
+    static constexpr int LDCD = 20 + 16 * ((NCOL > 20 ? NCOL - 20 : 0) + 15) / 16 * (NCOL > 20); /* >= NCOL, = 4 mod 16 */
+    static constexpr int SM_M0 = D * LDR > D * LDC ? D * LDR : D * LDC;
+    static constexpr int SM_M = (DMMA && D * LDCD > SM_M0) ? D * LDCD : SM_M0;
     static constexpr int SMEM = SM_M + 2 * (NCOL + 2) + 3 * D + 2;
 };
+
+/* D(8x8) += A(8x4) * B(4x8), FP64: lane T holds A[T/4][T%4], B[T%4][T/4], C[T/4][2(T%4) + {0,1}] */
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 #ifndef TQB_BF_MINBLOCKS
 #define TQB_BF_MINBLOCKS 4
@@ -108,6 +122,114 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
     for (int attempt = 0; attempt < 2; attempt++)
     {
         const double shift = (v.o.regType == 1 || attempt == 1) ? v.o.regValue : 0.0;
+        double res = 0.0;
+        if constexpr (Cfg::DMMA)
+        {
+            /* ---- tensor-core build: W = C diag(p) C' tile by tile (lower tiles only) ----
+             * fragment (i, ks) of this lane = C[8i + gid][4ks + tig]; the B operand of tile column n
+             * is the same fragment of row tile n scaled by p (= Cp), so one pass over C in HBM feeds
+             * both operands, the gradient and the Ut rows */
+            constexpr int TR = Cfg::TR, KS = Cfg::KS, LDCD = Cfg::LDCD;
+            const int gid = lane >> 2, tig = lane & 3;
+            double pf[KS], zf[KS], af[TR][KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+            {
+                const int c = 4 * ks + tig;
+                pf[ks] = zf[ks] = 0.0;
+                if (c < NCOL)
+                {
+                    pf[ks] = c < PNX ? v.P[xo + c] : v.Rt[uo + c - PNX];
+                    zf[ks] = c < PNX ? v.x[xo + c] : v.u[uo + c - PNX];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < TR; i++)
+            {
+                const int r = 8 * i + gid, kr = r / NX, ir = r - kr * NX;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++)
+                {
+                    const int c = 4 * ks + tig;
+                    double val = 0.0;
+                    if (r < D && c < NCOL) val = c < PNX ? Ag[kr * NX * PNX + ir + c * NX] : Bg[kr * NX * NU + ir + (c - PNX) * NX];
+                    af[i][ks] = val;
+                }
+            }
+            if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
+            __syncwarp(); /* previous attempt's readers of Ms are done */
+            double acc[TR * (TR + 1) / 2][2];
+#pragma unroll
+            for (int i = 0; i < TR; i++)
+            {
+                const int r = 8 * i + gid;
+                double sg = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++)
+                {
+                    sg += af[i][ks] * zf[ks];
+                    if (r < D && 4 * ks + tig < NCOL) Cp[r * LDCD + 4 * ks + tig] = af[i][ks] * pf[ks];
+                }
+                sg += __shfl_xor_sync(FULL, sg, 1);
+                sg += __shfl_xor_sync(FULL, sg, 2);
+                if (tig == 0 && r < D) ys[r] = sg;
+            }
+#pragma unroll
+            for (int i = 0; i < TR; i++)
+#pragma unroll
+                for (int n = 0; n <= i; n++)
+                {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) dmma884(c0, c1, af[i][ks], af[n][ks] * pf[ks]);
+                    acc[i * (i + 1) / 2 + n][0] = c0;
+                    acc[i * (i + 1) / 2 + n][1] = c1;
+                }
+            __syncwarp();
+            if (isW)
+            {
+                res += ys[lane];
+                v.res[xb + lane] = res;
+                if (NCOLU > 0)
+                {
+#pragma unroll
+                    for (int cc = 0; cc < NCOLU; cc++) utc[cc] = -Cp[lane * LDCD + NROWL + cc];
+                }
+            }
+            else if (!ROOT && lane < RL)
+            {   /* Ut rows: M[D+c][K] = -P_p[c] * A[K][c] = -Cp[K][c] */
+#pragma unroll
+                for (int K = 0; K < D; K++) wA[K] = -Cp[K * LDCD + (lane - D)];
+            }
+            if (attempt == 0)
+            {   /* contribution to the termination norm (calculate_error_in_residuals, :412-442) */
+                double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
+                part = (v.o.termCondition == 2) ? warp_max(part) : warp_sum(part);
+                if (lane == 0) v.nva[g] = part;
+            }
+            __syncwarp(); /* Cp is dead: the W tiles go to the same words, row-major with leading dimension LDR */
+#pragma unroll
+            for (int i = 0; i < TR; i++)
+#pragma unroll
+                for (int n = 0; n <= i; n++)
+                    if (8 * i + gid < D)
+                        *reinterpret_cast<double2 *>(Ms + (8 * i + gid) * LDR + 8 * n + 2 * tig) =
+                            make_double2(acc[i * (i + 1) / 2 + n][0], acc[i * (i + 1) / 2 + n][1]);
+            __syncwarp();
+            if (isW)
+            {
+                const double pk = v.P[xb + lane];
+#pragma unroll
+                for (int K = 0; K < D; K += 2)
+                {
+                    const double2 t2 = *reinterpret_cast<const double2 *>(Ms + lane * LDR + K);
+                    wA[K] = t2.x + ((K == lane) ? pk + shift : 0.0);
+                    wA[K + 1] = t2.y + ((K + 1 == lane) ? pk + shift : 0.0);
+                }
+            }
+        }
+        else
+        {
         for (int c = lane; c < NCOL; c += 32)
         {
             ps[c] = c < PNX ? v.P[xo + c] : v.Rt[uo + c - PNX];
@@ -122,7 +244,6 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
             if (isW) val = c < PNX ? Ag[kid * NX * PNX + ii + c * NX] : Bg[kid * NX * NU + ii + (c - PNX) * NX];
             crow[c] = val;
         }
-        double res = 0.0;
         if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
         __syncwarp();
         /* gradient of this lane's multiplier component, and its scaled C row for the others */
@@ -173,6 +294,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
 #pragma unroll
             for (int K = 0; K < D; K++) wA[K] += (K == lane) ? pk + shift : 0.0;
         }
+        }
         /* ---- everything below needs the kids' level ---- */
         if (attempt == 0) { pdl_wait(); pdl_release(); }
         rr = res - ((kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0);
@@ -190,7 +312,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
                 }
             }
         }
-        else if (!ROOT && lane < RL)
+        else if (!Cfg::DMMA && !ROOT && lane < RL)
         {   /* Ut rows: M[D+c][K] = -P_p[c] * A[K][c] = -Cp[K][c] */
 #pragma unroll
             for (int K = 0; K < D; K++) wA[K] = -Cp[K * LDC + (lane - D)];
@@ -281,6 +403,30 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
          * Lower-triangle entries enumerated as a (NX/2) x (NX+1) rectangle: rows p and NX-1-p share a line */
         double *Sg = v.schur + (size_t) g * NX * NX;
         constexpr int NE = (NX % 2 == 0) ? (NX / 2) * (NX + 1) : NX * NX;
+        if constexpr (Cfg::DMMA)
+        {   /* tensor-core S = Utilde Utilde': fragment (i, ks) = Utilde[8i + gid][4ks + tig] is both operands */
+            constexpr int TRU = (NX + 7) / 8, KSU = (D + 3) / 4;
+            const int gid = lane >> 2, tig = lane & 3;
+            double uf[TRU][KSU];
+#pragma unroll
+            for (int i = 0; i < TRU; i++)
+#pragma unroll
+                for (int ks = 0; ks < KSU; ks++)
+                    uf[i][ks] = (8 * i + gid < NX && 4 * ks + tig < D) ? Ms[(4 * ks + tig) * LDR + D + 8 * i + gid] : 0.0;
+#pragma unroll
+            for (int i = 0; i < TRU; i++)
+#pragma unroll
+                for (int n = 0; n <= i; n++)
+                {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KSU; ks++) dmma884(c0, c1, uf[i][ks], uf[n][ks]);
+                    const int a = 8 * i + gid, b = 8 * n + 2 * tig;
+                    if (a < NX && b < NX) Sg[a * NX + b] = c0;
+                    if (a < NX && b + 1 < NX) Sg[a * NX + b + 1] = c1;
+                }
+        }
+        else
         for (int e = lane; e < NE; e += 32)
         {
             int a, b;

@@ -762,6 +762,20 @@ __global__ void k_lambda_step(View v)
     for (int i = 0; i < nx; i++) v.lam[xo + i] += step * v.dlam[xo + i];
 }
 
+/* the same with 32/NXP nodes per warp (NXP >= largest nx, a power of two): unit-stride accesses */
+template <int NXP>
+__global__ void __launch_bounds__(256) k_lambda_step_w(View v)
+{
+    constexpr int LPW = 32 / NXP;
+    const int lane = threadIdx.x & 31, slot = lane / NXP, i = lane - slot * NXP;
+    const int g = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * LPW + slot;
+    if (g >= v.Nn) return;
+    const int t = v.T.tree[g];
+    if (v.status[t] != TQB_RUNNING || v.T.dad[g] < 0 || i >= v.T.nx[g]) return;
+    const int e = v.T.xoff[g] + i;
+    v.lam[e] += v.t_taufin[t] * v.dlam[e];
+}
+
 /* Armijo test of one trial (dual_Newton_tree.c:970-1000) */
 __global__ void k_decide_ls_trial(View v)
 {
@@ -881,46 +895,45 @@ __global__ void __launch_bounds__(256) k_ls_eval(View v, int first)
     if (first && tid == NT) v.cva[c] = sh[NT][0];
 }
 
-/* descent test (first) + Armijo loop over the batch of k_ls_eval (dual_Newton_tree.c:940-1000) */
-__global__ void k_ls_decide(View v, int first)
+/* descent test (first) + Armijo loop over the batch of k_ls_eval (dual_Newton_tree.c:940-1000).
+ * One CTA per tree, warp m < NT reduces the chunk values of step length m, warp NT those of
+ * res'*dlam (same additions as tree_reduce, four independent loads in flight per lane); thread 0
+ * then walks the Armijo sequence. */
+__global__ void __launch_bounds__(32 * (TQB_LS_NT + 1)) k_ls_decide(View v, int first)
 {
     constexpr int NT = TQB_LS_NT;
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= v.nT) return;
+    __shared__ double sf[NT + 1];
+    const int lane = threadIdx.x & 31, m = threadIdx.x >> 5;
+    const int t = blockIdx.x;
     if (first ? (v.status[t] != TQB_RUNNING) : !v.ls_active[t]) return;
-    double f[NT], dot = 0.0;
     if (v.sharded)
     {
-#pragma unroll
-        for (int m = 0; m < NT; m++) f[m] = v.t_red[(size_t) (1 + m) * v.nT + t];
-        if (first) dot = -v.t_red[t];
+        if (lane == 0) sf[m] = m < NT ? v.t_red[(size_t) (1 + m) * v.nT + t] : (first ? v.t_red[t] : 0.0);
     }
-    else
-    {   /* all NT+1 per-tree sums in one sweep over the chunk values (same additions as tree_reduce,
-         * but the loads of one sweep step are independent: one memory latency instead of NT+1) */
-        const int c0 = v.T.tchunk0[t], c1 = v.T.tchunk0[t + 1];
-#pragma unroll
-        for (int m = 0; m < NT; m++) f[m] = 0.0;
-#pragma unroll 2
-        for (int c = c0 + lane; c < c1; c += 32)
+    else if (m < NT || first)
+    {
+        const double *cv = m < NT ? v.cvb + (size_t) m * v.nchunk : v.cva;
+        const int c1 = v.T.tchunk0[t + 1];
+        int c = v.T.tchunk0[t] + lane;
+        double acc = 0.0;
+        for (; c + 96 < c1; c += 128)
         {
-            double ld[NT + 1];
-#pragma unroll
-            for (int m = 0; m < NT; m++) ld[m] = v.cvb[(size_t) m * v.nchunk + c];
-            ld[NT] = first ? v.cva[c] : 0.0;
-#pragma unroll
-            for (int m = 0; m < NT; m++) f[m] += ld[m];
-            dot += ld[NT];
+            const double a0 = cv[c], a1 = cv[c + 32], a2 = cv[c + 64], a3 = cv[c + 96];
+            acc += a0; acc += a1; acc += a2; acc += a3;
         }
-#pragma unroll
-        for (int m = 0; m < NT; m++) f[m] = warp_sum(f[m]);
-        dot = -warp_sum(dot);
+        for (; c < c1; c += 32) acc += cv[c];
+        acc = warp_sum(acc);
+        if (lane == 0) sf[m] = acc;
     }
-    if (lane != 0) return;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double f[NT];
+#pragma unroll
+    for (int k = 0; k < NT; k++) f[k] = sf[k];
     int m0 = 0;
     if (first)
     {
+        const double dot = -sf[NT];
         v.t_dot[t] = dot;
         v.t_f0[t] = f[0];
         if (dot > 1e-10 || !((dot > 1e-10) || (dot < 1e-10)))
@@ -936,32 +949,35 @@ __global__ void k_ls_decide(View v, int first)
         m0 = 1;
     }
     const double f0 = v.t_f0[t], tdot = v.t_dot[t];
-    double tau = v.t_tau[t];
+    const int restart = v.restart_cnt[t];
+    double tau = v.t_tau[t], taufin = tau, tauprev = v.t_tauprev[t];
     int ls = v.ls_cnt[t];
     bool done = false;
     int recorded = 0;
 #pragma unroll
-    for (int m = 0; m < NT; m++)
+    for (int k = 0; k < NT; k++)
     {
-        if (m < m0 || done) continue;
+        if (k < m0 || done) continue;
         ls++;
         recorded = ls;
-        v.t_taufin[t] = tau; /* lambda of the last evaluated trial */
-        if (v.restart_cnt[t] == v.o.lsRestartTrigger) done = true; /* full step when stuck (:973-977) */
-        else if (f[m] <= f0 + v.o.gamma * tau * tdot) done = true;
+        taufin = tau; /* lambda of the last evaluated trial */
+        if (restart == v.o.lsRestartTrigger) done = true; /* full step when stuck (:973-977) */
+        else if (f[k] <= f0 + v.o.gamma * tau * tdot) done = true;
         else
         {
-            v.t_tauprev[t] = tau;
+            tauprev = tau;
             tau = v.o.beta * tau;
             if (ls >= v.o.lsMaxIter) { done = true; recorded = v.o.lsMaxIter + 1; }
         }
     }
+    v.t_taufin[t] = taufin;
+    v.t_tauprev[t] = tauprev;
     v.t_tau[t] = tau;
     v.ls_cnt[t] = ls;
     if (done)
     {
         v.ls_active[t] = 0;
-        v.restart_cnt[t] = (recorded >= v.o.lsMaxIter) ? v.restart_cnt[t] + 1 : 0; /* :993-1000 */
+        v.restart_cnt[t] = (recorded >= v.o.lsMaxIter) ? restart + 1 : 0; /* :993-1000 */
         const int it = v.iter[t]++;
         if (t == 0 && it < 256) v.ls_hist[it] = recorded;
         atomicAdd(&v.counters[3], ls);

@@ -32,131 +32,131 @@ struct LeafDesc { int g, xo, tree, root; };
 
 __host__ __device__ constexpr int tqb_pow2_ge(int n) { return n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
 
+/* one parent: d0,d1,d2 = its LvlDesc record (already in registers) */
 template <int NX, int NU, int MODE>
-__global__ void __launch_bounds__(32 * TQB_STAGE_WPB) k_stage_fused(View v, int Np, int nroots, int root_nx, int nleaf)
+__device__ __forceinline__ void stage_parent(const View &v, const int4 d0, const int4 d1, const int4 d2, bool root, int root_nx,
+                                             double *sL, double *sS, int lane)
 {
-    constexpr int NXP = tqb_pow2_ge(NX), LPW = 32 / NXP;
-    __shared__ double sLs[TQB_STAGE_WPB][32];
-    __shared__ double sSs[TQB_STAGE_WPB][TQB_STAGE_MAXPAIR];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int w = blockIdx.x * TQB_STAGE_WPB + wib;
     const double *src = (MODE == 2) ? v.dlam : v.lam;
+    const int g = d0.x, xo = d0.z, uo = d0.w, xb = d1.x, md = d2.z;
+    const int running = v.status[d2.y] == TQB_RUNNING; /* tested before the first store */
+    const int pnx = root ? root_nx : NX, ncol = pnx + NU, D = md * NX, npair = md * ncol;
 
-    if (w < Np)
-    {   /* ------------------------------ parent ------------------------------ */
-        const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) w;
-        const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
-        const int g = d0.x, xo = d0.z, uo = d0.w, xb = d1.x, md = d2.z;
-        if (v.status[d2.y] != TQB_RUNNING) return;
-        const bool root = w < nroots;
-        const int pnx = root ? root_nx : NX, ncol = pnx + NU, D = md * NX, npair = md * ncol;
-        double *sL = sLs[wib], *sS = sSs[wib];
-
-        /* inputs of the epilogue first (independent of everything below) */
-        const bool own = lane < ncol, isx = lane < pnx;
-        const int i = isx ? lane : lane - pnx;
-        double base = 0.0, winv = 0.0, lo = 0.0, hi = 0.0, rs = 0.0;
-        if (own)
+    /* inputs of the epilogue first (independent of everything below) */
+    const bool own = lane < ncol, isx = lane < pnx;
+    const int i = isx ? lane : lane - pnx;
+    double base = 0.0, winv = 0.0, lo = 0.0, hi = 0.0, rs = 0.0;
+    if (own)
+    {
+        if (isx)
         {
+            const double l = root ? 0.0 : src[xo + i];
+            if (MODE == 2) { base = l; rs = root ? 0.0 : v.res[xo + i]; }
+            else
+            {
+                base = -v.in.q[xo + i] + l;
+                winv = v.in.Qinv[xo + i]; lo = v.in.xmin[xo + i]; hi = v.in.xmax[xo + i];
+            }
+        }
+        else if (MODE != 2)
+        {
+            base = -v.in.r[uo + i];
+            winv = v.in.Rinv[uo + i]; lo = v.in.umin[uo + i]; hi = v.in.umax[uo + i];
+        }
+    }
+    /* the kids' multipliers (one contiguous range) and cmod = sum_kids b_j' lambda_j (:892) */
+    double cpart = 0.0, lkid = 0.0;
+    if (lane < D)
+    {
+        lkid = src[xb + lane];
+        if (MODE != 3) cpart = v.in.b[xb + lane] * lkid;
+    }
+    /* first (kid, column) pair of this lane: NX contiguous doubles straight into registers */
+    double cr[NX];
+    int p = lane;
+    auto load_col = [&](int pp) {
+        const int kid = pp / ncol, c = pp - kid * ncol;
+        const double *col = c < pnx ? v.in.A + d1.y + (size_t) (kid * pnx + c) * NX
+                                    : v.in.B + d1.z + (size_t) (kid * NU + (c - pnx)) * NX;
+        if (NX % 2 == 0)
+        {
+            const double2 *c2 = reinterpret_cast<const double2 *>(col);
+#pragma unroll
+            for (int r = 0; r < NX / 2; r++) { const double2 t = __ldg(c2 + r); cr[2 * r] = t.x; cr[2 * r + 1] = t.y; }
+        }
+        else
+        {
+#pragma unroll
+            for (int r = 0; r < NX; r++) cr[r] = __ldg(col + r);
+        }
+        return kid;
+    };
+    int kid = 0;
+    if (p < npair) kid = load_col(p);
+    if (!running) return; /* warp-uniform */
+    if (lane < D) sL[lane] = lkid;
+    __syncwarp();
+    if (MODE != 3)
+    {
+        const double c = warp_sum(cpart);
+        if (lane == 0) { if (MODE == 0) v.cmod0[g] = c; else v.dc[g] = c; }
+    }
+    while (p < npair)
+    {   /* s = column' * lambda_kid, sequential (dgemv_t order) */
+        const double *lk = sL + kid * NX;
+        double s = 0.0;
+#pragma unroll
+        for (int r = 0; r < NX; r++) s += cr[r] * lk[r];
+        sS[p] = s;
+        p += 32;
+        if (p < npair) kid = load_col(p);
+    }
+    __syncwarp();
+    if (own)
+    {
+        double acc = base;
+        for (int j = 0; j < md; j++) acc -= sS[j * ncol + lane];
+        if (MODE == 2)
+        {
+            if (isx) v.dq[xo + i] = acc; else v.dr[uo + i] = acc;
+        }
+        else
+        {
+            int mask;
+            const double unc = winv * acc;
+            const double val = clip_mask(unc, lo, hi, mask);
             if (isx)
             {
-                const double l = root ? 0.0 : src[xo + i];
-                if (MODE == 2) { base = l; rs = root ? 0.0 : v.res[xo + i]; }
-                else
-                {
-                    base = -v.in.q[xo + i] + l;
-                    winv = v.in.Qinv[xo + i]; lo = v.in.xmin[xo + i]; hi = v.in.xmax[xo + i];
-                }
-            }
-            else if (MODE != 2)
-            {
-                base = -v.in.r[uo + i];
-                winv = v.in.Rinv[uo + i]; lo = v.in.umin[uo + i]; hi = v.in.umax[uo + i];
-            }
-        }
-        /* the kids' multipliers (one contiguous range) and cmod = sum_kids b_j' lambda_j (:892) */
-        double cpart = 0.0;
-        if (lane < D)
-        {
-            const double l = src[xb + lane];
-            sL[lane] = l;
-            if (MODE != 3) cpart = v.in.b[xb + lane] * l;
-        }
-        __syncwarp();
-        if (MODE != 3)
-        {
-            const double c = warp_sum(cpart);
-            if (lane == 0) { if (MODE == 0) v.cmod0[g] = c; else v.dc[g] = c; }
-        }
-        /* one (kid, column) pair per lane: s = column' * lambda_kid */
-        for (int p = lane; p < npair; p += 32)
-        {
-            const int kid = p / ncol, c = p - kid * ncol;
-            const double *col = c < pnx ? v.in.A + d1.y + (size_t) (kid * pnx + c) * NX
-                                        : v.in.B + d1.z + (size_t) (kid * NU + (c - pnx)) * NX;
-            const double *lk = sL + kid * NX;
-            double cr[NX];
-            if (NX % 2 == 0)
-            {
-                const double2 *c2 = reinterpret_cast<const double2 *>(col);
-#pragma unroll
-                for (int r = 0; r < NX / 2; r++) { const double2 t = __ldg(c2 + r); cr[2 * r] = t.x; cr[2 * r + 1] = t.y; }
+                v.x[xo + i] = val;
+                if (MODE == 0) { v.qmod0[xo + i] = acc; v.xUnc[xo + i] = unc; v.P[xo + i] = mask == 0 ? winv : 0.0; }
             }
             else
             {
-#pragma unroll
-                for (int r = 0; r < NX; r++) cr[r] = __ldg(col + r);
-            }
-            double s = 0.0;
-#pragma unroll
-            for (int r = 0; r < NX; r++) s += cr[r] * lk[r];
-            sS[p] = s;
-        }
-        __syncwarp();
-        if (own)
-        {
-            double acc = base;
-            for (int j = 0; j < md; j++) acc -= sS[j * ncol + lane];
-            if (MODE == 2)
-            {
-                if (isx) v.dq[xo + i] = acc; else v.dr[uo + i] = acc;
-            }
-            else
-            {
-                int mask;
-                const double unc = winv * acc;
-                const double val = clip_mask(unc, lo, hi, mask);
-                if (isx)
-                {
-                    v.x[xo + i] = val;
-                    if (MODE == 0) { v.qmod0[xo + i] = acc; v.xUnc[xo + i] = unc; v.P[xo + i] = mask == 0 ? winv : 0.0; }
-                }
-                else
-                {
-                    v.u[uo + i] = val;
-                    if (MODE == 0) { v.rmod0[uo + i] = acc; v.uUnc[uo + i] = unc; v.Rt[uo + i] = mask == 0 ? winv : 0.0; }
-                }
+                v.u[uo + i] = val;
+                if (MODE == 0) { v.rmod0[uo + i] = acc; v.uUnc[uo + i] = unc; v.Rt[uo + i] = mask == 0 ? winv : 0.0; }
             }
         }
-        if (MODE == 2)
-        {   /* node's part of res'*dlam */
-            const double dotp = warp_sum((own && isx) ? rs * base : 0.0);
-            if (lane == 0) v.nvb[g] = dotp;
-        }
-        return;
     }
+    if (MODE == 2)
+    {   /* node's part of res'*dlam */
+        const double dotp = warp_sum((own && isx) ? rs * base : 0.0);
+        if (lane == 0) v.nvb[g] = dotp;
+    }
+    __syncwarp(); /* sL / sS are reused by the warp's next item */
+}
 
-    /* -------------------------------- leaves -------------------------------- */
-    const int slot = lane / NXP, i = lane - slot * NXP;
-    const int lf = (w - Np) * LPW + slot;
-    const bool act = lf < nleaf && i < NX;
+/* 32/NXP leaves: ld = this lane's LeafDesc (valid = the leaf exists) */
+template <int NX, int MODE>
+__device__ __forceinline__ void stage_leaves(const View &v, const int4 ld, bool valid, int i)
+{
+    constexpr int NXP = tqb_pow2_ge(NX);
+    const double *src = (MODE == 2) ? v.dlam : v.lam;
     double part = 0.0;
     int g = -1;
-    if (lf < nleaf)
+    if (valid)
     {
-        const int4 ld = __ldg(reinterpret_cast<const int4 *>(v.leaf_desc) + lf);
         if (v.status[ld.z] == TQB_RUNNING) g = ld.x;
-        if (act && g >= 0)
+        if (i < NX && g >= 0)
         {
             const int e = ld.y + i;
             const double l = ld.w ? 0.0 : src[e];
@@ -184,5 +184,43 @@ __global__ void __launch_bounds__(32 * TQB_STAGE_WPB) k_stage_fused(View v, int 
     else if (MODE == 0)
     {
         if (g >= 0 && i == 0) v.cmod0[g] = 0.0;
+    }
+}
+
+/* Persistent warps: item = a parent (items [0, Np)) or a group of 32/NXP leaves; a warp walks the
+ * items w, w + nwarps, ... and fetches the descriptor of its next item before it works on the
+ * current one, so the descriptor -> data dependency costs one memory latency per warp, not per item. */
+template <int NX, int NU, int MODE>
+__global__ void __launch_bounds__(32 * TQB_STAGE_WPB) k_stage_fused(View v, int Np, int nroots, int root_nx, int nleaf)
+{
+    constexpr int NXP = tqb_pow2_ge(NX), LPW = 32 / NXP;
+    __shared__ double sLs[TQB_STAGE_WPB][32];
+    __shared__ double sSs[TQB_STAGE_WPB][TQB_STAGE_MAXPAIR];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nwarps = gridDim.x * TQB_STAGE_WPB, nitems = Np + (nleaf + LPW - 1) / LPW;
+    const int slot = lane / NXP, li = lane - slot * NXP;
+    int4 n0 = make_int4(0, 0, 0, 0), n1 = n0, n2 = n0;
+    auto fetch = [&](int it) {
+        if (it < Np)
+        {
+            const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) it;
+            n0 = __ldg(dp); n1 = __ldg(dp + 1); n2 = __ldg(dp + 2);
+        }
+        else if (it < nitems)
+        {
+            const int lf = (it - Np) * LPW + slot;
+            if (lf < nleaf) n0 = __ldg(reinterpret_cast<const int4 *>(v.leaf_desc) + lf);
+        }
+    };
+    int it = blockIdx.x * TQB_STAGE_WPB + wib;
+    fetch(it);
+    while (it < nitems)
+    {
+        const int4 d0 = n0, d1 = n1, d2 = n2;
+        const int nxt = it + nwarps;
+        fetch(nxt);
+        if (it < Np) stage_parent<NX, NU, MODE>(v, d0, d1, d2, it < nroots, root_nx, sLs[wib], sSs[wib], lane);
+        else stage_leaves<NX, MODE>(v, d0, (it - Np) * LPW + slot < nleaf, li);
+        it = nxt;
     }
 }
