@@ -28,6 +28,10 @@
 #pragma once
 #include "tdunes_kernels.cuh"
 
+#ifndef TQB_DMMA_MIN_D
+#define TQB_DMMA_MIN_D 8 /* smallest block dimension built on the tensor cores */
+#endif
+
 /* Programmatic dependent launch (sm_90+): the level kernels of one sweep are launched with
  * cudaLaunchAttributeProgrammaticStreamSerialization, so level l starts while level l+1 still
  * runs, does everything that does not depend on it (descriptor + A/B loads, gradient, the
@@ -65,7 +69,7 @@ struct FusedCfg
      * build) | p (NCOL) | z (NCOL) | ys (D) | dgs (D) | invs (D) */
     /* FP64 tensor-core (DMMA m8n8k4) build of C diag(p) C' and of the Schur complement for the
      * larger blocks: 8x8 output tiles, operands in fragment layout straight from HBM / shared memory */
-    static constexpr bool DMMA = D >= 16;
+    static constexpr bool DMMA = D >= TQB_DMMA_MIN_D;
     static constexpr int TR = (D + 7) / 8;          /* row tiles of W */
     static constexpr int KS = (NCOL + 3) / 4;       /* k-steps of the build */
     static constexpr int LDCD = 20 + 16 * ((NCOL > 20 ? NCOL - 20 : 0) + 15) / 16 * (NCOL > 20); /* >= NCOL, = 4 mod 16 */
@@ -161,17 +165,16 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
             double acc[TR * (TR + 1) / 2][2];
 #pragma unroll
             for (int i = 0; i < TR; i++)
-            {
+            {   /* C z as one more tile column (z in column 0): the tensor core accumulates k in
+                 * ascending order with one rounding per term, like the scalar fma chain */
                 const int r = 8 * i + gid;
-                double sg = 0.0;
+                double sg = 0.0, sg1 = 0.0;
 #pragma unroll
                 for (int ks = 0; ks < KS; ks++)
                 {
-                    sg += af[i][ks] * zf[ks];
+                    dmma884(sg, sg1, af[i][ks], gid == 0 ? zf[ks] : 0.0);
                     if (r < D && 4 * ks + tig < NCOL) Cp[r * LDCD + 4 * ks + tig] = af[i][ks] * pf[ks];
                 }
-                sg += __shfl_xor_sync(FULL, sg, 1);
-                sg += __shfl_xor_sync(FULL, sg, 2);
                 if (tig == 0 && r < D) ys[r] = sg;
             }
 #pragma unroll
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
             for (int i = 0; i < TR; i++)
 #pragma unroll
                 for (int n = 0; n <= i; n++)
-                    if (8 * i + gid < D)
+                    if (8 * i + gid < D && 8 * n + 2 * tig < D) /* D is even: a pair never straddles the row end */
                         *reinterpret_cast<double2 *>(Ms + (8 * i + gid) * LDR + 8 * n + 2 * tig) =
                             make_double2(acc[i * (i + 1) / 2 + n][0], acc[i * (i + 1) / 2 + n][1]);
             __syncwarp();
