@@ -76,19 +76,58 @@ def launches_per_call(prob):
 
 # ------------------------------------------------------------------------------ clock sampling
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every 5 ms from a
+    thread (nvidia-smi -lms as the fallback; it needs ~0.3 s to start, longer than a short run)."""
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
              "clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.on = index, [], None, None, False
+        self.source = None
+
+    def _nvml_loop(self):
+        n, h = self.nvml, self.handle
+        bits = [(n.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (n.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (n.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (n.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        while self.on:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(sm), self.mx, [nm for b, nm in bits if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
+            import pynvml as n
+            n.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.index])
+                except Exception:
+                    pass
+            self.handle = n.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            self.nvml, self.on, self.source = n, True, "nvml 5 ms"
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi -lms 20"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -96,28 +135,34 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+                self.rows.append((float(r[0]), float(r[1]), [n for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")]))
             except Exception:
                 pass
+
+    def mark(self):
+        """index of the next sample: brackets the timed region"""
+        return len(self.rows)
+
+    def stop(self, lo=0, hi=None):
+        if self.nvml is not None:
+            self.on = False
+            self.thread.join(timeout=1)
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
+        rows = self.rows[lo:hi]
+        sm = [r[0] for r in rows]
+        mx = [r[1] for r in rows]
+        reasons = sorted({n for r in rows for n in r[2]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 # ------------------------------------------------------------------------------ reference arm
@@ -257,6 +302,49 @@ def bench_sdunes(lib, reps=10):
     return out
 
 
+def bench_dense(lib, reps=5):
+    """config 5: dense stage QPs (qp_solver = TREEQP_QPOASES_SOLVER): linear_chain nm=8 nu=7 (nx=16) md=4
+    Nr=2 Nh=20 with dense Q/R/S blocks, plus trees of the quadcopter (nx=6, nu=4) and crane (nx=4, nu=1)
+    dimensions, md=3 Nr=2 Nh=20"""
+    def ubox(p, ub):
+        p.umin[:] = -ub; p.umax[:] = ub; p.xmin[:] = -1e12; p.xmax[:] = 1e12
+        return p
+    probs = {
+        "linear_chain_nm8_nu7_md4_Nh20": P.densify(ubox(P.linear_chain(8, 7, 4, 2, 20, seed=2), 0.3), 6, 0.1, 0.0),
+        "quadcopter_dims_nx6_nu4_md3_Nh20": P.densify(P.random_tree(P.multistage_nk(3, 2, 20), 6, 4, seed=8, ubound=0.3), 4, 0.1, 0.0),
+        "crane_dims_nx4_nu1_md3_Nh20": P.densify(P.random_tree(P.multistage_nk(3, 2, 20), 4, 1, seed=9, ubound=0.2), 5, 0.05, 0.0),
+    }
+    out = {}
+    path = ref_lib_path(False)
+    ref = capi.TreeQpLib(path) if path else None
+    for name, prob in probs.items():
+        qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+        s = capi.Tdunes(lib, qp_in, qp_solver=1, maxIter=200)
+        lam0 = np.zeros(prob.n_lambda)
+        s.set_dual_initialization(lam0)
+        assert s.upload() == capi.TREEQP_OK
+        best, e2e = 1e9, 1e9
+        for _ in range(reps):
+            st = s.solve_resident(); best = min(best, s.stats()["gpu_ms"])
+        for _ in range(reps):
+            s.set_dual_initialization(lam0)
+            t0 = time.perf_counter(); st = s.solve(qp_out); e2e = min(e2e, 1e3 * (time.perf_counter() - t0))
+        rec = {"nodes": int(prob.Nn), "status": int(st), "newton_iters": int(qp_out.iter), "ms_per_solve_resident": best,
+               "ms_per_solve_e2e": e2e, "us_per_newton_iter": 1e3 * best / max(qp_out.iter, 1),
+               "kkt": float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))}
+        s.destroy()
+        if ref is not None:
+            rin, rout = capi.QpIn(ref, prob), capi.QpOut(ref, prob)
+            rs = capi.Tdunes(ref, rin, qp_solver=1, maxIter=200)
+            tb = 1e9
+            for _ in range(3):
+                rs.set_dual_initialization(lam0); rs.solve(rout); tb = min(tb, 1e3 * rout.total_time)
+            rec["cpu_reference_ms_per_solve"] = tb
+            rec["cpu_reference_newton_iters"] = int(rout.iter)
+        out[name] = rec
+    return out
+
+
 def bench_sharded(lib, args, rank, world, local, dist, barrier, max_over_ranks):
     """N > 1: ONE tree (the N=1 workload) sharded by subtree over the ranks: strong scaling"""
     def bcast(b):
@@ -297,7 +385,7 @@ def bench_sharded(lib, args, rank, world, local, dist, barrier, max_over_ranks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--depth", type=int, default=16)
@@ -307,9 +395,13 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
+    # host threads of the packer (OpenMP): torchrun exports OMP_NUM_THREADS=1 to every rank, which
+    # would serialise the BLASFEO -> SoA conversion of the e2e path; give each rank its share of cores
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
     import torch
     rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
@@ -343,12 +435,13 @@ def main():
 
     # ---- resident (inputs already in HBM): value
     assert solver.upload() == capi.TREEQP_OK
-    for _ in range(args.warmup):
-        st = solver.solve_resident()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        st = solver.solve_resident()
     barrier()
+    clk_lo = clocks.mark()
     t0 = time.perf_counter()
     dev_ms = 0.0
     for _ in range(args.steps):
@@ -373,7 +466,7 @@ def main():
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     e2e_stats = solver.stats()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(clk_lo, clocks.mark()) if rank == 0 else None
     assert st2 == 0 and qp_out.iter == iters
     kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
 
@@ -416,9 +509,17 @@ def main():
     breakdown = {k: {"ms": round(v[0], 4), "launches": v[1],
                      "GBps": round(alg[k] * (v[1] / lpc[k]) / (v[0] * 1e-3) / 1e9, 1) if k in alg else None}
                  for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+        if tr.get("depth") == args.depth and top in tr["per_launch_bytes"]:
+            traffic, traffic_src = tr["per_launch_bytes"][top], tr["source"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": ("k_build_factor (fused K2+K3, one launch per depth)" if fused and top == "k_factor_level" else top),
                 "achieved": achieved, "peak": peaks, "unit": "GB/s",
-                "frac": achieved / peaks, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peaks, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": alg[top] / lpc[top], "peak_source": peak_src,
                 "algorithmic_bytes_per_call": alg[top], "launches_per_call": lpc[top],
                 "avg_launch_us": 1e3 * t_ms / n_launch, "kernel_share_of_solve": t_ms / prof["gpu_ms"],
                 "per_kernel": breakdown}
@@ -437,7 +538,8 @@ def main():
 
     extra = {}
     if world == 1 and not args.no_extra:
-        for name, fn in (("batch4096_linear_chain", bench_batch), ("sdunes_spring_mass_cfg2", bench_sdunes)):
+        for name, fn in (("batch4096_linear_chain", bench_batch), ("sdunes_spring_mass_cfg2", bench_sdunes),
+                         ("dense_stage_qps_cfg5", bench_dense)):
             try:
                 extra[name] = fn(lib)
             except Exception as e:

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round-trip used for the record: GPU parity tests, headline bench (defaults), and one ncu pass for
+# the DRAM traffic per launch of every kernel class (tools/ncu_traffic.py turns it into
+# profiles/traffic_latest.json, which bench.py reports as roofline.traffic).
+tag=${1:-dev}
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+tail -3 gpurun_out/bench_$tag.err
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
+    --log-file gpurun_out/${tag}_traffic.csv python tools/profile_solve.py --depth 16 --max-iter 2 > gpurun_out/${tag}_traffic.log 2>&1
+python tools/ncu_traffic.py gpurun_out/${tag}_traffic.csv 16 gpurun_out/${tag}_traffic.json "ncu dram__bytes_{read,write}.sum, 2 Newton iterations of the depth-16 QP ($tag)" | cut -c1-600
+python - <<PY
+import json
+d = json.load(open("gpurun_out/bench_$tag.json"))
+print("ms/solve", round(d["ms_per_step"], 3), "e2e", {k: (round(v, 2) if isinstance(v, float) else v) for k, v in d["e2e"].items()})
+print("clocks", d["clocks"], "frac", round(d["roofline"]["frac"], 3))
+print({k: (round(x["ms"], 2), x["launches"]) for k, x in d["roofline"]["per_kernel"].items()})
+for k, v in d["other_workloads"].items():
+    print(k, json.dumps(v)[:900])
+PY

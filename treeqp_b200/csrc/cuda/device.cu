@@ -469,6 +469,32 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     free(D);
 }
 
+/* pipelined upload: the host packs node ranges while earlier ranges are already on the wire;
+ * begin/end bracket the copies with events (ms_total = first byte to last byte on the stream,
+ * ms_tail = what the host still had to wait for after its last range was packed) */
+extern "C" int tqb_device_upload_begin(tqb_device *D)
+{
+    CK(cudaEventRecord(D->ev0, D->stream));
+    return 0;
+}
+
+extern "C" int tqb_device_upload_range(tqb_device *D, const double *h_in, long long off, long long n)
+{
+    if (n <= 0) return 0;
+    CK(cudaMemcpyAsync(D->d_in + off, h_in + off, sizeof(double) * (size_t) n, cudaMemcpyHostToDevice, D->stream));
+    return 0;
+}
+
+extern "C" int tqb_device_upload_end(tqb_device *D, double *ms_total)
+{
+    CK(cudaEventRecord(D->ev1, D->stream));
+    CK(cudaStreamSynchronize(D->stream));
+    float t = 0.f;
+    CK(cudaEventElapsedTime(&t, D->ev0, D->ev1));
+    if (ms_total) *ms_total = t;
+    return 0;
+}
+
 extern "C" int tqb_device_upload(tqb_device *D, const double *h_in, long long n_in, double *ms)
 {
     CK(cudaEventRecord(D->ev0, D->stream));

@@ -302,21 +302,34 @@ void tqb_forest_destroy(tqb_forest *f)
 /* panel-major -> column-major, 4 rows of a panel at a time */
 static void unpack_dmat(const struct blasfeo_dmat *M, double *dst)
 {
-    int m = M->m, n = M->n;
-    for (int j = 0; j < n; j++)
-        for (int i = 0; i < m; i++) dst[i + (size_t) j * m] = BLASFEO_DMATEL(M, i, j);
+    const int m = M->m, n = M->n, sda = M->cn;
+    const double *pA = M->pA;
+    int ip = 0;
+    for (; ip + TQB_PS <= m; ip += TQB_PS)
+    {   /* a full panel: the 4 rows of column j are contiguous on both sides */
+        const double *src = pA + (size_t) ip * sda;
+        double *d = dst + ip;
+        for (int j = 0; j < n; j++) memcpy(d + (size_t) j * m, src + TQB_PS * j, TQB_PS * sizeof(double));
+    }
+    if (ip < m)
+    {
+        const int r = m - ip;
+        const double *src = pA + (size_t) ip * sda;
+        double *d = dst + ip;
+        for (int j = 0; j < n; j++)
+            for (int i = 0; i < r; i++) d[i + (size_t) j * m] = src[TQB_PS * j + i];
+    }
 }
 
 /* gmap == NULL: tree t of the forest is qp itself; otherwise local node j is node gmap[j] of qp */
-void tqb_forest_pack_mapped_(tqb_forest *f, int t, const tree_qp_in *qp, const int *gmap)
+static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gmap, int j0, int j1)
 {
     const tqb_tables *T = &f->ht;
     tqb_inputs *in = &f->hin;
     int g0 = T->tnode0[t];
-    const int N = T->tnode0[t + 1] - g0;
-    assert(gmap || N == qp->N);
-#pragma omp parallel for schedule(static) if (N > 2048)
-    for (int j = 0; j < N; j++)
+    assert(gmap || T->tnode0[t + 1] - g0 == qp->N);
+#pragma omp parallel for schedule(static) if (j1 - j0 > 2048)
+    for (int j = j0; j < j1; j++)
     {
         const int k = gmap ? gmap[j] : j;
         int g = g0 + j, nx = qp->nx[k], nu = qp->nu[k], xo = T->xoff[g], uo = T->uoff[g];
@@ -378,7 +391,80 @@ void tqb_forest_pack_mapped_(tqb_forest *f, int t, const tree_qp_in *qp, const i
     }
 }
 
+void tqb_forest_pack_mapped_(tqb_forest *f, int t, const tree_qp_in *qp, const int *gmap)
+{
+    pack_range(f, t, qp, gmap, 0, f->ht.tnode0[t + 1] - f->ht.tnode0[t]);
+}
+
 void tqb_forest_pack(tqb_forest *f, int t, const tree_qp_in *qp) { tqb_forest_pack_mapped_(f, t, qp, NULL); }
+
+/* H2D of the slices of every input array that belong to forest nodes [ga, gb): the offset tables
+ * are prefix sums over the node order, so each slice is one contiguous range */
+static int upload_nodes(tqb_forest *f, int ga, int gb)
+{
+    const tqb_tables *T = &f->ht;
+    const tqb_dims *d = &f->dims;
+    const tqb_inputs *in = &f->hin;
+    const int last = gb >= d->Nn;
+    const long long a0 = T->aoff[ga], a1 = last ? d->szA : T->aoff[gb];
+    const long long b0 = T->boff[ga], b1 = last ? d->szB : T->boff[gb];
+    const long long x0 = T->xoff[ga], x1 = last ? d->X : T->xoff[gb];
+    const long long u0 = T->uoff[ga], u1 = last ? d->U : T->uoff[gb];
+    int rc = 0;
+    rc |= tqb_device_upload_range(f->dev, f->h_in, (in->A - f->h_in) + a0, a1 - a0);
+    rc |= tqb_device_upload_range(f->dev, f->h_in, (in->B - f->h_in) + b0, b1 - b0);
+    const double *xs[] = {in->b, in->q, in->Qd, in->Qinv, in->xmin, in->xmax, in->lam0, in->dxmin, in->dxmax};
+    const double *us[] = {in->r, in->Rd, in->Rinv, in->umin, in->umax, in->dumin, in->dumax};
+    for (unsigned i = 0; i < sizeof xs / sizeof xs[0]; i++)
+        if (xs[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (xs[i] - f->h_in) + x0, x1 - x0);
+    for (unsigned i = 0; i < sizeof us / sizeof us[0]; i++)
+        if (us[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (us[i] - f->h_in) + u0, u1 - u0);
+    return rc;
+}
+
+#ifndef TQB_UPLOAD_CHUNK_DOUBLES
+#define TQB_UPLOAD_CHUNK_DOUBLES (3LL << 20) /* 24 MB of input per pipeline stage */
+#endif
+
+int tqb_forest_pack_upload(tqb_forest *f, const tree_qp_in *const *qp, double *tail_ms)
+{
+    const tqb_tables *T = &f->ht;
+    const tqb_dims *d = &f->dims;
+    const int nT = d->nT;
+    long long nstage = d->n_in / TQB_UPLOAD_CHUNK_DOUBLES;
+    if (nstage < 1) nstage = 1;
+    if (nstage > 32) nstage = 32;
+    int rc = tqb_device_upload_begin(f->dev);
+    if (nT == 1)
+    {
+        const int N = T->tnode0[1];
+        for (int c = 0; c < nstage; c++)
+        {
+            const int j0 = (int) ((long long) N * c / nstage), j1 = (int) ((long long) N * (c + 1) / nstage);
+            pack_range(f, 0, qp[0], NULL, j0, j1);
+            rc |= upload_nodes(f, j0, j1);
+        }
+    }
+    else
+    {
+        for (int c = 0; c < nstage; c++)
+        {
+            const int t0 = (int) ((long long) nT * c / nstage), t1 = (int) ((long long) nT * (c + 1) / nstage);
+            if (t1 == t0) continue;
+#pragma omp parallel for schedule(dynamic, 8) if (t1 - t0 > 32)
+            for (int t = t0; t < t1; t++) tqb_forest_pack(f, t, qp[t]);
+            rc |= upload_nodes(f, T->tnode0[t0], T->tnode0[t1]);
+        }
+    }
+    /* dense Hessian blocks: offsets exist only for the dense nodes, sent as one range at the end */
+    if (d->has_dense) rc |= tqb_device_upload_range(f->dev, f->h_in, f->hin.H - f->h_in, d->szH);
+    const double t0 = tqb_wall_ms();
+    double total = 0.0;
+    rc |= tqb_device_upload_end(f->dev, &total);
+    if (tail_ms) *tail_ms = tqb_wall_ms() - t0;
+    f->h2d_ms = total;
+    return rc;
+}
 
 /* lambda: multipliers of nodes 1..N-1 of tree t, concatenated (dual_Newton_tree.c:1654-1663) */
 void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda)

@@ -118,6 +118,9 @@ void tqb_forest_destroy(tqb_forest *f);
 /* BLASFEO views -> pinned staging (reciprocals of the weights are formed here,
  * dual_Newton_tree_clipping.c:149-170) */
 void tqb_forest_pack(tqb_forest *f, int t, const struct tree_qp_in_ *qp);
+/* pack + H2D as a pipeline over node ranges (single tree) or tree ranges (batch); tail_ms = the
+ * wait after the last range was packed.  Returns 0 on success. */
+int tqb_forest_pack_upload(tqb_forest *f, const struct tree_qp_in_ *const *qp, double *tail_ms);
 void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda);
 void tqb_forest_unpack(const tqb_forest *f, int t, struct tree_qp_out_ *out);
 void tqb_layout_tables(const tqb_dims *d, int *base, tqb_tables *t);
@@ -135,6 +138,9 @@ tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int, const int 
 void tqb_device_destroy(tqb_device *d);
 /* async H2D of the input block, returns 0 on success */
 int tqb_device_upload(tqb_device *d, const double *h_in, long long n_in, double *ms);
+int tqb_device_upload_begin(tqb_device *d);
+int tqb_device_upload_range(tqb_device *d, const double *h_in, long long off, long long n);
+int tqb_device_upload_end(tqb_device *d, double *ms_total);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
 int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,
                      int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms, long long *launches,

@@ -279,10 +279,12 @@ return_t treeqp_tdunes_upload(const tree_qp_in *qp_in, const treeqp_tdunes_opts_
     (void) opts;
     tqb_ctx *ctx = ctx_of(work);
     if (!ctx || !ctx->forest) return TREEQP_UNKNOWN_ERROR;
-    double t0 = tqb_wall_ms();
-    tqb_forest_pack(ctx->forest, 0, qp_in);
-    ctx->forest->pack_ms = tqb_wall_ms() - t0;
-    if (forest_upload(ctx->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    /* pack and H2D pipelined by node range: pack_ms = wall time of the whole phase minus the
+     * wait for the last ranges (h2d_tail), h2d_ms = first to last byte on the stream */
+    double t0 = tqb_wall_ms(), tail = 0.0;
+    if (tqb_forest_pack_upload(ctx->forest, (const tree_qp_in *const *) &qp_in, &tail)) return TREEQP_UNKNOWN_ERROR;
+    ctx->forest->pack_ms = tqb_wall_ms() - t0 - tail;
+    ctx->forest->h2d_bytes = (long long) sizeof(double) * ctx->forest->dims.n_in;
     ctx->uploaded = 1;
     ctx->lam_dirty = 0;
     return TREEQP_OK;
@@ -380,11 +382,10 @@ void treeqp_tdunes_batch_set_dual_initialization(treeqp_tdunes_batch *b, int i, 
 
 return_t treeqp_tdunes_batch_upload(treeqp_tdunes_batch *b, const tree_qp_in *const *qp_in)
 {
-    double t0 = tqb_wall_ms();
-#pragma omp parallel for schedule(dynamic, 16) if (b->n > 32)
-    for (int i = 0; i < b->n; i++) tqb_forest_pack(b->forest, i, qp_in[i]);
-    b->forest->pack_ms = tqb_wall_ms() - t0;
-    if (forest_upload(b->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    double t0 = tqb_wall_ms(), tail = 0.0;
+    if (tqb_forest_pack_upload(b->forest, qp_in, &tail)) return TREEQP_UNKNOWN_ERROR;
+    b->forest->pack_ms = tqb_wall_ms() - t0 - tail;
+    b->forest->h2d_bytes = (long long) sizeof(double) * b->forest->dims.n_in;
     b->uploaded = 1;
     return TREEQP_OK;
 }
