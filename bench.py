@@ -232,9 +232,13 @@ def reference_arm(args):
 
 
 # ----------------------------------------------------------------- secondary workloads (N = 1)
-def bench_batch(lib, n=4096, reps=3):
-    """config 4: n independent linear_chain tree QPs (175 nodes each) as one forest"""
-    probs = P.linear_chain_batch(n, seed=0)
+def bench_batch(lib, n=4096, reps=3, rank=0, world=1, barrier=None, max_over_ranks=None):
+    """config 4: n independent linear_chain tree QPs (175 nodes each) as one forest; with N ranks each
+    rank takes n/N instances (QP i -> rank i // (n/N)), no collective on the data path"""
+    barrier = barrier or (lambda: None)
+    max_over_ranks = max_over_ranks or (lambda x: x)
+    nl = n // world
+    probs = P.linear_chain_batch(nl, seed=rank * nl)
     qp_ins = [capi.QpIn(lib, p) for p in probs]
     qp_outs = [capi.QpOut(lib, p) for p in probs]
     batch = capi.TdunesBatch(lib, qp_ins)
@@ -242,19 +246,24 @@ def bench_batch(lib, n=4096, reps=3):
     batch.solve_resident()
     t_res = []
     for _ in range(reps):
-        t0 = time.perf_counter(); batch.solve_resident(); t_res.append(time.perf_counter() - t0)
+        barrier(); t0 = time.perf_counter(); batch.solve_resident(); barrier()
+        t_res.append(max_over_ranks(time.perf_counter() - t0))
     assert (batch.status == 0).all()
     t_e2e = []
     for _ in range(reps):
-        t0 = time.perf_counter(); batch.solve(qp_outs); t_e2e.append(time.perf_counter() - t0)
+        barrier(); t0 = time.perf_counter(); batch.solve(qp_outs); barrier()
+        t_e2e.append(max_over_ranks(time.perf_counter() - t0))
     st = batch.stats()
     iters = np.array([o.iter for o in qp_outs])
-    out = {"workload": "%d x linear_chain nm=4 nu=3 md=3 Nr=2 Nh=20 (175 nodes), |u|<=0.5, x0 seeded" % n,
+    n = nl * world
+    out = {"workload": "%d x linear_chain nm=4 nu=3 md=3 Nr=2 Nh=20 (175 nodes), |u|<=0.5, x0 seeded%s" % (n, "" if world == 1 else ", %d per GPU" % nl),
            "qp_per_s_resident": n / min(t_res), "qp_per_s_e2e": n / min(t_e2e), "ms_per_batch_resident": 1e3 * min(t_res),
            "ms_per_batch_e2e": 1e3 * min(t_e2e), "newton_iters_max": int(iters.max()), "newton_iters_median": float(np.median(iters)),
            "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "launches": st["kernel_launches"]}
+    if world > 1:
+        out["scaling"] = "strong (4096 QPs in total)"
     path = ref_lib_path(False)
-    if path:
+    if path and world == 1:
         ref = capi.TreeQpLib(path)
         m, tt = 32, 0.0
         for i in range(m):
@@ -483,6 +492,13 @@ def main():
         except Exception as e:  # report, never hide
             sharded = {"error": repr(e)}
 
+    batch_sharded = None
+    if dist is not None and not args.no_extra:
+        try:
+            batch_sharded = bench_batch(lib, 4096, 3, rank, world, barrier, max_over_ranks)
+        except Exception as e:
+            batch_sharded = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -537,6 +553,8 @@ def main():
         cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
 
     extra = {}
+    if batch_sharded is not None:
+        extra["batch4096_linear_chain"] = batch_sharded
     if world == 1 and not args.no_extra:
         for name, fn in (("batch4096_linear_chain", bench_batch), ("sdunes_spring_mass_cfg2", bench_sdunes),
                          ("dense_stage_qps_cfg5", bench_dense)):
