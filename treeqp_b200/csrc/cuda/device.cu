@@ -72,6 +72,7 @@ struct tqb_device
     /* fast path (uniform dimensions, see tdunes_fused.cuh) */
     int fast, f_nx, f_nu, f_pnx;
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
+    int *chain_link;      /* [Nh] depth l continues the chains of depth l-1 (one kid per parent, same order) */
     double *d_schur;
     int *d_lvl_desc;
     int *d_leaf_desc; /* LeafDesc records (tdunes_stage.cuh) */
@@ -190,6 +191,77 @@ static int launch_bs(tqb_device *D, int begin, int cnt)
     return 0;
 }
 
+template <int NX, int NU>
+static int launch_bf_chain(tqb_device *D, int top_begin, int cnt, int nlev, int kp_bottom, int pre_ok)
+{
+    using Cfg = FusedCfg<NX, NU, 1, NX, false>;
+    static bool attr_done = false;
+    const int wpb = 4;
+    const size_t smem = (size_t) wpb * Cfg::SMEM * sizeof(double);
+    if (!attr_done)
+    {
+        CK(cudaFuncSetAttribute(k_build_factor_chain<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr_done = true;
+    }
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
+    CK(launch_pdl(k_build_factor_chain<NX, NU>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
+                  D->v, top_begin, cnt, nlev, kp_bottom, pre_ok));
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    return 0;
+}
+
+template <int NX>
+static int launch_bs_chain(tqb_device *D, int top_begin, int cnt, int nlev)
+{
+    const int wpb = 4;
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    CK(launch_pdl(k_backsolve_chain<NX>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, top_begin, cnt, nlev));
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    return 0;
+}
+
+/* chain segment that has depth l as its deepest level: returns its top depth (== l: no segment) */
+static int chain_top(const tqb_device *D, int l)
+{
+    if (!D->chain_link || D->comm) return l;
+    int lt = l;
+    while (lt >= 2 && D->chain_link[lt]) lt--;
+    return lt;
+}
+
+/* chain segment that has depth l as its top level: returns its deepest depth */
+static int chain_bottom(const tqb_device *D, int l)
+{
+    if (!D->chain_link || D->comm) return l;
+    int lb = l;
+    while (lb + 1 < D->dims.Nh && D->chain_link[lb + 1]) lb++;
+    return lb;
+}
+
+static int fused_factor_chain(tqb_device *D, int lt, int lb, int pre_ok)
+{
+    const int begin = D->lvl_ptr[lt], cnt = D->lvl_ptr[lt + 1] - begin;
+    const int nx = D->f_nx, nu = D->f_nu;
+#define X(a, b) if (nx == a && nu == b) return launch_bf_chain<a, b>(D, begin, cnt, lb - lt + 1, D->lvl_kp[lb], pre_ok);
+    X(4, 1) X(6, 4) X(8, 3) X(12, 4)
+#undef X
+    return 1;
+}
+
+static int fused_backsolve_chain(tqb_device *D, int lt, int lb)
+{
+    const int begin = D->lvl_ptr[lt], cnt = D->lvl_ptr[lt + 1] - begin;
+    const int nx = D->f_nx;
+#define X(a) if (nx == a) return launch_bs_chain<a>(D, begin, cnt, lb - lt + 1);
+    X(4) X(6) X(8) X(12)
+#undef X
+    return 1;
+}
+
 static int fused_factor_level(tqb_device *D, int l, int pre_ok)
 {
     const int begin = D->lvl_ptr[l], cnt = D->lvl_ptr[l + 1] - begin;
@@ -278,6 +350,21 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
         D->v.lvl_desc = D->d_lvl_desc;
     }
     D->fast = 1;
+    {   /* chain links: depth l continues depth l-1 when both have one kid per parent and the w-th
+         * parent of depth l is the kid of the w-th parent of depth l-1 */
+        const char *e0 = getenv("TREEQP_B200_NO_CHAIN");
+        D->chain_link = (int *) calloc((size_t) d->Nh + 1, sizeof(int));
+        if (!(e0 && e0[0] == '1') && !ghost)
+            for (int l = 2; l < d->Nh; l++)
+            {
+                const int c0 = D->lvl_ptr[l] - D->lvl_ptr[l - 1], c1 = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+                if (D->lvl_md[l] != 1 || D->lvl_md[l - 1] != 1 || c0 != c1 || c1 <= 0) continue;
+                int ok = 1;
+                for (int w = 0; w < c1 && ok; w++)
+                    ok = T.kid0[T.lvl_nodes[D->lvl_ptr[l - 1] + w]] == T.lvl_nodes[D->lvl_ptr[l] + w];
+                D->chain_link[l] = ok;
+            }
+    }
     {   /* leaf records for k_stage_fused; it needs leaves without inputs and few (kid, column) pairs */
         int nleaf = 0, ok = 1;
         for (int g = 0; g < d->Nn; g++)
@@ -458,7 +545,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (!D) return;
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
-    cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); cudaFree(D->d_leaf_desc); free(D->lvl_md); free(D->lvl_kp);
+    cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); cudaFree(D->d_leaf_desc); free(D->lvl_md); free(D->lvl_kp); free(D->chain_link);
     cudaFree(D->d_cut_nodes); cudaFree(D->d_send); cudaFree(D->d_recv); cudaFree(D->d_tred);
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
@@ -650,14 +737,31 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             {
                 const bool exch = D->comm && l == D->cut_depth - 1;
                 if (exch && exchange_cut_nodes(D)) return 1;
-                if (fused_factor_level(D, l, (l < Nh - 1 && !exch) ? 1 : 0)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+                const int pre_ok = (l < Nh - 1 && !exch) ? 1 : 0;
+                const int lt = chain_top(D, l);
+                if (lt < l)
+                {   /* depths lt..l are chains: one launch walks them all */
+                    if (fused_factor_chain(D, lt, l, pre_ok)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+                    l = lt;
+                    continue;
+                }
+                if (fused_factor_level(D, l, pre_ok)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
             }
             LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
             if (D->comm && allreduce_tree_sums(D, 1, 0, o->termCondition == 2)) return 1;
             LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
             if (peek_counter(D, 0, 4)) return 1;
             for (int l = 1; l < Nh; l++)
+            {
+                const int lb = chain_bottom(D, l);
+                if (lb > l && D->chain_link[l + 1])
+                {
+                    if (fused_backsolve_chain(D, l, lb)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+                    l = lb;
+                    continue;
+                }
                 if (fused_backsolve_level(D, l)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
+            }
         }
         else
         {

@@ -88,27 +88,36 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 #ifndef TQB_BF_MINBLOCKS
 #define TQB_BF_MINBLOCKS 4
 #endif
+/* small blocks need few registers: ask for more resident CTAs (the kernel is latency bound) */
+#ifndef TQB_BF_MINBLOCKS_D8
+#define TQB_BF_MINBLOCKS_D8 6
+#endif
+#ifndef TQB_BF_MINBLOCKS_D16
+#define TQB_BF_MINBLOCKS_D16 5
+#endif
+__host__ __device__ constexpr int tqb_bf_minblocks(int d) { return d <= 8 ? TQB_BF_MINBLOCKS_D8 : d <= 16 ? TQB_BF_MINBLOCKS_D16 : TQB_BF_MINBLOCKS; }
+
+/* one parent block by one warp: `desc` = index of its level descriptor, `Ms` = the warp's shared
+ * memory (Cfg::SMEM doubles), `wait_here` = this block is the first thing the warp does in a kernel
+ * launched with programmatic stream serialisation (the wait sits between build and factorisation) */
 template <int NX, int NU, int MD, int PNX, bool ROOT>
-__global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents, int pre_ok)
+__device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_are_parents, bool wait_here, double *Ms, int lane)
 {
     using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
     constexpr int D = Cfg::D, NCOL = Cfg::NCOL, LDC = Cfg::LDC, LDR = Cfg::LDR;
     constexpr int NROWL = Cfg::NROWL, NCOLU = Cfg::NCOLU, RL = Cfg::RL;
     static_assert(D <= 32, "block dimension must fit one warp");
     static_assert((D & 1) == 0, "even block dimension required (vectorised rows)");
-    extern __shared__ double smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int w = blockIdx.x * wpb + wib;
-    /* pre_ok = 0: the launch before this one wrote data read by the build phase (k_stage<0> before
-     * the bottom level, the cut-node exchange of a sharded solve): wait first */
-    if (!pre_ok) { pdl_wait(); pdl_release(); }
-    if (w >= count) { pdl_wait(); pdl_release(); return; }
-    const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) (lvl_begin + w);
+    const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * desc;
     const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
     const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
-    if (v.status[d2.y] != TQB_RUNNING) { pdl_wait(); pdl_release(); return; }
+    if (v.status[d2.y] != TQB_RUNNING)
+    {
+        if (wait_here) { pdl_wait(); pdl_release(); }
+        return;
+    }
 
-    double *Ms = smem + (size_t) wib * Cfg::SMEM; /* Ms[j][r] = column j of the factored augmented matrix */
+    /* Ms[j][r] = column j of the factored augmented matrix */
     double *Cp = Ms;                              /* Cp[K][c] = p_c * C[K][c] (build phase only) */
     double *ps = Ms + Cfg::SM_M;                  /* [P_p ; Rt_p] */
     double *zs = ps + NCOL + 2;                   /* [x_p ; u_p] */
@@ -299,7 +308,7 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
         }
         }
         /* ---- everything below needs the kids' level ---- */
-        if (attempt == 0) { pdl_wait(); pdl_release(); }
+        if (attempt == 0 && wait_here) { pdl_wait(); pdl_release(); }
         rr = res - ((kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0);
         if (isW)
         {
@@ -470,14 +479,51 @@ __global__ void __launch_bounds__(128, TQB_BF_MINBLOCKS) k_build_factor(View v, 
     }
 }
 
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+__global__ void __launch_bounds__(128, tqb_bf_minblocks(NX * MD)) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents, int pre_ok)
+{
+    using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    /* pre_ok = 0: the launch before this one wrote data read by the build phase (k_stage<0> before
+     * the bottom level, the cut-node exchange of a sharded solve): wait first */
+    if (!pre_ok) { pdl_wait(); pdl_release(); }
+    if (w >= count) { pdl_wait(); pdl_release(); return; }
+    bf_block<NX, NU, MD, PNX, ROOT>(v, (size_t) (lvl_begin + w), kids_are_parents, true, smem + (size_t) wib * Cfg::SMEM, lane);
+}
+
+/* Chain segments (consecutive depths whose parents have ONE kid each: the scenario chains below the
+ * robust horizon of a multistage tree): warp w walks chain w from its deepest parent up to the
+ * top of the segment in ONE launch instead of one launch per depth.  Breadth-first numbering keeps
+ * the order of the chains from depth to depth, so block w of depth l-1 is the parent of block w
+ * of depth l; the Schur complement travels through v.schur / v.rsub (written and re-read by the
+ * same warp, L1/L2 hits).  Same arithmetic per block as k_build_factor<NX,NU,1,NX,false>. */
+template <int NX, int NU>
+__global__ void __launch_bounds__(128, tqb_bf_minblocks(NX)) k_build_factor_chain(View v, int top_begin, int count, int nlev, int bottom_kids_are_parents, int pre_ok)
+{
+    using Cfg = FusedCfg<NX, NU, 1, NX, false>;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (!pre_ok) { pdl_wait(); pdl_release(); }
+    if (w >= count) { pdl_wait(); pdl_release(); return; }
+    double *Ms = smem + (size_t) wib * Cfg::SMEM;
+#pragma unroll 1
+    for (int l = nlev - 1; l >= 0; l--)
+    {
+        const bool first = l == nlev - 1;
+        bf_block<NX, NU, 1, NX, false>(v, (size_t) top_begin + (size_t) l * count + w, first ? bottom_kids_are_parents : 1, first, Ms, lane);
+        __syncwarp(); /* S, s of this block are visible to the whole warp; Ms may be reused */
+    }
+}
+
+/* one block of the root-to-leaves substitution; `wait_here` as in bf_block */
 template <int NX, int MD>
-__global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, int count)
+__device__ __forceinline__ void bs_block(const View &v, size_t desc, bool wait_here, int lane)
 {
     constexpr int D = NX * MD;
-    const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= count) { pdl_wait(); pdl_release(); return; }
-    const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) (lvl_begin + w);
+    const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * desc;
     const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
     const int xb = d1.x, xo = d0.z;
     const double *Lp = v.W + d1.w, *Up = v.Ut + d2.x;
@@ -490,8 +536,11 @@ __global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, 
     for (int c = 0; c < NX; c++) ucol[c] = act ? Up[c * D + lane] : 0.0;
     double y = act ? v.dlam[xb + lane] : 0.0;
     const double inv = act ? v.Linv[xb + lane] : 0.0;
-    pdl_wait();
-    pdl_release();
+    if (wait_here)
+    {
+        pdl_wait();
+        pdl_release();
+    }
     if (v.status[d2.y] != TQB_RUNNING) return;
     double s = 0.0;
 #pragma unroll
@@ -505,4 +554,29 @@ __global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, 
         else if (lane < i) y -= lcol[i] * yi;
     }
     if (act) v.dlam[xb + lane] = y;
+}
+
+template <int NX, int MD>
+__global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, int count)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= count) { pdl_wait(); pdl_release(); return; }
+    bs_block<NX, MD>(v, (size_t) (lvl_begin + w), true, lane);
+}
+
+/* root-to-leaves substitution along chain w (see k_build_factor_chain): dlam of the block just
+ * finished is the parent value of the next one */
+template <int NX>
+__global__ void __launch_bounds__(128) k_backsolve_chain(View v, int top_begin, int count, int nlev)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= count) { pdl_wait(); pdl_release(); return; }
+#pragma unroll 1
+    for (int l = 0; l < nlev; l++)
+    {
+        bs_block<NX, 1>(v, (size_t) top_begin + (size_t) l * count + w, l == 0, lane);
+        __syncwarp();
+    }
 }
