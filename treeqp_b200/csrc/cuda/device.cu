@@ -73,6 +73,7 @@ struct tqb_device
     int fast, f_nx, f_nu, f_pnx;
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
     int *chain_link;      /* [Nh] depth l continues the chains of depth l-1 (one kid per parent, same order) */
+    int pair_begin;       /* level descriptors from here on are non-root parents with one kid (k_stage_fused pairs them) */
     double *d_schur;
     int *d_lvl_desc;
     int *d_leaf_desc; /* LeafDesc records (tdunes_stage.cuh) */
@@ -388,6 +389,12 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
             free(h);
             D->v.leaf_desc = D->d_leaf_desc;
             D->nleaf = nleaf;
+            {   /* deepest run of depths (>= 1) whose parents have one kid each */
+                const char *e4 = getenv("TREEQP_B200_NO_PAIR");
+                int l = d->Nh;
+                while (l - 1 >= 1 && D->lvl_md[l - 1] == 1) l--;
+                D->pair_begin = (ghost || (e4 && e4[0] == '1')) ? d->Np : D->lvl_ptr[l];
+            }
             D->fast_stage = 1;
             int dev = 0, sms = 148;
             cudaGetDevice(&dev);
@@ -413,14 +420,15 @@ static int launch_stage(tqb_device *D, int cls)
         if (nx == a && nu == b)                                                                        \
         {                                                                                              \
             constexpr int lpw = 32 / tqb_pow2_ge(a);                                                   \
-            const int warps = Np + (D->nleaf + lpw - 1) / lpw;                                         \
+            const int PB = (a + b <= 16 && a <= 8) ? D->pair_begin : Np;                                        \
+            const int warps = PB + (Np - PB + 1) / 2 + (D->nleaf + lpw - 1) / lpw;                     \
             const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;                \
             if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = cls; }    \
             static int per_sm = 0;                                                                     \
             if (per_sm == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stage_fused<a, b, MODE>, 32 * wpb, 0) != cudaSuccess) per_sm = 2; \
             const int res = D->stage_grid > 0 ? D->stage_grid : D->n_sm * per_sm;                      \
             const int full = (warps + wpb - 1) / wpb, grid = full < res ? full : res;                  \
-            k_stage_fused<a, b, MODE><<<grid, 32 * wpb, 0, D->stream>>>(v, Np, nroots, D->f_pnx, D->nleaf); \
+            k_stage_fused<a, b, MODE><<<grid, 32 * wpb, 0, D->stream>>>(v, Np, nroots, D->f_pnx, D->nleaf, PB); \
             if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);                             \
             D->launches++;                                                                             \
             return 0;                                                                                  \

@@ -26,6 +26,9 @@
 #include "tdunes_fused.cuh"
 
 #define TQB_STAGE_WPB 8       /* warps per CTA */
+#ifndef TQB_STAGE_MINBLOCKS
+#define TQB_STAGE_MINBLOCKS 4 /* resident CTAs per SM asked of the register allocator */
+#endif
 #define TQB_STAGE_MAXPAIR 64  /* max kids * (NX + NU) per parent */
 
 struct LeafDesc { int g, xo, tree, root; };
@@ -145,6 +148,117 @@ __device__ __forceinline__ void stage_parent(const View &v, const int4 d0, const
     __syncwarp(); /* sL / sS are reused by the warp's next item */
 }
 
+/* Two chain parents per warp (one kid each, NX + NU <= 16): lanes 0-15 work on one parent, lanes
+ * 16-31 on the next one.  A chain parent keeps only NX + NU of a warp's 32 lanes busy; pairing
+ * doubles the bytes a warp has in flight, which is what bounds this kernel.  d0,d1,d2 = the
+ * descriptor of THIS lane's parent (valid = it exists).  Same arithmetic as stage_parent with
+ * md = 1: the 16-lane butterfly performs the additions of the 32-lane one padded with zeros. */
+__device__ __forceinline__ double half_sum(double v)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+template <int NX, int NU, int MODE>
+__device__ __forceinline__ void stage_parent_pair(const View &v, const int4 d0, const int4 d1, const int4 d2, bool valid,
+                                                  double *sL, int lane)
+{
+    static_assert(NX + NU <= 16, "a chain parent must fit 16 lanes");
+    constexpr int ncol = NX + NU;
+    const double *src = (MODE == 2) ? v.dlam : v.lam;
+    const int sl = lane & 15, grp = lane >> 4;
+    const int g = d0.x, xo = d0.z, uo = d0.w, xb = d1.x;
+    const bool act = valid && v.status[d2.y] == TQB_RUNNING;
+    const bool own = valid && sl < ncol, isx = sl < NX;
+    const int i = isx ? sl : sl - NX;
+    double base = 0.0, winv = 0.0, lo = 0.0, hi = 0.0, rs = 0.0;
+    if (own)
+    {
+        if (isx)
+        {
+            const double l = src[xo + i];
+            if (MODE == 2) { base = l; rs = v.res[xo + i]; }
+            else
+            {
+                base = -v.in.q[xo + i] + l;
+                winv = v.in.Qinv[xo + i]; lo = v.in.xmin[xo + i]; hi = v.in.xmax[xo + i];
+            }
+        }
+        else if (MODE != 2)
+        {
+            base = -v.in.r[uo + i];
+            winv = v.in.Rinv[uo + i]; lo = v.in.umin[uo + i]; hi = v.in.umax[uo + i];
+        }
+    }
+    double cpart = 0.0, lkid = 0.0;
+    if (valid && sl < NX)
+    {
+        lkid = src[xb + sl];
+        if (MODE != 3) cpart = v.in.b[xb + sl] * lkid;
+    }
+    double cr[NX];
+#pragma unroll
+    for (int r = 0; r < NX; r++) cr[r] = 0.0;
+    if (own)
+    {
+        const double *col = isx ? v.in.A + d1.y + (size_t) sl * NX : v.in.B + d1.z + (size_t) (sl - NX) * NX;
+        if (NX % 2 == 0)
+        {
+            const double2 *c2 = reinterpret_cast<const double2 *>(col);
+#pragma unroll
+            for (int r = 0; r < NX / 2; r++) { const double2 t = __ldg(c2 + r); cr[2 * r] = t.x; cr[2 * r + 1] = t.y; }
+        }
+        else
+        {
+#pragma unroll
+            for (int r = 0; r < NX; r++) cr[r] = __ldg(col + r);
+        }
+    }
+    sL[lane] = lkid; /* lanes sl >= NX publish zeros that nobody reads */
+    __syncwarp();
+    if (MODE != 3)
+    {
+        const double c = half_sum(cpart);
+        if (sl == 0 && act) { if (MODE == 0) v.cmod0[g] = c; else v.dc[g] = c; }
+    }
+    const double *lk = sL + 16 * grp;
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < NX; r++) s += cr[r] * lk[r];
+    if (own && act)
+    {
+        double acc = base;
+        acc -= s;
+        if (MODE == 2)
+        {
+            if (isx) v.dq[xo + i] = acc; else v.dr[uo + i] = acc;
+        }
+        else
+        {
+            int mask;
+            const double unc = winv * acc;
+            const double val = clip_mask(unc, lo, hi, mask);
+            if (isx)
+            {
+                v.x[xo + i] = val;
+                if (MODE == 0) { v.qmod0[xo + i] = acc; v.xUnc[xo + i] = unc; v.P[xo + i] = mask == 0 ? winv : 0.0; }
+            }
+            else
+            {
+                v.u[uo + i] = val;
+                if (MODE == 0) { v.rmod0[uo + i] = acc; v.uUnc[uo + i] = unc; v.Rt[uo + i] = mask == 0 ? winv : 0.0; }
+            }
+        }
+    }
+    if (MODE == 2)
+    {
+        const double dotp = half_sum((own && isx) ? rs * base : 0.0);
+        if (sl == 0 && act) v.nvb[g] = dotp;
+    }
+    __syncwarp(); /* sL is reused by the warp's next item */
+}
+
 /* 32/NXP leaves: ld = this lane's LeafDesc (valid = the leaf exists) */
 template <int NX, int MODE>
 __device__ __forceinline__ void stage_leaves(const View &v, const int4 ld, bool valid, int i)
@@ -191,24 +305,32 @@ __device__ __forceinline__ void stage_leaves(const View &v, const int4 ld, bool 
  * items w, w + nwarps, ... and fetches the descriptor of its next item before it works on the
  * current one, so the descriptor -> data dependency costs one memory latency per warp, not per item. */
 template <int NX, int NU, int MODE>
-__global__ void __launch_bounds__(32 * TQB_STAGE_WPB) k_stage_fused(View v, int Np, int nroots, int root_nx, int nleaf)
+__global__ void __launch_bounds__(32 * TQB_STAGE_WPB, TQB_STAGE_MINBLOCKS) k_stage_fused(View v, int Np, int nroots, int root_nx, int nleaf, int pair_begin)
 {
+    /* items: [0, PB) single parents | NPR pairs of chain parents (descriptors PB + 2j, PB + 2j + 1) |
+     * groups of 32/NXP leaves */
     constexpr int NXP = tqb_pow2_ge(NX), LPW = 32 / NXP;
+    constexpr bool PAIR = NX + NU <= 16 && NX <= 8; /* larger NX: the second code path costs registers the binary-tree case needs */
     __shared__ double sLs[TQB_STAGE_WPB][32];
     __shared__ double sSs[TQB_STAGE_WPB][TQB_STAGE_MAXPAIR];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int nwarps = gridDim.x * TQB_STAGE_WPB, nitems = Np + (nleaf + LPW - 1) / LPW;
+    const int PB = PAIR ? pair_begin : Np, NPR = (Np - PB + 1) / 2, NPI = PB + NPR;
+    const int nwarps = gridDim.x * TQB_STAGE_WPB, nitems = NPI + (nleaf + LPW - 1) / LPW;
     const int slot = lane / NXP, li = lane - slot * NXP;
     int4 n0 = make_int4(0, 0, 0, 0), n1 = n0, n2 = n0;
     auto fetch = [&](int it) {
-        if (it < Np)
+        if (it < NPI)
         {
-            const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) it;
-            n0 = __ldg(dp); n1 = __ldg(dp + 1); n2 = __ldg(dp + 2);
+            const int e = it < PB ? it : PB + 2 * (it - PB) + (lane >> 4);
+            if (e < Np)
+            {
+                const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * (size_t) e;
+                n0 = __ldg(dp); n1 = __ldg(dp + 1); n2 = __ldg(dp + 2);
+            }
         }
         else if (it < nitems)
         {
-            const int lf = (it - Np) * LPW + slot;
+            const int lf = (it - NPI) * LPW + slot;
             if (lf < nleaf) n0 = __ldg(reinterpret_cast<const int4 *>(v.leaf_desc) + lf);
         }
     };
@@ -219,8 +341,12 @@ __global__ void __launch_bounds__(32 * TQB_STAGE_WPB) k_stage_fused(View v, int 
         const int4 d0 = n0, d1 = n1, d2 = n2;
         const int nxt = it + nwarps;
         fetch(nxt);
-        if (it < Np) stage_parent<NX, NU, MODE>(v, d0, d1, d2, it < nroots, root_nx, sLs[wib], sSs[wib], lane);
-        else stage_leaves<NX, MODE>(v, d0, (it - Np) * LPW + slot < nleaf, li);
+        if (it < PB) stage_parent<NX, NU, MODE>(v, d0, d1, d2, it < nroots, root_nx, sLs[wib], sSs[wib], lane);
+        else if (it < NPI)
+        {
+            if constexpr (PAIR) stage_parent_pair<NX, NU, MODE>(v, d0, d1, d2, PB + 2 * (it - PB) + (lane >> 4) < Np, sLs[wib], lane);
+        }
+        else stage_leaves<NX, MODE>(v, d0, (it - NPI) * LPW + slot < nleaf, li);
         it = nxt;
     }
 }
