@@ -225,6 +225,45 @@ static int launch_bs_chain(tqb_device *D, int top_begin, int cnt, int nlev)
     return 0;
 }
 
+template <int NX, int NU>
+static int launch_bf_chain2(tqb_device *D, int top_begin, int cnt, int nlev, int kp_bottom, int pre_ok)
+{
+    using Cfg = HalfCfg<NX, NU>;
+    const int wpb = 4, warps = (cnt + 1) / 2;
+    const size_t smem = (size_t) wpb * 2 * Cfg::SMEM * sizeof(double);
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
+    CK(launch_pdl(k_build_factor_chain2<NX, NU>, dim3((warps + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
+                  D->v, top_begin, cnt, nlev, kp_bottom, pre_ok));
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    return 0;
+}
+
+template <int NX>
+static int launch_bs_chain2(tqb_device *D, int top_begin, int cnt, int nlev)
+{
+    const int wpb = 4, warps = (cnt + 1) / 2;
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    CK(launch_pdl(k_backsolve_chain2<NX>, dim3((warps + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, top_begin, cnt, nlev));
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    return 0;
+}
+
+/* two chains per warp for blocks of dimension <= 8 (TREEQP_B200_NO_CHAIN2=1: one chain per warp) */
+static int g_chain2 = -1;
+static bool chain2_on()
+{
+    if (g_chain2 < 0)
+    {
+        const char *e = getenv("TREEQP_B200_NO_CHAIN2");
+        g_chain2 = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_chain2 == 1;
+}
+
 /* chain segment that has depth l as its deepest level: returns its top depth (== l: no segment) */
 static int chain_top(const tqb_device *D, int l)
 {
@@ -247,6 +286,12 @@ static int fused_factor_chain(tqb_device *D, int lt, int lb, int pre_ok)
 {
     const int begin = D->lvl_ptr[lt], cnt = D->lvl_ptr[lt + 1] - begin;
     const int nx = D->f_nx, nu = D->f_nu;
+    if (chain2_on())
+    {
+#define X(a, b) if (nx == a && nu == b) return launch_bf_chain2<a, b>(D, begin, cnt, lb - lt + 1, D->lvl_kp[lb], pre_ok);
+        X(4, 1) X(6, 4) X(8, 3)
+#undef X
+    }
 #define X(a, b) if (nx == a && nu == b) return launch_bf_chain<a, b>(D, begin, cnt, lb - lt + 1, D->lvl_kp[lb], pre_ok);
     X(4, 1) X(6, 4) X(8, 3) X(12, 4)
 #undef X
@@ -257,6 +302,12 @@ static int fused_backsolve_chain(tqb_device *D, int lt, int lb)
 {
     const int begin = D->lvl_ptr[lt], cnt = D->lvl_ptr[lt + 1] - begin;
     const int nx = D->f_nx;
+    if (chain2_on())
+    {
+#define X(a) if (nx == a) return launch_bs_chain2<a>(D, begin, cnt, lb - lt + 1);
+        X(4) X(6) X(8)
+#undef X
+    }
 #define X(a) if (nx == a) return launch_bs_chain<a>(D, begin, cnt, lb - lt + 1);
     X(4) X(6) X(8) X(12)
 #undef X

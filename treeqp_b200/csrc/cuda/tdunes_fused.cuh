@@ -518,6 +518,284 @@ __global__ void __launch_bounds__(128, tqb_bf_minblocks(NX)) k_build_factor_chai
     }
 }
 
+/* ---- chains of small blocks: TWO chains per warp ------------------------------------------------
+ * A chain block of dimension D = NX <= 8 has 2 NX <= 16 rows in its augmented matrix [W ; Ut]: half
+ * of a warp idles in bf_block and the chain kernel is bound by instruction issue.  Here lanes 0-15
+ * own the rows of chain 2w, lanes 16-31 those of chain 2w+1 (sub-lane sl = lane & 15, shuffles of
+ * width 16, one shared-memory region per half).  Same operations in the same order per block as
+ * bf_block<NX,NU,1,NX,false>; the build is the scalar fma chain, which the tensor-core build
+ * reproduces bit for bit (tools/micro/dmma_order.cu).  A half whose chain does not exist or has
+ * finished computes on zeros and stores nothing. */
+template <int NX, int NU>
+struct HalfCfg
+{
+    static constexpr int D = NX, NCOL = NX + NU, R = 2 * NX;
+    static constexpr int LDC = tqb_ld2(NCOL), LDR = tqb_ld2(R);
+    static constexpr int SM_M = D * LDR > D * LDC ? D * LDR : D * LDC;
+    static constexpr int SMEM = SM_M + 2 * (NCOL + 2) + 3 * D + 2; /* doubles per half-warp */
+};
+
+__device__ __forceinline__ double half_sum16(double v)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double half_max16(double v)
+{
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+template <int NX, int NU>
+__device__ __forceinline__ void bf_block_half(const View &v, size_t desc, bool valid, int kids_are_parents, bool wait_here, double *Ms, int lane)
+{
+    using Cfg = HalfCfg<NX, NU>;
+    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, LDC = Cfg::LDC, LDR = Cfg::LDR, PNX = NX;
+    static_assert(2 * NX <= 16 && (NX & 1) == 0, "two chains per warp need 2 NX <= 16, NX even");
+    const int sl = lane & 15;
+    int4 d0 = make_int4(0, 0, 0, 0), d1 = d0, d2 = d0;
+    bool act = false;
+    if (valid)
+    {
+        const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * desc;
+        d0 = __ldg(dp); d1 = __ldg(dp + 1); d2 = __ldg(dp + 2);
+        act = v.status[d2.y] == TQB_RUNNING;
+    }
+    if (!__any_sync(FULL, act))
+    {
+        if (wait_here) { pdl_wait(); pdl_release(); }
+        return;
+    }
+    const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
+    double *Cp = Ms;
+    double *ps = Ms + Cfg::SM_M, *zs = ps + NCOL + 2, *ys = zs + NCOL + 2, *dgs = ys + D, *invs = dgs + D;
+    const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
+    const bool isW = sl < D, isU = sl >= D && sl < 2 * D; /* Ut row sl - D */
+    const bool ldW = act && isW;
+
+    double wA[D];
+    double rr = 0.0;
+    bool small = false;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        /* the half that does not need the retry repeats its first attempt (same shift, same result) */
+        const double shift = (v.o.regType == 1 || (attempt == 1 && small)) ? v.o.regValue : 0.0;
+        double res = 0.0;
+        for (int c = sl; c < NCOL; c += 16)
+        {
+            ps[c] = act ? (c < PNX ? v.P[xo + c] : v.Rt[uo + c - PNX]) : 0.0;
+            zs[c] = act ? (c < PNX ? v.x[xo + c] : v.u[uo + c - PNX]) : 0.0;
+        }
+        double crow[NCOL];
+#pragma unroll
+        for (int c = 0; c < NCOL; c++)
+        {
+            double val = 0.0;
+            if (ldW) val = c < PNX ? Ag[sl + c * NX] : Bg[sl + (c - PNX) * NX];
+            crow[c] = val;
+        }
+        if (ldW) res = v.in.b[xb + sl] - v.x[xb + sl];
+        __syncwarp();
+        if (isW)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < NCOL; c++)
+            {
+                s += crow[c] * zs[c];
+                Cp[sl * LDC + c] = crow[c] * ps[c];
+            }
+            res += s;
+            if (act) v.res[xb + sl] = res;
+        }
+        if (attempt == 0)
+        {   /* contribution to the termination norm (calculate_error_in_residuals, :412-442) */
+            double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
+            part = (v.o.termCondition == 2) ? half_max16(part) : half_sum16(part);
+            if (sl == 0 && act) v.nva[g] = part;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int K = 0; K < D; K++)
+        {
+            double s = 0.0;
+            const double2 *cpk = reinterpret_cast<const double2 *>(Cp + K * LDC);
+#pragma unroll
+            for (int c2 = 0; c2 < NCOL / 2; c2++)
+            {
+                const double2 t2 = cpk[c2];
+                s += crow[2 * c2] * t2.x;
+                s += crow[2 * c2 + 1] * t2.y;
+            }
+            if (NCOL & 1) s += crow[NCOL - 1] * Cp[K * LDC + NCOL - 1];
+            wA[K] = s;
+        }
+        if (isW)
+        {
+            const double pk = act ? v.P[xb + sl] : 0.0;
+#pragma unroll
+            for (int K = 0; K < D; K++) wA[K] += (K == sl) ? pk + shift : 0.0;
+        }
+        /* ---- everything below needs the kids' level ---- */
+        if (attempt == 0 && wait_here) { pdl_wait(); pdl_release(); }
+        rr = res - ((kids_are_parents && ldW) ? v.rsub[xb + sl] : 0.0);
+        if (isW)
+        {
+            if (kids_are_parents && act)
+            {   /* minus the Schur complement of the kid (lower triangle) */
+                const double *Sk = v.schur + (size_t) k0 * NX * NX + sl * NX;
+#pragma unroll
+                for (int kk = 0; kk < NX; kk++) wA[kk] -= (kk <= sl) ? Sk[kk] : 0.0;
+            }
+        }
+        else if (isU)
+        {   /* Ut rows: M[D+c][K] = -P_p[c] * A[K][c] = -Cp[K][c] */
+#pragma unroll
+            for (int K = 0; K < D; K++) wA[K] = -Cp[K * LDC + (sl - D)];
+        }
+        small = false;
+        __syncwarp(); /* Cp is dead, Ms may be written */
+#pragma unroll
+        for (int j = 0; j < D; j++)
+        {
+            double piv = __shfl_sync(FULL, wA[j], j, 16), inv;
+            tqb_pivot(piv, inv);
+            small |= (piv <= v.o.regTol);
+            wA[j] *= inv;
+            const double yj = __shfl_sync(FULL, rr, j, 16) * inv;
+            rr = fma(-wA[j], yj, rr);
+            if (sl < 2 * D) Ms[j * LDR + sl] = wA[j];
+            ys[j] = yj; dgs[j] = piv; invs[j] = inv;
+            __syncwarp();
+            const double lj = wA[j];
+            const double *col = Ms + j * LDR;
+            if (j + 1 < D)
+            {
+                if ((j + 1) & 1) wA[j + 1] -= lj * col[j + 1];
+#pragma unroll
+                for (int k = (j + 2) & ~1; k < D; k += 2)
+                {
+                    const double2 l2 = *reinterpret_cast<const double2 *>(col + k);
+                    wA[k] -= lj * l2.x;
+                    wA[k + 1] -= lj * l2.y;
+                }
+            }
+        }
+        small = small && act;
+        if (!(v.o.regType == 2 && attempt == 0 && __any_sync(FULL, small))) break;
+        if (sl == 0 && small) atomicAdd(&v.counters[2], 1);
+        __syncwarp();
+    }
+
+    /* ---- results to HBM ---- */
+    if (ldW)
+    {
+        double *Lp = v.W + d1.w + (sl * (sl + 1)) / 2;
+#pragma unroll
+        for (int t = 0; t < D; t++)
+            if (t < sl) Lp[t] = wA[t];
+        Lp[sl] = dgs[sl];
+        v.Linv[xb + sl] = invs[sl];
+        v.dlam[xb + sl] = ys[sl];
+    }
+    if (isU && act)
+    {
+        double2 *dst = reinterpret_cast<double2 *>(v.Ut + d2.x + (sl - D) * D);
+#pragma unroll
+        for (int t = 0; t < D / 2; t++) dst[t] = make_double2(wA[2 * t], wA[2 * t + 1]);
+    }
+    /* Schur complement for the parent's block: S = Utilde Utilde' (lower), s = Utilde y */
+    double *Sg = v.schur + (size_t) g * NX * NX;
+    constexpr int NE = (NX / 2) * (NX + 1);
+    for (int e = sl; e < NE; e += 16)
+    {
+        const int p = e / (NX + 1), q = e - p * (NX + 1);
+        const int a = q <= p ? p : NX - 1 - p;
+        const int b = q <= p ? q : q - p - 1;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) s += Ms[j * LDR + D + a] * Ms[j * LDR + D + b];
+        if (act) Sg[a * NX + b] = s;
+    }
+    if (sl < NX)
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) s += Ms[j * LDR + D + sl] * ys[j];
+        if (act) v.rsub[xo + sl] = s;
+    }
+}
+
+template <int NX, int NU>
+__global__ void __launch_bounds__(128, 6) k_build_factor_chain2(View v, int top_begin, int count, int nlev, int bottom_kids_are_parents, int pre_ok)
+{
+    using Cfg = HalfCfg<NX, NU>;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (!pre_ok) { pdl_wait(); pdl_release(); }
+    if (2 * w >= count) { pdl_wait(); pdl_release(); return; }
+    const int chain = 2 * w + (lane >> 4);
+    double *Ms = smem + (size_t) (2 * wib + (lane >> 4)) * Cfg::SMEM;
+#pragma unroll 1
+    for (int l = nlev - 1; l >= 0; l--)
+    {
+        const bool first = l == nlev - 1;
+        bf_block_half<NX, NU>(v, (size_t) top_begin + (size_t) l * count + chain, chain < count, first ? bottom_kids_are_parents : 1, first, Ms, lane);
+        __syncwarp();
+    }
+}
+
+/* substitution along two chains per warp (see k_backsolve_chain) */
+template <int NX>
+__global__ void __launch_bounds__(128) k_backsolve_chain2(View v, int top_begin, int count, int nlev)
+{
+    constexpr int D = NX;
+    const int lane = threadIdx.x & 31, sl = lane & 15;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (2 * w >= count) { pdl_wait(); pdl_release(); return; }
+    const int chain = 2 * w + (lane >> 4);
+    const bool valid = chain < count;
+#pragma unroll 1
+    for (int l = 0; l < nlev; l++)
+    {
+        int4 d0 = make_int4(0, 0, 0, 0), d1 = d0, d2 = d0;
+        if (valid)
+        {
+            const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * ((size_t) top_begin + (size_t) l * count + chain);
+            d0 = __ldg(dp); d1 = __ldg(dp + 1); d2 = __ldg(dp + 2);
+        }
+        const int xb = d1.x, xo = d0.z;
+        const double *Lp = v.W + d1.w, *Up = v.Ut + d2.x;
+        const bool ld = valid && sl < D;
+        double lcol[D], ucol[NX];
+#pragma unroll
+        for (int i = 0; i < D; i++) lcol[i] = (ld && sl <= i) ? Lp[(i * (i + 1)) / 2 + sl] : 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; c++) ucol[c] = ld ? Up[c * D + sl] : 0.0;
+        double y = ld ? v.dlam[xb + sl] : 0.0;
+        const double inv = ld ? v.Linv[xb + sl] : 0.0;
+        if (l == 0) { pdl_wait(); pdl_release(); }
+        const bool act = ld && v.status[d2.y] == TQB_RUNNING;
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; c++) s += ucol[c] * (ld ? v.dlam[xo + c] : 0.0);
+        y -= s;
+#pragma unroll
+        for (int i = D - 1; i >= 0; i--)
+        {
+            const double yi = __shfl_sync(FULL, y, i, 16) * __shfl_sync(FULL, inv, i, 16);
+            if (sl == i) y = yi;
+            else if (sl < i) y -= lcol[i] * yi;
+        }
+        if (act) v.dlam[xb + sl] = y;
+        __syncwarp();
+    }
+}
+
 /* one block of the root-to-leaves substitution; `wait_here` as in bf_block */
 template <int NX, int MD>
 __device__ __forceinline__ void bs_block(const View &v, size_t desc, bool wait_here, int lane)
