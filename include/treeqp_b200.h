@@ -461,6 +461,12 @@ void tree_qp_in_set_node_bounds(const double *const xmin, const double *const xm
                                 const double *const umin, const double *const umax,
                                 tree_qp_in *const qp_in, const int indx);
 void tree_qp_in_set_inf_bounds(tree_qp_in *qp_in);
+/* initial state: pinned through the root's bounds, or eliminated (nx[0] becomes 0; only b of the
+ * root's children, r[0], dmin/dmax[0] depend on x0)          tree_qp_common.h:167-169, 314-316 */
+void tree_qp_in_eliminate_x0(tree_qp_in *const qp_in);
+void tree_qp_out_eliminate_x0(tree_qp_out *const qp_out);
+void tree_qp_in_set_x0_strvec(tree_qp_in *qp_in, struct blasfeo_dvec *sx0);
+void tree_qp_in_set_x0_colmaj(tree_qp_in *qp_in, double *x0);
 /* concatenated per-edge / per-node data, tree_qp_common.c:1959-2100 */
 void tree_qp_in_set_ltv_dynamics_colmajor(double *A, double *B, double *b, tree_qp_in *qp_in);
 void tree_qp_in_set_ltv_objective_diag(double *Qd, double *Rd, double *q, double *r,
@@ -517,6 +523,14 @@ return_t treeqp_tdunes_upload(const tree_qp_in *qp_in, const treeqp_tdunes_opts_
 return_t treeqp_tdunes_solve_resident(const treeqp_tdunes_opts_t *opts,
                                       treeqp_tdunes_workspace *work);
 return_t treeqp_tdunes_download(tree_qp_out *qp_out, treeqp_tdunes_workspace *work);
+/* MPC re-solve fast path (benchmark/treeqp_main.m:235-237: between consecutive QPs of a closed loop
+ * only x0 changes).  After tree_qp_in_set_x0_colmaj/strvec on an uploaded QP, update_x0 re-sends only
+ * what depends on x0 -- the root and its children, a few hundred bytes -- instead of the whole
+ * problem; warm_start_resident makes the multipliers of the last solve, still in HBM, the dual
+ * start of the next one (what treeqp_tdunes_set_dual_initialization(lambda_prev) would do through
+ * the host). */
+return_t treeqp_tdunes_update_x0(const tree_qp_in *qp_in, treeqp_tdunes_workspace *work);
+return_t treeqp_tdunes_warm_start_resident(treeqp_tdunes_workspace *work);
 
 /* Batch of n independent tree QPs solved as one forest: every kernel launch covers the same
  * tree level of all QPs.  All QPs share `opts` (qp_solver is read from opts for the first Nn

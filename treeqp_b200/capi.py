@@ -223,6 +223,12 @@ class TreeQpLib:
         L.treeqp_sdunes_set_dual_initialization.restype = None
         L.treeqp_sdunes_solve.argtypes = [vp, vp, C.POINTER(SdunesOpts), vp]
         L.treeqp_sdunes_solve.restype = C.c_int
+        L.tree_qp_in_eliminate_x0.argtypes = [vp]
+        L.tree_qp_in_eliminate_x0.restype = None
+        L.tree_qp_out_eliminate_x0.argtypes = [vp]
+        L.tree_qp_out_eliminate_x0.restype = None
+        L.tree_qp_in_set_x0_colmaj.argtypes = [vp, c_double_p]
+        L.tree_qp_in_set_x0_colmaj.restype = None
         L.setup_multistage_tree.argtypes = [C.c_int, C.c_int, C.c_int, c_int_p]
         L.setup_multistage_tree.restype = None
         L.calculate_number_of_nodes.argtypes = [C.c_int, C.c_int, C.c_int]
@@ -232,6 +238,10 @@ class TreeQpLib:
             L.treeqp_b200_device_count.restype = C.c_int
             L.treeqp_b200_set_device.argtypes = [C.c_int]
             L.treeqp_b200_set_device.restype = C.c_int
+            L.treeqp_tdunes_update_x0.argtypes = [vp, vp]
+            L.treeqp_tdunes_update_x0.restype = C.c_int
+            L.treeqp_tdunes_warm_start_resident.argtypes = [vp]
+            L.treeqp_tdunes_warm_start_resident.restype = C.c_int
             L.treeqp_b200_set_profiling.argtypes = [C.c_int]
             L.treeqp_b200_set_profiling.restype = None
             L.treeqp_b200_num_kernel_classes.restype = C.c_int
@@ -376,6 +386,16 @@ class QpIn:
         L.tree_qp_in_set_ltv_bounds(_dp(xmin), _dp(xmax), _dp(umin), _dp(umax), self.ptr)
 
 
+    def eliminate_x0(self):
+        """tree_qp_in_eliminate_x0 (tree_qp_common.c:404): the pinned root state leaves the QP"""
+        self.lib.lib.tree_qp_in_eliminate_x0(self.ptr)
+
+    def set_x0(self, x0):
+        """tree_qp_in_set_x0_colmaj (tree_qp_common.c:2229): works on pinned and eliminated roots"""
+        x0 = _f64(x0)
+        self.lib.lib.tree_qp_in_set_x0_colmaj(self.ptr, _dp(x0))
+
+
 class QpOut:
     """tree_qp_out plus vectorised readers of its BLASFEO vector views."""
 
@@ -480,6 +500,14 @@ class Tdunes:
 
     def download(self, qp_out: QpOut) -> int:
         return int(self.lib.lib.treeqp_tdunes_download(qp_out.ptr, self.work.ptr))
+
+    def update_x0(self) -> int:
+        """after qp_in.set_x0(...): re-send only the root and its children"""
+        return int(self.lib.lib.treeqp_tdunes_update_x0(self.qp_in.ptr, self.work.ptr))
+
+    def warm_start_resident(self) -> int:
+        """dual start of the next solve = multipliers of the last one, without leaving HBM"""
+        return int(self.lib.lib.treeqp_tdunes_warm_start_resident(self.work.ptr))
 
     def stats(self) -> dict:
         st = Stats()

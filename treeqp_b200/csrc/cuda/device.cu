@@ -641,6 +641,13 @@ extern "C" int tqb_device_upload_end(tqb_device *D, double *ms_total)
     return 0;
 }
 
+/* the multipliers of the last solve (still in HBM) become the dual start of the next one */
+extern "C" int tqb_device_warm_start(tqb_device *D, long long lam0_off, long long n)
+{
+    CK(cudaMemcpyAsync(D->d_in + lam0_off, D->v.lam, sizeof(double) * (size_t) n, cudaMemcpyDeviceToDevice, D->stream));
+    return 0;
+}
+
 extern "C" int tqb_device_upload(tqb_device *D, const double *h_in, long long n_in, double *ms)
 {
     CK(cudaEventRecord(D->ev0, D->stream));

@@ -416,6 +416,116 @@ void tree_qp_in_set_node_objective_colmajor(const double *const Q, const double 
     }
 }
 
+/* ---- initial state: pinned on the root or eliminated (tree_qp_common.c:404-536, 2154-2235) ---- */
+
+/* y = y0 + sign * M x  (blasfeo_dgemv_n of the reference, plain loops) */
+static void gemv_n_add(const struct blasfeo_dmat *M, int n, double sign, const double *x, const double *y0, double *y)
+{
+    for (int i = 0; i < M->m; i++)
+    {
+        double acc = y0[i];
+        for (int j = 0; j < n; j++) acc += sign * BLASFEO_DMATEL(M, i, j) * x[j];
+        y[i] = acc;
+    }
+}
+
+/* nx[0] > 0: x0 is pinned through the root's bounds.  nx[0] == 0 (x0 eliminated): only b of the
+ * root's children, r[0] and dmin/dmax[0] depend on x0 and are rebuilt from the kept copies
+ * (tree_qp_common.c:2154-2227) */
+void tree_qp_in_set_x0_strvec(tree_qp_in *qp, struct blasfeo_dvec *sx0)
+{
+    qp_internal_t *im = &qp->internal_memory;
+    if (qp->nx[0] > 0)
+    {
+        assert(qp->xmin[0].m == sx0->m && qp->xmax[0].m == sx0->m);
+        memcpy(qp->xmin[0].pa, sx0->pa, sizeof(double) * (size_t) sx0->m);
+        memcpy(qp->xmax[0].pa, sx0->pa, sizeof(double) * (size_t) sx0->m);
+        return;
+    }
+    const int nx0 = sx0->m, nc0 = im->C0.m, nu0 = im->S0.m;
+    assert(im->x0.m == nx0 && qp->nu[0] == nu0 && qp->nc[0] == nc0);
+    if (im->x0.pa != sx0->pa) memcpy(im->x0.pa, sx0->pa, sizeof(double) * (size_t) nx0);
+    for (int ii = 1; ii <= qp->tree[0].nkids; ii++)
+    {
+        assert(im->is_A_initialized[ii - 1] == 1 && im->is_b_initialized[ii - 1] == 1);
+        gemv_n_add(&im->A0[ii - 1], nx0, 1.0, sx0->pa, im->b0[ii - 1].pa, qp->b[ii - 1].pa);
+    }
+    if (nc0 > 0)
+    {
+        assert(im->is_C_initialized == 1);
+        gemv_n_add(&im->C0, nx0, -1.0, sx0->pa, im->dmin0.pa, qp->dmin[0].pa);
+        gemv_n_add(&im->C0, nx0, -1.0, sx0->pa, im->dmax0.pa, qp->dmax[0].pa);
+    }
+    assert(im->is_S_initialized == 1 && im->is_r_initialized == 1);
+    gemv_n_add(&im->S0, nx0, 1.0, sx0->pa, im->r0.pa, qp->r[0].pa);
+}
+
+void tree_qp_in_set_x0_colmaj(tree_qp_in *qp, double *x0)
+{
+    struct blasfeo_dvec *sx0 = &qp->internal_memory.x0;
+    memcpy(sx0->pa, x0, sizeof(double) * (size_t) sx0->m);
+    tree_qp_in_set_x0_strvec(qp, sx0);
+}
+
+/* removes the root's state from the QP: the pinned value xmin[0] (= xmax[0]) goes into b of the
+ * root's children, r[0] and dmin/dmax[0]; copies of A, b, S, r, C, dmin, dmax of the root are kept
+ * so that x0 can be changed afterwards (tree_qp_common.c:404-525) */
+void tree_qp_in_eliminate_x0(tree_qp_in *const qp)
+{
+    const int nx0 = qp->nx[0], nc0 = qp->nc[0];
+    if (nx0 == 0) return;
+    qp_internal_t *im = &qp->internal_memory;
+    if (im->is_C_initialized == 0 && nc0 > 0)
+    {
+        dmat_copy(&qp->C[0], &im->C0);
+        im->is_C_initialized = 1;
+    }
+    if (im->is_dmin_initialized == 0 && nc0 > 0) memcpy(im->dmin0.pa, qp->dmin[0].pa, sizeof(double) * (size_t) nc0);
+    if (im->is_dmax_initialized == 0 && nc0 > 0) memcpy(im->dmax0.pa, qp->dmax[0].pa, sizeof(double) * (size_t) nc0);
+    qp->C[0].pA = NULL;
+    qp->C[0].n = 0;
+    if (im->is_S_initialized == 0)
+    {
+        dmat_copy(&qp->S[0], &im->S0);
+        im->is_S_initialized = 1;
+    }
+    if (im->is_r_initialized == 0)
+    {
+        memcpy(im->r0.pa, qp->r[0].pa, sizeof(double) * (size_t) qp->nu[0]);
+        im->is_r_initialized = 1;
+    }
+    qp->S[0].pA = NULL;
+    qp->S[0].n = 0;
+    for (int ii = 0; ii < qp->tree[0].nkids; ii++)
+    {
+        if (im->is_A_initialized[ii] == 0)
+        {
+            dmat_copy(&qp->A[ii], &im->A0[ii]);
+            im->is_A_initialized[ii] = 1;
+        }
+        if (im->is_b_initialized[ii] == 0)
+        {
+            memcpy(im->b0[ii].pa, qp->b[ii].pa, sizeof(double) * (size_t) qp->b[ii].m);
+            im->is_b_initialized[ii] = 1;
+        }
+        qp->A[ii].n = 0;
+        qp->A[ii].pA = NULL;
+    }
+    for (int i = 0; i < nx0; i++) assert(fabs(qp->xmin[0].pa[i] - qp->xmax[0].pa[i]) < 1e-10);
+    qp->nx[0] = 0;
+    tree_qp_in_set_x0_strvec(qp, &qp->xmin[0]);
+    qp->Q[0].pA = NULL; qp->Q[0].m = 0; qp->Q[0].n = 0;
+    qp->q[0].pa = NULL; qp->q[0].m = 0;
+    qp->xmin[0].pa = NULL; qp->xmin[0].m = 0;
+    qp->xmax[0].pa = NULL; qp->xmax[0].m = 0;
+}
+
+void tree_qp_out_eliminate_x0(tree_qp_out *const qp_out)
+{
+    qp_out->x[0].pa = NULL; qp_out->x[0].m = 0;
+    qp_out->mu_x[0].pa = NULL; qp_out->mu_x[0].m = 0;
+}
+
 /* diagonal weights; the cross term is zeroed (tree_qp_common.c:1377-1430) */
 void tree_qp_in_set_node_objective_diag(const double *const Qd, const double *const Rd,
                                         const double *const q, const double *const r,

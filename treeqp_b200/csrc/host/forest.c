@@ -422,6 +422,29 @@ static int upload_nodes(tqb_forest *f, int ga, int gb)
     return rc;
 }
 
+int tqb_forest_update_nodes(tqb_forest *f, int t, const tree_qp_in *qp, int j0, int j1)
+{
+    const int g0 = f->ht.tnode0[t];
+    pack_range(f, t, qp, NULL, j0, j1);
+    int rc = tqb_device_upload_begin(f->dev);
+    rc |= upload_nodes(f, g0 + j0, g0 + j1);
+    rc |= tqb_device_upload_end(f->dev, &f->h2d_ms);
+    return rc;
+}
+
+int tqb_forest_upload_lambda0(tqb_forest *f)
+{
+    int rc = tqb_device_upload_begin(f->dev);
+    rc |= tqb_device_upload_range(f->dev, f->h_in, f->hin.lam0 - f->h_in, f->dims.X);
+    rc |= tqb_device_upload_end(f->dev, &f->h2d_ms);
+    return rc;
+}
+
+int tqb_forest_warm_start(tqb_forest *f)
+{
+    return tqb_device_warm_start(f->dev, f->hin.lam0 - f->h_in, f->dims.X);
+}
+
 #ifndef TQB_UPLOAD_CHUNK_DOUBLES
 #define TQB_UPLOAD_CHUNK_DOUBLES (3LL << 20) /* 24 MB of input per pipeline stage */
 #endif

@@ -121,6 +121,10 @@ void tqb_forest_pack(tqb_forest *f, int t, const struct tree_qp_in_ *qp);
 /* pack + H2D as a pipeline over node ranges (single tree) or tree ranges (batch); tail_ms = the
  * wait after the last range was packed.  Returns 0 on success. */
 int tqb_forest_pack_upload(tqb_forest *f, const struct tree_qp_in_ *const *qp, double *tail_ms);
+/* re-pack and re-send nodes [j0, j1) of tree t only (what an x0 update touches) / the dual start only */
+int tqb_forest_update_nodes(tqb_forest *f, int t, const struct tree_qp_in_ *qp, int j0, int j1);
+int tqb_forest_upload_lambda0(tqb_forest *f);
+int tqb_forest_warm_start(tqb_forest *f);
 void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda);
 void tqb_forest_unpack(const tqb_forest *f, int t, struct tree_qp_out_ *out);
 void tqb_layout_tables(const tqb_dims *d, int *base, tqb_tables *t);
@@ -141,6 +145,7 @@ int tqb_device_upload(tqb_device *d, const double *h_in, long long n_in, double 
 int tqb_device_upload_begin(tqb_device *d);
 int tqb_device_upload_range(tqb_device *d, const double *h_in, long long off, long long n);
 int tqb_device_upload_end(tqb_device *d, double *ms_total);
+int tqb_device_warm_start(tqb_device *d, long long lam0_off, long long n);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
 int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,
                      int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms, long long *launches,

@@ -298,8 +298,9 @@ return_t treeqp_tdunes_solve_resident(const treeqp_tdunes_opts_t *opts, treeqp_t
     if (st != TREEQP_OK) return st;
     tqb_forest *f = ctx->forest;
     if (ctx->lam_dirty)
-    {   /* lambda0 is the tail of the input block: re-send the block (rare on this path) */
-        if (forest_upload(f) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    {   /* a new dual start was set on the host: send that vector only */
+        if (tqb_forest_upload_lambda0(f)) return TREEQP_UNKNOWN_ERROR;
+        f->h2d_bytes = (long long) sizeof(double) * f->dims.X;
         ctx->lam_dirty = 0;
     }
     tqb_opts o;
@@ -310,6 +311,33 @@ return_t treeqp_tdunes_solve_resident(const treeqp_tdunes_opts_t *opts, treeqp_t
     int it = f->h_iter[0];
     work->lsIter = (it > 0 && it <= 256) ? f->ls_iters[it - 1] : 0;
     return ctx->last_status;
+}
+
+/* only b of the root's children, r[0] and the root's bounds depend on x0 (tree_qp_common.c:2154-2227):
+ * re-pack and re-send the root and its children */
+return_t treeqp_tdunes_update_x0(const tree_qp_in *qp_in, treeqp_tdunes_workspace *work)
+{
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest || !ctx->uploaded) return TREEQP_UNKNOWN_ERROR;
+    tqb_forest *f = ctx->forest;
+    const int n = 1 + qp_in->tree[0].nkids;
+    double t0 = tqb_wall_ms();
+    if (tqb_forest_update_nodes(f, 0, qp_in, 0, n)) return TREEQP_UNKNOWN_ERROR;
+    f->pack_ms = tqb_wall_ms() - t0;
+    const int last = n >= f->dims.Nn;
+    const long long x1 = last ? f->dims.X : f->ht.xoff[n], u1 = last ? f->dims.U : f->ht.uoff[n];
+    const long long a1 = last ? f->dims.szA : f->ht.aoff[n], b1 = last ? f->dims.szB : f->ht.boff[n];
+    f->h2d_bytes = (long long) sizeof(double) * (a1 + b1 + 7 * x1 + 5 * u1);
+    return TREEQP_OK;
+}
+
+return_t treeqp_tdunes_warm_start_resident(treeqp_tdunes_workspace *work)
+{
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest || !ctx->uploaded) return TREEQP_UNKNOWN_ERROR;
+    if (tqb_forest_warm_start(ctx->forest)) return TREEQP_UNKNOWN_ERROR;
+    ctx->lam_dirty = 0;
+    return TREEQP_OK;
 }
 
 return_t treeqp_tdunes_download(tree_qp_out *qp_out, treeqp_tdunes_workspace *work)
