@@ -65,6 +65,24 @@ def _ubox(prob, ub, xb=None):
 
 _X0B = [0.3, 0.5, -0.4, 0.2]
 
+# the reference's OWN golden vectors for the dense TDUNES path (examples/random_qp_utils/data0N.c,
+# checked by examples/random_qp.c:196-254); fixtures made by tests/golden/make_random_qp_fixtures.py
+REF_RANDOM_QP = ["%02d" % n for n in range(6)]
+REF_RANDOM_QP_OPTS = dict(qp_solver=1, maxIter=10, stationarityTolerance=1e-10, regType=0)  # random_qp.c:131-140
+
+
+def ref_random_qp(n):
+    """(problem, xopt, uopt) of examples/random_qp_utils/data<n>.c: dense Q/R/S, infinite bounds
+    (tree_qp_in_set_inf_bounds, +-TREEQP_INF = 1e12), irregular nx/nu"""
+    from treeqp_b200.capi import Problem
+    d = np.load(os.path.join(GOLDEN, "refdata_random_qp_%s.npz" % n))
+    X, U = int(d["nx"].sum()), int(d["nu"].sum())
+    prob = Problem(nk=d["nk"].astype(np.int32), nx=d["nx"].astype(np.int32), nu=d["nu"].astype(np.int32),
+                   A=d["A"], B=d["B"], b=d["b"], q=d["q"], r=d["r"], Q=d["Q"], R=d["R"], S=d["S"],
+                   xmin=np.full(X, -1e12), xmax=np.full(X, 1e12), umin=np.full(U, -1e12), umax=np.full(U, 1e12),
+                   meta=dict(source="examples/random_qp_utils/data%s.c" % n))
+    return prob, d["xopt"], d["uopt"]
+
 
 def sdunes_cases():
     """SDUNES parity cases (x0 eliminated).  The reference's SDUNES does not converge once state

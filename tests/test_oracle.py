@@ -130,3 +130,27 @@ def test_dense_port_matches_live_reference(name, ref_lib):
     assert (s["status"], s["iter"]) == (r.status, r.iter)
     for k in ("x", "u", "lam", "mu_x", "mu_u"):
         assert CS.rel_err(s[k], getattr(r, k)) < 1e-10, k
+
+
+# --------------------------------------- the reference's own golden vectors (examples/random_qp.c)
+def _max_abs(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)))) if len(a) else 0.0
+
+
+@pytest.mark.parametrize("n", CS.REF_RANDOM_QP)
+def test_port_reproduces_reference_random_qp_goldens(n):
+    """examples/random_qp.c:196-254: max |x - xopt|, |u - uopt| < 1e-12, KKT < 1e-12, status 0, with
+    the options of :131-140 (dense stage QPs, maxIter 10, tolerance 1e-10, no regularisation)"""
+    prob, xopt, uopt = CS.ref_random_qp(n)
+    s = OP.solve_port(prob, **CS.port_opts(CS.REF_RANDOM_QP_OPTS))
+    assert s["status"] == 0 and s["iter"] <= 1
+    assert _max_abs(s["x"], xopt) < 1e-12 and _max_abs(s["u"], uopt) < 1e-12
+
+
+@pytest.mark.parametrize("n", CS.REF_RANDOM_QP)
+def test_live_reference_reproduces_its_random_qp_goldens(n, ref_lib):
+    """the compiled reference through our ctypes driver: proves the fixture + driver path"""
+    prob, xopt, uopt = CS.ref_random_qp(n)
+    r = capi.solve_tdunes(ref_lib, prob, **CS.REF_RANDOM_QP_OPTS)
+    assert r.status == 0 and r.kkt < 1e-12
+    assert _max_abs(r.x, xopt) < 1e-12 and _max_abs(r.u, uopt) < 1e-12

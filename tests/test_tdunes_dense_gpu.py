@@ -88,3 +88,14 @@ def test_dense_batch(product_lib):
         assert o.iter == s.iter
         assert np.array_equal(o.x, s.x) and np.array_equal(o.lam, s.lam)
     batch.destroy()
+
+
+@pytest.mark.parametrize("n", CS.REF_RANDOM_QP)
+def test_reference_random_qp_goldens(n, product_lib):
+    """the reference's OWN test vectors for this path (examples/random_qp_utils/data0N.c) with its own
+    acceptance bar (examples/random_qp.c:196-254): |x - xopt|, |u - uopt| < 1e-12, KKT < 1e-12"""
+    prob, xopt, uopt = CS.ref_random_qp(n)
+    sol = capi.solve_tdunes(product_lib, prob, **CS.REF_RANDOM_QP_OPTS)
+    assert sol.status == 0 and sol.iter <= 1
+    assert sol.kkt < 1e-12
+    assert float(np.max(np.abs(sol.x - xopt))) < 1e-12 and float(np.max(np.abs(sol.u - uopt))) < 1e-12
