@@ -66,6 +66,7 @@ struct SdView
     int per_warp;                     /* doubles of shared-memory scratch per warp */
     double *jarena;                   /* operands of the J chain when they do not fit in shared memory */
     int jay_in_smem;
+    int no_small_jay;                 /* TREEQP_B200_GENERIC_JAY=1: always the generic chain walk */
 };
 
 struct Team
@@ -674,6 +675,188 @@ __device__ void sd_jay_chain(const SdView &v, const JayArena &A, int lane)
     }
 }
 
+/* The same chain for small blocks (every block dimension <= DM, DM = 4 or 8), entirely in
+ * registers: lane l owns ROW l of the current diagonal block, of the coupling block to the next
+ * scenario pair and of the carried Schur complement; rows of other lanes arrive by shuffle.  No
+ * shared-memory round trips or warp barriers inside a step (the generic walk above spends ~4500
+ * cycles per step on them for 4 x 4 blocks).  Operation order per entry is that of sd_jay_chain
+ * (left-looking Cholesky of warp_potrf32, dtrsv/dtrsm with the stored inverse diagonal). */
+template <int DM>
+__device__ void sd_jay_chain_small(const SdView &v, const JayArena &A, int lane)
+{
+    const int nu = v.d.nu, Ns = v.d.Ns;
+    const int regType = v.o.regType;
+    const double regTol = v.o.regTol, regValue = v.o.regValue;
+    const int l = lane < DM ? lane : DM - 1; /* idle lanes mirror the last row and store nothing */
+    const bool mine = lane < DM;
+    int nreg = 0;
+    double car[DM], scv = 0.0;
+#pragma unroll
+    for (int c = 0; c < DM; c++) car[c] = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < Ns - 1; i++)
+    {
+        const int dim = nu * A.cn[i], lo = A.lo[i];
+        double *W = A.JD0 + A.jdo[i];
+        const double *W1 = A.JD1 + A.jdo[i];
+        const bool row = mine && l < dim;
+        double w[DM], w0[DM], inv[DM];
+#pragma unroll
+        for (int c = 0; c < DM; c++)
+        {
+            double val = 0.0;
+            if (row && c < dim)
+            {
+                val = (i > 0 && l >= c) ? car[c] : 0.0;
+                val += W[l + c * dim];
+                val += W1[l + c * dim];
+                if (regType == 1 && c == l) val += regValue;
+            }
+            w[c] = w0[c] = val;
+            inv[c] = 0.0;
+        }
+        double y = 0.0;
+        if (row)
+        {
+            double rhs = A.rhs[lo + l];
+            if (i > 0) rhs = rhs + scv;
+            y = -1.0 * rhs;
+        }
+#pragma unroll 1
+        for (int attempt = 0; attempt < 2; attempt++)
+        {
+            bool small = false;
+#pragma unroll
+            for (int j = 0; j < DM; j++)
+            {
+                if (j < dim)
+                {   /* column j: s = W[l][j] - sum_{t<j} L[l][t] L[j][t], t ascending */
+                    double sacc = w[j];
+#pragma unroll
+                    for (int t = 0; t < j; t++) sacc -= w[t] * __shfl_sync(FULL, w[t], j);
+                    double piv = __shfl_sync(FULL, sacc, j), pinv;
+                    tqb_pivot(piv, pinv);
+                    if (l == j) w[j] = piv;
+                    else if (l > j) w[j] = sacc * pinv;
+                    inv[j] = pinv;
+                    small |= (piv <= regTol);
+                }
+            }
+            if (!(regType == 2 && attempt == 0 && small)) { nreg += (regType == 1 || attempt == 1); break; }
+#pragma unroll
+            for (int c = 0; c < DM; c++) w[c] = w0[c] + ((c == l && row) ? regValue : 0.0);
+        }
+        /* y <- L^-1 y (dtrsv_lnn) */
+#pragma unroll
+        for (int j = 0; j < DM; j++)
+            if (j < dim)
+            {
+                const double yj = __shfl_sync(FULL, y, j) * inv[j];
+                if (l == j) y = yj;
+                else if (l > j && l < dim) y -= w[j] * yj;
+            }
+        if (row)
+        {
+            A.rhs[lo + l] = y;
+#pragma unroll
+            for (int c = 0; c < DM; c++)
+                if (c < dim && c <= l) W[l + c * dim] = w[c];
+        }
+        if (mine)
+        {
+#pragma unroll
+            for (int c = 0; c < DM; c++)
+                if (c < dim && c == l) A.inv[lo + c] = inv[c];
+        }
+        if (i < Ns - 2)
+        {
+            const int dimN = nu * A.cn[i + 1];
+            double *JL = A.JL + A.jlo[i];
+            const bool rowN = mine && l < dimN;
+            double jl[DM];
+#pragma unroll
+            for (int c = 0; c < DM; c++) jl[c] = (rowN && c < dim) ? JL[l + c * dimN] : 0.0;
+            /* JL <- JL L^-T (dtrsm_rltn): row l, column by column */
+#pragma unroll
+            for (int j = 0; j < DM; j++)
+                if (j < dim)
+                {
+                    double t = jl[j];
+#pragma unroll
+                    for (int c = 0; c < j; c++) t -= jl[c] * __shfl_sync(FULL, w[c], j);
+                    jl[j] = t * inv[j];
+                    if (rowN) JL[l + j * dimN] = jl[j];
+                }
+            /* carried Schur complement (lower) and right-hand side for the next pair */
+#pragma unroll
+            for (int b = 0; b < DM; b++)
+            {
+                double t = 0.0;
+#pragma unroll
+                for (int c = 0; c < DM; c++)
+                {
+                    const double o = __shfl_sync(FULL, jl[c], b);
+                    if (c < dim) t += jl[c] * o;
+                }
+                car[b] = 0.0 - t;
+            }
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < DM; c++)
+            {
+                const double yc = __shfl_sync(FULL, y, c);
+                if (c < dim) t += jl[c] * yc;
+            }
+            scv = t;
+        }
+    }
+    if (nreg > 0 && lane == 0) atomicAdd(&v.info[3], nreg);
+    __syncwarp();
+    scv = 0.0;
+#pragma unroll 1
+    for (int i = Ns - 2; i >= 0; i--)
+    {
+        const int dim = nu * A.cn[i], lo = A.lo[i];
+        const double *W = A.JD0 + A.jdo[i];
+        const bool row = mine && l < dim;
+        double lc[DM];
+#pragma unroll
+        for (int r = 0; r < DM; r++) lc[r] = (row && r < dim && r > l) ? W[r + l * dim] : 0.0;
+        double y = 0.0, pinv = 0.0;
+        if (row)
+        {
+            double rhs = A.rhs[lo + l];
+            if (i < Ns - 2) rhs = rhs - scv;
+            y = rhs;
+            pinv = A.inv[lo + l];
+        }
+        /* y <- L^-T y (dtrsv_ltn) */
+#pragma unroll
+        for (int r = DM - 1; r >= 0; r--)
+            if (r < dim)
+            {
+                const double yi = __shfl_sync(FULL, y, r) * __shfl_sync(FULL, pinv, r);
+                if (l == r) y = yi;
+                else if (l < r) y -= lc[r] * yi;
+            }
+        if (row) v.dlam[lo + l] = y;
+        if (i > 0)
+        {
+            const int dimP = nu * A.cn[i - 1];
+            const double *CJL = A.JL + A.jlo[i - 1]; /* dim x dimP */
+            double t = 0.0;
+#pragma unroll
+            for (int a = 0; a < DM; a++)
+            {
+                const double ya = __shfl_sync(FULL, y, a);
+                if (a < dim && mine && l < dimP) t += CJL[a + l * dim] * ya;
+            }
+            scv = t;
+        }
+    }
+    __syncwarp();
+}
+
 /* ------------------------------------------------------------------------------------------
  * dmu_i = Lambda_i^-1 (-res_i + Zbar (dlam_{i-1} - dlam_i))  (calculate_delta_mu :1077-1205), then
  * the derivative of the unconstrained stage solutions along (dmu, dlam): along the step the stage
@@ -866,7 +1049,12 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
                 const JayArena A = jay_arena(v, v.jay_in_smem ? smem : v.jarena);
                 sd_jay_gather(v, A, tm);
                 __syncthreads();
-                if (tm.wib == 0) sd_jay_chain(v, A, tm.lane);
+                if (tm.wib == 0)
+                {
+                    if (v.d.mJ <= 4 && !v.no_small_jay) sd_jay_chain_small<4>(v, A, tm.lane);
+                    else if (v.d.mJ <= 8 && !v.no_small_jay) sd_jay_chain_small<8>(v, A, tm.lane);
+                    else sd_jay_chain(v, A, tm.lane);
+                }
             }
             team_sync();
         }
@@ -998,6 +1186,10 @@ static int sd_build_device(tqb_sd_device *D, const int *h_int)
     D->nblocks = nb;
     size_t sm = (size_t) wpb * per_warp;
     v.jay_in_smem = jay * 8 <= lim;
+    {
+        const char *e = getenv("TREEQP_B200_GENERIC_JAY");
+        v.no_small_jay = (e && e[0] == '1') ? 1 : 0;
+    }
     if (v.jay_in_smem && jay > sm) sm = jay;
     D->smem = sm * 8;
     v.per_warp = (int) per_warp;
