@@ -531,6 +531,10 @@ return_t treeqp_tdunes_download(tree_qp_out *qp_out, treeqp_tdunes_workspace *wo
  * the host). */
 return_t treeqp_tdunes_update_x0(const tree_qp_in *qp_in, treeqp_tdunes_workspace *work);
 return_t treeqp_tdunes_warm_start_resident(treeqp_tdunes_workspace *work);
+/* tree_qp_out_max_KKT_res (tree_qp_common.c:769) of the last solve, evaluated on the device from the
+ * resident iterates: no O(Nn) host pass and no download needed for a convergence certificate.
+ * The batch form fills kkt[n], one value per QP. */
+return_t treeqp_tdunes_kkt_resident(treeqp_tdunes_workspace *work, double *kkt);
 
 /* Batch of n independent tree QPs solved as one forest: every kernel launch covers the same
  * tree level of all QPs.  All QPs share `opts` (qp_solver is read from opts for the first Nn
@@ -547,6 +551,7 @@ return_t treeqp_tdunes_batch_download(treeqp_tdunes_batch *batch, tree_qp_out *c
 /* upload + solve_resident + download */
 return_t treeqp_tdunes_solve_batch(treeqp_tdunes_batch *batch, const tree_qp_in *const *qp_in,
                                    tree_qp_out *const *qp_out, return_t *status);
+return_t treeqp_tdunes_batch_kkt_resident(treeqp_tdunes_batch *batch, double *kkt);
 void treeqp_tdunes_batch_get_stats(const treeqp_tdunes_batch *batch, treeqp_b200_stats *stats);
 void treeqp_tdunes_batch_destroy(treeqp_tdunes_batch *batch);
 

@@ -57,6 +57,7 @@ struct tqb_device
     tqb_dims dims;
     int *d_int;
     double *d_in, *d_work;
+    unsigned long long *d_kkt; /* [nT] per-tree KKT residual bits (tqb_device_kkt) */
     int *d_tint;      /* per-tree ints + counters + ls history */
     double *d_tdbl;   /* per-tree doubles */
     int *h_counters;  /* pinned [4] */
@@ -610,6 +611,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
     if (D->pev) { for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) cudaEventDestroy(D->pev[i]); free(D->pev); free(D->pev_class); }
+    if (D->d_kkt) cudaFree(D->d_kkt);
     if (D->stream) cudaStreamDestroy(D->stream);
     free(D->lvl_ptr);
     free(D);
@@ -669,6 +671,19 @@ extern "C" int tqb_device_download(tqb_device *D, double *h_out, double *ms)
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, D->ev0, D->ev1));
     if (ms) *ms = t;
+    return 0;
+}
+
+/* KKT residual of every tree from the resident iterates (k_kkt): h_kkt[nT] */
+extern "C" int tqb_device_kkt(tqb_device *D, double *h_kkt)
+{
+    const int nT = D->dims.nT;
+    if (!D->d_kkt) CK(cudaMalloc(&D->d_kkt, sizeof(unsigned long long) * (size_t) nT));
+    CK(cudaMemsetAsync(D->d_kkt, 0, sizeof(unsigned long long) * (size_t) nT, D->stream));
+    k_kkt<<<(D->v.Nn + 7) / 8, 256, 0, D->stream>>>(D->v, D->d_kkt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_kkt, D->d_kkt, sizeof(double) * (size_t) nT, cudaMemcpyDeviceToHost, D->stream));
+    CK(cudaStreamSynchronize(D->stream));
     return 0;
 }
 

@@ -1013,3 +1013,70 @@ __global__ void k_finish(View v)
     if (i < v.X) v.mux[i] = v.in.Qd[i] * (v.xUnc[i] - v.x[i]);
     if (i < v.U) v.muu[i] = v.in.Rd[i] * (v.uUnc[i] - v.u[i]);
 }
+
+
+/* Largest KKT residual of every tree from the iterates in HBM, with the definition of
+ * tree_qp_out_max_KKT_res (tree_qp_common.c:540-788; host restatement in containers.c): infinity norm
+ * over stationarity (Q x + S'u + q + mu_x - lam + sum_kids A_k' lam_k ; R u + S x + r + mu_u +
+ * sum_kids B_k' lam_k), dynamics (A x_dad + B u_dad + b - x), bound violation and complementarity
+ * (mu > 0 <=> upper bound).  One warp per node; the per-tree maximum is taken on the bit patterns of
+ * the absolute values (order preserving for non-negative doubles, NaN sorts above everything, so
+ * it propagates like in the host version). */
+__device__ __forceinline__ unsigned long long kkt_bits(double v) { return (unsigned long long) __double_as_longlong(fabs(v)); }
+
+__global__ void __launch_bounds__(256) k_kkt(View v, unsigned long long *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= v.Nn) return;
+    const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
+    const int dad = v.T.dad[g], k0 = v.T.kid0[g], nk = v.T.nkids[g], ho = v.T.hoff[g], nv = nx + nu;
+    const double *x = v.x + xo, *u = v.u + uo;
+    const double *H = ho >= 0 ? v.in.H + ho : nullptr;
+    unsigned long long err = 0ull;
+    for (int r = lane; r < nv; r += 32)
+    {   /* stationarity, row r of z = [x; u] */
+        const bool isx = r < nx;
+        const int i = isx ? r : r - nx;
+        double s = isx ? v.in.q[xo + i] + v.mux[xo + i] : v.in.r[uo + i] + v.muu[uo + i];
+        if (H)
+        {
+            for (int c = 0; c < nx; c++) s += H[r + c * nv] * x[c];
+            for (int c = 0; c < nu; c++) s += H[r + (nx + c) * nv] * u[c];
+        }
+        else s += isx ? v.in.Qd[xo + i] * x[i] : v.in.Rd[uo + i] * u[i];
+        if (isx && dad >= 0) s -= v.lam[xo + i];
+        for (int j = 0; j < nk; j++)
+        {
+            const int k = k0 + j, nxk = v.T.nx[k];
+            const double *M = isx ? v.in.A + v.T.aoff[k] + (size_t) i * nxk : v.in.B + v.T.boff[k] + (size_t) i * nxk;
+            const double *lk = v.lam + v.T.xoff[k];
+            for (int c = 0; c < nxk; c++) s += M[c] * lk[c];
+        }
+        err = max(err, kkt_bits(s));
+        /* bounds and complementarity of the same variable */
+        double lo, hi;
+        if (H) { lo = isx ? v.in.dxmin[xo + i] : v.in.dumin[uo + i]; hi = isx ? v.in.dxmax[xo + i] : v.in.dumax[uo + i]; }
+        else { lo = isx ? v.in.xmin[xo + i] : v.in.umin[uo + i]; hi = isx ? v.in.xmax[xo + i] : v.in.umax[uo + i]; }
+        const double z = isx ? x[i] : u[i], m = isx ? v.mux[xo + i] : v.muu[uo + i];
+        if (z > hi) err = max(err, kkt_bits(z - hi));
+        else if (z < lo) err = max(err, kkt_bits(lo - z));
+        err = max(err, kkt_bits(m > 0 ? m * (z - hi) : m * (lo - z)));
+    }
+    if (dad >= 0)
+    {   /* dynamics of the edge into this node */
+        const int nxp = v.T.nx[dad], nup = v.T.nu[dad];
+        const double *xp = v.x + v.T.xoff[dad], *up = v.u + v.T.uoff[dad];
+        const double *A = v.in.A + v.T.aoff[g], *B = v.in.B + v.T.boff[g];
+        for (int r = lane; r < nx; r += 32)
+        {
+            double s = v.in.b[xo + r] - x[r];
+            for (int c = 0; c < nxp; c++) s += A[r + c * nx] * xp[c];
+            for (int c = 0; c < nup; c++) s += B[r + c * nx] * up[c];
+            err = max(err, kkt_bits(s));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err = max(err, __shfl_xor_sync(FULL, err, o));
+    if (lane == 0) atomicMax(out + v.T.tree[g], err);
+}

@@ -146,6 +146,7 @@ int tqb_device_upload_begin(tqb_device *d);
 int tqb_device_upload_range(tqb_device *d, const double *h_in, long long off, long long n);
 int tqb_device_upload_end(tqb_device *d, double *ms_total);
 int tqb_device_warm_start(tqb_device *d, long long lam0_off, long long n);
+int tqb_device_kkt(tqb_device *d, double *h_kkt);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
 int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,
                      int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms, long long *launches,

@@ -340,6 +340,14 @@ return_t treeqp_tdunes_warm_start_resident(treeqp_tdunes_workspace *work)
     return TREEQP_OK;
 }
 
+/* tree_qp_out_max_KKT_res (tree_qp_common.c:769) of the last solve, computed where the iterates are */
+return_t treeqp_tdunes_kkt_resident(treeqp_tdunes_workspace *work, double *kkt)
+{
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest || !ctx->uploaded || !kkt) return TREEQP_UNKNOWN_ERROR;
+    return tqb_device_kkt(ctx->forest->dev, kkt) ? TREEQP_UNKNOWN_ERROR : TREEQP_OK;
+}
+
 return_t treeqp_tdunes_download(tree_qp_out *qp_out, treeqp_tdunes_workspace *work)
 {
     tqb_ctx *ctx = ctx_of(work);
@@ -451,6 +459,12 @@ return_t treeqp_tdunes_solve_batch(treeqp_tdunes_batch *b, const tree_qp_in *con
     st = treeqp_tdunes_batch_solve_resident(b, status);
     if (st != TREEQP_OK) return st;
     return treeqp_tdunes_batch_download(b, qp_out);
+}
+
+return_t treeqp_tdunes_batch_kkt_resident(treeqp_tdunes_batch *b, double *kkt)
+{
+    if (!b || !b->uploaded || !kkt) return TREEQP_UNKNOWN_ERROR;
+    return tqb_device_kkt(b->forest->dev, kkt) ? TREEQP_UNKNOWN_ERROR : TREEQP_OK;
 }
 
 void treeqp_tdunes_batch_get_stats(const treeqp_tdunes_batch *b, treeqp_b200_stats *s)
