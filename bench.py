@@ -478,6 +478,7 @@ def main():
     clk = clocks.stop(clk_lo, clocks.mark()) if rank == 0 else None
     assert st2 == 0 and qp_out.iter == iters
     kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
+    kkt_dev = solver.kkt_resident()  # the same certificate evaluated on the device (k_kkt)
 
     # ---- roofline of the dominant kernel class: one profiled solve (CUDA events per launch)
     lib.lib.treeqp_b200_set_profiling(1)
@@ -569,7 +570,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, 1 tree per GPU" % (args.depth, prob.Nn),
-                   "newton_iters": iters, "ls_trials": stats["ls_total"], "kkt": kkt,
+                   "newton_iters": iters, "ls_trials": stats["ls_total"], "kkt": kkt, "kkt_device": kkt_dev,
                    "l2": "inputs %.2f GB + iterates/Hessian blocks, all >> 126 MB L2: no flush between steps" % (stats["h2d_bytes"] / 1e9),
                    "parallelism": "1 QP per GPU, no collective"},
         "us_per_newton_iter": 1e3 * (1e3 * t_res / args.steps) / max(iters, 1),

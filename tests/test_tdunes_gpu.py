@@ -179,3 +179,41 @@ def test_sharded_solve_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "run_sharded.py"), "9"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert r.returncode == 0 and "MISMATCH" not in r.stdout and r.stdout.count(" OK") == 2, r.stdout[-3000:]
+
+
+@pytest.mark.parametrize("dense", [False, True])
+def test_device_kkt_matches_host_kkt(dense, product_lib):
+    """treeqp_tdunes_kkt_resident (k_kkt) = tree_qp_out_max_KKT_res (tree_qp_common.c:769) of the same
+    iterates: on a NON-converged state (2 iterations) the residual is O(1e-2) and must agree to
+    rounding; on the converged state both are at the tolerance level"""
+    L = product_lib
+    if dense:
+        prob, opts = CS.get_dense_case("random_vary_dims")
+    else:
+        prob, opts = CS.get_case("random_vary_dims")
+    for max_iter in (2, 200):
+        qp_in, qp_out = capi.QpIn(L, prob), capi.QpOut(L, prob)
+        s = capi.Tdunes(L, qp_in, **dict(opts, maxIter=max_iter))
+        s.set_dual_initialization(np.zeros(prob.n_lambda))
+        st = s.solve(qp_out)
+        host = float(L.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
+        dev = s.kkt_resident()
+        if max_iter == 2:
+            assert st == capi.TREEQP_MAXIMUM_ITERATIONS_REACHED and host > 1e-6
+            assert abs(dev - host) <= 1e-9 * host
+        else:
+            assert st == 0 and host < 1e-8 and dev < 1e-8
+        s.destroy()
+
+
+def test_device_kkt_batch(product_lib):
+    L = product_lib
+    probs = P.linear_chain_batch(16, seed=3)
+    qp_ins = [capi.QpIn(L, p) for p in probs]
+    qp_outs = [capi.QpOut(L, p) for p in probs]
+    b = capi.TdunesBatch(L, qp_ins)
+    assert b.solve(qp_outs) == capi.TREEQP_OK and (b.status == 0).all()
+    dev = b.kkt_resident()
+    host = np.array([L.lib.tree_qp_out_max_KKT_res(i.ptr, o.ptr) for i, o in zip(qp_ins, qp_outs)])
+    assert dev.shape == (16,) and (dev < 1e-8).all() and (host < 1e-8).all()
+    b.destroy()

@@ -242,6 +242,10 @@ class TreeQpLib:
             L.treeqp_tdunes_update_x0.restype = C.c_int
             L.treeqp_tdunes_warm_start_resident.argtypes = [vp]
             L.treeqp_tdunes_warm_start_resident.restype = C.c_int
+            L.treeqp_tdunes_kkt_resident.argtypes = [vp, c_double_p]
+            L.treeqp_tdunes_kkt_resident.restype = C.c_int
+            L.treeqp_tdunes_batch_kkt_resident.argtypes = [vp, c_double_p]
+            L.treeqp_tdunes_batch_kkt_resident.restype = C.c_int
             L.treeqp_b200_set_profiling.argtypes = [C.c_int]
             L.treeqp_b200_set_profiling.restype = None
             L.treeqp_b200_num_kernel_classes.restype = C.c_int
@@ -505,6 +509,12 @@ class Tdunes:
         """after qp_in.set_x0(...): re-send only the root and its children"""
         return int(self.lib.lib.treeqp_tdunes_update_x0(self.qp_in.ptr, self.work.ptr))
 
+    def kkt_resident(self) -> float:
+        """tree_qp_out_max_KKT_res of the last solve, evaluated on the device"""
+        out = np.zeros(1)
+        assert self.lib.lib.treeqp_tdunes_kkt_resident(self.work.ptr, _dp(out)) == TREEQP_OK
+        return float(out[0])
+
     def warm_start_resident(self) -> int:
         """dual start of the next solve = multipliers of the last one, without leaving HBM"""
         return int(self.lib.lib.treeqp_tdunes_warm_start_resident(self.work.ptr))
@@ -580,6 +590,12 @@ class TdunesBatch:
 
     def solve_resident(self) -> int:
         return int(self.lib.lib.treeqp_tdunes_batch_solve_resident(self.handle, _ip(self.status)))
+
+    def kkt_resident(self) -> np.ndarray:
+        """per-QP tree_qp_out_max_KKT_res of the last solve, evaluated on the device"""
+        out = np.zeros(self.n)
+        assert self.lib.lib.treeqp_tdunes_batch_kkt_resident(self.handle, _dp(out)) == TREEQP_OK
+        return out
 
     def _out_ptrs(self, qp_outs):
         return (C.c_void_p * self.n)(*[q.ptr.value for q in qp_outs])
