@@ -13,8 +13,10 @@ QPs, FP64).  One "step" = one complete dual Newton solve of that QP from the dua
   roofline      dominant kernel class: algorithmic bytes (SURVEY.md 8d formulas) / CUDA-event time
   cpu_baseline  the unmodified reference (oracle/_ref, OpenMP build, all host cores) on the same QP
 
-N>1: one process per GPU (torchrun), each rank solves its own tree of the same shape (seed = rank):
-the path partitions by independent QP, no data-path collective -> weak scaling.
+N>1: one process per GPU (torchrun), each rank solves its own copy of the same tree QP: the path
+partitions by independent QP, no data-path collective -> weak scaling.  Next to it the record carries
+ONE tree sharded by subtree over the N GPUs (strong scaling, NCCL exchange of the cut-node Schur
+complements) and the 4096-QP batch split over the ranks.
 --impl reference: times the reference's own CPU implementation (rank 0 only).
 """
 import argparse
@@ -424,7 +426,9 @@ def main():
 
     lib = capi.TreeQpLib(capi.PRODUCT_LIB)
     assert lib.lib.treeqp_b200_set_device(local) == 0
-    prob = workload(args.depth, rank)
+    # every rank solves its own copy of the SAME QP (seed 0): per-GPU work is then identical at every
+    # N (the Newton iteration count depends on the data), which is what weak scaling compares
+    prob = workload(args.depth, 0)
     qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
     solver = capi.Tdunes(lib, qp_in, **OPTS)
     lam0 = np.zeros(prob.n_lambda)
