@@ -11,6 +11,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n", type=int, default=4096)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--profile", type=int, default=1)
+ap.add_argument("--e2e", type=int, default=2)
+ap.add_argument("--ref", type=int, default=1)
 args = ap.parse_args()
 lib = capi.TreeQpLib(capi.PRODUCT_LIB)
 t0 = time.perf_counter()
@@ -25,10 +27,12 @@ for r in range(args.reps):
     s = batch.stats()
     print("resident: %.2f ms wall, gpu %.2f ms, max iter %d, launches %d, %.0f QP/s" % (1e3 * t, s["gpu_ms"], s["iter"], s["kernel_launches"], args.n / t), flush=True)
 assert (batch.status == 0).all(), np.unique(batch.status, return_counts=True)
-for r in range(2):
+for r in range(args.e2e):
     t0 = time.perf_counter(); st = batch.solve(qp_outs); t = time.perf_counter() - t0
     s = batch.stats()
     print("e2e: %.2f ms wall (pack %.2f, h2d %.2f, gpu %.2f, d2h %.2f) %.0f QP/s" % (1e3 * t, s["pack_ms"], s["h2d_ms"], s["gpu_ms"], s["d2h_ms"], args.n / t), flush=True)
+if args.e2e == 0:
+    batch.solve(qp_outs) if False else None
 iters = np.array([o.iter for o in qp_outs])
 print("iterations: min %d median %d max %d" % (iters.min(), np.median(iters), iters.max()))
 if args.profile:
@@ -38,7 +42,7 @@ if args.profile:
     lib.lib.treeqp_b200_set_profiling(0)
     for k, v in sorted(s["kernels"].items(), key=lambda kv: -kv[1][0]):
         print("   %-22s %8.3f ms %6d launches" % (k, v[0], v[1]))
-if os.path.exists(OP.REF_LIB):
+if args.ref and args.e2e and os.path.exists(OP.REF_LIB):
     ref = capi.TreeQpLib(OP.REF_LIB)
     m = min(args.n, 64)
     tt = 0.0

@@ -53,20 +53,32 @@ __device__ __forceinline__ void tqb_rsqrt_core(double c, double &root, double &i
     root = g;
 }
 /* rare pivots: non-positive (BLASFEO: l = 0, inv = 0) or outside [1e-290, 1e290] (rescaled by an exact 4^k) */
-static __device__ __noinline__ void tqb_pivot_rare(double &piv, double &inv)
+/* by value: reference parameters of a non-inlined function would force the caller's pivot into local
+ * memory (one store per Cholesky step whether or not the rare path runs; ncu showed 76 local-store
+ * sectors per 8 x 8 block, a third of the kernel's L1 traffic) */
+static __device__ __noinline__ double2 tqb_pivot_rare(double piv)
 {
-    if (!(piv > 0.0)) { piv = 0.0; inv = 0.0; return; }
-    double sc, isc;
+    if (!(piv > 0.0)) return make_double2(0.0, 0.0);
+    double sc, isc, inv;
     if (piv < 1.0) { piv *= 0x1p600; sc = 0x1p-300; isc = 0x1p300; }
     else { piv *= 0x1p-600; sc = 0x1p300; isc = 0x1p-300; }
     tqb_rsqrt_core(piv, piv, inv);
-    piv *= sc; inv *= isc;
+    return make_double2(piv * sc, inv * isc);
 }
 __device__ __forceinline__ void tqb_pivot(double &piv, double &inv)
 {
 #ifndef TQB_IEEE_PIVOT
-    if (piv > 1e-290 && piv < 1e290) tqb_rsqrt_core(piv, piv, inv); /* the only branch of the common case */
-    else tqb_pivot_rare(piv, inv);
+    if (piv > 1e-290 && piv < 1e290)
+    {   /* the only branch of the common case */
+        double root, rinv;
+        tqb_rsqrt_core(piv, root, rinv);
+        piv = root; inv = rinv;
+    }
+    else
+    {
+        const double2 t = tqb_pivot_rare(piv);
+        piv = t.x; inv = t.y;
+    }
 #else
     if (piv > 0.0) { piv = sqrt(piv); inv = 1.0 / piv; }
     else { piv = 0.0; inv = 0.0; }
