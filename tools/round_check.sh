@@ -19,3 +19,9 @@ print({k: (round(x["ms"], 2), x["launches"]) for k, x in d["roofline"]["per_kern
 for k, v in d["other_workloads"].items():
     print(k, json.dumps(v)[:900])
 PY
+# one --set full capture of the dominant kernel (bottom level of the leaves-to-root sweep)
+ncu --set full --clock-control none --import-source on -k regex:k_build_factor -c 1 -o gpurun_out/${tag}_bf -f \
+    python tools/profile_solve.py --depth 16 --max-iter 1 > gpurun_out/${tag}_bf.log 2>&1
+ncu -i gpurun_out/${tag}_bf.ncu-rep --page details > gpurun_out/${tag}_bf.txt 2>/dev/null
+ncu -i gpurun_out/${tag}_bf.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/${tag}_bf_src.csv 2>/dev/null
+grep -E "Duration|DRAM Throughput|L1/TEX Cache Throughput|Issue Slots Busy|Registers Per|Achieved Occupancy" gpurun_out/${tag}_bf.txt | head -8
