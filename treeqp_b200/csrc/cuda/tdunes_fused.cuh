@@ -66,7 +66,7 @@ struct FusedCfg
     static constexpr int LDC = tqb_ld2(NCOL > 0 ? NCOL : 2);
     static constexpr int LDR = tqb_ld2(R);
     /* shared memory per warp, in doubles: Ms (D x LDR; its head doubles as Cp, D x LDC, during the
-     * build) | p (NCOL) | z (NCOL) | ys (D) | dgs (D) | invs (D) */
+     * build) | p (NCOL) | z (NCOL) | ys (D) (+ 2 D spare) */
     /* FP64 tensor-core (DMMA m8n8k4) build of C diag(p) C' and of the Schur complement for the
      * larger blocks: 8x8 output tiles, operands in fragment layout straight from HBM / shared memory */
     static constexpr bool DMMA = D >= TQB_DMMA_MIN_D;
@@ -122,14 +122,13 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
     double *ps = Ms + Cfg::SM_M;                  /* [P_p ; Rt_p] */
     double *zs = ps + NCOL + 2;                   /* [x_p ; u_p] */
     double *ys = zs + NCOL + 2;                   /* y = L^-1 resMod */
-    double *dgs = ys + D, *invs = dgs + D;        /* diagonal of L and its inverse */
 
     const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
     const bool isW = lane < D;
     const int kid = isW ? lane / NX : 0, ii = isW ? lane - kid * NX : 0;
 
     double wA[D], utc[NCOLU > 0 ? NCOLU : 1];
-    double myinv = 0.0, rr = 0.0;
+    double myinv = 0.0, my_y = 0.0, my_d = 0.0, rr = 0.0;
     bool small = false;
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; attempt++)
@@ -352,12 +351,22 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
                 for (int cc = 0; cc < NCOLU; cc++) us[cc] = utc[cc] * inv;
                 if (lane == j)
                 {
+                    if constexpr ((NCOLU & 1) == 0 && (RL & 1) == 0)
+                    {
 #pragma unroll
-                    for (int cc = 0; cc < NCOLU; cc++) Ms[j * LDR + RL + cc] = us[cc];
+                        for (int cc = 0; cc < NCOLU; cc += 2)
+                            *reinterpret_cast<double2 *>(Ms + j * LDR + RL + cc) = make_double2(us[cc], us[cc + 1]);
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int cc = 0; cc < NCOLU; cc++) Ms[j * LDR + RL + cc] = us[cc];
+                    }
                 }
             }
-            /* piv, inv and yj are warp-uniform: every lane stores the same value to the same word (no branch) */
-            ys[j] = yj; dgs[j] = piv; invs[j] = inv;
+            /* piv, inv and yj are warp-uniform; lane j keeps them (the kernel is bound by L1/shared
+             * wavefronts: three uniform stores per step cost more than three selects) */
+            if (lane == j) { my_y = yj; my_d = piv; myinv = inv; }
             __syncwarp();
             const double lj = wA[j];
             const double *col = Ms + j * LDR;
@@ -374,8 +383,21 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
                 }
                 if (NCOLU > 0)
                 {   /* Ut[c][lane] -= Utilde[c][j] * L[lane][j] on the lanes still to come */
+                    if constexpr ((NCOLU & 1) == 0 && (RL & 1) == 0)
+                    {
 #pragma unroll
-                    for (int cc = 0; cc < NCOLU; cc++) utc[cc] -= col[RL + cc] * lj;
+                        for (int cc = 0; cc < NCOLU; cc += 2)
+                        {
+                            const double2 u2 = *reinterpret_cast<const double2 *>(col + RL + cc);
+                            utc[cc] -= u2.x * lj;
+                            utc[cc + 1] -= u2.y * lj;
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int cc = 0; cc < NCOLU; cc++) utc[cc] -= col[RL + cc] * lj;
+                    }
                 }
             }
         }
@@ -387,13 +409,13 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
     /* ---- results to HBM ---- */
     if (isW)
     {
-        rr = ys[lane];
-        myinv = invs[lane];
+        rr = my_y;
+        ys[lane] = my_y; /* read below by the lanes that form s_p = Utilde y */
         double *Lp = v.W + d1.w + (lane * (lane + 1)) / 2;
 #pragma unroll
         for (int t = 0; t < D; t++)
             if (t < lane) Lp[t] = wA[t];
-        Lp[lane] = dgs[lane];
+        Lp[lane] = my_d;
         v.Linv[xb + lane] = myinv;
     }
     if (!ROOT)
@@ -458,6 +480,7 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
             for (int j = 0; j < D; j++) s += Ms[j * LDR + D + a] * Ms[j * LDR + D + b];
             Sg[a * NX + b] = s;
         }
+        __syncwarp(); /* ys */
         for (int a = lane; a < NX; a += 32)
         {
             double s = 0.0;
@@ -570,13 +593,13 @@ __device__ __forceinline__ void bf_block_half(const View &v, size_t desc, bool v
     }
     const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
     double *Cp = Ms;
-    double *ps = Ms + Cfg::SM_M, *zs = ps + NCOL + 2, *ys = zs + NCOL + 2, *dgs = ys + D, *invs = dgs + D;
+    double *ps = Ms + Cfg::SM_M, *zs = ps + NCOL + 2, *ys = zs + NCOL + 2;
     const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
     const bool isW = sl < D, isU = sl >= D && sl < 2 * D; /* Ut row sl - D */
     const bool ldW = act && isW;
 
     double wA[D];
-    double rr = 0.0;
+    double rr = 0.0, my_y = 0.0, my_d = 0.0, my_inv = 0.0;
     bool small = false;
 #pragma unroll 1
     for (int attempt = 0; attempt < 2; attempt++)
@@ -668,7 +691,7 @@ __device__ __forceinline__ void bf_block_half(const View &v, size_t desc, bool v
             const double yj = __shfl_sync(FULL, rr, j, 16) * inv;
             rr = fma(-wA[j], yj, rr);
             if (sl < 2 * D) Ms[j * LDR + sl] = wA[j];
-            ys[j] = yj; dgs[j] = piv; invs[j] = inv;
+            if (sl == j) { my_y = yj; my_d = piv; my_inv = inv; }
             __syncwarp();
             const double lj = wA[j];
             const double *col = Ms + j * LDR;
@@ -697,10 +720,12 @@ __device__ __forceinline__ void bf_block_half(const View &v, size_t desc, bool v
 #pragma unroll
         for (int t = 0; t < D; t++)
             if (t < sl) Lp[t] = wA[t];
-        Lp[sl] = dgs[sl];
-        v.Linv[xb + sl] = invs[sl];
-        v.dlam[xb + sl] = ys[sl];
+        Lp[sl] = my_d;
+        v.Linv[xb + sl] = my_inv;
+        v.dlam[xb + sl] = my_y;
     }
+    if (isW) ys[sl] = my_y;
+    __syncwarp();
     if (isU && act)
     {
         double2 *dst = reinterpret_cast<double2 *>(v.Ut + d2.x + (sl - D) * D);
