@@ -74,6 +74,7 @@ struct tqb_device
     int fast, f_nx, f_nu, f_pnx;
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
     int *chain_link;      /* [Nh] depth l continues the chains of depth l-1 (one kid per parent, same order) */
+    int has_ghost;        /* sharded local forest: reduction chunks cover the owned nodes only */
     int pair_begin;       /* level descriptors from here on are non-root parents with one kid (k_stage_fused pairs them) */
     double *d_schur;
     int *d_lvl_desc;
@@ -500,6 +501,7 @@ static int launch_stage(tqb_device *D, int cls)
 static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, const int *ghost)
 {
     const tqb_dims *d = &D->dims;
+    D->has_ghost = ghost != NULL;
     CK(cudaStreamCreateWithFlags(&D->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&D->ev0));
     CK(cudaEventCreate(&D->ev1));
@@ -899,7 +901,8 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             }
         }
         if (D->h_counters[4] == 0) break; /* every tree has terminated */
-        if (v.nxmax <= 4) LAUNCH(K_STEP, k_lambda_step_w<4>, cdiv(v.Nn, 64), 256, 0, v);
+        if (!D->comm && !D->has_ghost) LAUNCH(K_STEP, k_lambda_step_chunks, v.nchunk, 256, 0, v);
+        else if (v.nxmax <= 4) LAUNCH(K_STEP, k_lambda_step_w<4>, cdiv(v.Nn, 64), 256, 0, v);
         else if (v.nxmax <= 8) LAUNCH(K_STEP, k_lambda_step_w<8>, cdiv(v.Nn, 32), 256, 0, v);
         else if (v.nxmax <= 16) LAUNCH(K_STEP, k_lambda_step_w<16>, cdiv(v.Nn, 16), 256, 0, v);
         else if (v.nxmax <= 32) LAUNCH(K_STEP, k_lambda_step_w<32>, cdiv(v.Nn, 8), 256, 0, v);

@@ -776,6 +776,19 @@ __global__ void __launch_bounds__(256) k_lambda_step_w(View v)
     v.lam[e] += v.t_taufin[t] * v.dlam[e];
 }
 
+/* the same as a stream over x-space: one CTA per fixed reduction chunk (a node range of ONE tree, so
+ * status and step length are CTA-uniform and nothing is looked up per element); roots carry no
+ * multiplier and are skipped.  Needs chunks that cover every node (not a sharded solve). */
+__global__ void __launch_bounds__(256) k_lambda_step_chunks(View v)
+{
+    const int c = blockIdx.x, t = v.T.chunk_tree[c];
+    if (v.status[t] != TQB_RUNNING) return;
+    const double step = v.t_taufin[t];
+    const int gb = v.T.chunk_beg[c];
+    const int x0 = v.T.chunk_x0[c] + (v.T.dad[gb] < 0 ? v.T.nx[gb] : 0), x1 = v.T.chunk_x1[c];
+    for (int e = x0 + threadIdx.x; e < x1; e += 256) v.lam[e] += step * v.dlam[e];
+}
+
 /* Armijo test of one trial (dual_Newton_tree.c:970-1000) */
 __global__ void k_decide_ls_trial(View v)
 {
