@@ -22,8 +22,9 @@
  * k_backsolve_fused<NX,MD>: dlam_p = L_p^-T (y_p - Utilde_p' dlam_dad[p]), lane t owns COLUMN t of L.
  *
  * HBM format of a factored block: L packed by rows (row i at i(i+1)/2, i+1 entries), Utilde
- * row-major NX x D, inverse diagonal in x-space (Linv), Schur complement S_p (NX x NX row-major,
- * lower triangle valid) and s_p in x-space (rsub).
+ * row-major NX x D, inverse diagonal in x-space (Linv), Schur complement S_p (NX x NX, entry (a, b)
+ * with a >= b at b*NX + a: the consumer's lanes own rows and read a column step by step) and s_p
+ * in x-space (rsub).
  */
 #pragma once
 #include "tdunes_kernels.cuh"
@@ -313,11 +314,11 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
         {
             if (kids_are_parents)
             {   /* minus the Schur complement of the kid this row belongs to (lower triangle) */
-                const double *Sk = v.schur + (size_t) (k0 + kid) * NX * NX + ii * NX;
+                const double *Sk = v.schur + (size_t) (k0 + kid) * NX * NX + ii;
 #pragma unroll
                 for (int kk = 0; kk < NX; kk++)
                 {
-                    const double sv = (kk <= ii) ? Sk[kk] : 0.0;
+                    const double sv = (kk <= ii) ? Sk[kk * NX] : 0.0; /* S[ii][kk], stored by columns */
 #pragma unroll
                     for (int m = 0; m < MD; m++) wA[m * NX + kk] -= (m == kid) ? sv : 0.0;
                 }
@@ -459,8 +460,8 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
 #pragma unroll
                     for (int ks = 0; ks < KSU; ks++) dmma884(c0, c1, uf[i][ks], uf[n][ks]);
                     const int a = 8 * i + gid, b = 8 * n + 2 * tig;
-                    if (a < NX && b < NX) Sg[a * NX + b] = c0;
-                    if (a < NX && b + 1 < NX) Sg[a * NX + b + 1] = c1;
+                    if (a < NX && b < NX) Sg[b * NX + a] = c0;
+                    if (a < NX && b + 1 < NX) Sg[(b + 1) * NX + a] = c1;
                 }
         }
         else
@@ -481,7 +482,7 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
             double s = 0.0;
 #pragma unroll
             for (int j = 0; j < D; j++) s += Ms[j * LDR + D + a] * Ms[j * LDR + D + b];
-            Sg[a * NX + b] = s;
+            Sg[b * NX + a] = s;
         }
         __syncwarp(); /* ys */
         for (int a = lane; a < NX; a += 32)
@@ -672,9 +673,9 @@ __device__ __forceinline__ void bf_block_half(const View &v, size_t desc, bool v
         {
             if (kids_are_parents && act)
             {   /* minus the Schur complement of the kid (lower triangle) */
-                const double *Sk = v.schur + (size_t) k0 * NX * NX + sl * NX;
+                const double *Sk = v.schur + (size_t) k0 * NX * NX + sl;
 #pragma unroll
-                for (int kk = 0; kk < NX; kk++) wA[kk] -= (kk <= sl) ? Sk[kk] : 0.0;
+                for (int kk = 0; kk < NX; kk++) wA[kk] -= (kk <= sl) ? Sk[kk * NX] : 0.0;
             }
         }
         else if (isU)
@@ -746,7 +747,7 @@ __device__ __forceinline__ void bf_block_half(const View &v, size_t desc, bool v
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < D; j++) s += Ms[j * LDR + D + a] * Ms[j * LDR + D + b];
-        if (act) Sg[a * NX + b] = s;
+        if (act) Sg[b * NX + a] = s;
     }
     if (sl < NX)
     {
