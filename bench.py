@@ -353,6 +353,36 @@ def bench_dense(lib, reps=5):
             rec["cpu_reference_ms_per_solve"] = tb
             rec["cpu_reference_newton_iters"] = int(rout.iter)
         out[name] = rec
+    # the GPU regime of small dense trees is the batch: 256 QPs of the quadcopter dimensions as one forest
+    try:
+        n = 256
+        bp = [P.densify(P.random_tree(P.multistage_nk(3, 2, 20), 6, 4, seed=100 + i, ubound=0.3), 4, 0.1, 0.0) for i in range(n)]
+        qi = [capi.QpIn(lib, p) for p in bp]
+        qo = [capi.QpOut(lib, p) for p in bp]
+        b = capi.TdunesBatch(lib, qi, qp_solver=1, maxIter=200)
+        assert b.upload() == capi.TREEQP_OK
+        b.solve_resident()
+        t_res = []
+        for _ in range(3):
+            t0 = time.perf_counter(); b.solve_resident(); t_res.append(time.perf_counter() - t0)
+        t0 = time.perf_counter(); b.solve(qo); t_e2e = time.perf_counter() - t0
+        iters = np.array([o.iter for o in qo])
+        rec = {"workload": "%d x dense tree nx=6 nu=4 md=3 Nr=2 Nh=20 (175 nodes) as one forest" % n, "converged": int((b.status == 0).sum()),
+               "qp_per_s_resident": n / min(t_res), "qp_per_s_e2e": n / t_e2e, "ms_per_batch_resident": 1e3 * min(t_res),
+               "newton_iters_median": float(np.median(iters)), "newton_iters_max": int(iters.max())}
+        if ref is not None:
+            m, tt = 8, 0.0
+            for i in range(m):
+                rin, rout = capi.QpIn(ref, bp[i]), capi.QpOut(ref, bp[i])
+                rs = capi.Tdunes(ref, rin, qp_solver=1, maxIter=200)
+                rs.set_dual_initialization(np.zeros(bp[i].n_lambda)); rs.solve(rout); tt += rout.total_time
+                rec.setdefault("cpu_iters_match", True)
+                rec["cpu_iters_match"] = bool(rec["cpu_iters_match"] and rout.iter == iters[i])
+            rec["cpu_reference_qp_per_s_per_core"] = m / tt
+        b.destroy()
+        out["batch256_quadcopter_dims"] = rec
+    except Exception as e:
+        out["batch256_quadcopter_dims"] = {"error": repr(e)}
     return out
 
 
