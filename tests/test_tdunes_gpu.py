@@ -217,3 +217,24 @@ def test_device_kkt_batch(product_lib):
     host = np.array([L.lib.tree_qp_out_max_KKT_res(i.ptr, o.ptr) for i, o in zip(qp_ins, qp_outs)])
     assert dev.shape == (16,) and (dev < 1e-8).all() and (host < 1e-8).all()
     b.destroy()
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 4, 4, 1), (3, 1, 6, 8, 3), (1, 1, 7, 6, 4), (2, 2, 5, 12, 4), (2, 1, 3, 8, 3)])
+def test_chain_kernels_odd_counts_match_oracle(shape, product_lib, monkeypatch):
+    """chain segments with an ODD number of chains / chain parents (one half-warp of the paired stage
+    kernel and of the two-chains-per-warp sweeps stays empty), a pure chain (md = 1 at the root), and
+    nx = 12 (one chain per warp): same iterates as the oracle and as the per-depth kernels"""
+    md, Nr, Nh, nx, nu = shape
+    prob = P.random_tree(P.multistage_nk(md, Nr, Nh), nx, nu, seed=11 + Nh, ubound=0.3)
+    opts = dict(maxIter=200)
+    s = OP.solve_port(prob, **CS.port_opts(opts))
+    sol = capi.solve_tdunes(product_lib, prob, **opts)
+    assert (sol.status, sol.iter) == (s["status"], s["iter"]) and sol.status == 0
+    assert sol.stats["ls_iters"] == s["ls_iters"]
+    check_against(sol, s, prob, tol=1e-9)
+    monkeypatch.setenv("TREEQP_B200_NO_CHAIN", "1")
+    monkeypatch.setenv("TREEQP_B200_NO_PAIR", "1")
+    ref = capi.solve_tdunes(product_lib, prob, **opts)
+    assert ref.iter == sol.iter
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        assert np.array_equal(getattr(sol, k), getattr(ref, k)), k + ": chain kernels are not bit-identical to the per-depth kernels"
