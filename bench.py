@@ -386,6 +386,58 @@ def bench_dense(lib, reps=5):
     return out
 
 
+def bench_mpc(lib, steps=20):
+    """closed-loop re-solves.  Between consecutive QPs only x0 changes
+    (benchmark/treeqp_main.m:235-237): set_x0 -> update_x0 (root + children travel) -> dual start =
+    previous multipliers (device to device) -> solve -> download, against a full treeqp_tdunes_solve
+    per sample and against the reference doing the same loop on one host core."""
+    prob = P.spring_mass(3, 4, 20)                      # 1417 nodes, x0 pinned on the root
+    dims = P.eliminate_x0(prob)
+    rng = np.random.default_rng(5)
+    x0s = [np.array([0.01, 0.02, 0.03, 0.04]) + 0.002 * rng.standard_normal(4) for _ in range(steps + 1)]
+    qi, qo = capi.QpIn(lib, prob), capi.QpOut(lib, dims)
+    qi.eliminate_x0()
+    s = capi.Tdunes(lib, qi)
+    s.set_dual_initialization(np.zeros(dims.n_lambda))
+    assert s.upload() == capi.TREEQP_OK and s.solve_resident() == 0
+    iters, t0 = [], time.perf_counter()
+    for k in range(steps):
+        qi.set_x0(x0s[k + 1])
+        assert s.update_x0() == capi.TREEQP_OK and s.warm_start_resident() == capi.TREEQP_OK
+        assert s.solve_resident() == 0 and s.download(qo) == capi.TREEQP_OK
+        iters.append(s.stats()["iter"])
+    t_fast = (time.perf_counter() - t0) / steps
+    h2d_fast = s.stats()["h2d_bytes"]
+    lam = qo.lam.copy()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        qi.set_x0(x0s[k + 1])
+        s.set_dual_initialization(lam)
+        assert s.solve(qo) == 0
+        lam = qo.lam.copy()
+    t_full = (time.perf_counter() - t0) / steps
+    out = {"workload": "spring-mass md=3 Nr=4 Nh=20 (1417 nodes), %d closed-loop samples, x0 perturbed, warm-started duals" % steps,
+           "ms_per_sample_update_x0_path": 1e3 * t_fast, "ms_per_sample_full_solve_call": 1e3 * t_full,
+           "h2d_bytes_update_x0": h2d_fast, "h2d_bytes_full": s.stats()["h2d_bytes"], "newton_iters_median": float(np.median(iters))}
+    s.destroy()
+    path = ref_lib_path(False)
+    if path:
+        ref = capi.TreeQpLib(path)
+        ri, ro = capi.QpIn(ref, prob), capi.QpOut(ref, dims)
+        ri.eliminate_x0()
+        rs = capi.Tdunes(ref, ri)
+        rs.set_dual_initialization(np.zeros(dims.n_lambda)); rs.solve(ro)
+        lam, rit, t0 = ro.lam.copy(), [], time.perf_counter()
+        for k in range(steps):
+            ri.set_x0(x0s[k + 1])
+            rs.set_dual_initialization(lam)
+            assert rs.solve(ro) == 0
+            lam = ro.lam.copy(); rit.append(ro.iter)
+        out["cpu_reference_ms_per_sample"] = 1e3 * (time.perf_counter() - t0) / steps
+        out["cpu_reference_iters_median"] = float(np.median(rit))
+    return out
+
+
 def bench_sharded(lib, args, rank, world, local, dist, barrier, max_over_ranks):
     """N > 1: ONE tree (the N=1 workload) sharded by subtree over the ranks: strong scaling"""
     def bcast(b):
@@ -592,7 +644,7 @@ def main():
         extra["batch4096_linear_chain"] = batch_sharded
     if world == 1 and not args.no_extra:
         for name, fn in (("batch4096_linear_chain", bench_batch), ("sdunes_spring_mass_cfg2", bench_sdunes),
-                         ("dense_stage_qps_cfg5", bench_dense)):
+                         ("dense_stage_qps_cfg5", bench_dense), ("mpc_resolve_x0_fast_path", bench_mpc)):
             try:
                 extra[name] = fn(lib)
             except Exception as e:
