@@ -226,8 +226,8 @@ def reference_arm(args):
     value = 1.0 / sec
     print(json.dumps(dict(
         base, value=value, ms_per_step=1e3 * sec, us_per_newton_iter=1e6 * sec / iters_full,
-        config={"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, 1 tree" % (args.depth, prob.Nn),
-                "newton_iters": iters_full, "status": st},
+        config={"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, 1 tree per GPU" % (args.depth, prob.Nn),
+                "newton_iters": iters_full, "status": st, "parallelism": "reference CPU implementation, OpenMP over nodes/blocks, rank 0 only"},
         cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         gpu_launches=0)))
