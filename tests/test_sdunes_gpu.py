@@ -109,6 +109,26 @@ def test_warm_start_and_repeatability(product_lib):
     solver.destroy()
 
 
+@pytest.mark.parametrize("name", ["spring_mass_cfg2", "spring_mass_u02_nocache", "linear_chain_u05"])
+def test_fixed_and_runtime_dimension_chains_identical(name, product_lib, monkeypatch):
+    """the scenario chains instantiated for nx = 4 / 8 and the runtime-dimension instance
+    (TREEQP_B200_GENERIC_NX=1, read at create) keep the same operation order: same iterates"""
+    prob, opts = CS.get_sdunes_case(name)
+    res = []
+    for generic in ("0", "1"):
+        monkeypatch.setenv("TREEQP_B200_GENERIC_NX", generic)
+        qp_in, qp_out = capi.QpIn(product_lib, prob), capi.QpOut(product_lib, prob)
+        solver = capi.Sdunes(product_lib, qp_in, **opts)
+        solver.set_dual_initialization(np.zeros(solver.n_lambda), np.zeros(solver.n_mu))
+        status = solver.solve(qp_out)
+        res.append((status, qp_out.iter, solver.stats()["ls_iters"], qp_out.x.copy(), qp_out.u.copy(), qp_out.lam.copy()))
+        solver.destroy()
+    a, b = res
+    assert a[:3] == b[:3]
+    for p, q in zip(a[3:], b[3:]):
+        assert CS.rel_err(p, q) < 1e-13
+
+
 def test_sdunes_and_tdunes_agree(product_lib):
     """the two decompositions solve the same QP: primal solutions agree to solver tolerance"""
     prob, _ = CS.get_sdunes_case("spring_mass_cfg2")

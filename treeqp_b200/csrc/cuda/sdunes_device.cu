@@ -67,6 +67,7 @@ struct SdView
     double *jarena;                   /* operands of the J chain when they do not fit in shared memory */
     int jay_in_smem;
     int no_small_jay;                 /* TREEQP_B200_GENERIC_JAY=1: always the generic chain walk */
+    int fixed_nx;                     /* 4 / 8: compile-time-dimension scenario chains; 0: runtime (TREEQP_B200_GENERIC_NX=1) */
 };
 
 struct Team
@@ -312,9 +313,14 @@ __device__ __forceinline__ WarpScratch warp_scratch(const SdView &v, double *bas
 /* banded substitution with the factor of Lambda_i (scenarios.c:893-958 and :1129-1188):
  * out = Lambda_i^-1 in (in may alias out).  One element per lane (nx <= 32); the factor blocks of
  * the next stage are prefetched while the current stage is substituted. */
+#ifndef TQB_SD_FIXED_NX_DEFAULT
+#define TQB_SD_FIXED_NX_DEFAULT 0
+#endif
+
+template <int NX>
 __device__ void sd_banded_solve(const SdView &v, int i, const double *in_vec, double *out_vec, const WarpScratch &S, int lane)
 {
-    const int nx = v.d.nx, Nh = v.d.Nh, nxx = nx * nx, ld = nx | 1;
+    const int nx = NX > 0 ? NX : v.d.nx, Nh = v.d.Nh, nxx = nx * nx, ld = nx | 1;
     const size_t ik0 = (size_t) i * Nh;
     for (int phase = 0; phase < 2; phase++)
     {   /* phase 0: L-solves in factorisation order; phase 1: L'-solves in the opposite order */
@@ -378,9 +384,10 @@ __device__ void sd_banded_solve(const SdView &v, int i, const double *in_vec, do
  *   checkLastActiveSet), Ut_i and K_i = -Ut Ut' + diag(RinvCal) (form_K :692-792),
  *   resMod_i = Lambda_i^-1 res_i (:893-958).
  * ---------------------------------------------------------------------------------------- */
+template <int NX>
 __device__ void sd_factor_scenario(const SdView &v, int i, const WarpScratch &S, int lane)
 {
-    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, nK = v.d.nK, nxx = nx * nx, ld = nx | 1;
+    const int nx = NX > 0 ? NX : v.d.nx, nu = v.d.nu, Nh = v.d.Nh, nK = v.d.nK, nxx = nx * nx, ld = nx | 1;
     const size_t ik0 = (size_t) i * Nh;
     double *sinv = S.binv(0);
     int nreg = 0;
@@ -491,7 +498,7 @@ __device__ void sd_factor_scenario(const SdView &v, int i, const WarpScratch &S,
         if (a == b) val += v.Rc[(ik0 + ja) * nu + (a - ja * nu)];
         K[a + b * nK] = val;
     }
-    sd_banded_solve(v, i, v.res + ik0 * nx, v.resMod + ik0 * nx, S, lane);
+    sd_banded_solve<NX>(v, i, v.res + ik0 * nx, v.resMod + ik0 * nx, S, lane);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -863,9 +870,10 @@ __device__ void sd_jay_chain_small(const SdView &v, const JayArena &A, int lane)
  * gradients are affine in the step length, so a line-search trial is a pure vector pass.
  * Returns this lane's part of res'dmu.
  * ---------------------------------------------------------------------------------------- */
+template <int NX>
 __device__ double sd_delta_mu_scenario(const SdView &v, int i, const WarpScratch &S, int lane)
 {
-    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, Ns = v.d.Ns, Nr = v.d.Nr, nv = nx + nu;
+    const int nx = NX > 0 ? NX : v.d.nx, nu = v.d.nu, Nh = v.d.Nh, Ns = v.d.Ns, Nr = v.d.Nr, nv = nx + nu;
     const size_t ik0 = (size_t) i * Nh;
     double *dmu = v.dmu + ik0 * nx;
     for (int e = lane; e < Nh * nx; e += 32)
@@ -890,7 +898,7 @@ __device__ double sd_delta_mu_scenario(const SdView &v, int i, const WarpScratch
         dmu[e] = val;
     }
     __syncwarp();
-    sd_banded_solve(v, i, dmu, dmu, S, lane);
+    sd_banded_solve<NX>(v, i, dmu, dmu, S, lane);
     double part = 0.0;
     for (int e = lane; e < Nh * nv; e += 32)
     {
@@ -1039,7 +1047,12 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
         if (v.o.termCondition == 1) err = sqrt(err);
         if (err < v.o.tol) { status = 0; break; }
 
-        for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario(v, i, S, tm.lane);
+        /* the scenario-local chains are instantiated for the state dimensions of the reference's
+         * examples (spring-mass nx = 4, linear_chain nm = 4 -> nx = 8): constant trip counts and
+         * index arithmetic, same operation order as the runtime-dimension instance */
+        if (v.fixed_nx == 4) for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario<4>(v, i, S, tm.lane);
+        else if (v.fixed_nx == 8) for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario<8>(v, i, S, tm.lane);
+        else for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario<0>(v, i, S, tm.lane);
         team_sync();
         PHASE(2);
         if (Ns > 1)
@@ -1060,7 +1073,9 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
         }
         PHASE(3);
         double dot = 0.0;
-        for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario(v, i, S, tm.lane);
+        if (v.fixed_nx == 4) for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario<4>(v, i, S, tm.lane);
+        else if (v.fixed_nx == 8) for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario<8>(v, i, S, tm.lane);
+        else for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario<0>(v, i, S, tm.lane);
         for (int e = tm.tid; e < nl; e += tm.T) dot += v.resNA[e] * v.dlam[e];
         /* the reduction's barrier also publishes dxU/duU/dmu; f(0) needs only this scenario's own
          * data for x but all of it is team-visible after the barrier, so evaluate f0 afterwards */
@@ -1189,6 +1204,13 @@ static int sd_build_device(tqb_sd_device *D, const int *h_int)
     {
         const char *e = getenv("TREEQP_B200_GENERIC_JAY");
         v.no_small_jay = (e && e[0] == '1') ? 1 : 0;
+    }
+    {
+        /* TREEQP_B200_GENERIC_NX: 1 = runtime-dimension chains, 0 = the nx = 4 / 8 instances;
+         * unset = TQB_SD_FIXED_NX_DEFAULT */
+        const char *e = getenv("TREEQP_B200_GENERIC_NX");
+        const int fixed = (e && (e[0] == '0' || e[0] == '1')) ? e[0] == '0' : TQB_SD_FIXED_NX_DEFAULT;
+        v.fixed_nx = (fixed && (d->nx == 4 || d->nx == 8)) ? d->nx : 0;
     }
     if (v.jay_in_smem && jay > sm) sm = jay;
     D->smem = sm * 8;
