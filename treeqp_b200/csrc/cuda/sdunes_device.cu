@@ -67,7 +67,7 @@ struct SdView
     double *jarena;                   /* operands of the J chain when they do not fit in shared memory */
     int jay_in_smem;
     int no_small_jay;                 /* TREEQP_B200_GENERIC_JAY=1: always the generic chain walk */
-    int fixed_nx;                     /* 4 / 8: compile-time-dimension scenario chains; 0: runtime (TREEQP_B200_GENERIC_NX=1) */
+    int fixed_nx;                     /* 4 / 8 / 16: compile-time-dimension scenario chains; 0: runtime (TREEQP_B200_GENERIC_NX=1) */
 };
 
 struct Team
@@ -314,7 +314,7 @@ __device__ __forceinline__ WarpScratch warp_scratch(const SdView &v, double *bas
  * out = Lambda_i^-1 in (in may alias out).  One element per lane (nx <= 32); the factor blocks of
  * the next stage are prefetched while the current stage is substituted. */
 #ifndef TQB_SD_FIXED_NX_DEFAULT
-#define TQB_SD_FIXED_NX_DEFAULT 0
+#define TQB_SD_FIXED_NX_DEFAULT 1
 #endif
 
 template <int NX>
@@ -1048,10 +1048,11 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
         if (err < v.o.tol) { status = 0; break; }
 
         /* the scenario-local chains are instantiated for the state dimensions of the reference's
-         * examples (spring-mass nx = 4, linear_chain nm = 4 -> nx = 8): constant trip counts and
+         * examples (spring-mass nx = 4, linear_chain nm = 4 / 8 -> nx = 8 / 16): constant trip counts and
          * index arithmetic, same operation order as the runtime-dimension instance */
         if (v.fixed_nx == 4) for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario<4>(v, i, S, tm.lane);
         else if (v.fixed_nx == 8) for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario<8>(v, i, S, tm.lane);
+        else if (v.fixed_nx == 16) for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario<16>(v, i, S, tm.lane);
         else for (int i = tm.gw; i < Ns; i += tm.W) sd_factor_scenario<0>(v, i, S, tm.lane);
         team_sync();
         PHASE(2);
@@ -1075,6 +1076,7 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
         double dot = 0.0;
         if (v.fixed_nx == 4) for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario<4>(v, i, S, tm.lane);
         else if (v.fixed_nx == 8) for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario<8>(v, i, S, tm.lane);
+        else if (v.fixed_nx == 16) for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario<16>(v, i, S, tm.lane);
         else for (int i = tm.gw; i < Ns; i += tm.W) dot += sd_delta_mu_scenario<0>(v, i, S, tm.lane);
         for (int e = tm.tid; e < nl; e += tm.T) dot += v.resNA[e] * v.dlam[e];
         /* the reduction's barrier also publishes dxU/duU/dmu; f(0) needs only this scenario's own
@@ -1206,11 +1208,11 @@ static int sd_build_device(tqb_sd_device *D, const int *h_int)
         v.no_small_jay = (e && e[0] == '1') ? 1 : 0;
     }
     {
-        /* TREEQP_B200_GENERIC_NX: 1 = runtime-dimension chains, 0 = the nx = 4 / 8 instances;
+        /* TREEQP_B200_GENERIC_NX: 1 = runtime-dimension chains, 0 = the nx = 4 / 8 / 16 instances;
          * unset = TQB_SD_FIXED_NX_DEFAULT */
         const char *e = getenv("TREEQP_B200_GENERIC_NX");
         const int fixed = (e && (e[0] == '0' || e[0] == '1')) ? e[0] == '0' : TQB_SD_FIXED_NX_DEFAULT;
-        v.fixed_nx = (fixed && (d->nx == 4 || d->nx == 8)) ? d->nx : 0;
+        v.fixed_nx = (fixed && (d->nx == 4 || d->nx == 8 || d->nx == 16)) ? d->nx : 0;
     }
     if (v.jay_in_smem && jay > sm) sm = jay;
     D->smem = sm * 8;
