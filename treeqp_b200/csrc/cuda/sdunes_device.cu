@@ -180,9 +180,10 @@ __device__ void sd_stage_solve(const SdView &v, const Team &tm, bool with_cal)
  *   Zbar = B RinvCal,  LambdaD[k] = Zbar B' + QinvCal[k] + A QinvCal[k-1] A',  LambdaL[k-1] = -A QinvCal[k-1]
  * (stored transposed when reverse).  Returns this thread's part of the termination norm.
  * ---------------------------------------------------------------------------------------- */
+template <int NX>
 __device__ double sd_build(const SdView &v, const Team &tm)
 {
-    const int nx = v.d.nx, nu = v.d.nu, Nh = v.d.Nh, nxx = nx * nx;
+    const int nx = NX > 0 ? NX : v.d.nx, nu = v.d.nu, Nh = v.d.Nh, nxx = nx * nx;
     const double *x = v.out.xs, *u = v.out.us;
     const bool is_max = v.o.termCondition == 2;
     double part = 0.0;
@@ -1041,7 +1042,8 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
         sd_stage_solve(v, tm, true);
         team_sync();
         PHASE(0);
-        double err = sd_build(v, tm), dummy = 0.0;
+        double err = v.fixed_nx == 4 ? sd_build<4>(v, tm) : v.fixed_nx == 8 ? sd_build<8>(v, tm)
+                   : v.fixed_nx == 16 ? sd_build<16>(v, tm) : sd_build<0>(v, tm), dummy = 0.0;
         team_reduce2(v, tm, err, dummy, v.o.termCondition == 2, s_red);
         PHASE(1);
         if (v.o.termCondition == 1) err = sqrt(err);
