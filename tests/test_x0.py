@@ -93,3 +93,53 @@ def test_update_x0_matches_full_upload(eliminated, product_lib):
     assert s.download(qo) == capi.TREEQP_OK
     assert CS.rel_err(qo.x, x) < 1e-12
     s.destroy()
+
+
+@pytest.mark.gpu
+def test_warm_start_survives_update_x0(product_lib):
+    """warm_start_resident BEFORE update_x0: the x0 update must not overwrite the device-resident dual
+    start of the root's children with the stale host copy (zeros)"""
+    L = product_lib
+    prob = P.spring_mass(3, 2, 10, x0=X0A, xmax1=0.2)
+    qi = capi.QpIn(L, prob)
+    qi.eliminate_x0()
+    dims = P.eliminate_x0(prob)
+    qo = capi.QpOut(L, dims)
+    s = capi.Tdunes(L, qi)
+    s.set_dual_initialization(np.zeros(dims.n_lambda))
+    assert s.upload() == capi.TREEQP_OK and s.solve_resident() == 0
+    cold_iters = s.stats()["iter"]
+    assert s.download(qo) == capi.TREEQP_OK
+    lam, x = qo.lam.copy(), qo.x.copy()
+    # order A (the one that used to lose the warm start): warm start, THEN the x0 update (same x0)
+    assert s.warm_start_resident() == capi.TREEQP_OK
+    qi.set_x0(X0A)
+    assert s.update_x0() == capi.TREEQP_OK
+    assert s.solve_resident() == 0
+    assert s.stats()["iter"] == 0, "dual start was overwritten by update_x0 (cold start needs %d iterations)" % cold_iters
+    assert s.download(qo) == capi.TREEQP_OK
+    assert CS.rel_err(qo.lam, lam) < 1e-14 and CS.rel_err(qo.x, x) < 1e-12
+    s.destroy()
+
+
+@pytest.mark.gpu
+def test_second_solve_continues_from_last_multipliers(product_lib, ref_lib):
+    """The reference iterates work->slambda in place (dual_Newton_tree.c:966): treeqp_tdunes_solve called
+    again WITHOUT set_dual_initialization starts from the multipliers of the previous solve.  Same
+    sequence of calls on both libraries, truncated first solve so that the second one has work to do."""
+    prob = P.spring_mass(3, 2, 10, x0=X0A, xmax1=0.2)
+    res = {}
+    for name, lib in (("ours", product_lib), ("ref", ref_lib)):
+        qi, qo = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+        s = capi.Tdunes(lib, qi, maxIter=10)
+        s.set_dual_initialization(np.zeros(prob.n_lambda))
+        seq = []
+        for _ in range(7):   # 58 Newton iterations in slices of 10: (1, 10) x 5, (0, 8), (0, 0)
+            st = s.solve(qo)
+            seq.append((int(st), int(qo.iter)))
+        res[name] = (seq, qo.x.copy(), qo.lam.copy())
+        if lib is product_lib:
+            s.destroy()
+    assert res["ours"][0] == res["ref"][0], (res["ours"][0], res["ref"][0])
+    assert res["ref"][0][0] == (1, 10) and res["ref"][0][-1] == (0, 0)
+    assert CS.rel_err(res["ours"][1], res["ref"][1]) < 1e-10 and CS.rel_err(res["ours"][2], res["ref"][2]) < 1e-10

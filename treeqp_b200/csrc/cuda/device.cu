@@ -89,6 +89,14 @@ struct tqb_device
 
 extern "C" const char *tqb_cuda_last_error(void) { return g_err; }
 
+#ifdef TQB_BF_TIMING
+/* debug builds only: the phase stamps of k_build_factor (tdunes_fused.cuh), 32 slots x 16 values */
+extern "C" int tqb_debug_bf_timing(long long *out)
+{
+    return cudaMemcpyFromSymbol(out, g_bf_t, sizeof(long long) * 32 * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 extern "C" int tqb_cuda_device_count(void)
 {
     int n = 0;

@@ -86,6 +86,26 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+/* -DTQB_BF_TIMING: thread 0 of CTA 0 leaves clock64 / globaltimer stamps of the phases of its block
+ * (slot = 0 for the root level, else 1 + log2(gridDim.x)); read back with tqb_debug_bf_timing */
+#ifdef TQB_BF_TIMING
+__device__ long long g_bf_t[32][16];
+__device__ __forceinline__ void bf_stamp(bool root, int i)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+    {
+        long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        const int slot = root ? 0 : 32 - __clz(gridDim.x);
+        g_bf_t[slot][i] = clock64();
+        g_bf_t[slot][8 + i] = gt;
+    }
+}
+#define BF_STAMP(i) bf_stamp(ROOT, i)
+#else
+#define BF_STAMP(i)
+#endif
+
 #ifndef TQB_BF_MINBLOCKS
 #define TQB_BF_MINBLOCKS 4
 #endif
@@ -117,6 +137,7 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
         if (wait_here) { pdl_wait(); pdl_release(); }
         return;
     }
+    BF_STAMP(1);
 
     /* Ms[j][r] = column j of the factored augmented matrix */
     double *Cp = Ms;                              /* Cp[K][c] = p_c * C[K][c] (build phase only) */
@@ -308,7 +329,9 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
         }
         }
         /* ---- everything below needs the kids' level ---- */
+        BF_STAMP(2);
         if (attempt == 0 && wait_here) { pdl_wait(); pdl_release(); }
+        BF_STAMP(3);
         rr = res - ((kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0);
         if (isW)
         {
@@ -331,6 +354,7 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
         }
         small = false;
         __syncwarp(); /* Cp is dead, Ms may be written */
+        BF_STAMP(4);
         /* ---- right-looking Cholesky of the augmented matrix ---- */
 #pragma unroll
         for (int j = 0; j < D; j++)
@@ -402,6 +426,7 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
                 }
             }
         }
+        BF_STAMP(5);
         if (!(v.o.regType == 2 && attempt == 0 && small)) break;
         if (lane == 0) atomicAdd(&v.counters[2], 1);
         __syncwarp();
@@ -427,6 +452,7 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
         for (int r = 0; r < D; r++)
             if (lane <= r) Lg[(r * (r + 1)) / 2 + lane] = Ms[lane * LDR + r];
     }
+    BF_STAMP(6);
     if (!ROOT)
     {
         if (isW) v.dlam[xb + lane] = rr;
@@ -504,6 +530,7 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
         }
         if (isW) v.dlam[xb + lane] = rr;
     }
+    BF_STAMP(7);
 }
 
 template <int NX, int NU, int MD, int PNX, bool ROOT>
@@ -513,6 +540,7 @@ __global__ void __launch_bounds__(128, tqb_bf_minblocks(NX * MD)) k_build_factor
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = blockIdx.x * wpb + wib;
+    BF_STAMP(0);
     /* pre_ok = 0: the launch before this one wrote data read by the build phase (k_stage<0> before
      * the bottom level, the cut-node exchange of a sharded solve): wait first */
     if (!pre_ok) { pdl_wait(); pdl_release(); }

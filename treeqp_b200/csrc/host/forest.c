@@ -400,7 +400,9 @@ void tqb_forest_pack(tqb_forest *f, int t, const tree_qp_in *qp) { tqb_forest_pa
 
 /* H2D of the slices of every input array that belong to forest nodes [ga, gb): the offset tables
  * are prefix sums over the node order, so each slice is one contiguous range */
-static int upload_nodes(tqb_forest *f, int ga, int gb)
+/* with_lam0 = 0: the dual start is left alone (an x0 update must not overwrite a device-resident warm
+ * start with the stale host copy) */
+static int upload_nodes(tqb_forest *f, int ga, int gb, int with_lam0)
 {
     const tqb_tables *T = &f->ht;
     const tqb_dims *d = &f->dims;
@@ -413,7 +415,7 @@ static int upload_nodes(tqb_forest *f, int ga, int gb)
     int rc = 0;
     rc |= tqb_device_upload_range(f->dev, f->h_in, (in->A - f->h_in) + a0, a1 - a0);
     rc |= tqb_device_upload_range(f->dev, f->h_in, (in->B - f->h_in) + b0, b1 - b0);
-    const double *xs[] = {in->b, in->q, in->Qd, in->Qinv, in->xmin, in->xmax, in->lam0, in->dxmin, in->dxmax};
+    const double *xs[] = {in->b, in->q, in->Qd, in->Qinv, in->xmin, in->xmax, with_lam0 ? in->lam0 : NULL, in->dxmin, in->dxmax};
     const double *us[] = {in->r, in->Rd, in->Rinv, in->umin, in->umax, in->dumin, in->dumax};
     for (unsigned i = 0; i < sizeof xs / sizeof xs[0]; i++)
         if (xs[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (xs[i] - f->h_in) + x0, x1 - x0);
@@ -427,7 +429,7 @@ int tqb_forest_update_nodes(tqb_forest *f, int t, const tree_qp_in *qp, int j0, 
     const int g0 = f->ht.tnode0[t];
     pack_range(f, t, qp, NULL, j0, j1);
     int rc = tqb_device_upload_begin(f->dev);
-    rc |= upload_nodes(f, g0 + j0, g0 + j1);
+    rc |= upload_nodes(f, g0 + j0, g0 + j1, 0);
     rc |= tqb_device_upload_end(f->dev, &f->h2d_ms);
     return rc;
 }
@@ -465,7 +467,7 @@ int tqb_forest_pack_upload(tqb_forest *f, const tree_qp_in *const *qp, double *t
         {
             const int j0 = (int) ((long long) N * c / nstage), j1 = (int) ((long long) N * (c + 1) / nstage);
             pack_range(f, 0, qp[0], NULL, j0, j1);
-            rc |= upload_nodes(f, j0, j1);
+            rc |= upload_nodes(f, j0, j1, 1);
         }
     }
     else
@@ -476,7 +478,7 @@ int tqb_forest_pack_upload(tqb_forest *f, const tree_qp_in *const *qp, double *t
             if (t1 == t0) continue;
 #pragma omp parallel for schedule(dynamic, 8) if (t1 - t0 > 32)
             for (int t = t0; t < t1; t++) tqb_forest_pack(f, t, qp[t]);
-            rc |= upload_nodes(f, T->tnode0[t0], T->tnode0[t1]);
+            rc |= upload_nodes(f, T->tnode0[t0], T->tnode0[t1], 1);
         }
     }
     /* dense Hessian blocks: offsets exist only for the dense nodes, sent as one range at the end */

@@ -34,6 +34,7 @@ typedef struct tqb_sd_ctx
     int *node_nx, *node_nu; /* actual per-node dimensions (root nx = 0, leaves nu = 0) */
     tqb_sd_device *dev;
     int uploaded, dual_dirty;
+    int solved; /* a Newton loop has run: hout.lam_s / mu_s hold its final multipliers */
     /* statistics of the last solve */
     double gpu_ms, h2d_ms, d2h_ms, pack_ms;
     long long launches;
@@ -547,6 +548,13 @@ return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdun
         fprintf(stderr, "[treeqp_b200] treeqp_sdunes_solve: workspace has no device arena (no GPU?)\n");
         return TREEQP_UNKNOWN_ERROR;
     }
+    if (ctx->solved && !ctx->dual_dirty)
+    {   /* the reference iterates work->slambda / work->smu in place (scenarios.c:1172-1186): without a
+         * new set_dual_initialization the next solve continues from the last multipliers */
+        const tqb_sd_dims *d = &ctx->dims;
+        if (d->nl > 0) memcpy(ctx->hin.lam0, ctx->hout.lam_s, sizeof(double) * (size_t) d->nl);
+        memcpy(ctx->hin.mu0, ctx->hout.mu_s, sizeof(double) * (size_t) d->SK * d->nx);
+    }
     return_t st = treeqp_sdunes_upload(qp_in, opts, work);
     if (st != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
     const double t_solver = tqb_wall_ms();
@@ -556,6 +564,7 @@ return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdun
     if (st == TREEQP_UNKNOWN_ERROR) return st;
     qp_out->info.solver_time = 1e-3 * (t_after - t_solver);
     if (treeqp_sdunes_download(qp_out, work) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    ctx->solved = 1;
     const double t_end = tqb_wall_ms();
     qp_out->info.interface_time += 1e-3 * (t_end - t_after);
     qp_out->info.total_time = 1e-3 * (t_end - t_total);

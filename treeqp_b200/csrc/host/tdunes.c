@@ -24,6 +24,7 @@ typedef struct tqb_ctx
     tqb_forest *forest;
     int lam_dirty;  /* lambda0 changed on the host since the last upload */
     int uploaded;   /* problem data present on the device */
+    int solved;     /* a Newton loop has run: the device holds its final multipliers */
     return_t last_status;
 } tqb_ctx;
 
@@ -307,6 +308,7 @@ return_t treeqp_tdunes_solve_resident(const treeqp_tdunes_opts_t *opts, treeqp_t
     forward_opts(opts, &o);
     work->lineSearchRestartCounter = 0;
     if (forest_solve(f, &o) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    ctx->solved = 1;
     ctx->last_status = (return_t) f->h_status[0];
     int it = f->h_iter[0];
     work->lsIter = (it > 0 && it <= 256) ? f->ls_iters[it - 1] : 0;
@@ -327,7 +329,7 @@ return_t treeqp_tdunes_update_x0(const tree_qp_in *qp_in, treeqp_tdunes_workspac
     const int last = n >= f->dims.Nn;
     const long long x1 = last ? f->dims.X : f->ht.xoff[n], u1 = last ? f->dims.U : f->ht.uoff[n];
     const long long a1 = last ? f->dims.szA : f->ht.aoff[n], b1 = last ? f->dims.szB : f->ht.boff[n];
-    f->h2d_bytes = (long long) sizeof(double) * (a1 + b1 + 7 * x1 + 5 * u1);
+    f->h2d_bytes = (long long) sizeof(double) * (a1 + b1 + 6 * x1 + 5 * u1);
     return TREEQP_OK;
 }
 
@@ -373,9 +375,13 @@ return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
         fprintf(stderr, "[treeqp_b200] treeqp_tdunes_solve: workspace has no device arena (no GPU?)\n");
         return TREEQP_UNKNOWN_ERROR;
     }
+    /* The reference iterates work->slambda in place (dual_Newton_tree.c:966): a solve that is not
+     * preceded by set_dual_initialization continues from the multipliers of the previous one. */
+    const int continue_duals = ctx->solved && !ctx->lam_dirty;
     /* "interface" part 1: BLASFEO views -> pinned SoA -> HBM */
     st = treeqp_tdunes_upload(qp_in, opts, work);
     if (st != TREEQP_OK) return st;
+    if (continue_duals && tqb_forest_warm_start(ctx->forest)) return TREEQP_UNKNOWN_ERROR;
     const double t_solver = tqb_wall_ms();
     qp_out->info.interface_time = 1e-3 * (t_solver - t_total);
 
