@@ -7,17 +7,20 @@ QPs, FP64).  One "step" = one complete dual Newton solve of that QP from the dua
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--depth D]
 
-  value  whole-job throughput with the QP data already resident in HBM (treeqp_tdunes_solve_resident)
-  e2e    same metric through the drop-in C-ABI call treeqp_tdunes_solve with HOST buffers
-         (BLASFEO views -> pinned SoA -> H2D -> Newton loop -> D2H -> BLASFEO views), every step
-  roofline      dominant kernel class: algorithmic bytes (SURVEY.md 8d formulas) / CUDA-event time
-  cpu_baseline  the unmodified reference (oracle/_ref, OpenMP build, all host cores) on the same QP
+  value  whole-job throughput with the QP data already resident in HBM
+         (N = 1: treeqp_tdunes_solve_resident; N > 1: the SAME tree sharded by subtree over the N GPUs,
+         treeqp_tdunes_sharded_solve_resident -- strong scaling, BASELINE config 3)
+  e2e    same metric through the call with HOST buffers (treeqp_tdunes_solve / ..._sharded_solve:
+         BLASFEO views -> pinned SoA -> H2D -> Newton loop -> D2H -> BLASFEO views), every step
+  parity the solution of the timed QP against the unmodified reference's solution of the same QP (status,
+         Newton iterations, active sets, x/u/lam/mu to 1e-10 relative); the run FAILS if it differs
+  roofline      dominant kernel class: SURVEY.md 8d bytes (K2 + K3 for the fused build/factor kernel) over
+                the CUDA-event time of its launches; frac_dram = measured DRAM bytes (ncu) over the same
+                time; compute = factor/solve FLOPs over the measured FP64 peak
+  cpu_baseline  the unmodified reference (oracle/_ref, OpenMP build, all host cores) on the same QP,
+                min over 5 solves
 
-N>1: one process per GPU (torchrun), each rank solves its own copy of the same tree QP: the path
-partitions by independent QP, no data-path collective -> weak scaling.  Next to it the record carries
-ONE tree sharded by subtree over the N GPUs (strong scaling, NCCL exchange of the cut-node Schur
-complements) and the 4096-QP batch split over the ranks.
---impl reference: times the reference's own CPU implementation (rank 0 only).
+--impl reference: times the reference's own CPU implementation (rank 0 only, all host cores).
 """
 import argparse
 import json
@@ -47,7 +50,9 @@ OPTS = dict(maxIter=200)
 
 # ------------------------------------------------------------------ algorithmic bytes
 def algorithmic_bytes(prob):
-    """bytes each kernel class must move per call, from the problem dimensions only"""
+    """bytes each phase must move per call, from the problem dimensions only: the K1..K5 formulas of
+    SURVEY.md 8(d) verbatim (doubles x 8), plus the vector streams of one line-search pass and the
+    factor + substitution FLOPs of the same section"""
     nx, nu, nk = prob.nx.astype(np.int64), prob.nu.astype(np.int64), prob.nk.astype(np.int64)
     dad = prob.dad
     Nn = prob.Nn
@@ -56,24 +61,97 @@ def algorithmic_bytes(prob):
     kid_ab = np.bincount(dad[1:], weights=ab[1:], minlength=Nn).astype(np.int64)
     d = np.bincount(dad[1:], weights=nx[1:], minlength=Nn).astype(np.int64)
     par = nk > 0
-    nonroot_par = par.copy(); nonroot_par[0] = False
-    k1 = 8 * int(((5 * nx + 4 * nu) + kid_ab + 2 * d + 5 * nx + 5 * nu + 1).sum())   # k_stage<0>
-    k5 = 8 * int((2 * nx + kid_ab + 2 * d + nx + nu + 2).sum())                        # k_stage<2>
-    trial = 8 * int(6 * nx.sum() + 6 * nu.sum() + 2 * Nn)                               # k_trial
-    grad = 8 * int((ab[1:] + 4 * nx[1:] + nx[dad[1:]] + nu[dad[1:]]).sum())
-    hess = 8 * int((kid_ab + nx + nu + d + d * (d + 1) // 2)[par].sum() + (nx * d)[nonroot_par].sum())
-    k3 = 8 * int((d * (d + 1) + 2 * d)[par].sum() + (2 * nx * d + nx * (nx + 1) + 2 * nx)[nonroot_par].sum())
-    k4 = 8 * int((d * (d + 1) // 2 + 2 * d)[par].sum() + (nx * d + nx)[nonroot_par].sum())
-    return {"k_stage<0>": k1, "k_stage<2>": k5, "k_trial": trial, "k_gradient": grad, "k_hessian": hess,
-            "k_factor_level": k3, "k_backsolve_level": k4}
+    nrp = par.copy(); nrp[0] = False            # non-root parents
+    k1 = 8 * int(((5 * nx + 4 * nu) + kid_ab + d + 4 * nx + 4 * nu).sum())
+    k2 = 8 * int((ab[1:] + 4 * nx[1:]).sum() + (2 * nx + 2 * nu + d * (d + 1) // 2)[par].sum() + (nx * d)[nrp].sum())
+    k3 = 8 * int((d * (d + 1) + 2 * d)[par].sum() + (2 * nx * d + nx * (nx + 1) + 2 * nx)[nrp].sum())
+    k4 = 8 * int((d * (d + 1) // 2 + 2 * d)[par].sum() + (nx * d + nx)[nrp].sum())
+    k5 = 8 * int(((6 * nx + 5 * nu) + kid_ab + 2 * d + nx + nu).sum())
+    model = 8 * int((2 * nx + kid_ab + 2 * d + nx + nu + 2).sum())      # k_stage<2>: affine direction model
+    trial = 8 * int(6 * nx.sum() + 6 * nu.sum() + 2 * Nn)               # one k_ls_eval pass (vectors only)
+    flops = int((d ** 3 // 3 + 3 * d * d)[par].sum() + (nx * d * d + nx * nx * d + 2 * nx * d)[nrp].sum())
+    return {"K1": k1, "K2": k2, "K3": k3, "K4": k4, "K5": k5, "model": model, "trial": trial, "factor_flops": flops,
+            "iteration_L1": k1 + k2 + k3 + k4 + 2 * k5}
 
 
-def launches_per_call(prob):
+def class_bytes(alg, fused):
+    """algorithmic bytes per CALL of each event class (names of device.cu)"""
+    if fused:
+        return {"k_stage_fused<0>": alg["K1"], "k_stage_fused<2>": alg["model"], "k_ls_eval": alg["trial"],
+                "k_build_factor": alg["K2"] + alg["K3"], "k_backsolve_fused": alg["K4"]}
+    return {"k_stage<0>": alg["K1"], "k_stage<2>": alg["model"], "k_trial": alg["trial"],
+            "k_gradient+k_hessian": alg["K2"], "k_factor_level": alg["K3"], "k_backsolve_level": alg["K4"]}
+
+
+def launches_per_call(prob, kern):
     """how many launches make up ONE call of each phase (level kernels: one per depth)"""
     stage = P.tree_tables(prob.nk)[1]
     Nh = int(stage.max())
-    return {"k_stage<0>": 1, "k_stage<2>": 1, "k_trial": 1, "k_gradient": 1, "k_hessian": 1,
-            "k_factor_level": Nh, "k_backsolve_level": max(Nh - 1, 1)}
+    out = {k: 1 for k in kern}
+    for k in ("k_build_factor", "k_factor_level"):
+        out[k] = Nh
+    for k in ("k_backsolve_fused", "k_backsolve_level"):
+        out[k] = max(Nh - 1, 1)
+    return out
+
+
+def measured_peaks():
+    """HBM GB/s from the driver's MEASURED_PEAKS.json; FP64 TFLOP/s from this repo's own microbenchmark
+    (tools/micro/dmma_rate.cu on a B200 of this pool, profiles/r02_micro_fp64_peak.txt: DFMA 33.9, DMMA 37.1)"""
+    hbm, src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm, src = float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        pass
+    return hbm, src, 33.9, "measured DFMA rate, tools/micro/dmma_rate.cu (profiles/r02_micro_fp64_peak.txt)"
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    if b.size == 0:
+        return 0.0
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+def parity_block(prob, sol, ref, against):
+    """sol / ref: dicts with status, iter, x, u, lam, mu_x, mu_u (flat).  north_star bar: identical status,
+    Newton iteration count and active sets; primal/dual solution within 1e-10 relative"""
+    errs = {k: rel_err(sol[k], ref[k]) for k in ("x", "u", "lam", "mu_x", "mu_u")}
+    act = True
+    n_active = 0
+    for k, lo, hi in (("x", prob.xmin, prob.xmax), ("u", prob.umin, prob.umax)):
+        act = act and bool(np.array_equal(sol[k] == lo, ref[k] == lo)) and bool(np.array_equal(sol[k] == hi, ref[k] == hi))
+        n_active += int((ref[k] == lo).sum() + (ref[k] == hi).sum())
+    ok = (int(sol["status"]) == int(ref["status"]) and int(sol["iter"]) == int(ref["iter"]) and act
+          and all(e < 1e-10 for e in errs.values()))
+    return {"ok": bool(ok), "against": against, "tolerance": 1e-10, "status": [int(sol["status"]), int(ref["status"])],
+            "newton_iters": [int(sol["iter"]), int(ref["iter"])], "active_sets_identical": bool(act), "active_bounds": n_active,
+            "max_rel_err": {k: float("%.3e" % v) for k, v in errs.items()}}
+
+
+def out_dict(qp_out, status):
+    return {"status": int(status), "iter": int(qp_out.iter), "x": qp_out.x, "u": qp_out.u, "lam": qp_out.lam,
+            "mu_x": qp_out.mu_x, "mu_u": qp_out.mu_u}
+
+
+def omp_threads(n=None):
+    """set (n given) and read the thread count the OpenMP runtime will really use"""
+    import ctypes
+    try:
+        g = ctypes.CDLL("libgomp.so.1")
+        if n:
+            g.omp_set_num_threads(int(n))
+        return int(g.omp_get_max_threads())
+    except Exception:
+        return None
+
+
+def config_dict(depth, Nn, n_gpus):
+    """identical in both arms: the workload BASELINE.json's metric is quoted on"""
+    return {"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, FP64, dual start 0, maxIter 200" % (depth, Nn),
+            "sharding": "one GPU" if n_gpus == 1 else "the one tree sharded by subtree over %d GPUs" % n_gpus,
+            "l2": "inputs 0.30 GB + iterates/factors per solve, all >> 126 MB L2: no flush between steps"}
 
 
 # ------------------------------------------------------------------------------ clock sampling
@@ -174,7 +252,8 @@ def ref_lib_path(omp=True):
 
 
 def run_reference_solve(prob, max_iter=None):
-    """one treeqp_tdunes_solve of the UNMODIFIED reference (OpenMP build, all host cores)"""
+    """treeqp_tdunes_solve of the UNMODIFIED reference (OpenMP build, all host cores): returns a closure
+    that solves once from lambda = 0 and the qp_out it fills"""
     path = ref_lib_path(True)
     lib = capi.TreeQpLib(path)
     qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
@@ -189,6 +268,8 @@ def run_reference_solve(prob, max_iter=None):
         t = time.perf_counter()
         st = solver.solve(qp_out)
         return time.perf_counter() - t, st, qp_out.iter
+    once.qp_out = qp_out
+    once.keep = (lib, qp_in, solver)
     return once
 
 
@@ -197,15 +278,18 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # torchrun exports OMP_NUM_THREADS=1 to every rank: the reference gets ALL host cores, set before
+    # its library (and with it the OpenMP runtime) is loaded, and checked against the runtime afterwards
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    prob = workload(args.depth, 0)
     base = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic"}
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.depth, prob.Nn, args.gpus)}
     if ref_lib_path(True) is None:
         print(json.dumps(dict(base, unavailable="oracle/_ref/libtreeqp_ref_omp.so missing (built from /root/reference)")))
         return
-    prob = workload(args.depth, 0)
     once = run_reference_solve(prob)
+    threads = omp_threads(cores)
     t_full, st, iters_full = once()  # untimed probe = first warm-up step, full solve
     budget = 240.0
     total_steps = args.steps + max(args.warmup - 1, 0)
@@ -226,11 +310,25 @@ def reference_arm(args):
     value = 1.0 / sec
     print(json.dumps(dict(
         base, value=value, ms_per_step=1e3 * sec, us_per_newton_iter=1e6 * sec / iters_full,
-        config={"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, 1 tree per GPU" % (args.depth, prob.Nn),
-                "newton_iters": iters_full, "status": st, "parallelism": "reference CPU implementation, OpenMP over nodes/blocks, rank 0 only"},
-        cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        detail={"newton_iters": iters_full, "status": st, "best_ms": 1e3 * float(np.min(times)),
+                "parallelism": "reference CPU implementation, OpenMP over nodes/blocks, rank 0 only, %s OpenMP threads" % threads},
+        cpu_baseline={"value": value, "unit": UNIT, "cores": threads or cores, "host_cores": cores, "kind": "reference", "sample": sample},
         e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         gpu_launches=0)))
+
+
+def solve_roofline(prob, newton_iters_total, seconds, io_bytes, ls_per_iter=1.0):
+    """whole-solve HBM roofline of a secondary workload: SURVEY 8(d) bytes of one Newton iteration
+    (K1+K2+K3+K4+(L+1)K5, L = line-search trials per iteration) x iterations over the resident time,
+    next to the compulsory traffic (inputs + outputs once per solve) for the on-chip regime"""
+    hbm, hbm_src, _, _ = measured_peaks()
+    alg = algorithmic_bytes(prob)
+    per_it = alg["K1"] + alg["K2"] + alg["K3"] + alg["K4"] + (ls_per_iter + 1.0) * alg["K5"]
+    ach = per_it * newton_iters_total / seconds / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+            "bytes_per_newton_iter_per_qp": per_it, "newton_iters_total": newton_iters_total,
+            "compulsory_io_GBps": io_bytes / seconds / 1e9, "peak_source": hbm_src,
+            "note": "small trees are latency/on-chip bound: SURVEY 8(d) asks for the HBM line for batch throughput"}
 
 
 # ----------------------------------------------------------------- secondary workloads (N = 1)
@@ -261,7 +359,9 @@ def bench_batch(lib, n=4096, reps=3, rank=0, world=1, barrier=None, max_over_ran
     out = {"workload": "%d x linear_chain nm=4 nu=3 md=3 Nr=2 Nh=20 (175 nodes), |u|<=0.5, x0 seeded%s" % (n, "" if world == 1 else ", %d per GPU" % nl),
            "qp_per_s_resident": n / min(t_res), "qp_per_s_e2e": n / min(t_e2e), "ms_per_batch_resident": 1e3 * min(t_res),
            "ms_per_batch_e2e": 1e3 * min(t_e2e), "newton_iters_max": int(iters.max()), "newton_iters_median": float(np.median(iters)),
-           "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "launches": st["kernel_launches"]}
+           "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "launches": st["kernel_launches"],
+           "roofline": solve_roofline(probs[0], int(iters.sum()) * world, min(t_res), (st["h2d_bytes"] + st["d2h_bytes"]) * world,
+                                      st["ls_total"] / max(int(iters.sum()), 1))}
     if world > 1:
         out["scaling"] = "strong (4096 QPs in total)"
     path = ref_lib_path(False)
@@ -298,7 +398,9 @@ def bench_sdunes(lib, reps=10):
     out = {"workload": "spring-mass SDUNES md=3 Nr=4 Nh=20 (81 scenarios, 1417 nodes)", "status": st, "newton_iters": qp_out.iter,
            "ms_per_solve_resident": best, "ms_per_solve_e2e": e2e, "solves_per_s_resident": 1e3 / best,
            "us_per_newton_iter": 1e3 * best / max(qp_out.iter, 1), "kernel_launches": stats["kernel_launches"],
-           "phases_ms": {k: round(v[0], 4) for k, v in stats["kernels"].items()}}
+           "phases_ms": {k: round(v[0], 4) for k, v in stats["kernels"].items()},
+           "roofline": solve_roofline(prob, int(qp_out.iter), 1e-3 * best, stats["h2d_bytes"] + stats["d2h_bytes"],
+                                      stats["ls_total"] / max(int(qp_out.iter), 1))}
     path = ref_lib_path(False)
     if path:
         ref = capi.TreeQpLib(path)
@@ -343,6 +445,9 @@ def bench_dense(lib, reps=5):
         rec = {"nodes": int(prob.Nn), "status": int(st), "newton_iters": int(qp_out.iter), "ms_per_solve_resident": best,
                "ms_per_solve_e2e": e2e, "us_per_newton_iter": 1e3 * best / max(qp_out.iter, 1),
                "kkt": float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))}
+        sst = s.stats()
+        rec["roofline"] = solve_roofline(prob, int(qp_out.iter), 1e-3 * best, sst["h2d_bytes"] + sst["d2h_bytes"],
+                                         sst["ls_total"] / max(int(qp_out.iter), 1))
         s.destroy()
         if ref is not None:
             rin, rout = capi.QpIn(ref, prob), capi.QpOut(ref, prob)
@@ -438,39 +543,162 @@ def bench_mpc(lib, steps=20):
     return out
 
 
-def bench_sharded(lib, args, rank, world, local, dist, barrier, max_over_ranks):
-    """N > 1: ONE tree (the N=1 workload) sharded by subtree over the ranks: strong scaling"""
+def run_single(lib, args, prob, barrier, max_over_ranks, clocks, rank):
+    """N = 1 headline (and, at N > 1, the replica line: every rank solves its own copy of the tree)"""
+    qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+    solver = capi.Tdunes(lib, qp_in, **OPTS)
+    lam0 = np.zeros(prob.n_lambda)
+    solver.set_dual_initialization(lam0)
+    # ---- resident (inputs already in HBM): value
+    assert solver.upload() == capi.TREEQP_OK
+    for _ in range(args.warmup):
+        st = solver.solve_resident()
+    barrier()
+    clk_lo = clocks.mark()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        st = solver.solve_resident()
+        dev_ms += solver.stats()["gpu_ms"]
+    barrier()
+    t_res = max_over_ranks(time.perf_counter() - t0)
+    stats = solver.stats()
+    assert st == 0, "benchmark QP did not converge: status %d" % st
+    # ---- end to end through the drop-in call with host buffers
+    for _ in range(min(args.warmup, 1)):
+        solver.set_dual_initialization(lam0)
+        solver.solve(qp_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        solver.set_dual_initialization(lam0)
+        st2 = solver.solve(qp_out)
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_stats = solver.stats()
+    clk_hi = clocks.mark()
+    assert st2 == 0 and qp_out.iter == stats["iter"]
+    kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
+    kkt_dev = solver.kkt_resident()  # the same certificate evaluated on the device (k_kkt)
+    # ---- one profiled solve (CUDA events around every launch) for the roofline block
+    lib.lib.treeqp_b200_set_profiling(1)
+    solver.solve_resident()
+    prof = solver.stats()
+    lib.lib.treeqp_b200_set_profiling(0)
+    sol = out_dict(qp_out, st2)
+    solver.destroy()
+    return dict(t_res=t_res, t_e2e=t_e2e, dev_ms=dev_ms, stats=stats, e2e_stats=e2e_stats, prof=prof, sol=sol,
+                kkt=kkt, kkt_dev=kkt_dev, clk=(clk_lo, clk_hi), launches=stats["kernel_launches"] * args.steps)
+
+
+def run_sharded(lib, args, prob, rank, world, local, dist, barrier, max_over_ranks, clocks):
+    """N > 1 headline: ONE tree (the N=1 workload) sharded by subtree over the ranks: strong scaling"""
+    import torch
+
     def bcast(b):
         obj = [b]
         dist.broadcast_object_list(obj, src=0)
         return obj[0]
     comm = capi.Comm(lib, rank, world, local, bcast)
-    prob = workload(args.depth, 0)
     qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
     sh = capi.TdunesSharded(lib, qp_in, comm, **OPTS)
-    sh.set_dual_initialization(np.zeros(prob.n_lambda))
+    lam0 = np.zeros(prob.n_lambda)
+    sh.set_dual_initialization(lam0)
     assert sh.upload() == capi.TREEQP_OK
     for _ in range(max(args.warmup, 1)):
         st = sh.solve_resident()
     barrier()
+    clk_lo = clocks.mark()
     t0 = time.perf_counter()
+    dev_ms = 0.0
     for _ in range(args.steps):
         st = sh.solve_resident()
+        dev_ms += sh.stats()["gpu_ms"]
     barrier()
-    t = max_over_ranks(time.perf_counter() - t0)
+    t_res = max_over_ranks(time.perf_counter() - t0)
     stats, plan = sh.stats(), sh.plan()
+    assert st == 0, "benchmark QP did not converge: status %d" % st
+    # ---- end to end: every rank packs + uploads its subtrees, solves, downloads its part
+    sh.set_dual_initialization(lam0)
+    sh.solve(qp_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sh.set_dual_initialization(lam0)
+        st2 = sh.solve(qp_out)
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_stats = sh.stats()
+    clk_hi = clocks.mark()
+    assert st2 == 0 and qp_out.iter == stats["iter"]
+    # ---- assemble the solution on every rank: owned parts are disjoint, a SUM of masked vectors is the solution
+    own = capi.shard_plan(lib, qp_in, rank, world)["owned"]
+    nxm, num, lamm = np.repeat(own, prob.nx), np.repeat(own, prob.nu), np.repeat(own[1:], prob.nx[1:])
+    sol = {"status": int(st2), "iter": int(qp_out.iter)}
+    for key, mask in (("x", nxm), ("u", num), ("lam", lamm), ("mu_x", nxm), ("mu_u", num)):
+        t = torch.from_numpy(np.where(mask, getattr(qp_out, key), 0.0)).cuda()
+        dist.all_reduce(t)
+        sol[key] = t.cpu().numpy()
+    cnt = torch.tensor(own.astype(np.int64)).cuda()
+    dist.all_reduce(cnt)
+    sol["owners_per_node_ok"] = bool((cnt.cpu().numpy() == 1).all())
+    h2d = torch.tensor([float(e2e_stats["h2d_bytes"]), float(e2e_stats["d2h_bytes"])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(h2d)
+    e2e_stats = dict(e2e_stats, h2d_bytes=int(h2d[0].item()), d2h_bytes=int(h2d[1].item()))
     lib.lib.treeqp_b200_set_profiling(1)
     sh.solve_resident()
     prof = sh.stats()
     lib.lib.treeqp_b200_set_profiling(0)
     comm_ms = prof["kernels"].get("nccl+pack", (0.0, 0))
-    out = {"workload": "the N=1 tree (%d nodes) sharded by subtree over %d GPUs" % (prob.Nn, world), "scaling": "strong",
-           "status": st, "newton_iters": stats["iter"], "ls_trials": stats["ls_total"], "ms_per_solve": 1e3 * t / args.steps,
-           "solves_per_s": args.steps / t, "us_per_newton_iter": 1e6 * t / args.steps / max(stats["iter"], 1),
-           "cut_depth": plan["cut_depth"], "cut_nodes": plan["ncut"], "local_nodes": plan["n_local"],
-           "collectives_ms_per_solve": comm_ms[0], "collectives_per_solve": comm_ms[1]}
+    shard = {"cut_depth": plan["cut_depth"], "cut_nodes": plan["ncut"], "local_nodes": plan["n_local"],
+             "collectives_ms_per_solve": comm_ms[0], "collectives_per_solve": comm_ms[1],
+             "us_per_collective": 1e3 * comm_ms[0] / max(comm_ms[1], 1)}
     sh.destroy()
     comm.destroy()
+    return dict(t_res=t_res, t_e2e=t_e2e, dev_ms=dev_ms, stats=stats, e2e_stats=e2e_stats, prof=prof, sol=sol,
+                kkt=None, kkt_dev=None, clk=(clk_lo, clk_hi), launches=stats["kernel_launches"] * args.steps * world, shard=shard)
+
+
+def roofline_block(prob, prof, world, depth):
+    hbm, hbm_src, fp64, fp64_src = measured_peaks()
+    alg = algorithmic_bytes(prob)
+    kern = prof["kernels"]
+    fused = "k_build_factor" in kern
+    cb = class_bytes(alg, fused)
+    lpc = launches_per_call(prob, cb)
+    top = max((k for k in kern if k in cb), key=lambda k: kern[k][0])
+    t_ms, n_launch = kern[top]
+    calls = n_launch / lpc[top]
+    share = 1.0 / world           # a rank of a sharded solve moves its subtrees' share of the bytes
+    achieved = cb[top] * share * calls / (t_ms * 1e-3) / 1e9
+    per_kernel = {}
+    for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0]):
+        rec = {"ms": round(v[0], 4), "launches": v[1]}
+        if k in cb:
+            rec["GBps"] = round(cb[k] * share * (v[1] / lpc[k]) / (v[0] * 1e-3) / 1e9, 1)
+            rec["frac"] = round(rec["GBps"] / hbm, 3)
+        per_kernel[k] = rec
+    traffic, traffic_src = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
+        if tr.get("depth") == depth and world == 1 and top in tr["per_launch_bytes"]:
+            traffic, traffic_src = tr["per_launch_bytes"][top], tr["source"]
+    except Exception:
+        pass
+    avg_us = 1e3 * t_ms / n_launch
+    out = {"bound": "hbm", "kernel": top + (" (fused K2+K3 of SURVEY 8d, one launch per depth)" if top == "k_build_factor" else ""),
+           "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+           "traffic": traffic, "traffic_source": traffic_src,
+           "frac_dram": (traffic / (avg_us * 1e-6) / 1e9 / hbm) if traffic else None,
+           "algorithmic_bytes_per_launch": cb[top] * share / lpc[top], "peak_source": hbm_src,
+           "algorithmic_bytes_per_call": cb[top] * share, "launches_per_call": lpc[top],
+           "avg_launch_us": avg_us, "kernel_share_of_profiled_solve": t_ms / prof["gpu_ms"],
+           "note": "event times come from one solve with an event pair around every launch (launches serialised, no PDL overlap)",
+           "per_kernel": per_kernel}
+    if top in ("k_build_factor", "k_factor_level"):
+        tf = alg["factor_flops"] * share * calls / (t_ms * 1e-3) / 1e12
+        out["compute"] = {"achieved": tf, "peak": fp64, "unit": "TFLOP/s", "frac": tf / fp64, "peak_source": fp64_src,
+                          "flops_per_call": alg["factor_flops"] * share}
     return out
 
 
@@ -483,7 +711,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--depth", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (config 4 batch, config 2 SDUNES)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (config 4 batch, config 2 SDUNES, ...)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -491,8 +719,9 @@ def main():
     # host threads of the packer (OpenMP): torchrun exports OMP_NUM_THREADS=1 to every rank, which
     # would serialise the BLASFEO -> SoA conversion of the e2e path; give each rank its share of cores
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    cores = os.cpu_count() or 1
     if world > 1:
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
+        os.environ["OMP_NUM_THREADS"] = str(max(1, cores // world))
     import torch
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -508,13 +737,7 @@ def main():
 
     lib = capi.TreeQpLib(capi.PRODUCT_LIB)
     assert lib.lib.treeqp_b200_set_device(local) == 0
-    # every rank solves its own copy of the SAME QP (seed 0): per-GPU work is then identical at every
-    # N (the Newton iteration count depends on the data), which is what weak scaling compares
     prob = workload(args.depth, 0)
-    qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
-    solver = capi.Tdunes(lib, qp_in, **OPTS)
-    lam0 = np.zeros(prob.n_lambda)
-    solver.set_dual_initialization(lam0)
 
     def barrier():
         if dist is not None:
@@ -528,120 +751,69 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- resident (inputs already in HBM): value
-    assert solver.upload() == capi.TREEQP_OK
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    for _ in range(args.warmup):
-        st = solver.solve_resident()
-    barrier()
-    clk_lo = clocks.mark()
-    t0 = time.perf_counter()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        st = solver.solve_resident()
-        dev_ms += solver.stats()["gpu_ms"]
-    barrier()
-    t_res = max_over_ranks(time.perf_counter() - t0)
-    stats = solver.stats()
-    assert st == 0, "benchmark QP did not converge: status %d" % st
-    iters = stats["iter"]
-    launches = stats["kernel_launches"] * args.steps
+    if world == 1:
+        R = run_single(lib, args, prob, barrier, max_over_ranks, clocks, rank)
+    else:
+        R = run_sharded(lib, args, prob, rank, world, local, dist, barrier, max_over_ranks, clocks)
+    clk = clocks.stop(*R["clk"]) if rank == 0 else None
 
-    # ---- end to end through the drop-in call with host buffers
-    for _ in range(min(args.warmup, 1)):
-        solver.set_dual_initialization(lam0)
-        solver.solve(qp_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        solver.set_dual_initialization(lam0)
-        st2 = solver.solve(qp_out)
-    barrier()
-    t_e2e = max_over_ranks(time.perf_counter() - t0)
-    e2e_stats = solver.stats()
-    clk = clocks.stop(clk_lo, clocks.mark()) if rank == 0 else None
-    assert st2 == 0 and qp_out.iter == iters
-    kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
-    kkt_dev = solver.kkt_resident()  # the same certificate evaluated on the device (k_kkt)
-
-    # ---- roofline of the dominant kernel class: one profiled solve (CUDA events per launch)
-    lib.lib.treeqp_b200_set_profiling(1)
-    solver.solve_resident()
-    prof = solver.stats()
-    lib.lib.treeqp_b200_set_profiling(0)
-
-    sharded = None
-    if dist is not None:
-        try:
-            sharded = bench_sharded(lib, args, rank, world, local, dist, barrier, max_over_ranks)
-        except Exception as e:  # report, never hide
-            sharded = {"error": repr(e)}
-
-    batch_sharded = None
+    extra = {}
     if dist is not None and not args.no_extra:
+        # replicas: every rank solves its own copy of the tree, no collective (weak scaling of independent QPs)
         try:
-            batch_sharded = bench_batch(lib, 4096, 3, rank, world, barrier, max_over_ranks)
+            rep = run_single(lib, args, prob, barrier, max_over_ranks, ClockSampler(local), rank)
+            extra["replicas_one_tree_per_gpu"] = {
+                "workload": "every rank solves its own copy of the N=1 tree, no data-path collective", "scaling": "weak",
+                "solves_per_s_resident": world * args.steps / rep["t_res"], "solves_per_s_e2e": world * args.steps / rep["t_e2e"],
+                "ms_per_solve_resident": 1e3 * rep["t_res"] / args.steps, "ms_per_solve_e2e": 1e3 * rep["t_e2e"] / args.steps,
+                "pack_ms": rep["e2e_stats"]["pack_ms"], "h2d_ms": rep["e2e_stats"]["h2d_ms"]}
+        except Exception as e:  # report, never hide
+            extra["replicas_one_tree_per_gpu"] = {"error": repr(e)}
+        try:
+            extra["batch4096_linear_chain"] = bench_batch(lib, 4096, 3, rank, world, barrier, max_over_ranks)
         except Exception as e:
-            batch_sharded = {"error": repr(e)}
+            extra["batch4096_linear_chain"] = {"error": repr(e)}
 
     if rank != 0:
         if dist is not None:
+            dist.barrier()      # rank 0 runs the reference for the parity block meanwhile
             dist.destroy_process_group()
         return
 
-    peaks, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peaks, peak_src = float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    except Exception:
-        pass
-    alg = algorithmic_bytes(prob)
-    lpc = launches_per_call(prob)
-    kern = prof["kernels"]
-    fused = "k_hessian" not in kern
-    if fused:
-        # uniform trees run k_build_factor: dual gradient + Hessian blocks + Cholesky + Schur complement
-        # in one kernel per depth (event class "k_factor_level"), i.e. SURVEY 8d's K2 + K3 together
-        alg["k_factor_level"] = alg["k_gradient"] + alg["k_hessian"] + alg["k_factor_level"]
-    top = max((k for k in kern if k in alg), key=lambda k: kern[k][0])
-    t_ms, n_launch = kern[top]
-    calls = n_launch / lpc[top]
-    achieved = alg[top] * calls / (t_ms * 1e-3) / 1e9
-    breakdown = {k: {"ms": round(v[0], 4), "launches": v[1],
-                     "GBps": round(alg[k] * (v[1] / lpc[k]) / (v[0] * 1e-3) / 1e9, 1) if k in alg else None}
-                 for k, v in sorted(kern.items(), key=lambda kv: -kv[1][0])}
-    traffic, traffic_src = None, None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_latest.json")))
-        if tr.get("depth") == args.depth and top in tr["per_launch_bytes"]:
-            traffic, traffic_src = tr["per_launch_bytes"][top], tr["source"]
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": ("k_build_factor (fused K2+K3, one launch per depth)" if fused and top == "k_factor_level" else top),
-                "achieved": achieved, "peak": peaks, "unit": "GB/s",
-                "frac": achieved / peaks, "traffic": traffic, "traffic_source": traffic_src,
-                "algorithmic_bytes_per_launch": alg[top] / lpc[top], "peak_source": peak_src,
-                "algorithmic_bytes_per_call": alg[top], "launches_per_call": lpc[top],
-                "avg_launch_us": 1e3 * t_ms / n_launch, "kernel_share_of_solve": t_ms / prof["gpu_ms"],
-                "per_kernel": breakdown}
+    iters = R["stats"]["iter"]
+    roofline = roofline_block(prob, R["prof"], world, args.depth)
 
-    cpu_baseline = None
-    if not args.no_cpu_baseline and args.gpus == 1 and ref_lib_path(True):
-        cores = os.cpu_count() or 1
-        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    # ---- parity against the unmodified reference on the SAME QP (+ the CPU baseline at N = 1)
+    cpu_baseline, parity = None, None
+    if ref_lib_path(True) and not args.no_cpu_baseline:
+        threads = omp_threads(cores)
         once = run_reference_solve(prob)
-        t_cpu, st_cpu, it_cpu = once()
-        cpu_baseline = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": cores, "kind": "reference",
-                        "sample": "1 full solve of the same QP (%d Newton iterations, status %d), OpenMP build of the unmodified reference" % (it_cpu, st_cpu),
-                        "us_per_newton_iter": 1e6 * t_cpu / max(it_cpu, 1), "newton_iters": it_cpu}
-    elif not args.no_cpu_baseline and args.gpus == 1:
-        cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+        nrep = 5 if world == 1 else 1
+        runs = [once() for _ in range(nrep)]
+        t_cpu = min(r[0] for r in runs)
+        _, st_cpu, it_cpu = runs[-1]
+        parity = parity_block(prob, R["sol"], out_dict(once.qp_out, st_cpu),
+                              "unmodified reference (oracle/_ref, treeqp_tdunes_solve) on the same QP, %s OpenMP threads" % threads)
+        if world > 1:
+            parity["owners_per_node_ok"] = R["sol"]["owners_per_node_ok"]
+            parity["ok"] = bool(parity["ok"] and R["sol"]["owners_per_node_ok"])
+        parity["ls_trials"] = R["stats"]["ls_total"]
+        if world == 1:
+            cpu_baseline = {"value": 1.0 / t_cpu, "unit": UNIT, "cores": threads or cores, "host_cores": cores, "kind": "reference",
+                            "sample": "min over %d full solves of the same QP (%d Newton iterations, status %d), OpenMP build of the unmodified reference" % (nrep, it_cpu, st_cpu),
+                            "us_per_newton_iter": 1e6 * t_cpu / max(it_cpu, 1), "newton_iters": it_cpu,
+                            "ms_per_solve_all": [round(1e3 * r[0], 1) for r in runs]}
+        omp_threads(max(1, cores // world))
+    elif not args.no_cpu_baseline:
+        parity = {"ok": None, "against": "oracle/_ref missing: parity unchecked in this run"}
+        if world == 1:
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}
+    if dist is not None:
+        dist.barrier()
 
-    extra = {}
-    if batch_sharded is not None:
-        extra["batch4096_linear_chain"] = batch_sharded
     if world == 1 and not args.no_extra:
         for name, fn in (("batch4096_linear_chain", bench_batch), ("sdunes_spring_mass_cfg2", bench_sdunes),
                          ("dense_stage_qps_cfg5", bench_dense), ("mpc_resolve_x0_fast_path", bench_mpc)):
@@ -650,27 +822,29 @@ def main():
             except Exception as e:
                 extra[name] = {"error": repr(e)}
 
-    n = world
+    t_res, t_e2e, es = R["t_res"], R["t_e2e"], R["e2e_stats"]
     out = {
-        "metric": METRIC, "value": n * args.steps / t_res, "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "metric": METRIC, "value": args.steps / t_res, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "random_qp binary tree depth %d (%d nodes) nx=12 nu=4 |u|<=0.2, TDUNES clipping, 1 tree per GPU" % (args.depth, prob.Nn),
-                   "newton_iters": iters, "ls_trials": stats["ls_total"], "kkt": kkt, "kkt_device": kkt_dev,
-                   "l2": "inputs %.2f GB + iterates/Hessian blocks, all >> 126 MB L2: no flush between steps" % (stats["h2d_bytes"] / 1e9),
-                   "parallelism": "1 QP per GPU, no collective"},
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args.depth, prob.Nn, world),
+        "detail": {"newton_iters": iters, "ls_trials": R["stats"]["ls_total"], "kkt": R["kkt"], "kkt_device": R["kkt_dev"],
+                   "parallelism": "1 QP on 1 GPU" if world == 1 else "1 QP sharded by subtree over %d GPUs: NCCL all-gather of the cut-node Schur complements + all-reduced scalars" % world,
+                   "sharding": R.get("shard")},
         "us_per_newton_iter": 1e3 * (1e3 * t_res / args.steps) / max(iters, 1),
-        "device_ms_per_step": dev_ms / args.steps,
-        "e2e": {"value": n * args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": e2e_stats["h2d_bytes"],
-                "d2h_bytes_per_step": e2e_stats["d2h_bytes"], "ms_per_step": 1e3 * t_e2e / args.steps,
-                "pack_ms": e2e_stats["pack_ms"], "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"],
-                "gpu_ms": e2e_stats["gpu_ms"]},
-        "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "other_workloads": extra, "sharded_single_tree": sharded,
+        "device_ms_per_step": R["dev_ms"] / args.steps,
+        "e2e": {"value": args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": es["h2d_bytes"],
+                "d2h_bytes_per_step": es["d2h_bytes"], "ms_per_step": 1e3 * t_e2e / args.steps,
+                "pack_ms": es["pack_ms"], "h2d_ms": es["h2d_ms"], "d2h_ms": es["d2h_ms"], "gpu_ms": es["gpu_ms"]},
+        "gpu_launches": int(R["launches"]), "clocks": clk, "parity": parity, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "other_workloads": extra,
     }
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+    if parity is not None and parity.get("ok") is False:
+        sys.stderr.write("bench.py: PARITY FAILURE against the reference: %s\n" % json.dumps(parity))
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":

@@ -12,10 +12,12 @@ import sys
 src, depth, dst = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 note = sys.argv[4] if len(sys.argv) > 4 else src
 
-CLASS = [(r"k_build_factor", "k_factor_level"), (r"k_backsolve_fused", "k_backsolve_level"),
-         (r"k_stage_fused<.*, 0>|k_stage<0>", "k_stage<0>"), (r"k_stage_fused<.*, 2>|k_stage<2>", "k_stage<2>"),
-         (r"k_stage_fused<.*, 3>|k_stage<3>", "k_stage<3>"), (r"k_ls_eval", "k_trial"),
-         (r"k_lambda_step", "k_lambda_step"), (r"k_top_factor", "k_factor_level"), (r"k_top_backsolve", "k_backsolve_level")]
+CLASS = [(r"k_build_factor", "k_build_factor"), (r"k_backsolve_fused|k_backsolve_chain", "k_backsolve_fused"),
+         (r"k_stage_fused<.*, 0>", "k_stage_fused<0>"), (r"k_stage_fused<.*, 2>", "k_stage_fused<2>"),
+         (r"k_stage_fused<.*, 3>", "k_stage_fused<3>"), (r"k_ls_eval", "k_ls_eval"),
+         (r"k_stage<0>", "k_stage<0>"), (r"k_stage<2>", "k_stage<2>"), (r"k_trial", "k_trial"),
+         (r"k_factor_level", "k_factor_level"), (r"k_backsolve_level", "k_backsolve_level"), (r"k_hessian", "k_hessian"),
+         (r"k_lambda_step", "k_lambda_step")]
 
 rows = list(csv.reader(open(src, errors="replace")))
 h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)

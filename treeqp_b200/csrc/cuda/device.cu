@@ -30,9 +30,16 @@ static thread_local char g_err[512] = "";
     } while (0)
 
 enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DIR, K_TRIAL, K_STEP, K_FINISH, K_COMM, K_NCLASS };
-static const char *const k_names[K_NCLASS] = {"k_init", "k_stage<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
-                                              "k_hessian", "k_factor_level", "k_backsolve_level", "k_stage<2>",
-                                              "k_trial", "k_lambda_step", "k_finish", "nccl+pack"};
+/* event classes carry the names of the kernels that run: uniform trees take the compile-time-dimension
+ * kernels (tdunes_fused.cuh, tdunes_stage.cuh), everything else the runtime-dimension ones; the table in
+ * use is that of the most recent solve of this thread */
+static const char *const k_names_generic[K_NCLASS] = {"k_init", "k_stage<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
+                                                      "k_hessian", "k_factor_level", "k_backsolve_level", "k_stage<2>",
+                                                      "k_trial", "k_lambda_step", "k_finish", "nccl+pack"};
+static const char *const k_names_fused[K_NCLASS] = {"k_init", "k_stage_fused<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
+                                                    "k_hessian", "k_build_factor", "k_backsolve_fused", "k_stage_fused<2>",
+                                                    "k_ls_eval", "k_lambda_step", "k_finish", "nccl+pack"};
+static thread_local const char *const *k_names = k_names_generic;
 static int g_profile = -1;
 #define TQB_MAX_EVENTS 65536
 
@@ -793,6 +800,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
 {
     D->pev_on = profiling_on();
     D->pev_n = 0;
+    k_names = D->fast ? k_names_fused : k_names_generic;
     if (D->pev_on && !D->pev)
     {
         D->pev = (cudaEvent_t *) calloc(2 * TQB_MAX_EVENTS, sizeof(cudaEvent_t));

@@ -355,16 +355,54 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
         small = false;
         __syncwarp(); /* Cp is dead, Ms may be written */
         BF_STAMP(4);
-        /* ---- right-looking Cholesky of the augmented matrix ---- */
+        /* ---- right-looking Cholesky of the augmented matrix ----
+         * Software-pipelined by one column: the only chain that has to be serial is
+         *   diagonal of row j -> shuffle -> rsqrt core (100 cycles) -> scale -> diagonal of row j+1,
+         * so lane j+1 forms its next diagonal `dn` from its OWN scaled entry (the same fma the trailing
+         * update would do with the broadcast value), and the trailing update with column j-1 (shared-memory
+         * broadcast + D fmas) is issued inside the latency of column j's pivot instead of in front of it. */
+        double dn = wA[0], ljp = 0.0;
 #pragma unroll
         for (int j = 0; j < D; j++)
         {
             /* lanes <= j carry don't-care values in column j and in rr from here on: the diagonal,
              * its inverse and y are published by lane 0 (no per-lane selects in the loop) */
-            double piv = __shfl_sync(FULL, wA[j], j), inv;
-            tqb_pivot(piv, inv);
+            double piv = __shfl_sync(FULL, dn, j), inv;
+            if (j > 0)
+            {   /* trailing update with column j-1 (published before the barrier that ended step j-1) */
+                const double *col = Ms + (j - 1) * LDR;
+                /* wA[k] -= L[lane][j-1] * L[k][j-1], k >= j: column broadcast from shared memory, two at a time */
+                if (j & 1) wA[j] -= ljp * col[j];
+#pragma unroll
+                for (int k = (j + 1) & ~1; k < D; k += 2)
+                {
+                    const double2 l2 = *reinterpret_cast<const double2 *>(col + k);
+                    wA[k] -= ljp * l2.x;
+                    wA[k + 1] -= ljp * l2.y;
+                }
+                if (NCOLU > 0)
+                {   /* Ut[c][lane] -= Utilde[c][j-1] * L[lane][j-1] on the lanes still to come */
+                    if constexpr ((NCOLU & 1) == 0 && (RL & 1) == 0)
+                    {
+#pragma unroll
+                        for (int cc = 0; cc < NCOLU; cc += 2)
+                        {
+                            const double2 u2 = *reinterpret_cast<const double2 *>(col + RL + cc);
+                            utc[cc] -= u2.x * ljp;
+                            utc[cc + 1] -= u2.y * ljp;
+                        }
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int cc = 0; cc < NCOLU; cc++) utc[cc] -= col[RL + cc] * ljp;
+                    }
+                }
+            }
+            tqb_pivot_spec(piv, inv);
             small |= (piv <= v.o.regTol);
             wA[j] *= inv;
+            if (j + 1 < D) dn = fma(-wA[j], wA[j], wA[j + 1]); /* lane j+1: its diagonal after column j */
             /* forward substitution of the right-hand side on the fly (dtrsv_lnn) */
             const double yj = __shfl_sync(FULL, rr, j) * inv;
             rr = fma(-wA[j], yj, rr);
@@ -392,39 +430,8 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
             /* piv, inv and yj are warp-uniform; lane j keeps them (the kernel is bound by L1/shared
              * wavefronts: three uniform stores per step cost more than three selects) */
             if (lane == j) { my_y = yj; my_d = piv; myinv = inv; }
+            ljp = wA[j];
             __syncwarp();
-            const double lj = wA[j];
-            const double *col = Ms + j * LDR;
-            if (j + 1 < D)
-            {
-                /* wA[k] -= L[lane][j] * L[k][j], k > j: column j broadcast from shared memory, two at a time */
-                if ((j + 1) & 1) wA[j + 1] -= lj * col[j + 1];
-#pragma unroll
-                for (int k = (j + 2) & ~1; k < D; k += 2)
-                {
-                    const double2 l2 = *reinterpret_cast<const double2 *>(col + k);
-                    wA[k] -= lj * l2.x;
-                    wA[k + 1] -= lj * l2.y;
-                }
-                if (NCOLU > 0)
-                {   /* Ut[c][lane] -= Utilde[c][j] * L[lane][j] on the lanes still to come */
-                    if constexpr ((NCOLU & 1) == 0 && (RL & 1) == 0)
-                    {
-#pragma unroll
-                        for (int cc = 0; cc < NCOLU; cc += 2)
-                        {
-                            const double2 u2 = *reinterpret_cast<const double2 *>(col + RL + cc);
-                            utc[cc] -= u2.x * lj;
-                            utc[cc + 1] -= u2.y * lj;
-                        }
-                    }
-                    else
-                    {
-#pragma unroll
-                        for (int cc = 0; cc < NCOLU; cc++) utc[cc] -= col[RL + cc] * lj;
-                    }
-                }
-            }
         }
         BF_STAMP(5);
         if (!(v.o.regType == 2 && attempt == 0 && small)) break;

@@ -85,6 +85,26 @@ __device__ __forceinline__ void tqb_pivot(double &piv, double &inv)
 #endif
 }
 
+/* same results as tqb_pivot; the common-case arithmetic runs unconditionally and the rare cases patch
+ * it afterwards, so that the caller's independent work (the trailing update of the previous column)
+ * sits in the same basic block as the 100-cycle dependent chain and is scheduled into its bubbles */
+__device__ __forceinline__ void tqb_pivot_spec(double &piv, double &inv)
+{
+#ifndef TQB_IEEE_PIVOT
+    const double c = piv;
+    double root, rinv;
+    tqb_rsqrt_core(c, root, rinv);
+    piv = root; inv = rinv;
+    if (!(c > 1e-290 && c < 1e290))
+    {
+        const double2 t = tqb_pivot_rare(c);
+        piv = t.x; inv = t.y;
+    }
+#else
+    tqb_pivot(piv, inv);
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------
  * In-shared-memory Cholesky of a d x d block by one warp (left-looking, column by column) with
  * BLASFEO's pivot rule (kernel_dgemm_4x4_lib4.c:4633-4646): pivot>0 ? (l=sqrt,inv=1/l) : (0,0).
