@@ -316,6 +316,13 @@ void treeqp_tdunes_set_dual_initialization(const double *lambda, treeqp_tdunes_w
  * a CUDA failure returns TREEQP_UNKNOWN_ERROR.  There is no CPU fallback. */
 return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
                              const treeqp_tdunes_opts_t *opts, treeqp_tdunes_workspace *work);
+/* replaces dual_Newton_tree.c:1023 (public header dual_Newton_tree.h:172; called unconditionally by
+ * examples/spring_mass_dual_newton_tree.c:142).  Dumps the iterates of the last solve -- read back from
+ * HBM -- into the reference's files, same names and format ("%.16e" per line):
+ * examples/spring_mass_utils/{x_opt,u_opt,deltalambda_opt,lambda_opt,iter}.txt (like the reference,
+ * deltalambda_opt.txt receives lambda, :1056).  Np and tree are unused (as good as in the reference). */
+void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct node *tree,
+                           treeqp_tdunes_workspace *work);
 
 /* ------------------------------------------------------------------------------------------
  * 4b. SDUNES: dual Newton strategy on the scenario decomposition (dual_Newton_scenarios.h:49-163)
@@ -431,6 +438,11 @@ void treeqp_sdunes_set_dual_initialization(double *lam, double *mu, treeqp_sdune
  * failure.  No CPU fallback. */
 return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdunes_opts_t *opts,
                              treeqp_sdunes_workspace *work);
+/* replaces dual_Newton_scenarios.c:204 (public header dual_Newton_scenarios.h:163; called unconditionally
+ * by examples/spring_mass_dual_newton_scenarios.c:149): scenario iterates and duals of the last solve to
+ * examples/spring_mass_utils/{lambdaIter,muIter,xIter,uIter,iter}.txt */
+void write_scenarios_solution_to_txt(int Ns, int Nh, int Nr, int md, int nx, int nu, int NewtonIter,
+                                     treeqp_sdunes_workspace *work);
 
 /* ------------------------------------------------------------------------------------------
  * 5. container helpers (same names and semantics as tree_qp_common.h / utils/tree.h)

@@ -179,7 +179,7 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 template <int NX, int NU, int MD, int PNX, bool ROOT>
 static int launch_bf(tqb_device *D, int begin, int cnt, int kp, int pre_ok)
 {
-    using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
+    using Cfg = BfSel<NX, NU, MD, PNX, ROOT>;
     static bool attr_done = false;
     const int wpb = 4;
     const size_t smem = (size_t) wpb * Cfg::SMEM * sizeof(double);

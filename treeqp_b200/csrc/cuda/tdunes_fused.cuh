@@ -540,10 +540,333 @@ __device__ __forceinline__ void bf_block(const View &v, size_t desc, int kids_ar
     BF_STAMP(7);
 }
 
+/* ---- blocked variant for block dimensions D >= 16 -----------------------------------------------
+ * Same arithmetic per entry, in the same order, as bf_block (so the iterates are bit-identical), but
+ * organised as a LEFT-LOOKING Cholesky on 8-column panels with the augmented matrix [W ; Ut] resident in
+ * shared memory, column-major with leading dimension LDM (LDM % 8 == 4: the 8 x 4 DMMA fragment loads are
+ * bank-conflict free):
+ *   build    W = C diag(p) C' on the FP64 tensor cores, tiles stored straight into Ms; the Ut rows are
+ *            the scaled fragments themselves (no staging of C in shared memory)
+ *   panel p  (a) M[:, p] -= L[:, 0..p) L[p, 0..p)'  as DMMA m8n8k4 products accumulating INTO the tile
+ *                (k ascending, one rounding per term: what the right-looking scalar update does);
+ *            (b) the panel's 8 columns are pulled into registers, one ROW per lane (rows >= 32 form a
+ *                second, short row-set) and factorised right-looking inside the panel only: per column
+ *                one shuffle, one pivot, at most 7 fmas per row instead of D;
+ *   the column broadcast inside a panel is software-pipelined behind the pivot chain as in bf_block.
+ * Against bf_block<12,4,2>: shared-memory wavefronts per block 726 -> ~330, DFMA instructions in the
+ * factorisation 24 x 28 -> 24 x 8 + 20 DMMA. */
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+struct BlockedCfg
+{
+    static constexpr int D = NX * MD;
+    static constexpr int NCOL = PNX + NU;
+    static constexpr int NUT = ROOT ? 0 : NX;
+    static constexpr int R = D + NUT;                 /* rows of [W ; Ut] */
+    static constexpr int RT = (R + 7) / 8;            /* row tiles */
+    static constexpr int NP = (D + 7) / 8;            /* column panels */
+    static constexpr int NB = R > 32 ? R - 32 : 0;    /* rows of the second row-set */
+    static constexpr int LDM = 8 * RT + 4;            /* % 8 == 4 */
+    static constexpr int TR = (D + 7) / 8;
+    static constexpr int KS = (NCOL + 3) / 4;
+    static constexpr int SM_M = D * LDM;
+    static constexpr int SMEM = SM_M + 2 * D + 4;     /* Ms | ys (D) | spare */
+};
+
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+__device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids_are_parents, bool wait_here, double *Ms, int lane)
+{
+    using Cfg = BlockedCfg<NX, NU, MD, PNX, ROOT>;
+    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, R = Cfg::R, RT = Cfg::RT, NP = Cfg::NP, NB = Cfg::NB, LDM = Cfg::LDM;
+    constexpr int TR = Cfg::TR, KS = Cfg::KS;
+    static_assert(D <= 32 && (D & 1) == 0, "block dimension: even, at most one warp of rows");
+    const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * desc;
+    const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
+    const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
+    if (v.status[d2.y] != TQB_RUNNING)
+    {
+        if (wait_here) { pdl_wait(); pdl_release(); }
+        return;
+    }
+    BF_STAMP(1);
+    double *ys = Ms + Cfg::SM_M;                  /* C z, later y = L^-1 resMod */
+    const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
+    const bool isW = lane < D;
+    const int kid = isW ? lane / NX : 0, ii = isW ? lane - kid * NX : 0;
+    const int gid = lane >> 2, tig = lane & 3;
+
+    double myinv = 0.0, my_y = 0.0, my_d = 0.0, rr = 0.0;
+    bool small = false;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        const double shift = (v.o.regType == 1 || attempt == 1) ? v.o.regValue : 0.0;
+        double res = 0.0;
+        {
+            /* ---- tensor-core build (see bf_block): fragment (i, ks) = C[8i + gid][4ks + tig] ---- */
+            double pf[KS], zf[KS], af[TR][KS];
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+            {
+                const int c = 4 * ks + tig;
+                pf[ks] = zf[ks] = 0.0;
+                if (c < NCOL)
+                {
+                    pf[ks] = c < PNX ? v.P[xo + c] : v.Rt[uo + c - PNX];
+                    zf[ks] = c < PNX ? v.x[xo + c] : v.u[uo + c - PNX];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < TR; i++)
+            {
+                const int r = 8 * i + gid, kr = r / NX, ir = r - kr * NX;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++)
+                {
+                    const int c = 4 * ks + tig;
+                    double val = 0.0;
+                    if (r < D && c < NCOL) val = c < PNX ? Ag[kr * NX * PNX + ir + c * NX] : Bg[kr * NX * NU + ir + (c - PNX) * NX];
+                    af[i][ks] = val;
+                }
+            }
+            if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
+            __syncwarp(); /* previous attempt's readers of Ms / ys are done */
+#pragma unroll
+            for (int i = 0; i < TR; i++)
+            {   /* C z as one more tile column (z in column 0) */
+                const int r = 8 * i + gid;
+                double sg = 0.0, sg1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) dmma884(sg, sg1, af[i][ks], gid == 0 ? zf[ks] : 0.0);
+                if (tig == 0 && r < D) ys[r] = sg;
+            }
+#pragma unroll
+            for (int i = 0; i < TR; i++)
+            {
+#pragma unroll
+                for (int n = 0; n <= i; n++)
+                {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++) dmma884(c0, c1, af[i][ks], af[n][ks] * pf[ks]);
+                    /* W tile (i, n) -> Ms, column-major */
+                    const int r = 8 * i + gid, c = 8 * n + 2 * tig;
+                    if (r < D && c < D) { Ms[c * LDM + r] = c0; Ms[(c + 1) * LDM + r] = c1; }
+                }
+                if (!ROOT)
+                {   /* Ut[c][K] = -P_p[c] * A[K][c]: the scaled fragments, row D + c of column K = 8i + gid */
+                    const int K = 8 * i + gid;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ks++)
+                        if (4 * ks < PNX)
+                        {
+                            const int c = 4 * ks + tig;
+                            if (K < D && c < PNX) Ms[K * LDM + D + c] = -(af[i][ks] * pf[ks]);
+                        }
+                }
+            }
+            __syncwarp();
+            if (isW)
+            {
+                res += ys[lane];
+                v.res[xb + lane] = res;
+                Ms[lane * LDM + lane] += v.P[xb + lane] + shift;
+            }
+            if (attempt == 0)
+            {   /* contribution to the termination norm (calculate_error_in_residuals, :412-442) */
+                double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
+                part = (v.o.termCondition == 2) ? warp_max(part) : warp_sum(part);
+                if (lane == 0) v.nva[g] = part;
+            }
+        }
+        /* ---- everything below needs the kids' level ---- */
+        BF_STAMP(2);
+        if (attempt == 0 && wait_here) { pdl_wait(); pdl_release(); }
+        BF_STAMP(3);
+        rr = res - ((kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0);
+        if (kids_are_parents && isW)
+        {   /* minus the Schur complement of the kid this row belongs to (lower triangle, row `lane`) */
+            const double *Sk = v.schur + (size_t) (k0 + kid) * NX * NX + ii;
+            double sv[NX];
+#pragma unroll
+            for (int kk = 0; kk < NX; kk++) sv[kk] = (kk <= ii) ? Sk[kk * NX] : 0.0; /* S[ii][kk], stored by columns */
+#pragma unroll
+            for (int kk = 0; kk < NX; kk++)
+                if (kk <= ii) Ms[(kid * NX + kk) * LDM + lane] -= sv[kk];
+        }
+        small = false;
+        __syncwarp();
+        BF_STAMP(4);
+        /* ---- left-looking blocked Cholesky of the augmented matrix ---- */
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+        {
+            constexpr int PWMAX = 8;
+            const int PW = (D - 8 * p) < PWMAX ? (D - 8 * p) : PWMAX; /* compile-time after unrolling */
+            if (p > 0)
+            {   /* (a) panel update on the tensor cores: tile (i, p) -= sum_k L[8i.., k] L[8p.., k] */
+                double bfr[2 * (NP - 1)];
+#pragma unroll
+                for (int ks = 0; ks < 2 * p; ks++) bfr[ks] = Ms[(4 * ks + tig) * LDM + 8 * p + gid];
+#pragma unroll
+                for (int i = p; i < RT; i++)
+                {
+                    const int r = 8 * i + gid, c = 8 * p + 2 * tig;
+                    double c0 = 0.0, c1 = 0.0;
+                    if (c < D) { c0 = Ms[c * LDM + r]; c1 = Ms[(c + 1) * LDM + r]; }
+#pragma unroll
+                    for (int ks = 0; ks < 2 * p; ks++)
+                    {
+                        const double a = (i == p) ? bfr[ks] : Ms[(4 * ks + tig) * LDM + r];
+                        dmma884(c0, c1, -a, bfr[ks]);
+                    }
+                    if (c < D) { Ms[c * LDM + r] = c0; Ms[(c + 1) * LDM + r] = c1; }
+                }
+                __syncwarp();
+            }
+            /* (b) the panel in registers, one row per lane */
+            double pa[PWMAX], pb[PWMAX];
+#pragma unroll
+            for (int k = 0; k < PWMAX; k++)
+            {
+                pa[k] = pb[k] = 0.0;
+                if (k < PW)
+                {
+                    pa[k] = Ms[(8 * p + k) * LDM + lane];
+                    if (NB > 0 && lane < NB) pb[k] = Ms[(8 * p + k) * LDM + 32 + lane];
+                }
+            }
+            /* (c) right-looking inside the panel, pivot chain decoupled from the column broadcast */
+            double dn = pa[0], ljp = 0.0, ljpb = 0.0;
+#pragma unroll
+            for (int j = 0; j < PWMAX; j++)
+            {
+                if (j < PW)
+                {
+                    const int J = 8 * p + j;
+                    double piv = __shfl_sync(FULL, dn, J), inv;
+                    if (j > 0)
+                    {   /* trailing update inside the panel with column J-1 (published before the last barrier) */
+                        const double *col = Ms + (J - 1) * LDM + 8 * p;
+                        if (j & 1)
+                        {
+                            const double l = col[j];
+                            pa[j] -= ljp * l;
+                            if (NB > 0) pb[j] -= ljpb * l;
+                        }
+#pragma unroll
+                        for (int k = (j + 1) & ~1; k < PW; k += 2)
+                        {
+                            const double2 l2 = *reinterpret_cast<const double2 *>(col + k);
+                            pa[k] -= ljp * l2.x;
+                            pa[k + 1] -= ljp * l2.y;
+                            if (NB > 0) { pb[k] -= ljpb * l2.x; pb[k + 1] -= ljpb * l2.y; }
+                        }
+                    }
+                    tqb_pivot_spec(piv, inv);
+                    small |= (piv <= v.o.regTol);
+                    pa[j] *= inv;
+                    if (NB > 0) pb[j] *= inv;
+                    if (j + 1 < PW) dn = fma(-pa[j], pa[j], pa[j + 1]); /* lane J+1: its diagonal after column J */
+                    /* forward substitution of the right-hand side on the fly (dtrsv_lnn) */
+                    const double yj = __shfl_sync(FULL, rr, J) * inv;
+                    rr = fma(-pa[j], yj, rr);
+                    Ms[J * LDM + lane] = pa[j];
+                    if (NB > 0 && lane < NB) Ms[J * LDM + 32 + lane] = pb[j];
+                    if (lane == J) { my_y = yj; my_d = piv; myinv = inv; }
+                    ljp = pa[j]; ljpb = pb[j];
+                    __syncwarp();
+                }
+            }
+        }
+        BF_STAMP(5);
+        if (!(v.o.regType == 2 && attempt == 0 && small)) break;
+        if (lane == 0) atomicAdd(&v.counters[2], 1);
+        __syncwarp();
+    }
+
+    /* ---- results to HBM (as bf_block: Ms[j][r] holds column j of [L ; Utilde] but the diagonal) ---- */
+    if (isW)
+    {
+        rr = my_y;
+        ys[lane] = my_y;
+        Ms[lane * LDM + lane] = my_d;
+        v.Linv[xb + lane] = myinv;
+    }
+    __syncwarp();
+    {
+        double *Lg = v.W + d1.w;
+#pragma unroll
+        for (int r = 0; r < D; r++)
+            if (lane <= r) Lg[(r * (r + 1)) / 2 + lane] = Ms[lane * LDM + r];
+    }
+    BF_STAMP(6);
+    if (!ROOT)
+    {
+        if (isW) v.dlam[xb + lane] = rr;
+        double *Up = v.Ut + d2.x;
+#pragma unroll
+        for (int e0 = 0; e0 < NX * D; e0 += 32)
+        {   /* Utilde row-major NX x D: element a*D + j is Ms[j][D + a] */
+            const int e = e0 + lane, a = e / D, j = e - a * D;
+            if (e < NX * D) Up[e] = Ms[j * LDM + D + a];
+        }
+        /* Schur complement for the parent's block: S = Utilde Utilde' (lower), s = Utilde y */
+        double *Sg = v.schur + (size_t) g * NX * NX;
+        constexpr int TRU = (NX + 7) / 8, KSU = (D + 3) / 4;
+        double uf[TRU][KSU];
+#pragma unroll
+        for (int i = 0; i < TRU; i++)
+#pragma unroll
+            for (int ks = 0; ks < KSU; ks++)
+                uf[i][ks] = (8 * i + gid < NX && 4 * ks + tig < D) ? Ms[(4 * ks + tig) * LDM + D + 8 * i + gid] : 0.0;
+#pragma unroll
+        for (int i = 0; i < TRU; i++)
+#pragma unroll
+            for (int n = 0; n <= i; n++)
+            {
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < KSU; ks++) dmma884(c0, c1, uf[i][ks], uf[n][ks]);
+                const int a = 8 * i + gid, b = 8 * n + 2 * tig;
+                if (a < NX && b < NX) Sg[b * NX + a] = c0;
+                if (a < NX && b + 1 < NX) Sg[(b + 1) * NX + a] = c1;
+            }
+        for (int a = lane; a < NX; a += 32)
+        {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; j++) s += Ms[j * LDM + D + a] * ys[j];
+            v.rsub[xo + a] = s;
+        }
+    }
+    else
+    {   /* root: backward substitution dlam = L^-T y; lane t owns column t of L = Ms[t][*] */
+#pragma unroll
+        for (int i = D - 1; i >= 0; i--)
+        {
+            const double yi = __shfl_sync(FULL, rr, i) * __shfl_sync(FULL, myinv, i);
+            if (lane == i) rr = yi;
+            else if (lane < i) rr -= Ms[lane * LDM + i] * yi;
+        }
+        if (isW) v.dlam[xb + lane] = rr;
+    }
+    BF_STAMP(7);
+}
+
+#ifndef TQB_BF_BLOCKED_MIN_D
+#define TQB_BF_BLOCKED_MIN_D 16 /* smallest block dimension that takes the blocked left-looking variant */
+#endif
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+struct BfSel
+{
+    static constexpr bool BLOCKED = NX * MD >= TQB_BF_BLOCKED_MIN_D;
+    static constexpr int SMEM = BLOCKED ? BlockedCfg<NX, NU, MD, PNX, ROOT>::SMEM : FusedCfg<NX, NU, MD, PNX, ROOT>::SMEM;
+};
+
 template <int NX, int NU, int MD, int PNX, bool ROOT>
 __global__ void __launch_bounds__(128, tqb_bf_minblocks(NX * MD)) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents, int pre_ok)
 {
-    using Cfg = FusedCfg<NX, NU, MD, PNX, ROOT>;
+    using Sel = BfSel<NX, NU, MD, PNX, ROOT>;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = blockIdx.x * wpb + wib;
@@ -552,7 +875,10 @@ __global__ void __launch_bounds__(128, tqb_bf_minblocks(NX * MD)) k_build_factor
      * the bottom level, the cut-node exchange of a sharded solve): wait first */
     if (!pre_ok) { pdl_wait(); pdl_release(); }
     if (w >= count) { pdl_wait(); pdl_release(); return; }
-    bf_block<NX, NU, MD, PNX, ROOT>(v, (size_t) (lvl_begin + w), kids_are_parents, true, smem + (size_t) wib * Cfg::SMEM, lane);
+    if constexpr (Sel::BLOCKED)
+        bf_block_lb<NX, NU, MD, PNX, ROOT>(v, (size_t) (lvl_begin + w), kids_are_parents, true, smem + (size_t) wib * Sel::SMEM, lane);
+    else
+        bf_block<NX, NU, MD, PNX, ROOT>(v, (size_t) (lvl_begin + w), kids_are_parents, true, smem + (size_t) wib * Sel::SMEM, lane);
 }
 
 /* Chain segments (consecutive depths whose parents have ONE kid each: the scenario chains below the

@@ -271,6 +271,11 @@ int tqb_sd_device_solve(tqb_sd_device *d, const tqb_opts *o, int reverse, int *h
                         long long *launches);
 int tqb_sd_device_download(tqb_sd_device *d, double *h_out, double *ms);
 
+int tqb_verbose(void); /* TREEQP_B200_VERBOSE=1 */
+/* "%.16e" / "%d" per line, as utils/utils.c:98-143 */
+int tqb_write_doubles_txt(const double *v, long long n, const char *filename);
+int tqb_write_ints_txt(const int *v, long long n, const char *filename);
+
 #ifdef __cplusplus
 }
 #endif

@@ -538,6 +538,28 @@ return_t treeqp_sdunes_download(tree_qp_out *qp_out, treeqp_sdunes_workspace *wo
     return TREEQP_OK;
 }
 
+void write_scenarios_solution_to_txt(int Ns, int Nh, int Nr, int md, int nx, int nu, int NewtonIter,
+                                     treeqp_sdunes_workspace *work)
+{
+    (void) Nr; (void) md;
+    tqb_sd_ctx *ctx = sd_ctx_of(work);
+    if (!ctx || !ctx->h_out || !ctx->solved)
+    {
+        fprintf(stderr, "[treeqp_b200] write_scenarios_solution_to_txt: no solve on this workspace yet\n");
+        return;
+    }
+    /* scenario iterates and duals of the last solve: the output block treeqp_sdunes_solve downloaded */
+    const tqb_sd_dims *d = &ctx->dims;
+    const tqb_sd_outputs *o = &ctx->hout;
+    if (Ns != d->Ns || Nh != d->Nh || nx != d->nx || nu != d->nu)
+        fprintf(stderr, "[treeqp_b200] write_scenarios_solution_to_txt: dimensions differ from the workspace\n");
+    tqb_write_doubles_txt(o->lam_s, d->nl, "examples/spring_mass_utils/lambdaIter.txt");
+    tqb_write_doubles_txt(o->mu_s, (long long) d->SK * d->nx, "examples/spring_mass_utils/muIter.txt");
+    tqb_write_doubles_txt(o->xs, (long long) d->SK * d->nx, "examples/spring_mass_utils/xIter.txt");
+    tqb_write_doubles_txt(o->us, (long long) d->SK * d->nu, "examples/spring_mass_utils/uIter.txt");
+    tqb_write_ints_txt(&NewtonIter, 1, "examples/spring_mass_utils/iter.txt");
+}
+
 return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdunes_opts_t *opts,
                              treeqp_sdunes_workspace *work)
 {
@@ -568,5 +590,8 @@ return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdun
     const double t_end = tqb_wall_ms();
     qp_out->info.interface_time += 1e-3 * (t_end - t_after);
     qp_out->info.total_time = 1e-3 * (t_end - t_total);
+    if (tqb_verbose())
+        fprintf(stderr, "[treeqp_b200] treeqp_sdunes_solve: status %d, %d Newton iterations, %lld kernel launches, gpu %.3f ms, total %.3f ms\n",
+                (int) st, qp_out->info.iter, ctx->launches, ctx->gpu_ms, t_end - t_total);
     return st;
 }

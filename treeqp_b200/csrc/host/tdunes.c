@@ -37,6 +37,18 @@ struct treeqp_tdunes_batch_
     int uploaded;
 };
 
+/* TREEQP_B200_VERBOSE=1: one line per drop-in solve on stderr (which library ran, how many launches) */
+int tqb_verbose(void)
+{
+    static int v = -1;
+    if (v < 0)
+    {
+        const char *e = getenv("TREEQP_B200_VERBOSE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v;
+}
+
 const char *treeqp_b200_version(void) { return "treeqp_b200 0.1 (sm_100a)"; }
 int treeqp_b200_device_count(void) { return tqb_cuda_device_count(); }
 int treeqp_b200_set_device(int device) { return tqb_cuda_set_device(device); }
@@ -397,7 +409,62 @@ return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
     const double t_end = tqb_wall_ms();
     qp_out->info.interface_time += 1e-3 * (t_end - t_after);
     qp_out->info.total_time = 1e-3 * (t_end - t_total);
+    if (tqb_verbose())
+        fprintf(stderr, "[treeqp_b200] treeqp_tdunes_solve: status %d, %d Newton iterations, %lld kernel launches, gpu %.3f ms, total %.3f ms\n",
+                (int) st, qp_out->info.iter, ctx->forest->launches, ctx->forest->gpu_ms, t_end - t_total);
     return st;
+}
+
+/* ------------------------------------------------------------------- write_solution_to_txt ---- */
+
+/* same format as write_double_vector_to_txt / write_int_vector_to_txt (utils/utils.c:98-143) */
+int tqb_write_doubles_txt(const double *v, long long n, const char *filename)
+{
+    FILE *f = fopen(filename, "w");
+    if (f == NULL)
+    {
+        printf("Error opening file (%s)\n", filename);
+        return 1;
+    }
+    for (long long i = 0; i < n; i++) fprintf(f, "%.16e\n", v[i]);
+    fclose(f);
+    return 0;
+}
+
+int tqb_write_ints_txt(const int *v, long long n, const char *filename)
+{
+    FILE *f = fopen(filename, "w");
+    if (f == NULL)
+    {
+        printf("Error opening file (%s)\n", filename);
+        return 1;
+    }
+    for (long long i = 0; i < n; i++) fprintf(f, "%d\n", v[i]);
+    fclose(f);
+    return 0;
+}
+
+void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct node *tree,
+                           treeqp_tdunes_workspace *work)
+{
+    (void) Np; (void) tree;
+    tqb_ctx *ctx = ctx_of(work);
+    if (!ctx || !ctx->forest || !ctx->solved)
+    {
+        fprintf(stderr, "[treeqp_b200] write_solution_to_txt: no solve on this workspace yet\n");
+        return;
+    }
+    tqb_forest *f = ctx->forest;
+    /* the iterates live in HBM: bring x, u, lambda back (one copy) */
+    if (forest_download(f) != TREEQP_OK) return;
+    const tqb_dims *d = &f->dims;
+    const double *x = f->h_out, *u = x + d->X, *lam = u + d->U;
+    const int nx0 = qp_in->nx[0];
+    tqb_write_doubles_txt(x, d->X, "examples/spring_mass_utils/x_opt.txt");
+    tqb_write_doubles_txt(u, d->U, "examples/spring_mass_utils/u_opt.txt");
+    tqb_write_doubles_txt(lam + nx0, d->X - nx0, "examples/spring_mass_utils/deltalambda_opt.txt");
+    tqb_write_doubles_txt(lam + nx0, d->X - nx0, "examples/spring_mass_utils/lambda_opt.txt");
+    tqb_write_ints_txt(&iter, 1, "examples/spring_mass_utils/iter.txt");
 }
 
 /* ------------------------------------------------------------------------------- batch ---- */
