@@ -324,6 +324,13 @@ return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
 void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct node *tree,
                            treeqp_tdunes_workspace *work);
 
+/* PROFILE > 0 is NOT supported: the workspace structs above are the PROFILE = 0 layout (the reference adds
+ * a trailing `timings` member otherwise, dual_Newton_tree.h:146-148).  A caller compiled with PROFILE > 0
+ * binds timers_print / timers_write_to_txt (utils/profiling.h:75-77) to this library, which stops the
+ * program with a message rather than let it print timers nobody filled. */
+void timers_print(void *timings);
+void timers_write_to_txt(void *timings);
+
 /* ------------------------------------------------------------------------------------------
  * 4b. SDUNES: dual Newton strategy on the scenario decomposition (dual_Newton_scenarios.h:49-163)
  * ---------------------------------------------------------------------------------------- */

@@ -564,6 +564,7 @@ struct BlockedCfg
     static constexpr int R = D + NUT;                 /* rows of [W ; Ut] */
     static constexpr int RT = (R + 7) / 8;            /* row tiles */
     static constexpr int NP = (D + 7) / 8;            /* column panels */
+    static constexpr int NA = R < 32 ? R : 32;        /* rows of the first row-set (lane = row) */
     static constexpr int NB = R > 32 ? R - 32 : 0;    /* rows of the second row-set */
     static constexpr int LDM = 8 * RT + 4;            /* % 8 == 4 */
     static constexpr int TR = (D + 7) / 8;
@@ -576,7 +577,7 @@ template <int NX, int NU, int MD, int PNX, bool ROOT>
 __device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids_are_parents, bool wait_here, double *Ms, int lane)
 {
     using Cfg = BlockedCfg<NX, NU, MD, PNX, ROOT>;
-    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, R = Cfg::R, RT = Cfg::RT, NP = Cfg::NP, NB = Cfg::NB, LDM = Cfg::LDM;
+    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, RT = Cfg::RT, NP = Cfg::NP, NA = Cfg::NA, NB = Cfg::NB, LDM = Cfg::LDM;
     constexpr int TR = Cfg::TR, KS = Cfg::KS;
     static_assert(D <= 32 && (D & 1) == 0, "block dimension: even, at most one warp of rows");
     const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * desc;
@@ -731,7 +732,7 @@ __device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids
                 pa[k] = pb[k] = 0.0;
                 if (k < PW)
                 {
-                    pa[k] = Ms[(8 * p + k) * LDM + lane];
+                    if (NA == 32 || lane < NA) pa[k] = Ms[(8 * p + k) * LDM + lane]; /* lanes without a row compute on zeros */
                     if (NB > 0 && lane < NB) pb[k] = Ms[(8 * p + k) * LDM + 32 + lane];
                 }
             }
@@ -770,7 +771,7 @@ __device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids
                     /* forward substitution of the right-hand side on the fly (dtrsv_lnn) */
                     const double yj = __shfl_sync(FULL, rr, J) * inv;
                     rr = fma(-pa[j], yj, rr);
-                    Ms[J * LDM + lane] = pa[j];
+                    if (NA == 32 || lane < NA) Ms[J * LDM + lane] = pa[j];
                     if (NB > 0 && lane < NB) Ms[J * LDM + 32 + lane] = pb[j];
                     if (lane == J) { my_y = yj; my_d = piv; myinv = inv; }
                     ljp = pa[j]; ljpb = pb[j];

@@ -467,6 +467,24 @@ void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct nod
     tqb_write_ints_txt(&iter, 1, "examples/spring_mass_utils/iter.txt");
 }
 
+/* ------------------------------------------------------------------ PROFILE > 0 guard ---- */
+
+/* The reference's workspace structs grow a `timings` member when the CALLER is compiled with PROFILE > 0
+ * (dual_Newton_tree.h:146-148, dual_Newton_scenarios.h:135-137) and its drivers then read arrays that
+ * only the reference's solve fills (utils/profiling.c).  This ABI is the PROFILE = 0 one; a PROFILE > 0
+ * program reaches for these two symbols right after its solve (examples/...:145, :152, random_qp.c:191),
+ * binds them here (the library precedes libtreeqp.a on the link line) and is stopped with a message
+ * instead of printing uninitialised timers.  Per-kernel-class GPU times: treeqp_tdunes_get_stats. */
+static void profile_unsupported(const char *fn)
+{
+    fprintf(stderr, "[treeqp_b200] %s: this program was compiled with PROFILE > 0; libtreeqp_b200 implements the "
+                    "PROFILE = 0 workspace ABI only (rebuild the caller with -DPROFILE=0; GPU timings: "
+                    "treeqp_tdunes_get_stats / treeqp_sdunes_get_stats)\n", fn);
+    exit(1);
+}
+void timers_print(void *timings) { (void) timings; profile_unsupported("timers_print"); }
+void timers_write_to_txt(void *timings) { (void) timings; profile_unsupported("timers_write_to_txt"); }
+
 /* ------------------------------------------------------------------------------- batch ---- */
 
 treeqp_tdunes_batch *treeqp_tdunes_batch_create(int n, const tree_qp_in *const *qp_in,
