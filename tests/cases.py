@@ -9,6 +9,13 @@ from treeqp_b200 import problems as P
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
+# closed-loop states a few samples into the manoeuvre: input (quadcopter) / state (crane) bounds active,
+# and the reference meets its own KKT bar with both stage solvers (at x0 = 0 its qpOASES path stops after
+# one iteration with a KKT residual of 0.46 on the crane, so x0 = 0 cannot serve as a golden)
+QUAD_X0 = [0.03, -0.03, 0.01, 0.8, -0.8, 0.3]
+CRANE_X0 = [0.0, 0.2, 0.1, -0.3]
+
+
 def cases():
     yield "spring_mass_cfg1", P.spring_mass(3, 2, 10), {}
     yield "spring_mass_tight", P.spring_mass(3, 2, 10, xmax1=0.2), {}
@@ -21,6 +28,9 @@ def cases():
     yield "linear_chain_cfg4", P.linear_chain(4, 3, 3, 2, 20, seed=0), {}
     yield "linear_chain_cfg4_s7", P.linear_chain(4, 3, 3, 2, 20, seed=7), {}
     yield "linear_chain_pinned_x0", P.linear_chain(2, 1, 2, 2, 6, seed=1, eliminate_x0=False), {}
+    # config 5's benchmark models (benchmark/quadcopter, benchmark/crane), diagonal weights, clipping
+    yield "quadcopter_cfg5", P.quadcopter(3, 2, 20, i_mpc=14, x0=QUAD_X0), dict(maxIter=200)
+    yield "crane_cfg5", P.crane(3, 2, 20, x0=CRANE_X0), dict(maxIter=200)
 
 
 def dense_cases():
@@ -36,6 +46,10 @@ def dense_cases():
     yield "random_nx6_nu4_md3", D(P.random_tree(P.multistage_nk(3, 2, 8), 6, 4, seed=8, ubound=0.3), 4, 0.1, 0.0), dict(Q, maxIter=200)
     yield "random_nx4_nu1_xbox", D(P.random_tree(P.multistage_nk(3, 2, 8), 4, 1, seed=9, ubound=0.2, xbound=3.0), 5, 0.05, 0.0), dict(Q, maxIter=200)
     yield "linear_chain_nm8_md4", D(_ubox(P.linear_chain(8, 7, 4, 2, 5, seed=2), 0.3, 1e12), 6, 0.1, 0.0), dict(Q)
+    # config 5 as named: the quadcopter and crane trees with dense stage Hessians (qpOASES stage solver)
+    yield "quadcopter_cfg5", P.densify_scaled(P.quadcopter(3, 2, 20, i_mpc=14, x0=QUAD_X0), 4), dict(Q, maxIter=200)
+    yield "crane_cfg5", P.densify_scaled(P.crane(3, 2, 20, x0=CRANE_X0), 5), dict(Q, maxIter=200)
+    yield "quadcopter_cfg5_diag", P.quadcopter(3, 2, 20, i_mpc=12), dict(Q, maxIter=200)
     lc = _ubox(P.linear_chain(4, 3, 3, 2, 8, seed=3), 0.4, 1e12)
     # per-node choice: dense solver on the parents, clipping on the leaves (the reference's own
     # workspace carving only supports mixes whose dense nodes come first: create_strmat asserts
@@ -138,6 +152,34 @@ def checksum(prob):
 
 def golden(name):
     return np.load(os.path.join(GOLDEN, "tdunes_%s.npz" % name))
+
+
+# ---- large-tree golden: config 3's QP two depths below the benchmark size (32 767 nodes, 21 Newton
+# iterations, 6 s on the reference).  The solution vectors are 12 MB, so the fixture keeps every
+# LARGE_STRIDE-th entry of each vector, the packed active-set masks of ALL bounds and the exact sums.
+LARGE_NAME, LARGE_DEPTH, LARGE_STRIDE = "random_d14_u02", 14, 29
+
+
+def large_case():
+    return P.random_tree(P.binary_tree_nk(LARGE_DEPTH), 12, 4, seed=0, ubound=0.2), dict(maxIter=200)
+
+
+def large_summary(prob, sol):
+    """what the fixture stores of a solution (dict with status, iter, x, u, lam, mu_x, mu_u)"""
+    out = {"status": int(sol["status"]), "iter": int(sol["iter"])}
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        v = np.asarray(sol[k])
+        out[k + "_sample"] = v[::LARGE_STRIDE].copy()
+        out[k + "_sum"] = float(np.sum(v))
+        out[k + "_absmax"] = float(np.max(np.abs(v)))
+    out["u_lower"] = np.packbits(np.asarray(sol["u"]) == prob.umin)
+    out["u_upper"] = np.packbits(np.asarray(sol["u"]) == prob.umax)
+    out["x_bound"] = np.packbits((np.asarray(sol["x"]) == prob.xmin) | (np.asarray(sol["x"]) == prob.xmax))
+    return out
+
+
+def large_golden():
+    return np.load(os.path.join(GOLDEN, "tdunes_large_%s.npz" % LARGE_NAME))
 
 
 def rel_err(a, b):

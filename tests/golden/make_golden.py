@@ -50,12 +50,17 @@ def make_spring_mass_data():
 
 
 from cases import cases, checksum, dense_cases, sdunes_cases  # noqa: E402  (tests/cases.py)
+import cases as CS  # noqa: E402
+
+ONLY = set(os.environ.get("GOLDEN_ONLY", "").split(",")) - {""}   # GOLDEN_ONLY=name1,name2: just these cases
 
 
 def make_tdunes_goldens():
     from treeqp_b200 import capi
     ref = capi.TreeQpLib(os.path.join(ROOT, "oracle/_ref/libtreeqp_ref.so"))
     for name, prob, opts in cases():
+        if ONLY and name not in ONLY:
+            continue
         sol = capi.solve_tdunes(ref, prob, **opts)
         np.savez_compressed(os.path.join(HERE, "tdunes_%s.npz" % name), status=sol.status, iter=sol.iter,
                             x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u, kkt=sol.kkt,
@@ -69,6 +74,8 @@ def make_dense_goldens():
     from treeqp_b200 import capi
     ref = capi.TreeQpLib(os.path.join(ROOT, "oracle/_ref/libtreeqp_ref.so"))
     for name, prob, opts in dense_cases():
+        if ONLY and name not in ONLY:
+            continue
         sol = capi.solve_tdunes(ref, prob, **opts)
         np.savez_compressed(os.path.join(HERE, "tdunes_dense_%s.npz" % name), status=sol.status, iter=sol.iter,
                             x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u, kkt=sol.kkt,
@@ -82,6 +89,8 @@ def make_sdunes_goldens():
     from treeqp_b200 import capi
     ref = capi.TreeQpLib(os.path.join(ROOT, "oracle/_ref/libtreeqp_ref.so"))
     for name, prob, opts in sdunes_cases():
+        if ONLY and name not in ONLY:
+            continue
         sol = capi.solve_sdunes(ref, prob, **opts)
         np.savez_compressed(os.path.join(HERE, "sdunes_%s.npz" % name), status=sol.status, iter=sol.iter,
                             x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u, kkt=sol.kkt,
@@ -90,8 +99,24 @@ def make_sdunes_goldens():
             name, prob.Nn, sol.status, sol.iter, sol.kkt, 1e3 * sol.total_time))
 
 
+def make_large_golden():
+    """config 3's QP at depth 14 through the UNMODIFIED reference (OpenMP build: 32 767 nodes)"""
+    from treeqp_b200 import capi
+    ref = capi.TreeQpLib(os.path.join(ROOT, "oracle/_ref/libtreeqp_ref_omp.so"))
+    prob, opts = CS.large_case()
+    sol = capi.solve_tdunes(ref, prob, **opts)
+    d = CS.large_summary(prob, dict(status=sol.status, iter=sol.iter, x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u))
+    np.savez_compressed(os.path.join(HERE, "tdunes_large_%s.npz" % CS.LARGE_NAME), kkt=sol.kkt, input_sha256=checksum(prob),
+                        opts=repr(opts), stride=CS.LARGE_STRIDE, **d)
+    print("large  %-28s Nn=%6d status=%d iter=%3d kkt=%.2e time=%.1f s, active inputs %d" % (
+        CS.LARGE_NAME, prob.Nn, sol.status, sol.iter, sol.kkt, sol.total_time,
+        int(np.unpackbits(d["u_lower"]).sum() + np.unpackbits(d["u_upper"]).sum())))
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["data", "tdunes", "sdunes", "dense"]
+    what = sys.argv[1:] or ["data", "tdunes", "sdunes", "dense", "large"]
+    if "large" in what:
+        make_large_golden()
     if "dense" in what:
         make_dense_goldens()
     if "data" in what:

@@ -238,3 +238,21 @@ def test_chain_kernels_odd_counts_match_oracle(shape, product_lib, monkeypatch):
     assert ref.iter == sol.iter
     for k in ("x", "u", "lam", "mu_x", "mu_u"):
         assert np.array_equal(getattr(sol, k), getattr(ref, k)), k + ": chain kernels are not bit-identical to the per-depth kernels"
+
+
+def test_large_tree_matches_reference_golden(product_lib):
+    """config 3's QP at depth 14 (32 767 nodes) against the unmodified reference: same status and Newton
+    iteration count, identical active sets over ALL 65 532 input bounds, x/u/lam/mu to 1e-10 on every
+    29th entry plus the exact sums (fixture made by tests/golden/make_golden.py large)"""
+    prob, opts = CS.large_case()
+    g = CS.large_golden()
+    assert str(g["input_sha256"]) == CS.checksum(prob)
+    sol = capi.solve_tdunes(product_lib, prob, **opts)
+    s = CS.large_summary(prob, dict(status=sol.status, iter=sol.iter, x=sol.x, u=sol.u, lam=sol.lam, mu_x=sol.mu_x, mu_u=sol.mu_u))
+    assert (s["status"], s["iter"]) == (int(g["status"]), int(g["iter"]))
+    for k in ("u_lower", "u_upper", "x_bound"):
+        assert np.array_equal(s[k], g[k]), "active set differs: " + k
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        assert CS.rel_err(s[k + "_sample"], g[k + "_sample"]) < TOL, k
+        assert abs(s[k + "_sum"] - float(g[k + "_sum"])) <= 1e-9 * max(1.0, abs(float(g[k + "_sum"]))), k
+    assert sol.kkt < 1e-8

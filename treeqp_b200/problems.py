@@ -328,3 +328,131 @@ def scenario_dims(prob: Problem):
     nu = int(prob.nu[0])
     nl = -1 if Ns == 1 else (Nr * Ns - (Ns - 1) // (md - 1)) * nu
     return Ns, Nh, Nr, md, nl
+
+
+# ------------------------------------------------------------------ benchmark models of config 5
+def _benchmark_tree(Ad, Bd, Qw, Rw, Pw, xref, uref, xmin, xmax, umin, umax, xNmin, xNmax, x0,
+                    md, Nr, Nh, name, eliminate: bool = True) -> Problem:
+    """Tree QP of the benchmark harness (benchmark/utils/setup_tree.m): realisation j of the dynamics on
+    the j-th child of every branching node, stage weights scaled by md^(Nr - stage) up to the robust
+    horizon (:84-91; the root gets Nscenarios = md^Nr, :48-51), terminal weight P unscaled on the leaves
+    (:97-100), linear terms q = -Q.*xref, r = -R.*uref, p = q (benchmark/treeqp_main.m:147-160), leaf
+    bounds xNmin/xNmax, x0 pinned on the root and eliminated like the JSON driver does
+    (examples/solve_qp_json.cpp:353)."""
+    nxs_, nu = Bd[0].shape
+    nk = multistage_nk(md, Nr, Nh)
+    Nn = len(nk)
+    dad, stage, real = tree_tables(nk)
+    nx = np.full(Nn, nxs_, dtype=np.int32)
+    nus = np.where(nk > 0, nu, 0).astype(np.int32)
+    As, Bs, bs, Qd, Rd, q, r, lo, hi, ulo, uhi = ([] for _ in range(11))
+    for k in range(Nn):
+        leaf = nk[k] == 0
+        w = 1.0 if leaf else float(md ** max(Nr - stage[k], 0))
+        if k > 0:
+            As.append(Ad[real[k]].flatten(order="F")); Bs.append(Bd[real[k]].flatten(order="F")); bs.append(np.zeros(nxs_))
+        Qk = Pw if leaf else Qw
+        Qd.append(w * Qk); q.append(-(w * Qk) * xref)
+        lo.append(xNmin if leaf else xmin); hi.append(xNmax if leaf else xmax)
+        if not leaf:
+            Rd.append(w * Rw); r.append(-(w * Rw) * uref); ulo.append(umin); uhi.append(umax)
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    p = Problem(nk=nk, nx=nx, nu=nus, A=cat(As), B=cat(Bs), b=cat(bs), Qd=cat(Qd), Rd=cat(Rd), q=cat(q), r=cat(r),
+                xmin=cat(lo), xmax=cat(hi), umin=cat(ulo), umax=cat(uhi), lam0=np.zeros(int(nx.sum()) - nxs_),
+                meta=dict(name=name, md=md, Nr=Nr, Nh=Nh))
+    p.xmin[:nxs_] = x0
+    p.xmax[:nxs_] = x0
+    return eliminate_x0(p) if eliminate else p
+
+
+def _discretize(Ac, Bc, Ts):
+    """benchmark/common/discretize_model.m:8-10: expm([Ts*A Ts*B; 0 0])"""
+    n, m = Bc.shape
+    M = np.zeros((n + m, n + m))
+    M[:n, :n] = Ts * Ac
+    M[:n, n:] = Ts * Bc
+    E = _expm(M)
+    return E[:n, :n].copy(), E[:n, n:].copy()
+
+
+def quadcopter(md: int = 3, Nr: int = 2, Nh: int = 20, i_mpc: int = 12, nsim: int = 50, x0=None) -> Problem:
+    """Config 5, quadcopter attitude model (nx = 6: quaternion vector part + body rates, nu = 4 rotor speed
+    deviations), restating benchmark/quadcopter/initialize_quadcopter.m:33-114:
+    dynamics_quadcopter_mpc.m linearised at hover (x = 0, W_i = omega_hover(m)) -- the Jacobians the
+    harness gets from CasADi, written out by hand: d(quat)/d(Omega) = I/2, dOmega1/dW = a L [0 1 0 -1]/J1,
+    dOmega2/dW = a L [-1 0 1 0]/J2, dOmega3/dW = a_d L2 [1 -1 1 -1]/J3 with a = A Cl rho omega_hover,
+    a_d = A Cd rho omega_hover -- discretised exactly (Ts = 0.05), one realisation per mass in
+    linspace(8, 12, md) (import_benchmark.m:52-59); Q = [500 500 500 1e-3 1e-3 1e-3], R = 1e-3, P = Q,
+    |Omega| <= 1, |dW| <= 4, terminal state free, x0 = 0; reference = sample i_mpc of the attitude
+    reference (:57-83, myeul2quat.m)."""
+    rho, Ar, Cl, g, L, L2, J1, J2, J3, inf, Ts = 1.23, 0.1, 0.25, 9.81, 0.5, 1.0, 0.25, 0.25, 1.0, 1e8, 0.05
+    Cd = 0.3 * Cl
+    Ad, Bd = [], []
+    for m in np.linspace(8.0, 12.0, md):
+        wh = np.sqrt(2.0 * m * g / (Ar * Cl * rho) / 4.0)
+        Ac = np.zeros((6, 6)); Ac[:3, 3:] = 0.5 * np.eye(3)
+        Bc = np.zeros((6, 4))
+        a, ad = Ar * Cl * rho * wh, Ar * Cd * rho * wh
+        Bc[3] = a * L * np.array([0.0, 1.0, 0.0, -1.0]) / J1
+        Bc[4] = a * L * np.array([-1.0, 0.0, 1.0, 0.0]) / J2
+        Bc[5] = ad * L2 * np.array([1.0, -1.0, 1.0, -1.0]) / J3
+        A_, B_ = _discretize(Ac, Bc, Ts)
+        Ad.append(A_); Bd.append(B_)
+    # attitude reference (initialize_quadcopter.m:57-83)
+    period, ang, lam = nsim // 4, -1.0 * np.pi / 2 / 9 * 5 * 0.1, 0.3
+    ref = np.zeros(3)
+    for i in range(i_mpc):
+        ph = (i // period) % 3
+        s1, s2 = (+1, -1) if ph == 0 else ((-1, -1) if ph == 1 else (-1, +1))
+        ref = np.array([ref[0] - lam * (ref[0] + s1 * ang), ref[1] - lam * (ref[1] + s2 * ang), 0.0])
+    rr, pp, yy = ref
+    cy, sy, cr, sr, cp, sp = np.cos(yy / 2), np.sin(yy / 2), np.cos(rr / 2), np.sin(rr / 2), np.cos(pp / 2), np.sin(pp / 2)
+    xref = np.array([cy * sr * cp - sy * cr * sp, cy * cr * sp + sy * sr * cp, sy * cr * cp - cy * sr * sp, 0.0, 0.0, 0.0])
+    Qw = np.array([500.0, 500.0, 500.0, 1e-3, 1e-3, 1e-3])
+    xmax = np.array([inf, inf, inf, 1.0, 1.0, 1.0])
+    return _benchmark_tree(Ad, Bd, Qw, np.full(4, 1e-3), Qw, xref, np.zeros(4), -xmax, xmax, np.full(4, -4.0), np.full(4, 4.0),
+                           np.full(6, -inf), np.full(6, inf), np.zeros(6) if x0 is None else np.asarray(x0, float),
+                           md, Nr, Nh, "quadcopter")
+
+
+def crane(md: int = 3, Nr: int = 2, Nh: int = 20, xref0: float = 0.2, x0=None) -> Problem:
+    """Config 5, overhead crane (nx = 4: cart position/velocity, cable angle/rate; nu = 1 cart
+    acceleration), restating benchmark/crane/initialize_crane.m:33-72 with dynamics_crane.m linearised at
+    the origin: A_c = [0 1 0 0; 0 0 0 0; 0 0 0 1; 0 0 -g -b], B_c = [0; 1; 0; -1], Ts = 0.2, friction
+    b in linspace(0.1, 0.3, md) (import_benchmark.m:72-79); Q = [10 1 1 1], R = 0.1, P = Q, |v| <= 0.2,
+    |omega| <= 0.4 (also on the leaves), |a| <= 0.5, x0 = 0, position reference 0.2."""
+    g, inf, Ts = 9.81, 1e8, 0.2
+    Ad, Bd = [], []
+    for bf in np.linspace(0.1, 0.3, md):
+        Ac = np.zeros((4, 4)); Ac[0, 1] = 1.0; Ac[2, 3] = 1.0; Ac[3, 2] = -g; Ac[3, 3] = -bf
+        Bc = np.array([[0.0], [1.0], [0.0], [-1.0]])
+        A_, B_ = _discretize(Ac, Bc, Ts)
+        Ad.append(A_); Bd.append(B_)
+    Qw = np.array([10.0, 1.0, 1.0, 1.0])
+    xmax = np.array([inf, 0.2, inf, 0.4])
+    return _benchmark_tree(Ad, Bd, Qw, np.array([0.1]), Qw, np.array([xref0, 0.0, 0.0, 0.0]), np.zeros(1), -xmax, xmax,
+                           np.array([-0.5]), np.array([0.5]), -xmax, xmax, np.zeros(4) if x0 is None else np.asarray(x0, float),
+                           md, Nr, Nh, "crane")
+
+
+def densify_scaled(prob: Problem, seed: int = 1, coupling: float = 0.1, s_scale: float = 0.05) -> Problem:
+    """Dense stage Hessians for weights that span decades (quadcopter: 500 ... 1e-3): the coupling of
+    examples/random_qp_utils/generate_random_tree.m:65-70 applied in the scaled metric,
+    Q <- D^(1/2) (I + coupling (G + G')/n) D^(1/2) with D = diag(Qd) (positive definite for coupling < 1),
+    R likewise, S <- s_scale * sqrt(R_i Q_j) * U(0,1)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    Q, R, S = [], [], []
+    ix = iu = 0
+    for k in range(prob.Nn):
+        nx, nu = int(prob.nx[k]), int(prob.nu[k])
+        dq, dr = np.sqrt(prob.Qd[ix:ix + nx]), np.sqrt(prob.Rd[iu:iu + nu])
+        G = rng.random((nx, nx))
+        Q.append((np.outer(dq, dq) * (np.eye(nx) + coupling * (G + G.T) / max(nx, 1))).flatten(order="F"))
+        G = rng.random((nu, nu))
+        R.append((np.outer(dr, dr) * (np.eye(nu) + coupling * (G + G.T) / max(nu, 1))).flatten(order="F"))
+        S.append((s_scale * np.outer(dr, dq) * rng.random((nu, nx))).flatten(order="F"))
+        ix += nx; iu += nu
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    return Problem(nk=prob.nk, nx=prob.nx, nu=prob.nu, A=prob.A, B=prob.B, b=prob.b, q=prob.q, r=prob.r,
+                   xmin=prob.xmin, xmax=prob.xmax, umin=prob.umin, umax=prob.umax,
+                   Q=cat(Q), R=cat(R), S=cat(S), lam0=prob.lam0, meta=dict(prob.meta, dense=True))
