@@ -360,7 +360,8 @@ def bench_batch(lib, n=4096, reps=3, rank=0, world=1, barrier=None, max_over_ran
            "qp_per_s_resident": n / min(t_res), "qp_per_s_e2e": n / min(t_e2e), "ms_per_batch_resident": 1e3 * min(t_res),
            "ms_per_batch_e2e": 1e3 * min(t_e2e), "newton_iters_max": int(iters.max()), "newton_iters_median": float(np.median(iters)),
            "h2d_bytes": st["h2d_bytes"], "d2h_bytes": st["d2h_bytes"], "launches": st["kernel_launches"],
-           "roofline": solve_roofline(probs[0], int(iters.sum()) * world, min(t_res), (st["h2d_bytes"] + st["d2h_bytes"]) * world,
+           # per GPU: this rank's QPs over the (max over ranks) time, against ONE GPU's HBM peak
+           "roofline": solve_roofline(probs[0], int(iters.sum()), min(t_res), st["h2d_bytes"] + st["d2h_bytes"],
                                       st["ls_total"] / max(int(iters.sum()), 1))}
     if world > 1:
         out["scaling"] = "strong (4096 QPs in total)"
@@ -449,6 +450,11 @@ def bench_dense(lib, reps=5):
         rec = {"nodes": int(prob.Nn), "status": int(st), "newton_iters": int(qp_out.iter), "ms_per_solve_resident": best,
                "ms_per_solve_e2e": e2e, "us_per_newton_iter": 1e3 * best / max(qp_out.iter, 1),
                "kkt": float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))}
+        lib.lib.treeqp_b200_set_profiling(1)
+        s.solve_resident()
+        rec["profiled_kernel_ms"] = {k: (round(v[0], 3), v[1]) for k, v in sorted(s.stats()["kernels"].items(), key=lambda kv: -kv[1][0])}
+        rec["launches_per_solve"] = s.stats()["kernel_launches"]
+        lib.lib.treeqp_b200_set_profiling(0)
         sst = s.stats()
         rec["roofline"] = solve_roofline(prob, int(qp_out.iter), 1e-3 * best, sst["h2d_bytes"] + sst["d2h_bytes"],
                                          sst["ls_total"] / max(int(qp_out.iter), 1))
@@ -589,10 +595,15 @@ def run_single(lib, args, prob, barrier, max_over_ranks, clocks, rank):
     assert st2 == 0 and qp_out.iter == stats["iter"]
     kkt = float(lib.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
     kkt_dev = solver.kkt_resident()  # the same certificate evaluated on the device (k_kkt)
-    # ---- one profiled solve (CUDA events around every launch) for the roofline block
-    lib.lib.treeqp_b200_set_profiling(1)
+    # ---- profiled solves for the roofline block: level 2 = CUDA events around every launch, but ONE pair
+    # around each PDL-chained level sweep (the sweep is timed the way it runs); level 1 = a pair around
+    # every launch (serialises the level kernels), kept next to it
+    lib.lib.treeqp_b200_set_profiling(2)
     solver.solve_resident()
     prof = solver.stats()
+    lib.lib.treeqp_b200_set_profiling(1)
+    solver.solve_resident()
+    prof["serialised"] = solver.stats()["kernels"]
     lib.lib.treeqp_b200_set_profiling(0)
     sol = out_dict(qp_out, st2)
     solver.destroy()
@@ -654,9 +665,12 @@ def run_sharded(lib, args, prob, rank, world, local, dist, barrier, max_over_ran
     h2d = torch.tensor([float(e2e_stats["h2d_bytes"]), float(e2e_stats["d2h_bytes"])], dtype=torch.float64, device="cuda")
     dist.all_reduce(h2d)
     e2e_stats = dict(e2e_stats, h2d_bytes=int(h2d[0].item()), d2h_bytes=int(h2d[1].item()))
-    lib.lib.treeqp_b200_set_profiling(1)
+    lib.lib.treeqp_b200_set_profiling(2)
     sh.solve_resident()
     prof = sh.stats()
+    lib.lib.treeqp_b200_set_profiling(1)
+    sh.solve_resident()
+    prof["serialised"] = sh.stats()["kernels"]
     lib.lib.treeqp_b200_set_profiling(0)
     comm_ms = prof["kernels"].get("nccl+pack", (0.0, 0))
     shard = {"cut_depth": plan["cut_depth"], "cut_nodes": plan["ncut"], "local_nodes": plan["n_local"],
@@ -702,8 +716,12 @@ def roofline_block(prob, prof, world, depth):
            "algorithmic_bytes_per_launch": cb[top] * share / lpc[top], "peak_source": hbm_src,
            "algorithmic_bytes_per_call": cb[top] * share, "launches_per_call": lpc[top],
            "avg_launch_us": avg_us, "kernel_share_of_profiled_solve": t_ms / prof["gpu_ms"],
-           "note": "event times come from one solve with an event pair around every launch (launches serialised, no PDL overlap)",
-           "per_kernel": per_kernel}
+           "note": "CUDA events on the solver's stream inside one extra solve: a pair around every launch, except that the "
+                   "launches of one level sweep (k_build_factor / k_backsolve_fused, one launch per depth, chained with "
+                   "programmatic dependent launch) share ONE pair -- avg_launch_us = sweep time / launches of the sweep, "
+                   "measured with the overlap the solver runs with; per_kernel_serialised = a pair around every single launch",
+           "per_kernel": per_kernel,
+           "per_kernel_serialised": {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(prof.get("serialised", {}).items(), key=lambda kv: -kv[1][0])}}
     if top in ("k_build_factor", "k_factor_level"):
         tf = alg["factor_flops"] * share * calls / (t_ms * 1e-3) / 1e12
         out["compute"] = {"achieved": tf, "peak": fp64, "unit": "TFLOP/s", "frac": tf / fp64, "peak_source": fp64_src,

@@ -62,6 +62,13 @@ struct tqb_comm
 {
     ncclComm_t comm;
     int rank, nranks, device;
+    /* peer mailboxes (tqb_comm_p2p_setup) */
+    int p2p_ready;
+    tqb_p2p_dev p2p;
+    void *box;                       /* this rank's mailbox allocation */
+    void *peer_box[TQB_P2P_MAXR];    /* IPC mappings of the peers' */
+    unsigned long long seq;
+    int *h_err;
 };
 
 #define NCK(call)                                                                                   \
@@ -105,9 +112,90 @@ extern "C" tqb_comm *tqb_comm_create(int rank, int nranks, const char *id128, in
     return c;
 }
 
+/* ---- peer mailboxes over NVLink (see comm.cuh) ---- */
+#define P2P_HEADER_BYTES 4096 /* flags [2][MAXR] u64 + error word, then the data slots */
+
+int tqb_comm_p2p_setup(tqb_comm *c, size_t cap_doubles, cudaStream_t s)
+{
+    if (c->p2p_ready) return (size_t) c->p2p.cap >= cap_doubles ? 0 : 1;
+    const char *e = getenv("TREEQP_B200_NO_P2P");
+    int ok = !(e && e[0] == '1') && c->nranks <= TQB_P2P_MAXR && c->nranks > 1;
+    const size_t bytes = P2P_HEADER_BYTES + sizeof(double) * 2 * (size_t) c->nranks * cap_doubles;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (ok && cudaMalloc(&c->box, bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaMemset(c->box, 0, bytes) != cudaSuccess) ok = 0;
+    if (ok && cudaIpcGetMemHandle(&mine, c->box) != cudaSuccess) ok = 0;
+    /* every rank takes part in the hand-shake whatever its own outcome: handle + ok flag, all-gathered */
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    char *h_send = (char *) calloc(1, rec), *h_all = (char *) calloc((size_t) c->nranks, rec);
+    memcpy(h_send, &mine, sizeof mine);
+    h_send[sizeof mine] = (char) ok;
+    char *d_send = NULL, *d_all = NULL;
+    if (cudaMalloc(&d_send, rec) != cudaSuccess || cudaMalloc(&d_all, rec * (size_t) c->nranks) != cudaSuccess) return 1;
+    cudaMemcpyAsync(d_send, h_send, rec, cudaMemcpyHostToDevice, s);
+    NCK(g_nccl.AllGather(d_send, d_all, rec, ncclChar, c->comm, s));
+    cudaMemcpyAsync(h_all, d_all, rec * (size_t) c->nranks, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    for (int r = 0; r < c->nranks; r++) ok = ok && h_all[(size_t) r * rec + sizeof mine];
+    for (int r = 0; r < c->nranks && ok; r++)
+    {
+        if (r == c->rank) { c->peer_box[r] = c->box; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_all + (size_t) r * rec, sizeof h);
+        if (cudaIpcOpenMemHandle(&c->peer_box[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+        {
+            fprintf(stderr, "[treeqp_b200] rank %d: cudaIpcOpenMemHandle(rank %d) failed (%s): NCCL collectives stay on the data path\n",
+                    c->rank, r, cudaGetErrorString(cudaGetLastError()));
+            ok = 0;
+        }
+    }
+    /* agree on the outcome: one more tiny all-gather (a rank that failed to map a peer vetoes) */
+    h_send[0] = (char) ok;
+    cudaMemcpyAsync(d_send, h_send, 1, cudaMemcpyHostToDevice, s);
+    NCK(g_nccl.AllGather(d_send, d_all, 1, ncclChar, c->comm, s));
+    cudaMemcpyAsync(h_all, d_all, (size_t) c->nranks, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    for (int r = 0; r < c->nranks; r++) ok = ok && h_all[r];
+    cudaFree(d_send); cudaFree(d_all); free(h_send); free(h_all);
+    if (!ok) return 1;
+    for (int r = 0; r < c->nranks; r++)
+    {
+        c->p2p.flags[r] = (unsigned long long *) c->peer_box[r];
+        c->p2p.slots[r] = (double *) ((char *) c->peer_box[r] + P2P_HEADER_BYTES);
+    }
+    c->p2p.err = (int *) ((char *) c->box + sizeof(unsigned long long) * 2 * TQB_P2P_MAXR);
+    c->p2p.rank = c->rank; c->p2p.nranks = c->nranks; c->p2p.cap = (int) cap_doubles;
+    if (cudaMallocHost(&c->h_err, sizeof(int)) != cudaSuccess) return 1;
+    *c->h_err = 0;
+    c->seq = 0;
+    c->p2p_ready = 1;
+    return 0;
+}
+
+const tqb_p2p_dev *tqb_comm_p2p(const tqb_comm *c) { return (c && c->p2p_ready) ? &c->p2p : NULL; }
+unsigned long long tqb_comm_p2p_next_seq(tqb_comm *c) { return ++c->seq; }
+
+/* stream-ordered read of the time-out word (call before a synchronisation, check *after* it) */
+int tqb_comm_p2p_error(tqb_comm *c, cudaStream_t s)
+{
+    if (!c->p2p_ready) return 0;
+    if (*c->h_err) return 1;
+    cudaMemcpyAsync(c->h_err, c->p2p.err, sizeof(int), cudaMemcpyDeviceToHost, s);
+    return 0;
+}
+
 extern "C" void tqb_comm_destroy(tqb_comm *c)
 {
     if (!c) return;
+    if (c->p2p_ready)
+    {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < c->nranks; r++)
+            if (r != c->rank && c->peer_box[r]) cudaIpcCloseMemHandle(c->peer_box[r]);
+        cudaFreeHost(c->h_err);
+    }
+    if (c->box) cudaFree(c->box);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     free(c);
 }

@@ -43,7 +43,10 @@ static thread_local const char *const *k_names = k_names_generic;
 static int g_profile = -1;
 #define TQB_MAX_EVENTS 65536
 
-extern "C" void tqb_set_profiling(int on) { g_profile = on ? 1 : 0; }
+/* 0 off | 1 an event pair around EVERY launch (serialises the launches: no PDL overlap between the level
+ * kernels) | 2 as 1, but one pair around each leaves-to-root / root-to-leaves sweep, whose launches stay
+ * chained with programmatic dependent launch -- the sweep is timed the way it runs */
+extern "C" void tqb_set_profiling(int on) { g_profile = on < 0 ? 0 : on; }
 extern "C" int tqb_num_kernel_classes(void) { return K_NCLASS; }
 extern "C" const char *tqb_kernel_class_name(int k) { return (k >= 0 && k < K_NCLASS) ? k_names[k] : ""; }
 static int profiling_on(void)
@@ -51,7 +54,7 @@ static int profiling_on(void)
     if (g_profile < 0)
     {
         const char *e = getenv("TREEQP_B200_PROFILE");
-        g_profile = (e && e[0] == '1') ? 1 : 0;
+        g_profile = (e && e[0] >= '1' && e[0] <= '2') ? e[0] - '0' : 0;
     }
     return g_profile;
 }
@@ -60,7 +63,9 @@ struct tqb_device
 {
     cudaEvent_t *pev; /* profiling event pool (pairs) */
     unsigned char *pev_class;
+    unsigned short *pev_cnt; /* launches an event pair brackets */
     int pev_n, pev_on;
+    int in_sweep, sweep_launches, sweep_pe; /* profiling level 2: ONE event pair around a PDL-chained level sweep */
     tqb_dims dims;
     int *d_int;
     double *d_in, *d_work;
@@ -92,6 +97,7 @@ struct tqb_device
     int cut_depth, ncut, my_cut0, my_ncut;
     int *d_cut_nodes;
     double *d_send, *d_recv, *d_tred;
+    const tqb_p2p_dev *p2p; /* peer mailboxes over NVLink; NULL: NCCL collectives */
 };
 
 extern "C" const char *tqb_cuda_last_error(void) { return g_err; }
@@ -188,7 +194,8 @@ static int launch_bf(tqb_device *D, int begin, int cnt, int kp, int pre_ok)
         CK(cudaFuncSetAttribute(k_build_factor<NX, NU, MD, PNX, ROOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr_done = true;
     }
-    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (D->in_sweep) D->sweep_launches++;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
     CK(launch_pdl(k_build_factor<NX, NU, MD, PNX, ROOT>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
                   D->v, begin, cnt, kp, pre_ok));
@@ -201,7 +208,8 @@ template <int NX, int MD>
 static int launch_bs(tqb_device *D, int begin, int cnt)
 {
     const int wpb = 4;
-    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (D->in_sweep) D->sweep_launches++;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
     CK(launch_pdl(k_backsolve_fused<NX, MD>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, begin, cnt));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
@@ -221,7 +229,8 @@ static int launch_bf_chain(tqb_device *D, int top_begin, int cnt, int nlev, int 
         CK(cudaFuncSetAttribute(k_build_factor_chain<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr_done = true;
     }
-    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (D->in_sweep) D->sweep_launches++;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
     CK(launch_pdl(k_build_factor_chain<NX, NU>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
                   D->v, top_begin, cnt, nlev, kp_bottom, pre_ok));
@@ -234,7 +243,8 @@ template <int NX>
 static int launch_bs_chain(tqb_device *D, int top_begin, int cnt, int nlev)
 {
     const int wpb = 4;
-    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (D->in_sweep) D->sweep_launches++;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
     CK(launch_pdl(k_backsolve_chain<NX>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, top_begin, cnt, nlev));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
@@ -248,7 +258,8 @@ static int launch_bf_chain2(tqb_device *D, int top_begin, int cnt, int nlev, int
     using Cfg = HalfCfg<NX, NU>;
     const int wpb = 4, warps = (cnt + 1) / 2;
     const size_t smem = (size_t) wpb * 2 * Cfg::SMEM * sizeof(double);
-    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (D->in_sweep) D->sweep_launches++;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
     CK(launch_pdl(k_build_factor_chain2<NX, NU>, dim3((warps + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
                   D->v, top_begin, cnt, nlev, kp_bottom, pre_ok));
@@ -261,7 +272,8 @@ template <int NX>
 static int launch_bs_chain2(tqb_device *D, int top_begin, int cnt, int nlev)
 {
     const int wpb = 4, warps = (cnt + 1) / 2;
-    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (D->in_sweep) D->sweep_launches++;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
     CK(launch_pdl(k_backsolve_chain2<NX>, dim3((warps + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, top_begin, cnt, nlev));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
@@ -436,8 +448,10 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
     }
     {   /* leaf records for k_stage_fused; it needs leaves without inputs and few (kid, column) pairs */
         int nleaf = 0, ok = 1;
+        /* ghost nodes of a sharded solve (cut nodes owned by another rank) are leaves of the local tree
+         * whose stage solution arrives with the exchange: no stage QP here */
         for (int g = 0; g < d->Nn; g++)
-            if (T.nkids[g] == 0) { nleaf++; if (T.nu[g] != 0 || T.nx[g] != (T.dad[g] < 0 ? PNX : NX)) ok = 0; }
+            if (T.nkids[g] == 0 && !(ghost && ghost[g])) { nleaf++; if (T.nu[g] != 0 || T.nx[g] != (T.dad[g] < 0 ? PNX : NX)) ok = 0; }
         for (int l = 0; l < d->Nh; l++)
             if (D->lvl_md[l] * (NX + NU) > TQB_STAGE_MAXPAIR || D->lvl_md[l] * NX > 32) ok = 0;
         const char *e2 = getenv("TREEQP_B200_GENERIC_STAGE");
@@ -447,7 +461,7 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
             int *h = (int *) calloc(4 * (size_t) nleaf + 4, sizeof(int));
             size_t e = 0;
             for (int g = 0; g < d->Nn; g++)
-                if (T.nkids[g] == 0)
+                if (T.nkids[g] == 0 && !(ghost && ghost[g]))
                 {
                     int *r = h + 4 * e++;
                     r[0] = g; r[1] = T.xoff[g]; r[2] = T.tree[g]; r[3] = T.dad[g] < 0;
@@ -627,7 +641,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
-    if (D->pev) { for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) cudaEventDestroy(D->pev[i]); free(D->pev); free(D->pev_class); }
+    if (D->pev) { for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) cudaEventDestroy(D->pev[i]); free(D->pev); free(D->pev_class); free(D->pev_cnt); }
     if (D->d_kkt) cudaFree(D->d_kkt);
     if (D->stream) cudaStreamDestroy(D->stream);
     free(D->lvl_ptr);
@@ -715,6 +729,23 @@ extern "C" int tqb_device_kkt(tqb_device *D, double *h_kkt)
 
 static inline int cdiv(long long a, int b) { return (int) ((a + b - 1) / b); }
 
+static void sweep_begin(tqb_device *D, int cls)
+{
+    if (D->pev_on != 2 || D->pev_n >= TQB_MAX_EVENTS) return;
+    D->sweep_pe = D->pev_n++;
+    D->pev_class[D->sweep_pe] = (unsigned char) cls;
+    D->in_sweep = 1; D->sweep_launches = 0;
+    cudaEventRecord(D->pev[2 * D->sweep_pe], D->stream);
+}
+
+static void sweep_end(tqb_device *D)
+{
+    if (!D->in_sweep) return;
+    cudaEventRecord(D->pev[2 * D->sweep_pe + 1], D->stream);
+    D->pev_cnt[D->sweep_pe] = (unsigned short) D->sweep_launches;
+    D->in_sweep = 0;
+}
+
 extern "C" int tqb_device_enable_sharding(tqb_device *D, tqb_comm *comm, int cut_depth, int ncut, int my_cut0,
                                           int my_ncut, const int *cut_nodes_local)
 {
@@ -733,6 +764,11 @@ extern "C" int tqb_device_enable_sharding(tqb_device *D, tqb_comm *comm, int cut
     CK(cudaMalloc(&D->d_tred, sizeof(double) * (1 + TQB_LS_NT) * (size_t) D->dims.nT));
     D->v.t_red = D->d_tred;
     D->v.sharded = 1;
+    {   /* peer mailboxes for the per-iteration exchanges (comm.cuh); NCCL stays as the fall-back */
+        size_t cap = per * (size_t) my_ncut, cap2 = (size_t) (1 + TQB_LS_NT) * D->dims.nT;
+        if (cap2 > cap) cap = cap2;
+        D->p2p = (ncut * per <= 65536 && tqb_comm_p2p_setup(comm, cap, D->stream) == 0) ? tqb_comm_p2p(comm) : NULL;
+    }
     return 0;
 }
 
@@ -744,6 +780,14 @@ static int exchange_cut_nodes(tqb_device *D)
     const size_t per = (size_t) nx * (nx + 3);
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
+    if (D->p2p)
+    {
+        k_cut_exchange<<<1, 512, 0, D->stream>>>(D->v, *D->p2p, tqb_comm_p2p_next_seq(D->comm), D->d_cut_nodes, D->my_cut0,
+                                                  D->my_ncut, D->ncut, nx);
+        if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+        D->launches++;
+        return 0;
+    }
     k_cut_pack<<<(D->my_ncut + 3) / 4, 128, 0, D->stream>>>(D->v, D->d_cut_nodes, D->my_cut0, D->my_ncut, nx, D->d_send);
     if (tqb_comm_allgather(D->comm, D->d_send, D->d_recv, per * (size_t) D->my_ncut, D->stream)) return 1;
     k_cut_unpack<<<(D->ncut + 3) / 4, 128, 0, D->stream>>>(D->v, D->d_cut_nodes, D->ncut, nx, D->d_recv);
@@ -762,7 +806,14 @@ static int allreduce_tree_sums(tqb_device *D, int use_a, int use_b, int a_is_max
     if (use_a) { k_tree_partial<<<grid, 128, 0, D->stream>>>(v, v.cva, D->d_tred, a_is_max); D->launches++; }
     if (use_b) { k_tree_partial<<<grid, 128, 0, D->stream>>>(v, v.cvb, D->d_tred + nT, 0); D->launches++; }
     int rc = 0;
-    if (use_a && use_b && !a_is_max) rc = tqb_comm_allreduce(D->comm, D->d_tred, 2 * (size_t) nT, 0, D->stream);
+    if (D->p2p)
+    {   /* one exchange: [0, nT) from cva (max or sum), [nT, 2 nT) from cvb (sum) */
+        double *buf = use_a ? D->d_tred : D->d_tred + nT;
+        const int cnt = (use_a ? nT : 0) + (use_b ? nT : 0);
+        k_red_exchange<<<1, 256, 0, D->stream>>>(*D->p2p, tqb_comm_p2p_next_seq(D->comm), buf, cnt, (use_a && a_is_max) ? nT : 0);
+        D->launches++;
+    }
+    else if (use_a && use_b && !a_is_max) rc = tqb_comm_allreduce(D->comm, D->d_tred, 2 * (size_t) nT, 0, D->stream);
     else
     {
         if (use_a) rc |= tqb_comm_allreduce(D->comm, D->d_tred, (size_t) nT, a_is_max, D->stream);
@@ -782,7 +833,14 @@ static int allreduce_ls_batch(tqb_device *D, int first)
     k_tree_partial_ls<<<dim3((nT + 3) / 4, 1 + TQB_LS_NT), 128, 0, D->stream>>>(v, D->d_tred);
     D->launches++;
     const size_t off = first ? 0 : (size_t) nT;
-    const int rc = tqb_comm_allreduce(D->comm, D->d_tred + off, (size_t) (1 + TQB_LS_NT) * nT - off, 0, D->stream);
+    int rc = 0;
+    if (D->p2p)
+    {
+        k_red_exchange<<<1, 256, 0, D->stream>>>(*D->p2p, tqb_comm_p2p_next_seq(D->comm), D->d_tred + off,
+                                                  (int) ((size_t) (1 + TQB_LS_NT) * nT - off), 0);
+        D->launches++;
+    }
+    else rc = tqb_comm_allreduce(D->comm, D->d_tred + off, (size_t) (1 + TQB_LS_NT) * nT - off, 0, D->stream);
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     return rc;
 }
@@ -800,11 +858,14 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
 {
     D->pev_on = profiling_on();
     D->pev_n = 0;
+    D->in_sweep = 0;
+    if (D->pev_cnt) memset(D->pev_cnt, 0, sizeof(unsigned short) * TQB_MAX_EVENTS);
     k_names = D->fast ? k_names_fused : k_names_generic;
     if (D->pev_on && !D->pev)
     {
         D->pev = (cudaEvent_t *) calloc(2 * TQB_MAX_EVENTS, sizeof(cudaEvent_t));
         D->pev_class = (unsigned char *) calloc(TQB_MAX_EVENTS, 1);
+        D->pev_cnt = (unsigned short *) calloc(TQB_MAX_EVENTS, sizeof(unsigned short));
         for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) CK(cudaEventCreate(&D->pev[i]));
     }
     View &v = D->v;
@@ -832,10 +893,16 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         if (D->fast)
         {   /* gradient + Hessian + factorisation fused, leaves to root; the termination test comes
              * after the sweep (the sweep of the last iteration is the price of the fusion) */
+            sweep_begin(D, K_FACTOR);
             for (int l = Nh - 1; l >= 0; l--)
             {
                 const bool exch = D->comm && l == D->cut_depth - 1;
-                if (exch && exchange_cut_nodes(D)) return 1;
+                if (exch)
+                {   /* the exchange is its own class: close the bracket around it */
+                    sweep_end(D);
+                    if (exchange_cut_nodes(D)) return 1;
+                    sweep_begin(D, K_FACTOR);
+                }
                 const int pre_ok = (l < Nh - 1 && !exch) ? 1 : 0;
                 const int lt = chain_top(D, l);
                 if (lt < l)
@@ -846,10 +913,12 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 }
                 if (fused_factor_level(D, l, pre_ok)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
             }
+            sweep_end(D);
             LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
             if (D->comm && allreduce_tree_sums(D, 1, 0, o->termCondition == 2)) return 1;
             LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
             if (peek_counter(D, 0, 4)) return 1;
+            sweep_begin(D, K_BACK);
             for (int l = 1; l < Nh; l++)
             {
                 const int lb = chain_bottom(D, l);
@@ -861,6 +930,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 }
                 if (fused_backsolve_level(D, l)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
             }
+            sweep_end(D);
         }
         else
         {
@@ -933,12 +1003,19 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         if (v.has_dense) LAUNCH(K_FINISH, k_finish_dense, cdiv(v.Nn, 256), 256, 0, v);
     }
     CK(cudaEventRecord(D->ev1, D->stream));
+    if (D->comm) tqb_comm_p2p_error(D->comm, D->stream);
     CK(cudaMemcpyAsync(h_status, v.status, sizeof(int) * (size_t) (2 * nT), cudaMemcpyDeviceToHost, D->stream));
     CK(cudaMemcpyAsync(D->h_counters, v.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, D->stream));
     if (ls_iters256)
         CK(cudaMemcpyAsync(ls_iters256, v.ls_hist, sizeof(int) * 256, cudaMemcpyDeviceToHost, D->stream));
     CK(cudaStreamSynchronize(D->stream));
     CK(cudaGetLastError());
+    if (D->comm && tqb_comm_p2p_error(D->comm, D->stream))
+    {
+        snprintf(g_err, sizeof g_err, "sharded solve: a peer GPU did not answer an exchange within 3 s");
+        fprintf(stderr, "[treeqp_b200] %s\n", g_err);
+        return 1;
+    }
     (void) h_iter; /* h_iter == h_status + nT: filled by the copy above (status and iter are adjacent) */
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, D->ev0, D->ev1));
@@ -954,7 +1031,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             float t = 0.f;
             CK(cudaEventElapsedTime(&t, D->pev[2 * i], D->pev[2 * i + 1]));
             kernel_ms16[D->pev_class[i]] += t;
-            kernel_count16[D->pev_class[i]]++;
+            kernel_count16[D->pev_class[i]] += D->pev_cnt[i] ? D->pev_cnt[i] : 1;
         }
     }
     return 0;

@@ -24,6 +24,7 @@
 #include "../host/host_internal.h"
 
 #include "warp_helpers.cuh"
+#include "comm.cuh"
 #include "tdunes_dense.cuh"
 
 #define TQB_RUNNING (-1)
@@ -432,6 +433,86 @@ __global__ void k_cut_unpack(View v, const int *cut_nodes, int count, int nx, co
     }
     double *S = v.schur + (size_t) g * nx * nx;
     for (int e = lane; e < nx * nx; e += 32) S[e] = src[3 * nx + e];
+}
+
+/* ---- the same exchanges through the peer mailboxes (comm.cuh), ONE CTA each ------------------------ */
+
+/* all payload stores of this CTA are done -> publish `seq` to every peer, wait for every peer's `seq` */
+__device__ __forceinline__ void p2p_signal_wait(const tqb_p2p_dev &x, unsigned long long seq)
+{
+    __threadfence_system();
+    __syncthreads();
+    const int par = (int) (seq & 1);
+    if ((int) threadIdx.x < x.nranks)
+    {
+        const int r = threadIdx.x;
+        volatile unsigned long long *theirs = x.flags[r] + par * TQB_P2P_MAXR + x.rank;
+        *theirs = seq;
+        volatile unsigned long long *mine = x.flags[x.rank] + par * TQB_P2P_MAXR + r;
+        const long long t0 = clock64();
+        while (*mine != seq)
+            if (clock64() - t0 > 6000000000LL) { atomicExch(x.err, 1); break; } /* ~3 s: a peer died */
+    }
+    __syncthreads();
+    __threadfence_system();
+}
+
+__device__ __forceinline__ double *p2p_slot(const tqb_p2p_dev &x, int owner, unsigned long long seq, int src)
+{
+    return x.slots[owner] + ((size_t) (seq & 1) * x.nranks + src) * x.cap;
+}
+
+/* cut nodes -> every rank (k_cut_pack + all-gather + k_cut_unpack in one launch) */
+__global__ void __launch_bounds__(512) k_cut_exchange(View v, tqb_p2p_dev x, unsigned long long seq, const int *cut_nodes,
+                                                      int my_cut0, int my_ncut, int ncut, int nx)
+{
+    const int per = nx * (nx + 3), nmine = my_ncut * per;
+    for (int e = threadIdx.x; e < nmine; e += blockDim.x)
+    {
+        const int w = e / per, i = e - w * per;
+        const int g = cut_nodes[my_cut0 + w], xo = v.T.xoff[g];
+        double val;
+        if (i < nx) val = v.x[xo + i];
+        else if (i < 2 * nx) val = v.P[xo + i - nx];
+        else if (i < 3 * nx) val = v.rsub[xo + i - 2 * nx];
+        else val = v.schur[(size_t) g * nx * nx + (i - 3 * nx)];
+        for (int r = 0; r < x.nranks; r++) p2p_slot(x, r, seq, x.rank)[e] = val;
+    }
+    p2p_signal_wait(x, seq);
+    const int ntot = ncut * per;
+    for (int e = threadIdx.x; e < ntot; e += blockDim.x)
+    {
+        const int q = e / per, i = e - q * per, src = q / my_ncut, w = q - src * my_ncut;
+        if (src == x.rank) continue; /* own nodes are already in place */
+        const double val = __ldcv(p2p_slot(x, x.rank, seq, src) + w * per + i);
+        const int g = cut_nodes[q], xo = v.T.xoff[g];
+        if (i < nx) v.x[xo + i] = val;
+        else if (i < 2 * nx) v.P[xo + i - nx] = val;
+        else if (i < 3 * nx) v.rsub[xo + i - 2 * nx] = val;
+        else v.schur[(size_t) g * nx * nx + (i - 3 * nx)] = val;
+    }
+}
+
+/* in-place all-reduce of buf[0..count): the first `nmax` entries with max, the others as sums in rank
+ * order (the same association on every rank: all ranks hold bit-identical results) */
+__global__ void __launch_bounds__(256) k_red_exchange(tqb_p2p_dev x, unsigned long long seq, double *buf, int count, int nmax)
+{
+    for (int e = threadIdx.x; e < count; e += blockDim.x)
+    {
+        const double val = buf[e];
+        for (int r = 0; r < x.nranks; r++) p2p_slot(x, r, seq, x.rank)[e] = val;
+    }
+    p2p_signal_wait(x, seq);
+    for (int e = threadIdx.x; e < count; e += blockDim.x)
+    {
+        double acc = __ldcv(p2p_slot(x, x.rank, seq, 0) + e);
+        for (int r = 1; r < x.nranks; r++)
+        {
+            const double t = __ldcv(p2p_slot(x, x.rank, seq, r) + e);
+            acc = e < nmax ? fmax(acc, t) : acc + t;
+        }
+        buf[e] = acc;
+    }
 }
 
 /* termination test per tree (dual_Newton_tree.c:542-546) */

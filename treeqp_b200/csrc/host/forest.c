@@ -451,7 +451,21 @@ int tqb_forest_warm_start(tqb_forest *f)
 #define TQB_UPLOAD_CHUNK_DOUBLES (3LL << 20) /* 24 MB of input per pipeline stage */
 #endif
 
+static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const int *gmap, double *tail_ms);
+
 int tqb_forest_pack_upload(tqb_forest *f, const tree_qp_in *const *qp, double *tail_ms)
+{
+    return pack_upload_impl(f, qp, NULL, tail_ms);
+}
+
+/* sharded solve: the local tree's nodes are nodes gmap[j] of the caller's FULL tree_qp_in */
+int tqb_forest_pack_upload_mapped(tqb_forest *f, const tree_qp_in *full_qp, const int *gmap, double *tail_ms)
+{
+    const tree_qp_in *one[1] = {full_qp};
+    return pack_upload_impl(f, one, gmap, tail_ms);
+}
+
+static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const int *gmap, double *tail_ms)
 {
     const tqb_tables *T = &f->ht;
     const tqb_dims *d = &f->dims;
@@ -466,7 +480,7 @@ int tqb_forest_pack_upload(tqb_forest *f, const tree_qp_in *const *qp, double *t
         for (int c = 0; c < nstage; c++)
         {
             const int j0 = (int) ((long long) N * c / nstage), j1 = (int) ((long long) N * (c + 1) / nstage);
-            pack_range(f, 0, qp[0], NULL, j0, j1);
+            pack_range(f, 0, qp[0], gmap, j0, j1);
             rc |= upload_nodes(f, j0, j1, 1);
         }
     }

@@ -122,6 +122,7 @@ void tqb_forest_pack(tqb_forest *f, int t, const struct tree_qp_in_ *qp);
  * wait after the last range was packed.  Returns 0 on success. */
 int tqb_forest_pack_upload(tqb_forest *f, const struct tree_qp_in_ *const *qp, double *tail_ms);
 /* re-pack and re-send nodes [j0, j1) of tree t only (what an x0 update touches) / the dual start only */
+int tqb_forest_pack_upload_mapped(tqb_forest *f, const struct tree_qp_in_ *full_qp, const int *gmap, double *tail_ms);
 int tqb_forest_update_nodes(tqb_forest *f, int t, const struct tree_qp_in_ *qp, int j0, int j1);
 int tqb_forest_upload_lambda0(tqb_forest *f);
 int tqb_forest_warm_start(tqb_forest *f);

@@ -663,10 +663,11 @@ void treeqp_tdunes_sharded_set_dual_initialization(treeqp_tdunes_sharded *sh, co
 
 return_t treeqp_tdunes_sharded_upload(treeqp_tdunes_sharded *sh, const tree_qp_in *qp_in)
 {
-    double t0 = tqb_wall_ms();
-    tqb_forest_pack_sharded(sh->forest, qp_in, sh->plan);
-    sh->forest->pack_ms = tqb_wall_ms() - t0;
-    if (forest_upload(sh->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    /* pack and H2D pipelined by node range, as the single-GPU upload */
+    double t0 = tqb_wall_ms(), tail = 0.0;
+    if (tqb_forest_pack_upload_mapped(sh->forest, qp_in, sh->plan->gmap, &tail)) return TREEQP_UNKNOWN_ERROR;
+    sh->forest->pack_ms = tqb_wall_ms() - t0 - tail;
+    sh->forest->h2d_bytes = (long long) sizeof(double) * sh->forest->dims.n_in;
     sh->uploaded = 1;
     sh->lam_dirty = 0;
     return TREEQP_OK;
