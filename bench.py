@@ -79,7 +79,7 @@ def class_bytes(alg, fused):
     if fused:
         return {"k_stage_fused<0>": alg["K1"], "k_stage_fused<2>": alg["model"], "k_ls_eval": alg["trial"],
                 "k_build_factor": alg["K2"] + alg["K3"], "k_backsolve_fused": alg["K4"]}
-    return {"k_stage<0>": alg["K1"], "k_stage<2>": alg["model"], "k_trial": alg["trial"],
+    return {"k_stage<0>": alg["K1"], "k_stage<2>": alg["model"], "k_trial_dense+k_ls_eval": alg["trial"],
             "k_gradient+k_hessian": alg["K2"], "k_factor_level": alg["K3"], "k_backsolve_level": alg["K4"]}
 
 

@@ -35,7 +35,7 @@ enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_
  * use is that of the most recent solve of this thread */
 static const char *const k_names_generic[K_NCLASS] = {"k_init", "k_stage<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
                                                       "k_hessian", "k_factor_level", "k_backsolve_level", "k_stage<2>",
-                                                      "k_trial", "k_lambda_step", "k_finish", "nccl+pack"};
+                                                      "k_trial_dense+k_ls_eval", "k_lambda_step", "k_finish", "nccl+pack"};
 static const char *const k_names_fused[K_NCLASS] = {"k_init", "k_stage_fused<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
                                                     "k_hessian", "k_build_factor", "k_backsolve_fused", "k_stage_fused<2>",
                                                     "k_ls_eval", "k_lambda_step", "k_finish", "nccl+pack"};
@@ -551,7 +551,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
                    + 8 * X + 4 * U + 16      /* dlam res resMod xUnc P Linv qmod0 dq | uUnc Rt rmod0 dr */
                    + (size_t) d->szW + (size_t) d->szUt + 4
                    + 4 * (size_t) d->Nn + (1 + TQB_LS_NT) * (size_t) d->nchunk + 4
-                   + (d->has_dense ? (size_t) d->szH + (size_t) d->Nn + 4 : 0);
+                   + (d->has_dense ? (size_t) d->szH + (size_t) TQB_LS_NT * d->Nn + 4 : 0);
     CK(cudaMalloc(&D->d_work, sizeof(double) * nwork));
     double *p = D->d_work;
     v.x = p; p += X; v.u = p; p += U; v.lam = p; p += X; v.mux = p; p += X; v.muu = p; p += U;
@@ -562,7 +562,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     p += ((uintptr_t) p & 8) ? 1 : 0;
     v.W = p; p += d->szW; v.Ut = p; p += d->szUt;
     v.nva = p; p += d->Nn; v.nvb = p; p += d->Nn; v.cmod0 = p; p += d->Nn; v.dc = p; p += d->Nn; v.cva = p; p += d->nchunk; v.cvb = p; p += (size_t) TQB_LS_NT * d->nchunk;
-    if (d->has_dense) { v.Pd = p; p += d->szH; v.fdense = p; p += d->Nn; }
+    if (d->has_dense) { v.Pd = p; p += d->szH; v.fdense = p; p += (size_t) TQB_LS_NT * d->Nn; }
     v.has_dense = d->has_dense; v.nvmax = d->nvmax;
     if ((size_t) (p - D->d_work) > nwork) { snprintf(g_err, sizeof g_err, "work arena overflow"); return 1; }
 
@@ -955,35 +955,21 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         }
         /* affine model of the stage gradients along dlam + res'*dlam, then the line search */
         if (launch_stage<2>(D, K_DIR)) return 1;
-        if (!v.has_dense)
-        {   /* f(0), res'*dlam and the first TQB_LS_NT-1 step lengths in one pass, Armijo on the device */
-            for (int batch = 0; batch * TQB_LS_NT <= o->lsMaxIter + 1; batch++)
+        {   /* f(0), res'*dlam and the first TQB_LS_NT-1 step lengths in one pass, Armijo on the device;
+             * dense stage QPs: the same step lengths solved by k_trial_dense first */
+            for (int batch = 0, trials = 0; trials <= o->lsMaxIter + 1; batch++)
             {
+                /* slots looked at in this pass: all TQB_LS_NT for clipping trees (a pass only streams vectors);
+                 * with dense stage QPs the first pass solves tau = 0 and the full step only */
+                const int nt = (v.has_dense && batch == 0) ? 2 : TQB_LS_NT;
+                if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, batch == 0, nt);
                 LAUNCH(K_TRIAL, k_ls_eval, v.nchunk, 256, 0, v, batch == 0);
                 if (D->comm && allreduce_ls_batch(D, batch == 0)) return 1;
-                LAUNCH(K_DECIDE, k_ls_decide, nT, 32 * (TQB_LS_NT + 1), 0, v, batch == 0);
+                LAUNCH(K_DECIDE, k_ls_decide, nT, 32 * (TQB_LS_NT + 1), 0, v, batch == 0, nt);
                 if (peek_counter(D, 1, 5)) return 1;
                 CK(cudaStreamSynchronize(D->stream));
                 if (D->h_counters[4] == 0 || D->h_counters[5] == 0) break;
-            }
-        }
-        else
-        {
-            LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nvb, v.cva, 0);
-            LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 1);
-            LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 1);
-            if (D->comm && allreduce_tree_sums(D, 1, 1, 0)) return 1;
-            LAUNCH(K_DECIDE, k_decide_ls_init, tgrid, 128, 0, v);
-            for (int ls = 0; ls <= o->lsMaxIter; ls++)
-            {
-                CK(cudaMemsetAsync(v.counters + 1, 0, sizeof(int), D->stream));
-                LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, 0);
-                LAUNCH(K_TRIAL, k_trial, v.nchunk, 256, 0, v, 0);
-                if (D->comm && allreduce_tree_sums(D, 0, 1, 0)) return 1;
-                LAUNCH(K_DECIDE, k_decide_ls_trial, tgrid, 128, 0, v);
-                if (peek_counter(D, 1, 5)) return 1;
-                CK(cudaStreamSynchronize(D->stream));
-                if (D->h_counters[4] == 0 || D->h_counters[5] == 0) break;
+                trials += nt - (batch == 0 ? 1 : 0);
             }
         }
         if (D->h_counters[4] == 0) break; /* every tree has terminated */

@@ -9,7 +9,7 @@
  *
  * Kernel                replaces (reference file:line)
  *   k_stage<0>          solve_stage_problems dual_Newton_tree.c:218 + stage_qp_clipping_solve_extended clipping.c:188
- *   k_stage<2>, k_trial evaluate_dual_function :823 + stage_qp_clipping_solve clipping.c:231 + eval_dual_term clipping.c:359
+ *   k_stage<2>, k_ls_eval evaluate_dual_function :823 + stage_qp_clipping_solve clipping.c:231 + eval_dual_term clipping.c:359
  *   k_gradient          build_dual_problem :519-539 + calculate_error_in_residuals :412
  *   k_hessian           build_dual_problem :551-615 + clipping.c:264-355 (set_CmPnCmT/add_EPmE/add_CmPnCkT)
  *   k_factor_level      calculate_delta_lambda :668-758 + treeqp_dpotrf_l_with_reg_opts dual_Newton_common.c:35
@@ -63,6 +63,10 @@ struct View
     tqb_opts o;
 };
 
+#ifndef TQB_LS_NT
+#define TQB_LS_NT 8 /* step lengths evaluated per line-search pass (k_ls_eval, k_trial_dense) */
+#endif
+
 __global__ void k_init(View v)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -72,7 +76,8 @@ __global__ void k_init(View v)
     {   /* empty working sets (QProblemB_init is a cold start, qpoases.c:286) */
         if (i < v.X) v.P[i] = 0.0;
         if (i < v.U) v.Rt[i] = 0.0;
-        if (i < v.Nn) v.fdense[i] = 0.0;
+        if (i < v.Nn)
+            for (int m = 0; m < TQB_LS_NT; m++) v.fdense[(size_t) m * v.Nn + i] = 0.0; /* clipping nodes keep zeros */
     }
     if (i < v.nT)
     {
@@ -94,7 +99,7 @@ __global__ void k_init(View v)
  *           constant part of the affine model used by the line search.
  *   MODE 2  direction: the same operator applied to dlam (without q, r): dq, dr, dc and the
  *           node's part of res'*dlam.  Along lambda + tau*dlam the stage gradients are
- *           qmod0 + tau*dq, so a line-search trial never touches A or B again (k_trial).
+ *           qmod0 + tau*dq, so a line-search trial never touches A or B again (k_ls_eval).
  *   MODE 3  clip-only solve at lambda writing x,u (state of the reference's work->sx after its
  *           last line-search trial; only needed when maxIter is hit).
  * Algorithmic bytes per node (MODE 0): (5nx+4nu) + sum_kids (nx_j(nx+nu) + 2nx_j) read,
@@ -233,9 +238,12 @@ __global__ void __launch_bounds__(256) k_stage(View v)
 
 /* Line-search trial of the dense nodes (stage_qp_qpoases_solve + eval_dual_term, qpoases.c:384,478):
  * box QP at the stage gradient g0 + tau*dg, warm-started from the working set of the last extended
- * solve; the node's dual term goes to fdense[g] and is picked up by k_trial's chunk reduction. */
-__global__ void __launch_bounds__(256) k_trial_dense(View v, int at_zero)
+ * solve; the node's dual term goes to fdense[g] and is picked up by k_ls_eval's chunk reduction. */
+__global__ void __launch_bounds__(256) k_trial_dense(View v, int first, int nt)
 {
+    /* Batched like k_ls_eval: the TQB_LS_NT step lengths of one line-search pass are solved in ONE launch
+     * (slot m of fdense; first = 1: slot 0 is tau = 0, then 1, beta, beta^2, ...).  Every solve starts from
+     * the working set of the last extended solve, so the trials are independent of each other. */
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int g = blockIdx.x * wpb + wib;
@@ -243,27 +251,38 @@ __global__ void __launch_bounds__(256) k_trial_dense(View v, int at_zero)
     const int hoff = v.T.hoff[g];
     if (hoff < 0) return;
     const int t = v.T.tree[g];
-    if (!v.ls_active[t]) return;
-    const double tau = at_zero ? 0.0 : v.t_tau[t];
+    if (first ? (v.status[t] != TQB_RUNNING) : !v.ls_active[t]) return;
     const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
     const int n = nx + nu, ld = tqb_dense_ld(v.nvmax);
     double *Hs = smem + (size_t) wib * tqb_dense_smem(v.nvmax), *sLd = Hs + v.nvmax * ld, *sinv = sLd + 2 * v.nvmax * ld;
     warp_load_H(n, ld, v.in.H + hoff, Hs, lane);
     const bool isx = lane < nx, act = lane < n;
     const int i = isx ? lane : lane - nx;
-    double lb = 0.0, ub = 0.0, z = 0.0, mu = 0.0, gz = 0.0;
-    int ws = 0;
+    double lb = 0.0, ub = 0.0, g0 = 0.0, dg = 0.0;
+    int ws0 = 0;
     if (act)
     {
         lb = isx ? v.in.dxmin[xo + i] : v.in.dumin[uo + i];
         ub = isx ? v.in.dxmax[xo + i] : v.in.dumax[uo + i];
-        ws = (int) (isx ? v.P[xo + i] : v.Rt[uo + i]);
-        gz = isx ? v.qmod0[xo + i] + tau * v.dq[xo + i] : v.rmod0[uo + i] + tau * v.dr[uo + i];
+        ws0 = (int) (isx ? v.P[xo + i] : v.Rt[uo + i]);
+        g0 = isx ? v.qmod0[xo + i] : v.rmod0[uo + i];
+        dg = isx ? v.dq[xo + i] : v.dr[uo + i];
     }
-    const int fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
-    if (fail && lane == 0) v.status[t] = TQB_STAGE_QP_SOLVE_FAILED;
-    const double f = warp_dense_dual_term(nx, n, Hs, ld, z, gz, lane);
-    if (lane == 0) v.fdense[g] = f;
+    double tm = first ? 1.0 : v.t_tau[t];
+    for (int m = 0; m < nt; m++)
+    {   /* nt <= TQB_LS_NT slots: a dense solve is not a stream over vectors, the first pass of an iteration
+         * only looks at tau = 0 and the full step */
+        double tau = tm;
+        if (first && m == 0) tau = 0.0; else tm = v.o.beta * tm;
+        const double gz = g0 + tau * dg;
+        double z = 0.0, mu = 0.0;
+        int ws = ws0;
+        const int fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
+        if (fail && lane == 0) v.status[t] = TQB_STAGE_QP_SOLVE_FAILED;
+        const double f = warp_dense_dual_term(nx, n, Hs, ld, z, gz, lane);
+        if (lane == 0) v.fdense[(size_t) m * v.Nn + g] = f;
+        __syncwarp();
+    }
 }
 
 /* mu_x, mu_u of the dense nodes: the multipliers of the last extended solve (qpoases.c:527-565) */
@@ -274,50 +293,6 @@ __global__ void k_finish_dense(View v)
     const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
     for (int i = 0; i < nx; i++) v.mux[xo + i] = v.xUnc[xo + i];
     for (int i = 0; i < nu; i++) v.muu[uo + i] = v.uUnc[uo + i];
-}
-
-/* ------------------------------------------------------------------------------------------
- * One line-search trial (evaluate_dual_function, dual_Newton_tree.c:823-918, with
- * stage_qp_clipping_solve + eval_dual_term, clipping.c:231-382) for every tree with a pending
- * trial, at that tree's step length tau:
- *   f(tau) = sum_x [ -1/2 Q x^2 + qmod x ] + sum_u [ -1/2 R u^2 + rmod u ] - sum_nodes cmod,
- *   qmod = qmod0 + tau*dq,  x = clip(Qinv.*qmod)   (same for u, cmod).
- * One CTA per reduction chunk (<=1024 consecutive nodes of one tree), fixed-shape reduction.
- * Bytes per trial: 6(X+U) + 2 Nn doubles read, nothing written but one double per chunk.
- * ---------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(256) k_trial(View v, int at_zero)
-{
-    __shared__ double sh[256];
-    const int c = blockIdx.x;
-    const int t = v.T.chunk_tree[c];
-    if (!v.ls_active[t]) return;
-    const double tau = at_zero ? 0.0 : v.t_tau[t];
-    double acc = 0.0;
-    int dummy;
-    for (int i = v.T.chunk_x0[c] + threadIdx.x; i < v.T.chunk_x1[c]; i += 256)
-    {
-        const double qm = v.qmod0[i] + tau * v.dq[i];
-        const double val = clip_mask(v.in.Qinv[i] * qm, v.in.xmin[i], v.in.xmax[i], dummy);
-        acc += -0.5 * ((v.in.Qd[i] * val) * val) + qm * val;
-    }
-    for (int i = v.T.chunk_u0[c] + threadIdx.x; i < v.T.chunk_u1[c]; i += 256)
-    {
-        const double rm = v.rmod0[i] + tau * v.dr[i];
-        const double val = clip_mask(v.in.Rinv[i] * rm, v.in.umin[i], v.in.umax[i], dummy);
-        acc += -0.5 * ((v.in.Rd[i] * val) * val) + rm * val;
-    }
-    for (int g = v.T.chunk_beg[c] + threadIdx.x; g < v.T.chunk_end[c]; g += 256)
-        acc -= v.cmod0[g] + tau * v.dc[g];
-    if (v.has_dense)
-        for (int g = v.T.chunk_beg[c] + threadIdx.x; g < v.T.chunk_end[c]; g += 256) acc += v.fdense[g];
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = 128; s > 0; s >>= 1)
-    {
-        if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) v.cvb[c] = sh[0];
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -801,34 +776,6 @@ __global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, 
     for (int e = lane; e < d; e += 32) v.dlam[xb + e] = sy[e];
 }
 
-/* start of a line search (dual_Newton_tree.c:940-956): descent test, tau = 1 */
-__global__ void k_decide_ls_init(View v)
-{
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= v.nT) return;
-    if (v.status[t] != TQB_RUNNING) return;
-    const double dot = -(v.sharded ? v.t_red[t] : tree_reduce(v, v.cva, t, lane, false));
-    const double f0 = v.sharded ? v.t_red[v.nT + t] : tree_reduce(v, v.cvb, t, lane, false);
-    if (lane == 0)
-    {
-        v.t_dot[t] = dot;
-        v.t_f0[t] = f0;
-        if (dot > 1e-10 || !((dot > 1e-10) || (dot < 1e-10)))
-        {
-            v.status[t] = 2; /* TREEQP_DN_NOT_DESCENT_DIRECTION */
-            v.ls_active[t] = 0;
-        }
-        else
-        {
-            v.t_tau[t] = 1.0;
-            v.t_tauprev[t] = 0.0;
-            v.ls_cnt[t] = 0;
-            v.ls_active[t] = 1;
-        }
-    }
-}
-
 /* lambda += tau_final * dlam once the line search of a tree is over.  (The reference moves
  * lambda incrementally by (tau - tauPrev)*dlam at every trial, dual_Newton_tree.c:964-968; the
  * end point is the same up to rounding.) */
@@ -870,45 +817,8 @@ __global__ void __launch_bounds__(256) k_lambda_step_chunks(View v)
     for (int e = x0 + threadIdx.x; e < x1; e += 256) v.lam[e] += step * v.dlam[e];
 }
 
-/* Armijo test of one trial (dual_Newton_tree.c:970-1000) */
-__global__ void k_decide_ls_trial(View v)
-{
-    const int lane = threadIdx.x & 31;
-    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= v.nT) return;
-    if (!v.ls_active[t]) return;
-    const double f = v.sharded ? v.t_red[v.nT + t] : tree_reduce(v, v.cvb, t, lane, false);
-    if (lane == 0)
-    {
-        const int ls = ++v.ls_cnt[t];
-        const double tau = v.t_tau[t];
-        v.t_taufin[t] = tau; /* lambda of the last evaluated trial */
-        bool done = false;
-        int recorded = ls;
-        if (v.restart_cnt[t] == v.o.lsRestartTrigger) done = true; /* full step when stuck (:973-977) */
-        else if (f <= v.t_f0[t] + v.o.gamma * tau * v.t_dot[t]) done = true;
-        else
-        {
-            v.t_tauprev[t] = tau;
-            v.t_tau[t] = v.o.beta * tau;
-            if (ls >= v.o.lsMaxIter) { done = true; recorded = v.o.lsMaxIter + 1; }
-        }
-        if (done)
-        {
-            v.ls_active[t] = 0;
-            v.restart_cnt[t] = (recorded >= v.o.lsMaxIter) ? v.restart_cnt[t] + 1 : 0; /* :993-1000 */
-            const int it = v.iter[t]++;
-            if (t == 0 && it < 256) v.ls_hist[it] = recorded;
-            atomicAdd(&v.counters[3], ls);
-        }
-        else
-            atomicAdd(&v.counters[1], 1);
-    }
-}
-
-
 /* ------------------------------------------------------------------------------------------
- * Batched line search (clipping stage QPs only).  The Armijo sequence tau, beta*tau, ... is known
+ * Batched line search.  The Armijo sequence tau, beta*tau, ... is known
  * in advance and a trial only streams the affine model (qmod0, dq, ...), so TQB_LS_NT step lengths
  * are evaluated in ONE pass over the vectors and the Armijo loop of dual_Newton_tree.c:960-1000
  * then runs on the device over the batch: no host round trip per trial.
@@ -918,9 +828,6 @@ __global__ void k_decide_ls_trial(View v)
  * Step lengths are generated by repeated multiplication exactly as k_ls_decide does.
  * Bytes per pass: 6(X+U) + 3 Nn doubles read, (NT+1) doubles per chunk written.
  * ---------------------------------------------------------------------------------------- */
-#ifndef TQB_LS_NT
-#define TQB_LS_NT 8
-#endif
 __global__ void __launch_bounds__(256) k_ls_eval(View v, int first)
 {
     constexpr int NT = TQB_LS_NT;
@@ -971,6 +878,11 @@ __global__ void __launch_bounds__(256) k_ls_eval(View v, int first)
 #pragma unroll
         for (int m = 0; m < NT; m++) acc[m] -= c0 + tau[m] * dc;
         if (first) accd += v.nvb[g];
+        if (v.has_dense)
+        {   /* dual terms of the dense nodes (k_trial_dense, one slot per step length) */
+#pragma unroll
+            for (int m = 0; m < NT; m++) acc[m] += v.fdense[(size_t) m * v.Nn + g];
+        }
     }
 #pragma unroll
     for (int m = 0; m < NT; m++) sh[m][tid] = acc[m];
@@ -993,7 +905,7 @@ __global__ void __launch_bounds__(256) k_ls_eval(View v, int first)
  * One CTA per tree, warp m < NT reduces the chunk values of step length m, warp NT those of
  * res'*dlam (same additions as tree_reduce, four independent loads in flight per lane); thread 0
  * then walks the Armijo sequence. */
-__global__ void __launch_bounds__(32 * (TQB_LS_NT + 1)) k_ls_decide(View v, int first)
+__global__ void __launch_bounds__(32 * (TQB_LS_NT + 1)) k_ls_decide(View v, int first, int nt)
 {
     constexpr int NT = TQB_LS_NT;
     __shared__ double sf[NT + 1];
@@ -1051,7 +963,7 @@ __global__ void __launch_bounds__(32 * (TQB_LS_NT + 1)) k_ls_decide(View v, int 
 #pragma unroll
     for (int k = 0; k < NT; k++)
     {
-        if (k < m0 || done) continue;
+        if (k < m0 || k >= nt || done) continue;
         ls++;
         recorded = ls;
         taufin = tau; /* lambda of the last evaluated trial */
