@@ -480,6 +480,15 @@ void tree_qp_in_set_node_bounds(const double *const xmin, const double *const xm
                                 const double *const umin, const double *const umax,
                                 tree_qp_in *const qp_in, const int indx);
 void tree_qp_in_set_inf_bounds(tree_qp_in *qp_in);
+/* general stage constraints dmin <= C x + D u <= dmax (tree_qp_common.h:249-265; lda < 0 = tight).  TDUNES
+ * takes them on nodes that use the dense stage solver (TREEQP_QPOASES_SOLVER), nx + nu + nc <= 32, nc <= 8 */
+void tree_qp_in_set_node_C_colmajor(const double *const C, const int lda, tree_qp_in *const qp_in, const int indx);
+void tree_qp_in_set_node_D_colmajor(const double *const D, const int lda, tree_qp_in *const qp_in, const int indx);
+void tree_qp_in_set_node_dmin(const double *const dmin, tree_qp_in *const qp_in, const int indx);
+void tree_qp_in_set_node_dmax(const double *const dmax, tree_qp_in *const qp_in, const int indx);
+void tree_qp_in_set_node_general_constraints(const double *const C, const double *const D, const double *const dmin,
+                                             const double *const dmax, tree_qp_in *const qp_in, const int indx);
+void tree_qp_out_get_node_mu_d(double *const mu, const tree_qp_out *const qp_out, const int indx);
 /* initial state: pinned through the root's bounds, or eliminated (nx[0] becomes 0; only b of the
  * root's children, r[0], dmin/dmax[0] depend on x0)          tree_qp_common.h:167-169, 314-316 */
 void tree_qp_in_eliminate_x0(tree_qp_in *const qp_in);

@@ -57,6 +57,38 @@ def dense_cases():
     yield "linear_chain_mixed", lc, dict(qp_solver=[1 if lc.nk[k] > 0 else 0 for k in range(lc.Nn)])
 
 
+def general_cases():
+    """General stage constraints dmin <= C x + D u <= dmax on dense-solver nodes (the reference's
+    QProblem path, dual_Newton_tree_qpoases.c:181-193, 288-298).  The reference's own data for this path
+    (examples/spring_mass.c:100-223) turns bounds into unit rows; the same is done here on the dense cases on
+    which the reference's nc > 0 path converges to the solution of the bounded QP (it does not on every QP:
+    on e.g. quadcopter_cfg5 with only u[0] converted it runs into maxIter with a KKT residual of 0.3 while the
+    bounded twin takes 17 iterations -- those conversions cannot be goldens)."""
+    G = P.bounds_to_general
+    Q = dict(qp_solver=1, maxIter=200)
+    yield "spring_mass_rows", G(P.spring_mass(3, 2, 10, xmax1=0.2), (1,), (0,)), dict(Q)
+    yield "spring_mass_dense_rows", G(P.densify(P.spring_mass(3, 2, 10, xmax1=0.2), 1, 0.05, 0.05), (1,), (0,)), dict(Q)
+    for name, xi, ui in (("random_nx6_nu4_md3", (), (0, 1)), ("random_nx4_nu1_xbox", (1,), (0,)), ("linear_chain_nm8_md4", (), (0, 1)),
+                         ("quadcopter_cfg5", (), (0, 1)), ("crane_cfg5", (1,), (0,)), ("random_vary_dims", (1,), (0,))):
+        prob, opts = get_dense_case(name)
+        yield name + "_rows", G(prob, xi, ui), dict(opts)
+
+
+GENERAL_CASE_NAMES = ["spring_mass_rows", "spring_mass_dense_rows", "random_nx6_nu4_md3_rows", "random_nx4_nu1_xbox_rows",
+                      "linear_chain_nm8_md4_rows", "quadcopter_cfg5_rows", "crane_cfg5_rows", "random_vary_dims_rows"]
+
+
+def get_general_case(name):
+    for n, p, o in general_cases():
+        if n == name:
+            return p, o
+    raise KeyError(name)
+
+
+def general_golden(name):
+    return np.load(os.path.join(GOLDEN, "tdunes_general_%s.npz" % name))
+
+
 def get_dense_case(name):
     for n, p, o in dense_cases():
         if n == name:
@@ -144,7 +176,8 @@ def get_case(name):
 
 def checksum(prob):
     h = hashlib.sha256()
-    for name in ["nk", "nx", "nu", "A", "B", "b", "Qd", "Rd", "Q", "R", "S", "q", "r", "xmin", "xmax", "umin", "umax"]:
+    for name in ["nk", "nx", "nu", "A", "B", "b", "Qd", "Rd", "Q", "R", "S", "q", "r", "xmin", "xmax", "umin", "umax",
+                 "nc", "C", "D", "dmin", "dmax"]:
         if getattr(prob, name) is not None:
             h.update(np.ascontiguousarray(getattr(prob, name)).tobytes())
     return h.hexdigest()

@@ -99,6 +99,26 @@ def make_sdunes_goldens():
             name, prob.Nn, sol.status, sol.iter, sol.kkt, 1e3 * sol.total_time))
 
 
+def make_general_goldens():
+    """outputs of the UNMODIFIED reference with general stage constraints (QProblem path of qpOASES_e)"""
+    from treeqp_b200 import capi
+    ref = capi.TreeQpLib(os.path.join(ROOT, "oracle/_ref/libtreeqp_ref.so"))
+    for name, prob, opts in CS.general_cases():
+        if ONLY and name not in ONLY:
+            continue
+        qp_in, qp_out = capi.QpIn(ref, prob), capi.QpOut(ref, prob)
+        s = capi.Tdunes(ref, qp_in, **opts)
+        s.set_dual_initialization(np.zeros(prob.n_lambda))
+        st = s.solve(qp_out)
+        kkt = float(ref.lib.tree_qp_out_max_KKT_res(qp_in.ptr, qp_out.ptr))
+        assert st == 0 and kkt < 1e-8, (name, st, kkt)
+        np.savez_compressed(os.path.join(HERE, "tdunes_general_%s.npz" % name), status=st, iter=qp_out.iter, x=qp_out.x, u=qp_out.u,
+                            lam=qp_out.lam, mu_x=qp_out.mu_x, mu_u=qp_out.mu_u, mu_d=qp_out.mu_d, kkt=kkt,
+                            input_sha256=checksum(prob), opts=repr(opts))
+        print("general %-28s Nn=%6d rows=%4d status=%d iter=%3d kkt=%.2e active rows %d" % (
+            name, prob.Nn, int(prob.nc.sum()), st, qp_out.iter, kkt, int((qp_out.mu_d != 0).sum())))
+
+
 def make_large_golden():
     """config 3's QP at depth 14 through the UNMODIFIED reference (OpenMP build: 32 767 nodes)"""
     from treeqp_b200 import capi
@@ -114,7 +134,9 @@ def make_large_golden():
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["data", "tdunes", "sdunes", "dense", "large"]
+    what = sys.argv[1:] or ["data", "tdunes", "sdunes", "dense", "large", "general"]
+    if "general" in what:
+        make_general_goldens()
     if "large" in what:
         make_large_golden()
     if "dense" in what:

@@ -128,6 +128,13 @@ class Problem:
     R: Optional[np.ndarray] = None
     S: Optional[np.ndarray] = None
     lam0: Optional[np.ndarray] = None
+    # general stage constraints dmin <= C x + D u <= dmax (tree_qp_common.h:104-109): nc per node,
+    # C (nc x nx) and D (nc x nu) column-major and concatenated per node, dmin/dmax concatenated
+    nc: Optional[np.ndarray] = None
+    C: Optional[np.ndarray] = None
+    D: Optional[np.ndarray] = None
+    dmin: Optional[np.ndarray] = None
+    dmax: Optional[np.ndarray] = None
     meta: dict = field(default_factory=dict)
 
     @property
@@ -190,6 +197,8 @@ class TreeQpLib:
         L.tree_qp_in_set_ltv_bounds.restype = None
         L.tree_qp_in_set_node_objective_colmajor.argtypes = [c_double_p] * 5 + [vp, C.c_int]
         L.tree_qp_in_set_node_objective_colmajor.restype = None
+        L.tree_qp_in_set_node_general_constraints.argtypes = [c_double_p] * 4 + [vp, C.c_int]
+        L.tree_qp_in_set_node_general_constraints.restype = None
         L.tree_qp_out_max_KKT_res.argtypes = [vp, vp]
         L.tree_qp_out_max_KKT_res.restype = C.c_double
         L.treeqp_tdunes_opts_calculate_size.argtypes = [C.c_int]
@@ -360,12 +369,14 @@ class QpIn:
         self.lib, self.prob = lib, prob
         L = lib.lib
         self.nk, self.nx, self.nu = _i32(prob.nk), _i32(prob.nx), _i32(prob.nu)
+        self.nc = _i32(prob.nc) if prob.nc is not None else None
+        ncp = _ip(self.nc) if self.nc is not None else None
         Nn = prob.Nn
-        size = L.tree_qp_in_calculate_size(Nn, _ip(self.nx), _ip(self.nu), None, _ip(self.nk))
+        size = L.tree_qp_in_calculate_size(Nn, _ip(self.nx), _ip(self.nu), ncp, _ip(self.nk))
         assert size > 0, "tree_qp_in size overflows the int return type of the reference API"
         self.mem = _Buf(size)
         self.struct = _Buf(1024)  # opaque tree_qp_in (≈400 B)
-        L.tree_qp_in_create(Nn, _ip(self.nx), _ip(self.nu), None, _ip(self.nk), self.struct.ptr, self.mem.ptr)
+        L.tree_qp_in_create(Nn, _ip(self.nx), _ip(self.nu), ncp, _ip(self.nk), self.struct.ptr, self.mem.ptr)
         self.ptr = self.struct.ptr
         self.set_data(prob)
 
@@ -388,6 +399,15 @@ class QpIn:
                 iq += nx * nx; ir += nu * nu; is_ += nu * nx; ix += nx; iu += nu
         xmin, xmax, umin, umax = _f64(prob.xmin), _f64(prob.xmax), _f64(prob.umin), _f64(prob.umax)
         L.tree_qp_in_set_ltv_bounds(_dp(xmin), _dp(xmax), _dp(umin), _dp(umax), self.ptr)
+        if prob.nc is not None and int(np.sum(prob.nc)) > 0:
+            Cm, Dm, dlo, dhi = _f64(prob.C), _f64(prob.D), _f64(prob.dmin), _f64(prob.dmax)
+            ic = idd = iv = 0
+            for k in range(prob.Nn):
+                nx, nu, nc = int(prob.nx[k]), int(prob.nu[k]), int(prob.nc[k])
+                if nc > 0:
+                    L.tree_qp_in_set_node_general_constraints(
+                        _dp(Cm[ic:]) if nx else None, _dp(Dm[idd:]) if nu else None, _dp(dlo[iv:]), _dp(dhi[iv:]), self.ptr, k)
+                ic += nc * nx; idd += nc * nu; iv += nc
 
 
     def eliminate_x0(self):
@@ -407,10 +427,12 @@ class QpOut:
         self.lib, self.prob = lib, prob
         L = lib.lib
         nx, nu = _i32(prob.nx), _i32(prob.nu)
-        size = L.tree_qp_out_calculate_size(prob.Nn, _ip(nx), _ip(nu), None)
+        nc = _i32(prob.nc) if prob.nc is not None else None
+        ncp = _ip(nc) if nc is not None else None
+        size = L.tree_qp_out_calculate_size(prob.Nn, _ip(nx), _ip(nu), ncp)
         self.mem = _Buf(size)
         self.struct_buf = _Buf(C.sizeof(QpOutStruct) + 64)
-        L.tree_qp_out_create(prob.Nn, _ip(nx), _ip(nu), None, self.struct_buf.ptr, self.mem.ptr)
+        L.tree_qp_out_create(prob.Nn, _ip(nx), _ip(nu), ncp, self.struct_buf.ptr, self.mem.ptr)
         self.ptr = self.struct_buf.ptr
         self.s = QpOutStruct.from_address(self.struct_buf.addr)
 
@@ -441,6 +463,8 @@ class QpOut:
     def mu_x(self): return self._gather(self.s.mu_x, self.prob.Nn)
     @property
     def mu_u(self): return self._gather(self.s.mu_u, self.prob.Nn)
+    @property
+    def mu_d(self): return self._gather(self.s.mu_d, self.prob.Nn)
     @property
     def iter(self): return int(self.s.info.iter)
     @property

@@ -546,8 +546,8 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     tqb_layout_inputs(d, D->d_in, &v.in);
 
     const size_t X = d->X, U = d->U;
-    D->out_doubles = 3 * X + 2 * U;
-    size_t nwork = D->out_doubles + 8 /* x u lam mux muu */
+    D->out_doubles = 3 * X + 2 * U + (size_t) d->NC;
+    size_t nwork = D->out_doubles + 8 /* x u lam mux muu mud */ + (size_t) d->NC + 2
                    + 8 * X + 4 * U + 16      /* dlam res resMod xUnc P Linv qmod0 dq | uUnc Rt rmod0 dr */
                    + (size_t) d->szW + (size_t) d->szUt + 4
                    + 4 * (size_t) d->Nn + (1 + TQB_LS_NT) * (size_t) d->nchunk + 4
@@ -555,6 +555,8 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     CK(cudaMalloc(&D->d_work, sizeof(double) * nwork));
     double *p = D->d_work;
     v.x = p; p += X; v.u = p; p += U; v.lam = p; p += X; v.mux = p; p += X; v.muu = p; p += U;
+    v.mud = p; p += d->NC; v.wsd = p; p += d->NC;
+    v.ncmax = d->ncmax; v.NC = d->NC;
     p += ((uintptr_t) p & 8) ? 1 : 0;
     v.dlam = p; p += X; v.res = p; p += X; v.resMod = p; p += X; v.xUnc = p; p += X; v.P = p; p += X;
     v.Linv = p; p += X; v.uUnc = p; p += U; v.Rt = p; p += U;
@@ -587,14 +589,14 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     CK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     const size_t lim = (size_t) smem_max > 8192 ? (size_t) smem_max - 2048 : 40000;
     const int ldw = d->dmax | 1, ldu = d->nxmax | 1;
-    v.pw_stage = d->abmax + d->dmax + (d->has_dense ? tqb_dense_smem(d->nvmax) : 0);
+    v.pw_stage = d->abmax + d->dmax + (d->has_dense ? tqb_dense_smem(d->nvmax, d->ncmax) : 0);
     v.pw_hess = d->abmax + d->nxmax + d->numax + d->dmax +
                 (d->has_dense ? d->dmax / 2 + 1 + d->nvmax * d->nvmax + d->dmax * d->nvmax : 0);
     const size_t pw_stage = 8ull * v.pw_stage;
     const size_t pw_hess = 8ull * v.pw_hess;
     if (d->has_dense)
     {
-        if (pick_wpb(8ull * tqb_dense_smem(d->nvmax), lim, &D->wpb_dense, &D->sm_dense)) return 1;
+        if (pick_wpb(8ull * tqb_dense_smem(d->nvmax, d->ncmax), lim, &D->wpb_dense, &D->sm_dense)) return 1;
         CK(cudaFuncSetAttribute(k_trial_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_dense));
     }
     D->pw_fact = ldw * d->dmax + 2 * d->dmax + ldu * d->dmax;
@@ -881,6 +883,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         if (n < 256) n = 256;
         if (n < v.Nn) n = v.Nn;
         if (v.has_dense && n < v.U) n = v.U;
+        if (n < d->NC) n = d->NC;
         LAUNCH(K_INIT, k_init, cdiv(n, 256), 256, 0, v);
     }
     /* Host round trips: ONE per Newton iteration (after the first line-search batch).  The

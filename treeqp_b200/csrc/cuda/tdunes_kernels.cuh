@@ -58,6 +58,9 @@ struct View
      * working set (-1, 0, +1) and those of xUnc/uUnc its bound multipliers */
     double *Pd, *fdense;
     int has_dense, nvmax;
+    /* general stage constraints of the dense nodes: multipliers (output, d-space) and working set */
+    double *mud, *wsd;
+    int ncmax, NC;
     /* per-warp shared memory layout, in doubles */
     int abmax, dmax, nxmax, numax, pw_stage, pw_hess;
     tqb_opts o;
@@ -78,6 +81,7 @@ __global__ void k_init(View v)
         if (i < v.U) v.Rt[i] = 0.0;
         if (i < v.Nn)
             for (int m = 0; m < TQB_LS_NT; m++) v.fdense[(size_t) m * v.Nn + i] = 0.0; /* clipping nodes keep zeros */
+        if (v.ncmax > 0 && i < v.NC) { v.wsd[i] = 0.0; v.mud[i] = 0.0; }
     }
     if (i < v.nT)
     {
@@ -211,7 +215,8 @@ __global__ void __launch_bounds__(256) k_stage(View v)
         double *Hs = sL + v.dmax, *sLd = Hs + v.nvmax * ld, *sY = sLd + v.nvmax * ld, *sinv = sY + v.nvmax * ld;
         __syncwarp();
         warp_load_H(n, ld, v.in.H + hoff, Hs, lane);
-        const bool isx = lane < nx, act = lane < n;
+        const int m = v.ncmax > 0 ? v.T.ncn[g] : 0, dof = m > 0 ? v.T.doff[g] : 0;
+        const bool isx = lane < nx, act = lane < n, isr = lane >= n && lane < n + m;
         const int i = isx ? lane : lane - nx;
         double lb = 0.0, ub = 0.0, z = 0.0, mu = 0.0;
         int ws = 0;
@@ -221,7 +226,21 @@ __global__ void __launch_bounds__(256) k_stage(View v)
             ub = isx ? v.in.dxmax[xo + i] : v.in.dumax[uo + i];
             ws = (int) (isx ? v.P[xo + i] : v.Rt[uo + i]);
         }
-        const int fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
+        int fail, ma = 0;
+        double *Cs = sinv + v.nvmax + 1, *Ws = Cs + v.ncmax * ld, *Ss = Ws + v.ncmax * ld, *sv = Ss + v.ncmax * v.ncmax;
+        if (m > 0)
+        {   /* general constraints: rows of [C D] into shared memory, lane n + a owns row a */
+            const double *Cg = v.in.Cg + v.T.cgoff[g];
+            for (int e = lane; e < m * n; e += 32) Cs[(e % m) * ld + e / m] = Cg[e];
+            if (isr) { lb = v.in.dmin[dof + lane - n]; ub = v.in.dmax[dof + lane - n]; ws = (int) v.wsd[dof + lane - n]; }
+            /* start from the previous solution of this node (feasible: only the gradient changes); first
+             * iteration of a solve: from the origin */
+            if (act) z = v.iter[t] == 0 ? 0.0 : (isx ? v.x[xo + i] : v.u[uo + i]);
+            __syncwarp();
+            fail = warp_genqp(n, m, Hs, ld, Cs, gz, lb, ub, ws, z, mu, sLd, sinv, Ws, Ss, sv, ma, lane);
+        }
+        else
+            fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
         if (fail && lane == 0) v.status[t] = TQB_STAGE_QP_SOLVE_FAILED;
         if (act)
         {
@@ -232,7 +251,13 @@ __global__ void __launch_bounds__(256) k_stage(View v)
                 else { v.rmod0[uo + i] = gz; v.Rt[uo + i] = (double) ws; v.uUnc[uo + i] = mu; }
             }
         }
-        if (MODE == 0) warp_boxqp_projector(n, ld, ws, sLd, sinv, sY, v.Pd + hoff, lane);
+        if (isr && MODE == 0) { v.wsd[dof + lane - n] = (double) ws; v.mud[dof + lane - n] = mu; }
+        if (MODE == 0)
+        {
+            const int wsv = act ? ws : 1; /* the projector of the box part reads the variables' working set only */
+            warp_boxqp_projector(n, ld, wsv, sLd, sinv, sY, v.Pd + hoff, lane);
+            if (m > 0) warp_genqp_projector(n, m, ld, ma, Ws, Ss, sY, v.Pd + hoff, lane);
+        }
     }
 }
 
@@ -241,9 +266,10 @@ __global__ void __launch_bounds__(256) k_stage(View v)
  * solve; the node's dual term goes to fdense[g] and is picked up by k_ls_eval's chunk reduction. */
 __global__ void __launch_bounds__(256) k_trial_dense(View v, int first, int nt)
 {
-    /* Batched like k_ls_eval: the TQB_LS_NT step lengths of one line-search pass are solved in ONE launch
-     * (slot m of fdense; first = 1: slot 0 is tau = 0, then 1, beta, beta^2, ...).  Every solve starts from
-     * the working set of the last extended solve, so the trials are independent of each other. */
+    /* Batched like k_ls_eval: the step lengths of one line-search pass are solved in ONE launch (slot m of
+     * fdense; first = 1: slot 0 is tau = 0, then 1, beta, beta^2, ...).  Every solve starts from the working
+     * set (and, with general constraints, the point) of the last extended solve, so the trials are
+     * independent of each other. */
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int g = blockIdx.x * wpb + wib;
@@ -254,11 +280,13 @@ __global__ void __launch_bounds__(256) k_trial_dense(View v, int first, int nt)
     if (first ? (v.status[t] != TQB_RUNNING) : !v.ls_active[t]) return;
     const int nx = v.T.nx[g], nu = v.T.nu[g], xo = v.T.xoff[g], uo = v.T.uoff[g];
     const int n = nx + nu, ld = tqb_dense_ld(v.nvmax);
-    double *Hs = smem + (size_t) wib * tqb_dense_smem(v.nvmax), *sLd = Hs + v.nvmax * ld, *sinv = sLd + 2 * v.nvmax * ld;
+    double *Hs = smem + (size_t) wib * tqb_dense_smem(v.nvmax, v.ncmax), *sLd = Hs + v.nvmax * ld, *sinv = sLd + 2 * v.nvmax * ld;
+    double *Cs = sinv + v.nvmax + 1, *Ws = Cs + v.ncmax * ld, *Ss = Ws + v.ncmax * ld, *sv = Ss + v.ncmax * v.ncmax;
     warp_load_H(n, ld, v.in.H + hoff, Hs, lane);
-    const bool isx = lane < nx, act = lane < n;
+    const int mrows = v.ncmax > 0 ? v.T.ncn[g] : 0, dof = mrows > 0 ? v.T.doff[g] : 0;
+    const bool isx = lane < nx, act = lane < n, isr = lane >= n && lane < n + mrows;
     const int i = isx ? lane : lane - nx;
-    double lb = 0.0, ub = 0.0, g0 = 0.0, dg = 0.0;
+    double lb = 0.0, ub = 0.0, g0 = 0.0, dg = 0.0, z0 = 0.0;
     int ws0 = 0;
     if (act)
     {
@@ -267,6 +295,14 @@ __global__ void __launch_bounds__(256) k_trial_dense(View v, int first, int nt)
         ws0 = (int) (isx ? v.P[xo + i] : v.Rt[uo + i]);
         g0 = isx ? v.qmod0[xo + i] : v.rmod0[uo + i];
         dg = isx ? v.dq[xo + i] : v.dr[uo + i];
+        z0 = isx ? v.x[xo + i] : v.u[uo + i];
+    }
+    if (mrows > 0)
+    {
+        const double *Cg = v.in.Cg + v.T.cgoff[g];
+        for (int e = lane; e < mrows * n; e += 32) Cs[(e % mrows) * ld + e / mrows] = Cg[e];
+        if (isr) { lb = v.in.dmin[dof + lane - n]; ub = v.in.dmax[dof + lane - n]; ws0 = (int) v.wsd[dof + lane - n]; }
+        __syncwarp();
     }
     double tm = first ? 1.0 : v.t_tau[t];
     for (int m = 0; m < nt; m++)
@@ -275,11 +311,12 @@ __global__ void __launch_bounds__(256) k_trial_dense(View v, int first, int nt)
         double tau = tm;
         if (first && m == 0) tau = 0.0; else tm = v.o.beta * tm;
         const double gz = g0 + tau * dg;
-        double z = 0.0, mu = 0.0;
-        int ws = ws0;
-        const int fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
+        double z = z0, mu = 0.0;
+        int ws = ws0, fail, ma = 0;
+        if (mrows > 0) fail = warp_genqp(n, mrows, Hs, ld, Cs, gz, lb, ub, ws, z, mu, sLd, sinv, Ws, Ss, sv, ma, lane);
+        else fail = warp_boxqp(n, Hs, ld, gz, lb, ub, ws, z, mu, sLd, sinv, lane);
         if (fail && lane == 0) v.status[t] = TQB_STAGE_QP_SOLVE_FAILED;
-        const double f = warp_dense_dual_term(nx, n, Hs, ld, z, gz, lane);
+        const double f = warp_dense_dual_term(nx, n, Hs, ld, act ? z : 0.0, gz, lane);
         if (lane == 0) v.fdense[(size_t) m * v.Nn + g] = f;
         __syncwarp();
     }
@@ -1039,6 +1076,8 @@ __global__ void __launch_bounds__(256) k_kkt(View v, unsigned long long *out)
     const int dad = v.T.dad[g], k0 = v.T.kid0[g], nk = v.T.nkids[g], ho = v.T.hoff[g], nv = nx + nu;
     const double *x = v.x + xo, *u = v.u + uo;
     const double *H = ho >= 0 ? v.in.H + ho : nullptr;
+    const int mrows = (v.ncmax > 0 && ho >= 0) ? v.T.ncn[g] : 0;
+    const double *Cg = mrows > 0 ? v.in.Cg + v.T.cgoff[g] : nullptr, *md = mrows > 0 ? v.mud + v.T.doff[g] : nullptr;
     unsigned long long err = 0ull;
     for (int r = lane; r < nv; r += 32)
     {   /* stationarity, row r of z = [x; u] */
@@ -1052,6 +1091,8 @@ __global__ void __launch_bounds__(256) k_kkt(View v, unsigned long long *out)
         }
         else s += isx ? v.in.Qd[xo + i] * x[i] : v.in.Rd[uo + i] * u[i];
         if (isx && dad >= 0) s -= v.lam[xo + i];
+        if (mrows > 0)
+            for (int a = 0; a < mrows; a++) s += Cg[a + r * mrows] * md[a]; /* + C' mu_d / D' mu_d */
         for (int j = 0; j < nk; j++)
         {
             const int k = k0 + j, nxk = v.T.nx[k];
@@ -1068,6 +1109,16 @@ __global__ void __launch_bounds__(256) k_kkt(View v, unsigned long long *out)
         if (z > hi) err = max(err, kkt_bits(z - hi));
         else if (z < lo) err = max(err, kkt_bits(lo - z));
         err = max(err, kkt_bits(m > 0 ? m * (z - hi) : m * (lo - z)));
+    }
+    for (int a = lane; a < mrows; a += 32)
+    {   /* general constraints: feasibility and complementarity (tree_qp_common.c:723-755) */
+        double gv = 0.0;
+        for (int c = 0; c < nx; c++) gv += Cg[a + c * mrows] * x[c];
+        for (int c = 0; c < nu; c++) gv += Cg[a + (nx + c) * mrows] * u[c];
+        const double lo = v.in.dmin[v.T.doff[g] + a], hi = v.in.dmax[v.T.doff[g] + a], m = md[a];
+        if (gv > hi) err = max(err, kkt_bits(gv - hi));
+        else if (gv < lo) err = max(err, kkt_bits(lo - gv));
+        err = max(err, kkt_bits(m > 0 ? m * (gv - hi) : m * (lo - gv)));
     }
     if (dad >= 0)
     {   /* dynamics of the edge into this node */

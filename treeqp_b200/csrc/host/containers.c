@@ -560,6 +560,47 @@ void tree_qp_in_set_node_bounds(const double *const xmin, const double *const xm
     if (umax && bu) memcpy(qp->umax[indx].pa, umax, bu);
 }
 
+/* general stage constraints dmin <= C x + D u <= dmax (tree_qp_common.c:1700-1821); lda < 0 = tight */
+void tree_qp_in_set_node_C_colmajor(const double *const C, const int lda, tree_qp_in *const qp, const int indx)
+{
+    assert(indx >= 0 && indx < qp->N);
+    const int nc = qp->nc[indx], nx = qp->nx[indx];
+    if (C && nc > 0 && nx > 0) tqb_dmat_from_colmajor(nc, nx, C, lda < 0 ? nc : lda, &qp->C[indx]);
+}
+
+void tree_qp_in_set_node_D_colmajor(const double *const D, const int lda, tree_qp_in *const qp, const int indx)
+{
+    assert(indx >= 0 && indx < qp->N);
+    const int nc = qp->nc[indx], nu = qp->nu[indx];
+    if (D && nc > 0 && nu > 0) tqb_dmat_from_colmajor(nc, nu, D, lda < 0 ? nc : lda, &qp->D[indx]);
+}
+
+void tree_qp_in_set_node_dmin(const double *const dmin, tree_qp_in *const qp, const int indx)
+{
+    assert(indx >= 0 && indx < qp->N);
+    if (dmin && qp->nc[indx] > 0) memcpy(qp->dmin[indx].pa, dmin, sizeof(double) * (size_t) qp->nc[indx]);
+}
+
+void tree_qp_in_set_node_dmax(const double *const dmax, tree_qp_in *const qp, const int indx)
+{
+    assert(indx >= 0 && indx < qp->N);
+    if (dmax && qp->nc[indx] > 0) memcpy(qp->dmax[indx].pa, dmax, sizeof(double) * (size_t) qp->nc[indx]);
+}
+
+void tree_qp_in_set_node_general_constraints(const double *const C, const double *const D, const double *const dmin,
+                                             const double *const dmax, tree_qp_in *const qp, const int indx)
+{
+    tree_qp_in_set_node_C_colmajor(C, -1, qp, indx);
+    tree_qp_in_set_node_D_colmajor(D, -1, qp, indx);
+    tree_qp_in_set_node_dmin(dmin, qp, indx);
+    tree_qp_in_set_node_dmax(dmax, qp, indx);
+}
+
+void tree_qp_out_get_node_mu_d(double *const mu, const tree_qp_out *const out, const int i)
+{
+    memcpy(mu, out->mu_d[i].pa, sizeof(double) * (size_t) out->mu_d[i].m);
+}
+
 void tree_qp_in_set_ltv_dynamics_colmajor(double *A, double *B, double *b, tree_qp_in *qp)
 {
     size_t ia = 0, ib = 0, iv = 0;
@@ -687,6 +728,7 @@ double tree_qp_out_max_KKT_res(const tree_qp_in *const qp, const tree_qp_out *co
         for (int r = 0; r < nx; r++)
         {
             double s = qp->q[i].pa[r] + out->mu_x[i].pa[r];
+            for (int a = 0; a < qp->nc[i]; a++) s += BLASFEO_DMATEL(&qp->C[i], a, r) * out->mu_d[i].pa[a];
             for (int c = 0; c < nx; c++) s += BLASFEO_DMATEL(&qp->Q[i], r, c) * x[c];
             for (int c = 0; c < nu; c++) s += BLASFEO_DMATEL(&qp->S[i], c, r) * u[c];
             if (i > 0) s -= out->lam[i - 1].pa[r];
@@ -695,6 +737,7 @@ double tree_qp_out_max_KKT_res(const tree_qp_in *const qp, const tree_qp_out *co
         for (int r = 0; r < nu; r++)
         {
             double s = qp->r[i].pa[r] + out->mu_u[i].pa[r];
+            for (int a = 0; a < qp->nc[i]; a++) s += BLASFEO_DMATEL(&qp->D[i], a, r) * out->mu_d[i].pa[a];
             for (int c = 0; c < nu; c++) s += BLASFEO_DMATEL(&qp->R[i], r, c) * u[c];
             for (int c = 0; c < nx; c++) s += BLASFEO_DMATEL(&qp->S[i], r, c) * x[c];
             tu[r] = s;
@@ -736,6 +779,16 @@ double tree_qp_out_max_KKT_res(const tree_qp_in *const qp, const tree_qp_out *co
             if (u[r] > hi) err = absmax(err, u[r] - hi);
             else if (u[r] < lo) err = absmax(err, lo - u[r]);
             err = absmax(err, m > 0 ? m * (u[r] - hi) : m * (lo - u[r]));
+        }
+        for (int a = 0; a < qp->nc[i]; a++)
+        {   /* general constraints: feasibility and complementarity (tree_qp_common.c:723-755) */
+            double gv = 0.0;
+            for (int c = 0; c < nx; c++) gv += BLASFEO_DMATEL(&qp->C[i], a, c) * x[c];
+            for (int c = 0; c < nu; c++) gv += BLASFEO_DMATEL(&qp->D[i], a, c) * u[c];
+            const double lo = qp->dmin[i].pa[a], hi = qp->dmax[i].pa[a], m = out->mu_d[i].pa[a];
+            if (gv > hi) err = absmax(err, gv - hi);
+            else if (gv < lo) err = absmax(err, lo - gv);
+            err = absmax(err, m > 0 ? m * (gv - hi) : m * (lo - gv));
         }
     }
     free(tx);

@@ -35,6 +35,7 @@ void tqb_layout_tables(const tqb_dims *d, int *base, tqb_tables *t)
     TK(tree, d->Nn); TK(depth, d->Nn); TK(pos, d->Nn); TK(dim, d->Nn);
     TK(xoff, d->Nn); TK(uoff, d->Nn); TK(aoff, d->Nn); TK(boff, d->Nn);
     TK(woff, d->Nn); TK(utoff, d->Nn); TK(hoff, d->Nn);
+    TK(ncn, d->Nn); TK(doff, d->Nn); TK(cgoff, d->Nn);
     TK(lvl_nodes, d->Np > 0 ? d->Np : 1);
     TK(tnode0, d->nT + 1);
     TK(chunk_beg, d->nchunk); TK(chunk_end, d->nchunk); TK(chunk_tree, d->nchunk);
@@ -60,6 +61,8 @@ void tqb_layout_inputs(const tqb_dims *d, double *base, tqb_inputs *in)
     }
     else
         in->H = in->dxmin = in->dxmax = in->dumin = in->dumax = NULL;
+    if (d->NC > 0) { TK(Cg, d->szCg); TK(dmin, d->NC); TK(dmax, d->NC); }
+    else in->Cg = in->dmin = in->dmax = NULL;
 #undef TK
     assert(p - base == d->n_in);
 }
@@ -68,6 +71,7 @@ static long long inputs_size(const tqb_dims *d)
 {
     long long n = pad2(d->szA) + pad2(d->szB) + 7 * pad2(d->X) + 5 * pad2(d->U);
     if (d->has_dense) n += pad2(d->szH) + 2 * pad2(d->X) + 2 * pad2(d->U);
+    if (d->NC > 0) n += pad2(d->szCg) + 2 * pad2(d->NC);
     return n;
 }
 
@@ -120,7 +124,7 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
     d->Nn = (int) Nn;
 
     /* pass 1: counts */
-    long long X = 0, U = 0, szA = 0, szB = 0, szW = 0, szUt = 0, szH = 0;
+    long long X = 0, U = 0, szA = 0, szB = 0, szW = 0, szUt = 0, szH = 0, NC = 0, szCg = 0;
     int Np = 0, Nh = 0, nchunk = 0;
     for (int t = 0; t < nT; t++)
     {
@@ -137,6 +141,12 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
                 szH += (long long) nv * nv;
                 d->has_dense = 1;
                 if (nv > d->nvmax) d->nvmax = nv;
+                if (qp->nc[k] > 0)
+                {   /* general stage constraints ride on the dense stage QP (dual_Newton_tree_qpoases.c:288-298) */
+                    NC += qp->nc[k];
+                    szCg += (long long) qp->nc[k] * nv;
+                    if (qp->nc[k] > d->ncmax) d->ncmax = qp->nc[k];
+                }
             }
             if (nd->stage > Nh) Nh = nd->stage;
             if (k > 0)
@@ -162,7 +172,8 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
     }
     d->X = (int) X; d->U = (int) U; d->szA = szA; d->szB = szB; d->szW = szW; d->szUt = szUt; d->szH = szH;
     d->Np = Np; d->Nh = Nh; d->nchunk = nchunk;
-    d->n_int = 16 * d->Nn + (Np > 0 ? Np : 1) + 2 * (nT + 1) + 7 * nchunk;
+    d->NC = (int) NC; d->szCg = szCg;
+    d->n_int = 19 * d->Nn + (Np > 0 ? Np : 1) + 2 * (nT + 1) + 7 * nchunk;
     d->n_in = inputs_size(d);
 
     f->h_int = (int *) malloc(sizeof(int) * (size_t) d->n_int);
@@ -170,7 +181,7 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
     tqb_tables *T = &f->ht;
 
     /* pass 2: tables */
-    int g0 = 0, xo = 0, uo = 0, ao = 0, bo = 0, wo = 0, uto = 0, c = 0, ho = 0;
+    int g0 = 0, xo = 0, uo = 0, ao = 0, bo = 0, wo = 0, uto = 0, c = 0, ho = 0, dofs = 0, cgo = 0;
     int *lvl_count = (int *) calloc((size_t) Nh + 2, sizeof(int));
     for (int t = 0; t < nT; t++)
     {
@@ -202,10 +213,14 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
             T->xoff[g] = xo; xo += qp->nx[k];
             T->uoff[g] = uo; uo += qp->nu[k];
             T->hoff[g] = -1;
+            T->ncn[g] = 0; T->doff[g] = dofs; T->cgoff[g] = cgo;
             if (solver && solver[k] == TREEQP_QPOASES_SOLVER)
             {
                 T->hoff[g] = ho;
                 ho += (qp->nx[k] + qp->nu[k]) * (qp->nx[k] + qp->nu[k]);
+                T->ncn[g] = qp->nc[k];
+                dofs += qp->nc[k];
+                cgo += qp->nc[k] * (qp->nx[k] + qp->nu[k]);
             }
             T->aoff[g] = ao; T->boff[g] = bo;
             if (k > 0)
@@ -274,7 +289,7 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
     free(lvl_count);
 
     f->h_in = (double *) tqb_pinned_alloc(sizeof(double) * (size_t) d->n_in);
-    size_t nout = (size_t) 3 * d->X + 2 * d->U + 8;
+    size_t nout = (size_t) 3 * d->X + 2 * d->U + (size_t) d->NC + 8;
     f->h_out = (double *) tqb_pinned_alloc(sizeof(double) * nout);
     f->h_status = (int *) tqb_pinned_alloc(sizeof(int) * (size_t) (2 * nT + 2));
     if (!f->h_in || !f->h_out || !f->h_status) { tqb_forest_destroy(f); return NULL; }
@@ -360,6 +375,17 @@ static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gm
             memcpy(in->dxmax + xo, qp->xmax[k].pa, sizeof(double) * (size_t) nx);
             memcpy(in->dumin + uo, qp->umin[k].pa, sizeof(double) * (size_t) nu);
             memcpy(in->dumax + uo, qp->umax[k].pa, sizeof(double) * (size_t) nu);
+            if (T->ncn[g] > 0)
+            {   /* [C D] column-major nc x nv, dmin, dmax (stage_qp_qpoases_init :288-298) */
+                const int nc = T->ncn[g];
+                double *Cg = in->Cg + T->cgoff[g];
+                for (int jc = 0; jc < nx; jc++)
+                    for (int a = 0; a < nc; a++) Cg[a + jc * nc] = BLASFEO_DMATEL(&qp->C[k], a, jc);
+                for (int jc = 0; jc < nu; jc++)
+                    for (int a = 0; a < nc; a++) Cg[a + (nx + jc) * nc] = BLASFEO_DMATEL(&qp->D[k], a, jc);
+                memcpy(in->dmin + T->doff[g], qp->dmin[k].pa, sizeof(double) * (size_t) nc);
+                memcpy(in->dmax + T->doff[g], qp->dmax[k].pa, sizeof(double) * (size_t) nc);
+            }
             for (int i = 0; i < nx; i++)
             {
                 in->Qd[xo + i] = 1.0; in->Qinv[xo + i] = 0.0;
@@ -421,6 +447,14 @@ static int upload_nodes(tqb_forest *f, int ga, int gb, int with_lam0)
         if (xs[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (xs[i] - f->h_in) + x0, x1 - x0);
     for (unsigned i = 0; i < sizeof us / sizeof us[0]; i++)
         if (us[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (us[i] - f->h_in) + u0, u1 - u0);
+    if (d->NC > 0)
+    {
+        const long long c0 = T->cgoff[ga], c1 = last ? d->szCg : T->cgoff[gb];
+        const long long e0 = T->doff[ga], e1 = last ? d->NC : T->doff[gb];
+        rc |= tqb_device_upload_range(f->dev, f->h_in, (in->Cg - f->h_in) + c0, c1 - c0);
+        rc |= tqb_device_upload_range(f->dev, f->h_in, (in->dmin - f->h_in) + e0, e1 - e0);
+        rc |= tqb_device_upload_range(f->dev, f->h_in, (in->dmax - f->h_in) + e0, e1 - e0);
+    }
     return rc;
 }
 
@@ -522,7 +556,7 @@ void tqb_forest_unpack(const tqb_forest *f, int t, tree_qp_out *out)
 {
     const tqb_tables *T = &f->ht;
     const tqb_dims *d = &f->dims;
-    const double *x = f->h_out, *u = x + d->X, *lam = u + d->U, *mux = lam + d->X, *muu = mux + d->X;
+    const double *x = f->h_out, *u = x + d->X, *lam = u + d->U, *mux = lam + d->X, *muu = mux + d->X, *mud = muu + d->U;
     int g0 = T->tnode0[t], N = T->tnode0[t + 1] - g0;
 #pragma omp parallel for schedule(static) if (N > 2048)
     for (int k = 0; k < N; k++)
@@ -533,5 +567,6 @@ void tqb_forest_unpack(const tqb_forest *f, int t, tree_qp_out *out)
         memcpy(out->mu_x[k].pa, mux + xo, sizeof(double) * (size_t) nx);
         memcpy(out->mu_u[k].pa, muu + uo, sizeof(double) * (size_t) nu);
         if (k > 0) memcpy(out->lam[k - 1].pa, lam + xo, sizeof(double) * (size_t) nx);
+        if (T->ncn[g] > 0) memcpy(out->mu_d[k].pa, mud + T->doff[g], sizeof(double) * (size_t) T->ncn[g]);
     }
 }

@@ -37,6 +37,8 @@ typedef struct tqb_tables
     int *aoff, *boff;    /* [Nn] offsets of A_k (nx[k] x nx[dad]) / B_k (nx[k] x nu[dad]), column-major */
     int *woff, *utoff;   /* [Nn] offsets of W_p / Ut_p */
     int *hoff;           /* [Nn] dense stage QP: offset of H_k / P_k ((nx+nu)^2 doubles), -1 = clipping node */
+    int *ncn, *doff, *cgoff; /* [Nn] general stage constraints: rows, offset into d-space (dmin, dmax, mu_d),
+                              * offset of Cg_k = [C_k D_k] (nc x (nx+nu) column-major) */
     int *lvl_nodes;      /* [Np] parents sorted by depth (level lists) */
     int *tnode0;         /* [nT+1] node range of each tree */
     int *chunk_beg, *chunk_end, *chunk_tree; /* [nchunk] fixed-shape reduction chunks (node ranges) */
@@ -51,6 +53,8 @@ typedef struct tqb_dims
     long long szA, szB, szW, szUt;
     long long szH;       /* doubles in the dense stage Hessians (0: every node uses clipping) */
     int has_dense, nvmax; /* any dense stage QP; largest nx+nu among them */
+    int NC, ncmax;       /* general stage constraints: rows in total (d-space), most rows of one node */
+    long long szCg;      /* doubles in the [C D] blocks */
     int dmax, nxmax, numax, nkmax, abmax; /* abmax = max over parents of dim*(nx+nu) */
     int nchunk;
     int n_int;           /* ints in the table block */
@@ -70,7 +74,11 @@ typedef struct tqb_inputs
      * vector-only line-search kernel sees an inactive, weightless variable) */
     double *H;           /* [szH] */
     double *dxmin, *dxmax, *dumin, *dumax; /* [X] [X] [U] [U] */
+    /* general stage constraints dmin <= C x + D u <= dmax of the dense nodes (only when dims.NC > 0) */
+    double *Cg, *dmin, *dmax; /* [szCg] [NC] [NC] */
 } tqb_inputs;
+
+#define TQB_NC_MAX 8 /* general constraint rows per node the warp active-set solver handles */
 
 /* ---- options forwarded to the device ---- */
 typedef struct tqb_opts
@@ -91,7 +99,7 @@ typedef struct tqb_forest
     tqb_tables ht;           /* pointers into h_int */
     double *h_in;            /* pinned input staging (n_in doubles) */
     tqb_inputs hin;          /* pointers into h_in */
-    double *h_out;           /* pinned output staging: x[X] u[U] lam[X] mu_x[X] mu_u[U] */
+    double *h_out;           /* pinned output staging: x[X] u[U] lam[X] mu_x[X] mu_u[U] mu_d[NC] */
     int *h_status, *h_iter;  /* pinned [nT] */
     tqb_device *dev;
     /* statistics of the last solve */

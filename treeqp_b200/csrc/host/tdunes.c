@@ -144,12 +144,11 @@ static void check_stage_solvers(const tree_qp_in *qp_in, const treeqp_tdunes_opt
             }
         }
         else if (opts->qp_solver[k] == TREEQP_QPOASES_SOLVER)
-        {   /* dense stage QP: one warp per node, one lane per variable; general constraints are a
-             * "next" row */
-            if (qp_in->nc[k] > 0 || qp_in->nx[k] + qp_in->nu[k] > 32)
+        {   /* dense stage QP: one warp per node, one lane per variable and per general constraint row */
+            if (qp_in->nx[k] + qp_in->nu[k] + qp_in->nc[k] > 32 || qp_in->nc[k] > TQB_NC_MAX)
             {
-                printf("[TREEQP_B200]: Error! Dense stage QPs need nc = 0 and nx + nu <= 32 (node %d: nx=%d nu=%d nc=%d).\n",
-                       k, qp_in->nx[k], qp_in->nu[k], qp_in->nc[k]);
+                printf("[TREEQP_B200]: Error! Dense stage QPs need nx + nu + nc <= 32 and nc <= %d (node %d: nx=%d nu=%d nc=%d).\n",
+                       TQB_NC_MAX, k, qp_in->nx[k], qp_in->nu[k], qp_in->nc[k]);
                 exit(1);
             }
         }
@@ -282,7 +281,7 @@ static return_t forest_solve(tqb_forest *f, const tqb_opts *o)
 static return_t forest_download(tqb_forest *f)
 {
     if (tqb_device_download(f->dev, f->h_out, &f->d2h_ms)) return TREEQP_UNKNOWN_ERROR;
-    f->d2h_bytes = (long long) sizeof(double) * (3LL * f->dims.X + 2LL * f->dims.U);
+    f->d2h_bytes = (long long) sizeof(double) * (3LL * f->dims.X + 2LL * f->dims.U + f->dims.NC);
     return TREEQP_OK;
 }
 

@@ -456,3 +456,54 @@ def densify_scaled(prob: Problem, seed: int = 1, coupling: float = 0.1, s_scale:
     return Problem(nk=prob.nk, nx=prob.nx, nu=prob.nu, A=prob.A, B=prob.B, b=prob.b, q=prob.q, r=prob.r,
                    xmin=prob.xmin, xmax=prob.xmax, umin=prob.umin, umax=prob.umax,
                    Q=cat(Q), R=cat(R), S=cat(S), lam0=prob.lam0, meta=dict(prob.meta, dense=True))
+
+
+# ------------------------------------------------------------------ general stage constraints
+def bounds_to_general(prob: Problem, xidx=(1,), uidx=(0,)) -> Problem:
+    """The reference's own general-constraint test data (examples/spring_mass.c:100-223, TEST_GENERAL_CONSTRAINTS):
+    the bounds on x[xidx] and u[uidx] of every node become rows of dmin <= C x + D u <= dmax (unit rows) and
+    the bounds themselves are removed; a pinned root state keeps its bounds.  Same QP, same solution."""
+    import copy
+    p = copy.deepcopy(prob)
+    nc, Cl, Dl, lo_l, hi_l = [], [], [], [], []
+    ix = iu = 0
+    for k in range(p.Nn):
+        nx, nu = int(p.nx[k]), int(p.nu[k])
+        rows = [("x", j) for j in xidx if j < nx and not (k == 0 and p.xmin[ix + j] == p.xmax[ix + j])]
+        rows += [("u", j) for j in uidx if j < nu]
+        n = len(rows)
+        Ck, Dk, lo, hi = np.zeros((n, nx)), np.zeros((n, nu)), np.zeros(n), np.zeros(n)
+        for i, (kind, j) in enumerate(rows):
+            if kind == "x":
+                Ck[i, j] = 1.0; lo[i], hi[i] = p.xmin[ix + j], p.xmax[ix + j]
+                p.xmin[ix + j], p.xmax[ix + j] = -TREEQP_INF, TREEQP_INF
+            else:
+                Dk[i, j] = 1.0; lo[i], hi[i] = p.umin[iu + j], p.umax[iu + j]
+                p.umin[iu + j], p.umax[iu + j] = -TREEQP_INF, TREEQP_INF
+        nc.append(n); Cl.append(Ck.flatten(order="F")); Dl.append(Dk.flatten(order="F")); lo_l.append(lo); hi_l.append(hi)
+        ix += nx; iu += nu
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    p.nc, p.C, p.D, p.dmin, p.dmax = np.asarray(nc, dtype=np.int32), cat(Cl), cat(Dl), cat(lo_l), cat(hi_l)
+    p.meta = dict(p.meta, general="bounds_to_general")
+    return p
+
+
+def add_general_rows(prob: Problem, seed: int = 1, nrows: int = 2, width: float = 0.3, leaf_rows: int = 1) -> Problem:
+    """Random coupled rows -width <= c'x + d'u <= width (c, d ~ U(-1, 1), so the origin is strictly feasible)
+    on every node: `nrows` on parents, `leaf_rows` on leaves."""
+    import copy
+    p = copy.deepcopy(prob)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    nc, Cl, Dl, lo_l, hi_l = [], [], [], [], []
+    for k in range(p.Nn):
+        nx, nu = int(p.nx[k]), int(p.nu[k])
+        n = nrows if nu > 0 else leaf_rows
+        if nx == 0:
+            n = min(n, 1) if nu > 0 else 0
+        Ck, Dk = rng.uniform(-1.0, 1.0, (n, nx)), rng.uniform(-1.0, 1.0, (n, nu))
+        nc.append(n); Cl.append(Ck.flatten(order="F")); Dl.append(Dk.flatten(order="F"))
+        lo_l.append(np.full(n, -width)); hi_l.append(np.full(n, width))
+    cat = lambda l: np.concatenate(l) if l else np.zeros(0)
+    p.nc, p.C, p.D, p.dmin, p.dmax = np.asarray(nc, dtype=np.int32), cat(Cl), cat(Dl), cat(lo_l), cat(hi_l)
+    p.meta = dict(p.meta, general="add_general_rows", general_seed=seed)
+    return p
