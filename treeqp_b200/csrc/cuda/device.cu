@@ -372,6 +372,31 @@ static int fused_backsolve_level(tqb_device *D, int l)
     return 1;
 }
 
+/* chain links: depth l continues depth l-1 when every parent of both depths has one kid and the w-th parent of
+ * depth l is the kid of the w-th parent of depth l-1 (the scenario chains below the robust horizon of a
+ * multistage tree): such runs of depths are walked by one warp per chain in one launch */
+static int compute_chain_links(tqb_device *D, const tqb_tables *T, const int *ghost)
+{
+    const tqb_dims *d = &D->dims;
+    if (D->chain_link) return 0;
+    const char *e0 = getenv("TREEQP_B200_NO_CHAIN");
+    D->chain_link = (int *) calloc((size_t) d->Nh + 2, sizeof(int));
+    if ((e0 && e0[0] == '1') || ghost) return 0;
+    for (int l = 2; l < d->Nh; l++)
+    {
+        const int c0 = D->lvl_ptr[l] - D->lvl_ptr[l - 1], c1 = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+        if (c0 != c1 || c1 <= 0) continue;
+        int ok = 1;
+        for (int w = 0; w < c1 && ok; w++)
+        {
+            const int gp = T->lvl_nodes[D->lvl_ptr[l - 1] + w], gk = T->lvl_nodes[D->lvl_ptr[l] + w];
+            ok = T->nkids[gp] == 1 && T->nkids[gk] == 1 && T->kid0[gp] == gk;
+        }
+        D->chain_link[l] = ok;
+    }
+    return 0;
+}
+
 /* The fast path needs: every non-root node nx == NX, every root nx in {0, NX} (the same for all
  * trees), every parent nu == NU, all parents of one depth the same number of kids, kids of one
  * depth either all parents or all leaves, and the combination compiled in. */
@@ -431,21 +456,7 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
         D->v.lvl_desc = D->d_lvl_desc;
     }
     D->fast = 1;
-    {   /* chain links: depth l continues depth l-1 when both have one kid per parent and the w-th
-         * parent of depth l is the kid of the w-th parent of depth l-1 */
-        const char *e0 = getenv("TREEQP_B200_NO_CHAIN");
-        D->chain_link = (int *) calloc((size_t) d->Nh + 1, sizeof(int));
-        if (!(e0 && e0[0] == '1') && !ghost)
-            for (int l = 2; l < d->Nh; l++)
-            {
-                const int c0 = D->lvl_ptr[l] - D->lvl_ptr[l - 1], c1 = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
-                if (D->lvl_md[l] != 1 || D->lvl_md[l - 1] != 1 || c0 != c1 || c1 <= 0) continue;
-                int ok = 1;
-                for (int w = 0; w < c1 && ok; w++)
-                    ok = T.kid0[T.lvl_nodes[D->lvl_ptr[l - 1] + w]] == T.lvl_nodes[D->lvl_ptr[l] + w];
-                D->chain_link[l] = ok;
-            }
-    }
+    if (compute_chain_links(D, &T, ghost)) return 1;
     {   /* leaf records for k_stage_fused; it needs leaves without inputs and few (kid, column) pairs */
         int nleaf = 0, ok = 1;
         /* ghost nodes of a sharded solve (cut nodes owned by another rank) are leaves of the local tree
@@ -582,6 +593,12 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     v.abmax = d->abmax; v.dmax = d->dmax; v.nxmax = d->nxmax; v.numax = d->numax;
 
     if (detect_fast_path(D, h_int, ghost)) return 1;
+    if (!D->chain_link)
+    {   /* trees on the runtime-dimension kernels walk their chain segments in one launch as well */
+        tqb_tables Th;
+        tqb_layout_tables(d, const_cast<int *>(h_int), &Th);
+        if (compute_chain_links(D, &Th, ghost)) return 1;
+    }
 
     /* shared memory per warp (bytes) and warps per CTA for the block kernels */
     int dev = 0, smem_max = 0;
@@ -944,16 +961,21 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
 
             LAUNCH(K_HESS, k_hessian, cdiv(v.Nn, D->wpb_hess), 32 * D->wpb_hess, D->sm_hess, v);
             for (int l = Nh - 1; l >= 0; l--)
-            {
-                const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+            {   /* depths lt..l that form chain segments are walked by one launch */
+                const int lt = chain_top(D, l);
+                const int cnt = D->lvl_ptr[lt + 1] - D->lvl_ptr[lt];
                 if (cnt > 0)
-                    LAUNCH(K_FACTOR, k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[l], cnt, D->pw_fact);
+                    LAUNCH(K_FACTOR, k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1);
+                l = lt;
             }
             for (int l = 1; l < Nh; l++)
             {
+                int lb = chain_bottom(D, l);
+                if (!(lb > l && D->chain_link[l + 1])) lb = l;
                 const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
                 if (cnt > 0)
-                    LAUNCH(K_BACK, k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back);
+                    LAUNCH(K_BACK, k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1);
+                l = lb;
             }
         }
         /* affine model of the stage gradients along dlam + res'*dlam, then the line search */
@@ -965,7 +987,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 /* slots looked at in this pass: all TQB_LS_NT for clipping trees (a pass only streams vectors);
                  * with dense stage QPs the first pass solves tau = 0 and the full step only */
                 const int nt = (v.has_dense && batch == 0) ? 2 : TQB_LS_NT;
-                if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv(v.Nn, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, batch == 0, nt);
+                if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv((long long) v.Nn * nt, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, batch == 0, nt);
                 LAUNCH(K_TRIAL, k_ls_eval, v.nchunk, 256, 0, v, batch == 0);
                 if (D->comm && allreduce_ls_batch(D, batch == 0)) return 1;
                 LAUNCH(K_DECIDE, k_ls_decide, nT, 32 * (TQB_LS_NT + 1), 0, v, batch == 0, nt);

@@ -272,7 +272,8 @@ __global__ void __launch_bounds__(256) k_trial_dense(View v, int first, int nt)
      * independent of each other. */
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int g = blockIdx.x * wpb + wib;
+    /* one warp per (node, step length): the solves of a pass run side by side */
+    const int wid = blockIdx.x * wpb + wib, g = wid / nt, mslot = wid - g * nt;
     if (g >= v.Nn) return;
     const int hoff = v.T.hoff[g];
     if (hoff < 0) return;
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(256) k_trial_dense(View v, int first, int nt)
          * only looks at tau = 0 and the full step */
         double tau = tm;
         if (first && m == 0) tau = 0.0; else tm = v.o.beta * tm;
+        if (m != mslot) continue; /* the step lengths are generated by repeated multiplication, as k_ls_decide does */
         const double gz = g0 + tau * dg;
         double z = z0, mu = 0.0;
         int ws = ws0, fail, ma = 0;
@@ -672,14 +674,21 @@ __global__ void __launch_bounds__(256) k_hessian(View v)
  * dual_Newton_common.c:35-78), y = L^-1 resMod_p, Utilde = Ut_p L^-T, then downdate the parent's
  * diagonal sub-block and right-hand side.  Roots finish with the backward substitution.
  * Bytes per block: d^2 + d + nx*d read, d(d+1)/2 + d + nx*d + d written, nx(nx+1)+2nx RMW. */
-__global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int count, int per_warp)
+/* nlev > 1: depths lvl_begin .. are a chain segment (one kid per parent, `count` parents each, block w of a
+ * depth is the parent of block w of the next one): the warp walks its chain from the deepest block up in ONE
+ * launch; what a block leaves for its parent (W, resMod in HBM) is re-read by the same warp. */
+__global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int count, int per_warp, int nlev)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = blockIdx.x * wpb + wib;
     if (w >= count) return;
-    const int g = v.T.lvl_nodes[lvl_begin + w];
-    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+    if (v.status[v.T.tree[v.T.lvl_nodes[lvl_begin + w]]] != TQB_RUNNING) return;
+#pragma unroll 1
+    for (int lev = nlev - 1; lev >= 0; lev--)
+    {
+    const int g = v.T.lvl_nodes[lvl_begin + lev * count + w];
+    __syncwarp();
 
     const int d = v.T.dim[g], nx = v.T.nx[g], k0 = v.T.kid0[g], dad = v.T.dad[g];
     const int ld = d | 1, ldu = nx | 1;
@@ -773,18 +782,23 @@ __global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int
         warp_trsv_ltn(sW, ld, d, sinv, sy, lane);
     __syncwarp();
     for (int e = lane; e < d; e += 32) v.dlam[xb + e] = sy[e];
+    }
 }
 
 /* One depth level of the root-to-leaves sweep:
  * dlam_p <- L_p^-T (y_p - Utilde_p' dlam_dad[segment of p])   (dual_Newton_tree.c:764-773) */
-__global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, int count, int per_warp)
+__global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, int count, int per_warp, int nlev)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int w = blockIdx.x * wpb + wib;
     if (w >= count) return;
-    const int g = v.T.lvl_nodes[lvl_begin + w];
-    if (v.status[v.T.tree[g]] != TQB_RUNNING) return;
+    if (v.status[v.T.tree[v.T.lvl_nodes[lvl_begin + w]]] != TQB_RUNNING) return;
+#pragma unroll 1
+    for (int lev = 0; lev < nlev; lev++)
+    {   /* nlev > 1: chain segment walked top-down by one warp (see k_factor_level) */
+    const int g = v.T.lvl_nodes[lvl_begin + lev * count + w];
+    __syncwarp();
     const int d = v.T.dim[g], nx = v.T.nx[g], k0 = v.T.kid0[g];
     const int ld = d | 1;
     double *sW = smem + (size_t) wib * per_warp;
@@ -811,6 +825,7 @@ __global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, 
     warp_trsv_ltn(sW, ld, d, sinv, sy, lane);
     __syncwarp();
     for (int e = lane; e < d; e += 32) v.dlam[xb + e] = sy[e];
+    }
 }
 
 /* lambda += tau_final * dlam once the line search of a tree is over.  (The reference moves
