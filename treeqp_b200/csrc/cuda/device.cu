@@ -92,6 +92,7 @@ struct tqb_device
     int *d_lvl_desc;
     int *d_leaf_desc; /* LeafDesc records (tdunes_stage.cuh) */
     int nleaf, fast_stage, stage_grid, n_sm;
+    int n_sm_all; /* SMs of the device (n_sm is only set on the fused stage path) */
     /* subtree sharding (tqb_device_enable_sharding) */
     tqb_comm *comm;
     int cut_depth, ncut, my_cut0, my_ncut;
@@ -212,6 +213,30 @@ static int launch_bs(tqb_device *D, int begin, int cnt)
     if (D->in_sweep) D->sweep_launches++;
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
     CK(launch_pdl(k_backsolve_fused<NX, MD>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, begin, cnt));
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    return 0;
+}
+
+/* fat levels of the root-to-leaves sweep: persistent warps + bulk copies (k_backsolve_tma); TREEQP_B200_NO_TMA=1
+ * keeps the one-block-per-warp kernel everywhere */
+static int g_bs_tma = -1;
+template <int NX, int MD>
+static int launch_bs_tma(tqb_device *D, int begin, int cnt)
+{
+    using Cfg = BsTmaCfg<NX, MD>;
+    static int per_sm = 0;
+    const size_t smem = (size_t) 4 * 2 * Cfg::BUF;
+    if (per_sm == 0)
+    {
+        CK(cudaFuncSetAttribute(k_backsolve_tma<NX, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_backsolve_tma<NX, MD>, 128, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    }
+    const int full = (cnt + 3) / 4, res = D->n_sm_all * per_sm, grid = full < res ? full : res;
+    const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (D->in_sweep) D->sweep_launches++;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    CK(launch_pdl(k_backsolve_tma<NX, MD>, dim3(grid), dim3(128), smem, D->stream, pe_ < 0, D->v, begin, cnt));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
     return 0;
@@ -366,6 +391,18 @@ static int fused_backsolve_level(tqb_device *D, int l)
     const int begin = D->lvl_ptr[l], cnt = D->lvl_ptr[l + 1] - begin;
     if (cnt <= 0) return 0;
     const int nx = D->f_nx, nu = D->f_nu, md = D->lvl_md[l];
+    if (g_bs_tma < 0)
+    {
+        const char *e = getenv("TREEQP_B200_NO_TMA");
+        g_bs_tma = (e && e[0] == '1') ? 0 : 1;
+    }
+    /* at least four blocks per resident warp: below that the one-block-per-warp kernel overlaps better */
+    if (g_bs_tma && cnt >= 64 * D->n_sm_all)
+    {
+#define X(a, b, c) if (nx == a && nu == b && md == c) { if constexpr (BsTmaCfg<a, c>::OK) return launch_bs_tma<a, c>(D, begin, cnt); }
+        TQB_FUSED_LIST(X)
+#undef X
+    }
 #define X(a, b, c) if (nx == a && nu == b && md == c) return launch_bs<a, c>(D, begin, cnt);
     TQB_FUSED_LIST(X)
 #undef X
@@ -592,6 +629,12 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     v.Nn = d->Nn; v.nT = d->nT; v.X = d->X; v.U = d->U; v.nchunk = d->nchunk;
     v.abmax = d->abmax; v.dmax = d->dmax; v.nxmax = d->nxmax; v.numax = d->numax;
 
+    {
+        int dev0 = 0, sms = 148;
+        cudaGetDevice(&dev0);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev0);
+        D->n_sm_all = sms;
+    }
     if (detect_fast_path(D, h_int, ghost)) return 1;
     if (!D->chain_link)
     {   /* trees on the runtime-dimension kernels walk their chain segments in one launch as well */

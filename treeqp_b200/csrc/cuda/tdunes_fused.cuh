@@ -1234,6 +1234,122 @@ __global__ void __launch_bounds__(128) k_backsolve_fused(View v, int lvl_begin, 
     bs_block<NX, MD>(v, (size_t) (lvl_begin + w), true, lane);
 }
 
+/* ---- the same substitution for the FAT levels: persistent warps fed by the bulk-copy engine ------------
+ * A block of the root-to-leaves sweep streams 4.7 KB (packed L, Utilde, y, inverse diagonal) for ~1 us of
+ * dependent arithmetic, and k_backsolve_fused has every warp wait for its own loads (ncu, round 1: 42 % of
+ * the stall samples on the first use of a load, 3.7 TB/s at the bottom level).  Here a warp walks blocks
+ * w, w + nwarps, ... and lane 0 hands the NEXT block's five contiguous pieces to the TMA unit
+ * (cp.async.bulk global -> shared, completion on a warp-private mbarrier) before the warp starts on the
+ * current one: two 5 KB buffers per warp, loads of block i+1 in flight under the arithmetic of block i.
+ * Same arithmetic in the same order as bs_block (bit-identical). */
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+template <int NX, int MD>
+struct BsTmaCfg
+{
+    static constexpr int D = NX * MD;
+    static constexpr int LB = ((D * (D + 1) / 2) * 8 + 15) / 16 * 16;  /* packed L, rounded up (the block owns D*D doubles) */
+    static constexpr int UB = NX * D * 8, YB = D * 8, DB = ((NX * 8) + 15) / 16 * 16;
+    static constexpr int OFF_U = LB, OFF_Y = LB + UB, OFF_I = OFF_Y + YB, OFF_D = OFF_I + YB;
+    static constexpr int BUF = OFF_D + DB;                               /* bytes per buffer */
+    static constexpr bool OK = (D % 2 == 0) && (NX % 2 == 0);           /* 16-byte alignment of every piece */
+};
+
+template <int NX, int MD>
+__global__ void __launch_bounds__(128) k_backsolve_tma(View v, int lvl_begin, int count)
+{
+    using Cfg = BsTmaCfg<NX, MD>;
+    constexpr int D = Cfg::D;
+    extern __shared__ __align__(16) unsigned char bsm[];
+    __shared__ unsigned long long bars[4][2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nwarps = gridDim.x * 4;
+    int w = blockIdx.x * 4 + wib;
+    unsigned char *buf0 = bsm + (size_t) wib * 2 * Cfg::BUF;
+    if (lane == 0) { mbar_init(&bars[wib][0], 1); mbar_init(&bars[wib][1], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    const int4 *descs = reinterpret_cast<const int4 *>(v.lvl_desc);
+    auto issue = [&](const int4 d0, const int4 d1, const int4 d2, int s) {
+        /* lane 0: the five pieces of one block -> buffer s */
+        unsigned char *b = buf0 + (size_t) s * Cfg::BUF;
+        unsigned long long *bar = &bars[wib][s];
+        mbar_expect_tx(bar, (unsigned) Cfg::BUF);
+        bulk_g2s(b, v.W + d1.w, Cfg::LB, bar);
+        bulk_g2s(b + Cfg::OFF_U, v.Ut + d2.x, Cfg::UB, bar);
+        bulk_g2s(b + Cfg::OFF_Y, v.dlam + d1.x, Cfg::YB, bar);
+        bulk_g2s(b + Cfg::OFF_I, v.Linv + d1.x, Cfg::YB, bar);
+        bulk_g2s(b + Cfg::OFF_D, v.dlam + d0.z, Cfg::DB, bar);
+    };
+    /* everything this kernel reads that the previous level wrote is dlam of the parents: wait first */
+    pdl_wait();
+    pdl_release();
+    if (w >= count) return;
+    int4 c0 = __ldg(descs + 3 * (size_t) (lvl_begin + w)), c1 = __ldg(descs + 3 * (size_t) (lvl_begin + w) + 1),
+         c2 = __ldg(descs + 3 * (size_t) (lvl_begin + w) + 2);
+    int4 n0 = c0, n1 = c1, n2 = c2;
+    if (w + nwarps < count)
+    {
+        const size_t e = 3 * (size_t) (lvl_begin + w + nwarps);
+        n0 = __ldg(descs + e); n1 = __ldg(descs + e + 1); n2 = __ldg(descs + e + 2);
+    }
+    if (lane == 0) issue(c0, c1, c2, 0);
+#pragma unroll 1
+    for (int it = 0; w < count; w += nwarps, it++)
+    {
+        const int s = it & 1;
+        const unsigned parity = (unsigned) (it >> 1) & 1u;
+        const bool has_next = w + nwarps < count;
+        if (has_next && lane == 0) issue(n0, n1, n2, s ^ 1);
+        int4 m0 = n0, m1 = n1, m2 = n2; /* descriptor two blocks ahead: in flight under this block's arithmetic */
+        if (w + 2 * nwarps < count)
+        {
+            const size_t e = 3 * (size_t) (lvl_begin + w + 2 * nwarps);
+            m0 = __ldg(descs + e); m1 = __ldg(descs + e + 1); m2 = __ldg(descs + e + 2);
+        }
+        const bool running = v.status[c2.y] == TQB_RUNNING;
+        mbar_wait(&bars[wib][s], parity);
+        const double *Ls = reinterpret_cast<const double *>(buf0 + (size_t) s * Cfg::BUF);
+        const double *Us = Ls + Cfg::OFF_U / 8, *ys = Ls + Cfg::OFF_Y / 8, *is = Ls + Cfg::OFF_I / 8, *dd = Ls + Cfg::OFF_D / 8;
+        const bool act = lane < D;
+        double y = act ? ys[lane] : 0.0;
+        const double inv = act ? is[lane] : 0.0;
+        double sacc = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; c++) sacc += (act ? Us[c * D + lane] : 0.0) * dd[c];
+        y -= sacc;
+#pragma unroll
+        for (int i = D - 1; i >= 0; i--)
+        {
+            const double yi = __shfl_sync(FULL, y, i) * __shfl_sync(FULL, inv, i);
+            if (lane == i) y = yi;
+            else if (lane < i) y -= Ls[(i * (i + 1)) / 2 + lane] * yi;
+        }
+        if (act && running) v.dlam[c1.x + lane] = y;
+        __syncwarp(); /* the buffer is free for the block after the next one */
+        c0 = n0; c1 = n1; c2 = n2;
+        n0 = m0; n1 = m1; n2 = m2;
+    }
+}
+
 /* root-to-leaves substitution along chain w (see k_build_factor_chain): dlam of the block just
  * finished is the parent value of the next one */
 template <int NX>
