@@ -12,7 +12,7 @@ import sys
 src, depth, dst = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 note = sys.argv[4] if len(sys.argv) > 4 else src
 
-CLASS = [(r"k_build_factor", "k_build_factor"), (r"k_backsolve_fused|k_backsolve_chain", "k_backsolve_fused"),
+CLASS = [(r"k_build_factor", "k_build_factor"), (r"k_backsolve_fused|k_backsolve_chain|k_backsolve_tma", "k_backsolve_fused"),
          (r"k_stage_fused<.*, 0>", "k_stage_fused<0>"), (r"k_stage_fused<.*, 2>", "k_stage_fused<2>"),
          (r"k_stage_fused<.*, 3>", "k_stage_fused<3>"), (r"k_ls_eval", "k_ls_eval"),
          (r"k_stage<0>", "k_stage<0>"), (r"k_stage<2>", "k_stage<2>"), (r"k_trial", "k_trial"),
