@@ -220,6 +220,9 @@ static int launch_bs(tqb_device *D, int begin, int cnt)
 
 /* fat levels of the root-to-leaves sweep: persistent warps + bulk copies (k_backsolve_tma); TREEQP_B200_NO_TMA=1
  * keeps the one-block-per-warp kernel everywhere */
+#ifndef TQB_BS_TMA_MIN_PER_SM
+#define TQB_BS_TMA_MIN_PER_SM 64 /* blocks per SM from which a level takes the persistent bulk-copy kernel */
+#endif
 static int g_bs_tma = -1;
 template <int NX, int MD>
 static int launch_bs_tma(tqb_device *D, int begin, int cnt)
@@ -397,7 +400,7 @@ static int fused_backsolve_level(tqb_device *D, int l)
         g_bs_tma = (e && e[0] == '1') ? 0 : 1;
     }
     /* at least four blocks per resident warp: below that the one-block-per-warp kernel overlaps better */
-    if (g_bs_tma && cnt >= 64 * D->n_sm_all)
+    if (g_bs_tma && cnt >= TQB_BS_TMA_MIN_PER_SM * D->n_sm_all)
     {
 #define X(a, b, c) if (nx == a && nu == b && md == c) { if constexpr (BsTmaCfg<a, c>::OK) return launch_bs_tma<a, c>(D, begin, cnt); }
         TQB_FUSED_LIST(X)
