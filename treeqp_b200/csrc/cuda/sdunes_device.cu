@@ -67,6 +67,7 @@ struct SdView
     double *jarena;                   /* operands of the J chain when they do not fit in shared memory */
     int jay_in_smem;
     int no_small_jay;                 /* TREEQP_B200_GENERIC_JAY=1: always the generic chain walk */
+    int serial_jay;                   /* TREEQP_B200_SERIAL_JAY=1: one warp walks the whole chain (no twisted factorisation) */
     int fixed_nx;                     /* 4 / 8 / 16: compile-time-dimension scenario chains; 0: runtime (TREEQP_B200_GENERIC_NX=1) */
 };
 
@@ -866,6 +867,285 @@ __device__ void sd_jay_chain_small(const SdView &v, const JayArena &A, int lane)
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Twisted ("burn at both ends") factorisation of the same chain for small blocks: warp 0 eliminates
+ * the pairs 0 .. m-1 from the left exactly as sd_jay_chain_small does, warp 1 eliminates the pairs
+ * Ns-2 .. m+1 from the RIGHT (the same recursion on the transposed coupling blocks), both hand their
+ * Schur complement and right-hand side to the middle pair m, which warp 0 factors; then the two warps
+ * substitute outwards from the middle at the same time.  The dependent chain is half as long (config 2:
+ * 80 block eliminations per Newton iteration on one warp were 60 % of a solve).  Same pivot rule and
+ * Levenberg-Marquardt policy per block; the elimination ORDER differs from the reference's for the right
+ * half, so the iterates differ in the last bits (parity: iteration counts and 1e-10 on the goldens).
+ *   DIR = +1: block i, successor n = i + 1, coupling M = JL_i L_i^-T            (rows of n, dim_n x dim_i), in JL_i's slot
+ *   DIR = -1: block i, successor n = i - 1, coupling M = JL_n' L_i^-T           (rows of n, dim_n x dim_i), in JL_n's slot
+ *             (element (l, c) of M at [c + l * dim_i], the position of the transposed entry)
+ * ---------------------------------------------------------------------------------------- */
+template <int DM>
+struct JayBlock
+{   /* one block elimination in registers: lane l owns row l (see sd_jay_chain_small) */
+    double w[DM], inv[DM], y;
+};
+
+template <int DM>
+__device__ __forceinline__ int sd_jay_factor_block(const SdView &v, const JayArena &A, int i, int l, bool mine, bool has_carry,
+                                                   const double (&car)[DM], double scv_in, double scv_in2, JayBlock<DM> &B)
+{
+    const int nu = v.d.nu, dim = nu * A.cn[i], lo = A.lo[i];
+    const int regType = v.o.regType;
+    const double regTol = v.o.regTol, regValue = v.o.regValue;
+    double *W = A.JD0 + A.jdo[i];
+    const double *W1 = A.JD1 + A.jdo[i];
+    const bool row = mine && l < dim;
+    double w0[DM];
+    int nreg = 0;
+#pragma unroll
+    for (int c = 0; c < DM; c++)
+    {
+        double val = 0.0;
+        if (row && c < dim)
+        {
+            val = (has_carry && l >= c) ? car[c] : 0.0;
+            val += W[l + c * dim];
+            val += W1[l + c * dim];
+            if (regType == 1 && c == l) val += regValue;
+        }
+        B.w[c] = w0[c] = val;
+        B.inv[c] = 0.0;
+    }
+    double y = 0.0;
+    if (row)
+    {
+        double rhs = A.rhs[lo + l];
+        rhs = rhs + scv_in;
+        rhs = rhs + scv_in2;
+        y = -1.0 * rhs;
+    }
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        bool small = false;
+#pragma unroll
+        for (int j = 0; j < DM; j++)
+        {
+            if (j < dim)
+            {
+                double sacc = B.w[j];
+#pragma unroll
+                for (int t = 0; t < j; t++) sacc -= B.w[t] * __shfl_sync(FULL, B.w[t], j);
+                double piv = __shfl_sync(FULL, sacc, j), pinv;
+                tqb_pivot(piv, pinv);
+                if (l == j) B.w[j] = piv;
+                else if (l > j) B.w[j] = sacc * pinv;
+                B.inv[j] = pinv;
+                small |= (piv <= regTol);
+            }
+        }
+        if (!(regType == 2 && attempt == 0 && small)) { nreg += (regType == 1 || attempt == 1); break; }
+#pragma unroll
+        for (int c = 0; c < DM; c++) B.w[c] = w0[c] + ((c == l && row) ? regValue : 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < DM; j++)
+        if (j < dim)
+        {
+            const double yj = __shfl_sync(FULL, y, j) * B.inv[j];
+            if (l == j) y = yj;
+            else if (l > j && l < dim) y -= B.w[j] * yj;
+        }
+    B.y = y;
+    if (row)
+    {
+        A.rhs[lo + l] = y;
+#pragma unroll
+        for (int c = 0; c < DM; c++)
+            if (c < dim && c <= l) W[l + c * dim] = B.w[c];
+    }
+    if (mine)
+    {
+#pragma unroll
+        for (int c = 0; c < DM; c++)
+            if (c < dim && c == l) A.inv[lo + c] = B.inv[c];
+    }
+    return nreg;
+}
+
+/* elimination half: blocks i0, i0 + DIR, ..., up to (not including) the middle block m; leaves the carried Schur
+ * complement (row l, columns <= l, at car_out[l * DM + c]) and right-hand side (scv_out[l]) for the middle block */
+template <int DM, int DIR>
+__device__ void sd_jay_half_eliminate(const SdView &v, const JayArena &A, int lane, int i0, int m, double *car_out, double *scv_out)
+{
+    const int nu = v.d.nu;
+    const int l = lane < DM ? lane : DM - 1;
+    const bool mine = lane < DM;
+    int nreg = 0;
+    double car[DM], scv = 0.0;
+#pragma unroll
+    for (int c = 0; c < DM; c++) car[c] = 0.0;
+#pragma unroll 1
+    for (int i = i0; i != m; i += DIR)
+    {
+        JayBlock<DM> B;
+        nreg += sd_jay_factor_block<DM>(v, A, i, l, mine, i != i0, car, i != i0 ? scv : 0.0, 0.0, B);
+        const int dim = nu * A.cn[i], n = i + DIR, dimN = nu * A.cn[n];
+        double *JL = A.JL + A.jlo[DIR > 0 ? i : n];
+        const bool rowN = mine && l < dimN;
+        double jl[DM];
+#pragma unroll
+        for (int c = 0; c < DM; c++) jl[c] = (rowN && c < dim) ? (DIR > 0 ? JL[l + c * dimN] : JL[c + l * dim]) : 0.0;
+        /* M <- (coupling) L^-T (dtrsm_rltn): row l, column by column */
+#pragma unroll
+        for (int j = 0; j < DM; j++)
+            if (j < dim)
+            {
+                double t = jl[j];
+#pragma unroll
+                for (int c = 0; c < j; c++) t -= jl[c] * __shfl_sync(FULL, B.w[c], j);
+                jl[j] = t * B.inv[j];
+                if (rowN) { if (DIR > 0) JL[l + j * dimN] = jl[j]; else JL[j + l * dim] = jl[j]; }
+            }
+        /* carried Schur complement (lower) and right-hand side for the successor */
+#pragma unroll
+        for (int b = 0; b < DM; b++)
+        {
+            double t = 0.0;
+#pragma unroll
+            for (int c = 0; c < DM; c++)
+            {
+                const double o = __shfl_sync(FULL, jl[c], b);
+                if (c < dim) t += jl[c] * o;
+            }
+            car[b] = 0.0 - t;
+        }
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < DM; c++)
+        {
+            const double yc = __shfl_sync(FULL, B.y, c);
+            if (c < dim) t += jl[c] * yc;
+        }
+        scv = t;
+    }
+    const int mJ = v.d.mJ; /* the scratch regions hold mJ x mJ / mJ doubles */
+    if (mine && l < mJ)
+    {
+#pragma unroll
+        for (int c = 0; c < DM; c++)
+            if (c < mJ) car_out[l * mJ + c] = car[c];
+        scv_out[l] = scv;
+    }
+    if (nreg > 0 && lane == 0) atomicAdd(&v.info[3], nreg);
+}
+
+/* the middle block: both carries in, factor, solve, and the right-hand-side parts its two neighbours subtract */
+template <int DM>
+__device__ void sd_jay_middle(const SdView &v, const JayArena &A, int lane, int m, const double *carL, const double *scvL,
+                              const double *carR, const double *scvR, double *outL, double *outR)
+{
+    const int nu = v.d.nu, Ns = v.d.Ns, mJ = v.d.mJ;
+    const int l = lane < DM ? lane : DM - 1;
+    const bool mine = lane < DM, in = mine && l < mJ;
+    const int dim = nu * A.cn[m], lo = A.lo[m];
+    double car[DM];
+#pragma unroll
+    for (int c = 0; c < DM; c++) car[c] = (in && c < mJ) ? carL[l * mJ + c] + carR[l * mJ + c] : 0.0;
+    const double sl = in ? scvL[l] : 0.0, sr = in ? scvR[l] : 0.0;
+    JayBlock<DM> B;
+    const int nreg = sd_jay_factor_block<DM>(v, A, m, l, mine, true, car, sl, sr, B);
+    if (nreg > 0 && lane == 0) atomicAdd(&v.info[3], nreg);
+    __syncwarp(); /* the factor of the block is in the arena */
+    /* dlam_m = L^-T y (dtrsv_ltn), as the substitution halves do it */
+    const double *W = A.JD0 + A.jdo[m];
+    const bool row = mine && l < dim;
+    double lc[DM];
+#pragma unroll
+    for (int r = 0; r < DM; r++) lc[r] = (row && r < dim && r > l) ? W[r + l * dim] : 0.0;
+    double y = row ? B.y : 0.0;
+    const double pinv = row ? A.inv[lo + l] : 0.0;
+#pragma unroll
+    for (int r = DM - 1; r >= 0; r--)
+        if (r < dim)
+        {
+            const double yi = __shfl_sync(FULL, y, r) * __shfl_sync(FULL, pinv, r);
+            if (l == r) y = yi;
+            else if (l < r) y -= lc[r] * yi;
+        }
+    if (row) v.dlam[lo + l] = y;
+    /* what the neighbours subtract from their right-hand sides: M' dlam_m */
+    double tl = 0.0, tr = 0.0;
+    if (m > 0)
+    {   /* left neighbour m-1: M = JL_{m-1} L_{m-1}^-T (dim_m x dim_{m-1}), column l */
+        const int dimP = nu * A.cn[m - 1];
+        const double *CJL = A.JL + A.jlo[m - 1];
+#pragma unroll
+        for (int a = 0; a < DM; a++)
+        {
+            const double ya = __shfl_sync(FULL, y, a);
+            if (a < dim && mine && l < dimP) tl += CJL[a + l * dim] * ya;
+        }
+    }
+    if (m < Ns - 2)
+    {   /* right neighbour m+1: M(l', c) at JL_m[c + l' * dim_{m+1}], lane c */
+        const int dimP = nu * A.cn[m + 1];
+        const double *CJL = A.JL + A.jlo[m];
+#pragma unroll
+        for (int a = 0; a < DM; a++)
+        {
+            const double ya = __shfl_sync(FULL, y, a);
+            if (a < dim && mine && l < dimP) tr += CJL[l + a * dimP] * ya;
+        }
+    }
+    __syncwarp();
+    if (in) { outL[l] = tl; outR[l] = tr; }
+}
+
+/* substitution half: from the block next to the middle outwards to i0 */
+template <int DM, int DIR>
+__device__ void sd_jay_half_substitute(const SdView &v, const JayArena &A, int lane, int i0, int m, const double *scv_in)
+{
+    const int nu = v.d.nu;
+    const int l = lane < DM ? lane : DM - 1;
+    const bool mine = lane < DM;
+    double scv = (mine && l < v.d.mJ) ? scv_in[l] : 0.0;
+#pragma unroll 1
+    for (int i = m - DIR; ; i -= DIR)
+    {
+        const int dim = nu * A.cn[i], lo = A.lo[i];
+        const double *W = A.JD0 + A.jdo[i];
+        const bool row = mine && l < dim;
+        double lc[DM];
+#pragma unroll
+        for (int r = 0; r < DM; r++) lc[r] = (row && r < dim && r > l) ? W[r + l * dim] : 0.0;
+        double y = 0.0, pinv = 0.0;
+        if (row)
+        {
+            y = A.rhs[lo + l] - scv;
+            pinv = A.inv[lo + l];
+        }
+#pragma unroll
+        for (int r = DM - 1; r >= 0; r--)
+            if (r < dim)
+            {
+                const double yi = __shfl_sync(FULL, y, r) * __shfl_sync(FULL, pinv, r);
+                if (l == r) y = yi;
+                else if (l < r) y -= lc[r] * yi;
+            }
+        if (row) v.dlam[lo + l] = y;
+        if (i == i0) break;
+        const int p = i - DIR, dimP = nu * A.cn[p];
+        /* DIR = +1: M_p = JL_p L_p^-T (dim_i x dim_p) in JL_p: t_l = sum_a JL_p[a + l dim_i] y_a
+         * DIR = -1: M_p (rows of i, dim_i x dim_p) in JL_i at [c + l' dim_p]: t_c = sum_l' JL_i[c + l' dim_p] y_l' */
+        const double *CJL = A.JL + A.jlo[DIR > 0 ? p : i];
+        double t = 0.0;
+#pragma unroll
+        for (int a = 0; a < DM; a++)
+        {
+            const double ya = __shfl_sync(FULL, y, a);
+            if (a < dim && mine && l < dimP) t += (DIR > 0 ? CJL[a + l * dim] : CJL[l + a * dimP]) * ya;
+        }
+        scv = t;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
  * dmu_i = Lambda_i^-1 (-res_i + Zbar (dlam_{i-1} - dlam_i))  (calculate_delta_mu :1077-1205), then
  * the derivative of the unconstrained stage solutions along (dmu, dlam): along the step the stage
  * gradients are affine in the step length, so a line-search trial is a pure vector pass.
@@ -1065,7 +1345,32 @@ __global__ void __launch_bounds__(512) k_sdunes_solve(SdView v)
                 const JayArena A = jay_arena(v, v.jay_in_smem ? smem : v.jarena);
                 sd_jay_gather(v, A, tm);
                 __syncthreads();
-                if (tm.wib == 0)
+                if (v.d.mJ <= 8 && !v.no_small_jay && !v.serial_jay && Ns - 1 >= 5 && tm.wpb >= 2)
+                {   /* twisted factorisation: warps 0 and 1 eliminate towards the middle pair m */
+                    const int m = (Ns - 1) / 2;
+                    double *carL = A.car, *carR = A.w0, *scvL = A.scv, *scvR = A.sy; /* scratch of the generic walk, free here */
+                    if (v.d.mJ <= 4)
+                    {
+                        if (tm.wib == 0) sd_jay_half_eliminate<4, +1>(v, A, tm.lane, 0, m, carL, scvL);
+                        else if (tm.wib == 1) sd_jay_half_eliminate<4, -1>(v, A, tm.lane, Ns - 2, m, carR, scvR);
+                        __syncthreads();
+                        if (tm.wib == 0) sd_jay_middle<4>(v, A, tm.lane, m, carL, scvL, carR, scvR, scvL, scvR);
+                        __syncthreads();
+                        if (tm.wib == 0) sd_jay_half_substitute<4, +1>(v, A, tm.lane, 0, m, scvL);
+                        else if (tm.wib == 1) sd_jay_half_substitute<4, -1>(v, A, tm.lane, Ns - 2, m, scvR);
+                    }
+                    else
+                    {
+                        if (tm.wib == 0) sd_jay_half_eliminate<8, +1>(v, A, tm.lane, 0, m, carL, scvL);
+                        else if (tm.wib == 1) sd_jay_half_eliminate<8, -1>(v, A, tm.lane, Ns - 2, m, carR, scvR);
+                        __syncthreads();
+                        if (tm.wib == 0) sd_jay_middle<8>(v, A, tm.lane, m, carL, scvL, carR, scvR, scvL, scvR);
+                        __syncthreads();
+                        if (tm.wib == 0) sd_jay_half_substitute<8, +1>(v, A, tm.lane, 0, m, scvL);
+                        else if (tm.wib == 1) sd_jay_half_substitute<8, -1>(v, A, tm.lane, Ns - 2, m, scvR);
+                    }
+                }
+                else if (tm.wib == 0)
                 {
                     if (v.d.mJ <= 4 && !v.no_small_jay) sd_jay_chain_small<4>(v, A, tm.lane);
                     else if (v.d.mJ <= 8 && !v.no_small_jay) sd_jay_chain_small<8>(v, A, tm.lane);
@@ -1208,6 +1513,8 @@ static int sd_build_device(tqb_sd_device *D, const int *h_int)
     {
         const char *e = getenv("TREEQP_B200_GENERIC_JAY");
         v.no_small_jay = (e && e[0] == '1') ? 1 : 0;
+        const char *e2 = getenv("TREEQP_B200_SERIAL_JAY");
+        v.serial_jay = (e2 && e2[0] == '1') ? 1 : 0;
     }
     {
         /* TREEQP_B200_GENERIC_NX: 1 = runtime-dimension chains, 0 = the nx = 4 / 8 / 16 instances;
