@@ -363,6 +363,11 @@ def bench_batch(lib, n=4096, reps=3, rank=0, world=1, barrier=None, max_over_ran
            # per GPU: this rank's QPs over the (max over ranks) time, against ONE GPU's HBM peak
            "roofline": solve_roofline(probs[0], int(iters.sum()), min(t_res), st["h2d_bytes"] + st["d2h_bytes"],
                                       st["ls_total"] / max(int(iters.sum()), 1))}
+    if world == 1:
+        try:
+            out["mpc_step_x0_only"] = bench_batch_x0(lib, min(n, 1024))
+        except Exception as e:
+            out["mpc_step_x0_only"] = {"error": repr(e)}
     if world > 1:
         out["scaling"] = "strong (4096 QPs in total)"
     path = ref_lib_path(False)
@@ -378,6 +383,41 @@ def bench_batch(lib, n=4096, reps=3, rank=0, world=1, barrier=None, max_over_ran
         out["cpu_reference_qp_per_s_per_core"] = m / tt
         out["cpu_sample"] = "first %d QPs of the batch, 1 thread, unmodified reference; iteration counts identical" % m
     batch.destroy()
+    return out
+
+
+def bench_batch_x0(lib, n):
+    """closed-loop step of a batch of MPC QPs: between two samples only x0 of every QP changes
+    (benchmark/treeqp_main.m:235-237); treeqp_tdunes_batch_update_x0 re-sends b of the root's children instead
+    of the whole problem.  Timed: update_x0 + solve_resident + download (set_x0 on the host containers is the
+    caller's data preparation, like building qp_in for the other e2e numbers)."""
+    rng = np.random.default_rng(11)
+    probs = [P.linear_chain(4, 3, 3, 2, 20, seed=i, eliminate_x0=False) for i in range(n)]
+    for p in probs:
+        p.umin[:] = -0.5; p.umax[:] = 0.5
+        nx0 = int(p.nx[0])
+        p.xmin[nx0:] = -1e12; p.xmax[nx0:] = 1e12
+    qis = [capi.QpIn(lib, p) for p in probs]
+    for q in qis:
+        q.eliminate_x0()
+    dims = [P.eliminate_x0(p) for p in probs]
+    qos = [capi.QpOut(lib, d) for d in dims]
+    b = capi.TdunesBatch(lib, qis)
+    assert b.upload() == capi.TREEQP_OK and b.solve_resident() == capi.TREEQP_OK
+    full = b.stats()["h2d_bytes"]
+    ts = []
+    for step in range(3):
+        for q, p in zip(qis, probs):
+            q.set_x0(p.xmin[:int(p.nx[0])] * (0.9 + 0.1 * rng.random()))
+        t0 = time.perf_counter()
+        assert b.update_x0() == capi.TREEQP_OK
+        h2d = b.stats()["h2d_bytes"]
+        assert b.solve_resident() == capi.TREEQP_OK and b.download(qos) == capi.TREEQP_OK
+        ts.append(time.perf_counter() - t0)
+    out = {"workload": "%d x linear_chain (175 nodes), x0 of every QP changed, update_x0 + solve_resident + download" % n,
+           "qp_per_s": n / min(ts), "ms_per_step": 1e3 * min(ts), "h2d_bytes_update_x0": h2d, "h2d_bytes_full_upload": full,
+           "converged": int((b.status == 0).sum())}
+    b.destroy()
     return out
 
 

@@ -574,6 +574,9 @@ treeqp_tdunes_batch *treeqp_tdunes_batch_create(int n, const tree_qp_in *const *
 void treeqp_tdunes_batch_set_dual_initialization(treeqp_tdunes_batch *batch, int i,
                                                  const double *lambda);
 return_t treeqp_tdunes_batch_upload(treeqp_tdunes_batch *batch, const tree_qp_in *const *qp_in);
+/* closed-loop step of the whole batch: after tree_qp_in_set_x0_colmaj / _strvec on every qp_in, re-send only what
+ * depends on x0 (root + its children of every tree; one strided copy per array for a batch of equal shapes) */
+return_t treeqp_tdunes_batch_update_x0(treeqp_tdunes_batch *batch, const tree_qp_in *const *qp_in);
 return_t treeqp_tdunes_batch_solve_resident(treeqp_tdunes_batch *batch, return_t *status);
 return_t treeqp_tdunes_batch_download(treeqp_tdunes_batch *batch, tree_qp_out *const *qp_out);
 /* upload + solve_resident + download */

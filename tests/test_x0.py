@@ -143,3 +143,42 @@ def test_second_solve_continues_from_last_multipliers(product_lib, ref_lib):
     assert res["ours"][0] == res["ref"][0], (res["ours"][0], res["ref"][0])
     assert res["ref"][0][0] == (1, 10) and res["ref"][0][-1] == (0, 0)
     assert CS.rel_err(res["ours"][1], res["ref"][1]) < 1e-10 and CS.rel_err(res["ours"][2], res["ref"][2]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_batch_update_x0_matches_fresh_batch(product_lib):
+    """closed-loop step of a batch: set_x0 on every QP + treeqp_tdunes_batch_update_x0 (one strided copy per array)
+    against a batch built from scratch with the new initial states"""
+    L = product_lib
+    n = 12
+    rng = np.random.default_rng(3)
+    def make(x0s):
+        probs = [P.spring_mass(3, 2, 10, x0=x0) for x0 in x0s]
+        qis = [capi.QpIn(L, p) for p in probs]
+        for q in qis:
+            q.eliminate_x0()
+        dims = [P.eliminate_x0(p) for p in probs]
+        return probs, qis, dims
+    x0a = [np.array(X0A) + 0.01 * rng.standard_normal(4) for _ in range(n)]
+    x0b = [np.array(X0B) * (0.5 + 0.5 * rng.random()) for _ in range(n)]
+    _, qis, dims = make(x0a)
+    qos = [capi.QpOut(L, d) for d in dims]
+    b = capi.TdunesBatch(L, qis)
+    assert b.upload() == capi.TREEQP_OK and b.solve_resident() == capi.TREEQP_OK
+    full = b.stats()["h2d_bytes"]
+    for q, x0 in zip(qis, x0b):
+        q.set_x0(x0)
+    assert b.update_x0() == capi.TREEQP_OK
+    assert 0 < b.stats()["h2d_bytes"] < full / 4
+    assert b.solve_resident() == capi.TREEQP_OK and b.download(qos) == capi.TREEQP_OK
+    it_upd = [o.iter for o in qos]
+    x_upd = [o.x.copy() for o in qos]
+    _, qis2, dims2 = make(x0b)
+    qos2 = [capi.QpOut(L, d) for d in dims2]
+    b2 = capi.TdunesBatch(L, qis2)
+    assert b2.solve(qos2) == capi.TREEQP_OK
+    assert (b.status == 0).all() and (b2.status == 0).all()
+    for i in range(n):
+        assert qos2[i].iter == it_upd[i]
+        assert CS.rel_err(x_upd[i], qos2[i].x) < 1e-12
+    b.destroy(); b2.destroy()

@@ -276,6 +276,8 @@ class TreeQpLib:
             L.treeqp_tdunes_batch_set_dual_initialization.restype = None
             L.treeqp_tdunes_batch_upload.argtypes = [vp, C.POINTER(vp)]
             L.treeqp_tdunes_batch_upload.restype = C.c_int
+            L.treeqp_tdunes_batch_update_x0.argtypes = [vp, C.POINTER(vp)]
+            L.treeqp_tdunes_batch_update_x0.restype = C.c_int
             L.treeqp_tdunes_batch_solve_resident.argtypes = [vp, c_int_p]
             L.treeqp_tdunes_batch_solve_resident.restype = C.c_int
             L.treeqp_tdunes_batch_download.argtypes = [vp, C.POINTER(vp)]
@@ -611,6 +613,10 @@ class TdunesBatch:
 
     def upload(self) -> int:
         return int(self.lib.lib.treeqp_tdunes_batch_upload(self.handle, self.in_ptrs))
+
+    def update_x0(self) -> int:
+        """after QpIn.set_x0 on every member: re-send only what depends on x0"""
+        return int(self.lib.lib.treeqp_tdunes_batch_update_x0(self.handle, self.in_ptrs))
 
     def solve_resident(self) -> int:
         return int(self.lib.lib.treeqp_tdunes_batch_solve_resident(self.handle, _ip(self.status)))

@@ -729,6 +729,14 @@ extern "C" int tqb_device_upload_range(tqb_device *D, const double *h_in, long l
     return 0;
 }
 
+extern "C" int tqb_device_upload_2d(tqb_device *D, const double *h_in, long long off, long long pitch, long long width, int rows)
+{
+    if (width <= 0 || rows <= 0) return 0;
+    CK(cudaMemcpy2DAsync(D->d_in + off, sizeof(double) * (size_t) pitch, h_in + off, sizeof(double) * (size_t) pitch,
+                         sizeof(double) * (size_t) width, (size_t) rows, cudaMemcpyHostToDevice, D->stream));
+    return 0;
+}
+
 extern "C" int tqb_device_upload_end(tqb_device *D, double *ms_total)
 {
     CK(cudaEventRecord(D->ev1, D->stream));

@@ -468,6 +468,66 @@ int tqb_forest_update_nodes(tqb_forest *f, int t, const tree_qp_in *qp, int j0, 
     return rc;
 }
 
+/* Batch of closed-loop MPC QPs: only x0 changed since the last upload.  Re-pack the root and its children of every
+ * tree (b of the root's children, r[0] and the root's bounds / dmin / dmax depend on x0, tree_qp_common.c:2154-2227)
+ * and send those slices: trees of one shape sit at a constant stride in every array, so each array travels as ONE
+ * strided copy for the whole batch. */
+int tqb_forest_update_x0_batch(tqb_forest *f, const tree_qp_in *const *qp, long long *bytes)
+{
+    const tqb_tables *T = &f->ht;
+    const tqb_dims *d = &f->dims;
+    const tqb_inputs *in = &f->hin;
+    const int nT = d->nT;
+    const int n0 = 1 + qp[0]->tree[0].nkids, N0 = T->tnode0[1] - T->tnode0[0];
+    int uniform = d->NC == 0;
+    for (int t = 0; t < nT && uniform; t++)
+        uniform = qp[t]->N == N0 && 1 + qp[t]->tree[0].nkids == n0;
+    /* strides of one tree in every space; equal shapes give equal strides */
+    const long long sX = nT > 1 ? T->xoff[T->tnode0[1]] - T->xoff[0] : d->X, sU = nT > 1 ? T->uoff[T->tnode0[1]] - T->uoff[0] : d->U;
+    const long long sA = nT > 1 ? T->aoff[T->tnode0[1]] - T->aoff[0] : d->szA, sB = nT > 1 ? T->boff[T->tnode0[1]] - T->boff[0] : d->szB;
+    for (int t = 1; t < nT && uniform; t++)
+    {
+        const int g = T->tnode0[t];
+        uniform = T->xoff[g] == t * sX && T->uoff[g] == t * sU && T->aoff[g] == t * sA && T->boff[g] == t * sB;
+        for (int j = 0; j <= n0 && uniform && j < N0; j++)
+            uniform = T->xoff[g + j] - T->xoff[g] == T->xoff[j] && T->uoff[g + j] - T->uoff[g] == T->uoff[j];
+    }
+#pragma omp parallel for schedule(static) if (nT > 32)
+    for (int t = 0; t < nT; t++) pack_range(f, t, qp[t], NULL, 0, 1 + qp[t]->tree[0].nkids);
+    int rc = tqb_device_upload_begin(f->dev);
+    long long sent = 0;
+    if (!uniform)
+    {
+        for (int t = 0; t < nT; t++)
+        {
+            const int g0 = T->tnode0[t];
+            rc |= upload_nodes(f, g0, g0 + 1 + qp[t]->tree[0].nkids, 0);
+        }
+        sent = -1;
+    }
+    else
+    {
+        const int last = n0 >= N0;
+        const long long wx = last ? sX : T->xoff[n0], wu = last ? sU : T->uoff[n0];
+        const long long wa = last ? sA : T->aoff[n0], wb = last ? sB : T->boff[n0];
+        const double *xs[] = {in->b, in->q, in->Qd, in->Qinv, in->xmin, in->xmax, in->dxmin, in->dxmax};
+        const double *us[] = {in->r, in->Rd, in->Rinv, in->umin, in->umax, in->dumin, in->dumax};
+        rc |= tqb_device_upload_2d(f->dev, f->h_in, in->A - f->h_in, sA, wa, nT);
+        rc |= tqb_device_upload_2d(f->dev, f->h_in, in->B - f->h_in, sB, wb, nT);
+        sent += (wa + wb) * nT;
+        for (unsigned i = 0; i < sizeof xs / sizeof xs[0]; i++)
+            if (xs[i]) { rc |= tqb_device_upload_2d(f->dev, f->h_in, xs[i] - f->h_in, sX, wx, nT); sent += wx * nT; }
+        for (unsigned i = 0; i < sizeof us / sizeof us[0]; i++)
+            if (us[i]) { rc |= tqb_device_upload_2d(f->dev, f->h_in, us[i] - f->h_in, sU, wu, nT); sent += wu * nT; }
+        if (d->has_dense)
+        {   /* dense Hessian blocks do not depend on x0 */
+        }
+    }
+    rc |= tqb_device_upload_end(f->dev, &f->h2d_ms);
+    if (bytes) *bytes = sent < 0 ? -1 : (long long) sizeof(double) * sent;
+    return rc;
+}
+
 int tqb_forest_upload_lambda0(tqb_forest *f)
 {
     int rc = tqb_device_upload_begin(f->dev);

@@ -132,6 +132,7 @@ int tqb_forest_pack_upload(tqb_forest *f, const struct tree_qp_in_ *const *qp, d
 /* re-pack and re-send nodes [j0, j1) of tree t only (what an x0 update touches) / the dual start only */
 int tqb_forest_pack_upload_mapped(tqb_forest *f, const struct tree_qp_in_ *full_qp, const int *gmap, double *tail_ms);
 int tqb_forest_update_nodes(tqb_forest *f, int t, const struct tree_qp_in_ *qp, int j0, int j1);
+int tqb_forest_update_x0_batch(tqb_forest *f, const struct tree_qp_in_ *const *qp, long long *bytes);
 int tqb_forest_upload_lambda0(tqb_forest *f);
 int tqb_forest_warm_start(tqb_forest *f);
 void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda);
@@ -154,6 +155,8 @@ int tqb_device_upload(tqb_device *d, const double *h_in, long long n_in, double 
 int tqb_device_upload_begin(tqb_device *d);
 int tqb_device_upload_range(tqb_device *d, const double *h_in, long long off, long long n);
 int tqb_device_upload_end(tqb_device *d, double *ms_total);
+/* `rows` slices of `width` doubles at stride `pitch` starting at offset `off` of the input block */
+int tqb_device_upload_2d(tqb_device *d, const double *h_in, long long off, long long pitch, long long width, int rows);
 int tqb_device_warm_start(tqb_device *d, long long lam0_off, long long n);
 int tqb_device_kkt(tqb_device *d, double *h_kkt);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */

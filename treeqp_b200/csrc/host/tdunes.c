@@ -516,6 +516,18 @@ return_t treeqp_tdunes_batch_upload(treeqp_tdunes_batch *b, const tree_qp_in *co
     return TREEQP_OK;
 }
 
+/* closed-loop step of a batch: only x0 of every QP changed (tree_qp_in_set_x0_* was called on each qp_in) */
+return_t treeqp_tdunes_batch_update_x0(treeqp_tdunes_batch *b, const tree_qp_in *const *qp_in)
+{
+    if (!b || !b->uploaded) return TREEQP_UNKNOWN_ERROR;
+    double t0 = tqb_wall_ms();
+    long long bytes = 0;
+    if (tqb_forest_update_x0_batch(b->forest, qp_in, &bytes)) return TREEQP_UNKNOWN_ERROR;
+    b->forest->pack_ms = tqb_wall_ms() - t0;
+    b->forest->h2d_bytes = bytes;
+    return TREEQP_OK;
+}
+
 return_t treeqp_tdunes_batch_solve_resident(treeqp_tdunes_batch *b, return_t *status)
 {
     if (!b->opts_ok) return TREEQP_INVALID_OPTION;
