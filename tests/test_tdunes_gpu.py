@@ -23,12 +23,25 @@ def check_against(sol, ref, prob, tol=TOL):
         assert np.array_equal(getattr(sol, k) == hi, ref[k] == hi), "active set (upper) differs: " + k
 
 
-@pytest.mark.parametrize("path", ["fast", "generic"])
+def set_path(monkeypatch, path):
+    """path=fast: compile-time-dimension fused kernels where the tree is uniform (tdunes_fused.cuh), one launch per
+    phase and depth; path=small: the same device functions inside ONE persistent kernel, one CTA per tree
+    (tdunes_small.cuh; the default for uniform trees of up to 1024 nodes, forced here whatever the size);
+    path=generic: runtime-dimension kernels forced through TREEQP_B200_GENERIC=1 (all read at create)"""
+    monkeypatch.setenv("TREEQP_B200_GENERIC", "1" if path == "generic" else "0")
+    monkeypatch.setenv("TREEQP_B200_SMALL", "1" if path == "small" else "0")
+
+
+PATHS = ["fast", "small", "generic"]
+# uniform trees: the persistent kernel must be what ran (k_init + the kernel + copy-out: a handful of launches)
+UNIFORM = {"spring_mass_cfg1", "spring_mass_tight", "spring_mass_cfg2tree", "random_d6_u05", "random_d10_u02", "random_d8_u05",
+           "random_ternary_chain", "linear_chain_cfg4", "linear_chain_cfg4_s7", "quadcopter_cfg5", "crane_cfg5"}
+
+
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", CS.CASE_NAMES)
 def test_solve_matches_reference_golden(name, path, product_lib, monkeypatch):
-    """path=fast: compile-time-dimension fused kernels where the tree is uniform (tdunes_fused.cuh);
-    path=generic: runtime-dimension kernels forced through TREEQP_B200_GENERIC=1 (read at create)"""
-    monkeypatch.setenv("TREEQP_B200_GENERIC", "1" if path == "generic" else "0")
+    set_path(monkeypatch, path)
     prob, opts = CS.get_case(name)
     g = CS.golden(name)
     sol = capi.solve_tdunes(product_lib, prob, **opts)
@@ -37,12 +50,14 @@ def test_solve_matches_reference_golden(name, path, product_lib, monkeypatch):
     check_against(sol, g, prob)
     assert sol.kkt < 1e-8          # the reference's own acceptance threshold (spring_mass_dual_newton_tree.c:156)
     assert sol.stats["kernel_launches"] > 0
+    if path == "small" and name in UNIFORM:
+        assert sol.stats["kernel_launches"] <= 8, "the persistent small-tree kernel did not run"
 
 
-@pytest.mark.parametrize("path", ["fast", "generic"])
+@pytest.mark.parametrize("path", PATHS)
 @pytest.mark.parametrize("name", ["spring_mass_tight", "random_d6_u05", "random_d8_u05", "random_d10_u02"])
 def test_line_search_counts_match_oracle(name, path, product_lib, monkeypatch):
-    monkeypatch.setenv("TREEQP_B200_GENERIC", "1" if path == "generic" else "0")
+    set_path(monkeypatch, path)
     prob, opts = CS.get_case(name)
     s = OP.solve_port(prob, **CS.port_opts(opts))
     sol = capi.solve_tdunes(product_lib, prob, **opts)
@@ -54,7 +69,9 @@ def test_line_search_counts_match_oracle(name, path, product_lib, monkeypatch):
 @pytest.mark.parametrize("opts", [dict(regType=1), dict(termCondition=0, stationarityTolerance=1e-14),
                                   dict(termCondition=1), dict(lineSearchBeta=0.5, lineSearchGamma=0.2), dict(lineSearchBeta=0.8, lineSearchGamma=0.05),
                                   dict(maxIter=7), dict(lineSearchMaxIter=3, maxIter=20)])
-def test_options_match_oracle(opts, product_lib):
+@pytest.mark.parametrize("path", ["fast", "small"])
+def test_options_match_oracle(opts, path, product_lib, monkeypatch):
+    set_path(monkeypatch, path)
     prob, _ = CS.get_case("spring_mass_tight")
     s = OP.solve_port(prob, **CS.port_opts(opts))
     sol = capi.solve_tdunes(product_lib, prob, **opts)

@@ -16,6 +16,7 @@
 #include "tdunes_kernels.cuh"
 #include "tdunes_fused.cuh"
 #include "tdunes_stage.cuh"
+#include "tdunes_small.cuh"
 #include "comm.cuh"
 
 static thread_local char g_err[512] = "";
@@ -29,16 +30,16 @@ static thread_local char g_err[512] = "";
         }                                                                                        \
     } while (0)
 
-enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DIR, K_TRIAL, K_STEP, K_FINISH, K_COMM, K_NCLASS };
+enum { K_INIT, K_STAGE, K_GRAD, K_REDUCE, K_DECIDE, K_HESS, K_FACTOR, K_BACK, K_DIR, K_TRIAL, K_STEP, K_FINISH, K_COMM, K_SMALL, K_NCLASS };
 /* event classes carry the names of the kernels that run: uniform trees take the compile-time-dimension
  * kernels (tdunes_fused.cuh, tdunes_stage.cuh), everything else the runtime-dimension ones; the table in
  * use is that of the most recent solve of this thread */
 static const char *const k_names_generic[K_NCLASS] = {"k_init", "k_stage<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
                                                       "k_hessian", "k_factor_level", "k_backsolve_level", "k_stage<2>",
-                                                      "k_trial_dense+k_ls_eval", "k_lambda_step", "k_finish", "nccl+pack"};
+                                                      "k_trial_dense+k_ls_eval", "k_lambda_step", "k_finish", "nccl+pack", "k_tdunes_small"};
 static const char *const k_names_fused[K_NCLASS] = {"k_init", "k_stage_fused<0>", "k_gradient", "k_chunk_reduce", "k_decide_*",
                                                     "k_hessian", "k_build_factor", "k_backsolve_fused", "k_stage_fused<2>",
-                                                    "k_ls_eval", "k_lambda_step", "k_finish", "nccl+pack"};
+                                                    "k_ls_eval", "k_lambda_step", "k_finish", "nccl+pack", "k_tdunes_small"};
 static thread_local const char *const *k_names = k_names_generic;
 static int g_profile = -1;
 #define TQB_MAX_EVENTS 65536
@@ -99,6 +100,10 @@ struct tqb_device
     int *d_cut_nodes;
     double *d_send, *d_recv, *d_tred;
     const tqb_p2p_dev *p2p; /* peer mailboxes over NVLink; NULL: NCCL collectives */
+    /* small trees: the whole Newton loop in one persistent kernel, one CTA per tree (tdunes_small.cuh) */
+    int small, small_warps, small_mdmax;
+    size_t small_smem;
+    SmallPlan small_plan;
 };
 
 extern "C" const char *tqb_cuda_last_error(void) { return g_err; }
@@ -540,6 +545,115 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
     return 0;
 }
 
+/* ---- small trees: one persistent CTA per tree (tdunes_small.cuh) ------------------------------ */
+#ifndef TQB_SMALL_MAX_NODES
+#define TQB_SMALL_MAX_NODES 1024 /* nodes per tree up to which the one-CTA-per-tree kernel is taken */
+#endif
+template <int NX, int NU, int MD>
+struct SmallSm
+{
+    static constexpr int A = BfSel<NX, NU, MD, NX, false>::SMEM, B = BfSel<NX, NU, MD, 0, true>::SMEM, C = BfSel<NX, NU, MD, NX, true>::SMEM;
+    static constexpr int V = A > B ? (A > C ? A : C) : (B > C ? B : C);
+};
+template <int NX, int NU, int MDMAX>
+static constexpr int small_smem_warp()
+{
+    int m = SmallSm<NX, NU, 1>::V;
+    if constexpr (MDMAX >= 2) m = SmallSm<NX, NU, 2>::V > m ? SmallSm<NX, NU, 2>::V : m;
+    if constexpr (MDMAX >= 3) m = SmallSm<NX, NU, 3>::V > m ? SmallSm<NX, NU, 3>::V : m;
+    if constexpr (MDMAX >= 4) m = SmallSm<NX, NU, 4>::V > m ? SmallSm<NX, NU, 4>::V : m;
+    return m;
+}
+
+/* (NX, NU, largest MD compiled in) of the persistent kernel: one instance per (NX, NU) of TQB_FUSED_LIST */
+#define TQB_SMALL_LIST(X) X(4, 1, 4) X(6, 4, 4) X(8, 3, 4) X(12, 4, 2)
+
+/* The persistent kernel needs the fused stage path, no sharding, every tree of the forest the same shape (so that
+ * tree t owns the descriptors [t cnt_l, (t+1) cnt_l) of depth l and node / x- / u-space ranges of equal length)
+ * and small trees.  TREEQP_B200_SMALL=0 switches it off, =1 takes it whatever the size of the trees. */
+static int detect_small_path(tqb_device *D, const int *h_int, const int *ghost)
+{
+    const tqb_dims *d = &D->dims;
+    D->small = 0;
+    if (!D->fast || !D->fast_stage || ghost) return 0;
+    const char *env = getenv("TREEQP_B200_SMALL");
+    if (env && env[0] == '0') return 0;
+    const bool force = env && env[0] == '1';
+    const int nT = d->nT, Nh = d->Nh;
+    if (nT <= 0 || d->Nn % nT || d->Np % nT || Nh > TQB_SMALL_MAXH) return 0;
+    const int nodes = d->Nn / nT;
+    if (!force && nodes > TQB_SMALL_MAX_NODES) return 0;
+    tqb_tables T;
+    tqb_layout_tables(d, const_cast<int *>(h_int), &T);
+    SmallPlan &pl = D->small_plan;
+    memset(&pl, 0, sizeof pl);
+    int maxcnt = 1;
+    for (int l = 0; l < Nh; l++)
+    {
+        const int begin = D->lvl_ptr[l], tot = D->lvl_ptr[l + 1] - begin;
+        if (tot <= 0 || tot % nT || tot / nT > 32767) return 0;
+        const int cnt = tot / nT;
+        for (int e = 0; e < tot; e++)
+            if (T.tree[T.lvl_nodes[begin + e]] != e / cnt) return 0;
+        pl.lvl_begin[l] = begin; pl.lvl_cnt[l] = (short) cnt;
+        pl.lvl_md[l] = (signed char) D->lvl_md[l]; pl.lvl_kp[l] = (signed char) D->lvl_kp[l];
+        if (cnt > maxcnt) maxcnt = cnt;
+    }
+    for (int t = 0; t < nT; t++)
+        if (T.tnode0[t] != t * nodes) return 0;
+    if (D->nleaf % nT) return 0;
+    pl.Nh = Nh; pl.nroots_total = nT; pl.nleaf = D->nleaf / nT; pl.nodes = nodes;
+    pl.pnx = D->f_pnx;
+    pl.xlen = D->f_pnx + (nodes - 1) * D->f_nx;
+    pl.ulen = (d->Np / nT) * D->f_nu;
+    if ((long long) pl.xlen * nT != d->X || (long long) pl.ulen * nT != d->U) return 0;
+    {   /* leaves of tree t at [t nleaf, (t+1) nleaf) of the leaf records (node order) */
+        int seen = 0;
+        for (int g = 0; g < d->Nn; g++)
+            if (T.nkids[g] == 0) { if (T.tree[g] != seen / pl.nleaf) return 0; seen++; }
+    }
+    int mdmax = 0, smw = 0;
+#define X(a, b, c) if (D->f_nx == a && D->f_nu == b) { mdmax = c; smw = small_smem_warp<a, b, c>(); }
+    TQB_SMALL_LIST(X)
+#undef X
+    if (!mdmax) return 0;
+    for (int l = 0; l < Nh; l++) if (D->lvl_md[l] > mdmax) return 0;
+    pl.smem_warp = smw;
+    /* warps per CTA: four for a batch (four CTAs per SM), up to 16 for a few trees (a level of a single tree is
+     * spread over the warps of its CTA) */
+    int nw = 4;
+    if (nT < 2 * D->n_sm_all)
+    {
+        const int lpw = 32 / tqb_pow2_ge(D->f_nx), lgrp = (pl.nleaf + lpw - 1) / lpw;
+        const int want = maxcnt > lgrp ? maxcnt : lgrp;
+        nw = want <= 4 ? 4 : want <= 8 ? 8 : 16; /* the reductions need a divisor of TQB_SMALL_VL / 32 */
+    }
+    const char *ew = getenv("TREEQP_B200_SMALL_WARPS");
+    if (ew && (atoi(ew) == 4 || atoi(ew) == 8 || atoi(ew) == 16)) nw = atoi(ew);
+    D->small_warps = nw;
+    D->small_smem = (size_t) nw * smw * sizeof(double);
+    D->small_mdmax = mdmax;
+#define X(a, b, c) if (D->f_nx == a && D->f_nu == b) CK(cudaFuncSetAttribute(k_tdunes_small<a, b, c>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->small_smem));
+    TQB_SMALL_LIST(X)
+#undef X
+    D->small = 1;
+    return 0;
+}
+
+static int launch_small(tqb_device *D)
+{
+    const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_SMALL; }
+    int done = 0;
+#define X(a, b, c) if (D->f_nx == a && D->f_nu == b) { k_tdunes_small<a, b, c><<<D->dims.nT, 32 * D->small_warps, D->small_smem, D->stream>>>(D->v, D->small_plan); done = 1; }
+    TQB_SMALL_LIST(X)
+#undef X
+    if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
+    D->launches++;
+    CK(cudaGetLastError());
+    return done ? 0 : 1;
+}
+
 /* stage QPs of every node: compile-time-dimension kernel on uniform trees, generic otherwise */
 template <int MODE>
 static int launch_stage(tqb_device *D, int cls)
@@ -639,6 +753,7 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
         D->n_sm_all = sms;
     }
     if (detect_fast_path(D, h_int, ghost)) return 1;
+    if (detect_small_path(D, h_int, ghost)) return 1;
     if (!D->chain_link)
     {   /* trees on the runtime-dimension kernels walk their chain segments in one launch as well */
         tqb_tables Th;
@@ -960,6 +1075,11 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     /* Host round trips: ONE per Newton iteration (after the first line-search batch).  The
      * termination counter is fetched asynchronously and everything behind the termination test is
      * enqueued at once: kernels of a finished tree return at their status check. */
+    if (D->small && !D->comm)
+    {   /* small trees: the Newton loop of every tree runs inside one persistent CTA */
+        if (launch_small(D)) { snprintf(g_err, sizeof g_err, "small-tree dispatch failed"); return 1; }
+    }
+    else
     for (int it = 0; it < o->maxIter; it++)
     {
         CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
