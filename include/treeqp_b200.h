@@ -638,6 +638,10 @@ const char *treeqp_b200_kernel_class_name(int k);
 
 /* library / device introspection */
 const char *treeqp_b200_version(void);
+/* solver contexts (device arena + pinned staging) alive in this process.  The reference API has create but no
+ * destroy: a create over caller memory that already carries a workspace releases that workspace's context first,
+ * treeqp_*_destroy releases it explicitly. */
+int treeqp_b200_live_contexts(void);
 int treeqp_b200_device_count(void);
 int treeqp_b200_set_device(int device);
 

@@ -83,3 +83,22 @@ def test_no_gpu_fails_loudly(product_lib):
     solver = capi.Tdunes(product_lib, qp_in)
     solver.set_dual_initialization(np.zeros(prob.n_lambda))
     assert solver.solve(qp_out) == capi.TREEQP_UNKNOWN_ERROR
+
+
+def test_recreate_on_same_memory_does_not_leak_contexts(product_lib):
+    """The reference API has create but no destroy: a caller that re-creates its workspace over the same memory
+    (the benchmark harnesses do, once per QP) must not accumulate device arenas (registry.c).  Without a GPU the
+    context still exists (it then holds no arena), so the bookkeeping is testable here."""
+    import ctypes as C
+    from treeqp_b200 import problems as P
+    L = product_lib.lib
+    L.treeqp_b200_live_contexts.restype = C.c_int
+    prob = P.spring_mass(3, 2, 10)
+    qp_in = capi.QpIn(product_lib, prob)
+    s = capi.Tdunes(product_lib, qp_in)
+    n0 = L.treeqp_b200_live_contexts()
+    for _ in range(5):   # the reference's call sequence, again and again on the same work / memory
+        L.treeqp_tdunes_create(qp_in.ptr, C.byref(s.opts), s.work.ptr, s.work_mem.ptr)
+    assert L.treeqp_b200_live_contexts() == n0
+    s.destroy()
+    assert L.treeqp_b200_live_contexts() == n0 - 1

@@ -35,7 +35,7 @@ def set_path(monkeypatch, path):
 PATHS = ["fast", "small", "generic"]
 # uniform trees: the persistent kernel must be what ran (k_init + the kernel + copy-out: a handful of launches)
 UNIFORM = {"spring_mass_cfg1", "spring_mass_tight", "spring_mass_cfg2tree", "random_d6_u05", "random_d10_u02", "random_d8_u05",
-           "random_ternary_chain", "linear_chain_cfg4", "linear_chain_cfg4_s7", "quadcopter_cfg5", "crane_cfg5"}
+           "linear_chain_cfg4", "linear_chain_cfg4_s7", "quadcopter_cfg5", "crane_cfg5"}
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -273,3 +273,32 @@ def test_large_tree_matches_reference_golden(product_lib):
         assert CS.rel_err(s[k + "_sample"], g[k + "_sample"]) < TOL, k
         assert abs(s[k + "_sum"] - float(g[k + "_sum"])) <= 1e-9 * max(1.0, abs(float(g[k + "_sum"]))), k
     assert sol.kkt < 1e-8
+
+
+def test_strided_dma_upload_matches_staged_upload(product_lib, monkeypatch):
+    """Large single trees: once the caller's tree_qp_in buffer is page-locked (second time it is seen, or at once
+    with TREEQP_B200_PIN=1) the [A | B] blocks travel as one strided DMA copy and are transposed on the device
+    (tqb_device_upload_ab_direct).  Same bits as the host-packed upload, also after the caller refills the buffer."""
+    prob = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=8, ubound=0.3)
+    monkeypatch.setenv("TREEQP_B200_PIN", "0")
+    ref = capi.solve_tdunes(product_lib, prob, maxIter=200)
+    assert ref.status == 0
+    monkeypatch.setenv("TREEQP_B200_PIN", "2")
+    qp_in, qp_out = capi.QpIn(product_lib, prob), capi.QpOut(product_lib, prob)
+    solver = capi.Tdunes(product_lib, qp_in, maxIter=200)
+    for rep in range(3):   # 1st: staged (range seen once), 2nd: registers and takes the DMA path, 3rd: DMA path again
+        solver.set_dual_initialization(np.zeros(prob.n_lambda))
+        assert solver.solve(qp_out) == 0
+        assert qp_out.iter == ref.iter
+        for k in ("x", "u", "lam", "mu_x", "mu_u"):
+            assert np.array_equal(getattr(qp_out, k), getattr(ref, k)), (rep, k)
+    # new data in the same (now page-locked) buffer
+    prob2 = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=9, ubound=0.3)
+    monkeypatch.setenv("TREEQP_B200_PIN", "0")
+    ref2 = capi.solve_tdunes(product_lib, prob2, maxIter=200)
+    monkeypatch.setenv("TREEQP_B200_PIN", "2")
+    qp_in.set_data(prob2)
+    solver.set_dual_initialization(np.zeros(prob.n_lambda))
+    assert solver.solve(qp_out) == 0
+    assert qp_out.iter == ref2.iter and np.array_equal(qp_out.x, ref2.x) and np.array_equal(qp_out.lam, ref2.lam)
+    solver.destroy()

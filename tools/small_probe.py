@@ -26,7 +26,7 @@ def timed(prob, small, opts, warps=None):
     qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
     s = capi.Tdunes(lib, qp_in, **opts)
     s.set_dual_initialization(np.zeros(prob.n_lambda))
-    assert s.upload() == 0
+    assert s.upload() == capi.TREEQP_OK
     best, wall = 1e9, 1e9
     for r in range(args.reps):
         t0 = time.perf_counter(); st = s.solve_resident(); w = time.perf_counter() - t0

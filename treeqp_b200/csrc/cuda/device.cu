@@ -101,6 +101,8 @@ struct tqb_device
     double *d_send, *d_recv, *d_tred;
     const tqb_p2p_dev *p2p; /* peer mailboxes over NVLink; NULL: NCCL collectives */
     /* small trees: the whole Newton loop in one persistent kernel, one CTA per tree (tdunes_small.cuh) */
+    char *d_abstage;          /* staging of the strided [A | B] DMA copy (tqb_device_upload_ab_direct) */
+    size_t abstage_bytes;
     int small, small_warps, small_mdmax;
     size_t small_smem;
     SmallPlan small_plan;
@@ -547,7 +549,11 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
 
 /* ---- small trees: one persistent CTA per tree (tdunes_small.cuh) ------------------------------ */
 #ifndef TQB_SMALL_MAX_NODES
-#define TQB_SMALL_MAX_NODES 1024 /* nodes per tree up to which the one-CTA-per-tree kernel is taken */
+/* Measured (tools/small_probe.py, profiles/r02_small_probe.txt): the persistent kernel wins on a single tiny tree
+ * (85 nodes, nx = 4: 58 iterations in 5.6 instead of 9.7 ms), is level with the level-synchronous driver around
+ * 175 nodes and loses beyond (its per-level cost is one block latency, while the level kernels of a batch or of a
+ * wide tree keep every SM busy): it is the default for ONE tree of at most this many nodes only. */
+#define TQB_SMALL_MAX_NODES 100
 #endif
 template <int NX, int NU, int MD>
 struct SmallSm
@@ -582,7 +588,7 @@ static int detect_small_path(tqb_device *D, const int *h_int, const int *ghost)
     const int nT = d->nT, Nh = d->Nh;
     if (nT <= 0 || d->Nn % nT || d->Np % nT || Nh > TQB_SMALL_MAXH) return 0;
     const int nodes = d->Nn / nT;
-    if (!force && nodes > TQB_SMALL_MAX_NODES) return 0;
+    if (!force && (nodes > TQB_SMALL_MAX_NODES || nT > 1)) return 0;
     tqb_tables T;
     tqb_layout_tables(d, const_cast<int *>(h_int), &T);
     SmallPlan &pl = D->small_plan;
@@ -817,6 +823,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
     cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); cudaFree(D->d_leaf_desc); free(D->lvl_md); free(D->lvl_kp); free(D->chain_link);
+    cudaFree(D->d_abstage);
     cudaFree(D->d_cut_nodes); cudaFree(D->d_send); cudaFree(D->d_recv); cudaFree(D->d_tred);
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
@@ -859,6 +866,110 @@ extern "C" int tqb_device_upload_end(tqb_device *D, double *ms_total)
     float t = 0.f;
     CK(cudaEventElapsedTime(&t, D->ev0, D->ev1));
     if (ms_total) *ms_total = t;
+    return 0;
+}
+
+/* ---- caller-owned host memory as a DMA source ------------------------------------------------------------
+ * cudaHostRegister costs tens of milliseconds for a few hundred MB, so a range is page-locked the second time
+ * it is offered (a caller that solves once never pays; an MPC loop that refills the same tree_qp_in pays once) */
+#define TQB_PIN_SLOTS 8
+static struct { const char *lo, *hi; int seen, pinned; } g_pin[TQB_PIN_SLOTS];
+static int g_pin_mode = -1; /* 0 never, 1 at first sight, 2 at second sight */
+
+extern "C" int tqb_host_pin(const void *base, size_t bytes)
+{
+    {   /* read on every call (cheap next to an upload): tests switch it inside one process */
+        const char *e = getenv("TREEQP_B200_PIN");
+        g_pin_mode = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
+    }
+    if (g_pin_mode == 0 || bytes == 0) return 0;
+    /* whole pages: registration is per page anyway, and neighbouring ranges of one buffer then share a slot */
+    const uintptr_t pg = 4096;
+    const char *lo = (const char *) ((uintptr_t) base & ~(pg - 1)), *hi = (const char *) (((uintptr_t) base + bytes + pg - 1) & ~(pg - 1));
+    int slot = -1, freeslot = -1;
+    for (int i = 0; i < TQB_PIN_SLOTS; i++)
+    {
+        if (g_pin[i].lo == NULL) { if (freeslot < 0) freeslot = i; continue; }
+        if (g_pin[i].pinned && lo >= g_pin[i].lo && hi <= g_pin[i].hi) return 1;
+        if (g_pin[i].lo == lo && g_pin[i].hi == hi) slot = i;
+    }
+    if (slot < 0)
+    {   /* new range: drop registrations it overlaps (the caller has re-allocated), then remember it */
+        for (int i = 0; i < TQB_PIN_SLOTS; i++)
+            if (g_pin[i].lo && lo < g_pin[i].hi && hi > g_pin[i].lo)
+            {
+                if (g_pin[i].pinned) cudaHostUnregister((void *) g_pin[i].lo);
+                g_pin[i].lo = g_pin[i].hi = NULL; g_pin[i].pinned = g_pin[i].seen = 0;
+                if (freeslot < 0) freeslot = i;
+            }
+        if (freeslot < 0)
+        {   /* table full: recycle slot 0 */
+            if (g_pin[0].pinned) cudaHostUnregister((void *) g_pin[0].lo);
+            freeslot = 0;
+        }
+        slot = freeslot;
+        g_pin[slot].lo = lo; g_pin[slot].hi = hi; g_pin[slot].seen = 0; g_pin[slot].pinned = 0;
+    }
+    g_pin[slot].seen++;
+    if (g_pin[slot].seen < g_pin_mode) return 0;
+    cudaError_t e = cudaHostRegister((void *) lo, (size_t) (hi - lo), cudaHostRegisterDefault);
+    if (e == cudaErrorHostMemoryAlreadyRegistered) { cudaGetLastError(); g_pin[slot].pinned = 1; return 1; }
+    if (e != cudaSuccess)
+    {   /* not fatal: the staged path remains; do not try this range again */
+        cudaGetLastError();
+        g_pin[slot].seen = -(1 << 30);
+        return 0;
+    }
+    g_pin[slot].pinned = 1;
+    return 1;
+}
+
+extern "C" void tqb_host_unpin_all(void)
+{
+    for (int i = 0; i < TQB_PIN_SLOTS; i++)
+    {
+        if (g_pin[i].pinned) cudaHostUnregister((void *) g_pin[i].lo);
+        g_pin[i].lo = g_pin[i].hi = NULL; g_pin[i].pinned = g_pin[i].seen = 0;
+    }
+}
+
+/* BLASFEO panel-major (4-row panels, cn columns per panel row) -> column-major, one warp per node */
+__global__ void __launch_bounds__(256) k_unpack_ab(View v, const char *stage, long long width, int rows, int g_first,
+                                                   int ma, int na, int cna, int mb, int nb, int cnb, long long b_off)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= rows) return;
+    const int g = g_first + w;
+    const double *sa = reinterpret_cast<const double *>(stage + (size_t) w * width);
+    const double *sb = reinterpret_cast<const double *>(stage + (size_t) w * width + b_off);
+    double *A = v.in.A + v.T.aoff[g], *B = v.in.B + v.T.boff[g];
+    for (int e = lane; e < ma * na; e += 32)
+    {
+        const int j = e / ma, i = e - j * ma;
+        A[e] = sa[(size_t) (i >> 2) * 4 * cna + 4 * j + (i & 3)];
+    }
+    for (int e = lane; e < mb * nb; e += 32)
+    {
+        const int j = e / mb, i = e - j * mb;
+        B[e] = sb[(size_t) (i >> 2) * 4 * cnb + 4 * j + (i & 3)];
+    }
+}
+
+extern "C" int tqb_device_upload_ab_direct(tqb_device *D, const void *src, long long pitch, long long width, int rows, int g_first,
+                                           int ma, int na, int cna, int mb, int nb, int cnb, long long b_off)
+{
+    const size_t need = (size_t) width * (size_t) rows;
+    if (need > D->abstage_bytes)
+    {
+        cudaFree(D->d_abstage);
+        D->d_abstage = NULL; D->abstage_bytes = 0;
+        CK(cudaMalloc(&D->d_abstage, need));
+        D->abstage_bytes = need;
+    }
+    CK(cudaMemcpy2DAsync(D->d_abstage, (size_t) width, src, (size_t) pitch, (size_t) width, (size_t) rows, cudaMemcpyHostToDevice, D->stream));
+    k_unpack_ab<<<(rows + 7) / 8, 256, 0, D->stream>>>(D->v, D->d_abstage, width, rows, g_first, ma, na, cna, mb, nb, cnb, b_off);
+    CK(cudaGetLastError());
     return 0;
 }
 

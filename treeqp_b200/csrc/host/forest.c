@@ -11,6 +11,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <limits.h>
 #include <string.h>
 #include <time.h>
 
@@ -164,7 +165,10 @@ tqb_forest *tqb_forest_create_ex(int nT, const tree_qp_in *const *qps, const int
             }
         }
     }
-    if (X > 2000000000LL || szA > 2000000000LL || szW > 2000000000LL || szB > 2000000000LL || szH > 2000000000LL)
+    /* every offset table holds 32-bit element offsets, and so does the table block's own size */
+    const long long n_int_ll = 19LL * d->Nn + (Np > 0 ? Np : 1) + 2LL * (nT + 1) + 7LL * nchunk;
+    if (X > 2000000000LL || U > 2000000000LL || szA > 2000000000LL || szW > 2000000000LL || szB > 2000000000LL ||
+        szH > 2000000000LL || szUt > 2000000000LL || szCg > 2000000000LL || n_int_ll > 2000000000LL)
     {
         fprintf(stderr, "[treeqp_b200] problem too large for 32-bit element offsets\n");
         free(f);
@@ -342,6 +346,7 @@ static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gm
     const tqb_tables *T = &f->ht;
     tqb_inputs *in = &f->hin;
     int g0 = T->tnode0[t];
+    const int ab_from = f->ab_direct_from > 0 ? f->ab_direct_from : INT_MAX; /* these A / B travel by strided DMA */
     assert(gmap || T->tnode0[t + 1] - g0 == qp->N);
 #pragma omp parallel for schedule(static) if (j1 - j0 > 2048)
     for (int j = j0; j < j1; j++)
@@ -351,8 +356,11 @@ static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gm
         assert(nx == T->nx[g] && nu == T->nu[g]);
         if (k > 0)
         {
-            unpack_dmat(&qp->A[k - 1], in->A + T->aoff[g]);
-            unpack_dmat(&qp->B[k - 1], in->B + T->boff[g]);
+            if (k < ab_from)
+            {
+                unpack_dmat(&qp->A[k - 1], in->A + T->aoff[g]);
+                unpack_dmat(&qp->B[k - 1], in->B + T->boff[g]);
+            }
             memcpy(in->b + xo, qp->b[k - 1].pa, sizeof(double) * (size_t) nx);
         }
         else
@@ -439,8 +447,16 @@ static int upload_nodes(tqb_forest *f, int ga, int gb, int with_lam0)
     const long long x0 = T->xoff[ga], x1 = last ? d->X : T->xoff[gb];
     const long long u0 = T->uoff[ga], u1 = last ? d->U : T->uoff[gb];
     int rc = 0;
-    rc |= tqb_device_upload_range(f->dev, f->h_in, (in->A - f->h_in) + a0, a1 - a0);
-    rc |= tqb_device_upload_range(f->dev, f->h_in, (in->B - f->h_in) + b0, b1 - b0);
+    {   /* A / B of the nodes below ab_direct_from only (the others went by strided DMA) */
+        long long a1h = a1, b1h = b1;
+        if (f->ab_direct_from > 0 && f->ab_direct_from < gb)
+        {
+            const int ge = f->ab_direct_from > ga ? f->ab_direct_from : ga;
+            a1h = T->aoff[ge]; b1h = T->boff[ge];
+        }
+        if (a1h > a0) rc |= tqb_device_upload_range(f->dev, f->h_in, (in->A - f->h_in) + a0, a1h - a0);
+        if (b1h > b0) rc |= tqb_device_upload_range(f->dev, f->h_in, (in->B - f->h_in) + b0, b1h - b0);
+    }
     const double *xs[] = {in->b, in->q, in->Qd, in->Qinv, in->xmin, in->xmax, with_lam0 ? in->lam0 : NULL, in->dxmin, in->dxmax};
     const double *us[] = {in->r, in->Rd, in->Rinv, in->umin, in->umax, in->dumin, in->dumax};
     for (unsigned i = 0; i < sizeof xs / sizeof xs[0]; i++)
@@ -461,6 +477,7 @@ static int upload_nodes(tqb_forest *f, int ga, int gb, int with_lam0)
 int tqb_forest_update_nodes(tqb_forest *f, int t, const tree_qp_in *qp, int j0, int j1)
 {
     const int g0 = f->ht.tnode0[t];
+    f->ab_direct_from = 0; /* a partial update re-sends everything of its nodes through the staging buffer */
     pack_range(f, t, qp, NULL, j0, j1);
     int rc = tqb_device_upload_begin(f->dev);
     rc |= upload_nodes(f, g0 + j0, g0 + j1, 0);
@@ -492,6 +509,7 @@ int tqb_forest_update_x0_batch(tqb_forest *f, const tree_qp_in *const *qp, long 
         for (int j = 0; j <= n0 && uniform && j < N0; j++)
             uniform = T->xoff[g + j] - T->xoff[g] == T->xoff[j] && T->uoff[g + j] - T->uoff[g] == T->uoff[j];
     }
+    f->ab_direct_from = 0;
 #pragma omp parallel for schedule(static) if (nT > 32)
     for (int t = 0; t < nT; t++) pack_range(f, t, qp[t], NULL, 0, 1 + qp[t]->tree[0].nkids);
     int rc = tqb_device_upload_begin(f->dev);
@@ -559,6 +577,44 @@ int tqb_forest_pack_upload_mapped(tqb_forest *f, const tree_qp_in *full_qp, cons
     return pack_upload_impl(f, one, gmap, tail_ms);
 }
 
+/* Large single trees: the [A_k | B_k] blocks of the caller's tree_qp_in sit at a constant stride (tree_qp_in_create
+ * carves A, B, Q, R, S, ... node by node), so once the caller's buffer is page-locked they can travel as ONE
+ * strided DMA copy, panel-major as they are, and be transposed on the device -- two thirds of the input bytes skip
+ * the host packer and the pinned staging buffer.  Returns the first node of the run that was sent (0: none). */
+#ifndef TQB_AB_DIRECT_MIN_NODES
+#define TQB_AB_DIRECT_MIN_NODES 4096
+#endif
+static int upload_ab_direct(tqb_forest *f, const tree_qp_in *qp)
+{
+    const int N = qp->N;
+    if (N < TQB_AB_DIRECT_MIN_NODES) return 0;
+    /* the run is the tail of the node order: every node from k0 on has the dimensions and the stride of the last one */
+    const struct blasfeo_dmat *A = qp->A, *B = qp->B;
+    const int last = N - 2; /* index into A / B of node N-1 */
+    const long long pitch = (const char *) A[last].pA - (const char *) A[last - 1].pA;
+    const long long b_off = (const char *) B[last].pA - (const char *) A[last].pA;
+    const long long a_bytes = (long long) sizeof(double) * A[last].pm * A[last].cn, b_bytes = (long long) sizeof(double) * B[last].pm * B[last].cn;
+    if (pitch <= 0 || b_off < a_bytes || b_off + b_bytes > pitch || (pitch & 7) || (b_off & 7)) return 0;
+    int i0 = last;
+    while (i0 > 0)
+    {
+        const int i = i0 - 1;
+        if (A[i].m != A[last].m || A[i].n != A[last].n || A[i].cn != A[last].cn || A[i].pm != A[last].pm ||
+            B[i].m != B[last].m || B[i].n != B[last].n || B[i].cn != B[last].cn || B[i].pm != B[last].pm ||
+            (const char *) A[i + 1].pA - (const char *) A[i].pA != pitch || (const char *) B[i].pA - (const char *) A[i].pA != b_off)
+            break;
+        i0 = i;
+    }
+    const int k0 = i0 + 1, rows = N - k0;
+    if (rows < TQB_AB_DIRECT_MIN_NODES) return 0;
+    const long long width = b_off + b_bytes;
+    if (!tqb_host_pin(A[i0].pA, (size_t) (pitch * (rows - 1) + width))) return 0;
+    if (tqb_device_upload_ab_direct(f->dev, A[i0].pA, pitch, width, rows, f->ht.tnode0[0] + k0, A[last].m, A[last].n, A[last].cn,
+                                    B[last].m, B[last].n, B[last].cn, b_off))
+        return 0;
+    return k0;
+}
+
 static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const int *gmap, double *tail_ms)
 {
     const tqb_tables *T = &f->ht;
@@ -568,6 +624,8 @@ static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const in
     if (nstage < 1) nstage = 1;
     if (nstage > 32) nstage = 32;
     int rc = tqb_device_upload_begin(f->dev);
+    f->ab_direct_from = 0;
+    if (nT == 1 && !gmap) f->ab_direct_from = upload_ab_direct(f, qp[0]);
     if (nT == 1)
     {
         const int N = T->tnode0[1];

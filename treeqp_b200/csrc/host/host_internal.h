@@ -111,7 +111,13 @@ typedef struct tqb_forest
     int kernel_count[16];
     double comm_ms;          /* sharded solves: device time spent in collectives */
     int n_collectives;
+    int ab_direct_from;      /* nodes from here on had their A / B sent by the strided DMA path in the last upload (0: none) */
 } tqb_forest;
+
+/* ---- registry.c: contexts by the caller's workspace memory (a re-create on the same ptr frees the old arena) ---- */
+void tqb_registry_replace(const void *key, void *ctx, void (*dtor)(void *));
+void tqb_registry_remove(const void *ctx);
+int tqb_registry_size(void);
 
 /* ---- forest.c ---- */
 struct tree_qp_in_;
@@ -158,6 +164,16 @@ int tqb_device_upload_end(tqb_device *d, double *ms_total);
 /* `rows` slices of `width` doubles at stride `pitch` starting at offset `off` of the input block */
 int tqb_device_upload_2d(tqb_device *d, const double *h_in, long long off, long long pitch, long long width, int rows);
 int tqb_device_warm_start(tqb_device *d, long long lam0_off, long long n);
+/* Caller-owned host memory [base, base + bytes) as a DMA source: returns 1 when the range is page-locked
+ * (cudaHostRegister; a range is registered the SECOND time it is seen, or at once with TREEQP_B200_PIN=1, never with
+ * TREEQP_B200_PIN=0), 0 when it is not (the caller takes the staged path). */
+int tqb_host_pin(const void *base, size_t bytes);
+void tqb_host_unpin_all(void);
+/* `rows` nodes from node g_first on: their BLASFEO panel-major [A | B] blocks (each `width` bytes, `pitch` bytes
+ * apart in the caller's page-locked buffer, B `b_off` bytes after A) travel as ONE strided DMA copy into a device
+ * staging area and are turned into the column-major A / B arrays by a kernel (k_unpack_ab) */
+int tqb_device_upload_ab_direct(tqb_device *d, const void *src, long long pitch, long long width, int rows, int g_first,
+                                int ma, int na, int cna, int mb, int nb, int cnb, long long b_off);
 int tqb_device_kkt(tqb_device *d, double *h_kkt);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
 int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,

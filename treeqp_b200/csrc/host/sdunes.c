@@ -197,7 +197,7 @@ static tqb_sd_ctx *sd_ctx_of(const treeqp_sdunes_workspace *work)
 
 static void sd_ctx_free(tqb_sd_ctx *ctx)
 {
-    if (!ctx) return;
+    if (!ctx || ctx->magic != TQB_SD_MAGIC) return;
     if (ctx->dev) tqb_sd_device_destroy(ctx->dev);
     if (ctx->h_in) tqb_pinned_free(ctx->h_in);
     if (ctx->h_out) tqb_pinned_free(ctx->h_out);
@@ -344,6 +344,8 @@ void treeqp_sdunes_create(tree_qp_in *qp_in, treeqp_sdunes_opts_t *opts, treeqp_
         fprintf(stderr, "[treeqp_b200] treeqp_sdunes_create: no device arena (%s); solve will return "
                         "TREEQP_UNKNOWN_ERROR\n", tqb_cuda_last_error());
     ctx->dual_dirty = 1;
+    /* no destroy in the reference API: a re-create over the same caller memory releases the previous arena */
+    tqb_registry_replace(ptr, ctx, (void (*)(void *)) sd_ctx_free);
 
     /* views over the pinned output block: valid after every solve (what solve_qp_json.cpp reads) */
     for (int i = 0; i < Ns; i++)
@@ -369,6 +371,7 @@ void treeqp_sdunes_destroy(treeqp_sdunes_workspace *work)
 {
     tqb_sd_ctx *ctx = sd_ctx_of(work);
     if (!ctx) return;
+    tqb_registry_remove(ctx);
     sd_ctx_free(ctx);
     work->sTmpMats = NULL;
 }

@@ -50,6 +50,7 @@ int tqb_verbose(void)
 }
 
 const char *treeqp_b200_version(void) { return "treeqp_b200 0.1 (sm_100a)"; }
+int treeqp_b200_live_contexts(void) { return tqb_registry_size(); }
 int treeqp_b200_device_count(void) { return tqb_cuda_device_count(); }
 int treeqp_b200_set_device(int device) { return tqb_cuda_set_device(device); }
 void treeqp_b200_set_profiling(int on) { tqb_set_profiling(on); }
@@ -121,7 +122,7 @@ static int host_bytes(int Nn, int Nh)
     b += 2LL * Nn * sizeof(double);            /* fval, cmod */
     b += (long long) Nn * sizeof(void *);      /* stage_qp_data */
     b = (b + 63) / 64 * 64 + 3 * 64;
-    return (int) b;
+    return b > 2147483647LL ? -1 : (int) b; /* the reference's int return type cannot hold more (callers check <= 0) */
 }
 
 int treeqp_tdunes_calculate_size(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts)
@@ -159,6 +160,8 @@ static void check_stage_solvers(const tree_qp_in *qp_in, const treeqp_tdunes_opt
         }
     }
 }
+
+static void ctx_free(void *p);
 
 void treeqp_tdunes_create(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts,
                           treeqp_tdunes_workspace *work, void *ptr)
@@ -212,6 +215,9 @@ void treeqp_tdunes_create(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *o
     }
     ctx->lam_dirty = 1;
     work->stage_qp_data[0] = ctx;
+    /* the reference API has no destroy: a re-create over the same caller memory releases the arena of the
+     * workspace that lived there (registry.c) */
+    tqb_registry_replace(ptr, ctx, ctx_free);
 }
 
 static tqb_ctx *ctx_of(const treeqp_tdunes_workspace *work)
@@ -222,13 +228,21 @@ static tqb_ctx *ctx_of(const treeqp_tdunes_workspace *work)
     return ctx;
 }
 
+static void ctx_free(void *p)
+{
+    tqb_ctx *ctx = (tqb_ctx *) p;
+    if (!ctx || ctx->magic != TQB_MAGIC) return;
+    tqb_forest_destroy(ctx->forest);
+    ctx->magic = 0;
+    free(ctx);
+}
+
 void treeqp_tdunes_destroy(treeqp_tdunes_workspace *work)
 {
     tqb_ctx *ctx = ctx_of(work);
     if (!ctx) return;
-    tqb_forest_destroy(ctx->forest);
-    ctx->magic = 0;
-    free(ctx);
+    tqb_registry_remove(ctx);
+    ctx_free(ctx);
     work->stage_qp_data[0] = NULL;
 }
 
