@@ -601,6 +601,9 @@ def bench_mpc(lib, steps=20):
 def run_single(lib, args, prob, barrier, max_over_ranks, clocks, rank):
     """N = 1 headline (and, at N > 1, the replica line: every rank solves its own copy of the tree)"""
     qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+    # the caller's tree_qp_in / tree_qp_out buffers are page-locked once (treeqp_b200_host_register, the one line
+    # INTEGRATION.md asks of an MPC loop): e2e copies then run by DMA straight from / into them
+    pinned = bool(qp_in.pin() and qp_out.pin()) if os.environ.get("TREEQP_B200_BENCH_UNPINNED", "0") != "1" else False
     solver = capi.Tdunes(lib, qp_in, **OPTS)
     lam0 = np.zeros(prob.n_lambda)
     solver.set_dual_initialization(lam0)
@@ -646,8 +649,19 @@ def run_single(lib, args, prob, barrier, max_over_ranks, clocks, rank):
     prof["serialised"] = solver.stats()["kernels"]
     lib.lib.treeqp_b200_set_profiling(0)
     sol = out_dict(qp_out, st2)
+    # the same call with the buffers NOT page-locked (every byte through the host packer and the library's own pinned
+    # staging block): reported next to the headline e2e
+    t_unp = None
+    if pinned:
+        qp_in.mem.unpin(); qp_out.mem.unpin()
+        solver.set_dual_initialization(lam0); solver.solve(qp_out)
+        t0 = time.perf_counter()
+        for _ in range(max(2, args.steps // 4)):
+            solver.set_dual_initialization(lam0)
+            solver.solve(qp_out)
+        t_unp = (time.perf_counter() - t0) / max(2, args.steps // 4)
     solver.destroy()
-    return dict(t_res=t_res, t_e2e=t_e2e, dev_ms=dev_ms, stats=stats, e2e_stats=e2e_stats, prof=prof, sol=sol,
+    return dict(t_res=t_res, t_e2e=t_e2e, dev_ms=dev_ms, stats=stats, e2e_stats=e2e_stats, prof=prof, sol=sol, pinned=pinned, t_e2e_unpinned=t_unp,
                 kkt=kkt, kkt_dev=kkt_dev, clk=(clk_lo, clk_hi), launches=stats["kernel_launches"] * args.steps)
 
 
@@ -902,7 +916,10 @@ def main():
         "device_ms_per_step": R["dev_ms"] / args.steps,
         "e2e": {"value": args.steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": es["h2d_bytes"],
                 "d2h_bytes_per_step": es["d2h_bytes"], "ms_per_step": 1e3 * t_e2e / args.steps,
-                "pack_ms": es["pack_ms"], "h2d_ms": es["h2d_ms"], "d2h_ms": es["d2h_ms"], "gpu_ms": es["gpu_ms"]},
+                "pack_ms": es["pack_ms"], "h2d_ms": es["h2d_ms"], "d2h_ms": es["d2h_ms"], "gpu_ms": es["gpu_ms"],
+                "host_buffers": ("caller's tree_qp_in / tree_qp_out page-locked once with treeqp_b200_host_register: DMA straight from / into them"
+                                 if R.get("pinned") else "pageable: every byte through the host packer and the library's pinned staging block"),
+                "ms_per_step_unpinned_buffers": (1e3 * R["t_e2e_unpinned"] if R.get("t_e2e_unpinned") else None)},
         "gpu_launches": int(R["launches"]), "clocks": clk, "parity": parity, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "other_workloads": extra,
     }

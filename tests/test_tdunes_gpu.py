@@ -275,30 +275,58 @@ def test_large_tree_matches_reference_golden(product_lib):
     assert sol.kkt < 1e-8
 
 
-def test_strided_dma_upload_matches_staged_upload(product_lib, monkeypatch):
-    """Large single trees: once the caller's tree_qp_in buffer is page-locked (second time it is seen, or at once
-    with TREEQP_B200_PIN=1) the [A | B] blocks travel as one strided DMA copy and are transposed on the device
-    (tqb_device_upload_ab_direct).  Same bits as the host-packed upload, also after the caller refills the buffer."""
+def test_dma_from_registered_caller_buffers_matches_staged_path(product_lib):
+    """Large single trees with caller buffers page-locked through treeqp_b200_host_register: A, B and the vectors of
+    tree_qp_in travel as strided DMA copies in the caller's layout and are converted on the device (k_unpack_run), the
+    results are assembled on the device in tree_qp_out's layout and written in place (k_gather_run).  Same bits as the
+    staged path (host packer + pinned block), also after the caller refills the buffer."""
     prob = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=8, ubound=0.3)
-    monkeypatch.setenv("TREEQP_B200_PIN", "0")
-    ref = capi.solve_tdunes(product_lib, prob, maxIter=200)
+    ref = capi.solve_tdunes(product_lib, prob, maxIter=200)          # staged path
     assert ref.status == 0
-    monkeypatch.setenv("TREEQP_B200_PIN", "2")
+    prob2 = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=9, ubound=0.3)
+    ref2 = capi.solve_tdunes(product_lib, prob2, maxIter=200)
     qp_in, qp_out = capi.QpIn(product_lib, prob), capi.QpOut(product_lib, prob)
+    assert qp_in.pin() and qp_out.pin()
     solver = capi.Tdunes(product_lib, qp_in, maxIter=200)
-    for rep in range(3):   # 1st: staged (range seen once), 2nd: registers and takes the DMA path, 3rd: DMA path again
+    for rep in range(2):
         solver.set_dual_initialization(np.zeros(prob.n_lambda))
         assert solver.solve(qp_out) == 0
         assert qp_out.iter == ref.iter
         for k in ("x", "u", "lam", "mu_x", "mu_u"):
             assert np.array_equal(getattr(qp_out, k), getattr(ref, k)), (rep, k)
-    # new data in the same (now page-locked) buffer
-    prob2 = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=9, ubound=0.3)
-    monkeypatch.setenv("TREEQP_B200_PIN", "0")
-    ref2 = capi.solve_tdunes(product_lib, prob2, maxIter=200)
-    monkeypatch.setenv("TREEQP_B200_PIN", "2")
-    qp_in.set_data(prob2)
+        # the DMA path moves the caller's rows (padding included), the staged path the packed arrays: the byte counts tell them apart
+        assert solver.stats()["h2d_bytes"] != ref.stats["h2d_bytes"], "the DMA path did not run"
+    qp_in.set_data(prob2)   # new data in the same (page-locked) buffer
     solver.set_dual_initialization(np.zeros(prob.n_lambda))
     assert solver.solve(qp_out) == 0
-    assert qp_out.iter == ref2.iter and np.array_equal(qp_out.x, ref2.x) and np.array_equal(qp_out.lam, ref2.lam)
+    assert qp_out.iter == ref2.iter
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        assert np.array_equal(getattr(qp_out, k), getattr(ref2, k)), ("refilled", k)
     solver.destroy()
+    qp_in.mem.unpin(); qp_out.mem.unpin()
+    # unregistered again: the staged path, same results
+    solver = capi.Tdunes(product_lib, qp_in, maxIter=200)
+    solver.set_dual_initialization(np.zeros(prob.n_lambda))
+    assert solver.solve(qp_out) == 0 and np.array_equal(qp_out.x, ref2.x)
+    assert solver.stats()["h2d_bytes"] == ref2.stats["h2d_bytes"]
+    solver.destroy()
+
+
+@pytest.mark.parametrize("reg", [dict(), dict(regType=1), dict(regType=2, regTol=0.5, regValue=1e-2)])
+def test_reuse_of_unchanged_blocks_is_bit_identical(reg, product_lib, monkeypatch):
+    """Wide levels re-use the factorisation of blocks whose subtree kept its active set (the GPU form of
+    checkLastActiveSet, bf_block_reuse in tdunes_fused.cuh): only the right-hand side is redone.  Against
+    TREEQP_B200_NO_SKIP=1 (every block re-factored in every iteration): the same bits everywhere, the same
+    per-iteration line-search trial counts, the same count of regularised blocks (a large regTol makes the
+    on-the-fly regularisation fire, so that re-used regularised factors are counted too)."""
+    prob = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=5, ubound=0.2)
+    monkeypatch.setenv("TREEQP_B200_NO_SKIP", "1")
+    a = capi.solve_tdunes(product_lib, prob, maxIter=200, **reg)
+    monkeypatch.setenv("TREEQP_B200_NO_SKIP", "0")
+    b = capi.solve_tdunes(product_lib, prob, maxIter=200, **reg)
+    assert (a.status, a.iter) == (b.status, b.iter)
+    assert a.stats["ls_iters"] == b.stats["ls_iters"]
+    assert a.stats["n_reg"] == b.stats["n_reg"]
+    if reg.get("regType") == 2: assert a.stats["n_reg"] > 0
+    for k in ("x", "u", "lam", "mu_x", "mu_u"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k

@@ -244,6 +244,11 @@ class TreeQpLib:
         L.calculate_number_of_nodes.restype = C.c_int
         if self.is_product:
             L.treeqp_b200_version.restype = C.c_char_p
+            L.treeqp_b200_host_register.argtypes = [vp, C.c_size_t]
+            L.treeqp_b200_host_register.restype = C.c_int
+            L.treeqp_b200_host_unregister.argtypes = [vp]
+            L.treeqp_b200_host_unregister.restype = C.c_int
+            L.treeqp_b200_live_contexts.restype = C.c_int
             L.treeqp_b200_device_count.restype = C.c_int
             L.treeqp_b200_set_device.argtypes = [C.c_int]
             L.treeqp_b200_set_device.restype = C.c_int
@@ -356,12 +361,33 @@ class _Buf:
     """64-byte aligned host buffer (the caller-owned memory of the reference's protocol)."""
 
     def __init__(self, nbytes: int):
-        self.raw = np.zeros(nbytes + 64, dtype=np.uint8)
-        off = (-self.raw.ctypes.data) % 64
-        self.arr = self.raw[off:off + nbytes]
+        # large buffers: page-aligned, whole pages (so that treeqp_b200_host_register can lock all of it)
+        align = 4096 if nbytes >= (1 << 20) else 64
+        size = (nbytes + align - 1) // align * align
+        self.raw = np.zeros(size + align, dtype=np.uint8)
+        off = (-self.raw.ctypes.data) % align
+        self.arr = self.raw[off:off + size]
         self.ptr = C.c_void_p(self.arr.ctypes.data)
         self.addr = self.arr.ctypes.data
         self.nbytes = nbytes
+        self._pinned_by = None
+
+    def pin(self, lib) -> bool:
+        """page-lock this buffer for DMA (treeqp_b200_host_register); undone when the buffer dies"""
+        if self._pinned_by is None and lib.is_product and lib.lib.treeqp_b200_host_register(self.ptr, C.c_size_t(self.arr.size)) == 0:
+            self._pinned_by = lib
+        return self._pinned_by is not None
+
+    def unpin(self):
+        if self._pinned_by is not None:
+            self._pinned_by.lib.treeqp_b200_host_unregister(self.ptr)
+            self._pinned_by = None
+
+    def __del__(self):
+        try:
+            self.unpin()
+        except Exception:
+            pass
 
 
 class QpIn:
@@ -381,6 +407,10 @@ class QpIn:
         L.tree_qp_in_create(Nn, _ip(self.nx), _ip(self.nu), ncp, _ip(self.nk), self.struct.ptr, self.mem.ptr)
         self.ptr = self.struct.ptr
         self.set_data(prob)
+
+    def pin(self) -> bool:
+        """page-lock the tree_qp_in memory: large trees then upload by DMA straight from it"""
+        return self.mem.pin(self.lib)
 
     def set_data(self, prob: Problem):
         L = self.lib.lib
@@ -437,6 +467,10 @@ class QpOut:
         L.tree_qp_out_create(prob.Nn, _ip(nx), _ip(nu), ncp, self.struct_buf.ptr, self.mem.ptr)
         self.ptr = self.struct_buf.ptr
         self.s = QpOutStruct.from_address(self.struct_buf.addr)
+
+    def pin(self) -> bool:
+        """page-lock the tree_qp_out memory: large trees then download by DMA straight into it"""
+        return self.mem.pin(self.lib)
 
     def _gather(self, field_ptr, count) -> np.ndarray:
         """Concatenate `count` blasfeo_dvec views starting at field_ptr (all live in self.mem)."""

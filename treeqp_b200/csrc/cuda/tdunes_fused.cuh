@@ -573,8 +573,145 @@ struct BlockedCfg
     static constexpr int SMEM = SM_M + 2 * D + 4;     /* Ms | ys (D) | spare */
 };
 
+/* 16-byte asynchronous copies global -> shared (LDGSTS): the factor of an unchanged block is staged under its loads */
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned) __cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+/* Re-use of unchanged blocks -- the GPU form of the reference's checkLastActiveSet (dual_Newton_tree.c:334-371, 563,
+ * 703).  The reference skips the re-factorisation of the SUFFIX of the parent numbering behind the last changed active
+ * set; measured on config 3 that suffix is 0.2 % of the blocks for most iterations, while 94-100 % of ALL blocks have an
+ * unchanged subtree from the third Newton iteration on (profiles/r02_active_set_change_config3.txt).  A block whose
+ * own, kids' and descendants' active sets did not move has the W_p, L_p, Utilde_p and Schur complement of the last
+ * iteration bit for bit (same inputs, same operations): only the right-hand side is redone -- the gradient res, the
+ * termination norm, y = L^-1 (res - s_kids) with L from HBM (staged by cp.async under the gradient's loads), and
+ * s_p = Utilde y -- with the operations of the full path in the same order, so the iterates do not change by a bit.
+ * `try_skip` (wide levels only): returns true when the block was handled here; false: the caller runs the full path
+ * (`waited` tells it whether the programmatic-launch wait has been done). */
 template <int NX, int NU, int MD, int PNX, bool ROOT>
-__device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids_are_parents, bool wait_here, double *Ms, int lane)
+__device__ __forceinline__ bool bf_block_reuse(const View &v, const int4 d0, const int4 d1, const int4 d2, int kids_are_parents,
+                                               bool wait_here, bool &waited, double *Ms, int lane)
+{
+    using Cfg = BlockedCfg<NX, NU, MD, PNX, ROOT>;
+    constexpr int D = Cfg::D, NCOL = Cfg::NCOL, TR = Cfg::TR, KS = Cfg::KS;
+    constexpr int NL = D * (D + 1) / 2;          /* packed L */
+    constexpr int LDU = D + 2;                   /* staged Utilde rows: even (16-byte copies), spreads the NX reader lanes over the banks */
+    constexpr int OFFU = (NL + 1) & ~1;
+    static_assert(!ROOT, "roots always take the full path");
+    static_assert((D & 1) == 0 && OFFU + NX * LDU <= Cfg::SM_M, "staging must fit the block's shared memory");
+    const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
+    /* Everything is requested at once, before the flags are looked at: the flags of the node and its kids
+     * (k_stage_fused<0> finished before this sweep started), last iteration's factor (written by this block one sweep
+     * ago, nobody touches it in between), and the gradient's operands.  A changed block (a few per cent) wastes the
+     * staging copies. */
+    const int c_own = (lane == 0) ? v.chg[g] : (lane <= MD ? v.chg[k0 + lane - 1] : 0);
+    double *sL = Ms, *sU = Ms + OFFU, *ys = Ms + Cfg::SM_M;
+    {
+        const double *Lg = v.W + d1.w, *Up = v.Ut + d2.x;
+        for (int e = lane; e < (NL + 1) / 2; e += 32) cp_async16(sL + 2 * e, Lg + 2 * e); /* odd NL: one double of the next block rides along */
+        for (int e = lane; e < NX * D / 2; e += 32)
+        {
+            const int a = (2 * e) / D, j = 2 * e - a * D;
+            cp_async16(sU + a * LDU + j, Up + 2 * e);
+        }
+    }
+    const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
+    const bool isW = lane < D;
+    const int gid = lane >> 2, tig = lane & 3;
+    const double inv = isW ? v.Linv[xb + lane] : 0.0;
+    double res = 0.0;
+    {   /* gradient: exactly the tile column of the full path (C z on the tensor cores, k ascending) */
+        double zf[KS], af[TR][KS];
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++)
+        {
+            const int cc = 4 * ks + tig;
+            zf[ks] = 0.0;
+            if (cc < NCOL) zf[ks] = cc < PNX ? v.x[xo + cc] : v.u[uo + cc - PNX];
+        }
+#pragma unroll
+        for (int i = 0; i < TR; i++)
+        {
+            const int r = 8 * i + gid, kr = r / NX, ir = r - kr * NX;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++)
+            {
+                const int cc = 4 * ks + tig;
+                double val = 0.0;
+                if (r < D && cc < NCOL) val = cc < PNX ? Ag[kr * NX * PNX + ir + cc * NX] : Bg[kr * NX * NU + ir + (cc - PNX) * NX];
+                af[i][ks] = val;
+            }
+        }
+        if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
+        if (__any_sync(FULL, c_own != 0))
+        {   /* own or a kid's active set moved: full path (its loads now hit L1) */
+            cp_async_commit_wait_all();
+            __syncwarp();
+            return false;
+        }
+#pragma unroll
+        for (int i = 0; i < TR; i++)
+        {
+            const int r = 8 * i + gid;
+            double sg = 0.0, sg1 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) dmma884(sg, sg1, af[i][ks], gid == 0 ? zf[ks] : 0.0);
+            if (tig == 0 && r < D) ys[r] = sg;
+        }
+        __syncwarp();
+        if (isW) res += ys[lane];
+    }
+    if (wait_here) { pdl_wait(); pdl_release(); }
+    waited = true;
+    /* a kid whose block was re-factored in this sweep hands up a new Schur complement: full path */
+    const int c_kid = (kids_are_parents && lane < MD) ? v.bdirty[k0 + lane] : 0;
+    double rr = res - ((kids_are_parents && isW) ? v.rsub[xb + lane] : 0.0);
+    cp_async_commit_wait_all();
+    if (__any_sync(FULL, c_kid != 0)) { __syncwarp(); return false; }
+    if (isW) v.res[xb + lane] = res;
+    {
+        double part = (v.o.termCondition == 2) ? fabs(res) : res * res;
+        part = (v.o.termCondition == 2) ? warp_max(part) : warp_sum(part);
+        if (lane == 0)
+        {
+            v.nva[g] = part;
+            v.bdirty[g] = 0;
+            if (v.breg[g]) atomicAdd(&v.counters[2], 1); /* the re-used factor is a regularised one: counted as the full path would */
+        }
+    }
+    __syncwarp(); /* staged factor visible to the whole warp */
+    double lrow[D - 1];
+#pragma unroll
+    for (int j = 0; j < D - 1; j++) lrow[j] = (isW && j < lane) ? sL[(lane * (lane + 1)) / 2 + j] : 0.0;
+    double my_y = 0.0;
+#pragma unroll
+    for (int J = 0; J < D; J++)
+    {   /* forward substitution, column by column as the factorisation does it on the fly */
+        const double yj = __shfl_sync(FULL, rr, J) * __shfl_sync(FULL, inv, J);
+        if (J < D - 1) rr = fma(-lrow[J], yj, rr);
+        if (lane == J) my_y = yj;
+    }
+    if (isW) { ys[lane] = my_y; v.dlam[xb + lane] = my_y; }
+    __syncwarp();
+    for (int a = lane; a < NX; a += 32)
+    {   /* s = Utilde y */
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) s += sU[a * LDU + j] * ys[j];
+        v.rsub[xo + a] = s;
+    }
+    __syncwarp(); /* Ms is the next block's */
+    return true;
+}
+
+template <int NX, int NU, int MD, int PNX, bool ROOT>
+__device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids_are_parents, bool wait_here, double *Ms, int lane,
+                                            bool try_skip = false)
 {
     using Cfg = BlockedCfg<NX, NU, MD, PNX, ROOT>;
     constexpr int D = Cfg::D, NCOL = Cfg::NCOL, RT = Cfg::RT, NP = Cfg::NP, NA = Cfg::NA, NB = Cfg::NB, LDM = Cfg::LDM;
@@ -589,6 +726,15 @@ __device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids
         return;
     }
     BF_STAMP(1);
+    if constexpr (!ROOT)
+    {
+        if (try_skip)
+        {
+            bool waited = false;
+            if (bf_block_reuse<NX, NU, MD, PNX, ROOT>(v, d0, d1, d2, kids_are_parents, wait_here, waited, Ms, lane)) return;
+            if (waited) wait_here = false;
+        }
+    }
     double *ys = Ms + Cfg::SM_M;                  /* C z, later y = L^-1 resMod */
     const double *Ag = v.in.A + d1.y, *Bg = v.in.B + d1.z;
     const bool isW = lane < D;
@@ -780,7 +926,11 @@ __device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids
             }
         }
         BF_STAMP(5);
-        if (!(v.o.regType == 2 && attempt == 0 && small)) break;
+        if (!(v.o.regType == 2 && attempt == 0 && small))
+        {
+            if (lane == 0 && v.bdirty) { v.bdirty[g] = 1; v.breg[g] = attempt; }
+            break;
+        }
         if (lane == 0) atomicAdd(&v.counters[2], 1);
         __syncwarp();
     }
@@ -865,7 +1015,7 @@ struct BfSel
 };
 
 template <int NX, int NU, int MD, int PNX, bool ROOT>
-__global__ void __launch_bounds__(128, tqb_bf_minblocks(NX * MD)) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents, int pre_ok)
+__global__ void __launch_bounds__(128, tqb_bf_minblocks(NX * MD)) k_build_factor(View v, int lvl_begin, int count, int kids_are_parents, int pre_ok, int try_skip)
 {
     using Sel = BfSel<NX, NU, MD, PNX, ROOT>;
     extern __shared__ double smem[];
@@ -877,7 +1027,7 @@ __global__ void __launch_bounds__(128, tqb_bf_minblocks(NX * MD)) k_build_factor
     if (!pre_ok) { pdl_wait(); pdl_release(); }
     if (w >= count) { pdl_wait(); pdl_release(); return; }
     if constexpr (Sel::BLOCKED)
-        bf_block_lb<NX, NU, MD, PNX, ROOT>(v, (size_t) (lvl_begin + w), kids_are_parents, true, smem + (size_t) wib * Sel::SMEM, lane);
+        bf_block_lb<NX, NU, MD, PNX, ROOT>(v, (size_t) (lvl_begin + w), kids_are_parents, true, smem + (size_t) wib * Sel::SMEM, lane, try_skip != 0);
     else
         bf_block<NX, NU, MD, PNX, ROOT>(v, (size_t) (lvl_begin + w), kids_are_parents, true, smem + (size_t) wib * Sel::SMEM, lane);
 }

@@ -42,6 +42,10 @@ struct View
     const int *leaf_desc; /* fast path: LeafDesc records (tdunes_stage.cuh), one per leaf in node order */
     const int *lvl_desc;  /* fast path: LvlDesc records (tdunes_fused.cuh), one per parent in level order */
     double *schur, *rsub; /* fast path: per-node Schur complement (NX x NX) and its rhs part (x-space) */
+    /* fast path, re-use of unchanged blocks (the GPU form of checkLastActiveSet, dual_Newton_tree.c:334-371): per node,
+     * chg = the node's own active set differs from the last Newton iteration (k_stage_fused<0>), bdirty = its block
+     * was re-factored in this iteration (k_build_factor), breg = its last factorisation was regularised on the fly */
+    int *chg, *bdirty, *breg;
     double *nva, *nvb, *cva, *cvb; /* per-node and per-chunk reduction scratch */
     /* per tree */
     int *status, *iter, *ls_cnt, *ls_active, *restart_cnt;
@@ -75,6 +79,13 @@ __global__ void k_init(View v)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < v.X) v.lam[i] = v.in.lam0[i];
     if (i < v.Nn) v.nva[i] = 0.0; /* leaves never write their slot of the termination norm */
+    if (v.chg)
+    {   /* no active set yet: the first comparison of k_stage_fused<0> reports a change everywhere (P, Rt >= 0 later on),
+         * and kernels that never clear a flag leave their nodes marked for ever */
+        if (i < v.X) v.P[i] = -1.0;
+        if (i < v.U) v.Rt[i] = -1.0;
+        if (i < v.Nn) { v.chg[i] = 1; v.bdirty[i] = 1; v.breg[i] = 0; }
+    }
     if (v.has_dense)
     {   /* empty working sets (QProblemB_init is a cold start, qpoases.c:286) */
         if (i < v.X) v.P[i] = 0.0;

@@ -48,7 +48,7 @@ __device__ __forceinline__ void stage_parent(const View &v, const int4 d0, const
     /* inputs of the epilogue first (independent of everything below) */
     const bool own = lane < ncol, isx = lane < pnx;
     const int i = isx ? lane : lane - pnx;
-    double base = 0.0, winv = 0.0, lo = 0.0, hi = 0.0, rs = 0.0;
+    double base = 0.0, winv = 0.0, lo = 0.0, hi = 0.0, rs = 0.0, pold = 0.0;
     if (own)
     {
         if (isx)
@@ -59,12 +59,14 @@ __device__ __forceinline__ void stage_parent(const View &v, const int4 d0, const
             {
                 base = -v.in.q[xo + i] + l;
                 winv = v.in.Qinv[xo + i]; lo = v.in.xmin[xo + i]; hi = v.in.xmax[xo + i];
+                if (MODE == 0) pold = v.P[xo + i];
             }
         }
         else if (MODE != 2)
         {
             base = -v.in.r[uo + i];
             winv = v.in.Rinv[uo + i]; lo = v.in.umin[uo + i]; hi = v.in.umax[uo + i];
+            if (MODE == 0) pold = v.Rt[uo + i];
         }
     }
     /* the kids' multipliers (one contiguous range) and cmod = sum_kids b_j' lambda_j (:892) */
@@ -115,6 +117,7 @@ __device__ __forceinline__ void stage_parent(const View &v, const int4 d0, const
         if (p < npair) kid = load_col(p);
     }
     __syncwarp();
+    bool changed = false;
     if (own)
     {
         double acc = base;
@@ -128,17 +131,25 @@ __device__ __forceinline__ void stage_parent(const View &v, const int4 d0, const
             int mask;
             const double unc = winv * acc;
             const double val = clip_mask(unc, lo, hi, mask);
+            const double pnew = mask == 0 ? winv : 0.0;
+            changed = pnew != pold;
             if (isx)
             {
                 v.x[xo + i] = val;
-                if (MODE == 0) { v.qmod0[xo + i] = acc; v.xUnc[xo + i] = unc; v.P[xo + i] = mask == 0 ? winv : 0.0; }
+                if (MODE == 0) { v.qmod0[xo + i] = acc; v.xUnc[xo + i] = unc; v.P[xo + i] = pnew; }
             }
             else
             {
                 v.u[uo + i] = val;
-                if (MODE == 0) { v.rmod0[uo + i] = acc; v.uUnc[uo + i] = unc; v.Rt[uo + i] = mask == 0 ? winv : 0.0; }
+                if (MODE == 0) { v.rmod0[uo + i] = acc; v.uUnc[uo + i] = unc; v.Rt[uo + i] = pnew; }
             }
         }
+    }
+    if (MODE == 0)
+    {   /* did the active set of this node move since the last Newton iteration? (k_build_factor re-uses the
+         * factorisation of blocks whose whole subtree did not) */
+        const bool any = __any_sync(FULL, changed);
+        if (lane == 0 && v.chg) v.chg[g] = any;
     }
     if (MODE == 2)
     {   /* node's part of res'*dlam */
@@ -267,6 +278,7 @@ __device__ __forceinline__ void stage_leaves(const View &v, const int4 ld, bool 
     const double *src = (MODE == 2) ? v.dlam : v.lam;
     double part = 0.0;
     int g = -1;
+    bool changed = false;
     if (valid)
     {
         if (v.status[ld.z] == TQB_RUNNING) g = ld.x;
@@ -281,13 +293,26 @@ __device__ __forceinline__ void stage_leaves(const View &v, const int4 ld, bool 
             }
             else
             {
-                const double acc = -v.in.q[e] + l, winv = v.in.Qinv[e];
+                const double pold = (MODE == 0) ? v.P[e] : 0.0; /* with the other inputs: a load behind the stores would be a second round trip */
+                const double acc = -v.in.q[e] + l, winv = v.in.Qinv[e], lo = v.in.xmin[e], hi = v.in.xmax[e];
                 const double unc = winv * acc;
                 int mask;
-                v.x[e] = clip_mask(unc, v.in.xmin[e], v.in.xmax[e], mask);
-                if (MODE == 0) { v.qmod0[e] = acc; v.xUnc[e] = unc; v.P[e] = mask == 0 ? winv : 0.0; }
+                v.x[e] = clip_mask(unc, lo, hi, mask);
+                if (MODE == 0)
+                {
+                    const double pnew = mask == 0 ? winv : 0.0;
+                    changed = pnew != pold;
+                    v.qmod0[e] = acc; v.xUnc[e] = unc; v.P[e] = pnew;
+                }
             }
         }
+    }
+    if (MODE == 0)
+    {   /* per leaf (NXP lanes): any bound entered or left the active set */
+        const unsigned b = __ballot_sync(FULL, changed);
+        const int lane = threadIdx.x & 31, first = lane & ~(NXP - 1);
+        const unsigned grp = NXP == 32 ? 0xffffffffu : (((1u << NXP) - 1u) << first);
+        if (g >= 0 && i == 0 && v.chg) v.chg[g] = (b & grp) != 0;
     }
     if (MODE == 2)
     {   /* segmented butterfly: the same additions as a full-warp sum padded with zeros */

@@ -340,13 +340,20 @@ static void unpack_dmat(const struct blasfeo_dmat *M, double *dst)
     }
 }
 
+static inline int node_in_run(const tqb_forest *f, int k)
+{
+    for (int r = 0; r < f->n_in_runs; r++)
+        if (k >= f->in_runs[r].k0 && k < f->in_runs[r].k1) return 1;
+    return 0;
+}
+
 /* gmap == NULL: tree t of the forest is qp itself; otherwise local node j is node gmap[j] of qp */
 static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gmap, int j0, int j1)
 {
     const tqb_tables *T = &f->ht;
     tqb_inputs *in = &f->hin;
     int g0 = T->tnode0[t];
-    const int ab_from = f->ab_direct_from > 0 ? f->ab_direct_from : INT_MAX; /* these A / B travel by strided DMA */
+    const int direct = f->in_direct && !gmap; /* nodes inside a run: only the weights are packed here, the rest travels by strided DMA */
     assert(gmap || T->tnode0[t + 1] - g0 == qp->N);
 #pragma omp parallel for schedule(static) if (j1 - j0 > 2048)
     for (int j = j0; j < j1; j++)
@@ -354,13 +361,26 @@ static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gm
         const int k = gmap ? gmap[j] : j;
         int g = g0 + j, nx = qp->nx[k], nu = qp->nu[k], xo = T->xoff[g], uo = T->uoff[g];
         assert(nx == T->nx[g] && nu == T->nu[g]);
+        if (direct && node_in_run(f, k))
+        {   /* clipping node of a DMA run: diagonal weights and their reciprocals only */
+            for (int i = 0; i < nx; i++)
+            {
+                double w = BLASFEO_DMATEL(&qp->Q[k], i, i);
+                in->Qd[xo + i] = w;
+                in->Qinv[xo + i] = 1.0 / w;
+            }
+            for (int i = 0; i < nu; i++)
+            {
+                double w = BLASFEO_DMATEL(&qp->R[k], i, i);
+                in->Rd[uo + i] = w;
+                in->Rinv[uo + i] = 1.0 / w;
+            }
+            continue;
+        }
         if (k > 0)
         {
-            if (k < ab_from)
-            {
-                unpack_dmat(&qp->A[k - 1], in->A + T->aoff[g]);
-                unpack_dmat(&qp->B[k - 1], in->B + T->boff[g]);
-            }
+            unpack_dmat(&qp->A[k - 1], in->A + T->aoff[g]);
+            unpack_dmat(&qp->B[k - 1], in->B + T->boff[g]);
             memcpy(in->b + xo, qp->b[k - 1].pa, sizeof(double) * (size_t) nx);
         }
         else
@@ -442,27 +462,42 @@ static int upload_nodes(tqb_forest *f, int ga, int gb, int with_lam0)
     const tqb_dims *d = &f->dims;
     const tqb_inputs *in = &f->hin;
     const int last = gb >= d->Nn;
-    const long long a0 = T->aoff[ga], a1 = last ? d->szA : T->aoff[gb];
-    const long long b0 = T->boff[ga], b1 = last ? d->szB : T->boff[gb];
     const long long x0 = T->xoff[ga], x1 = last ? d->X : T->xoff[gb];
     const long long u0 = T->uoff[ga], u1 = last ? d->U : T->uoff[gb];
     int rc = 0;
-    {   /* A / B of the nodes below ab_direct_from only (the others went by strided DMA) */
-        long long a1h = a1, b1h = b1;
-        if (f->ab_direct_from > 0 && f->ab_direct_from < gb)
+    /* weights, their reciprocals, the dual start (and the dense nodes' bounds) always come from the staging block */
+    const double *xs_all[] = {in->Qd, in->Qinv, with_lam0 ? in->lam0 : NULL, in->dxmin, in->dxmax};
+    const double *us_all[] = {in->Rd, in->Rinv, in->dumin, in->dumax};
+    for (unsigned i = 0; i < sizeof xs_all / sizeof xs_all[0]; i++)
+        if (xs_all[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (xs_all[i] - f->h_in) + x0, x1 - x0);
+    for (unsigned i = 0; i < sizeof us_all / sizeof us_all[0]; i++)
+        if (us_all[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (us_all[i] - f->h_in) + u0, u1 - u0);
+    /* A, B and the vectors: only for the nodes of [ga, gb) outside the DMA runs */
+    const double *xs[] = {in->b, in->q, in->xmin, in->xmax};
+    const double *us[] = {in->r, in->umin, in->umax};
+    int s0 = ga;
+    for (int r = 0; r <= (f->in_direct ? f->n_in_runs : 0) && s0 < gb; r++)
+    {
+        /* host segment [s0, s1): up to the next run that starts at or after s0 (runs are sorted; single tree: g = k) */
+        int s1 = gb, next = gb;
+        if (f->in_direct && r < f->n_in_runs)
         {
-            const int ge = f->ab_direct_from > ga ? f->ab_direct_from : ga;
-            a1h = T->aoff[ge]; b1h = T->boff[ge];
+            const int r0 = f->in_runs[r].k0 + T->tnode0[0], r1 = f->in_runs[r].k1 + T->tnode0[0];
+            if (r1 <= s0) continue;
+            if (r0 < gb) { s1 = r0 > s0 ? r0 : s0; next = r1; }
         }
-        if (a1h > a0) rc |= tqb_device_upload_range(f->dev, f->h_in, (in->A - f->h_in) + a0, a1h - a0);
-        if (b1h > b0) rc |= tqb_device_upload_range(f->dev, f->h_in, (in->B - f->h_in) + b0, b1h - b0);
+        if (s1 > s0)
+        {
+            const int l1 = s1 >= d->Nn;
+            const long long ha0 = T->aoff[s0], ha1 = l1 ? d->szA : T->aoff[s1], hb0 = T->boff[s0], hb1 = l1 ? d->szB : T->boff[s1];
+            const long long hx0 = T->xoff[s0], hx1 = l1 ? d->X : T->xoff[s1], hu0 = T->uoff[s0], hu1 = l1 ? d->U : T->uoff[s1];
+            rc |= tqb_device_upload_range(f->dev, f->h_in, (in->A - f->h_in) + ha0, ha1 - ha0);
+            rc |= tqb_device_upload_range(f->dev, f->h_in, (in->B - f->h_in) + hb0, hb1 - hb0);
+            for (unsigned i = 0; i < sizeof xs / sizeof xs[0]; i++) rc |= tqb_device_upload_range(f->dev, f->h_in, (xs[i] - f->h_in) + hx0, hx1 - hx0);
+            for (unsigned i = 0; i < sizeof us / sizeof us[0]; i++) rc |= tqb_device_upload_range(f->dev, f->h_in, (us[i] - f->h_in) + hu0, hu1 - hu0);
+        }
+        s0 = next;
     }
-    const double *xs[] = {in->b, in->q, in->Qd, in->Qinv, in->xmin, in->xmax, with_lam0 ? in->lam0 : NULL, in->dxmin, in->dxmax};
-    const double *us[] = {in->r, in->Rd, in->Rinv, in->umin, in->umax, in->dumin, in->dumax};
-    for (unsigned i = 0; i < sizeof xs / sizeof xs[0]; i++)
-        if (xs[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (xs[i] - f->h_in) + x0, x1 - x0);
-    for (unsigned i = 0; i < sizeof us / sizeof us[0]; i++)
-        if (us[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (us[i] - f->h_in) + u0, u1 - u0);
     if (d->NC > 0)
     {
         const long long c0 = T->cgoff[ga], c1 = last ? d->szCg : T->cgoff[gb];
@@ -477,7 +512,7 @@ static int upload_nodes(tqb_forest *f, int ga, int gb, int with_lam0)
 int tqb_forest_update_nodes(tqb_forest *f, int t, const tree_qp_in *qp, int j0, int j1)
 {
     const int g0 = f->ht.tnode0[t];
-    f->ab_direct_from = 0; /* a partial update re-sends everything of its nodes through the staging buffer */
+    f->in_direct = 0; /* a partial update re-sends everything of its nodes through the staging buffer */
     pack_range(f, t, qp, NULL, j0, j1);
     int rc = tqb_device_upload_begin(f->dev);
     rc |= upload_nodes(f, g0 + j0, g0 + j1, 0);
@@ -509,7 +544,7 @@ int tqb_forest_update_x0_batch(tqb_forest *f, const tree_qp_in *const *qp, long 
         for (int j = 0; j <= n0 && uniform && j < N0; j++)
             uniform = T->xoff[g + j] - T->xoff[g] == T->xoff[j] && T->uoff[g + j] - T->uoff[g] == T->uoff[j];
     }
-    f->ab_direct_from = 0;
+    f->in_direct = 0;
 #pragma omp parallel for schedule(static) if (nT > 32)
     for (int t = 0; t < nT; t++) pack_range(f, t, qp[t], NULL, 0, 1 + qp[t]->tree[0].nkids);
     int rc = tqb_device_upload_begin(f->dev);
@@ -577,42 +612,104 @@ int tqb_forest_pack_upload_mapped(tqb_forest *f, const tree_qp_in *full_qp, cons
     return pack_upload_impl(f, one, gmap, tail_ms);
 }
 
-/* Large single trees: the [A_k | B_k] blocks of the caller's tree_qp_in sit at a constant stride (tree_qp_in_create
- * carves A, B, Q, R, S, ... node by node), so once the caller's buffer is page-locked they can travel as ONE
- * strided DMA copy, panel-major as they are, and be transposed on the device -- two thirds of the input bytes skip
- * the host packer and the pinned staging buffer.  Returns the first node of the run that was sent (0: none). */
-#ifndef TQB_AB_DIRECT_MIN_NODES
-#define TQB_AB_DIRECT_MIN_NODES 4096
+/* Large single trees: the views of the caller's tree_qp_in sit at constant strides over long runs of nodes (all
+ * parents of one shape, all leaves), so once the caller's buffer is page-locked (tqb_host_pin) A, B and the vectors
+ * travel as strided DMA copies in the caller's layout and are converted on the device: the host packer only forms
+ * the diagonal weights and their reciprocals, and the pinned staging block is by-passed for 90 % of the bytes. */
+#ifndef TQB_DIRECT_MIN_NODES
+#define TQB_DIRECT_MIN_NODES 4096
 #endif
-static int upload_ab_direct(tqb_forest *f, const tree_qp_in *qp)
-{
-    const int N = qp->N;
-    if (N < TQB_AB_DIRECT_MIN_NODES) return 0;
-    /* the run is the tail of the node order: every node from k0 on has the dimensions and the stride of the last one */
+static int in_layout_equal(const tree_qp_in *qp, int k, int r)
+{   /* nodes k and r (both >= 1): same dimensions and same offsets inside their matrix / vector chunks */
     const struct blasfeo_dmat *A = qp->A, *B = qp->B;
-    const int last = N - 2; /* index into A / B of node N-1 */
-    const long long pitch = (const char *) A[last].pA - (const char *) A[last - 1].pA;
-    const long long b_off = (const char *) B[last].pA - (const char *) A[last].pA;
-    const long long a_bytes = (long long) sizeof(double) * A[last].pm * A[last].cn, b_bytes = (long long) sizeof(double) * B[last].pm * B[last].cn;
-    if (pitch <= 0 || b_off < a_bytes || b_off + b_bytes > pitch || (pitch & 7) || (b_off & 7)) return 0;
-    int i0 = last;
-    while (i0 > 0)
+    if (qp->nx[k] != qp->nx[r] || qp->nu[k] != qp->nu[r] || qp->nc[k] != 0) return 0;
+    if (A[k - 1].m != A[r - 1].m || A[k - 1].n != A[r - 1].n || A[k - 1].cn != A[r - 1].cn || A[k - 1].pm != A[r - 1].pm) return 0;
+    if (B[k - 1].m != B[r - 1].m || B[k - 1].n != B[r - 1].n || B[k - 1].cn != B[r - 1].cn || B[k - 1].pm != B[r - 1].pm) return 0;
+    if ((const char *) B[k - 1].pA - (const char *) A[k - 1].pA != (const char *) B[r - 1].pA - (const char *) A[r - 1].pA) return 0;
+    const double *vb = qp->b[k - 1].pa, *vr = qp->b[r - 1].pa;
+    return qp->q[k].pa - vb == qp->q[r].pa - vr && qp->r[k].pa - vb == qp->r[r].pa - vr &&
+           qp->xmin[k].pa - vb == qp->xmin[r].pa - vr && qp->xmax[k].pa - vb == qp->xmax[r].pa - vr &&
+           qp->umin[k].pa - vb == qp->umin[r].pa - vr && qp->umax[k].pa - vb == qp->umax[r].pa - vr;
+}
+
+static void build_in_runs(tqb_forest *f, const tree_qp_in *qp)
+{
+    const void *key[3] = {qp->A, qp->N > 1 ? (const void *) qp->A[0].pA : NULL, qp->b};
+    if (f->in_key[0] == key[0] && f->in_key[1] == key[1] && f->in_key[2] == key[2]) return; /* same views as last time */
+    memcpy(f->in_key, key, sizeof key);
+    f->n_in_runs = 0;
+    const int N = qp->N;
+    for (int k = 1; k + 1 < N && f->n_in_runs < TQB_MAX_RUNS;)
     {
-        const int i = i0 - 1;
-        if (A[i].m != A[last].m || A[i].n != A[last].n || A[i].cn != A[last].cn || A[i].pm != A[last].pm ||
-            B[i].m != B[last].m || B[i].n != B[last].n || B[i].cn != B[last].cn || B[i].pm != B[last].pm ||
-            (const char *) A[i + 1].pA - (const char *) A[i].pA != pitch || (const char *) B[i].pA - (const char *) A[i].pA != b_off)
-            break;
-        i0 = i;
+        const long long mp = (const char *) qp->A[k].pA - (const char *) qp->A[k - 1].pA;
+        const long long vp = (const char *) qp->b[k].pa - (const char *) qp->b[k - 1].pa;
+        int e = k + 1;
+        while (e < N && in_layout_equal(qp, e, k) && (const char *) qp->A[e - 1].pA - (const char *) qp->A[e - 2].pA == mp &&
+               (const char *) qp->b[e - 1].pa - (const char *) qp->b[e - 2].pa == vp)
+            e++;
+        if (e - k >= TQB_DIRECT_MIN_NODES)
+        {
+            tqb_in_run *r = &f->in_runs[f->n_in_runs];
+            const struct blasfeo_dmat *A = &qp->A[k - 1], *B = &qp->B[k - 1];
+            r->k0 = k; r->k1 = e;
+            r->mbase = (const char *) A->pA; r->mpitch = mp;
+            r->b_off = (const char *) B->pA - (const char *) A->pA;
+            r->mwidth = r->b_off + (long long) sizeof(double) * B->pm * B->cn;
+            r->ma = A->m; r->na = A->n; r->cna = A->cn; r->mb = B->m; r->nb = B->n; r->cnb = B->cn;
+            r->nx = qp->nx[k]; r->nu = qp->nu[k];
+            const double *vb = qp->b[k - 1].pa;
+            const double *vs[7] = {vb, qp->q[k].pa, qp->r[k].pa, qp->xmin[k].pa, qp->xmax[k].pa, qp->umin[k].pa, qp->umax[k].pa};
+            const int len[7] = {r->nx, r->nx, r->nu, r->nx, r->nx, r->nu, r->nu};
+            long long lo = 0, hi = 0;
+            for (int i = 0; i < 7; i++)
+            {
+                const long long o = vs[i] - vb;
+                r->voff[i] = (int) o;
+                if (o < lo) lo = o;
+                if (o + len[i] > hi) hi = o + len[i];
+            }
+            r->vbase = (const char *) vb; r->vpitch = vp; r->vwidth = (long long) sizeof(double) * hi;
+            const int ok = lo == 0 && mp > 0 && vp > 0 && r->b_off >= (long long) sizeof(double) * A->pm * A->cn && r->mwidth <= mp &&
+                           r->vwidth <= vp && !(mp & 7) && !(vp & 7) && !(r->b_off & 7);
+            if (ok) f->n_in_runs++;
+        }
+        k = e;
     }
-    const int k0 = i0 + 1, rows = N - k0;
-    if (rows < TQB_AB_DIRECT_MIN_NODES) return 0;
-    const long long width = b_off + b_bytes;
-    if (!tqb_host_pin(A[i0].pA, (size_t) (pitch * (rows - 1) + width))) return 0;
-    if (tqb_device_upload_ab_direct(f->dev, A[i0].pA, pitch, width, rows, f->ht.tnode0[0] + k0, A[last].m, A[last].n, A[last].cn,
-                                    B[last].m, B[last].n, B[last].cn, b_off))
-        return 0;
-    return k0;
+}
+
+/* returns 1 when the runs were sent by DMA (f->in_direct), 0 when the whole tree takes the staged path */
+static int upload_in_runs(tqb_forest *f, const tree_qp_in *qp)
+{
+    f->in_direct = 0;
+    if (qp->N < TQB_DIRECT_MIN_NODES || f->dims.has_dense || f->dims.NC > 0) return 0;
+    build_in_runs(f, qp);
+    if (f->n_in_runs == 0) return 0;
+    /* one page-locked range from the first matrix to the last vector of the runs */
+    const char *lo = NULL, *hi = NULL;
+    size_t stage = 0;
+    for (int i = 0; i < f->n_in_runs; i++)
+    {
+        const tqb_in_run *r = &f->in_runs[i];
+        const long long rows = r->k1 - r->k0;
+        const char *p[4] = {r->mbase, r->mbase + r->mpitch * (rows - 1) + r->mwidth, r->vbase, r->vbase + r->vpitch * (rows - 1) + r->vwidth};
+        for (int j = 0; j < 4; j++)
+        {
+            if (!lo || p[j] < lo) lo = p[j];
+            if (!hi || p[j] > hi) hi = p[j];
+        }
+        stage += (size_t) rows * (size_t) (r->mwidth + r->vwidth);
+    }
+    if (!tqb_host_pin(lo, (size_t) (hi - lo))) return 0;
+    if (tqb_device_stage_reserve(f->dev, stage)) return 0;
+    size_t off = 0;
+    for (int i = 0; i < f->n_in_runs; i++)
+    {
+        const tqb_in_run *r = &f->in_runs[i];
+        if (tqb_device_upload_run(f->dev, r, f->ht.tnode0[0] + r->k0, off)) return 0;
+        off += (size_t) (r->k1 - r->k0) * (size_t) (r->mwidth + r->vwidth);
+    }
+    f->in_direct = 1;
+    return 1;
 }
 
 static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const int *gmap, double *tail_ms)
@@ -624,8 +721,10 @@ static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const in
     if (nstage < 1) nstage = 1;
     if (nstage > 32) nstage = 32;
     int rc = tqb_device_upload_begin(f->dev);
-    f->ab_direct_from = 0;
-    if (nT == 1 && !gmap) f->ab_direct_from = upload_ab_direct(f, qp[0]);
+    f->in_direct = 0;
+    const double tv0 = tqb_wall_ms();
+    if (nT == 1 && !gmap) upload_in_runs(f, qp[0]);
+    const double tv1 = tqb_wall_ms();
     if (nT == 1)
     {
         const int N = T->tnode0[1];
@@ -654,6 +753,9 @@ static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const in
     rc |= tqb_device_upload_end(f->dev, &total);
     if (tail_ms) *tail_ms = tqb_wall_ms() - t0;
     f->h2d_ms = total;
+    if (tqb_verbose())
+        fprintf(stderr, "[treeqp_b200] upload: runs %d (direct %d) enqueue %.3f ms, pack loop %.3f ms, tail %.3f ms, stream %.3f ms\n",
+                f->n_in_runs, f->in_direct, tv1 - tv0, t0 - tv1, tqb_wall_ms() - t0, total);
     return rc;
 }
 
@@ -687,4 +789,124 @@ void tqb_forest_unpack(const tqb_forest *f, int t, tree_qp_out *out)
         if (k > 0) memcpy(out->lam[k - 1].pa, lam + xo, sizeof(double) * (size_t) nx);
         if (T->ncn[g] > 0) memcpy(out->mu_d[k].pa, mud + T->doff[g], sizeof(double) * (size_t) T->ncn[g]);
     }
+}
+
+/* ---- results straight into the caller's tree_qp_out (large single trees) -------------------------------------
+ * tree_qp_out_create carves [x u mu_x mu_u mu_d lam] node by node: runs of nodes of one shape sit at a constant
+ * stride.  With the caller's buffer page-locked the device assembles each run in the caller's layout (k_gather_run)
+ * and ONE strided D2H copy per run writes it in place; only the nodes outside the runs (the root, its children) go
+ * through the pinned block and the host loop. */
+static void build_out_runs(tqb_forest *f, const tree_qp_out *out, int N)
+{
+    const void *key[3] = {out->x, out->x[0].pa, out->lam};
+    if (f->out_key[0] == key[0] && f->out_key[1] == key[1] && f->out_key[2] == key[2]) return;
+    memcpy(f->out_key, key, sizeof key);
+    f->n_out_runs = 0;
+    const tqb_tables *T = &f->ht;
+    const int g0 = T->tnode0[0];
+#define OFFS(k, o) do { const double *b_ = out->x[k].pa; (o)[0] = 0; (o)[1] = out->u[k].pa - b_; (o)[2] = out->mu_x[k].pa - b_; \
+                        (o)[3] = out->mu_u[k].pa - b_; (o)[4] = out->lam[(k) - 1].pa - b_; } while (0)
+    for (int k = 1; k + 1 < N && f->n_out_runs < TQB_MAX_RUNS;)
+    {
+        long long o0[5];
+        OFFS(k, o0);
+        const long long pitch = (const char *) out->x[k + 1].pa - (const char *) out->x[k].pa;
+        int e = k + 1;
+        for (; e < N; e++)
+        {
+            long long o[5];
+            OFFS(e, o);
+            if (T->nx[g0 + e] != T->nx[g0 + k] || T->nu[g0 + e] != T->nu[g0 + k] || T->ncn[g0 + e] != 0 || memcmp(o, o0, sizeof o) ||
+                (const char *) out->x[e].pa - (const char *) out->x[e - 1].pa != pitch)
+                break;
+        }
+        if (e - k >= TQB_DIRECT_MIN_NODES && T->ncn[g0 + k] == 0)
+        {
+            tqb_out_run *r = &f->out_runs[f->n_out_runs];
+            r->k0 = k; r->k1 = e; r->base = (char *) out->x[k].pa; r->pitch = pitch;
+            r->nx = T->nx[g0 + k]; r->nu = T->nu[g0 + k];
+            const int len[5] = {r->nx, r->nu, r->nx, r->nu, r->nx};
+            long long lo = 0, hi = 0;
+            for (int i = 0; i < 5; i++)
+            {
+                r->off[i] = (int) o0[i];
+                if (o0[i] < lo) lo = o0[i];
+                if (o0[i] + len[i] > hi) hi = o0[i] + len[i];
+            }
+            r->width = (long long) sizeof(double) * hi;
+            if (lo == 0 && pitch > 0 && r->width <= pitch && !(pitch & 7)) f->n_out_runs++;
+        }
+        k = e;
+    }
+#undef OFFS
+}
+
+/* returns 1 when qp_out has been filled (runs by DMA, the other nodes through the pinned block), 0: not applicable */
+int tqb_forest_download_direct(tqb_forest *f, tree_qp_out *out)
+{
+    const tqb_tables *T = &f->ht;
+    const tqb_dims *d = &f->dims;
+    if (d->nT != 1 || d->Nn < TQB_DIRECT_MIN_NODES || d->NC > 0) return 0;
+    const int N = d->Nn, g0 = T->tnode0[0];
+    build_out_runs(f, out, N);
+    if (f->n_out_runs == 0) return 0;
+    char *lo = NULL, *hi = NULL;
+    size_t stage = 0;
+    for (int i = 0; i < f->n_out_runs; i++)
+    {
+        const tqb_out_run *r = &f->out_runs[i];
+        const long long rows = r->k1 - r->k0;
+        char *e = r->base + r->pitch * (rows - 1) + r->width;
+        if (!lo || r->base < lo) lo = r->base;
+        if (!hi || e > hi) hi = e;
+        stage += (size_t) rows * (size_t) r->width;
+    }
+    if (!tqb_host_pin(lo, (size_t) (hi - lo))) return 0;
+    if (tqb_device_stage_reserve(f->dev, stage)) return 0;
+    int rc = tqb_device_download_begin(f->dev);
+    size_t off = 0;
+    long long bytes = 0;
+    for (int i = 0; i < f->n_out_runs; i++)
+    {
+        const tqb_out_run *r = &f->out_runs[i];
+        rc |= tqb_device_download_run(f->dev, r, g0 + r->k0, off);
+        off += (size_t) (r->k1 - r->k0) * (size_t) r->width;
+        bytes += (long long) (r->k1 - r->k0) * r->width;
+    }
+    /* nodes outside the runs: their slices of x, u, lam, mu_x, mu_u into the pinned block */
+    int s0 = 0;
+    for (int i = 0; i <= f->n_out_runs; i++)
+    {
+        const int s1 = i < f->n_out_runs ? f->out_runs[i].k0 : N;
+        if (s1 > s0)
+        {
+            const int l1 = g0 + s1 >= d->Nn;
+            const long long x0 = T->xoff[g0 + s0], x1 = l1 ? d->X : T->xoff[g0 + s1], u0 = T->uoff[g0 + s0], u1 = l1 ? d->U : T->uoff[g0 + s1];
+            rc |= tqb_device_download_nodes(f->dev, f->h_out, x0, x1, u0, u1);
+            bytes += (long long) sizeof(double) * (3 * (x1 - x0) + 2 * (u1 - u0));
+        }
+        if (i < f->n_out_runs) s0 = f->out_runs[i].k1;
+    }
+    const double td0 = tqb_wall_ms();
+    rc |= tqb_device_download_end(f->dev, &f->d2h_ms);
+    if (tqb_verbose()) fprintf(stderr, "[treeqp_b200] download: %d runs, wait %.3f ms, stream %.3f ms\n", f->n_out_runs, tqb_wall_ms() - td0, f->d2h_ms);
+    if (rc) return 0;
+    f->d2h_bytes = bytes;
+    const double *x = f->h_out, *u = x + d->X, *lam = u + d->U, *mux = lam + d->X, *muu = mux + d->X;
+    s0 = 0;
+    for (int i = 0; i <= f->n_out_runs; i++)
+    {
+        const int s1 = i < f->n_out_runs ? f->out_runs[i].k0 : N;
+        for (int k = s0; k < s1; k++)
+        {
+            const int g = g0 + k, nx = T->nx[g], nu = T->nu[g], xo = T->xoff[g], uo = T->uoff[g];
+            memcpy(out->x[k].pa, x + xo, sizeof(double) * (size_t) nx);
+            memcpy(out->u[k].pa, u + uo, sizeof(double) * (size_t) nu);
+            memcpy(out->mu_x[k].pa, mux + xo, sizeof(double) * (size_t) nx);
+            memcpy(out->mu_u[k].pa, muu + uo, sizeof(double) * (size_t) nu);
+            if (k > 0) memcpy(out->lam[k - 1].pa, lam + xo, sizeof(double) * (size_t) nx);
+        }
+        if (i < f->n_out_runs) s0 = f->out_runs[i].k1;
+    }
+    return 1;
 }

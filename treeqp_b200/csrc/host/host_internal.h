@@ -91,6 +91,31 @@ typedef struct tqb_opts
 typedef struct tqb_device tqb_device;
 
 /* host-side forest: tables + pinned staging for the inputs and the outputs */
+/* Runs of nodes whose views sit at a constant stride in the caller's tree_qp_in / tree_qp_out (tree_qp_in_create carves
+ * [A B Q R S C D] node by node and then [b q r xmin xmax umin umax dmin dmax] node by node; tree_qp_out_create carves
+ * [x u mu_x mu_u mu_d lam] node by node): once the caller's buffer is page-locked such a run travels as strided DMA
+ * copies, in the caller's layout, and is converted on the device (k_unpack_run / k_gather_run). */
+typedef struct tqb_in_run
+{
+    int k0, k1;                       /* nodes [k0, k1) of the tree, k0 >= 1 */
+    const char *mbase;                /* A of node k0 */
+    long long mpitch, mwidth, b_off;  /* bytes: node to node, A..end of B, A to B */
+    int ma, na, cna, mb, nb, cnb;     /* BLASFEO panel-major views of A and B */
+    const char *vbase;                /* b of node k0 */
+    long long vpitch, vwidth;         /* bytes */
+    int voff[7];                      /* doubles from vbase: b q r xmin xmax umin umax */
+    int nx, nu;
+} tqb_in_run;
+typedef struct tqb_out_run
+{
+    int k0, k1;
+    char *base;                       /* x of node k0 */
+    long long pitch, width;           /* bytes */
+    int off[5];                       /* doubles from base: x u mu_x mu_u lam */
+    int nx, nu;
+} tqb_out_run;
+#define TQB_MAX_RUNS 8
+
 typedef struct tqb_forest
 {
     tqb_dims dims;
@@ -111,7 +136,13 @@ typedef struct tqb_forest
     int kernel_count[16];
     double comm_ms;          /* sharded solves: device time spent in collectives */
     int n_collectives;
-    int ab_direct_from;      /* nodes from here on had their A / B sent by the strided DMA path in the last upload (0: none) */
+    /* strided DMA of the caller's own buffers (large single trees): runs of the last upload / download and what they
+     * were derived from */
+    int n_in_runs, n_out_runs;
+    tqb_in_run in_runs[TQB_MAX_RUNS];
+    tqb_out_run out_runs[TQB_MAX_RUNS];
+    const void *in_key[3], *out_key[3];
+    int in_direct;           /* the last upload used in_runs */
 } tqb_forest;
 
 /* ---- registry.c: contexts by the caller's workspace memory (a re-create on the same ptr frees the old arena) ---- */
@@ -137,6 +168,8 @@ void tqb_forest_pack(tqb_forest *f, int t, const struct tree_qp_in_ *qp);
 int tqb_forest_pack_upload(tqb_forest *f, const struct tree_qp_in_ *const *qp, double *tail_ms);
 /* re-pack and re-send nodes [j0, j1) of tree t only (what an x0 update touches) / the dual start only */
 int tqb_forest_pack_upload_mapped(tqb_forest *f, const struct tree_qp_in_ *full_qp, const int *gmap, double *tail_ms);
+/* results of a large single tree straight into the caller's (page-locked) tree_qp_out; 0 = not applicable */
+int tqb_forest_download_direct(tqb_forest *f, struct tree_qp_out_ *out);
 int tqb_forest_update_nodes(tqb_forest *f, int t, const struct tree_qp_in_ *qp, int j0, int j1);
 int tqb_forest_update_x0_batch(tqb_forest *f, const struct tree_qp_in_ *const *qp, long long *bytes);
 int tqb_forest_upload_lambda0(tqb_forest *f);
@@ -164,16 +197,19 @@ int tqb_device_upload_end(tqb_device *d, double *ms_total);
 /* `rows` slices of `width` doubles at stride `pitch` starting at offset `off` of the input block */
 int tqb_device_upload_2d(tqb_device *d, const double *h_in, long long off, long long pitch, long long width, int rows);
 int tqb_device_warm_start(tqb_device *d, long long lam0_off, long long n);
-/* Caller-owned host memory [base, base + bytes) as a DMA source: returns 1 when the range is page-locked
- * (cudaHostRegister; a range is registered the SECOND time it is seen, or at once with TREEQP_B200_PIN=1, never with
- * TREEQP_B200_PIN=0), 0 when it is not (the caller takes the staged path). */
+/* Caller-owned host memory as a DMA source / target (device.cu): register / unregister by the owner
+ * (treeqp_b200_host_register), tqb_host_pin = "is this range page-locked?" */
+int tqb_host_register(const void *base, size_t bytes);
+int tqb_host_unregister(const void *base);
 int tqb_host_pin(const void *base, size_t bytes);
 void tqb_host_unpin_all(void);
-/* `rows` nodes from node g_first on: their BLASFEO panel-major [A | B] blocks (each `width` bytes, `pitch` bytes
- * apart in the caller's page-locked buffer, B `b_off` bytes after A) travel as ONE strided DMA copy into a device
- * staging area and are turned into the column-major A / B arrays by a kernel (k_unpack_ab) */
-int tqb_device_upload_ab_direct(tqb_device *d, const void *src, long long pitch, long long width, int rows, int g_first,
-                                int ma, int na, int cna, int mb, int nb, int cnb, long long b_off);
+int tqb_device_stage_reserve(tqb_device *d, size_t bytes);
+int tqb_device_upload_run(tqb_device *d, const tqb_in_run *r, int g_first, size_t stage_off);
+int tqb_device_download_run(tqb_device *d, const tqb_out_run *r, int g_first, size_t stage_off);
+/* D2H of the slices of x, u, lam, mu_x, mu_u that belong to nodes [ga, gb) into the pinned output block */
+int tqb_device_download_nodes(tqb_device *d, double *h_out, long long x0, long long x1, long long u0, long long u1);
+int tqb_device_download_begin(tqb_device *d);
+int tqb_device_download_end(tqb_device *d, double *ms);
 int tqb_device_kkt(tqb_device *d, double *h_kkt);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
 int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,

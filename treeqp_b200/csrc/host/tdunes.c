@@ -51,6 +51,12 @@ int tqb_verbose(void)
 
 const char *treeqp_b200_version(void) { return "treeqp_b200 0.1 (sm_100a)"; }
 int treeqp_b200_live_contexts(void) { return tqb_registry_size(); }
+int treeqp_b200_host_register(void *ptr, size_t bytes) { return tqb_host_register(ptr, bytes); }
+int treeqp_b200_host_unregister(void *ptr)
+{
+    if (ptr == NULL) { tqb_host_unpin_all(); return 0; } /* everything, including ranges registered under TREEQP_B200_PIN */
+    return tqb_host_unregister(ptr);
+}
 int treeqp_b200_device_count(void) { return tqb_cuda_device_count(); }
 int treeqp_b200_set_device(int device) { return tqb_cuda_set_device(device); }
 void treeqp_b200_set_profiling(int on) { tqb_set_profiling(on); }
@@ -311,6 +317,20 @@ return_t treeqp_tdunes_upload(const tree_qp_in *qp_in, const treeqp_tdunes_opts_
     if (tqb_forest_pack_upload(ctx->forest, (const tree_qp_in *const *) &qp_in, &tail)) return TREEQP_UNKNOWN_ERROR;
     ctx->forest->pack_ms = tqb_wall_ms() - t0 - tail;
     ctx->forest->h2d_bytes = (long long) sizeof(double) * ctx->forest->dims.n_in;
+    if (ctx->forest->in_direct)
+    {   /* DMA runs: their rows in the caller's layout (padding included) instead of the packed A, B and vectors */
+        const tqb_forest *f = ctx->forest;
+        long long by = (long long) sizeof(double) * (3LL * f->dims.X + 2LL * f->dims.U); /* Qd Qinv lam0 | Rd Rinv */
+        int covered = 0;
+        for (int i = 0; i < f->n_in_runs; i++)
+        {
+            const tqb_in_run *r = &f->in_runs[i];
+            by += (long long) (r->k1 - r->k0) * (r->mwidth + r->vwidth);
+            covered += r->k1 - r->k0;
+        }
+        by += (long long) sizeof(double) * (f->dims.n_in / (f->dims.Nn > 0 ? f->dims.Nn : 1)) * (f->dims.Nn - covered); /* staged nodes */
+        ctx->forest->h2d_bytes = by;
+    }
     ctx->uploaded = 1;
     ctx->lam_dirty = 0;
     return TREEQP_OK;
@@ -380,10 +400,13 @@ return_t treeqp_tdunes_download(tree_qp_out *qp_out, treeqp_tdunes_workspace *wo
     tqb_ctx *ctx = ctx_of(work);
     if (!ctx || !ctx->forest) return TREEQP_UNKNOWN_ERROR;
     tqb_forest *f = ctx->forest;
-    if (forest_download(f) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
-    double t0 = tqb_wall_ms();
-    tqb_forest_unpack(f, 0, qp_out);
-    f->pack_ms += tqb_wall_ms() - t0;
+    if (!tqb_forest_download_direct(f, qp_out))
+    {   /* one D2H copy into the pinned block, then the host loop over the BLASFEO views */
+        if (forest_download(f) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+        double t0 = tqb_wall_ms();
+        tqb_forest_unpack(f, 0, qp_out);
+        f->pack_ms += tqb_wall_ms() - t0;
+    }
     qp_out->info.iter = f->h_iter[0];
     return TREEQP_OK;
 }
@@ -423,8 +446,10 @@ return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
     qp_out->info.interface_time += 1e-3 * (t_end - t_after);
     qp_out->info.total_time = 1e-3 * (t_end - t_total);
     if (tqb_verbose())
-        fprintf(stderr, "[treeqp_b200] treeqp_tdunes_solve: status %d, %d Newton iterations, %lld kernel launches, gpu %.3f ms, total %.3f ms\n",
-                (int) st, qp_out->info.iter, ctx->forest->launches, ctx->forest->gpu_ms, t_end - t_total);
+        fprintf(stderr, "[treeqp_b200] treeqp_tdunes_solve: status %d, %d Newton iterations, %lld kernel launches, gpu %.3f ms, total %.3f ms "
+                        "(upload %.3f, solve %.3f, download %.3f)\n",
+                (int) st, qp_out->info.iter, ctx->forest->launches, ctx->forest->gpu_ms, t_end - t_total, t_solver - t_total,
+                t_after - t_solver, t_end - t_after);
     return st;
 }
 
