@@ -675,6 +675,8 @@ def run_sharded(lib, args, prob, rank, world, local, dist, barrier, max_over_ran
         return obj[0]
     comm = capi.Comm(lib, rank, world, local, bcast)
     qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+    # as at N = 1: the caller's buffers are page-locked once, every rank moves its subtrees by DMA from / into them
+    pinned = bool(qp_in.pin() and qp_out.pin()) if os.environ.get("TREEQP_B200_BENCH_UNPINNED", "0") != "1" else False
     sh = capi.TdunesSharded(lib, qp_in, comm, **OPTS)
     lam0 = np.zeros(prob.n_lambda)
     sh.set_dual_initialization(lam0)
@@ -733,7 +735,8 @@ def run_sharded(lib, args, prob, rank, world, local, dist, barrier, max_over_ran
     sh.destroy()
     comm.destroy()
     return dict(t_res=t_res, t_e2e=t_e2e, dev_ms=dev_ms, stats=stats, e2e_stats=e2e_stats, prof=prof, sol=sol,
-                kkt=None, kkt_dev=None, clk=(clk_lo, clk_hi), launches=stats["kernel_launches"] * args.steps * world, shard=shard)
+                kkt=None, kkt_dev=None, clk=(clk_lo, clk_hi), launches=stats["kernel_launches"] * args.steps * world, shard=shard,
+                pinned=pinned)
 
 
 def roofline_block(prob, prof, world, depth):

@@ -31,8 +31,13 @@ def main():
     depth = int(sys.argv[1]) if len(sys.argv) > 1 else 9
     failures = []
     for name, prob, opts in [("random_d%d" % depth, P.random_tree(P.binary_tree_nk(depth), 12, 4, seed=3, ubound=0.2), dict(maxIter=200)),
-                             ("random_d7_u05", P.random_tree(P.binary_tree_nk(7), 12, 4, seed=1, ubound=0.5), dict(maxIter=200))]:
+                             ("random_d7_u05", P.random_tree(P.binary_tree_nk(7), 12, 4, seed=1, ubound=0.5), dict(maxIter=200)),
+                             # large enough for the DMA path: caller buffers page-locked, every rank moves its subtrees'
+                             # levels as strided copies from / into them (and wide levels re-use unchanged blocks)
+                             ("random_d14_pinned", P.random_tree(P.binary_tree_nk(14), 12, 4, seed=5, ubound=0.2), dict(maxIter=200))]:
         qp_in, qp_out = capi.QpIn(lib, prob), capi.QpOut(lib, prob)
+        if name.endswith("pinned"):
+            assert qp_in.pin() and qp_out.pin()
         sh = capi.TdunesSharded(lib, qp_in, comm, **opts)
         sh.set_dual_initialization(np.zeros(prob.n_lambda))
         st = sh.solve(qp_out)
@@ -53,6 +58,8 @@ def main():
                   and bool((cnt.cpu().numpy() == 1).all()))
             errs = {k: CS.rel_err(parts[k], getattr(ref, k)) for k in parts}
             ok = ok and all(e < 1e-10 for e in errs.values())
+            if name.endswith("pinned"):   # the DMA path moves the caller's rows: its byte count differs from the packed block's
+                ok = ok and stats["h2d_bytes"] != 8 * 0 and stats["pack_ms"] >= 0.0
             print("%s: sharded over %d GPUs (cut depth %d, %d local nodes): status %d iter %d (single GPU: %d %d) gpu %.2f ms vs %.2f ms, max rel err %.1e -> %s"
                   % (name, world, plan["cut_depth"], plan["n_local"], st, qp_out.iter, ref.status, ref.iter,
                      stats["gpu_ms"], ref.stats["gpu_ms"], max(errs.values()), "OK" if ok else "MISMATCH"), flush=True)

@@ -1062,6 +1062,22 @@ extern "C" int tqb_device_upload_run(tqb_device *D, const tqb_in_run *r, int g_f
     return 0;
 }
 
+__global__ void k_recip(View v)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v.X) v.in.Qinv[i] = 1.0 / v.in.Qd[i];
+    if (i < v.U) v.in.Rinv[i] = 1.0 / v.in.Rd[i];
+}
+
+extern "C" int tqb_device_finish_direct_upload(tqb_device *D, long long lam0_off, int lam0_zero)
+{
+    const int n = D->v.X > D->v.U ? D->v.X : D->v.U;
+    k_recip<<<(n + 255) / 256, 256, 0, D->stream>>>(D->v);
+    CK(cudaGetLastError());
+    if (lam0_zero) CK(cudaMemsetAsync(D->d_in + lam0_off, 0, sizeof(double) * (size_t) D->v.X, D->stream));
+    return 0;
+}
+
 extern "C" int tqb_device_download_begin(tqb_device *D)
 {
     CK(cudaEventRecord(D->ev0, D->stream));

@@ -595,7 +595,7 @@ __device__ __forceinline__ void cp_async_commit_wait_all()
  * (`waited` tells it whether the programmatic-launch wait has been done). */
 template <int NX, int NU, int MD, int PNX, bool ROOT>
 __device__ __forceinline__ bool bf_block_reuse(const View &v, const int4 d0, const int4 d1, const int4 d2, int kids_are_parents,
-                                               bool wait_here, bool &waited, double *Ms, int lane)
+                                               bool wait_here, bool &waited, double *Ms, int lane, int tree_status)
 {
     using Cfg = BlockedCfg<NX, NU, MD, PNX, ROOT>;
     constexpr int D = Cfg::D, NCOL = Cfg::NCOL, TR = Cfg::TR, KS = Cfg::KS;
@@ -610,6 +610,7 @@ __device__ __forceinline__ bool bf_block_reuse(const View &v, const int4 d0, con
      * ago, nobody touches it in between), and the gradient's operands.  A changed block (a few per cent) wastes the
      * staging copies. */
     const int c_own = (lane == 0) ? v.chg[g] : (lane <= MD ? v.chg[k0 + lane - 1] : 0);
+    const int was_reg = (lane == 0) ? v.breg[g] : 0; /* with the other requests: a load behind the wait is one more round trip */
     double *sL = Ms, *sU = Ms + OFFU, *ys = Ms + Cfg::SM_M;
     {
         const double *Lg = v.W + d1.w, *Up = v.Ut + d2.x;
@@ -648,8 +649,8 @@ __device__ __forceinline__ bool bf_block_reuse(const View &v, const int4 d0, con
             }
         }
         if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
-        if (__any_sync(FULL, c_own != 0))
-        {   /* own or a kid's active set moved: full path (its loads now hit L1) */
+        if (__any_sync(FULL, c_own != 0) || tree_status != TQB_RUNNING)
+        {   /* own or a kid's active set moved: full path (its loads now hit L1); a finished tree: the caller returns */
             cp_async_commit_wait_all();
             __syncwarp();
             return false;
@@ -681,7 +682,7 @@ __device__ __forceinline__ bool bf_block_reuse(const View &v, const int4 d0, con
         {
             v.nva[g] = part;
             v.bdirty[g] = 0;
-            if (v.breg[g]) atomicAdd(&v.counters[2], 1); /* the re-used factor is a regularised one: counted as the full path would */
+            if (was_reg) atomicAdd(&v.counters[2], 1); /* the re-used factor is a regularised one: counted as the full path would */
         }
     }
     __syncwarp(); /* staged factor visible to the whole warp */
@@ -720,18 +721,16 @@ __device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids
     const int4 *dp = reinterpret_cast<const int4 *>(v.lvl_desc) + 3 * desc;
     const int4 d0 = __ldg(dp), d1 = __ldg(dp + 1), d2 = __ldg(dp + 2);
     const int g = d0.x, k0 = d0.y, xo = d0.z, uo = d0.w, xb = d1.x;
-    if (v.status[d2.y] != TQB_RUNNING)
-    {
-        if (wait_here) { pdl_wait(); pdl_release(); }
-        return;
-    }
+    /* requested here, looked at behind the first batch of loads: a test right away would put one more dependent
+     * round trip (descriptor -> status -> data) in front of every block */
+    const int tree_status = v.status[d2.y];
     BF_STAMP(1);
     if constexpr (!ROOT)
     {
         if (try_skip)
         {
             bool waited = false;
-            if (bf_block_reuse<NX, NU, MD, PNX, ROOT>(v, d0, d1, d2, kids_are_parents, wait_here, waited, Ms, lane)) return;
+            if (bf_block_reuse<NX, NU, MD, PNX, ROOT>(v, d0, d1, d2, kids_are_parents, wait_here, waited, Ms, lane, tree_status)) return;
             if (waited) wait_here = false;
         }
     }
@@ -776,6 +775,11 @@ __device__ __forceinline__ void bf_block_lb(const View &v, size_t desc, int kids
                 }
             }
             if (isW) res = v.in.b[xb + lane] - v.x[xb + lane];
+            if (tree_status != TQB_RUNNING)
+            {   /* a finished tree of the forest: nothing to do (warp-uniform) */
+                if (wait_here) { pdl_wait(); pdl_release(); }
+                return;
+            }
             __syncwarp(); /* previous attempt's readers of Ms / ys are done */
 #pragma unroll
             for (int i = 0; i < TR; i++)

@@ -353,7 +353,7 @@ static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gm
     const tqb_tables *T = &f->ht;
     tqb_inputs *in = &f->hin;
     int g0 = T->tnode0[t];
-    const int direct = f->in_direct && !gmap; /* nodes inside a run: only the weights are packed here, the rest travels by strided DMA */
+    const int direct = f->in_direct; /* nodes inside a run (local index): only the weights are packed here, the rest travels by strided DMA */
     assert(gmap || T->tnode0[t + 1] - g0 == qp->N);
 #pragma omp parallel for schedule(static) if (j1 - j0 > 2048)
     for (int j = j0; j < j1; j++)
@@ -361,20 +361,10 @@ static void pack_range(tqb_forest *f, int t, const tree_qp_in *qp, const int *gm
         const int k = gmap ? gmap[j] : j;
         int g = g0 + j, nx = qp->nx[k], nu = qp->nu[k], xo = T->xoff[g], uo = T->uoff[g];
         assert(nx == T->nx[g] && nu == T->nu[g]);
-        if (direct && node_in_run(f, k))
-        {   /* clipping node of a DMA run: diagonal weights and their reciprocals only */
-            for (int i = 0; i < nx; i++)
-            {
-                double w = BLASFEO_DMATEL(&qp->Q[k], i, i);
-                in->Qd[xo + i] = w;
-                in->Qinv[xo + i] = 1.0 / w;
-            }
-            for (int i = 0; i < nu; i++)
-            {
-                double w = BLASFEO_DMATEL(&qp->R[k], i, i);
-                in->Rd[uo + i] = w;
-                in->Rinv[uo + i] = 1.0 / w;
-            }
+        if (direct && node_in_run(f, j))
+        {   /* clipping node of a DMA run: the diagonal weights only (the device forms the reciprocals, k_recip) */
+            for (int i = 0; i < nx; i++) in->Qd[xo + i] = BLASFEO_DMATEL(&qp->Q[k], i, i);
+            for (int i = 0; i < nu; i++) in->Rd[uo + i] = BLASFEO_DMATEL(&qp->R[k], i, i);
             continue;
         }
         if (k > 0)
@@ -466,8 +456,11 @@ static int upload_nodes(tqb_forest *f, int ga, int gb, int with_lam0)
     const long long u0 = T->uoff[ga], u1 = last ? d->U : T->uoff[gb];
     int rc = 0;
     /* weights, their reciprocals, the dual start (and the dense nodes' bounds) always come from the staging block */
-    const double *xs_all[] = {in->Qd, in->Qinv, with_lam0 ? in->lam0 : NULL, in->dxmin, in->dxmax};
-    const double *us_all[] = {in->Rd, in->Rinv, in->dumin, in->dumax};
+    /* DMA mode: the reciprocals are formed on the device from Qd / Rd (IEEE division: the same bits as the host's
+     * 1.0 / w), and a dual start of zeros is a device memset -- 34 MB less on the wire for config 3 */
+    const int dm = f->in_direct;
+    const double *xs_all[] = {in->Qd, dm ? NULL : in->Qinv, (with_lam0 && !(dm && f->lam0_zero)) ? in->lam0 : NULL, in->dxmin, in->dxmax};
+    const double *us_all[] = {in->Rd, dm ? NULL : in->Rinv, in->dumin, in->dumax};
     for (unsigned i = 0; i < sizeof xs_all / sizeof xs_all[0]; i++)
         if (xs_all[i]) rc |= tqb_device_upload_range(f->dev, f->h_in, (xs_all[i] - f->h_in) + x0, x1 - x0);
     for (unsigned i = 0; i < sizeof us_all / sizeof us_all[0]; i++)
@@ -617,7 +610,10 @@ int tqb_forest_pack_upload_mapped(tqb_forest *f, const tree_qp_in *full_qp, cons
  * travel as strided DMA copies in the caller's layout and are converted on the device: the host packer only forms
  * the diagonal weights and their reciprocals, and the pinned staging block is by-passed for 90 % of the bytes. */
 #ifndef TQB_DIRECT_MIN_NODES
-#define TQB_DIRECT_MIN_NODES 4096
+#define TQB_DIRECT_MIN_NODES 4096 /* smallest (local) tree that tries the DMA path */
+#endif
+#ifndef TQB_DIRECT_MIN_RUN
+#define TQB_DIRECT_MIN_RUN 1024   /* shortest run of nodes worth a strided copy of its own */
 #endif
 static int in_layout_equal(const tree_qp_in *qp, int k, int r)
 {   /* nodes k and r (both >= 1): same dimensions and same offsets inside their matrix / vector chunks */
@@ -632,26 +628,32 @@ static int in_layout_equal(const tree_qp_in *qp, int k, int r)
            qp->umin[k].pa - vb == qp->umin[r].pa - vr && qp->umax[k].pa - vb == qp->umax[r].pa - vr;
 }
 
-static void build_in_runs(tqb_forest *f, const tree_qp_in *qp)
-{
-    const void *key[3] = {qp->A, qp->N > 1 ? (const void *) qp->A[0].pA : NULL, qp->b};
-    if (f->in_key[0] == key[0] && f->in_key[1] == key[1] && f->in_key[2] == key[2]) return; /* same views as last time */
+static void build_in_runs(tqb_forest *f, const tree_qp_in *qp, const int *gmap)
+{   /* runs are kept in LOCAL node indices j (the forest's own numbering); the views are those of node k = gmap[j] of the
+     * caller's tree (gmap == NULL: k = j).  A sharded rank's local tree maps level by level onto consecutive nodes
+     * of the full tree, so every deep level is one run. */
+    const void *key[4] = {qp->A, qp->N > 1 ? (const void *) qp->A[0].pA : NULL, qp->b, gmap};
+    if (!memcmp(f->in_key, key, sizeof key)) return; /* same views as last time */
     memcpy(f->in_key, key, sizeof key);
     f->n_in_runs = 0;
-    const int N = qp->N;
-    for (int k = 1; k + 1 < N && f->n_in_runs < TQB_MAX_RUNS;)
+    const int Nl = f->ht.tnode0[1] - f->ht.tnode0[0];
+#define GK(j) (gmap ? gmap[j] : (j))
+    for (int j = 1; j + 1 < Nl && f->n_in_runs < TQB_MAX_RUNS;)
     {
+        const int k = GK(j);
+        if (k < 1 || GK(j + 1) != k + 1) { j++; continue; }
         const long long mp = (const char *) qp->A[k].pA - (const char *) qp->A[k - 1].pA;
         const long long vp = (const char *) qp->b[k].pa - (const char *) qp->b[k - 1].pa;
-        int e = k + 1;
-        while (e < N && in_layout_equal(qp, e, k) && (const char *) qp->A[e - 1].pA - (const char *) qp->A[e - 2].pA == mp &&
-               (const char *) qp->b[e - 1].pa - (const char *) qp->b[e - 2].pa == vp)
+        int e = j + 1;
+        while (e < Nl && GK(e) == k + (e - j) && in_layout_equal(qp, GK(e), k) &&
+               (const char *) qp->A[GK(e) - 1].pA - (const char *) qp->A[GK(e) - 2].pA == mp &&
+               (const char *) qp->b[GK(e) - 1].pa - (const char *) qp->b[GK(e) - 2].pa == vp)
             e++;
-        if (e - k >= TQB_DIRECT_MIN_NODES)
+        if (e - j >= TQB_DIRECT_MIN_RUN)
         {
             tqb_in_run *r = &f->in_runs[f->n_in_runs];
             const struct blasfeo_dmat *A = &qp->A[k - 1], *B = &qp->B[k - 1];
-            r->k0 = k; r->k1 = e;
+            r->k0 = j; r->k1 = e;
             r->mbase = (const char *) A->pA; r->mpitch = mp;
             r->b_off = (const char *) B->pA - (const char *) A->pA;
             r->mwidth = r->b_off + (long long) sizeof(double) * B->pm * B->cn;
@@ -673,16 +675,17 @@ static void build_in_runs(tqb_forest *f, const tree_qp_in *qp)
                            r->vwidth <= vp && !(mp & 7) && !(vp & 7) && !(r->b_off & 7);
             if (ok) f->n_in_runs++;
         }
-        k = e;
+        j = e;
     }
+#undef GK
 }
 
 /* returns 1 when the runs were sent by DMA (f->in_direct), 0 when the whole tree takes the staged path */
-static int upload_in_runs(tqb_forest *f, const tree_qp_in *qp)
+static int upload_in_runs(tqb_forest *f, const tree_qp_in *qp, const int *gmap)
 {
     f->in_direct = 0;
-    if (qp->N < TQB_DIRECT_MIN_NODES || f->dims.has_dense || f->dims.NC > 0) return 0;
-    build_in_runs(f, qp);
+    if (f->dims.Nn < TQB_DIRECT_MIN_NODES || f->dims.has_dense || f->dims.NC > 0) return 0;
+    build_in_runs(f, qp, gmap);
     if (f->n_in_runs == 0) return 0;
     /* one page-locked range from the first matrix to the last vector of the runs */
     const char *lo = NULL, *hi = NULL;
@@ -723,7 +726,7 @@ static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const in
     int rc = tqb_device_upload_begin(f->dev);
     f->in_direct = 0;
     const double tv0 = tqb_wall_ms();
-    if (nT == 1 && !gmap) upload_in_runs(f, qp[0]);
+    if (nT == 1) upload_in_runs(f, qp[0], gmap);
     const double tv1 = tqb_wall_ms();
     if (nT == 1)
     {
@@ -748,6 +751,7 @@ static int pack_upload_impl(tqb_forest *f, const tree_qp_in *const *qp, const in
     }
     /* dense Hessian blocks: offsets exist only for the dense nodes, sent as one range at the end */
     if (d->has_dense) rc |= tqb_device_upload_range(f->dev, f->h_in, f->hin.H - f->h_in, d->szH);
+    if (f->in_direct) rc |= tqb_device_finish_direct_upload(f->dev, f->hin.lam0 - f->h_in, f->lam0_zero);
     const double t0 = tqb_wall_ms();
     double total = 0.0;
     rc |= tqb_device_upload_end(f->dev, &total);
@@ -767,7 +771,33 @@ void tqb_forest_set_lambda0(tqb_forest *f, int t, const double *lambda)
     int xroot = T->xoff[g0], nx0 = T->nx[g0];
     int xend = (g1 < f->dims.Nn) ? T->xoff[g1] : f->dims.X;
     for (int i = 0; i < nx0; i++) f->hin.lam0[xroot + i] = 0.0;
-    memcpy(f->hin.lam0 + xroot + nx0, lambda, sizeof(double) * (size_t) (xend - xroot - nx0));
+    const long long n = xend - xroot - nx0;
+    double *dst = f->hin.lam0 + xroot + nx0;
+    if (n < (1 << 16))
+    {
+        memcpy(dst, lambda, sizeof(double) * (size_t) n);
+        f->lam0_zero = 0;
+    }
+    else
+    {   /* large trees: copy in parallel and notice a start of zeros (the cold start of every benchmark and example),
+         * which the DMA upload path turns into a device memset */
+        unsigned long long nz = 0;
+#pragma omp parallel for schedule(static) reduction(| : nz)
+        for (long long c = 0; c < (n + 4095) / 4096; c++)
+        {
+            const long long a = c * 4096, b = a + 4096 < n ? a + 4096 : n;
+            unsigned long long acc = 0;
+            for (long long i = a; i < b; i++)
+            {
+                unsigned long long bits;
+                memcpy(&bits, &lambda[i], sizeof bits);
+                acc |= bits;
+                dst[i] = lambda[i];
+            }
+            nz |= acc;
+        }
+        f->lam0_zero = (nz == 0) && f->dims.nT == 1; /* +0.0 everywhere */
+    }
 }
 
 /* device results (pinned staging) -> BLASFEO views of tree_qp_out
@@ -796,35 +826,40 @@ void tqb_forest_unpack(const tqb_forest *f, int t, tree_qp_out *out)
  * stride.  With the caller's buffer page-locked the device assembles each run in the caller's layout (k_gather_run)
  * and ONE strided D2H copy per run writes it in place; only the nodes outside the runs (the root, its children) go
  * through the pinned block and the host loop. */
-static void build_out_runs(tqb_forest *f, const tree_qp_out *out, int N)
-{
-    const void *key[3] = {out->x, out->x[0].pa, out->lam};
-    if (f->out_key[0] == key[0] && f->out_key[1] == key[1] && f->out_key[2] == key[2]) return;
+static void build_out_runs(tqb_forest *f, const tree_qp_out *out, const int *gmap, const int *owned)
+{   /* local indices j, views of node k = gmap[j]; nodes a sharded rank does not own are never written */
+    const void *key[4] = {out->x, out->x[0].pa, out->lam, gmap};
+    if (!memcmp(f->out_key, key, sizeof key)) return;
     memcpy(f->out_key, key, sizeof key);
     f->n_out_runs = 0;
     const tqb_tables *T = &f->ht;
-    const int g0 = T->tnode0[0];
+    const int g0 = T->tnode0[0], Nl = T->tnode0[1] - g0;
+#define GK(j) (gmap ? gmap[j] : (j))
 #define OFFS(k, o) do { const double *b_ = out->x[k].pa; (o)[0] = 0; (o)[1] = out->u[k].pa - b_; (o)[2] = out->mu_x[k].pa - b_; \
                         (o)[3] = out->mu_u[k].pa - b_; (o)[4] = out->lam[(k) - 1].pa - b_; } while (0)
-    for (int k = 1; k + 1 < N && f->n_out_runs < TQB_MAX_RUNS;)
+    for (int j = 1; j + 1 < Nl && f->n_out_runs < TQB_MAX_RUNS;)
     {
+        const int k = GK(j);
+        if (k < 1 || (owned && !owned[j]) || GK(j + 1) != k + 1) { j++; continue; }
         long long o0[5];
         OFFS(k, o0);
         const long long pitch = (const char *) out->x[k + 1].pa - (const char *) out->x[k].pa;
-        int e = k + 1;
-        for (; e < N; e++)
+        int e = j + 1;
+        for (; e < Nl; e++)
         {
+            const int ke = GK(e);
             long long o[5];
-            OFFS(e, o);
-            if (T->nx[g0 + e] != T->nx[g0 + k] || T->nu[g0 + e] != T->nu[g0 + k] || T->ncn[g0 + e] != 0 || memcmp(o, o0, sizeof o) ||
-                (const char *) out->x[e].pa - (const char *) out->x[e - 1].pa != pitch)
+            if (ke != k + (e - j) || (owned && !owned[e])) break;
+            OFFS(ke, o);
+            if (T->nx[g0 + e] != T->nx[g0 + j] || T->nu[g0 + e] != T->nu[g0 + j] || T->ncn[g0 + e] != 0 || memcmp(o, o0, sizeof o) ||
+                (const char *) out->x[ke].pa - (const char *) out->x[ke - 1].pa != pitch)
                 break;
         }
-        if (e - k >= TQB_DIRECT_MIN_NODES && T->ncn[g0 + k] == 0)
+        if (e - j >= TQB_DIRECT_MIN_RUN && T->ncn[g0 + j] == 0)
         {
             tqb_out_run *r = &f->out_runs[f->n_out_runs];
-            r->k0 = k; r->k1 = e; r->base = (char *) out->x[k].pa; r->pitch = pitch;
-            r->nx = T->nx[g0 + k]; r->nu = T->nu[g0 + k];
+            r->k0 = j; r->k1 = e; r->base = (char *) out->x[k].pa; r->pitch = pitch;
+            r->nx = T->nx[g0 + j]; r->nu = T->nu[g0 + j];
             const int len[5] = {r->nx, r->nu, r->nx, r->nu, r->nx};
             long long lo = 0, hi = 0;
             for (int i = 0; i < 5; i++)
@@ -836,19 +871,21 @@ static void build_out_runs(tqb_forest *f, const tree_qp_out *out, int N)
             r->width = (long long) sizeof(double) * hi;
             if (lo == 0 && pitch > 0 && r->width <= pitch && !(pitch & 7)) f->n_out_runs++;
         }
-        k = e;
+        j = e;
     }
 #undef OFFS
+#undef GK
 }
 
-/* returns 1 when qp_out has been filled (runs by DMA, the other nodes through the pinned block), 0: not applicable */
-int tqb_forest_download_direct(tqb_forest *f, tree_qp_out *out)
+/* returns 1 when qp_out has been filled (runs by DMA, the other nodes through the pinned block), 0: not applicable.
+ * gmap / owned: the local tree of a sharded rank (NULL: the tree itself, every node) */
+int tqb_forest_download_direct(tqb_forest *f, tree_qp_out *out, const int *gmap, const int *owned)
 {
     const tqb_tables *T = &f->ht;
     const tqb_dims *d = &f->dims;
     if (d->nT != 1 || d->Nn < TQB_DIRECT_MIN_NODES || d->NC > 0) return 0;
     const int N = d->Nn, g0 = T->tnode0[0];
-    build_out_runs(f, out, N);
+    build_out_runs(f, out, gmap, owned);
     if (f->n_out_runs == 0) return 0;
     char *lo = NULL, *hi = NULL;
     size_t stage = 0;
@@ -897,9 +934,11 @@ int tqb_forest_download_direct(tqb_forest *f, tree_qp_out *out)
     for (int i = 0; i <= f->n_out_runs; i++)
     {
         const int s1 = i < f->n_out_runs ? f->out_runs[i].k0 : N;
-        for (int k = s0; k < s1; k++)
+        for (int j = s0; j < s1; j++)
         {
-            const int g = g0 + k, nx = T->nx[g], nu = T->nu[g], xo = T->xoff[g], uo = T->uoff[g];
+            if (owned && !owned[j]) continue;
+            const int k = gmap ? gmap[j] : j;
+            const int g = g0 + j, nx = T->nx[g], nu = T->nu[g], xo = T->xoff[g], uo = T->uoff[g];
             memcpy(out->x[k].pa, x + xo, sizeof(double) * (size_t) nx);
             memcpy(out->u[k].pa, u + uo, sizeof(double) * (size_t) nu);
             memcpy(out->mu_x[k].pa, mux + xo, sizeof(double) * (size_t) nx);

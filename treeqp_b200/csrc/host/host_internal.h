@@ -97,7 +97,7 @@ typedef struct tqb_device tqb_device;
  * copies, in the caller's layout, and is converted on the device (k_unpack_run / k_gather_run). */
 typedef struct tqb_in_run
 {
-    int k0, k1;                       /* nodes [k0, k1) of the tree, k0 >= 1 */
+    int k0, k1;                       /* LOCAL nodes [k0, k1) of the forest's tree, k0 >= 1 (sharded: node gmap[k0] .. of the caller's tree) */
     const char *mbase;                /* A of node k0 */
     long long mpitch, mwidth, b_off;  /* bytes: node to node, A..end of B, A to B */
     int ma, na, cna, mb, nb, cnb;     /* BLASFEO panel-major views of A and B */
@@ -141,8 +141,9 @@ typedef struct tqb_forest
     int n_in_runs, n_out_runs;
     tqb_in_run in_runs[TQB_MAX_RUNS];
     tqb_out_run out_runs[TQB_MAX_RUNS];
-    const void *in_key[3], *out_key[3];
+    const void *in_key[4], *out_key[4];
     int in_direct;           /* the last upload used in_runs */
+    int lam0_zero;           /* the host dual start is all +0.0 (set_dual_initialization of a large single tree) */
 } tqb_forest;
 
 /* ---- registry.c: contexts by the caller's workspace memory (a re-create on the same ptr frees the old arena) ---- */
@@ -169,7 +170,7 @@ int tqb_forest_pack_upload(tqb_forest *f, const struct tree_qp_in_ *const *qp, d
 /* re-pack and re-send nodes [j0, j1) of tree t only (what an x0 update touches) / the dual start only */
 int tqb_forest_pack_upload_mapped(tqb_forest *f, const struct tree_qp_in_ *full_qp, const int *gmap, double *tail_ms);
 /* results of a large single tree straight into the caller's (page-locked) tree_qp_out; 0 = not applicable */
-int tqb_forest_download_direct(tqb_forest *f, struct tree_qp_out_ *out);
+int tqb_forest_download_direct(tqb_forest *f, struct tree_qp_out_ *out, const int *gmap, const int *owned);
 int tqb_forest_update_nodes(tqb_forest *f, int t, const struct tree_qp_in_ *qp, int j0, int j1);
 int tqb_forest_update_x0_batch(tqb_forest *f, const struct tree_qp_in_ *const *qp, long long *bytes);
 int tqb_forest_upload_lambda0(tqb_forest *f);
@@ -208,6 +209,8 @@ int tqb_device_upload_run(tqb_device *d, const tqb_in_run *r, int g_first, size_
 int tqb_device_download_run(tqb_device *d, const tqb_out_run *r, int g_first, size_t stage_off);
 /* D2H of the slices of x, u, lam, mu_x, mu_u that belong to nodes [ga, gb) into the pinned output block */
 int tqb_device_download_nodes(tqb_device *d, double *h_out, long long x0, long long x1, long long u0, long long u1);
+/* after a DMA-mode upload: Qinv = 1 / Qd, Rinv = 1 / Rd on the device, lam0 = 0 by memset when the host start is zero */
+int tqb_device_finish_direct_upload(tqb_device *d, long long lam0_off, int lam0_zero);
 int tqb_device_download_begin(tqb_device *d);
 int tqb_device_download_end(tqb_device *d, double *ms);
 int tqb_device_kkt(tqb_device *d, double *h_kkt);

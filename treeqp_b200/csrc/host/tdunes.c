@@ -305,6 +305,23 @@ static return_t forest_download(tqb_forest *f)
     return TREEQP_OK;
 }
 
+/* bytes of the last pack_upload: the packed input block, or -- DMA runs -- their rows in the caller's layout (padding
+ * included) plus what still goes through the staging block */
+static long long upload_bytes(const tqb_forest *f)
+{
+    if (!f->in_direct) return (long long) sizeof(double) * f->dims.n_in;
+    long long by = (long long) sizeof(double) * ((f->lam0_zero ? 1LL : 2LL) * f->dims.X + f->dims.U); /* Qd (lam0) | Rd */
+    int covered = 0;
+    for (int i = 0; i < f->n_in_runs; i++)
+    {
+        const tqb_in_run *r = &f->in_runs[i];
+        by += (long long) (r->k1 - r->k0) * (r->mwidth + r->vwidth);
+        covered += r->k1 - r->k0;
+    }
+    by += (long long) sizeof(double) * (f->dims.n_in / (f->dims.Nn > 0 ? f->dims.Nn : 1)) * (f->dims.Nn - covered); /* staged nodes */
+    return by;
+}
+
 return_t treeqp_tdunes_upload(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts,
                               treeqp_tdunes_workspace *work)
 {
@@ -317,20 +334,7 @@ return_t treeqp_tdunes_upload(const tree_qp_in *qp_in, const treeqp_tdunes_opts_
     if (tqb_forest_pack_upload(ctx->forest, (const tree_qp_in *const *) &qp_in, &tail)) return TREEQP_UNKNOWN_ERROR;
     ctx->forest->pack_ms = tqb_wall_ms() - t0 - tail;
     ctx->forest->h2d_bytes = (long long) sizeof(double) * ctx->forest->dims.n_in;
-    if (ctx->forest->in_direct)
-    {   /* DMA runs: their rows in the caller's layout (padding included) instead of the packed A, B and vectors */
-        const tqb_forest *f = ctx->forest;
-        long long by = (long long) sizeof(double) * (3LL * f->dims.X + 2LL * f->dims.U); /* Qd Qinv lam0 | Rd Rinv */
-        int covered = 0;
-        for (int i = 0; i < f->n_in_runs; i++)
-        {
-            const tqb_in_run *r = &f->in_runs[i];
-            by += (long long) (r->k1 - r->k0) * (r->mwidth + r->vwidth);
-            covered += r->k1 - r->k0;
-        }
-        by += (long long) sizeof(double) * (f->dims.n_in / (f->dims.Nn > 0 ? f->dims.Nn : 1)) * (f->dims.Nn - covered); /* staged nodes */
-        ctx->forest->h2d_bytes = by;
-    }
+    ctx->forest->h2d_bytes = upload_bytes(ctx->forest);
     ctx->uploaded = 1;
     ctx->lam_dirty = 0;
     return TREEQP_OK;
@@ -400,7 +404,7 @@ return_t treeqp_tdunes_download(tree_qp_out *qp_out, treeqp_tdunes_workspace *wo
     tqb_ctx *ctx = ctx_of(work);
     if (!ctx || !ctx->forest) return TREEQP_UNKNOWN_ERROR;
     tqb_forest *f = ctx->forest;
-    if (!tqb_forest_download_direct(f, qp_out))
+    if (!tqb_forest_download_direct(f, qp_out, NULL, NULL))
     {   /* one D2H copy into the pinned block, then the host loop over the BLASFEO views */
         if (forest_download(f) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
         double t0 = tqb_wall_ms();
@@ -717,7 +721,7 @@ return_t treeqp_tdunes_sharded_upload(treeqp_tdunes_sharded *sh, const tree_qp_i
     double t0 = tqb_wall_ms(), tail = 0.0;
     if (tqb_forest_pack_upload_mapped(sh->forest, qp_in, sh->plan->gmap, &tail)) return TREEQP_UNKNOWN_ERROR;
     sh->forest->pack_ms = tqb_wall_ms() - t0 - tail;
-    sh->forest->h2d_bytes = (long long) sizeof(double) * sh->forest->dims.n_in;
+    sh->forest->h2d_bytes = upload_bytes(sh->forest);
     sh->uploaded = 1;
     sh->lam_dirty = 0;
     return TREEQP_OK;
@@ -739,10 +743,13 @@ return_t treeqp_tdunes_sharded_solve_resident(treeqp_tdunes_sharded *sh)
 
 return_t treeqp_tdunes_sharded_download(treeqp_tdunes_sharded *sh, tree_qp_out *qp_out)
 {
-    if (forest_download(sh->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
-    double t0 = tqb_wall_ms();
-    tqb_forest_unpack_sharded(sh->forest, sh->plan, qp_out);
-    sh->forest->pack_ms += tqb_wall_ms() - t0;
+    if (!tqb_forest_download_direct(sh->forest, qp_out, sh->plan->gmap, sh->plan->owned))
+    {
+        if (forest_download(sh->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+        double t0 = tqb_wall_ms();
+        tqb_forest_unpack_sharded(sh->forest, sh->plan, qp_out);
+        sh->forest->pack_ms += tqb_wall_ms() - t0;
+    }
     qp_out->info.iter = sh->forest->h_iter[0];
     return TREEQP_OK;
 }
