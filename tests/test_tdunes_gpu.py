@@ -330,3 +330,21 @@ def test_reuse_of_unchanged_blocks_is_bit_identical(reg, product_lib, monkeypatc
     if reg.get("regType") == 2: assert a.stats["n_reg"] > 0
     for k in ("x", "u", "lam", "mu_x", "mu_u"):
         assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_affine_stage_update_matches_recomputation(product_lib, monkeypatch):
+    """Large trees form the stage solution of most iterations from the affine model of the line search (k_step_affine:
+    qmod0 += tau dq, no pass over A and B) and refresh it from lambda every 4th iteration.  Against recomputing it in
+    every iteration (TREEQP_B200_AFFINE=0, what the reference does): same status, Newton iterations, per-iteration
+    trial counts and active sets, solutions equal to rounding; and the reference golden of the depth-14 tree
+    (test_large_tree_matches_reference_golden) runs on the affine path."""
+    prob = P.random_tree(P.binary_tree_nk(13), 12, 4, seed=5, ubound=0.2)
+    monkeypatch.setenv("TREEQP_B200_AFFINE", "0")
+    a = capi.solve_tdunes(product_lib, prob, maxIter=200)
+    monkeypatch.delenv("TREEQP_B200_AFFINE")
+    b = capi.solve_tdunes(product_lib, prob, maxIter=200)
+    assert (a.status, a.iter) == (b.status, b.iter) and a.status == 0
+    assert a.stats["ls_iters"] == b.stats["ls_iters"]
+    assert b.stats["kernel_launches"] < a.stats["kernel_launches"], "the affine step did not replace any stage pass"
+    check_against(b, dict(x=a.x, u=a.u, lam=a.lam, mu_x=a.mu_x, mu_u=a.mu_u), prob, tol=1e-12)
+    assert b.kkt < 1e-8

@@ -375,3 +375,68 @@ __global__ void __launch_bounds__(32 * TQB_STAGE_WPB, TQB_STAGE_MINBLOCKS) k_sta
         it = nxt;
     }
 }
+
+
+/* ---- stage QPs from the affine model: lambda step + next iteration's stage solution in one stream -------------
+ * After the line search the multipliers move along dlam by the accepted step: lambda += tau dlam.  The stage
+ * gradients are affine in lambda -- qmod(lambda + tau dlam) = qmod0 + tau dq with dq from k_stage_fused<2> -- which
+ * is what every line-search trial already evaluates (k_ls_eval).  This kernel applies the step to lambda AND forms
+ * the next Newton iteration's stage solution from the model: qmod0 += tau dq, x = clip(Qinv qmod0), xUnc, P, the
+ * active-set change flags, cmod0 += tau dc (the same for u) -- vectors only, [A B] is not read: k_stage_fused<0>
+ * (a full pass over A and B, 201 MB on config 3) is skipped for that iteration.  Against recomputing from lambda the
+ * stage gradient differs by rounding (one fma per element and iteration), so the driver refreshes it from lambda
+ * with k_stage_fused<0> every TQB_AFFINE_REFRESH-th iteration (and at iteration 0): the drift never spans more than
+ * a few iterations.  LPN lanes per node (>= nx + nu, a power of two): lane e < nx owns x element e, lane nx + e u
+ * element e. */
+template <int LPN>
+__global__ void __launch_bounds__(256) k_step_affine(View v, int with_stage)
+{
+    constexpr int NPW = 32 / LPN;
+    const int lane = threadIdx.x & 31, slot = lane / LPN, e = lane - slot * LPN;
+    const int g = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * NPW + slot;
+    bool changed = false;
+    bool live = g < v.Nn;
+    int t = 0;
+    if (live) { t = v.T.tree[g]; live = v.status[t] == TQB_RUNNING; }
+    if (live)
+    {
+        const double tau = v.t_taufin[t];
+        const int nx = v.T.nx[g], nu = v.T.nu[g];
+        const bool root = v.T.dad[g] < 0;
+        if (e < nx)
+        {
+            const int i = v.T.xoff[g] + e;
+            if (!root) v.lam[i] += tau * v.dlam[i];
+            if (with_stage)
+            {
+                const double pold = v.P[i], winv = v.in.Qinv[i], lo = v.in.xmin[i], hi = v.in.xmax[i];
+                const double qm = v.qmod0[i] + tau * v.dq[i];
+                const double unc = winv * qm;
+                int mask;
+                const double val = clip_mask(unc, lo, hi, mask);
+                const double pnew = mask == 0 ? winv : 0.0;
+                changed = pnew != pold;
+                v.qmod0[i] = qm; v.x[i] = val; v.xUnc[i] = unc; v.P[i] = pnew;
+            }
+        }
+        else if (with_stage && e < nx + nu)
+        {
+            const int i = v.T.uoff[g] + e - nx;
+            const double pold = v.Rt[i], winv = v.in.Rinv[i], lo = v.in.umin[i], hi = v.in.umax[i];
+            const double rm = v.rmod0[i] + tau * v.dr[i];
+            const double unc = winv * rm;
+            int mask;
+            const double val = clip_mask(unc, lo, hi, mask);
+            const double pnew = mask == 0 ? winv : 0.0;
+            changed = pnew != pold;
+            v.rmod0[i] = rm; v.u[i] = val; v.uUnc[i] = unc; v.Rt[i] = pnew;
+        }
+        if (with_stage && e == 0) v.cmod0[g] += tau * v.dc[g];
+    }
+    if (with_stage)
+    {
+        const unsigned b = __ballot_sync(FULL, changed);
+        const unsigned grp = LPN == 32 ? 0xffffffffu : (((1u << LPN) - 1u) << (slot * LPN));
+        if (live && e == 0 && v.chg) v.chg[g] = (b & grp) != 0;
+    }
+}
