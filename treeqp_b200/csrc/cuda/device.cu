@@ -103,6 +103,7 @@ struct tqb_device
     /* small trees: the whole Newton loop in one persistent kernel, one CTA per tree (tdunes_small.cuh) */
     int affine_refresh;       /* > 0: stage QPs from the affine model, refreshed from lambda every so many iterations (k_step_affine) */
     int *d_flags;             /* chg | bdirty | breg per node (re-use of unchanged blocks) */
+    int *d_ghost;
     int skip_on;
     char *d_abstage;          /* staging of the strided [A | B] DMA copy (tqb_device_upload_ab_direct) */
     size_t abstage_bytes;
@@ -520,7 +521,13 @@ static int detect_fast_path(tqb_device *D, const int *h_int, const int *ghost)
          * maxIter = 7 iterate of spring_mass_tight leaves the 1e-5 band around the oracle's), so small trees keep recomputing
          * from lambda as the reference does. */
         if (!(ea && ea[0] == '1') && d->Nn / (d->nT > 0 ? d->nT : 1) < TQB_AFFINE_MIN_NODES) D->affine_refresh = 0;
-        if (ghost || NX + NU > 32) D->affine_refresh = 0; /* ghost cut nodes take their stage solution from the exchange */
+        if (NX + NU > 32) D->affine_refresh = 0;
+        if (ghost)
+        {   /* ghost cut nodes take their stage solution from the exchange: k_step_affine moves their multipliers only */
+            CK(cudaMalloc(&D->d_ghost, sizeof(int) * (size_t) d->Nn));
+            CK(cudaMemcpy(D->d_ghost, ghost, sizeof(int) * (size_t) d->Nn, cudaMemcpyHostToDevice));
+            D->v.ghost = D->d_ghost;
+        }
     }
     {   /* level descriptors (LvlDesc): one 48-byte record per parent in level order */
         const size_t n = (size_t) d->Np;
@@ -859,7 +866,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
     cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); cudaFree(D->d_leaf_desc); free(D->lvl_md); free(D->lvl_kp); free(D->chain_link);
-    cudaFree(D->d_abstage); cudaFree(D->d_flags);
+    cudaFree(D->d_abstage); cudaFree(D->d_flags); cudaFree(D->d_ghost);
     cudaFree(D->d_cut_nodes); cudaFree(D->d_send); cudaFree(D->d_recv); cudaFree(D->d_tred);
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
@@ -1371,7 +1378,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
         /* the step kernel of the last iteration has already formed this iteration's stage solution from the affine model,
          * except at iteration 0 and at every refresh */
-        const bool affine = D->fast && D->fast_stage && D->affine_refresh > 0 && !D->comm;
+        const bool affine = D->fast && D->fast_stage && D->affine_refresh > 0;
         if (!(affine && it % D->affine_refresh != 0))
         {
             if (launch_stage<0>(D, K_STAGE)) return 1;

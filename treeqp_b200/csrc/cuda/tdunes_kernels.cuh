@@ -46,6 +46,7 @@ struct View
      * chg = the node's own active set differs from the last Newton iteration (k_stage_fused<0>), bdirty = its block
      * was re-factored in this iteration (k_build_factor), breg = its last factorisation was regularised on the fly */
     int *chg, *bdirty, *breg;
+    const int *ghost; /* sharded local tree: cut nodes owned by another rank (their stage solution arrives with the exchange); else NULL */
     double *nva, *nvb, *cva, *cvb; /* per-node and per-chunk reduction scratch */
     /* per tree */
     int *status, *iter, *ls_cnt, *ls_active, *restart_cnt;

@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(256) k_step_affine(View v, int with_stage)
         const double tau = v.t_taufin[t];
         const int nx = v.T.nx[g], nu = v.T.nu[g];
         const bool root = v.T.dad[g] < 0;
+        if (v.ghost && v.ghost[g]) with_stage = 0; /* the multiplier moves everywhere, the stage solution comes from the owner */
         if (e < nx)
         {
             const int i = v.T.xoff[g] + e;
@@ -433,10 +434,9 @@ __global__ void __launch_bounds__(256) k_step_affine(View v, int with_stage)
         }
         if (with_stage && e == 0) v.cmod0[g] += tau * v.dc[g];
     }
-    if (with_stage)
     {
         const unsigned b = __ballot_sync(FULL, changed);
         const unsigned grp = LPN == 32 ? 0xffffffffu : (((1u << LPN) - 1u) << (slot * LPN));
-        if (live && e == 0 && v.chg) v.chg[g] = (b & grp) != 0;
+        if (live && with_stage && e == 0 && v.chg) v.chg[g] = (b & grp) != 0;
     }
 }
