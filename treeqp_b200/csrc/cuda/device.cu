@@ -100,6 +100,7 @@ struct tqb_device
     int *d_cut_nodes;
     double *d_send, *d_recv, *d_tred;
     const tqb_p2p_dev *p2p; /* peer mailboxes over NVLink; NULL: NCCL collectives */
+    int norm_on_cut;        /* sharded: the termination norm rides on the cut-node exchange */
     /* small trees: the whole Newton loop in one persistent kernel, one CTA per tree (tdunes_small.cuh) */
     int affine_refresh;       /* > 0: stage QPs from the affine model, refreshed from lambda every so many iterations (k_step_affine) */
     int *d_flags;             /* chg | bdirty | breg per node (re-use of unchanged blocks) */
@@ -1246,16 +1247,22 @@ extern "C" int tqb_device_enable_sharding(tqb_device *D, tqb_comm *comm, int cut
     D->v.t_red = D->d_tred;
     D->v.sharded = 1;
     {   /* peer mailboxes for the per-iteration exchanges (comm.cuh); NCCL stays as the fall-back */
-        size_t cap = per * (size_t) my_ncut, cap2 = (size_t) (1 + TQB_LS_NT) * D->dims.nT;
+        size_t cap = per * (size_t) my_ncut + (size_t) D->dims.nT, cap2 = (size_t) (1 + TQB_LS_NT) * D->dims.nT;
         if (cap2 > cap) cap = cap2;
         D->p2p = (ncut * per <= 65536 && tqb_comm_p2p_setup(comm, cap, D->stream) == 0) ? tqb_comm_p2p(comm) : NULL;
+        /* the termination norm rides on the cut exchange (one exchange less per Newton iteration): the ranks' partial
+         * norms over their subtrees travel behind the cut nodes, the replicated top is added by every rank itself.
+         * Needs the top to be the first local nodes (it keeps its numbering) and at least one replicated level. */
+        const char *en = getenv("TREEQP_B200_NORM_EXCHANGE");
+        D->norm_on_cut = (D->p2p && cut_depth >= 1 && cut_nodes_local[0] > 0 && !(en && en[0] == '1')) ? 1 : 0;
+        D->v.top_nodes = D->norm_on_cut ? cut_nodes_local[0] : 0;
     }
     return 0;
 }
 
 /* cut nodes -> every rank: one all-gather per Newton iteration, between the sweeps of the
  * subtrees (depth >= cut) and of the replicated top (depth < cut) */
-static int exchange_cut_nodes(tqb_device *D)
+static int exchange_cut_nodes(tqb_device *D, int is_max)
 {
     const int nx = D->f_nx;
     const size_t per = (size_t) nx * (nx + 3);
@@ -1263,8 +1270,14 @@ static int exchange_cut_nodes(tqb_device *D)
     if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
     if (D->p2p)
     {
+        if (D->norm_on_cut)
+        {   /* this rank's part of the termination norm over the subtrees below the cut rides along */
+            k_chunk_reduce<<<D->v.nchunk, 256, 0, D->stream>>>(D->v, D->v.nva, D->v.cva, is_max, D->v.top_nodes);
+            k_tree_partial<<<(D->dims.nT + 3) / 4, 128, 0, D->stream>>>(D->v, D->v.cva, D->d_tred, is_max);
+            D->launches += 2;
+        }
         k_cut_exchange<<<1, 512, 0, D->stream>>>(D->v, *D->p2p, tqb_comm_p2p_next_seq(D->comm), D->d_cut_nodes, D->my_cut0,
-                                                  D->my_ncut, D->ncut, nx);
+                                                  D->my_ncut, D->ncut, nx, D->norm_on_cut ? D->d_tred : NULL, D->dims.nT, is_max);
         if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
         D->launches++;
         return 0;
@@ -1393,7 +1406,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 if (exch)
                 {   /* the exchange is its own class: close the bracket around it */
                     sweep_end(D);
-                    if (exchange_cut_nodes(D)) return 1;
+                    if (exchange_cut_nodes(D, o->termCondition == 2)) return 1;
                     sweep_begin(D, K_FACTOR);
                 }
                 const int pre_ok = (l < Nh - 1 && !exch) ? 1 : 0;
@@ -1407,8 +1420,11 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 if (fused_factor_level(D, l, pre_ok)) { snprintf(g_err, sizeof g_err, "fused dispatch failed"); return 1; }
             }
             sweep_end(D);
-            LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
-            if (D->comm && allreduce_tree_sums(D, 1, 0, o->termCondition == 2)) return 1;
+            if (!(D->comm && D->norm_on_cut))
+            {
+                LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2, 0);
+                if (D->comm && allreduce_tree_sums(D, 1, 0, o->termCondition == 2)) return 1;
+            }
             LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
             if (peek_counter(D, 0, 4)) return 1;
             sweep_begin(D, K_BACK);
@@ -1428,7 +1444,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         else
         {
             LAUNCH(K_GRAD, k_gradient, cdiv(v.Nn, 8), 256, 0, v);
-            LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2);
+            LAUNCH(K_REDUCE, k_chunk_reduce, v.nchunk, 256, 0, v, v.nva, v.cva, o->termCondition == 2, 0);
             LAUNCH(K_DECIDE, k_decide_term, tgrid, 128, 0, v);
             if (peek_counter(D, 0, 4)) return 1;
 

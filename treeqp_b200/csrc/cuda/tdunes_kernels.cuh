@@ -58,6 +58,7 @@ struct View
      * [nT,2nT): dual function) instead of from this rank's chunk values */
     double *t_red;
     int sharded;
+    int top_nodes; /* sharded solve with the termination norm riding on the cut exchange: local nodes [0, top_nodes) are the replicated top */
     /* dense stage QPs (tdunes_dense.cuh): projectors P_k at hoff[k], dual terms of the dense nodes
      * of the current line-search trial; for a dense node the x-/u-space slots of P/Rt hold its
      * working set (-1, 0, +1) and those of xUnc/uUnc its bound multipliers */
@@ -383,11 +384,12 @@ __global__ void __launch_bounds__(256) k_gradient(View v)
 }
 
 /* fixed-shape reduction of a per-node array over each chunk of <=1024 consecutive nodes */
-__global__ void __launch_bounds__(256) k_chunk_reduce(View v, const double *src, double *dst, int is_max)
+__global__ void __launch_bounds__(256) k_chunk_reduce(View v, const double *src, double *dst, int is_max, int g_min = 0)
 {
     __shared__ double sh[256];
     const int c = blockIdx.x;
-    const int beg = v.T.chunk_beg[c], end = v.T.chunk_end[c];
+    /* g_min > 0 (sharded solve, termination norm taken before the cut exchange): nodes of the replicated top are left out */
+    const int beg = v.T.chunk_beg[c] > g_min ? v.T.chunk_beg[c] : g_min, end = v.T.chunk_end[c];
     double acc = 0.0;
     for (int g = beg + threadIdx.x; g < end; g += 256)
     {
@@ -489,10 +491,18 @@ __device__ __forceinline__ double *p2p_slot(const tqb_p2p_dev &x, int owner, uns
 }
 
 /* cut nodes -> every rank (k_cut_pack + all-gather + k_cut_unpack in one launch) */
+/* `tred` != NULL: the ranks' partial termination norms (nT values, the subtrees below the cut) ride along behind the cut
+ * nodes and are combined in rank order (max when is_max), saving the separate exchange after the sweep */
 __global__ void __launch_bounds__(512) k_cut_exchange(View v, tqb_p2p_dev x, unsigned long long seq, const int *cut_nodes,
-                                                      int my_cut0, int my_ncut, int ncut, int nx)
+                                                      int my_cut0, int my_ncut, int ncut, int nx, double *tred, int nT, int is_max)
 {
     const int per = nx * (nx + 3), nmine = my_ncut * per;
+    if (tred)
+        for (int e = threadIdx.x; e < nT; e += blockDim.x)
+        {
+            const double val = tred[e];
+            for (int r = 0; r < x.nranks; r++) p2p_slot(x, r, seq, x.rank)[nmine + e] = val;
+        }
     for (int e = threadIdx.x; e < nmine; e += blockDim.x)
     {
         const int w = e / per, i = e - w * per;
@@ -517,6 +527,17 @@ __global__ void __launch_bounds__(512) k_cut_exchange(View v, tqb_p2p_dev x, uns
         else if (i < 3 * nx) v.rsub[xo + i - 2 * nx] = val;
         else v.schur[(size_t) g * nx * nx + (i - 3 * nx)] = val;
     }
+    if (tred)
+        for (int e = threadIdx.x; e < nT; e += blockDim.x)
+        {
+            double acc = __ldcv(p2p_slot(x, x.rank, seq, 0) + nmine + e);
+            for (int r = 1; r < x.nranks; r++)
+            {
+                const double t = __ldcv(p2p_slot(x, x.rank, seq, r) + nmine + e);
+                acc = is_max ? fmax(acc, t) : acc + t;
+            }
+            tred[e] = acc;
+        }
 }
 
 /* in-place all-reduce of buf[0..count): the first `nmax` entries with max, the others as sums in rank
@@ -549,6 +570,10 @@ __global__ void k_decide_term(View v)
     if (t >= v.nT) return;
     if (v.status[t] != TQB_RUNNING) { if (lane == 0) v.ls_active[t] = 0; return; }
     double err = v.sharded ? v.t_red[t] : tree_reduce(v, v.cva, t, lane, v.o.termCondition == 2);
+    if (v.sharded && v.top_nodes > 0)
+    {   /* t_red came with the cut exchange (subtrees below the cut); the replicated top is every rank's own, in node order */
+        for (int g = 0; g < v.top_nodes; g++) err = (v.o.termCondition == 2) ? fmax(err, v.nva[g]) : err + v.nva[g];
+    }
     if (v.o.termCondition == 1) err = sqrt(err);
     if (lane == 0)
     {
