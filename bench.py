@@ -776,7 +776,10 @@ def roofline_block(prob, prof, world, depth):
            "note": "CUDA events on the solver's stream inside one extra solve: a pair around every launch, except that the "
                    "launches of one level sweep (k_build_factor / k_backsolve_fused, one launch per depth, chained with "
                    "programmatic dependent launch) share ONE pair -- avg_launch_us = sweep time / launches of the sweep, "
-                   "measured with the overlap the solver runs with; per_kernel_serialised = a pair around every single launch",
+                   "measured with the overlap the solver runs with; per_kernel_serialised = a pair around every single launch.  "
+                   "frac credits k_build_factor with the SURVEY 8d contract bytes (K2 + K3: Hessian blocks written and re-read), which the fused kernel never "
+                   "moves and which the re-use of unchanged blocks (27 of 29 iterations redo only right-hand sides on the wide levels) does not even "
+                   "compute: frac_dram (measured DRAM bytes of a whole solve over the same time) is the fraction of the memory system actually used",
            "per_kernel": per_kernel,
            "per_kernel_serialised": {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in sorted(prof.get("serialised", {}).items(), key=lambda kv: -kv[1][0])}}
     if top in ("k_build_factor", "k_factor_level"):
