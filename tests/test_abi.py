@@ -102,3 +102,18 @@ def test_recreate_on_same_memory_does_not_leak_contexts(product_lib):
     assert L.treeqp_b200_live_contexts() == n0
     s.destroy()
     assert L.treeqp_b200_live_contexts() == n0 - 1
+
+
+def test_host_register_without_gpu_fails_cleanly(product_lib):
+    """treeqp_b200_host_register page-locks a caller buffer through the CUDA runtime: without a device it reports
+    failure (non-zero) and the caller simply stays on the staged path; unregistering what was never registered is
+    harmless."""
+    import ctypes as C
+    L = product_lib.lib
+    if L.treeqp_b200_device_count() > 0:
+        pytest.skip("needs a box without a GPU")
+    buf = capi._Buf(1 << 21)
+    assert L.treeqp_b200_host_register(buf.ptr, C.c_size_t(buf.arr.size)) != 0
+    assert L.treeqp_b200_host_unregister(buf.ptr) != 0
+    assert L.treeqp_b200_host_unregister(None) == 0
+    assert buf.pin(product_lib) is False
