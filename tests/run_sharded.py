@@ -32,6 +32,9 @@ def main():
     failures = []
     for name, prob, opts in [("random_d%d" % depth, P.random_tree(P.binary_tree_nk(depth), 12, 4, seed=3, ubound=0.2), dict(maxIter=200)),
                              ("random_d7_u05", P.random_tree(P.binary_tree_nk(7), 12, 4, seed=1, ubound=0.5), dict(maxIter=200)),
+                             # infinity-norm termination: the ranks' partial norms ride on the cut exchange and are combined by max
+                             ("random_d8_maxnorm", P.random_tree(P.binary_tree_nk(8), 12, 4, seed=3, ubound=0.5), dict(maxIter=200, termCondition=2)),
+                             ("random_d8_2norm", P.random_tree(P.binary_tree_nk(8), 12, 4, seed=3, ubound=0.5), dict(maxIter=200, termCondition=1)),
                              # large enough for the DMA path: caller buffers page-locked, every rank moves its subtrees'
                              # levels as strided copies from / into them (and wide levels re-use unchanged blocks)
                              ("random_d14_pinned", P.random_tree(P.binary_tree_nk(14), 12, 4, seed=5, ubound=0.2), dict(maxIter=200))]:
