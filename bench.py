@@ -745,6 +745,13 @@ def roofline_block(prob, prof, world, depth):
     kern = prof["kernels"]
     fused = "k_build_factor" in kern
     cb = class_bytes(alg, fused)
+    if fused and "k_lambda_step" in kern and "k_stage_fused<0>" in kern and kern["k_stage_fused<0>"][1] < kern["k_lambda_step"][1]:
+        # large trees: k_step_affine (lambda step + next iteration's stage solution from the affine model, vectors only)
+        # on the iterations that are not refreshed by k_stage_fused<0>, a plain lambda step on the others
+        n_step, n_refresh = kern["k_lambda_step"][1], max(kern["k_stage_fused<0>"][1] - 2, 0)  # minus iteration 0 and the final clip-only pass
+        b_aff = 8 * int((10 * prob.nx + 10 * prob.nu + 2).sum())
+        b_plain = 8 * int(3 * prob.nx.sum())
+        cb["k_lambda_step"] = ((n_step - n_refresh) * b_aff + n_refresh * b_plain) / max(n_step, 1)
     lpc = launches_per_call(prob, cb)
     top = max((k for k in kern if k in cb), key=lambda k: kern[k][0])
     t_ms, n_launch = kern[top]
