@@ -348,3 +348,21 @@ def test_affine_stage_update_matches_recomputation(product_lib, monkeypatch):
     assert b.stats["kernel_launches"] < a.stats["kernel_launches"], "the affine step did not replace any stage pass"
     check_against(b, dict(x=a.x, u=a.u, lam=a.lam, mu_x=a.mu_x, mu_u=a.mu_u), prob, tol=1e-12)
     assert b.kkt < 1e-8
+
+
+def test_batch_of_large_trees_matches_individual_solves(product_lib):
+    """Two large trees as one forest: wide levels re-use unchanged blocks, the stage QPs come from the affine model
+    between refreshes, and one tree finishes earlier than the other (its blocks / nodes drop out at their status check).
+    Per tree exactly what treeqp_tdunes_solve returns for it alone."""
+    probs = [P.random_tree(P.binary_tree_nk(12), 12, 4, seed=21, ubound=0.2), P.random_tree(P.binary_tree_nk(12), 12, 4, seed=22, ubound=0.35)]
+    singles = [capi.solve_tdunes(product_lib, p, maxIter=200) for p in probs]
+    assert singles[0].iter != singles[1].iter, "the two trees should need different iteration counts"
+    qp_ins = [capi.QpIn(product_lib, p) for p in probs]
+    qp_outs = [capi.QpOut(product_lib, p) for p in probs]
+    batch = capi.TdunesBatch(product_lib, qp_ins, maxIter=200)
+    assert batch.solve(qp_outs) == capi.TREEQP_OK
+    for i, (s, o) in enumerate(zip(singles, qp_outs)):
+        assert batch.status[i] == s.status == 0 and o.iter == s.iter, i
+        for k in ("x", "u", "lam", "mu_x", "mu_u"):
+            assert np.array_equal(getattr(o, k), getattr(s, k)), (i, k)
+    batch.destroy()
