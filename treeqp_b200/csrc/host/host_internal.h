@@ -250,6 +250,7 @@ typedef struct tqb_shard_plan
     struct node *ltree;        /* [Nl] local tree (kids point into lkids) */
     int *lkids;
     int *lnx, *lnu, *lnc;      /* [Nl] */
+    long long *lam_off;        /* [Nl] offset of local node j's multiplier in the caller's full lambda vector (filled on first use) */
 } tqb_shard_plan;
 
 /* returns NULL (with a message on stderr) if the tree cannot be cut for this number of ranks */

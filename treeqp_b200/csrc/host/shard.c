@@ -107,7 +107,7 @@ void tqb_shard_plan_destroy(tqb_shard_plan *p)
 {
     if (!p) return;
     free(p->gmap); free(p->ghost); free(p->owned); free(p->ltree); free(p->lkids);
-    free(p->lnx); free(p->lnu); free(p->lnc);
+    free(p->lnx); free(p->lnu); free(p->lnc); free(p->lam_off);
     free(p);
 }
 
@@ -144,17 +144,20 @@ void tqb_forest_set_lambda0_sharded(tqb_forest *f, const double *lambda_full, co
                                     const tqb_shard_plan *plan)
 {
     const tqb_tables *T = &f->ht;
-    /* offset of node k's multiplier in the caller's vector: sum of nx over nodes 1..k-1 */
-    long long *off = (long long *) malloc(sizeof(long long) * (size_t) (full_qp->N + 1));
-    off[0] = 0; off[1] = 0;
-    for (int k = 1; k < full_qp->N; k++) off[k + 1] = off[k] + full_qp->nx[k];
-    for (int j = 0; j < plan->Nl; j++)
-    {
-        const int g = plan->gmap[j], nx = plan->lnx[j];
-        if (j == 0) { for (int i = 0; i < nx; i++) f->hin.lam0[T->xoff[0] + i] = 0.0; continue; }
-        memcpy(f->hin.lam0 + T->xoff[j], lambda_full + off[g], sizeof(double) * (size_t) nx);
+    tqb_shard_plan *pl = (tqb_shard_plan *) plan; /* the offsets are a cache inside the plan */
+    if (!pl->lam_off)
+    {   /* offset of node k's multiplier in the caller's vector: sum of nx over nodes 1..k-1; kept per local node */
+        long long *off = (long long *) malloc(sizeof(long long) * (size_t) (full_qp->N + 1));
+        off[0] = 0; off[1] = 0;
+        for (int k = 1; k < full_qp->N; k++) off[k + 1] = off[k] + full_qp->nx[k];
+        pl->lam_off = (long long *) malloc(sizeof(long long) * (size_t) (plan->Nl > 0 ? plan->Nl : 1));
+        for (int j = 0; j < plan->Nl; j++) pl->lam_off[j] = off[plan->gmap[j]];
+        free(off);
     }
-    free(off);
+    for (int i = 0; i < plan->lnx[0]; i++) f->hin.lam0[T->xoff[0] + i] = 0.0;
+#pragma omp parallel for schedule(static) if (plan->Nl > 4096)
+    for (int j = 1; j < plan->Nl; j++)
+        memcpy(f->hin.lam0 + T->xoff[j], lambda_full + pl->lam_off[j], sizeof(double) * (size_t) plan->lnx[j]);
 }
 
 void tqb_forest_unpack_sharded(const tqb_forest *f, const tqb_shard_plan *plan, tree_qp_out *out)
