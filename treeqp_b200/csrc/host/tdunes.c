@@ -279,13 +279,6 @@ void treeqp_tdunes_get_stats(const treeqp_tdunes_workspace *work, treeqp_b200_st
 
 /* ------------------------------------------------------------------------------- solve ---- */
 
-static return_t forest_upload(tqb_forest *f)
-{
-    if (tqb_device_upload(f->dev, f->h_in, f->dims.n_in, &f->h2d_ms)) return TREEQP_UNKNOWN_ERROR;
-    f->h2d_bytes = (long long) sizeof(double) * f->dims.n_in;
-    return TREEQP_OK;
-}
-
 static return_t forest_solve(tqb_forest *f, const tqb_opts *o)
 {
     if (tqb_device_solve(f->dev, o, f->h_status, f->h_iter, f->ls_iters, &f->ls_total, &f->n_reg,
@@ -732,8 +725,10 @@ return_t treeqp_tdunes_sharded_solve_resident(treeqp_tdunes_sharded *sh)
     if (!sh->opts_ok) return TREEQP_INVALID_OPTION;
     if (!sh->uploaded) return TREEQP_UNKNOWN_ERROR;
     if (sh->lam_dirty)
-    {
-        if (forest_upload(sh->forest) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
+    {   /* a new dual start was set on the host: send that vector only (after a DMA-mode upload the pinned block does
+         * not even hold the other inputs of the nodes that travelled straight from the caller's buffer) */
+        if (tqb_forest_upload_lambda0(sh->forest)) return TREEQP_UNKNOWN_ERROR;
+        sh->forest->h2d_bytes = (long long) sizeof(double) * sh->forest->dims.X;
         sh->lam_dirty = 0;
     }
     if (forest_solve(sh->forest, &sh->o) != TREEQP_OK) return TREEQP_UNKNOWN_ERROR;
