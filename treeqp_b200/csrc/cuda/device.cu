@@ -9,6 +9,7 @@
  * launching.
  */
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -923,10 +924,12 @@ extern "C" int tqb_device_upload_end(tqb_device *D, double *ms_total)
  * the page size (posix_memalign(4096); the Python wrapper allocates its buffers that way). */
 #define TQB_PIN_SLOTS 16
 static struct { const char *lo, *hi; } g_pin[TQB_PIN_SLOTS];
+static std::mutex g_pin_mu; /* solvers of several host threads share the table */
 
 extern "C" int tqb_host_register(const void *base, size_t bytes)
 {
     if (!base || bytes == 0) return 1;
+    std::lock_guard<std::mutex> lock(g_pin_mu);
     const uintptr_t pg = 4096;
     const char *lo = (const char *) (((uintptr_t) base + pg - 1) & ~(pg - 1)), *hi = (const char *) (((uintptr_t) base + bytes) & ~(pg - 1));
     if (hi <= lo) return 1;
@@ -954,6 +957,7 @@ extern "C" int tqb_host_register(const void *base, size_t bytes)
 
 extern "C" int tqb_host_unregister(const void *base)
 {   /* the range that holds `base` or starts within one page behind it (an unaligned buffer's first whole page) */
+    std::lock_guard<std::mutex> lock(g_pin_mu);
     int rc = 1;
     for (int i = 0; i < TQB_PIN_SLOTS; i++)
         if (g_pin[i].lo && (const char *) base + 4096 > g_pin[i].lo && (const char *) base < g_pin[i].hi)
@@ -969,6 +973,7 @@ extern "C" int tqb_host_unregister(const void *base)
 extern "C" int tqb_host_pin(const void *base, size_t bytes)
 {
     if (bytes == 0) return 0;
+    std::lock_guard<std::mutex> lock(g_pin_mu);
     const char *lo = (const char *) base, *hi = lo + bytes;
     for (int i = 0; i < TQB_PIN_SLOTS; i++)
         if (g_pin[i].lo && lo >= g_pin[i].lo && hi <= g_pin[i].hi) return 1;
@@ -977,6 +982,7 @@ extern "C" int tqb_host_pin(const void *base, size_t bytes)
 
 extern "C" void tqb_host_unpin_all(void)
 {
+    std::lock_guard<std::mutex> lock(g_pin_mu);
     for (int i = 0; i < TQB_PIN_SLOTS; i++)
     {
         if (g_pin[i].lo && cudaHostUnregister((void *) g_pin[i].lo) != cudaSuccess) cudaGetLastError();
