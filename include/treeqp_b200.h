@@ -11,7 +11,8 @@
  * function has the reference's exact signature and return codes.
  *
  * The ABI corresponds to the reference's default build: PROFILE=0 (no `timings` member in the
- * workspace, dual_Newton_tree.h:146-148) and BLASFEO HIGH_PERFORMANCE (panel-major matrices).
+ * workspace, dual_Newton_tree.h:146-148) and BLASFEO HIGH_PERFORMANCE (panel-major matrices); compiled with
+ * -DPROFILE=1..3 this header is the PROFILE > 0 layout, served by libtreeqp_b200_profile3.so (section 4, timers).
  *
  * Sections
  *   1. BLASFEO-compatible matrix/vector views          (blasfeo_common.h:46-89)
@@ -243,7 +244,34 @@ typedef struct treeqp_tdunes_opts_t_
     int lineSearchRestartTrigger;
 } treeqp_tdunes_opts_t;
 
-/* dual_Newton_tree.h:91-150 (PROFILE=0).  Field order is the reference's; on this
+#if defined(PROFILE) && PROFILE > 0
+/* utils/profiling.h:38-68, field for field (which members exist depends on the PROFILE level, as in the reference) */
+typedef struct treeqp_profiling_t_
+{
+    int num_iter;
+    int run_indx;
+    double total_time;      /* PROFILE > 0: seconds of the last solve, minimum over the runs, trials of the first run */
+    double min_total_time;
+    int total_ls_iter;
+#if PROFILE > 1
+    double *iter_times;     /* per Newton iteration (NaN beyond the last one) */
+    double *min_iter_times;
+    int *ls_iters;
+#endif
+#if PROFILE > 2
+    double *stage_qps_times;
+    double *min_stage_qps_times;
+    double *build_dual_times;
+    double *min_build_dual_times;
+    double *newton_direction_times;
+    double *min_newton_direction_times;
+    double *line_search_times;
+    double *min_line_search_times;
+#endif
+} treeqp_profiling_t;
+#endif
+
+/* dual_Newton_tree.h:91-150.  Field order is the reference's; on this
  * implementation only the members marked [host] are valid host memory after `create`, the
  * iterates live in HBM and are reached through the context stored in stage_qp_data[0]. */
 typedef struct treeqp_tdunes_workspace_
@@ -291,6 +319,9 @@ typedef struct treeqp_tdunes_workspace_
     struct blasfeo_dvec *sxasPrev;
     struct blasfeo_dvec *suasPrev;
     struct blasfeo_dmat *sWdiag;
+#if defined(PROFILE) && PROFILE > 0
+    treeqp_profiling_t timings; /* dual_Newton_tree.h:146-148: only in the PROFILE > 0 build (libtreeqp_b200_profile3.so) */
+#endif
 } treeqp_tdunes_workspace;
 
 #endif /* TREEQP_SRC_DUAL_NEWTON_TREE_H_ */
@@ -324,12 +355,24 @@ return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
 void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct node *tree,
                            treeqp_tdunes_workspace *work);
 
-/* PROFILE > 0 is NOT supported: the workspace structs above are the PROFILE = 0 layout (the reference adds
- * a trailing `timings` member otherwise, dual_Newton_tree.h:146-148).  A caller compiled with PROFILE > 0
- * binds timers_print / timers_write_to_txt (utils/profiling.h:75-77) to this library, which stops the
- * program with a message rather than let it print timers nobody filled. */
+/* PROFILE > 0 (Makefile.rule:112-119): the reference's workspace structs grow a trailing `timings` member and its solve fills
+ * it (utils/profiling.h:38-68).  The default library is the PROFILE = 0 ABI: a caller compiled with PROFILE > 0 that links it
+ * binds timers_print / timers_write_to_txt here and is stopped with a message rather than allowed to print timers nobody
+ * filled.  `make -C treeqp_b200/csrc profile3` builds libtreeqp_b200_profile3.so with -DPROFILE=3: the same solvers, the
+ * PROFILE = 3 struct layout, and `timings` fed from CUDA events around every launch (which serialises the launches, as the
+ * reference's own timers perturb its run): per Newton iteration the four phase times, the iteration time, the line-search
+ * trial count; total_time and the minima over repeated runs as utils/profiling.c keeps them. */
+#if defined(PROFILE) && PROFILE > 0
+int timers_calculate_size(int num_iter);
+void timers_create(int num_iter, treeqp_profiling_t *timings, void *ptr);
+void timers_initialize(treeqp_profiling_t *timings);
+void timers_update(treeqp_profiling_t *timings);
+void timers_print(treeqp_profiling_t *timings);
+void timers_write_to_txt(treeqp_profiling_t *timings);
+#else
 void timers_print(void *timings);
 void timers_write_to_txt(void *timings);
+#endif
 
 /* ------------------------------------------------------------------------------------------
  * 4b. SDUNES: dual Newton strategy on the scenario decomposition (dual_Newton_scenarios.h:49-163)
@@ -419,6 +462,9 @@ typedef struct treeqp_sdunes_workspace_
     struct blasfeo_dvec **sxasPrev;
     struct blasfeo_dvec **suasPrev;
     struct blasfeo_dmat **sTmpLambdaD;
+#if defined(PROFILE) && PROFILE > 0
+    treeqp_profiling_t timings; /* dual_Newton_scenarios.h:135-137 */
+#endif
 } treeqp_sdunes_workspace;
 
 #endif /* TREEQP_SRC_DUAL_NEWTON_SCENARIOS_H_ */

@@ -111,3 +111,86 @@ def test_scenarios_example_runs_on_the_gpu(tmp_path):
     assert np.abs(u[:, 0, :] - u[0, 0, :]).max() < 1e-8
     assert np.all(u <= 1.0 + 1e-12) and np.all(u >= -1.0 - 1e-12)
     assert np.isfinite(x).all() and np.isfinite(np.loadtxt(d / "muIter.txt")).all()
+
+
+# ---- PROFILE = 3 callers (Makefile.rule:112-113): the workspace structs carry the reference's `timings` member and the drivers
+# print it.  They link libtreeqp_b200_profile3.so (same solvers, PROFILE = 3 struct layout, timers fed from CUDA events).
+TREE_P3, SCEN_P3 = TREE + "_p3", SCEN + "_p3"
+
+
+@pytest.mark.parametrize("exe", [TREE_P3, SCEN_P3])
+def test_profile3_examples_bind_to_the_profile3_library(exe):
+    _build()
+    if not os.path.exists(exe):
+        pytest.skip("PROFILE = 3 drop-in not built")
+    nm = subprocess.check_output(["nm", exe], text=True)
+    table = {ln.split()[-1]: ln.split()[-2] for ln in nm.splitlines() if len(ln.split()) >= 2}
+    base = TREE if exe == TREE_P3 else SCEN
+    for sym in SOLVER_SYMS[base] + ["timers_print"]:
+        assert table.get(sym) == "U", (sym, table.get(sym))
+    assert "libtreeqp_b200_profile3.so" in subprocess.check_output(["readelf", "-d", exe], text=True)
+    assert not re.search(r"libtreeqp\.a\((dual_Newton|profiling)", open(exe + ".map").read())
+    # the default library, linked by a PROFILE > 0 caller by mistake, stops the program instead of printing garbage
+    prod = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ROOT, "treeqp_b200", "lib", "libtreeqp_b200_profile3.so")], text=True)
+    exported = {ln.split()[-1] for ln in prod.splitlines() if ln.split()}
+    assert {"timers_print", "timers_write_to_txt", "timers_create", "timers_update", "timers_calculate_size"} <= exported
+
+
+def test_profile3_struct_layout_matches_reference():
+    """sizeof of the PROFILE = 3 workspaces and the offset of `timings` as gcc sees them through our header and through the
+    reference's: the caller's compiled-in layout is what the library writes into"""
+    if not os.path.isdir("/root/reference/treeqp"):
+        pytest.skip("needs the reference headers")
+    import tempfile
+    src_ours = '#include <stdio.h>\n#include <stddef.h>\n#include "treeqp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(treeqp_tdunes_workspace), offsetof(treeqp_tdunes_workspace, timings), sizeof(treeqp_sdunes_workspace), offsetof(treeqp_sdunes_workspace, timings), sizeof(treeqp_profiling_t));return 0;}\n'
+    src_ref = '#include <stdio.h>\n#include <stddef.h>\n#include "treeqp/src/dual_Newton_tree.h"\n#include "treeqp/src/dual_Newton_scenarios.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(treeqp_tdunes_workspace), offsetof(treeqp_tdunes_workspace, timings), sizeof(treeqp_sdunes_workspace), offsetof(treeqp_sdunes_workspace, timings), sizeof(treeqp_profiling_t));return 0;}\n'
+    outs = []
+    with tempfile.TemporaryDirectory() as td:
+        for name, src, inc in (("ours", src_ours, ["-I" + os.path.join(ROOT, "include")]),
+                               ("ref", src_ref, ["-I/root/reference", "-I/root/reference/external", "-I/root/reference/external/blasfeo/include",
+                                                 "-I" + os.path.join(ROOT, "oracle", "_ref", "include")])):
+            c = os.path.join(td, name + ".c")
+            open(c, "w").write(src)
+            exe = os.path.join(td, name)
+            subprocess.check_call(["gcc", "-DPROFILE=3", "-w", c, "-o", exe] + inc)
+            outs.append(subprocess.check_output([exe], text=True).split())
+    assert outs[0] == outs[1], outs
+
+
+def _run_p3(exe, tmp_path):
+    r = subprocess.run([exe], cwd=tmp_path, env=dict(os.environ), capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+@pytest.mark.gpu
+def test_profile3_tree_example_prints_gpu_timers(tmp_path):
+    if not os.path.exists(TREE_P3):
+        pytest.skip("PROFILE = 3 drop-in not built")
+    d = _workdir(tmp_path)
+    out = _run_p3(TREE_P3, tmp_path)
+    assert "Maximum error in KKT residuals (tdunes)" in out          # the example's own KKT assert passed (rc 0)
+    g = CS.golden("spring_mass_cfg1")
+    m = re.search(r"algorithm converged in \((\d+) it\):\s+([0-9.]+) ms", out)
+    assert m and int(m.group(1)) == int(g["iter"]) and float(m.group(2)) > 0.0
+    assert out.count("Iteration #") == int(g["iter"])
+    for phase in ("solved stage QPs in", "built dual problem in", "calculated Newton direction in", "performed line-search"):
+        mm = re.search(re.escape(phase) + r".*?:\s+([0-9.]+) ms", out)
+        assert mm and float(mm.group(1)) > 0.0, phase
+    # the files the reference's write_solution_to_txt adds under PROFILE = 3 (utils/print.c:312-345)
+    ls = np.loadtxt(d / "ls_iters.txt")
+    assert ls[:int(g["iter"])].sum() > 0
+    st = np.loadtxt(d / "newton_direction_times.txt")
+    assert np.all(st[:int(g["iter"])] > 0.0) and np.isnan(st[int(g["iter"])])
+    assert CS.rel_err(np.loadtxt(d / "x_opt.txt"), g["x"]) < 1e-10
+
+
+@pytest.mark.gpu
+def test_profile3_scenarios_example_prints_gpu_timers(tmp_path):
+    if not os.path.exists(SCEN_P3):
+        pytest.skip("PROFILE = 3 drop-in not built")
+    _workdir(tmp_path)
+    out = _run_p3(SCEN_P3, tmp_path)
+    m = re.search(r"algorithm converged in \((\d+) it\):\s+([0-9.]+) ms", out)
+    assert m and int(m.group(1)) > 0 and float(m.group(2)) > 0.0
+    assert "calculated Newton direction in" in out

@@ -66,6 +66,8 @@ struct tqb_device
     cudaEvent_t *pev; /* profiling event pool (pairs) */
     unsigned char *pev_class;
     unsigned short *pev_cnt; /* launches an event pair brackets */
+    unsigned short *pev_iter; /* Newton iteration an event pair belongs to (65535: before / after the loop) */
+    int cur_it;
     int pev_n, pev_on;
     int in_sweep, sweep_launches, sweep_pe; /* profiling level 2: ONE event pair around a PDL-chained level sweep */
     tqb_dims dims;
@@ -115,6 +117,13 @@ struct tqb_device
 };
 
 extern "C" const char *tqb_cuda_last_error(void) { return g_err; }
+
+/* event pair `pe` brackets a launch of class `cls` of the Newton iteration being enqueued */
+static inline void pev_tag(tqb_device *D, int pe, int cls)
+{
+    D->pev_class[pe] = (unsigned char) cls;
+    D->pev_iter[pe] = (unsigned short) (D->cur_it < 65535 ? D->cur_it : 65535);
+}
 
 #ifdef TQB_BF_TIMING
 /* debug builds only: the phase stamps of k_build_factor (tdunes_fused.cuh), 32 slots x 16 values */
@@ -219,7 +228,7 @@ static int launch_bf(tqb_device *D, int begin, int cnt, int kp, int pre_ok)
     }
     const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (D->in_sweep) D->sweep_launches++;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_FACTOR); }
     /* wide levels try to re-use the factorisation of blocks whose subtree kept its active set; on narrow levels almost
      * every block has a changed descendant, and the build of a full block should start before the kids' level ends.
      * Sharded solves: a wide level lies below the cut, where every block and all its kids are this rank's own (ghost
@@ -238,7 +247,7 @@ static int launch_bs(tqb_device *D, int begin, int cnt)
     const int wpb = 4;
     const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (D->in_sweep) D->sweep_launches++;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_BACK); }
     CK(launch_pdl(k_backsolve_fused<NX, MD>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, begin, cnt));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
@@ -265,7 +274,7 @@ static int launch_bs_tma(tqb_device *D, int begin, int cnt)
     const int full = (cnt + 3) / 4, res = D->n_sm_all * per_sm, grid = full < res ? full : res;
     const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (D->in_sweep) D->sweep_launches++;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_BACK); }
     CK(launch_pdl(k_backsolve_tma<NX, MD>, dim3(grid), dim3(128), smem, D->stream, pe_ < 0, D->v, begin, cnt));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
@@ -286,7 +295,7 @@ static int launch_bf_chain(tqb_device *D, int top_begin, int cnt, int nlev, int 
     }
     const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (D->in_sweep) D->sweep_launches++;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_FACTOR); }
     CK(launch_pdl(k_build_factor_chain<NX, NU>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
                   D->v, top_begin, cnt, nlev, kp_bottom, pre_ok));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
@@ -300,7 +309,7 @@ static int launch_bs_chain(tqb_device *D, int top_begin, int cnt, int nlev)
     const int wpb = 4;
     const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (D->in_sweep) D->sweep_launches++;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_BACK); }
     CK(launch_pdl(k_backsolve_chain<NX>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, top_begin, cnt, nlev));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
@@ -315,7 +324,7 @@ static int launch_bf_chain2(tqb_device *D, int top_begin, int cnt, int nlev, int
     const size_t smem = (size_t) wpb * 2 * Cfg::SMEM * sizeof(double);
     const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (D->in_sweep) D->sweep_launches++;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_FACTOR; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_FACTOR); }
     CK(launch_pdl(k_build_factor_chain2<NX, NU>, dim3((warps + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
                   D->v, top_begin, cnt, nlev, kp_bottom, pre_ok));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
@@ -329,7 +338,7 @@ static int launch_bs_chain2(tqb_device *D, int top_begin, int cnt, int nlev)
     const int wpb = 4, warps = (cnt + 1) / 2;
     const int pe_ = (D->pev_on && !D->in_sweep && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
     if (D->in_sweep) D->sweep_launches++;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_BACK; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_BACK); }
     CK(launch_pdl(k_backsolve_chain2<NX>, dim3((warps + wpb - 1) / wpb), dim3(32 * wpb), 0, D->stream, pe_ < 0, D->v, top_begin, cnt, nlev));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
@@ -694,7 +703,7 @@ static int detect_small_path(tqb_device *D, const int *h_int, const int *ghost)
 static int launch_small(tqb_device *D)
 {
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_SMALL; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_SMALL); }
     int done = 0;
 #define X(a, b, c) if (D->f_nx == a && D->f_nu == b) { k_tdunes_small<a, b, c><<<D->dims.nT, 32 * D->small_warps, D->small_smem, D->stream>>>(D->v, D->small_plan); done = 1; }
     TQB_SMALL_LIST(X)
@@ -721,7 +730,7 @@ static int launch_stage(tqb_device *D, int cls)
             const int PB = (a + b <= 16 && a <= 8) ? D->pair_begin : Np;                                        \
             const int warps = PB + (Np - PB + 1) / 2 + (D->nleaf + lpw - 1) / lpw;                     \
             const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;                \
-            if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = cls; }    \
+            if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, cls); }    \
             static int per_sm = 0;                                                                     \
             if (per_sm == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stage_fused<a, b, MODE>, 32 * wpb, 0) != cudaSuccess) per_sm = 2; \
             const int res = D->stage_grid > 0 ? D->stage_grid : D->n_sm * per_sm;                      \
@@ -736,7 +745,7 @@ static int launch_stage(tqb_device *D, int cls)
         return 1;
     }
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = cls; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, cls); }
     k_stage<MODE><<<(v.Nn + D->wpb_stage - 1) / D->wpb_stage, 32 * D->wpb_stage, D->sm_stage, D->stream>>>(v);
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
     D->launches++;
@@ -873,7 +882,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (D->h_counters) cudaFreeHost(D->h_counters);
     if (D->ev0) cudaEventDestroy(D->ev0);
     if (D->ev1) cudaEventDestroy(D->ev1);
-    if (D->pev) { for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) cudaEventDestroy(D->pev[i]); free(D->pev); free(D->pev_class); free(D->pev_cnt); }
+    if (D->pev) { for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) cudaEventDestroy(D->pev[i]); free(D->pev); free(D->pev_class); free(D->pev_cnt); free(D->pev_iter); }
     if (D->d_kkt) cudaFree(D->d_kkt);
     if (D->stream) cudaStreamDestroy(D->stream);
     free(D->lvl_ptr);
@@ -1194,6 +1203,30 @@ extern "C" int tqb_device_download(tqb_device *D, double *h_out, double *ms)
 }
 
 /* KKT residual of every tree from the resident iterates (k_kkt): h_kkt[nT] */
+/* Per Newton iteration, the event time of the last profiled solve (tqb_set_profiling(1)) under the reference's four
+ * phase names (utils/profiling.h:58-68), in seconds: ph[0..n) solve_stage_problems (k_stage*<0>), ph[n..2n) build_dual_problem
+ * (k_gradient, k_hessian, reductions, termination test; on the fused path gradient and Hessian live inside k_build_factor and
+ * are counted with the Newton direction), ph[2n..3n) calculate_delta_lambda (factorisation + substitutions, exchanges),
+ * ph[3n..4n) line_search (direction model, trials, Armijo, step).  Returns the number of iterations that have entries. */
+extern "C" int tqb_device_iter_phase_times(tqb_device *D, double *ph, int n)
+{
+    static const signed char phase_of[K_NCLASS] = {/*K_INIT*/ -1, /*K_STAGE*/ 0, /*K_GRAD*/ 1, /*K_REDUCE*/ 1, /*K_DECIDE*/ 3, /*K_HESS*/ 1,
+                                                   /*K_FACTOR*/ 2, /*K_BACK*/ 2, /*K_DIR*/ 3, /*K_TRIAL*/ 3, /*K_STEP*/ 3, /*K_FINISH*/ -1,
+                                                   /*K_COMM*/ 2, /*K_SMALL*/ 2};
+    for (int i = 0; i < 4 * n; i++) ph[i] = 0.0;
+    int last = -1;
+    for (int i = 0; i < D->pev_n; i++)
+    {
+        const int it = D->pev_iter[i], p = phase_of[D->pev_class[i]];
+        if (it >= n || p < 0) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, D->pev[2 * i], D->pev[2 * i + 1]) != cudaSuccess) continue;
+        ph[p * n + it] += 1e-3 * t;
+        if (it > last) last = it;
+    }
+    return last + 1;
+}
+
 extern "C" int tqb_device_kkt(tqb_device *D, double *h_kkt)
 {
     const int nT = D->dims.nT;
@@ -1209,7 +1242,7 @@ extern "C" int tqb_device_kkt(tqb_device *D, double *h_kkt)
 #define LAUNCH(cls, kern, grid, block, smem, ...)                                          \
     do {                                                                                   \
         const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;        \
-        if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = (cls); } \
+        if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, (cls)); } \
         kern<<<(grid), (block), (smem), D->stream>>>(__VA_ARGS__);                         \
         if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);                     \
         D->launches++;                                                                     \
@@ -1221,7 +1254,7 @@ static void sweep_begin(tqb_device *D, int cls)
 {
     if (D->pev_on != 2 || D->pev_n >= TQB_MAX_EVENTS) return;
     D->sweep_pe = D->pev_n++;
-    D->pev_class[D->sweep_pe] = (unsigned char) cls;
+    pev_tag(D, D->sweep_pe, cls);
     D->in_sweep = 1; D->sweep_launches = 0;
     cudaEventRecord(D->pev[2 * D->sweep_pe], D->stream);
 }
@@ -1273,7 +1306,7 @@ static int exchange_cut_nodes(tqb_device *D, int is_max)
     const int nx = D->f_nx;
     const size_t per = (size_t) nx * (nx + 3);
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_COMM); }
     if (D->p2p)
     {
         if (D->norm_on_cut)
@@ -1302,7 +1335,7 @@ static int allreduce_tree_sums(tqb_device *D, int use_a, int use_b, int a_is_max
     View &v = D->v;
     const int nT = D->dims.nT, grid = (nT + 3) / 4;
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_COMM); }
     if (use_a) { k_tree_partial<<<grid, 128, 0, D->stream>>>(v, v.cva, D->d_tred, a_is_max); D->launches++; }
     if (use_b) { k_tree_partial<<<grid, 128, 0, D->stream>>>(v, v.cvb, D->d_tred + nT, 0); D->launches++; }
     int rc = 0;
@@ -1329,7 +1362,7 @@ static int allreduce_ls_batch(tqb_device *D, int first)
     View &v = D->v;
     const int nT = D->dims.nT;
     const int pe_ = (D->pev_on && D->pev_n < TQB_MAX_EVENTS) ? D->pev_n++ : -1;
-    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); D->pev_class[pe_] = K_COMM; }
+    if (pe_ >= 0) { cudaEventRecord(D->pev[2 * pe_], D->stream); pev_tag(D, pe_, K_COMM); }
     k_tree_partial_ls<<<dim3((nT + 3) / 4, 1 + TQB_LS_NT), 128, 0, D->stream>>>(v, D->d_tred);
     D->launches++;
     const size_t off = first ? 0 : (size_t) nT;
@@ -1366,6 +1399,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         D->pev = (cudaEvent_t *) calloc(2 * TQB_MAX_EVENTS, sizeof(cudaEvent_t));
         D->pev_class = (unsigned char *) calloc(TQB_MAX_EVENTS, 1);
         D->pev_cnt = (unsigned short *) calloc(TQB_MAX_EVENTS, sizeof(unsigned short));
+        D->pev_iter = (unsigned short *) calloc(TQB_MAX_EVENTS, sizeof(unsigned short));
         for (int i = 0; i < 2 * TQB_MAX_EVENTS; i++) CK(cudaEventCreate(&D->pev[i]));
     }
     View &v = D->v;
@@ -1375,6 +1409,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     const int tgrid = cdiv(nT, 4);
     D->launches = 0;
 
+    D->cur_it = 65535;
     CK(cudaEventRecord(D->ev0, D->stream));
     {
         int n = v.X > nT ? v.X : nT;
@@ -1387,14 +1422,16 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
     /* Host round trips: ONE per Newton iteration (after the first line-search batch).  The
      * termination counter is fetched asynchronously and everything behind the termination test is
      * enqueued at once: kernels of a finished tree return at their status check. */
-    if (D->small && !D->comm)
-    {   /* small trees: the Newton loop of every tree runs inside one persistent CTA */
+    if (D->small && !D->comm && D->pev_on != 1)
+    {   /* small trees: the Newton loop of every tree runs inside one persistent CTA (not under per-launch profiling, whose
+         * per-iteration phase times -- the PROFILE > 0 build's timers -- need the launches) */
         if (launch_small(D)) { snprintf(g_err, sizeof g_err, "small-tree dispatch failed"); return 1; }
     }
     else
     for (int it = 0; it < o->maxIter; it++)
     {
         CK(cudaMemsetAsync(v.counters, 0, sizeof(int) * 2, D->stream));
+        D->cur_it = it;
         /* the step kernel of the last iteration has already formed this iteration's stage solution from the affine model,
          * except at iteration 0 and at every refresh */
         const bool affine = D->fast && D->fast_stage && D->affine_refresh > 0;
@@ -1508,6 +1545,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
         else if (v.nxmax <= 32) LAUNCH(K_STEP, k_lambda_step_w<32>, cdiv(v.Nn, 8), 256, 0, v);
         else LAUNCH(K_STEP, k_lambda_step, cdiv(v.Nn, 256), 256, 0, v);
     }
+    D->cur_it = 65535;
     /* trees that ran out of iterations: x,u of the last trial point (what the reference holds) */
     if (launch_stage<3>(D, K_STAGE)) return 1;
     LAUNCH(K_DECIDE, k_finalize_status, cdiv(nT, 256), 256, 0, v);

@@ -214,6 +214,7 @@ int tqb_device_finish_direct_upload(tqb_device *d, long long lam0_off, int lam0_
 int tqb_device_download_begin(tqb_device *d);
 int tqb_device_download_end(tqb_device *d, double *ms);
 int tqb_device_kkt(tqb_device *d, double *h_kkt);
+int tqb_device_iter_phase_times(tqb_device *d, double *ph, int n);
 /* the whole Newton loop; fills h_status/h_iter (pinned, nT) */
 int tqb_device_solve(tqb_device *d, const tqb_opts *o, int *h_status, int *h_iter,
                      int *ls_iters256, int *ls_total, int *n_reg, double *gpu_ms, long long *launches,
@@ -340,6 +341,12 @@ int tqb_sd_device_solve(tqb_sd_device *d, const tqb_opts *o, int reverse, int *h
 int tqb_sd_device_download(tqb_sd_device *d, double *h_out, double *ms);
 
 int tqb_verbose(void); /* TREEQP_B200_VERBOSE=1 */
+void tqb_set_profiling(int on); /* device.cu: CUDA events around every launch */
+#if defined(PROFILE) && PROFILE > 0
+/* profiling.c: one solve's per-iteration phase seconds (4 x n), iterations run, trials per iteration, total seconds */
+struct treeqp_profiling_t_;
+void tqb_timers_fill(struct treeqp_profiling_t_ *t, const double *ph, int n, int nit, const int *ls_iters, double total_time);
+#endif
 /* "%.16e" / "%d" per line, as utils/utils.c:98-143 */
 int tqb_write_doubles_txt(const double *v, long long n, const char *filename);
 int tqb_write_ints_txt(const int *v, long long n, const char *filename);

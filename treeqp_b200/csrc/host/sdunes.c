@@ -179,10 +179,15 @@ static long long sd_host_bytes(const sd_shape *s)
 
 int treeqp_sdunes_calculate_size(tree_qp_in *qp_in, treeqp_sdunes_opts_t *opts)
 {
-    (void) opts;
     sd_shape s;
     shape_of(qp_in, &s);
-    return (int) sd_host_bytes(&s);
+    long long b = sd_host_bytes(&s);
+#if defined(PROFILE) && PROFILE > 0
+    b += timers_calculate_size(opts->maxIter) + 64; /* dual_Newton_scenarios.c (PROFILE > 0 branch of calculate_size) */
+#else
+    (void) opts;
+#endif
+    return (int) b;
 }
 
 static char *align64(char *p) { return (char *) (((uintptr_t) p + 63u) / 64u * 64u); }
@@ -344,6 +349,13 @@ void treeqp_sdunes_create(tree_qp_in *qp_in, treeqp_sdunes_opts_t *opts, treeqp_
         fprintf(stderr, "[treeqp_b200] treeqp_sdunes_create: no device arena (%s); solve will return "
                         "TREEQP_UNKNOWN_ERROR\n", tqb_cuda_last_error());
     ctx->dual_dirty = 1;
+#if defined(PROFILE) && PROFILE > 0
+    {   /* the timers live behind the workspace's own tables */
+        char *tp = align64((char *) ptr + sd_host_bytes(&s));
+        timers_create(opts->maxIter, &work->timings, tp);
+        timers_initialize(&work->timings);
+    }
+#endif
     /* no destroy in the reference API: a re-create over the same caller memory releases the previous arena */
     tqb_registry_replace(ptr, ctx, (void (*)(void *)) sd_ctx_free);
 
@@ -561,6 +573,9 @@ void write_scenarios_solution_to_txt(int Ns, int Nh, int Nr, int md, int nx, int
     tqb_write_doubles_txt(o->xs, (long long) d->SK * d->nx, "examples/spring_mass_utils/xIter.txt");
     tqb_write_doubles_txt(o->us, (long long) d->SK * d->nu, "examples/spring_mass_utils/uIter.txt");
     tqb_write_ints_txt(&NewtonIter, 1, "examples/spring_mass_utils/iter.txt");
+#if defined(PROFILE) && PROFILE > 0
+    timers_write_to_txt(&work->timings); /* dual_Newton_scenarios.c:241-243 */
+#endif
 }
 
 return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdunes_opts_t *opts,
@@ -593,6 +608,22 @@ return_t treeqp_sdunes_solve(tree_qp_in *qp_in, tree_qp_out *qp_out, treeqp_sdun
     const double t_end = tqb_wall_ms();
     qp_out->info.interface_time += 1e-3 * (t_end - t_after);
     qp_out->info.total_time = 1e-3 * (t_end - t_total);
+#if defined(PROFILE) && PROFILE > 0
+    {   /* The whole Newton loop is ONE kernel: its phase split is measured inside it per SOLVE (globaltimer stamps,
+         * treeqp_sdunes_get_stats), so the per-iteration entries are that split divided evenly over the iterations.
+         * Phases as dual_Newton_scenarios.c names them: stage QPs (incl. the Hessian blocks, as there), build, Newton
+         * direction (scenario factorisations, J chain, delta_mu), line search. */
+        treeqp_profiling_t *tm = &work->timings;
+        const int n = tm->num_iter > 0 ? tm->num_iter : 1, nit = qp_out->info.iter < n ? qp_out->info.iter : n;
+        double *ph = (double *) calloc(4 * (size_t) n, sizeof(double));
+        const int *ns = ctx->h_info + 8 + 256; /* nanoseconds per phase (sd_phase_names) */
+        const double tot[4] = {1e-9 * ns[0], 1e-9 * ns[1], 1e-9 * (ns[2] + ns[3] + ns[4]), 1e-9 * (ns[5] + ns[6] + ns[7])};
+        for (int p4 = 0; p4 < 4; p4++)
+            for (int i = 0; i < nit; i++) ph[p4 * n + i] = tot[p4] / (nit > 0 ? nit : 1);
+        tqb_timers_fill(tm, ph, n, nit, ctx->h_info + 8, qp_out->info.total_time);
+        free(ph);
+    }
+#endif
     if (tqb_verbose())
         fprintf(stderr, "[treeqp_b200] treeqp_sdunes_solve: status %d, %d Newton iterations, %lld kernel launches, gpu %.3f ms, total %.3f ms\n",
                 (int) st, qp_out->info.iter, ctx->launches, ctx->gpu_ms, t_end - t_total);

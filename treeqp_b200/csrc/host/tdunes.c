@@ -133,9 +133,14 @@ static int host_bytes(int Nn, int Nh)
 
 int treeqp_tdunes_calculate_size(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts)
 {
-    (void) opts;
     int Nn = qp_in->N;
-    return host_bytes(Nn, qp_in->tree[Nn - 1].stage);
+    int bytes = host_bytes(Nn, qp_in->tree[Nn - 1].stage);
+#if defined(PROFILE) && PROFILE > 0
+    if (bytes > 0) bytes += timers_calculate_size(opts->maxIter) + 64; /* dual_Newton_tree.c:1399-1401 */
+#else
+    (void) opts;
+#endif
+    return bytes;
 }
 
 static void check_stage_solvers(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *opts)
@@ -185,6 +190,15 @@ void treeqp_tdunes_create(const tree_qp_in *qp_in, const treeqp_tdunes_opts_t *o
     work->npar = (int *) cur;            cur += (size_t) (Nh + 1) * sizeof(int);
     work->idxpos = (int *) cur;          cur += (size_t) Nn * sizeof(int);
     assert(cur <= (char *) ptr + host_bytes(Nn, Nh));
+#if defined(PROFILE) && PROFILE > 0
+    {   /* dual_Newton_tree.c:1638-1642: the timers live behind the workspace's own tables */
+        char *tp = (char *) ptr + host_bytes(Nn, Nh);
+        tp = (char *) (((uintptr_t) tp + 63u) / 64u * 64u);
+        timers_create(opts->maxIter, &work->timings, tp);
+        timers_initialize(&work->timings);
+        tqb_set_profiling(1); /* an event pair around every launch feeds them */
+    }
+#endif
 
     int Np = 0;
     for (int l = 0; l <= Nh; l++) work->npar[l] = 0;
@@ -442,6 +456,21 @@ return_t treeqp_tdunes_solve(const tree_qp_in *qp_in, tree_qp_out *qp_out,
     const double t_end = tqb_wall_ms();
     qp_out->info.interface_time += 1e-3 * (t_end - t_after);
     qp_out->info.total_time = 1e-3 * (t_end - t_total);
+#if defined(PROFILE) && PROFILE > 0
+    {   /* dual_Newton_tree.c:1168-1226, :1257-1260 with CUDA-event times per Newton iteration */
+        treeqp_profiling_t *tm = &work->timings;
+        if (tm->num_iter != opts->maxIter)
+        {
+            fprintf(stderr, "[treeqp_b200] Number of iterations cannot be changed after initializing solver (when PROFILE > 0)\n");
+            exit(1);
+        }
+        const int n = tm->num_iter > 0 ? tm->num_iter : 1;
+        double *ph = (double *) calloc(4 * (size_t) n, sizeof(double));
+        const int nit = tqb_device_iter_phase_times(ctx->forest->dev, ph, n);
+        tqb_timers_fill(tm, ph, n, nit < qp_out->info.iter ? nit : qp_out->info.iter, ctx->forest->ls_iters, qp_out->info.total_time);
+        free(ph);
+    }
+#endif
     if (tqb_verbose())
         fprintf(stderr, "[treeqp_b200] treeqp_tdunes_solve: status %d, %d Newton iterations, %lld kernel launches, gpu %.3f ms, total %.3f ms "
                         "(upload %.3f, solve %.3f, download %.3f)\n",
@@ -500,6 +529,9 @@ void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct nod
     tqb_write_doubles_txt(lam + nx0, d->X - nx0, "examples/spring_mass_utils/deltalambda_opt.txt");
     tqb_write_doubles_txt(lam + nx0, d->X - nx0, "examples/spring_mass_utils/lambda_opt.txt");
     tqb_write_ints_txt(&iter, 1, "examples/spring_mass_utils/iter.txt");
+#if defined(PROFILE) && PROFILE > 0
+    timers_write_to_txt(&work->timings); /* dual_Newton_tree.c:1065-1067 */
+#endif
 }
 
 /* ------------------------------------------------------------------ PROFILE > 0 guard ---- */
@@ -510,6 +542,7 @@ void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct nod
  * program reaches for these two symbols right after its solve (examples/...:145, :152, random_qp.c:191),
  * binds them here (the library precedes libtreeqp.a on the link line) and is stopped with a message
  * instead of printing uninitialised timers.  Per-kernel-class GPU times: treeqp_tdunes_get_stats. */
+#if !(defined(PROFILE) && PROFILE > 0)
 static void profile_unsupported(const char *fn)
 {
     fprintf(stderr, "[treeqp_b200] %s: this program was compiled with PROFILE > 0; libtreeqp_b200 implements the "
@@ -519,6 +552,7 @@ static void profile_unsupported(const char *fn)
 }
 void timers_print(void *timings) { (void) timings; profile_unsupported("timers_print"); }
 void timers_write_to_txt(void *timings) { (void) timings; profile_unsupported("timers_write_to_txt"); }
+#endif
 
 /* ------------------------------------------------------------------------------- batch ---- */
 
