@@ -12,7 +12,8 @@
  *
  * The ABI corresponds to the reference's default build: PROFILE=0 (no `timings` member in the
  * workspace, dual_Newton_tree.h:146-148) and BLASFEO HIGH_PERFORMANCE (panel-major matrices); compiled with
- * -DPROFILE=1..3 this header is the PROFILE > 0 layout, served by libtreeqp_b200_profile3.so (section 4, timers).
+ * -DPROFILE=n (1..3) this header is the PROFILE = n layout, served by libtreeqp_b200_profile<n>.so (`make -C treeqp_b200/csrc
+ * profile PL=n`; section 4, timers).
  *
  * Sections
  *   1. BLASFEO-compatible matrix/vector views          (blasfeo_common.h:46-89)
@@ -358,8 +359,8 @@ void write_solution_to_txt(const tree_qp_in *qp_in, int Np, int iter, struct nod
 /* PROFILE > 0 (Makefile.rule:112-119): the reference's workspace structs grow a trailing `timings` member and its solve fills
  * it (utils/profiling.h:38-68).  The default library is the PROFILE = 0 ABI: a caller compiled with PROFILE > 0 that links it
  * binds timers_print / timers_write_to_txt here and is stopped with a message rather than allowed to print timers nobody
- * filled.  `make -C treeqp_b200/csrc profile3` builds libtreeqp_b200_profile3.so with -DPROFILE=3: the same solvers, the
- * PROFILE = 3 struct layout, and `timings` fed from CUDA events around every launch (which serialises the launches, as the
+ * filled.  `make -C treeqp_b200/csrc profile PL=n` builds libtreeqp_b200_profile<n>.so with -DPROFILE=n (n = 3: `make profile3`):
+ * the same solvers, the PROFILE = n struct layout, and `timings` fed from CUDA events around every launch (which serialises the launches, as the
  * reference's own timers perturb its run): per Newton iteration the four phase times, the iteration time, the line-search
  * trial count; total_time and the minima over repeated runs as utils/profiling.c keeps them. */
 #if defined(PROFILE) && PROFILE > 0
