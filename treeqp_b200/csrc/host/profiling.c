@@ -29,6 +29,7 @@ int timers_calculate_size(int num_iter)
 void timers_create(int num_iter, treeqp_profiling_t *t, void *ptr)
 {
     double *d = (double *) ptr;
+    (void) d;
     t->num_iter = num_iter;
 #if PROFILE > 1
     t->iter_times = d; d += num_iter;
