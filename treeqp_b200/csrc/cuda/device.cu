@@ -233,7 +233,9 @@ static int launch_bf(tqb_device *D, int begin, int cnt, int kp, int pre_ok)
      * every block has a changed descendant, and the build of a full block should start before the kids' level ends.
      * Sharded solves: a wide level lies below the cut, where every block and all its kids are this rank's own (ghost
      * cut nodes are kids of the replicated top levels only, which are narrow) */
-    const int try_skip = (D->skip_on && !ROOT && Cfg::BLOCKED && cnt >= TQB_SKIP_MIN_BLOCKS) ? 1 : 0;
+    static int min_blocks = 0; /* TREEQP_B200_SKIP_MIN_BLOCKS overrides the compiled-in threshold (A/B runs) */
+    if (min_blocks == 0) { const char *e = getenv("TREEQP_B200_SKIP_MIN_BLOCKS"); min_blocks = (e && atoi(e) > 0) ? atoi(e) : TQB_SKIP_MIN_BLOCKS; }
+    const int try_skip = (D->skip_on && !ROOT && Cfg::BLOCKED && cnt >= min_blocks) ? 1 : 0;
     CK(launch_pdl(k_build_factor<NX, NU, MD, PNX, ROOT>, dim3((cnt + wpb - 1) / wpb), dim3(32 * wpb), smem, D->stream, pe_ < 0,
                   D->v, begin, cnt, kp, pre_ok, try_skip));
     if (pe_ >= 0) cudaEventRecord(D->pev[2 * pe_ + 1], D->stream);
