@@ -90,6 +90,7 @@ struct tqb_device
     int fast, f_nx, f_nu, f_pnx;
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
     int *chain_link;      /* [Nh] depth l continues the chains of depth l-1 (one kid per parent, same order) */
+    int *lvl_udim;        /* [Nh] d when every block of the depth has dimension d and a parent state of d entries, else 0 */
     int has_ghost;        /* sharded local forest: reduction chunks cover the owned nodes only */
     int pair_begin;       /* level descriptors from here on are non-root parents with one kid (k_stage_fused pairs them) */
     double *d_schur;
@@ -472,8 +473,39 @@ static int compute_chain_links(tqb_device *D, const tqb_tables *T, const int *gh
         }
         D->chain_link[l] = ok;
     }
+    /* depths whose blocks all have d == nx == one value: their chain segments run the compile-time-dimension
+     * instances of the level kernels (k_factor_level<DC>, k_backsolve_level<DC>) */
+    D->lvl_udim = (int *) calloc((size_t) d->Nh + 2, sizeof(int));
+    for (int l = 0; l < d->Nh; l++)
+    {
+        const int c = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
+        if (c <= 0) continue;
+        const int u = T->dim[T->lvl_nodes[D->lvl_ptr[l]]];
+        int ok = 1;
+        for (int w = 0; w < c && ok; w++)
+        {
+            const int g = T->lvl_nodes[D->lvl_ptr[l] + w];
+            ok = T->dim[g] == u && T->nx[g] == u;
+        }
+        D->lvl_udim[l] = ok ? u : 0;
+    }
     return 0;
 }
+
+/* compile-time dimension of a chain segment (depths lt..lb) on the runtime-dimension path, 0 = none */
+static int chain_udim(const tqb_device *D, int lt, int lb)
+{
+    if (!D->lvl_udim || lb <= lt) return 0;
+    const char *e = getenv("TREEQP_B200_NO_CHAIN_DC"); /* A/B runs */
+    if (e && e[0] == '1') return 0;
+    const int u = D->lvl_udim[lt];
+    for (int l = lt; l <= lb; l++)
+        if (D->lvl_udim[l] != u) return 0;
+    return u;
+}
+
+/* dimensions with a compile-time instance of the level kernels */
+#define TQB_CHAIN_DC_LIST(X) X(2) X(4) X(6) X(8) X(10) X(12) X(16)
 
 /* The fast path needs: every non-root node nx == NX, every root nx in {0, NX} (the same for all
  * trees), every parent nu == NU, all parents of one depth the same number of kids, kids of one
@@ -854,8 +886,13 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     CK(cudaFuncSetAttribute(k_stage<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
     CK(cudaFuncSetAttribute(k_stage<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_stage));
     CK(cudaFuncSetAttribute(k_hessian, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_hess));
-    CK(cudaFuncSetAttribute(k_factor_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_fact));
-    CK(cudaFuncSetAttribute(k_backsolve_level, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
+    CK(cudaFuncSetAttribute(k_factor_level<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_fact));
+    CK(cudaFuncSetAttribute(k_backsolve_level<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
+#define X(a)                                                                                                       \
+    CK(cudaFuncSetAttribute(k_factor_level<a>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_fact));    \
+    CK(cudaFuncSetAttribute(k_backsolve_level<a>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
+    TQB_CHAIN_DC_LIST(X)
+#undef X
     return 0;
 }
 
@@ -878,7 +915,7 @@ extern "C" void tqb_device_destroy(tqb_device *D)
     if (!D) return;
     if (D->stream) cudaStreamSynchronize(D->stream);
     cudaFree(D->d_int); cudaFree(D->d_in); cudaFree(D->d_work); cudaFree(D->d_tint); cudaFree(D->d_tdbl);
-    cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); cudaFree(D->d_leaf_desc); free(D->lvl_md); free(D->lvl_kp); free(D->chain_link);
+    cudaFree(D->d_schur); cudaFree(D->d_lvl_desc); cudaFree(D->d_leaf_desc); free(D->lvl_md); free(D->lvl_kp); free(D->chain_link); free(D->lvl_udim);
     cudaFree(D->d_abstage); cudaFree(D->d_flags); cudaFree(D->d_ghost);
     cudaFree(D->d_cut_nodes); cudaFree(D->d_send); cudaFree(D->d_recv); cudaFree(D->d_tred);
     if (D->h_counters) cudaFreeHost(D->h_counters);
@@ -1499,7 +1536,14 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 const int lt = chain_top(D, l);
                 const int cnt = D->lvl_ptr[lt + 1] - D->lvl_ptr[lt];
                 if (cnt > 0)
-                    LAUNCH(K_FACTOR, k_factor_level, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1);
+                {
+                    const int dc = chain_udim(D, lt, l);
+                    bool done = false;
+#define X(a) if (dc == a) { LAUNCH(K_FACTOR, k_factor_level<a>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1); done = true; }
+                    TQB_CHAIN_DC_LIST(X)
+#undef X
+                    if (!done) LAUNCH(K_FACTOR, k_factor_level<0>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1);
+                }
                 l = lt;
             }
             for (int l = 1; l < Nh; l++)
@@ -1508,7 +1552,14 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 if (!(lb > l && D->chain_link[l + 1])) lb = l;
                 const int cnt = D->lvl_ptr[l + 1] - D->lvl_ptr[l];
                 if (cnt > 0)
-                    LAUNCH(K_BACK, k_backsolve_level, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1);
+                {
+                    const int dc = chain_udim(D, l, lb);
+                    bool done = false;
+#define X(a) if (dc == a) { LAUNCH(K_BACK, k_backsolve_level<a>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1); done = true; }
+                    TQB_CHAIN_DC_LIST(X)
+#undef X
+                    if (!done) LAUNCH(K_BACK, k_backsolve_level<0>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1);
+                }
                 l = lb;
             }
         }

@@ -714,6 +714,10 @@ __global__ void __launch_bounds__(256) k_hessian(View v)
 /* nlev > 1: depths lvl_begin .. are a chain segment (one kid per parent, `count` parents each, block w of a
  * depth is the parent of block w of the next one): the warp walks its chain from the deepest block up in ONE
  * launch; what a block leaves for its parent (W, resMod in HBM) is re-read by the same warp. */
+/* DC > 0: every block of the launch has d == nx == DC (the chains of a tree with one state dimension; the host checks
+ * it per depth, device.cu: lvl_udim): loop bounds, strides and the index arithmetic become compile-time constants, the
+ * operation order is the one of DC == 0. */
+template <int DC>
 __global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int count, int per_warp, int nlev)
 {
     extern __shared__ double smem[];
@@ -727,7 +731,7 @@ __global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int
     const int g = v.T.lvl_nodes[lvl_begin + lev * count + w];
     __syncwarp();
 
-    const int d = v.T.dim[g], nx = v.T.nx[g], k0 = v.T.kid0[g], dad = v.T.dad[g];
+    const int d = DC ? DC : v.T.dim[g], nx = DC ? DC : v.T.nx[g], k0 = v.T.kid0[g], dad = v.T.dad[g];
     const int ld = d | 1, ldu = nx | 1;
     double *sW = smem + (size_t) wib * per_warp;
     double *sy = sW + (v.dmax | 1) * v.dmax;
@@ -744,6 +748,9 @@ __global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int
         sW[i + j * ld] = val;
     }
     for (int e = lane; e < d; e += 32) sy[e] = v.resMod[xb + e];
+    double *Utp = v.Ut + v.T.utoff[g];
+    if (dad >= 0) /* staged with W: the loads do not wait for the factorisation */
+        for (int e = lane; e < nx * d; e += 32) sU[(e % nx) + (e / nx) * ldu] = Utp[e];
     __syncwarp();
     warp_potrf(sW, ld, d, sinv, lane);
     if (v.o.regType == 2)
@@ -784,9 +791,6 @@ __global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int
     if (dad >= 0)
     {
         /* Utilde = Ut L^-T (dtrsm_rltn): each lane owns one row of Ut */
-        double *Utp = v.Ut + v.T.utoff[g];
-        for (int e = lane; e < nx * d; e += 32) sU[(e % nx) + (e / nx) * ldu] = Utp[e];
-        __syncwarp();
         for (int c = lane; c < nx; c += 32)
             for (int j = 0; j < d; j++)
             {
@@ -803,16 +807,19 @@ __global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int
         {
             const int a = e % nx, b = e / nx;
             if (a < b) continue;
+            double *wd = Wd + (off + a) + (off + b) * dd;
+            const double w0 = *wd; /* requested before the dot product */
             double s = 0.0;
             for (int t = 0; t < d; t++) s += sU[a + t * ldu] * sU[b + t * ldu];
-            Wd[(off + a) + (off + b) * dd] -= s;
+            *wd = w0 - s;
         }
         const int xo = v.T.xoff[g];
         for (int a = lane; a < nx; a += 32)
         {
+            const double r0 = v.resMod[xo + a];
             double s = 0.0;
             for (int t = 0; t < d; t++) s += sU[a + t * ldu] * sy[t];
-            v.resMod[xo + a] -= s;
+            v.resMod[xo + a] = r0 - s;
         }
     }
     else
@@ -824,6 +831,7 @@ __global__ void __launch_bounds__(256) k_factor_level(View v, int lvl_begin, int
 
 /* One depth level of the root-to-leaves sweep:
  * dlam_p <- L_p^-T (y_p - Utilde_p' dlam_dad[segment of p])   (dual_Newton_tree.c:764-773) */
+template <int DC> /* DC > 0: d == nx == DC for every block of the launch (see k_factor_level) */
 __global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, int count, int per_warp, int nlev)
 {
     extern __shared__ double smem[];
@@ -836,7 +844,7 @@ __global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, 
     {   /* nlev > 1: chain segment walked top-down by one warp (see k_factor_level) */
     const int g = v.T.lvl_nodes[lvl_begin + lev * count + w];
     __syncwarp();
-    const int d = v.T.dim[g], nx = v.T.nx[g], k0 = v.T.kid0[g];
+    const int d = DC ? DC : v.T.dim[g], nx = DC ? DC : v.T.nx[g], k0 = v.T.kid0[g];
     const int ld = d | 1;
     double *sW = smem + (size_t) wib * per_warp;
     double *sy = sW + (v.dmax | 1) * v.dmax;
