@@ -504,6 +504,15 @@ static int chain_udim(const tqb_device *D, int lt, int lb)
     return u;
 }
 
+/* chain segments of 2..32 depths take the kernels that move the next block's inputs while a block is processed
+ * (k_factor_chain_pf, k_backsolve_chain_pf); TREEQP_B200_NO_CHAIN_PF=1 keeps the level kernels (A/B runs) */
+static bool chain_pf_on(int nlev)
+{
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("TREEQP_B200_NO_CHAIN_PF"); on = (e && e[0] == '1') ? 0 : 1; }
+    return on == 1 && nlev >= 2 && nlev <= 32;
+}
+
 /* dimensions with a compile-time instance of the level kernels */
 #define TQB_CHAIN_DC_LIST(X) X(2) X(4) X(6) X(8) X(10) X(12) X(16)
 
@@ -890,7 +899,9 @@ static int device_build(tqb_device *D, const int *h_int, const int *lvl_ptr, con
     CK(cudaFuncSetAttribute(k_backsolve_level<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
 #define X(a)                                                                                                       \
     CK(cudaFuncSetAttribute(k_factor_level<a>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_fact));    \
-    CK(cudaFuncSetAttribute(k_backsolve_level<a>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
+    CK(cudaFuncSetAttribute(k_backsolve_level<a>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back)); \
+    CK(cudaFuncSetAttribute(k_factor_chain_pf<a>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_fact)); \
+    CK(cudaFuncSetAttribute(k_backsolve_chain_pf<a>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) D->sm_back));
     TQB_CHAIN_DC_LIST(X)
 #undef X
     return 0;
@@ -1539,7 +1550,8 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 {
                     const int dc = chain_udim(D, lt, l);
                     bool done = false;
-#define X(a) if (dc == a) { LAUNCH(K_FACTOR, k_factor_level<a>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1); done = true; }
+#define X(a) if (dc == a) { if (chain_pf_on(l - lt + 1)) LAUNCH(K_FACTOR, k_factor_chain_pf<a>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1); \
+                             else LAUNCH(K_FACTOR, k_factor_level<a>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1); done = true; }
                     TQB_CHAIN_DC_LIST(X)
 #undef X
                     if (!done) LAUNCH(K_FACTOR, k_factor_level<0>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1);
@@ -1555,7 +1567,8 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 {
                     const int dc = chain_udim(D, l, lb);
                     bool done = false;
-#define X(a) if (dc == a) { LAUNCH(K_BACK, k_backsolve_level<a>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1); done = true; }
+#define X(a) if (dc == a) { if (chain_pf_on(lb - l + 1)) LAUNCH(K_BACK, k_backsolve_chain_pf<a>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1); \
+                             else LAUNCH(K_BACK, k_backsolve_level<a>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1); done = true; }
                     TQB_CHAIN_DC_LIST(X)
 #undef X
                     if (!done) LAUNCH(K_BACK, k_backsolve_level<0>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1);

@@ -873,6 +873,257 @@ __global__ void __launch_bounds__(256) k_backsolve_level(View v, int lvl_begin, 
     }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Chain segments with one block dimension (d == nx == DC at every depth of the segment, at most 32 depths), the
+ * arithmetic of k_factor_level<DC> / k_backsolve_level<DC> with the global-memory latency taken off the dependent
+ * chain of the walk:
+ *   - the tables of ALL depths of the chain are read up front, depth L by lane L, and handed out by shuffles;
+ *   - while a block is being processed, the inputs of the NEXT block of the chain travel into registers; what the
+ *     current block contributes to it (the Schur complement of the factor sweep, the parent's solution of the
+ *     substitution sweep) is applied on chip.  Everything is still written to HBM exactly as before (the
+ *     regularisation retry, the substitution sweep and the next Newton iteration read it there).
+ * Same operations in the same order as the level kernels: same bits.
+ * ---------------------------------------------------------------------------------------- */
+template <int DC>
+__global__ void __launch_bounds__(256) k_factor_chain_pf(View v, int lvl_begin, int count, int per_warp, int nlev)
+{
+    constexpr int NW = (DC * DC + 31) / 32, ld = DC | 1, ldu = DC | 1;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (w >= count) return;
+    if (v.status[v.T.tree[v.T.lvl_nodes[lvl_begin + w]]] != TQB_RUNNING) return;
+    double *sW = smem + (size_t) wib * per_warp;
+    double *sy = sW + (v.dmax | 1) * v.dmax;
+    double *sinv = sy + v.dmax;
+    double *sU = sinv + v.dmax;
+
+    /* tables of depth `lane` of the chain */
+    int t_w = 0, t_u = 0, t_xb = 0, t_xo = 0;
+    if (lane < nlev)
+    {
+        const int gl = v.T.lvl_nodes[lvl_begin + lane * count + w];
+        t_w = v.T.woff[gl]; t_u = v.T.utoff[gl]; t_xb = v.T.xoff[v.T.kid0[gl]]; t_xo = v.T.xoff[gl];
+    }
+    const int g0 = v.T.lvl_nodes[lvl_begin + w], dad0 = v.T.dad[g0]; /* top of the chain: its parent is outside */
+
+    /* inputs of the deepest block */
+    double pW[NW], pU[NW], pr = 0.0;
+    {
+        const int wo = __shfl_sync(FULL, t_w, nlev - 1), uo = __shfl_sync(FULL, t_u, nlev - 1), xb = __shfl_sync(FULL, t_xb, nlev - 1);
+#pragma unroll
+        for (int k = 0; k < NW; k++)
+        {
+            const int e = lane + 32 * k;
+            pW[k] = e < DC * DC ? v.W[wo + e] : 0.0;
+            pU[k] = e < DC * DC ? v.Ut[uo + e] : 0.0;
+        }
+        if (lane < DC) pr = v.resMod[xb + lane];
+    }
+#pragma unroll 1
+    for (int lev = nlev - 1; lev >= 0; lev--)
+    {
+        const int wo = __shfl_sync(FULL, t_w, lev), uo = __shfl_sync(FULL, t_u, lev);
+        const int xb = __shfl_sync(FULL, t_xb, lev), xo = __shfl_sync(FULL, t_xo, lev);
+        double *Wp = v.W + wo, *Utp = v.Ut + uo;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NW; k++)
+        {
+            const int e = lane + 32 * k;
+            if (e < DC * DC)
+            {
+                const int i = e % DC, j = e / DC;
+                sW[i + j * ld] = (i == j && v.o.regType == 1) ? pW[k] + v.o.regValue : pW[k];
+                sU[i + j * ldu] = pU[k];
+            }
+        }
+        if (lane < DC) sy[lane] = pr;
+        /* the next block of the chain (the parent): W and the right-hand side before this block's contribution */
+        if (lev > 0)
+        {
+            const int wn = __shfl_sync(FULL, t_w, lev - 1), un = __shfl_sync(FULL, t_u, lev - 1);
+#pragma unroll
+            for (int k = 0; k < NW; k++)
+            {
+                const int e = lane + 32 * k;
+                pW[k] = e < DC * DC ? v.W[wn + e] : 0.0;
+                pU[k] = e < DC * DC ? v.Ut[un + e] : 0.0;
+            }
+            if (lane < DC) pr = v.resMod[xo + lane];
+        }
+        __syncwarp();
+        warp_potrf(sW, ld, DC, sinv, lane);
+        if (v.o.regType == 2)
+        {
+            bool small = false;
+            for (int j = lane; j < DC; j += 32) small |= (sW[j + j * ld] <= v.o.regTol);
+            if (__any_sync(FULL, small))
+            {
+                __syncwarp();
+                for (int e = lane; e < DC * DC; e += 32)
+                {
+                    const int i = e % DC, j = e / DC;
+                    sW[i + j * ld] = Wp[e] + (i == j ? v.o.regValue : 0.0);
+                }
+                __syncwarp();
+                warp_potrf(sW, ld, DC, sinv, lane);
+                if (lane == 0) atomicAdd(&v.counters[2], 1);
+            }
+        }
+        for (int e = lane; e < DC * DC; e += 32)
+        {
+            const int i = e % DC, j = e / DC;
+            if (i >= j) Wp[e] = sW[i + j * ld];
+        }
+        for (int e = lane; e < DC; e += 32) v.Linv[xb + e] = sinv[e];
+        for (int j = 0; j < DC; j++)
+        {
+            const double yj = sy[j] * sinv[j];
+            __syncwarp();
+            if (lane == 0) sy[j] = yj;
+            for (int i = j + 1 + lane; i < DC; i += 32) sy[i] -= sW[i + j * ld] * yj;
+            __syncwarp();
+        }
+        if (lev > 0 || dad0 >= 0)
+        {
+            for (int c = lane; c < DC; c += 32)
+                for (int j = 0; j < DC; j++)
+                {
+                    double s = sU[c + j * ldu];
+                    for (int t = 0; t < j; t++) s -= sU[c + t * ldu] * sW[j + t * ld];
+                    sU[c + j * ldu] = s * sinv[j];
+                }
+            __syncwarp();
+            for (int e = lane; e < DC * DC; e += 32) Utp[e] = sU[(e % DC) + (e / DC) * ldu];
+            if (lev > 0)
+            {   /* parent inside the chain: its block is DC x DC, this kid is its only one */
+                double *Wd = v.W + __shfl_sync(FULL, t_w, lev - 1);
+#pragma unroll
+                for (int k = 0; k < NW; k++)
+                {
+                    const int e = lane + 32 * k, a = e % DC, b = e / DC;
+                    if (e >= DC * DC || a < b) continue;
+                    double s = 0.0;
+                    for (int t = 0; t < DC; t++) s += sU[a + t * ldu] * sU[b + t * ldu];
+                    pW[k] -= s;
+                    Wd[e] = pW[k];
+                }
+                if (lane < DC)
+                {
+                    double s = 0.0;
+                    for (int t = 0; t < DC; t++) s += sU[lane + t * ldu] * sy[t];
+                    pr -= s;
+                    v.resMod[xo + lane] = pr;
+                }
+            }
+            else
+            {   /* parent above the chain: any shape */
+                const int dd = v.T.dim[dad0], off = v.T.pos[g0];
+                double *Wd = v.W + v.T.woff[dad0];
+                for (int e = lane; e < DC * DC; e += 32)
+                {
+                    const int a = e % DC, b = e / DC;
+                    if (a < b) continue;
+                    double *wd = Wd + (off + a) + (off + b) * dd;
+                    const double w0 = *wd;
+                    double s = 0.0;
+                    for (int t = 0; t < DC; t++) s += sU[a + t * ldu] * sU[b + t * ldu];
+                    *wd = w0 - s;
+                }
+                for (int a = lane; a < DC; a += 32)
+                {
+                    const double r0 = v.resMod[xo + a];
+                    double s = 0.0;
+                    for (int t = 0; t < DC; t++) s += sU[a + t * ldu] * sy[t];
+                    v.resMod[xo + a] = r0 - s;
+                }
+            }
+        }
+        else
+            warp_trsv_ltn(sW, ld, DC, sinv, sy, lane);
+        __syncwarp();
+        for (int e = lane; e < DC; e += 32) v.dlam[xb + e] = sy[e];
+    }
+}
+
+template <int DC>
+__global__ void __launch_bounds__(256) k_backsolve_chain_pf(View v, int lvl_begin, int count, int per_warp, int nlev)
+{
+    constexpr int NW = (DC * DC + 31) / 32, ld = DC | 1;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int w = blockIdx.x * wpb + wib;
+    if (w >= count) return;
+    if (v.status[v.T.tree[v.T.lvl_nodes[lvl_begin + w]]] != TQB_RUNNING) return;
+    double *sW = smem + (size_t) wib * per_warp;
+    double *sy = sW + (v.dmax | 1) * v.dmax;
+    double *sinv = sy + v.dmax;
+    double *sd = sinv + v.dmax;
+
+    int t_w = 0, t_u = 0, t_xb = 0;
+    if (lane < nlev)
+    {
+        const int gl = v.T.lvl_nodes[lvl_begin + lane * count + w];
+        t_w = v.T.woff[gl]; t_u = v.T.utoff[gl]; t_xb = v.T.xoff[v.T.kid0[gl]];
+    }
+    /* inputs of the top block: lane j holds column j of Utilde (DC entries), its y and 1 / L_jj */
+    double pW[NW], pU[DC], py = 0.0, pinv = 0.0;
+    {
+        const int wo = __shfl_sync(FULL, t_w, 0), uo = __shfl_sync(FULL, t_u, 0), xb = __shfl_sync(FULL, t_xb, 0);
+#pragma unroll
+        for (int k = 0; k < NW; k++)
+        {
+            const int e = lane + 32 * k;
+            pW[k] = e < DC * DC ? v.W[wo + e] : 0.0;
+        }
+#pragma unroll
+        for (int c = 0; c < DC; c++) pU[c] = lane < DC ? v.Ut[uo + c + lane * DC] : 0.0;
+        if (lane < DC) { py = v.dlam[xb + lane]; pinv = v.Linv[xb + lane]; }
+        const int xo = v.T.xoff[v.T.lvl_nodes[lvl_begin + w]];
+        if (lane < DC) sd[lane] = v.dlam[xo + lane]; /* the solution of the parent above the chain */
+    }
+#pragma unroll 1
+    for (int lev = 0; lev < nlev; lev++)
+    {
+        const int xb = __shfl_sync(FULL, t_xb, lev);
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < NW; k++)
+        {
+            const int e = lane + 32 * k;
+            if (e < DC * DC) sW[(e % DC) + (e / DC) * ld] = pW[k];
+        }
+        double yv = 0.0;
+        if (lane < DC)
+        {
+            sinv[lane] = pinv;
+            double s = 0.0;
+#pragma unroll
+            for (int c = 0; c < DC; c++) s += pU[c] * sd[c];
+            yv = py - s;
+        }
+        if (lev + 1 < nlev)
+        {   /* the kid's inputs travel while this block is solved */
+            const int wn = __shfl_sync(FULL, t_w, lev + 1), un = __shfl_sync(FULL, t_u, lev + 1), xn = __shfl_sync(FULL, t_xb, lev + 1);
+#pragma unroll
+            for (int k = 0; k < NW; k++)
+            {
+                const int e = lane + 32 * k;
+                pW[k] = e < DC * DC ? v.W[wn + e] : 0.0;
+            }
+#pragma unroll
+            for (int c = 0; c < DC; c++) pU[c] = lane < DC ? v.Ut[un + c + lane * DC] : 0.0;
+            if (lane < DC) { py = v.dlam[xn + lane]; pinv = v.Linv[xn + lane]; }
+        }
+        if (lane < DC) sy[lane] = yv;
+        __syncwarp();
+        warp_trsv_ltn(sW, ld, DC, sinv, sy, lane);
+        __syncwarp();
+        if (lane < DC) { const double r = sy[lane]; v.dlam[xb + lane] = r; sd[lane] = r; }
+    }
+}
+
 /* lambda += tau_final * dlam once the line search of a tree is over.  (The reference moves
  * lambda incrementally by (tau - tauPrev)*dlam at every trial, dual_Newton_tree.c:964-968; the
  * end point is the same up to rounding.) */
