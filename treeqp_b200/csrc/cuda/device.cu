@@ -504,6 +504,16 @@ static int chain_udim(const tqb_device *D, int lt, int lb)
     return u;
 }
 
+/* dense stage QPs: does the first line-search pass solve all TQB_LS_NT step lengths?  Yes when that is at most
+ * four warps per resident-CTA slot of the device (TREEQP_B200_DENSE_FIRST_FULL = 0 / 1 forces it, A/B runs) */
+static bool dense_first_pass_full(const tqb_device *D)
+{
+    static int forced = -2;
+    if (forced == -2) { const char *e = getenv("TREEQP_B200_DENSE_FIRST_FULL"); forced = e ? (e[0] == '1' ? 1 : 0) : -1; }
+    if (forced >= 0) return forced == 1;
+    return (long long) D->dims.Nn * TQB_LS_NT <= 4LL * D->n_sm_all * D->wpb_dense;
+}
+
 /* chain segments of 2..32 depths take the kernels that move the next block's inputs while a block is processed
  * (k_factor_chain_pf, k_backsolve_chain_pf); TREEQP_B200_NO_CHAIN_PF=1 keeps the level kernels (A/B runs) */
 static bool chain_pf_on(int nlev)
@@ -1583,8 +1593,10 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
             for (int batch = 0, trials = 0; trials <= o->lsMaxIter + 1; batch++)
             {
                 /* slots looked at in this pass: all TQB_LS_NT for clipping trees (a pass only streams vectors);
-                 * with dense stage QPs the first pass solves tau = 0 and the full step only */
-                const int nt = (v.has_dense && batch == 0) ? 2 : TQB_LS_NT;
+                 * with dense stage QPs the first pass solves tau = 0 and the full step only -- unless the whole
+                 * pass is less than one wave of warps anyway (a single small tree: the extra step lengths cost
+                 * no time and save the passes of a backtracking iteration; same Armijo sequence either way) */
+                const int nt = (v.has_dense && batch == 0 && !dense_first_pass_full(D)) ? 2 : TQB_LS_NT;
                 if (v.has_dense) LAUNCH(K_TRIAL, k_trial_dense, cdiv((long long) v.Nn * nt, D->wpb_dense), 32 * D->wpb_dense, D->sm_dense, v, batch == 0, nt);
                 LAUNCH(K_TRIAL, k_ls_eval, v.nchunk, 256, 0, v, batch == 0);
                 if (D->comm && allreduce_ls_batch(D, batch == 0)) return 1;
