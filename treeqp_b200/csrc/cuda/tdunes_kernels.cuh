@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(256) k_factor_chain_pf(View v, int lvl_begin, 
             if (lane < DC) pr = v.resMod[xo + lane];
         }
         __syncwarp();
-        warp_potrf(sW, ld, DC, sinv, lane);
+        warp_potrf32(sW, ld, DC, sinv, lane); /* DC <= 32: one barrier per column, same operations */
         if (v.o.regType == 2)
         {
             bool small = false;
@@ -967,7 +967,7 @@ __global__ void __launch_bounds__(256) k_factor_chain_pf(View v, int lvl_begin, 
                     sW[i + j * ld] = Wp[e] + (i == j ? v.o.regValue : 0.0);
                 }
                 __syncwarp();
-                warp_potrf(sW, ld, DC, sinv, lane);
+                warp_potrf32(sW, ld, DC, sinv, lane); /* DC <= 32: one barrier per column, same operations */
                 if (lane == 0) atomicAdd(&v.counters[2], 1);
             }
         }
@@ -977,12 +977,10 @@ __global__ void __launch_bounds__(256) k_factor_chain_pf(View v, int lvl_begin, 
             if (i >= j) Wp[e] = sW[i + j * ld];
         }
         for (int e = lane; e < DC; e += 32) v.Linv[xb + e] = sinv[e];
-        for (int j = 0; j < DC; j++)
-        {
-            const double yj = sy[j] * sinv[j];
+        {   /* forward substitution, one entry per lane (the operations of warp_trsv_lnn) */
+            const double yl = warp_trsv_lnn32(sW, ld, DC, lane < DC ? sinv[lane] : 0.0, lane < DC ? sy[lane] : 0.0, lane);
             __syncwarp();
-            if (lane == 0) sy[j] = yj;
-            for (int i = j + 1 + lane; i < DC; i += 32) sy[i] -= sW[i + j * ld] * yj;
+            if (lane < DC) sy[lane] = yl;
             __syncwarp();
         }
         if (lev > 0 || dad0 >= 0)
@@ -1057,9 +1055,7 @@ __global__ void __launch_bounds__(256) k_backsolve_chain_pf(View v, int lvl_begi
     if (w >= count) return;
     if (v.status[v.T.tree[v.T.lvl_nodes[lvl_begin + w]]] != TQB_RUNNING) return;
     double *sW = smem + (size_t) wib * per_warp;
-    double *sy = sW + (v.dmax | 1) * v.dmax;
-    double *sinv = sy + v.dmax;
-    double *sd = sinv + v.dmax;
+    double *sd = sW + (v.dmax | 1) * v.dmax + 2 * v.dmax;
 
     int t_w = 0, t_u = 0, t_xb = 0;
     if (lane < nlev)
@@ -1095,9 +1091,9 @@ __global__ void __launch_bounds__(256) k_backsolve_chain_pf(View v, int lvl_begi
             if (e < DC * DC) sW[(e % DC) + (e / DC) * ld] = pW[k];
         }
         double yv = 0.0;
+        const double inv_cur = pinv;
         if (lane < DC)
         {
-            sinv[lane] = pinv;
             double s = 0.0;
 #pragma unroll
             for (int c = 0; c < DC; c++) s += pU[c] * sd[c];
@@ -1116,11 +1112,9 @@ __global__ void __launch_bounds__(256) k_backsolve_chain_pf(View v, int lvl_begi
             for (int c = 0; c < DC; c++) pU[c] = lane < DC ? v.Ut[un + c + lane * DC] : 0.0;
             if (lane < DC) { py = v.dlam[xn + lane]; pinv = v.Linv[xn + lane]; }
         }
-        if (lane < DC) sy[lane] = yv;
         __syncwarp();
-        warp_trsv_ltn(sW, ld, DC, sinv, sy, lane);
-        __syncwarp();
-        if (lane < DC) { const double r = sy[lane]; v.dlam[xb + lane] = r; sd[lane] = r; }
+        const double r = warp_trsv_ltn32(sW, ld, DC, inv_cur, yv, lane); /* one entry per lane, the operations of warp_trsv_ltn */
+        if (lane < DC) { v.dlam[xb + lane] = r; sd[lane] = r; }
     }
 }
 
