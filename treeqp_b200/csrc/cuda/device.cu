@@ -496,8 +496,9 @@ static int compute_chain_links(tqb_device *D, const tqb_tables *T, const int *gh
 static int chain_udim(const tqb_device *D, int lt, int lb)
 {
     if (!D->lvl_udim || lb <= lt) return 0;
-    const char *e = getenv("TREEQP_B200_NO_CHAIN_DC"); /* A/B runs */
-    if (e && e[0] == '1') return 0;
+    static int off = -1; /* TREEQP_B200_NO_CHAIN_DC=1: A/B runs */
+    if (off < 0) { const char *e = getenv("TREEQP_B200_NO_CHAIN_DC"); off = (e && e[0] == '1') ? 1 : 0; }
+    if (off) return 0;
     const int u = D->lvl_udim[lt];
     for (int l = lt; l <= lb; l++)
         if (D->lvl_udim[l] != u) return 0;

@@ -31,8 +31,14 @@ void tqb_registry_replace(const void *key, void *ctx, void (*dtor)(void *))
     {
         if (g_reg_n == g_reg_cap)
         {
-            g_reg_cap = g_reg_cap ? 2 * g_reg_cap : 16;
-            g_reg = (tqb_reg_entry *) realloc(g_reg, sizeof(tqb_reg_entry) * (size_t) g_reg_cap);
+            const int cap = g_reg_cap ? 2 * g_reg_cap : 16;
+            tqb_reg_entry *r = (tqb_reg_entry *) realloc(g_reg, sizeof(tqb_reg_entry) * (size_t) cap);
+            if (!r)
+            {   /* out of host memory: the context stays unregistered (released by treeqp_*_destroy only) */
+                pthread_mutex_unlock(&g_reg_mu);
+                return;
+            }
+            g_reg = r; g_reg_cap = cap;
         }
         g_reg_n++;
     }
