@@ -99,3 +99,32 @@ def test_reference_random_qp_goldens(n, product_lib):
     assert sol.status == 0 and sol.iter <= 1
     assert sol.kkt < 1e-12
     assert float(np.max(np.abs(sol.x - xopt))) < 1e-12 and float(np.max(np.abs(sol.u - uopt))) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["quadcopter", "crane", "linear_chain"])
+def test_chain_walk_variants_are_bit_identical(name, product_lib, monkeypatch):
+    """config-5 trees on the runtime-dimension path: the prefetching chain walk (k_factor_chain_pf / k_backsolve_chain_pf),
+    the compile-time-dimension level kernels (TREEQP_B200_NO_CHAIN_PF=1), the runtime-dimension level kernels
+    (+ NO_CHAIN_DC=1), one launch per depth (+ NO_CHAIN=1) and the two-slot first line-search pass
+    (TREEQP_B200_DENSE_FIRST_FULL=0) give the same bits, iteration and trial counts (all switches are read at create)"""
+    if name == "quadcopter":
+        prob = P.densify_scaled(P.quadcopter(3, 2, 20, i_mpc=14, x0=CS.QUAD_X0), 4)
+    elif name == "crane":
+        prob = P.densify_scaled(P.crane(3, 2, 20, x0=CS.CRANE_X0), 5)
+    else:
+        prob = P.linear_chain(8, 7, 3, 2, 12, seed=2)
+        prob.umin[:] = -0.3; prob.umax[:] = 0.3; prob.xmin[:] = -1e12; prob.xmax[:] = 1e12
+        prob = P.densify(prob, 6, 0.1, 0.0)
+    opts = dict(qp_solver=1, maxIter=200)
+    sol = capi.solve_tdunes(product_lib, prob, **opts)
+    assert sol.status == 0 and sol.kkt < 1e-8
+    variants = [dict(TREEQP_B200_NO_CHAIN_PF="1"), dict(TREEQP_B200_NO_CHAIN_PF="1", TREEQP_B200_NO_CHAIN_DC="1"),
+                dict(TREEQP_B200_NO_CHAIN="1"), dict(TREEQP_B200_DENSE_FIRST_FULL="0")]
+    for env in variants:
+        for k, val in env.items(): monkeypatch.setenv(k, val)
+        ref = capi.solve_tdunes(product_lib, prob, **opts)
+        for k in env: monkeypatch.delenv(k)
+        assert (ref.status, ref.iter) == (sol.status, sol.iter), env
+        assert ref.stats["ls_iters"] == sol.stats["ls_iters"], env
+        for k in ("x", "u", "lam", "mu_x", "mu_u"):
+            assert np.array_equal(getattr(sol, k), getattr(ref, k)), "%s differs under %s" % (k, env)

@@ -91,6 +91,7 @@ struct tqb_device
     int *lvl_md, *lvl_kp; /* [Nh] children per parent / kids are parents, per depth */
     int *chain_link;      /* [Nh] depth l continues the chains of depth l-1 (one kid per parent, same order) */
     int *lvl_udim;        /* [Nh] d when every block of the depth has dimension d and a parent state of d entries, else 0 */
+    int sw_chain_dc, sw_chain_pf, sw_dense_first; /* switches read at create: TREEQP_B200_NO_CHAIN_DC / NO_CHAIN_PF (0 = off), DENSE_FIRST_FULL (-1 = by size) */
     int has_ghost;        /* sharded local forest: reduction chunks cover the owned nodes only */
     int pair_begin;       /* level descriptors from here on are non-root parents with one kid (k_stage_fused pairs them) */
     double *d_schur;
@@ -496,9 +497,7 @@ static int compute_chain_links(tqb_device *D, const tqb_tables *T, const int *gh
 static int chain_udim(const tqb_device *D, int lt, int lb)
 {
     if (!D->lvl_udim || lb <= lt) return 0;
-    static int off = -1; /* TREEQP_B200_NO_CHAIN_DC=1: A/B runs */
-    if (off < 0) { const char *e = getenv("TREEQP_B200_NO_CHAIN_DC"); off = (e && e[0] == '1') ? 1 : 0; }
-    if (off) return 0;
+    if (!D->sw_chain_dc) return 0; /* TREEQP_B200_NO_CHAIN_DC=1 */
     const int u = D->lvl_udim[lt];
     for (int l = lt; l <= lb; l++)
         if (D->lvl_udim[l] != u) return 0;
@@ -509,19 +508,15 @@ static int chain_udim(const tqb_device *D, int lt, int lb)
  * four warps per resident-CTA slot of the device (TREEQP_B200_DENSE_FIRST_FULL = 0 / 1 forces it, A/B runs) */
 static bool dense_first_pass_full(const tqb_device *D)
 {
-    static int forced = -2;
-    if (forced == -2) { const char *e = getenv("TREEQP_B200_DENSE_FIRST_FULL"); forced = e ? (e[0] == '1' ? 1 : 0) : -1; }
-    if (forced >= 0) return forced == 1;
+    if (D->sw_dense_first >= 0) return D->sw_dense_first == 1;
     return (long long) D->dims.Nn * TQB_LS_NT <= 4LL * D->n_sm_all * D->wpb_dense;
 }
 
 /* chain segments of 2..32 depths take the kernels that move the next block's inputs while a block is processed
  * (k_factor_chain_pf, k_backsolve_chain_pf); TREEQP_B200_NO_CHAIN_PF=1 keeps the level kernels (A/B runs) */
-static bool chain_pf_on(int nlev)
+static bool chain_pf_on(const tqb_device *D, int nlev)
 {
-    static int on = -1;
-    if (on < 0) { const char *e = getenv("TREEQP_B200_NO_CHAIN_PF"); on = (e && e[0] == '1') ? 0 : 1; }
-    return on == 1 && nlev >= 2 && nlev <= 32;
+    return D->sw_chain_pf && nlev >= 2 && nlev <= 32;
 }
 
 /* dimensions with a compile-time instance of the level kernels */
@@ -928,6 +923,12 @@ extern "C" tqb_device *tqb_device_create(const tqb_dims *dims, const int *h_int,
     }
     tqb_device *D = (tqb_device *) calloc(1, sizeof(tqb_device));
     D->dims = *dims;
+    {   /* diagnostics switches of the runtime-dimension path */
+        const char *e1 = getenv("TREEQP_B200_NO_CHAIN_DC"), *e2 = getenv("TREEQP_B200_NO_CHAIN_PF"), *e3 = getenv("TREEQP_B200_DENSE_FIRST_FULL");
+        D->sw_chain_dc = (e1 && e1[0] == '1') ? 0 : 1;
+        D->sw_chain_pf = (e2 && e2[0] == '1') ? 0 : 1;
+        D->sw_dense_first = e3 ? (e3[0] == '1' ? 1 : 0) : -1;
+    }
     if (device_build(D, h_int, lvl_ptr, ghost)) { tqb_device_destroy(D); return NULL; }
     return D;
 }
@@ -1561,7 +1562,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 {
                     const int dc = chain_udim(D, lt, l);
                     bool done = false;
-#define X(a) if (dc == a) { if (chain_pf_on(l - lt + 1)) LAUNCH(K_FACTOR, k_factor_chain_pf<a>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1); \
+#define X(a) if (dc == a) { if (chain_pf_on(D, l - lt + 1)) LAUNCH(K_FACTOR, k_factor_chain_pf<a>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1); \
                              else LAUNCH(K_FACTOR, k_factor_level<a>, cdiv(cnt, D->wpb_fact), 32 * D->wpb_fact, D->sm_fact, v, D->lvl_ptr[lt], cnt, D->pw_fact, l - lt + 1); done = true; }
                     TQB_CHAIN_DC_LIST(X)
 #undef X
@@ -1578,7 +1579,7 @@ extern "C" int tqb_device_solve(tqb_device *D, const tqb_opts *o, int *h_status,
                 {
                     const int dc = chain_udim(D, l, lb);
                     bool done = false;
-#define X(a) if (dc == a) { if (chain_pf_on(lb - l + 1)) LAUNCH(K_BACK, k_backsolve_chain_pf<a>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1); \
+#define X(a) if (dc == a) { if (chain_pf_on(D, lb - l + 1)) LAUNCH(K_BACK, k_backsolve_chain_pf<a>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1); \
                              else LAUNCH(K_BACK, k_backsolve_level<a>, cdiv(cnt, D->wpb_back), 32 * D->wpb_back, D->sm_back, v, D->lvl_ptr[l], cnt, D->pw_back, lb - l + 1); done = true; }
                     TQB_CHAIN_DC_LIST(X)
 #undef X
